@@ -1,0 +1,99 @@
+"""ctypes binding of libavc_b200.so (include/avc_b200.h).  Fails loudly: no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libavc_b200.so"
+
+AVC_MAX_BLOCKS = 8
+
+
+class EncoderDesc(C.Structure):
+    _fields_ = [("c_in", C.c_int32), ("c_h", C.c_int32), ("c_out", C.c_int32), ("kernel_size", C.c_int32),
+                ("bank_size", C.c_int32), ("c_bank", C.c_int32), ("n_conv_blocks", C.c_int32),
+                ("n_dense_blocks", C.c_int32), ("subsample", C.c_int32 * AVC_MAX_BLOCKS), ("neg_slope", C.c_float)]
+
+
+class DecoderDesc(C.Structure):
+    _fields_ = [("c_in", C.c_int32), ("c_cond", C.c_int32), ("c_h", C.c_int32), ("c_out", C.c_int32),
+                ("kernel_size", C.c_int32), ("n_conv_blocks", C.c_int32), ("upsample", C.c_int32 * AVC_MAX_BLOCKS),
+                ("neg_slope", C.c_float)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("speaker", EncoderDesc), ("content", EncoderDesc), ("decoder", DecoderDesc)]
+
+
+class WeightView(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class AttackArgs(C.Structure):
+    _fields_ = [
+        ("vc_tgt", C.c_void_p), ("tgt_stride", C.c_int64 * 3), ("B", C.c_int32), ("T_tgt", C.c_int32),
+        ("adv_tgt", C.c_void_p), ("adv_stride", C.c_int64 * 3), ("T_adv", C.c_int32),
+        ("vc_src", C.c_void_p), ("src_stride", C.c_int64 * 3), ("T_src", C.c_int32),
+        ("w0", C.c_void_p), ("w0_stride", C.c_int64 * 3),
+        ("adv_out", C.c_void_p), ("out_stride", C.c_int64 * 3),
+        ("loss_out", C.c_void_p), ("grad_out", C.c_void_p),
+        ("eps", C.c_float), ("n_iters", C.c_int32), ("inv_norm", C.c_double), ("use_graph", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "avc_create", "avc_destroy", "avc_last_error", "avc_load_weights", "avc_emb_attack", "avc_e2e_attack",
+    "avc_fb_attack", "avc_speaker_encoder", "avc_inference", "avc_decoder_frames", "avc_conv1d_fwd",
+    "avc_conv1d_dgrad", "avc_instnorm_adain_act_fwd", "avc_instnorm_adain_act_bwd", "avc_adam_tanh_step",
+    "avc_kernel_launches", "avc_launches_per_iter", "avc_version",
+    "avc_attack_begin", "avc_attack_step", "avc_attack_end", "avc_session_launches", "avc_session_profile",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library.  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m attack_vc_b200.build` "
+            "(attack_vc_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    P = C.POINTER
+    lib.avc_create.argtypes = [P(vp), P(ModelDesc), C.c_int]
+    lib.avc_create.restype = C.c_int
+    lib.avc_destroy.argtypes = [vp]
+    lib.avc_destroy.restype = None
+    lib.avc_last_error.argtypes = [vp]
+    lib.avc_last_error.restype = C.c_char_p
+    lib.avc_load_weights.argtypes = [vp, P(WeightView), i32]
+    for nm in ("avc_emb_attack", "avc_e2e_attack", "avc_fb_attack"):
+        getattr(lib, nm).argtypes = [vp, P(AttackArgs), vp]
+    lib.avc_attack_begin.argtypes = [vp, i32, P(AttackArgs), vp, P(vp)]
+    lib.avc_attack_step.argtypes = [vp, i32, vp]
+    lib.avc_attack_end.argtypes = [vp, vp]
+    lib.avc_session_launches.argtypes = [vp]
+    lib.avc_session_launches.restype = i32
+    lib.avc_session_profile.argtypes = [vp, i32, P(i32), P(f32), P(C.c_double), P(C.c_double), vp]
+    lib.avc_speaker_encoder.argtypes = [vp, vp, P(i64), i32, i32, vp, vp]
+    lib.avc_inference.argtypes = [vp, vp, P(i64), i32, vp, P(i64), i32, i32, vp, vp]
+    lib.avc_decoder_frames.argtypes = [vp, i32]
+    lib.avc_decoder_frames.restype = i32
+    lib.avc_conv1d_fwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.avc_conv1d_dgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.avc_instnorm_adain_act_fwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp]
+    lib.avc_instnorm_adain_act_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
+    lib.avc_adam_tanh_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, f32, i32, vp]
+    lib.avc_kernel_launches.argtypes = [vp]
+    lib.avc_kernel_launches.restype = i64
+    lib.avc_launches_per_iter.argtypes = [vp]
+    lib.avc_launches_per_iter.restype = i32
+    lib.avc_version.argtypes = []
+    lib.avc_version.restype = C.c_char_p
+    _lib = lib
+    return lib

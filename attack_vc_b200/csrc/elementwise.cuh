@@ -1,0 +1,489 @@
+// elementwise.cuh -- HBM-bound kernels of the perturbation loop: layout conversion, InstanceNorm +
+// AdaIN + activation (+skip) forward/backward, MSE loss + gradient, the fused perturb/tanh/Adam
+// update, the speaker-encoder dense tail and the AdaIN affine layers.  All fp32, float4 accesses,
+// deterministic (fixed-order) reductions -- no float atomics anywhere.
+#pragma once
+#include "common.cuh"
+
+namespace avc {
+
+// ---------------------------------------------------------------------------------------------
+// [B, C, T] strided (reference layout, attack.py:49-50)  <->  [B, T, ld] time-major
+// ---------------------------------------------------------------------------------------------
+__global__ void layout_in_kernel(const float* __restrict__ src, long long sb, long long sc, long long st,
+                                 float* __restrict__ dst, long long d_bs, int d_rs, int B, int C, int T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)B * T * C;
+  if (i >= n) return;
+  int c = (int)(i % C);
+  long long bt = i / C;
+  int t = (int)(bt % T), b = (int)(bt / T);
+  dst[(long long)b * d_bs + (long long)t * d_rs + c] = src[b * sb + c * sc + t * st];
+}
+
+__global__ void layout_out_kernel(const float* __restrict__ src, long long s_bs, int s_rs,
+                                  float* __restrict__ dst, long long sb, long long sc, long long st,
+                                  int B, int C, int T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)B * T * C;
+  if (i >= n) return;
+  int c = (int)(i % C);
+  long long bt = i / C;
+  int t = (int)(bt % T), b = (int)(bt / T);
+  dst[b * sb + c * sc + t * st] = src[(long long)b * s_bs + (long long)t * s_rs + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm1d(affine=False) + AdaIN + act (+ skip)            (models.py:66-79, 176, 396, 414-431)
+//   out[b,t,c] = act( ((y - mu_bc) * rstd_bc) * std_bc + mean_bc ) + skip
+// grid (B, C/16); 256 threads = 4 float4 channel lanes x 64 time lanes.  Statistics are two-pass
+// (mean, then centred sum of squares; biased variance, eps 1e-5) -- the re-reads hit L1/L2, HBM sees
+// each tensor once: 8 B/element forward (+4 with a skip), 12 B/element backward.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNormCh = 16;
+constexpr int kNormTL = 64;
+
+struct NormArgs {
+  const float* y; int T; int C;        // [B,T,C] contiguous conv output (already pixel-shuffled)
+  const float* cond; int cond_bs;      // [B, ...] row with mean at [0,C), std at [C,2C); nullptr: mean 0, std 1
+  const float* stats_in;               // optional precomputed [B,C,2]
+  float* stats_out;                    // optional [B,C,2] (mean, rstd)
+  float* out;                          // [B,T,C]
+  ResArgs res;
+  float slope;
+};
+
+__device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[4], int lane_c, int lane_t) {
+  // reduce over the 64 time lanes for each of the 4 float4 channel lanes; result broadcast
+  red[lane_t][lane_c] = v;
+  __syncthreads();
+  for (int s = kNormTL / 2; s > 0; s >>= 1) {
+    if (lane_t < s) red[lane_t][lane_c] = f4add(red[lane_t][lane_c], red[lane_t + s][lane_c]);
+    __syncthreads();
+  }
+  float4 r = red[0][lane_c];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
+  __shared__ float4 red[kNormTL][4];
+  const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
+  const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
+  const float* yb = p.y + (long long)b * p.T * p.C + c;
+  float4 mu, rstd;
+  if (p.stats_in) {
+    const float* s = p.stats_in + ((long long)b * p.C + c) * 2;
+    float4 s0 = ld4(s), s1 = ld4(s + 4);
+    mu = make_float4(s0.x, s0.z, s1.x, s1.z);
+    rstd = make_float4(s0.y, s0.w, s1.y, s1.w);
+  } else {
+    float4 sum = f4zero();
+    for (int t = lane_t; t < p.T; t += kNormTL) sum = f4add(sum, ld4(yb + (long long)t * p.C));
+    sum = block_reduce_t(sum, red, lane_c, lane_t);
+    const float invT = 1.f / (float)p.T;
+    mu = f4scale(sum, invT);
+    float4 sq = f4zero();
+    for (int t = lane_t; t < p.T; t += kNormTL) {
+      float4 v = ld4(yb + (long long)t * p.C);
+      float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
+      sq.x = fmaf(dx, dx, sq.x); sq.y = fmaf(dy, dy, sq.y); sq.z = fmaf(dz, dz, sq.z); sq.w = fmaf(dw, dw, sq.w);
+    }
+    sq = block_reduce_t(sq, red, lane_c, lane_t);
+    rstd = make_float4(rsqrtf(sq.x * invT + 1e-5f), rsqrtf(sq.y * invT + 1e-5f),
+                       rsqrtf(sq.z * invT + 1e-5f), rsqrtf(sq.w * invT + 1e-5f));
+  }
+  if (p.stats_out && lane_t == 0) {
+    float* s = p.stats_out + ((long long)b * p.C + c) * 2;
+    st4(s, make_float4(mu.x, rstd.x, mu.y, rstd.y));
+    st4(s + 4, make_float4(mu.z, rstd.z, mu.w, rstd.w));
+  }
+  if (!p.out) return;
+  float4 cm = f4zero(), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.cond) {
+    cm = ld4(p.cond + (long long)b * p.cond_bs + c);
+    cs = ld4(p.cond + (long long)b * p.cond_bs + p.C + c);
+  }
+  float* ob = p.out + (long long)b * p.T * p.C + c;
+  for (int t = lane_t; t < p.T; t += kNormTL) {
+    float4 v = ld4(yb + (long long)t * p.C);
+    float4 a;
+    a.x = fmaf((v.x - mu.x) * rstd.x, cs.x, cm.x);
+    a.y = fmaf((v.y - mu.y) * rstd.y, cs.y, cm.y);
+    a.z = fmaf((v.z - mu.z) * rstd.z, cs.z, cm.z);
+    a.w = fmaf((v.w - mu.w) * rstd.w, cs.w, cm.w);
+    a = act4(a, p.slope);
+    if (p.res.mode != RES_NONE) a = f4add(a, res_load4(p.res, b, t, p.T, c));
+    st4(ob + (long long)t * p.C, a);
+  }
+}
+
+struct NormBwdArgs {
+  const float* g;       // [B,T,C] upstream gradient w.r.t. the activation output
+  const float* y;       // [B,T,C] conv output saved by forward
+  const float* stats;   // [B,C,2]
+  const float* cond; int cond_bs;
+  float* gy;            // [B,T,C] or nullptr (first AdaIN of the decoder: only gcond is needed)
+  float* gcond; int gcond_bs;   // row b: d mean at [0,C), d std at [C,2C); nullptr for plain InstanceNorm
+  int T; int C;
+  float slope;
+};
+
+__global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) {
+  __shared__ float4 red[kNormTL][4];
+  const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
+  const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
+  const float* yb = p.y + (long long)b * p.T * p.C + c;
+  const float* gb = p.g + (long long)b * p.T * p.C + c;
+  const float* s = p.stats + ((long long)b * p.C + c) * 2;
+  const float4 s0 = ld4(s), s1 = ld4(s + 4);
+  const float4 mu = make_float4(s0.x, s0.z, s1.x, s1.z), rstd = make_float4(s0.y, s0.w, s1.y, s1.w);
+  float4 cm = f4zero(), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.cond) {
+    cm = ld4(p.cond + (long long)b * p.cond_bs + c);
+    cs = ld4(p.cond + (long long)b * p.cond_bs + p.C + c);
+  }
+  // pass 1: S1 = sum_t ga, S2 = sum_t ga * xhat,  ga = g * act'(a)
+  float4 S1 = f4zero(), S2 = f4zero();
+  for (int t = lane_t; t < p.T; t += kNormTL) {
+    const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
+    const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
+    const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
+    const float4 ga = dact4mul(g, a, p.slope);
+    S1 = f4add(S1, ga);
+    S2.x = fmaf(ga.x, xh.x, S2.x); S2.y = fmaf(ga.y, xh.y, S2.y); S2.z = fmaf(ga.z, xh.z, S2.z); S2.w = fmaf(ga.w, xh.w, S2.w);
+  }
+  S1 = block_reduce_t(S1, red, lane_c, lane_t);
+  S2 = block_reduce_t(S2, red, lane_c, lane_t);
+  if (p.gcond && lane_t == 0) {
+    st4(p.gcond + (long long)b * p.gcond_bs + c, S1);
+    st4(p.gcond + (long long)b * p.gcond_bs + p.C + c, S2);
+  }
+  if (!p.gy) return;
+  // pass 2: gy = rstd * std * (ga - S1/T - xhat * S2/T)
+  const float invT = 1.f / (float)p.T;
+  const float4 m1 = f4scale(S1, invT), m2 = f4scale(S2, invT);
+  const float4 k = make_float4(rstd.x * cs.x, rstd.y * cs.y, rstd.z * cs.z, rstd.w * cs.w);
+  float* ob = p.gy + (long long)b * p.T * p.C + c;
+  for (int t = lane_t; t < p.T; t += kNormTL) {
+    const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
+    const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
+    const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
+    const float4 ga = dact4mul(g, a, p.slope);
+    float4 o;
+    o.x = k.x * (ga.x - m1.x - xh.x * m2.x);
+    o.y = k.y * (ga.y - m1.y - xh.y * m2.y);
+    o.z = k.z * (ga.z - m1.z - xh.z * m2.z);
+    o.w = k.w * (ga.w - m1.w - xh.w * m2.w);
+    st4(ob + (long long)t * p.C, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// e2e loss (attack_utils.py:43):  L = mean((o-tgt)^2) - 0.1*mean((o-org)^2) over ALL elements,
+// dL/do = 2*inv_norm*((o-tgt) - 0.1*(o-org)).  One partial per CTA -> loss_parts[step][cta].
+// 16 B/element (read o,tgt,org; write g).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__ o, const float* __restrict__ tgt,
+                                                       const float* __restrict__ org, float* __restrict__ g,
+                                                       long long n4, float inv_norm, float* __restrict__ loss_parts,
+                                                       const int* __restrict__ step, int parts_per_step) {
+  __shared__ float wsum[8];
+  float acc = 0.f;
+  const float k = 2.f * inv_norm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = ld4(o + i * 4), t = ld4(tgt + i * 4), r = ld4(org + i * 4);
+    const float4 d = make_float4(a.x - t.x, a.y - t.y, a.z - t.z, a.w - t.w);
+    const float4 e = make_float4(a.x - r.x, a.y - r.y, a.z - r.z, a.w - r.w);
+    acc += (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) - 0.1f * (e.x * e.x + e.y * e.y + e.z * e.z + e.w * e.w);
+    st4(g + i * 4, make_float4(k * (d.x - 0.1f * e.x), k * (d.y - 0.1f * e.y), k * (d.z - 0.1f * e.z), k * (d.w - 0.1f * e.w)));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += wsum[i];
+    if (loss_parts) loss_parts[(long long)(*step) * parts_per_step + blockIdx.x] = s * inv_norm;
+  }
+}
+
+__global__ void loss_sum_kernel(const float* __restrict__ parts, int parts_per_step, int n_iters, float* __restrict__ loss) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_iters) return;
+  double s = 0.0;
+  for (int p = 0; p < parts_per_step; ++p) s += (double)parts[(long long)i * parts_per_step + p];
+  loss[i] = (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused perturbation update (attack_utils.py:40,44-46 + torch/optim/adam.py _single_tensor_adam):
+//   y = tanh(w); g_w = (g_adv*eps) * (1 - y*y)
+//   m = m + (g_w - m)*(1-b1);  v = v*b2 + (1-b2)*g_w*g_w
+//   w = w + (-step_size * m) / (sqrt(v)/bc2_sqrt + 1e-8);   adv = x + eps*tanh(w)
+// step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) come from a host-computed (fp64) table indexed
+// by the device step counter, so one captured graph serves every iteration.
+// 36 B/element: read g,w,m,v,x ; write w,m,v,adv.
+// ---------------------------------------------------------------------------------------------
+struct UpdateArgs {
+  const float* g_adv; long long g_bs; int g_rs;   // [B,T,C] gradient w.r.t. adv
+  const float* x;                                  // [B,T,C] contiguous
+  float* w; float* m; float* v;                    // contiguous
+  float* adv; long long adv_bs; int adv_rs;        // may live inside the bank "cat" buffer
+  float* gw_out;                                   // optional contiguous copy of g_w
+  int B, T, C;
+  float eps;
+  const float2* table;                             // [n_iters] (step_size, bc2_sqrt)
+  int* step;                                       // device step counter (0-based); incremented by the last CTA
+  unsigned int* done;                              // CTA arrival counter
+};
+
+__global__ void __launch_bounds__(256) adam_tanh_update_kernel(const UpdateArgs p) {
+  const int c4n = p.C >> 2;
+  const long long n4 = (long long)p.B * p.T * c4n;
+  const int step = *p.step;
+  const float2 tab = p.table[step];
+  const float step_size = tab.x, bc2s = tab.y;
+  const float b1w = (float)(1.0 - 0.9), b2 = 0.999f, b2w = (float)(1.0 - 0.999);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const long long bt = i / c4n;
+    const int t = (int)(bt % p.T), b = (int)(bt / p.T);
+    const long long lin = i * 4;
+    const float4 g = ld4(p.g_adv + (long long)b * p.g_bs + (long long)t * p.g_rs + c);
+    float4 w = ld4(p.w + lin), m = ld4(p.m + lin), v = ld4(p.v + lin);
+    const float4 x = ld4(p.x + lin);
+    float gw[4], wa[4] = {w.x, w.y, w.z, w.w}, ma[4] = {m.x, m.y, m.z, m.w}, va[4] = {v.x, v.y, v.z, v.w};
+    const float ga[4] = {g.x, g.y, g.z, g.w}, xa[4] = {x.x, x.y, x.z, x.w};
+    float adv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = tanhf(wa[j]);
+      gw[j] = (ga[j] * p.eps) * (1.f - y * y);
+      ma[j] = ma[j] + (gw[j] - ma[j]) * b1w;
+      va[j] = va[j] * b2 + (b2w * gw[j]) * gw[j];
+      const float denom = sqrtf(va[j]) / bc2s + 1e-8f;
+      wa[j] = wa[j] + (-step_size * ma[j]) / denom;
+      adv[j] = xa[j] + p.eps * tanhf(wa[j]);
+    }
+    st4(p.w + lin, make_float4(wa[0], wa[1], wa[2], wa[3]));
+    st4(p.m + lin, make_float4(ma[0], ma[1], ma[2], ma[3]));
+    st4(p.v + lin, make_float4(va[0], va[1], va[2], va[3]));
+    st4(p.adv + (long long)b * p.adv_bs + (long long)t * p.adv_rs + c, make_float4(adv[0], adv[1], adv[2], adv[3]));
+    if (p.gw_out) st4(p.gw_out + lin, make_float4(gw[0], gw[1], gw[2], gw[3]));
+  }
+  // last CTA to finish advances the step counter (every CTA has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0 && p.done) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *p.done = 0u;
+      *p.step = step + 1;
+      __threadfence();
+    }
+  }
+}
+
+// adv = x + eps*tanh(w) only (initial perturbation and final result, attack_utils.py:40,48)
+__global__ void perturb_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ adv,
+                               long long adv_bs, int adv_rs, int B, int T, int C, float eps) {
+  const int c4n = C >> 2;
+  const long long n4 = (long long)B * T * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const long long bt = i / c4n;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float4 xv = ld4(x + i * 4), wv = ld4(w + i * 4);
+    st4(adv + (long long)b * adv_bs + (long long)t * adv_rs + c,
+        make_float4(xv.x + eps * tanhf(wv.x), xv.y + eps * tanhf(wv.y), xv.z + eps * tanhf(wv.z), xv.w + eps * tanhf(wv.w)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Speaker-encoder tail: AdaptiveAvgPool1d(1) -> 6 residual dense blocks -> output Linear
+// (models.py:307-325, 340-342), the emb/fb loss (attack_utils.py:81,125) and the whole backward of
+// the tail, one CTA (1024 threads = 8 K-slices x 128 outputs) per utterance.  Requires c_h = c_out = 128.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTailMaxDense = 8;
+enum TailMode : int { TAIL_FWD = 1, TAIL_LOSS = 2, TAIL_BWD = 4 };
+
+struct TailArgs {
+  const float* h; long long h_bs; int h_rs; int T_h;   // last conv block output [B,T_h,128]
+  int n_dense;
+  const float* Wt1[kTailMaxDense]; const float* Wt2[kTailMaxDense];   // transposed [c][n] (forward)
+  const float* W1[kTailMaxDense];  const float* W2[kTailMaxDense];    // PyTorch [n][c]  (backward)
+  const float* b1[kTailMaxDense];  const float* b2[kTailMaxDense];
+  const float* Wto; const float* Wo; const float* bo;
+  float slope;
+  int mode;
+  float* acts;            // [B][2*n_dense+1][128] saved activations: pooled v0, then (y1,y2) per block... see kernel
+  float* emb;             // [B,128] output embedding (TAIL_FWD)
+  const float* tgt; const float* org;   // [B,128] (TAIL_LOSS)
+  float inv_norm;
+  float* loss_parts; const int* step; int parts_per_step;
+  const float* gemb; int gemb_parts;    // TAIL_BWD without TAIL_LOSS: d emb = sum_p gemb[b][p][128]
+  float* gpool;           // [B,128]: d h[b,t,:] for every t (already divided by T_h)
+};
+
+__device__ __forceinline__ void dense128(const float* __restrict__ M, const float* __restrict__ vin,
+                                         float (*part)[128], int tid) {
+  // part[g][n] = sum_{c in slice g} M[c*128+n] * vin[c]
+  const int g = tid >> 7, n = tid & 127;
+  float a = 0.f;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int c = g * 16 + q;
+    a = fmaf(M[c * 128 + n], vin[c], a);
+  }
+  part[g][n] = a;
+}
+__device__ __forceinline__ float part_sum(float (*part)[128], int n) {
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) s += part[g][n];
+  return s;
+}
+
+__global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
+  __shared__ float part[8][128];
+  __shared__ float va[2 * kTailMaxDense + 2][128];   // va[0]=pooled v0; block l: va[1+2l]=y1, va[2+2l]=y2; running v in vcur
+  __shared__ float vcur[128];
+  __shared__ float gv[128], gt[128];
+  __shared__ float lred[4];
+  const int tid = threadIdx.x, b = blockIdx.x, n = tid & 127;
+  const int nsave = 2 * p.n_dense + 1;
+  float* acts_b = p.acts + (long long)b * (nsave + p.n_dense) * 128;   // + per-block inputs v_l
+
+  if (p.mode & TAIL_FWD) {
+    // global average pool over time
+    {
+      const int g = tid >> 7;
+      float a = 0.f;
+      const float* hb = p.h + (long long)b * p.h_bs + n;
+      for (int t = g; t < p.T_h; t += 8) a += hb[(long long)t * p.h_rs];
+      part[g][n] = a;
+      __syncthreads();
+      if (tid < 128) { vcur[n] = part_sum(part, n) / (float)p.T_h; va[0][n] = vcur[n]; }
+      __syncthreads();
+    }
+    for (int l = 0; l < p.n_dense; ++l) {
+      if (tid < 128) acts_b[(nsave + l) * 128 + n] = vcur[n];     // block input v_l (for nothing but completeness)
+      dense128(p.Wt1[l], vcur, part, tid);
+      __syncthreads();
+      if (tid < 128) va[1 + 2 * l][n] = actf(part_sum(part, n) + p.b1[l][n], p.slope);
+      __syncthreads();
+      dense128(p.Wt2[l], va[1 + 2 * l], part, tid);
+      __syncthreads();
+      if (tid < 128) { float y2 = actf(part_sum(part, n) + p.b2[l][n], p.slope); va[2 + 2 * l][n] = y2; vcur[n] = y2 + vcur[n]; }
+      __syncthreads();
+    }
+    dense128(p.Wto, vcur, part, tid);
+    __syncthreads();
+    if (tid < 128) {
+      gt[n] = part_sum(part, n) + p.bo[n];     // embedding
+      if (p.emb) p.emb[(long long)b * 128 + n] = gt[n];
+    }
+    if (tid < 128) for (int i = 0; i < nsave; ++i) acts_b[i * 128 + n] = va[i][n];
+    __syncthreads();
+  } else {
+    if (tid < 128) for (int i = 0; i < nsave; ++i) va[i][n] = acts_b[i * 128 + n];
+    __syncthreads();
+  }
+  if (!(p.mode & TAIL_BWD)) return;
+
+  // ---- d emb ------------------------------------------------------------------------------
+  if (p.mode & TAIL_LOSS) {
+    float lp = 0.f;
+    if (tid < 128) {
+      const float e = gt[n], d = e - p.tgt[(long long)b * 128 + n], o = e - p.org[(long long)b * 128 + n];
+      lp = d * d - 0.1f * (o * o);
+      gv[n] = 2.f * p.inv_norm * (d - 0.1f * o);
+      lp = warp_sum(lp);
+      if ((tid & 31) == 0) lred[tid >> 5] = lp;
+    }
+    __syncthreads();
+    if (tid == 0 && p.loss_parts)
+      p.loss_parts[(long long)(*p.step) * p.parts_per_step + b] = (lred[0] + lred[1] + lred[2] + lred[3]) * p.inv_norm;
+  } else {
+    if (tid < 128) {
+      float s = 0.f;
+      for (int q = 0; q < p.gemb_parts; ++q) s += p.gemb[((long long)b * p.gemb_parts + q) * 128 + n];
+      gv[n] = s;
+    }
+  }
+  __syncthreads();
+  // ---- output layer: g_v = Wo^T g_emb  (Wo is [n_out][c]: contraction over n_out) ----------------
+  dense128(p.Wo, gv, part, tid);
+  __syncthreads();
+  if (tid < 128) gv[n] = part_sum(part, n);
+  __syncthreads();
+  for (int l = p.n_dense - 1; l >= 0; --l) {
+    // v_{l+1} = y2 + v_l ; y2 = act(W2 y1 + b2) ; y1 = act(W1 v_l + b1)
+    if (tid < 128) gt[n] = gv[n] * dactf(va[2 + 2 * l][n], p.slope);     // d pre-act 2
+    __syncthreads();
+    dense128(p.W2[l], gt, part, tid);
+    __syncthreads();
+    if (tid < 128) gt[n] = part_sum(part, n) * dactf(va[1 + 2 * l][n], p.slope);   // d pre-act 1
+    __syncthreads();
+    dense128(p.W1[l], gt, part, tid);
+    __syncthreads();
+    if (tid < 128) gv[n] = gv[n] + part_sum(part, n);
+    __syncthreads();
+  }
+  if (tid < 128) p.gpool[(long long)b * 128 + n] = gv[n] / (float)p.T_h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdaIN affine layers: cond_l = Linear_l(emb), l < 2*n_blocks  (models.py:397-399, 420, 427)
+// forward grid (B, L): 256 outputs per CTA.  backward grid (B, L): partial d emb per layer, summed
+// (fixed order) by the tail kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxAffine = 2 * 8;
+struct AffineArgs {
+  const float* Wt[kMaxAffine];   // [c][2C] transposed
+  const float* W[kMaxAffine];    // [2C][c]
+  const float* bias[kMaxAffine];
+  const float* emb;              // [B,128]
+  float* cond;                   // [B][L][256]
+  const float* gcond;            // [B][L][256]
+  float* gemb_parts;             // [B][L][128]
+  int L;
+};
+
+__global__ void __launch_bounds__(1024) affine_fwd_kernel(const AffineArgs p) {
+  __shared__ float e[128];
+  __shared__ float part[4][256];
+  const int b = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, n = tid & 255, g = tid >> 8;
+  if (tid < 128) e[tid] = p.emb[(long long)b * 128 + tid];
+  __syncthreads();
+  const float* M = p.Wt[l];
+  float a = 0.f;
+#pragma unroll 8
+  for (int q = 0; q < 32; ++q) { const int c = g * 32 + q; a = fmaf(M[c * 256 + n], e[c], a); }
+  part[g][n] = a;
+  __syncthreads();
+  if (tid < 256) p.cond[((long long)b * p.L + l) * 256 + n] = part[0][n] + part[1][n] + part[2][n] + part[3][n] + p.bias[l][n];
+}
+
+__global__ void __launch_bounds__(1024) affine_bwd_kernel(const AffineArgs p) {
+  __shared__ float gc[256];
+  __shared__ float part[8][128];
+  const int b = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, c = tid & 127, g = tid >> 7;
+  if (tid < 256) gc[tid] = p.gcond[((long long)b * p.L + l) * 256 + tid];
+  __syncthreads();
+  const float* M = p.W[l];   // [n][c]
+  float a = 0.f;
+#pragma unroll 8
+  for (int q = 0; q < 32; ++q) { const int nn = g * 32 + q; a = fmaf(M[nn * 128 + c], gc[nn], a); }
+  part[g][c] = a;
+  __syncthreads();
+  if (tid < 128) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += part[q][c];
+    p.gemb_parts[((long long)b * p.L + l) * 128 + c] = s;
+  }
+}
+
+}  // namespace avc

@@ -1,0 +1,1339 @@
+// engine.cu -- host side of libavc_b200.so: handle, weight packing, launch plans for the three
+// attacks (attack_utils.py:7-130) and the C-ABI declared in include/avc_b200.h.
+//
+// A "plan" is the ordered list of kernel launches of one attack iteration for fixed shapes.  It is
+// built once, captured into a CUDA graph and replayed n_iters times; nothing in the loop touches the
+// host (the reference never reads the loss inside the loop either).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/avc_b200.h"
+#include "host_util.h"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "elementwise.cuh"
+
+using namespace avc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- packed weights ----------------------------------------------------------------------------
+struct ConvW {
+  int c_in = 0, c_out = 0, k = 0, stride = 1;
+  float* fwd = nullptr;   // [k][c_in][c_out']      c_out' = pixel-shuffle-permuted output channel
+  float* bwd = nullptr;   // [k reversed][c_out'][c_in]
+  float* bias = nullptr;  // [c_out']
+  TcPack tc_fwd, tc_bwd;  // tcgen05 operand images (conv_tc.cuh); empty when not eligible
+  int pl() const { return k / 2; }
+  int pr() const { return (k % 2) ? k / 2 : k / 2 - 1; }
+};
+
+struct EncoderW {
+  avc_encoder_desc d{};
+  int n_bank = 0, c_cat = 0;
+  ConvW bank[AVC_MAX_BANK];
+  float* bank_bias = nullptr;   // [n_bank*c_bank]
+  ConvW in_conv, c1[AVC_MAX_BLOCKS], c2[AVC_MAX_BLOCKS];
+  ConvW mean_layer;             // content encoder only
+  // dense tail (speaker encoder only)
+  float *Wt1[AVC_MAX_BLOCKS]{}, *Wt2[AVC_MAX_BLOCKS]{}, *W1[AVC_MAX_BLOCKS]{}, *W2[AVC_MAX_BLOCKS]{}, *b1[AVC_MAX_BLOCKS]{}, *b2[AVC_MAX_BLOCKS]{};
+  float *Wto = nullptr, *Wo = nullptr, *bo = nullptr;
+};
+
+struct DecoderW {
+  avc_decoder_desc d{};
+  ConvW in_conv, c1[AVC_MAX_BLOCKS], c2[AVC_MAX_BLOCKS], out_conv;
+  float *aWt[2 * AVC_MAX_BLOCKS]{}, *aW[2 * AVC_MAX_BLOCKS]{}, *ab[2 * AVC_MAX_BLOCKS]{};
+};
+
+enum LaunchKind : int { LK_CONV = 0, LK_NORM = 1, LK_TAIL = 2, LK_AFFINE = 3, LK_LOSS = 4, LK_UPDATE = 5, LK_LAYOUT = 6, LK_COPY = 7 };
+
+struct Launch {
+  std::function<void(cudaStream_t)> fn;
+  int kind = LK_COPY;
+  double flops = 0;   // algorithmic FLOPs of this launch (2 per MAC; dgrad of a strided conv counts real taps only)
+  double bytes = 0;   // algorithmic HBM bytes (each tensor touched once)
+  void operator()(cudaStream_t st) const { fn(st); }
+};
+
+struct Plan {
+  Arena mem;
+  std::vector<Launch> setup;    // once per attack call (targets, loop invariants)
+  std::vector<Launch> iter;     // one attack iteration
+  std::vector<Launch> finish;   // after the loop
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int n_iters = 0;      // iterations the Adam table / loss buffer were sized for
+  int done_iters = 0;
+  bool use_graph = true;
+  bool finished = false;
+  ~Plan() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+}  // namespace
+
+struct avc_handle {
+  int device = 0;
+  int sm_count = 148;
+  avc_model_desc desc{};
+  Arena wmem;
+  bool have_weights = false;
+  EncoderW se, ce;
+  DecoderW dec;
+  std::string err;
+  long long launches = 0;
+  int launches_per_iter = 0;
+  int conv_impl = 0;   // 0 auto, 1 simt, 2 tcgen05 (env AVC_CONV_IMPL overrides)
+};
+
+struct avc_session {
+  avc_handle* h;
+  std::unique_ptr<Plan> plan;
+};
+
+namespace {
+
+// =================================================================================================
+// conv launch
+// =================================================================================================
+template <int RM, int TXN, int TYN>
+void launch_conv_cfg(ConvArgs a, cudaStream_t st) {
+  constexpr int TM = RM * TYN, TN = TXN * 4;
+  a.win_rows = a.bwd ? TM + 16 : (TM - 1) * a.s + kMaxTaps;
+  const size_t smem = ((size_t)(a.win_rows + kMaxTaps) * kSRow + 2 * kKSub * TN) * sizeof(float);
+  if (smem > 200 * 1024) fail(AVC_ERR_INVALID, "conv window needs %zu B of shared memory", smem);
+  const int tiles_t = (a.T_y + TM - 1) / TM;
+  dim3 grid(a.B * tiles_t, (a.N + TN - 1) / TN, a.zsplit ? a.n_groups : 1);
+  conv_simt_kernel<RM, TXN, TYN><<<grid, TXN * TYN, smem, st>>>(a);
+  CK(cudaGetLastError());
+}
+
+void init_kernel_attributes() {
+  CK(cudaFuncSetAttribute(conv_simt_kernel<4, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(conv_simt_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(conv_simt_kernel<1, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  tc_init_attributes();
+}
+
+void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st) {
+  // pick the largest tile that still gives every SM about two CTAs; small-M problems (batch 1)
+  // get the 16x32 tile so the layer spreads over as many SMs as possible
+  const long long z = a.zsplit ? a.n_groups : 1;
+  auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
+  if (ctas(64, 64) >= 2LL * sm_count) launch_conv_cfg<4, 16, 16>(a, st);
+  else if (ctas(32, 32) >= 2LL * sm_count) launch_conv_cfg<2, 8, 16>(a, st);
+  else launch_conv_cfg<1, 8, 16>(a, st);
+}
+
+void launch_conv(avc_handle* h, const ConvArgs& a, const TcPack* tc, cudaStream_t st) {
+  int impl = h->conv_impl;
+  if (impl != 1 && tc && tc->ok && tc_eligible(a, *tc, impl == 2)) {
+    launch_conv_tc(a, *tc, h->sm_count, st);
+    return;
+  }
+  if (impl == 2 && tc == nullptr) { /* no tensor-core image for this op: fp32 path */ }
+  launch_conv_simt(a, h->sm_count, st);
+}
+
+// fill the channel groups of a plain Conv1d (forward) -- K split into <=128-channel groups
+void conv_groups_fwd(ConvArgs& a, const ConvW& w) {
+  const int ng = (w.c_in + 127) / 128;
+  if (ng > kMaxGroups) fail(AVC_ERR_INVALID, "conv c_in=%d too large", w.c_in);
+  a.n_groups = ng;
+  for (int g = 0; g < ng; ++g) {
+    TapGroup& G = a.g[g];
+    G.a_ch_off = g * 128;
+    G.kc = std::min(128, w.c_in - g * 128);
+    G.n_taps = w.k;
+    G.off0 = -w.pl();
+    G.pl = w.pl(); G.pr = w.pr();
+    G.wts = w.c_in;
+    G.W = w.fwd + (size_t)g * 128 * w.c_out;
+  }
+  a.bwd = 0; a.s = w.stride; a.N = w.c_out; a.bias = w.bias;
+}
+
+void conv_groups_bwd(ConvArgs& a, const ConvW& w) {
+  const int ng = (w.c_out + 127) / 128;
+  if (ng > kMaxGroups) fail(AVC_ERR_INVALID, "conv c_out=%d too large", w.c_out);
+  a.n_groups = ng;
+  for (int g = 0; g < ng; ++g) {
+    TapGroup& G = a.g[g];
+    G.a_ch_off = g * 128;
+    G.kc = std::min(128, w.c_out - g * 128);
+    G.n_taps = w.k;
+    G.off0 = w.pl() - (w.k - 1);
+    G.pl = w.pl(); G.pr = w.pr();
+    G.wts = w.c_out;
+    G.W = w.bwd + (size_t)g * 128 * w.c_in;
+  }
+  a.bwd = 1; a.s = w.stride; a.N = w.c_in; a.bias = nullptr;
+}
+
+struct Tens {   // time-major activation view
+  float* p = nullptr; long long bs = 0; int rs = 0; int T = 0;
+};
+Tens tens(float* p, int T, int C) { return Tens{p, (long long)T * C, C, T}; }
+
+ResArgs no_res() { ResArgs r{}; r.mode = RES_NONE; r.rf = 1; return r; }
+ResArgs mk_res(const Tens& t, int mode, int rf) { ResArgs r{}; r.R = t.p; r.bs = t.bs; r.rs = t.rs; r.T_r = t.T; r.mode = mode; r.rf = rf; return r; }
+
+int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// =================================================================================================
+// emitters: append launches to a vector
+// =================================================================================================
+struct Emitter {
+  avc_handle* h;
+  std::vector<Launch>* out;
+  void conv(const ConvArgs& a, const TcPack* tc = nullptr) {
+    avc_handle* hh = h;
+    ConvArgs ac = a;
+    TcPack tcc = tc ? *tc : TcPack{};
+    bool have = tc != nullptr;
+    double macs = 0;
+    const int g_n = ac.n_groups;
+    for (int g = 0; g < g_n; ++g) macs += (double)ac.g[g].kc * ac.g[g].n_taps;
+    macs *= (double)ac.B * ac.T_y * ac.N / (ac.bwd ? ac.s : 1);
+    const double bytes = 4.0 * ac.B * ((double)ac.T_a * ac.g[0].kc * (ac.zsplit ? 1 : g_n) + (double)ac.T_y * ac.N * (ac.zsplit ? g_n : 1));
+    Launch l;
+    l.fn = [hh, ac, tcc, have](cudaStream_t st) { launch_conv(hh, ac, have ? &tcc : nullptr, st); };
+    l.kind = LK_CONV; l.flops = 2.0 * macs; l.bytes = bytes;
+    out->push_back(std::move(l));
+  }
+  void push(int kind, double flops, double bytes, std::function<void(cudaStream_t)> fn) {
+    Launch l;
+    l.fn = std::move(fn); l.kind = kind; l.flops = flops; l.bytes = bytes;
+    out->push_back(std::move(l));
+  }
+};
+
+// forward conv through pad_layer (models.py:10-30)
+ConvArgs fwd_conv_args(const ConvW& w, const Tens& in, const Tens& outT, int B, bool act, float slope) {
+  ConvArgs a{};
+  a.A = in.p; a.a_bs = in.bs; a.a_rs = in.rs; a.T_a = in.T;
+  a.slope = slope; a.T_y = outT.T; a.B = B;
+  a.Y = outT.p; a.y_bs = outT.bs; a.y_rs = outT.rs;
+  a.act = act ? 1 : 0;
+  a.res = no_res();
+  conv_groups_fwd(a, w);
+  return a;
+}
+// gradient w.r.t. the conv input: dy (rows of the forward output) -> dx (rows of the forward input)
+ConvArgs bwd_conv_args(const ConvW& w, const Tens& dy, const Tens& dx, int B, float slope) {
+  ConvArgs a{};
+  a.A = dy.p; a.a_bs = dy.bs; a.a_rs = dy.rs; a.T_a = dy.T;
+  a.slope = slope; a.T_y = dx.T; a.B = B;
+  a.Y = dx.p; a.y_bs = dx.bs; a.y_rs = dx.rs;
+  a.res = no_res();
+  conv_groups_bwd(a, w);
+  return a;
+}
+
+void emit_norm_fwd(Emitter& E, const float* y, int B, int T, int C, const float* cond, int cond_bs,
+                   const float* stats_in, float* stats_out, float* outp, ResArgs res, float slope) {
+  NormArgs n{};
+  n.y = y; n.T = T; n.C = C; n.cond = cond; n.cond_bs = cond_bs; n.stats_in = stats_in; n.stats_out = stats_out;
+  n.out = outp; n.res = res; n.slope = slope;
+  if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
+  dim3 grid(B, C / kNormCh);
+  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid](cudaStream_t st) { norm_act_fwd_kernel<<<grid, 256, 0, st>>>(n); CK(cudaGetLastError()); });
+}
+
+void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stats, const float* cond, int cond_bs,
+                   float* gy, float* gcond, int gcond_bs, int B, int T, int C, float slope) {
+  NormBwdArgs n{};
+  n.g = g; n.y = y; n.stats = stats; n.cond = cond; n.cond_bs = cond_bs; n.gy = gy; n.gcond = gcond; n.gcond_bs = gcond_bs;
+  n.T = T; n.C = C; n.slope = slope;
+  dim3 grid(B, C / kNormCh);
+  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid](cudaStream_t st) { norm_act_bwd_kernel<<<grid, 256, 0, st>>>(n); CK(cudaGetLastError()); });
+}
+
+// ---- encoder (speaker / content) ------------------------------------------------------------------
+struct EncActs {
+  int B = 0, T = 0;
+  int Tl[AVC_MAX_BLOCKS + 1]{};
+  float* cat = nullptr;            // [B,T,c_cat]; the encoder INPUT lives at cat + n_bank*c_bank (concat "x last")
+  float* h0 = nullptr;
+  float *h1[AVC_MAX_BLOCKS]{}, *h2[AVC_MAX_BLOCKS]{}, *hout[AVC_MAX_BLOCKS]{};
+  float *tmp = nullptr, *tmp2 = nullptr;   // content encoder: raw conv outputs before InstanceNorm
+  float *tail_acts = nullptr, *emb = nullptr, *gpool = nullptr;
+  // backward scratch
+  float *gA = nullptr, *gB = nullptr, *gH = nullptr, *gcat = nullptr, *gin = nullptr;
+  Tens input(const EncoderW& W) const {
+    return Tens{cat + W.n_bank * W.d.c_bank, (long long)T * W.c_cat, W.c_cat, T};
+  }
+};
+
+EncActs alloc_encoder(Arena& m, const EncoderW& W, int B, int T, bool need_bwd, bool content) {
+  EncActs A;
+  A.B = B; A.T = T;
+  const int ch = W.d.c_h;
+  A.Tl[0] = T;
+  for (int l = 0; l < W.d.n_conv_blocks; ++l) A.Tl[l + 1] = cdiv(A.Tl[l], W.d.subsample[l]);
+  const int Tlast = A.Tl[W.d.n_conv_blocks];
+  // reflect padding needs pad < length at every level (PyTorch raises otherwise)
+  if (T <= W.d.bank_size / 2 || Tlast <= W.d.kernel_size / 2)
+    fail(AVC_ERR_INVALID, "utterance of %d frames is too short for reflect padding", T);
+  A.cat = m.f((size_t)B * T * W.c_cat);
+  A.h0 = m.f((size_t)B * T * ch);
+  for (int l = 0; l < W.d.n_conv_blocks; ++l) {
+    A.h1[l] = m.f((size_t)B * A.Tl[l] * ch);
+    if (!content) A.h2[l] = m.f((size_t)B * A.Tl[l + 1] * ch);
+    A.hout[l] = m.f((size_t)B * A.Tl[l + 1] * ch);
+  }
+  if (content) {
+    A.tmp = m.f((size_t)B * T * ch);
+    A.tmp2 = m.f((size_t)B * T * ch);
+  } else {
+    A.tail_acts = m.f((size_t)B * (3 * W.d.n_dense_blocks + 1) * 128);
+    A.emb = m.f((size_t)B * 128);
+    A.gpool = m.f((size_t)B * 128);
+  }
+  if (need_bwd) {
+    A.gA = m.f((size_t)B * T * ch);
+    A.gB = m.f((size_t)B * T * ch);
+    A.gH = m.f((size_t)B * T * ch);
+    A.gcat = m.f((size_t)B * T * W.c_cat);
+    A.gin = m.f((size_t)B * T * W.d.c_in);
+  }
+  return A;
+}
+
+void emit_bank_and_inconv(Emitter& E, const EncoderW& W, const EncActs& A, bool content) {
+  const float slope = W.d.neg_slope;
+  const Tens x = A.input(W);
+  {   // conv bank: 8 convs + act, written into their channel slots of `cat` (models.py:82-104)
+    ConvArgs a{};
+    a.A = x.p; a.a_bs = x.bs; a.a_rs = x.rs; a.T_a = A.T;
+    a.slope = slope; a.bwd = 0; a.s = 1; a.T_y = A.T; a.B = A.B;
+    a.Y = A.cat; a.y_bs = x.bs; a.y_rs = W.c_cat; a.N = W.d.c_bank; a.bias = W.bank_bias; a.act = 1;
+    a.res = no_res(); a.zsplit = 1; a.n_groups = W.n_bank;
+    for (int z = 0; z < W.n_bank; ++z) {
+      const ConvW& w = W.bank[z];
+      a.g[z] = TapGroup{w.fwd, 0, w.c_in, w.k, -w.pl(), w.pl(), w.pr(), w.c_in};
+    }
+    E.conv(a);
+  }
+  {   // 1x1 in-conv over the concatenation (models.py:192 / :337)
+    Tens cat{A.cat, x.bs, W.c_cat, A.T};
+    Tens outT = tens(content ? A.tmp : A.h0, A.T, W.d.c_h);
+    ConvArgs a = fwd_conv_args(W.in_conv, cat, outT, A.B, !content, slope);
+    E.conv(a, &W.in_conv.tc_fwd);
+    if (content) emit_norm_fwd(E, A.tmp, A.B, A.T, W.d.c_h, nullptr, 0, nullptr, nullptr, A.h0, no_res(), slope);
+  }
+}
+
+void emit_encoder_blocks_fwd(Emitter& E, const EncoderW& W, const EncActs& A, bool content) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h;
+  const float* hin = A.h0;
+  for (int l = 0; l < W.d.n_conv_blocks; ++l) {
+    const int Ti = A.Tl[l], To = A.Tl[l + 1], sub = W.d.subsample[l];
+    Tens in = tens(const_cast<float*>(hin), Ti, ch);
+    ResArgs res = mk_res(in, sub > 1 ? RES_POOL : RES_SAME, sub);
+    if (!content) {
+      ConvArgs a1 = fwd_conv_args(W.c1[l], in, tens(A.h1[l], Ti, ch), A.B, true, slope);
+      E.conv(a1, &W.c1[l].tc_fwd);
+      ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.h1[l], Ti, ch), tens(A.hout[l], To, ch), A.B, true, slope);
+      a2.Y2 = A.h2[l]; a2.y2_bs = (long long)To * ch; a2.y2_rs = ch;
+      a2.res = res;
+      E.conv(a2, &W.c2[l].tc_fwd);
+    } else {
+      ConvArgs a1 = fwd_conv_args(W.c1[l], in, tens(A.tmp, Ti, ch), A.B, false, slope);
+      E.conv(a1, &W.c1[l].tc_fwd);
+      emit_norm_fwd(E, A.tmp, A.B, Ti, ch, nullptr, 0, nullptr, nullptr, A.h1[l], no_res(), slope);
+      ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.h1[l], Ti, ch), tens(A.tmp2, To, ch), A.B, false, slope);
+      E.conv(a2, &W.c2[l].tc_fwd);
+      emit_norm_fwd(E, A.tmp2, A.B, To, ch, nullptr, 0, nullptr, nullptr, A.hout[l], res, slope);
+    }
+    hin = A.hout[l];
+  }
+}
+
+TailArgs tail_args(const EncoderW& W, const EncActs& A) {
+  TailArgs t{};
+  const int nb = W.d.n_conv_blocks;
+  t.h = nb ? A.hout[nb - 1] : A.h0;
+  t.T_h = A.Tl[nb]; t.h_rs = W.d.c_h; t.h_bs = (long long)t.T_h * W.d.c_h;
+  t.n_dense = W.d.n_dense_blocks;
+  for (int l = 0; l < t.n_dense; ++l) {
+    t.Wt1[l] = W.Wt1[l]; t.Wt2[l] = W.Wt2[l]; t.W1[l] = W.W1[l]; t.W2[l] = W.W2[l]; t.b1[l] = W.b1[l]; t.b2[l] = W.b2[l];
+  }
+  t.Wto = W.Wto; t.Wo = W.Wo; t.bo = W.bo;
+  t.slope = W.d.neg_slope;
+  t.acts = A.tail_acts; t.emb = A.emb; t.gpool = A.gpool;
+  return t;
+}
+
+void emit_tail(Emitter& E, const TailArgs& t, int B) {
+  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { se_tail_kernel<<<B, 1024, 0, st>>>(t); CK(cudaGetLastError()); });
+}
+
+// speaker-encoder backward from gpool ([B,128], gradient of every pooled row) down to d input
+void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Tens& gin) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h, nb = W.d.n_conv_blocks;
+  Tens gout{A.gpool, (long long)ch, 0, A.Tl[nb]};   // broadcast over time (row stride 0)
+  float* pingpong[2] = {A.gA, A.gB};
+  for (int l = nb - 1; l >= 0; --l) {
+    const int Ti = A.Tl[l], To = A.Tl[l + 1], sub = W.d.subsample[l];
+    gout.T = To;
+    // through act + second conv: gH = (conv2^T (gout * act'(h2))) * act'(h1)
+    Tens gH = tens(A.gH, Ti, ch);
+    ConvArgs a2 = bwd_conv_args(W.c2[l], gout, gH, A.B, slope);
+    a2.Mk = A.h2[l]; a2.m_bs = (long long)To * ch; a2.m_rs = ch;
+    a2.Om = A.h1[l]; a2.om_bs = (long long)Ti * ch; a2.om_rs = ch;
+    E.conv(a2, &W.c2[l].tc_bwd);
+    // through the first conv, plus the skip path (avg-pool backward when sub-sampled)
+    Tens gx = tens(pingpong[l & 1], Ti, ch);
+    ConvArgs a1 = bwd_conv_args(W.c1[l], gH, gx, A.B, slope);
+    a1.res = mk_res(gout, sub > 1 ? RES_POOL_BWD : RES_SAME, sub);
+    E.conv(a1, &W.c1[l].tc_bwd);
+    gout = gx;
+  }
+  if (nb == 0) fail(AVC_ERR_INVALID, "n_conv_blocks must be > 0");
+  {   // 1x1 in-conv: gcat = (gout * act'(h0)) W_in
+    Tens gcat = tens(A.gcat, A.T, W.c_cat);
+    ConvArgs a = bwd_conv_args(W.in_conv, gout, gcat, A.B, slope);
+    a.Mk = A.h0; a.m_bs = (long long)A.T * ch; a.m_rs = ch;
+    E.conv(a, &W.in_conv.tc_bwd);
+  }
+  {   // conv bank: sum of the 8 transposed convs of (gcat_k * act'(cat_k)) + pass-through slice
+    ConvArgs a{};
+    a.A = A.gcat; a.a_bs = (long long)A.T * W.c_cat; a.a_rs = W.c_cat; a.T_a = A.T;
+    a.Mk = A.cat; a.m_bs = a.a_bs; a.m_rs = W.c_cat;
+    a.slope = slope; a.bwd = 1; a.s = 1; a.T_y = A.T; a.B = A.B;
+    a.Y = gin.p; a.y_bs = gin.bs; a.y_rs = gin.rs; a.N = W.d.c_in;
+    Tens pass{A.gcat + W.n_bank * W.d.c_bank, a.a_bs, W.c_cat, A.T};
+    a.res = mk_res(pass, RES_SAME, 1);
+    a.n_groups = W.n_bank;
+    for (int z = 0; z < W.n_bank; ++z) {
+      const ConvW& w = W.bank[z];
+      a.g[z] = TapGroup{w.bwd, z * W.d.c_bank, w.c_out, w.k, w.pl() - (w.k - 1), w.pl(), w.pr(), w.c_out};
+    }
+    E.conv(a);
+  }
+}
+
+// ---- decoder ------------------------------------------------------------------------------------------
+struct DecActs {
+  int B = 0, L = 0, nb = 0;
+  int Td[AVC_MAX_BLOCKS + 1]{};
+  float* z = nullptr;                 // content code mu [B,L,c_in]
+  float* c0 = nullptr;                // in-conv raw output
+  float* h[AVC_MAX_BLOCKS + 1]{};     // block inputs/outputs
+  float *c1[AVC_MAX_BLOCKS]{}, *c2[AVC_MAX_BLOCKS]{}, *r1[AVC_MAX_BLOCKS]{};
+  float *st1[AVC_MAX_BLOCKS]{}, *st2[AVC_MAX_BLOCKS]{};
+  float *cond = nullptr, *gcond = nullptr, *gemb_parts = nullptr;
+  float *gh[2]{}, *gy = nullptr, *gr1 = nullptr;
+  int T_out() const { return Td[nb]; }
+};
+
+DecActs alloc_decoder(Arena& m, const DecoderW& W, int B, int L, bool need_bwd) {
+  DecActs A;
+  A.B = B; A.L = L; A.nb = W.d.n_conv_blocks;
+  const int ch = W.d.c_h;
+  if (L <= W.d.kernel_size / 2) fail(AVC_ERR_INVALID, "content code of %d frames is too short for reflect padding", L);
+  A.Td[0] = L;
+  for (int l = 0; l < A.nb; ++l) A.Td[l + 1] = A.Td[l] * W.d.upsample[l];
+  A.z = m.f((size_t)B * L * W.d.c_in);
+  A.c0 = m.f((size_t)B * L * ch);
+  A.h[0] = m.f((size_t)B * L * ch);
+  for (int l = 0; l < A.nb; ++l) {
+    A.c1[l] = m.f((size_t)B * A.Td[l] * ch);
+    A.r1[l] = m.f((size_t)B * A.Td[l] * ch);
+    A.c2[l] = m.f((size_t)B * A.Td[l + 1] * ch);
+    A.h[l + 1] = m.f((size_t)B * A.Td[l + 1] * ch);
+    A.st1[l] = m.f((size_t)B * ch * 2);
+    A.st2[l] = m.f((size_t)B * ch * 2);
+  }
+  A.cond = m.f((size_t)B * 2 * A.nb * 2 * ch);
+  if (need_bwd) {
+    A.gcond = m.f((size_t)B * 2 * A.nb * 2 * ch);
+    A.gemb_parts = m.f((size_t)B * 2 * A.nb * 128);
+    const size_t big = (size_t)B * A.Td[A.nb] * ch;
+    A.gh[0] = m.f(big); A.gh[1] = m.f(big); A.gy = m.f(big); A.gr1 = m.f(big);
+  }
+  return A;
+}
+
+// loop-invariant prefix: h0 = act(IN(in_conv(z))), c1[0] = conv1_0(h0) and its statistics (models.py:413-418)
+void emit_decoder_const(Emitter& E, const DecoderW& W, const DecActs& A) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h;
+  ConvArgs a = fwd_conv_args(W.in_conv, tens(A.z, A.L, W.d.c_in), tens(A.c0, A.L, ch), A.B, false, slope);
+  E.conv(a, &W.in_conv.tc_fwd);
+  emit_norm_fwd(E, A.c0, A.B, A.L, ch, nullptr, 0, nullptr, nullptr, A.h[0], no_res(), slope);
+  ConvArgs a1 = fwd_conv_args(W.c1[0], tens(A.h[0], A.L, ch), tens(A.c1[0], A.L, ch), A.B, false, slope);
+  E.conv(a1, &W.c1[0].tc_fwd);
+  emit_norm_fwd(E, A.c1[0], A.B, A.L, ch, nullptr, 0, nullptr, A.st1[0], nullptr, no_res(), slope);
+}
+
+AffineArgs affine_args(const DecoderW& W, const DecActs& A, const float* emb) {
+  AffineArgs f{};
+  f.L = 2 * A.nb;
+  for (int l = 0; l < f.L; ++l) { f.Wt[l] = W.aWt[l]; f.W[l] = W.aW[l]; f.bias[l] = W.ab[l]; }
+  f.emb = emb; f.cond = A.cond; f.gcond = A.gcond; f.gemb_parts = A.gemb_parts;
+  return f;
+}
+
+// emb-dependent part of the decoder forward (models.py:417-434); `outT` receives the [B,T,c_out] mel
+void emit_decoder_fwd(Emitter& E, const DecoderW& W, const DecActs& A, const float* emb, const Tens& outT) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
+  AffineArgs f = affine_args(W, A, emb);
+  dim3 ag(A.B, L2);
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { affine_fwd_kernel<<<ag, 1024, 0, st>>>(f); CK(cudaGetLastError()); });
+  for (int l = 0; l < A.nb; ++l) {
+    const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
+    if (l > 0) {
+      ConvArgs a1 = fwd_conv_args(W.c1[l], tens(A.h[l], Ti, ch), tens(A.c1[l], Ti, ch), A.B, false, slope);
+      E.conv(a1, &W.c1[l].tc_fwd);
+    }
+    emit_norm_fwd(E, A.c1[l], A.B, Ti, ch, A.cond + (2 * l) * 2 * ch, cb, l == 0 ? A.st1[0] : nullptr,
+                  l == 0 ? nullptr : A.st1[l], A.r1[l], no_res(), slope);
+    // second conv: c_h -> c_h*up channels; the packed weights are channel-permuted so that the
+    // [Ti, ch*up] result IS the pixel-shuffled [Ti*up, ch] tensor (models.py:33-49)
+    ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.r1[l], Ti, ch), Tens{A.c2[l], (long long)Ti * ch * up, ch * up, Ti}, A.B, false, slope);
+    E.conv(a2, &W.c2[l].tc_fwd);
+    ResArgs res = mk_res(tens(A.h[l], Ti, ch), up > 1 ? RES_UP : RES_SAME, up);
+    emit_norm_fwd(E, A.c2[l], A.B, To, ch, A.cond + (2 * l + 1) * 2 * ch, cb, nullptr, A.st2[l], A.h[l + 1], res, slope);
+  }
+  ConvArgs ao = fwd_conv_args(W.out_conv, tens(A.h[A.nb], A.Td[A.nb], ch), outT, A.B, false, slope);
+  E.conv(ao, &W.out_conv.tc_fwd);
+}
+
+// decoder backward: gout = dL/d(decoder output) -> gemb_parts [B, 2*nb, 128]
+void emit_decoder_bwd(Emitter& E, const DecoderW& W, const DecActs& A, const Tens& gout) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
+  int cur = 0;
+  {
+    ConvArgs a = bwd_conv_args(W.out_conv, gout, tens(A.gh[cur], A.Td[A.nb], ch), A.B, slope);
+    E.conv(a, &W.out_conv.tc_bwd);
+  }
+  for (int l = A.nb - 1; l >= 0; --l) {
+    const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
+    Tens gh = tens(A.gh[cur], To, ch);
+    emit_norm_bwd(E, gh.p, A.c2[l], A.st2[l], A.cond + (2 * l + 1) * 2 * ch, cb, A.gy, A.gcond + (2 * l + 1) * 2 * ch, cb,
+                  A.B, To, ch, slope);
+    ConvArgs a2 = bwd_conv_args(W.c2[l], Tens{A.gy, (long long)Ti * ch * up, ch * up, Ti}, tens(A.gr1, Ti, ch), A.B, slope);
+    E.conv(a2, &W.c2[l].tc_bwd);
+    emit_norm_bwd(E, A.gr1, A.c1[l], A.st1[l], A.cond + (2 * l) * 2 * ch, cb, l > 0 ? A.gy : nullptr,
+                  A.gcond + (2 * l) * 2 * ch, cb, A.B, Ti, ch, slope);
+    if (l > 0) {
+      Tens gnext = tens(A.gh[cur ^ 1], Ti, ch);
+      ConvArgs a1 = bwd_conv_args(W.c1[l], tens(A.gy, Ti, ch), gnext, A.B, slope);
+      a1.res = mk_res(gh, up > 1 ? RES_UP_BWD : RES_SAME, up);
+      E.conv(a1, &W.c1[l].tc_bwd);
+      cur ^= 1;
+    }
+  }
+  AffineArgs f = affine_args(W, A, nullptr);
+  dim3 ag(A.B, L2);
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { affine_bwd_kernel<<<ag, 1024, 0, st>>>(f); CK(cudaGetLastError()); });
+}
+
+// ---- misc launch helpers ------------------------------------------------------------------------------
+void emit_layout_in(Emitter& E, const float* src, const int64_t s[3], const Tens& dst, int B, int C) {
+  const long long sb = s[0], sc = s[1], st_ = s[2];
+  const long long n = (long long)B * dst.T * C;
+  const Tens d = dst;
+  E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
+    layout_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, sb, sc, st_, d.p, d.bs, d.rs, B, C, d.T);
+    CK(cudaGetLastError());
+  });
+}
+void emit_layout_out(Emitter& E, const Tens& src, float* dst, const int64_t s[3], int B, int C) {
+  const long long sb = s[0], sc = s[1], st_ = s[2];
+  const long long n = (long long)B * src.T * C;
+  const Tens d = src;
+  E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
+    layout_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.p, d.bs, d.rs, dst, sb, sc, st_, B, C, d.T);
+    CK(cudaGetLastError());
+  });
+}
+void emit_copy(Emitter& E, float* dst, const float* src, size_t n) {
+  E.push(LK_COPY, 0, 8.0 * n, [=](cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
+}
+void emit_zero(Emitter& E, void* dst, size_t bytes) {
+  E.push(LK_COPY, 0, (double)bytes, [=](cudaStream_t st) { CK(cudaMemsetAsync(dst, 0, bytes, st)); });
+}
+unsigned ew_grid(long long n4, int sm) {
+  long long g = (n4 + 255) / 256;
+  long long cap = (long long)sm * 8;
+  return (unsigned)std::max(1LL, std::min(g, cap));
+}
+
+// =================================================================================================
+// weights
+// =================================================================================================
+struct HostW {
+  std::map<std::string, std::vector<float>> t;
+  std::map<std::string, std::vector<int64_t>> shape;
+  const std::vector<float>& get(const std::string& k, std::initializer_list<int64_t> want) {
+    auto it = t.find(k);
+    if (it == t.end()) fail(AVC_ERR_WEIGHTS, "missing weight '%s'", k.c_str());
+    const auto& s = shape[k];
+    std::vector<int64_t> w(want);
+    if (s != w) {
+      std::string got, exp;
+      for (auto v : s) got += std::to_string(v) + ",";
+      for (auto v : w) exp += std::to_string(v) + ",";
+      fail(AVC_ERR_WEIGHTS, "weight '%s' has shape [%s] expected [%s]", k.c_str(), got.c_str(), exp.c_str());
+    }
+    return it->second;
+  }
+};
+
+// Conv1d weight [c_out][c_in][k] -> forward image [k][c_in][c_out'] and dgrad image [k rev][c_out'][c_in].
+// `shuffle` > 1 permutes output channels so pixel_shuffle_1d becomes a reinterpretation of the row
+// (n' = s*C + c  <->  n = shuffle*c + s).
+ConvW pack_conv(avc_handle* h, HostW& hw, const std::string& key, int c_in, int c_out, int k, int stride, int shuffle) {
+  const auto& w = hw.get(key + ".weight", {c_out, c_in, k});
+  const auto& b = hw.get(key + ".bias", {c_out});
+  ConvW c;
+  c.c_in = c_in; c.c_out = c_out; c.k = k; c.stride = stride;
+  std::vector<int> perm(c_out);
+  const int C = c_out / shuffle;
+  for (int np = 0; np < c_out; ++np) perm[np] = shuffle > 1 ? shuffle * (np % C) + np / C : np;
+  std::vector<float> f((size_t)k * c_in * c_out), r((size_t)k * c_out * c_in), bb(c_out);
+  for (int np = 0; np < c_out; ++np) {
+    const int n = perm[np];
+    bb[np] = b[n];
+    for (int ci = 0; ci < c_in; ++ci)
+      for (int j = 0; j < k; ++j) {
+        const float v = w[((size_t)n * c_in + ci) * k + j];
+        f[((size_t)j * c_in + ci) * c_out + np] = v;
+        r[((size_t)(k - 1 - j) * c_out + np) * c_in + ci] = v;
+      }
+  }
+  c.fwd = h->wmem.upload(f);
+  c.bwd = h->wmem.upload(r);
+  c.bias = h->wmem.upload(bb);
+  tc_pack_conv(h->wmem, c.tc_fwd, f, k, c_in, c_out);     // B operand images for the tcgen05 path
+  tc_pack_conv(h->wmem, c.tc_bwd, r, k, c_out, c_in);
+  return c;
+}
+
+void pack_linear(avc_handle* h, HostW& hw, const std::string& key, int n_out, int n_in, float*& Wt, float*& W, float*& b) {
+  const auto& w = hw.get(key + ".weight", {n_out, n_in});
+  const auto& bb = hw.get(key + ".bias", {n_out});
+  std::vector<float> t((size_t)n_in * n_out);
+  for (int n = 0; n < n_out; ++n)
+    for (int c = 0; c < n_in; ++c) t[(size_t)c * n_out + n] = w[(size_t)n * n_in + c];
+  Wt = h->wmem.upload(t);
+  W = h->wmem.upload(w);
+  b = h->wmem.upload(bb);
+}
+
+void pack_encoder(avc_handle* h, HostW& hw, const std::string& pfx, EncoderW& E, const avc_encoder_desc& d, bool content) {
+  E.d = d;
+  E.n_bank = d.bank_size;
+  E.c_cat = d.c_bank * E.n_bank + d.c_in;
+  std::vector<float> bias_cat;
+  for (int i = 0; i < E.n_bank; ++i) {
+    E.bank[i] = pack_conv(h, hw, pfx + "conv_bank." + std::to_string(i), d.c_in, d.c_bank, i + 1, 1, 1);
+    const auto& b = hw.get(pfx + "conv_bank." + std::to_string(i) + ".bias", {d.c_bank});
+    bias_cat.insert(bias_cat.end(), b.begin(), b.end());
+  }
+  E.bank_bias = h->wmem.upload(bias_cat);
+  E.in_conv = pack_conv(h, hw, pfx + "in_conv_layer", E.c_cat, d.c_h, 1, 1, 1);
+  for (int l = 0; l < d.n_conv_blocks; ++l) {
+    E.c1[l] = pack_conv(h, hw, pfx + "first_conv_layers." + std::to_string(l), d.c_h, d.c_h, d.kernel_size, 1, 1);
+    E.c2[l] = pack_conv(h, hw, pfx + "second_conv_layers." + std::to_string(l), d.c_h, d.c_h, d.kernel_size, d.subsample[l], 1);
+  }
+  if (content) {
+    E.mean_layer = pack_conv(h, hw, pfx + "mean_layer", d.c_h, d.c_out, 1, 1, 1);
+  } else {
+    for (int l = 0; l < d.n_dense_blocks; ++l) {
+      pack_linear(h, hw, pfx + "first_dense_layers." + std::to_string(l), d.c_h, d.c_h, E.Wt1[l], E.W1[l], E.b1[l]);
+      pack_linear(h, hw, pfx + "second_dense_layers." + std::to_string(l), d.c_h, d.c_h, E.Wt2[l], E.W2[l], E.b2[l]);
+    }
+    pack_linear(h, hw, pfx + "output_layer", d.c_out, d.c_h, E.Wto, E.Wo, E.bo);
+  }
+}
+
+void pack_decoder(avc_handle* h, HostW& hw, const std::string& pfx, DecoderW& D, const avc_decoder_desc& d) {
+  D.d = d;
+  D.in_conv = pack_conv(h, hw, pfx + "in_conv_layer", d.c_in, d.c_h, 1, 1, 1);
+  for (int l = 0; l < d.n_conv_blocks; ++l) {
+    D.c1[l] = pack_conv(h, hw, pfx + "first_conv_layers." + std::to_string(l), d.c_h, d.c_h, d.kernel_size, 1, 1);
+    D.c2[l] = pack_conv(h, hw, pfx + "second_conv_layers." + std::to_string(l), d.c_h, d.c_h * d.upsample[l], d.kernel_size, 1, d.upsample[l]);
+  }
+  for (int l = 0; l < 2 * d.n_conv_blocks; ++l)
+    pack_linear(h, hw, pfx + "conv_affine_layers." + std::to_string(l), 2 * d.c_h, d.c_cond, D.aWt[l], D.aW[l], D.ab[l]);
+  D.out_conv = pack_conv(h, hw, pfx + "out_conv_layer", d.c_h, d.c_out, 1, 1, 1);
+}
+
+void validate_desc(const avc_model_desc& m) {
+  auto enc = [](const avc_encoder_desc& d, const char* nm, bool content) {
+    if (d.c_in <= 0 || d.c_in % 4 || d.c_h != 128 || d.c_bank % 4 || d.c_bank > 128 || d.c_bank <= 0)
+      fail(AVC_ERR_INVALID, "%s: need c_in %% 4 == 0, c_h == 128, c_bank %% 4 == 0 and <= 128", nm);
+    if (d.c_in > 128) fail(AVC_ERR_INVALID, "%s: c_in > 128 unsupported", nm);
+    if (d.bank_size < 1 || d.bank_size > AVC_MAX_BANK) fail(AVC_ERR_INVALID, "%s: bank_size must be 1..%d", nm, AVC_MAX_BANK);
+    if (d.kernel_size < 1 || d.kernel_size > kMaxTaps) fail(AVC_ERR_INVALID, "%s: kernel_size must be 1..%d", nm, kMaxTaps);
+    if (d.n_conv_blocks < 1 || d.n_conv_blocks > AVC_MAX_BLOCKS) fail(AVC_ERR_INVALID, "%s: n_conv_blocks must be 1..%d", nm, AVC_MAX_BLOCKS);
+    for (int l = 0; l < d.n_conv_blocks; ++l)
+      if (d.subsample[l] < 1 || d.subsample[l] > 4) fail(AVC_ERR_INVALID, "%s: subsample must be 1..4", nm);
+    if ((d.c_bank * d.bank_size + d.c_in + 127) / 128 > kMaxGroups) fail(AVC_ERR_INVALID, "%s: bank concat too wide", nm);
+    if (!content && (d.c_out != 128 || d.n_dense_blocks < 0 || d.n_dense_blocks > kTailMaxDense))
+      fail(AVC_ERR_INVALID, "%s: need c_out == 128 and n_dense_blocks <= %d", nm, kTailMaxDense);
+    if (content && (d.c_out % 4 || d.c_out > 128)) fail(AVC_ERR_INVALID, "%s: c_out must be a multiple of 4, <= 128", nm);
+    if (d.neg_slope < 0.f || d.neg_slope >= 1.f) fail(AVC_ERR_INVALID, "%s: bad activation slope", nm);
+  };
+  enc(m.speaker, "SpeakerEncoder", false);
+  enc(m.content, "ContentEncoder", true);
+  const avc_decoder_desc& d = m.decoder;
+  if (d.c_h != 128 || d.c_cond != 128 || d.c_in != m.content.c_out || d.c_out != m.speaker.c_in || d.c_in % 4)
+    fail(AVC_ERR_INVALID, "Decoder: need c_h == c_cond == 128, c_in == content c_out, c_out == speaker c_in");
+  if (d.n_conv_blocks < 1 || d.n_conv_blocks > AVC_MAX_BLOCKS) fail(AVC_ERR_INVALID, "Decoder: n_conv_blocks must be 1..%d", AVC_MAX_BLOCKS);
+  if (d.kernel_size < 1 || d.kernel_size > kMaxTaps) fail(AVC_ERR_INVALID, "Decoder: kernel_size must be 1..%d", kMaxTaps);
+  for (int l = 0; l < d.n_conv_blocks; ++l)
+    if (d.upsample[l] < 1 || d.upsample[l] > 4) fail(AVC_ERR_INVALID, "Decoder: upsample must be 1..4");
+  if (d.neg_slope < 0.f || d.neg_slope >= 1.f) fail(AVC_ERR_INVALID, "Decoder: bad activation slope");
+}
+
+// =================================================================================================
+// attack plans
+// =================================================================================================
+enum AttackKind { K_EMB = 0, K_E2E = 1, K_FB = 2 };
+
+int content_frames(const avc_handle* h, int T_src) {
+  int t = T_src;
+  for (int l = 0; l < h->desc.content.n_conv_blocks; ++l) t = cdiv(t, h->desc.content.subsample[l]);
+  return t;
+}
+int decoder_frames(const avc_handle* h, int T_src) {
+  int t = content_frames(h, T_src);
+  for (int l = 0; l < h->desc.decoder.n_conv_blocks; ++l) t *= h->desc.decoder.upsample[l];
+  return t;
+}
+
+void run_list(const std::vector<Launch>& v, cudaStream_t st) {
+  for (const auto& l : v) l(st);
+}
+
+void check_strides(const int64_t s[3], const char* nm) {
+  (void)s; (void)nm;   // any strides are legal; element (b,c,t) = base[b*s0 + c*s1 + t*s2]
+}
+
+std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
+  if (!h->have_weights) fail(AVC_ERR_STATE, "avc_load_weights must be called before an attack");
+  if (!a || !a->vc_tgt || !a->adv_tgt || !a->w0 || !a->adv_out) fail(AVC_ERR_INVALID, "null tensor argument");
+  if (kind != K_EMB && !a->vc_src) fail(AVC_ERR_INVALID, "vc_src is required for e2e and fb attacks");
+  if (a->B <= 0 || a->T_tgt <= 0 || a->T_adv <= 0 || a->n_iters < 0) fail(AVC_ERR_INVALID, "bad B/T/n_iters");
+  const int B = a->B, T = a->T_tgt, C = h->desc.speaker.c_in, n_iters = a->n_iters;
+  const float eps = a->eps;
+  const EncoderW& SE = h->se;
+
+  std::unique_ptr<Plan> plan_ptr(new Plan());
+  Plan& plan = *plan_ptr;
+  plan.n_iters = n_iters;
+  plan.use_graph = a->use_graph != 0;
+  Arena& m = plan.mem;
+  Emitter S{h, &plan.setup}, I{h, &plan.iter}, F{h, &plan.finish};
+
+  // ---- state of the optimiser --------------------------------------------------------------
+  const size_t nel = (size_t)B * T * C;
+  float* x = m.f(nel);
+  float* w = m.f(nel);
+  float* mm = m.f(nel);
+  float* vv = m.f(nel);
+  float* gw = a->grad_out ? m.f(nel) : nullptr;
+  int* step = m.raw<int>(1);
+  unsigned int* done = m.raw<unsigned int>(1);
+  std::vector<float> tab((size_t)std::max(n_iters, 1) * 2);
+  for (int i = 0; i < n_iters; ++i) {   // torch/optim/adam.py: bias corrections in python floats (fp64)
+    const double t = i + 1;
+    const double bc1 = 1.0 - std::pow(0.9, t), bc2 = 1.0 - std::pow(0.999, t);
+    tab[2 * i] = (float)(1e-3 / bc1);
+    tab[2 * i + 1] = (float)std::sqrt(bc2);
+  }
+  float2* table = reinterpret_cast<float2*>(m.upload(tab));
+
+  EncActs se1 = alloc_encoder(m, SE, B, T, true, false);
+  const Tens adv = se1.input(SE);   // the perturbed utterance lives in the bank concat buffer
+  Tens xT = tens(x, T, C), wT = tens(w, T, C);
+  emit_layout_in(S, a->vc_tgt, a->tgt_stride, xT, B, C);
+  emit_layout_in(S, a->w0, a->w0_stride, wT, B, C);
+
+  float* org = nullptr;   // targets
+  float* tgt = nullptr;
+  double inv_norm = a->inv_norm;
+  int parts = B;
+  float* loss_parts = nullptr;
+
+  auto se_forward = [&](Emitter& E, const EncActs& A, int tail_mode, const float* tgt_e, const float* org_e,
+                        float* emb_dst) {
+    emit_bank_and_inconv(E, SE, A, false);
+    emit_encoder_blocks_fwd(E, SE, A, false);
+    TailArgs t = tail_args(SE, A);
+    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm;
+    t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+    if (emb_dst) t.emb = emb_dst;
+    emit_tail(E, t, A.B);
+  };
+  auto perturb = [&](Emitter& E) {
+    const unsigned g = ew_grid((long long)nel / 4, h->sm_count);
+    E.push(LK_UPDATE, 0, 12.0 * nel, [=](cudaStream_t s_) { perturb_kernel<<<g, 256, 0, s_>>>(x, w, adv.p, adv.bs, adv.rs, B, T, C, eps); CK(cudaGetLastError()); });
+  };
+  auto update = [&](Emitter& E, const Tens& gadv) {
+    UpdateArgs u{};
+    u.g_adv = gadv.p; u.g_bs = gadv.bs; u.g_rs = gadv.rs; u.x = x; u.w = w; u.m = mm; u.v = vv;
+    u.adv = adv.p; u.adv_bs = adv.bs; u.adv_rs = adv.rs; u.gw_out = gw; u.B = B; u.T = T; u.C = C; u.eps = eps;
+    u.table = table; u.step = step; u.done = done;
+    const unsigned g = ew_grid((long long)nel / 4, h->sm_count);
+    E.push(LK_UPDATE, 0, 36.0 * nel, [=](cudaStream_t s_) { adam_tanh_update_kernel<<<g, 256, 0, s_>>>(u); CK(cudaGetLastError()); });
+  };
+
+  if (kind == K_EMB) {
+    if (inv_norm <= 0) inv_norm = 1.0 / ((double)B * SE.d.c_out);
+    loss_parts = m.f((size_t)std::max(n_iters, 1) * parts);
+    org = m.f((size_t)B * 128);
+    tgt = m.f((size_t)B * 128);
+    // targets (attack_utils.py:73-75)
+    emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+    se_forward(S, se1, TAIL_FWD, nullptr, nullptr, org);
+    if (a->T_adv == T) {
+      emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+      se_forward(S, se1, TAIL_FWD, nullptr, nullptr, tgt);
+    } else {
+      EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
+      emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+      se_forward(S, seT, TAIL_FWD, nullptr, nullptr, tgt);
+    }
+    perturb(S);
+    // iteration (attack_utils.py:77-84)
+    se_forward(I, se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
+    Tens gin = tens(se1.gin, T, C);
+    emit_speaker_bwd(I, SE, se1, gin);
+    update(I, gin);
+  } else {
+    const int T_src = a->T_src;
+    if (T_src <= 0) fail(AVC_ERR_INVALID, "bad T_src");
+    const int L = content_frames(h, T_src), T_dec = decoder_frames(h, T_src), Cm = h->desc.decoder.c_out;
+    // content code (loop invariant; the reference recomputes it every iteration, models.py:482)
+    EncActs ce = alloc_encoder(m, h->ce, B, T_src, false, true);
+    DecActs dec = alloc_decoder(m, h->dec, B, L, true);
+    emit_layout_in(S, a->vc_src, a->src_stride, ce.input(h->ce), B, C);
+    emit_bank_and_inconv(S, h->ce, ce, true);
+    emit_encoder_blocks_fwd(S, h->ce, ce, true);
+    {
+      const int nb = h->ce.d.n_conv_blocks;
+      ConvArgs am = fwd_conv_args(h->ce.mean_layer, tens(ce.hout[nb - 1], L, h->ce.d.c_h), tens(dec.z, L, h->ce.d.c_out), B, false, 0.f);
+      S.conv(am, &h->ce.mean_layer.tc_fwd);
+    }
+    emit_decoder_const(S, h->dec, dec);
+
+    if (kind == K_E2E) {
+      const size_t nout = (size_t)B * T_dec * Cm;
+      if (inv_norm <= 0) inv_norm = 1.0 / ((double)nout);
+      float* dout = m.f(nout);
+      float* gout = m.f(nout);
+      org = m.f(nout);
+      tgt = m.f(nout);
+      Tens doutT = tens(dout, T_dec, Cm);
+      const long long n4 = (long long)nout / 4;
+      const unsigned mg = ew_grid(n4, h->sm_count);
+      parts = (int)mg;
+      loss_parts = m.f((size_t)std::max(n_iters, 1) * parts);
+      // targets (attack_utils.py:35-37)
+      emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+      se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
+      emit_decoder_fwd(S, h->dec, dec, se1.emb, doutT);
+      emit_copy(S, org, dout, nout);
+      if (a->T_adv == T) {
+        emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+        se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
+        emit_decoder_fwd(S, h->dec, dec, se1.emb, doutT);
+      } else {
+        EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
+        emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+        se_forward(S, seT, TAIL_FWD, nullptr, nullptr, nullptr);
+        emit_decoder_fwd(S, h->dec, dec, seT.emb, doutT);
+      }
+      emit_copy(S, tgt, dout, nout);
+      perturb(S);
+      // iteration (attack_utils.py:39-46)
+      se_forward(I, se1, TAIL_FWD, nullptr, nullptr, nullptr);
+      emit_decoder_fwd(I, h->dec, dec, se1.emb, doutT);
+      {
+        const float invn = (float)inv_norm;
+        float* lp = loss_parts; int* stp = step; const int pp = parts;
+        I.push(LK_LOSS, 0, 16.0 * nout, [=](cudaStream_t s_) { mse_grad_kernel<<<mg, 256, 0, s_>>>(dout, tgt, org, gout, n4, invn, lp, stp, pp); CK(cudaGetLastError()); });
+      }
+      emit_decoder_bwd(I, h->dec, dec, tens(gout, T_dec, Cm));
+    } else {   // K_FB
+      if (inv_norm <= 0) inv_norm = 1.0 / ((double)B * SE.d.c_out);
+      loss_parts = m.f((size_t)std::max(n_iters, 1) * parts);
+      org = m.f((size_t)B * 128);
+      tgt = m.f((size_t)B * 128);
+      EncActs se2 = alloc_encoder(m, SE, B, T_dec, true, false);   // speaker encoder on the converted utterance
+      const Tens conv_out = se2.input(SE);
+      // targets (attack_utils.py:117-119)
+      emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+      se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
+      emit_decoder_fwd(S, h->dec, dec, se1.emb, conv_out);
+      se_forward(S, se2, TAIL_FWD, nullptr, nullptr, org);
+      if (a->T_adv == T) {
+        emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+        se_forward(S, se1, TAIL_FWD, nullptr, nullptr, tgt);
+      } else {
+        EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
+        emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+        se_forward(S, seT, TAIL_FWD, nullptr, nullptr, tgt);
+      }
+      perturb(S);
+      // iteration (attack_utils.py:121-128)
+      se_forward(I, se1, TAIL_FWD, nullptr, nullptr, nullptr);
+      emit_decoder_fwd(I, h->dec, dec, se1.emb, conv_out);
+      se_forward(I, se2, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
+      Tens g2 = tens(se2.gin, T_dec, C);
+      emit_speaker_bwd(I, SE, se2, g2);
+      emit_decoder_bwd(I, h->dec, dec, g2);
+    }
+    // common tail of e2e / fb: d emb -> speaker encoder backward -> update
+    {
+      TailArgs t = tail_args(SE, se1);
+      t.mode = TAIL_BWD; t.gemb = dec.gemb_parts; t.gemb_parts = 2 * dec.nb;
+      emit_tail(I, t, B);
+    }
+    Tens gin = tens(se1.gin, T, C);
+    emit_speaker_bwd(I, SE, se1, gin);
+    update(I, gin);
+  }
+
+  // ---- finish: result, loss curve, last gradient -----------------------------------------------
+  emit_layout_out(F, adv, a->adv_out, a->out_stride, B, C);
+  if (a->loss_out && n_iters > 0) {
+    float* lp = loss_parts; float* lo = a->loss_out; const int pp = parts;
+    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) { loss_sum_kernel<<<(n_iters + 127) / 128, 128, 0, s_>>>(lp, pp, n_iters, lo); CK(cudaGetLastError()); });
+  }
+  if (a->grad_out && n_iters > 0) {
+    const int64_t cs[3] = {(int64_t)C * T, (int64_t)T, 1};
+    emit_layout_out(F, tens(gw, T, C), a->grad_out, cs, B, C);
+  }
+
+  // ---- setup: targets, loop invariants, initial perturbation; then capture one iteration -----------
+  CK(cudaDeviceSynchronize());   // arena memsets / uploads were issued on the legacy stream
+  try {
+    run_list(plan.setup, st);
+    h->launches += (long long)plan.setup.size();
+    h->launches_per_iter = (int)plan.iter.size();
+    if (n_iters > 0 && plan.use_graph) {
+      cudaStream_t cs;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+      try {
+        run_list(plan.iter, cs);
+      } catch (...) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(cs, &g);
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        throw;
+      }
+      e = cudaStreamEndCapture(cs, &plan.graph);
+      cudaStreamDestroy(cs);
+      if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+      CK(cudaGraphInstantiate(&plan.exec, plan.graph, 0));
+    }
+  } catch (...) {
+    cudaDeviceSynchronize();   // nothing may still be running when the arena is released
+    throw;
+  }
+  return plan_ptr;
+}
+
+void step_attack(avc_handle* h, Plan& plan, int n, cudaStream_t st) {
+  if (plan.finished) fail(AVC_ERR_STATE, "attack session already finished");
+  if (n < 0 || plan.done_iters + n > plan.n_iters)
+    fail(AVC_ERR_INVALID, "session was opened for %d iterations, %d done, %d more requested", plan.n_iters, plan.done_iters, n);
+  try {
+    if (plan.exec) {
+      for (int i = 0; i < n; ++i) CK(cudaGraphLaunch(plan.exec, st));
+    } else {
+      for (int i = 0; i < n; ++i) run_list(plan.iter, st);
+    }
+  } catch (...) {
+    cudaDeviceSynchronize();
+    throw;
+  }
+  plan.done_iters += n;
+  h->launches += (long long)plan.iter.size() * n;
+}
+
+void finish_attack(avc_handle* h, Plan& plan, cudaStream_t st) {
+  if (plan.finished) return;
+  plan.finished = true;
+  try {
+    run_list(plan.finish, st);
+    h->launches += (long long)plan.finish.size();
+    CK(cudaStreamSynchronize(st));   // the session's buffers are freed next
+  } catch (...) {
+    cudaDeviceSynchronize();
+    throw;
+  }
+}
+
+void run_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
+  std::unique_ptr<Plan> plan = build_attack(h, kind, a, st);
+  step_attack(h, *plan, a->n_iters, st);
+  finish_attack(h, *plan, st);
+}
+
+template <class Fn>
+int guarded(avc_handle* h, Fn&& fn) {
+  try {
+    if (h) CK(cudaSetDevice(h->device));
+    fn();
+    return AVC_OK;
+  } catch (const Fail& f) {
+    if (h) h->err = f.msg; else g_create_error = f.msg;
+    return f.code;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what(); else g_create_error = e.what();
+    return AVC_ERR_INVALID;
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* avc_version(void) { return "avc_b200 0.1 (sm_100a)"; }
+
+int avc_create(avc_handle** out, const avc_model_desc* desc, int device) {
+  if (!out || !desc) { g_create_error = "null argument"; return AVC_ERR_INVALID; }
+  *out = nullptr;
+  return guarded(nullptr, [&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) fail(AVC_ERR_CUDA, "no CUDA device available (%s); libavc_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) fail(AVC_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    validate_desc(*desc);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp p{};
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) fail(AVC_ERR_CUDA, "device %d is sm_%d%d; libavc_b200 is built for sm_100a only", device, p.major, p.minor);
+    auto h = std::make_unique<avc_handle>();
+    h->device = device;
+    h->sm_count = p.multiProcessorCount;
+    h->desc = *desc;
+    if (const char* s = getenv("AVC_CONV_IMPL")) h->conv_impl = atoi(s);
+    init_kernel_attributes();
+    *out = h.release();
+  });
+}
+
+void avc_destroy(avc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+const char* avc_last_error(const avc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int avc_load_weights(avc_handle* h, const avc_weight_view* tensors, int32_t n) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!tensors || n <= 0) fail(AVC_ERR_INVALID, "no tensors");
+    HostW hw;
+    for (int i = 0; i < n; ++i) {
+      const avc_weight_view& v = tensors[i];
+      if (!v.name || !v.data || v.ndim < 1 || v.ndim > 4) fail(AVC_ERR_WEIGHTS, "bad weight view %d", i);
+      size_t cnt = 1;
+      std::vector<int64_t> shp;
+      for (int d = 0; d < v.ndim; ++d) { cnt *= (size_t)v.shape[d]; shp.push_back(v.shape[d]); }
+      std::vector<float> host(cnt);
+      CK(cudaMemcpy(host.data(), v.data, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+      hw.t[v.name] = std::move(host);
+      hw.shape[v.name] = shp;
+    }
+    if (h->have_weights) fail(AVC_ERR_STATE, "weights already loaded; create a new handle");
+    pack_encoder(h, hw, "speaker_encoder.", h->se, h->desc.speaker, false);
+    pack_encoder(h, hw, "content_encoder.", h->ce, h->desc.content, true);
+    pack_decoder(h, hw, "decoder.", h->dec, h->desc.decoder);
+    CK(cudaDeviceSynchronize());
+    h->have_weights = true;
+  });
+}
+
+int avc_emb_attack(avc_handle* h, const avc_attack_args* a, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] { run_attack(h, K_EMB, a, (cudaStream_t)stream); });
+}
+int avc_e2e_attack(avc_handle* h, const avc_attack_args* a, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] { run_attack(h, K_E2E, a, (cudaStream_t)stream); });
+}
+int avc_fb_attack(avc_handle* h, const avc_attack_args* a, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] { run_attack(h, K_FB, a, (cudaStream_t)stream); });
+}
+
+int avc_attack_begin(avc_handle* h, int32_t kind, const avc_attack_args* a, void* stream, avc_session** out) {
+  if (!h || !out) return AVC_ERR_INVALID;
+  *out = nullptr;
+  return guarded(h, [&] {
+    if (kind < 0 || kind > 2) fail(AVC_ERR_INVALID, "kind must be 0 (emb), 1 (e2e) or 2 (fb)");
+    std::unique_ptr<Plan> plan = build_attack(h, (AttackKind)kind, a, (cudaStream_t)stream);
+    avc_session* s = new avc_session{h, std::move(plan)};
+    *out = s;
+  });
+}
+
+int avc_attack_step(avc_session* s, int32_t n, void* stream) {
+  if (!s) return AVC_ERR_INVALID;
+  return guarded(s->h, [&] { step_attack(s->h, *s->plan, n, (cudaStream_t)stream); });
+}
+
+int avc_attack_end(avc_session* s, void* stream) {
+  if (!s) return AVC_ERR_INVALID;
+  int rc = guarded(s->h, [&] { finish_attack(s->h, *s->plan, (cudaStream_t)stream); });
+  cudaSetDevice(s->h->device);
+  cudaDeviceSynchronize();
+  delete s;
+  return rc;
+}
+
+int32_t avc_session_launches(const avc_session* s) { return s ? (int32_t)s->plan->iter.size() : -1; }
+
+// Run ONE iteration eagerly with a CUDA event pair around every launch (stream-ordered, so each
+// kernel is timed in isolation).  Counts as one of the session's iterations.
+int avc_session_profile(avc_session* s, int32_t cap, int32_t* kind, float* ms, double* flops, double* bytes, void* stream) {
+  if (!s) return AVC_ERR_INVALID;
+  return guarded(s->h, [&] {
+    Plan& plan = *s->plan;
+    const int n = (int)plan.iter.size();
+    if (cap < n || !kind || !ms || !flops || !bytes) fail(AVC_ERR_INVALID, "profile arrays must hold %d entries", n);
+    if (plan.finished || plan.done_iters + 1 > plan.n_iters) fail(AVC_ERR_STATE, "no iteration left to profile");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    try {
+      CK(cudaEventRecord(ev[0], st));
+      for (int i = 0; i < n; ++i) {
+        plan.iter[i](st);
+        CK(cudaEventRecord(ev[i + 1], st));
+      }
+      CK(cudaStreamSynchronize(st));
+    } catch (...) {
+      cudaDeviceSynchronize();
+      for (auto& e : ev) cudaEventDestroy(e);
+      throw;
+    }
+    for (int i = 0; i < n; ++i) {
+      CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+      kind[i] = plan.iter[i].kind; flops[i] = plan.iter[i].flops; bytes[i] = plan.iter[i].bytes;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    plan.done_iters += 1;
+    s->h->launches += n;
+  });
+}
+
+int32_t avc_decoder_frames(const avc_handle* h, int32_t T_src) { return h ? decoder_frames(h, T_src) : -1; }
+
+int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], int32_t B, int32_t T, float* emb, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!h->have_weights) fail(AVC_ERR_STATE, "weights not loaded");
+    if (!x || !emb || B <= 0 || T <= 0) fail(AVC_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan plan;
+    Emitter S{h, &plan.setup};
+    EncActs A = alloc_encoder(plan.mem, h->se, B, T, false, false);
+    emit_layout_in(S, x, stride, A.input(h->se), B, h->desc.speaker.c_in);
+    emit_bank_and_inconv(S, h->se, A, false);
+    emit_encoder_blocks_fwd(S, h->se, A, false);
+    TailArgs t = tail_args(h->se, A);
+    t.mode = TAIL_FWD; t.emb = emb;
+    emit_tail(S, t, B);
+    run_list(plan.setup, st);
+    h->launches += (long long)plan.setup.size();
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int avc_inference(avc_handle* h, const float* src, const int64_t src_stride[3], int32_t T_src, const float* tgt,
+                  const int64_t tgt_stride[3], int32_t T_tgt, int32_t B, float* out, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!h->have_weights) fail(AVC_ERR_STATE, "weights not loaded");
+    if (!src || !tgt || !out || B <= 0 || T_src <= 0 || T_tgt <= 0) fail(AVC_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan plan;
+    Emitter S{h, &plan.setup};
+    const int C = h->desc.speaker.c_in, L = content_frames(h, T_src), T_dec = decoder_frames(h, T_src);
+    EncActs ce = alloc_encoder(plan.mem, h->ce, B, T_src, false, true);
+    EncActs se = alloc_encoder(plan.mem, h->se, B, T_tgt, false, false);
+    DecActs dec = alloc_decoder(plan.mem, h->dec, B, L, false);
+    float* dout = plan.mem.f((size_t)B * T_dec * C);
+    emit_layout_in(S, src, src_stride, ce.input(h->ce), B, C);
+    emit_bank_and_inconv(S, h->ce, ce, true);
+    emit_encoder_blocks_fwd(S, h->ce, ce, true);
+    const int nb = h->ce.d.n_conv_blocks;
+    ConvArgs am = fwd_conv_args(h->ce.mean_layer, tens(ce.hout[nb - 1], L, h->ce.d.c_h), tens(dec.z, L, h->ce.d.c_out), B, false, 0.f);
+    S.conv(am, &h->ce.mean_layer.tc_fwd);
+    emit_decoder_const(S, h->dec, dec);
+    emit_layout_in(S, tgt, tgt_stride, se.input(h->se), B, C);
+    emit_bank_and_inconv(S, h->se, se, false);
+    emit_encoder_blocks_fwd(S, h->se, se, false);
+    TailArgs t = tail_args(h->se, se);
+    t.mode = TAIL_FWD;
+    emit_tail(S, t, B);
+    emit_decoder_fwd(S, h->dec, dec, se.emb, tens(dout, T_dec, C));
+    const int64_t cs[3] = {(int64_t)C * T_dec, (int64_t)T_dec, 1};
+    emit_layout_out(S, tens(dout, T_dec, C), out, cs, B, C);
+    run_list(plan.setup, st);
+    h->launches += (long long)plan.setup.size();
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+// ---- unit-test entry points ---------------------------------------------------------------------------
+static ConvW pack_adhoc(avc_handle* h, Arena& tmp, const float* w_dev, const float* bias_dev, int c_in, int c_out, int k, int stride) {
+  std::vector<float> w((size_t)c_out * c_in * k), b(c_out, 0.f);
+  CK(cudaMemcpy(w.data(), w_dev, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  if (bias_dev) CK(cudaMemcpy(b.data(), bias_dev, b.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  ConvW c;
+  c.c_in = c_in; c.c_out = c_out; c.k = k; c.stride = stride;
+  std::vector<float> f((size_t)k * c_in * c_out), r((size_t)k * c_out * c_in);
+  for (int n = 0; n < c_out; ++n)
+    for (int ci = 0; ci < c_in; ++ci)
+      for (int j = 0; j < k; ++j) {
+        const float v = w[((size_t)n * c_in + ci) * k + j];
+        f[((size_t)j * c_in + ci) * c_out + n] = v;
+        r[((size_t)(k - 1 - j) * c_out + n) * c_in + ci] = v;
+      }
+  c.fwd = tmp.upload(f); c.bwd = tmp.upload(r); c.bias = tmp.upload(b);
+  tc_pack_conv(tmp, c.tc_fwd, f, k, c_in, c_out);
+  tc_pack_conv(tmp, c.tc_bwd, r, k, c_out, c_in);
+  (void)h;
+  return c;
+}
+
+static void check_conv_dims(int B, int T, int c_in, int c_out, int k, int stride) {
+  if (B <= 0 || T <= 0 || c_in <= 0 || c_out <= 0 || c_in % 4 || c_out % 4 || k < 1 || k > kMaxTaps || stride < 1 || stride > 4)
+    fail(AVC_ERR_INVALID, "conv1d: need channels %% 4 == 0, 1 <= k <= %d, 1 <= stride <= 4", kMaxTaps);
+  if (T <= k / 2) fail(AVC_ERR_INVALID, "conv1d: T=%d too short for reflect pad %d", T, k / 2);
+}
+
+int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t T,
+                   int32_t c_in, int32_t c_out, int32_t k, int32_t stride, int32_t impl, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    check_conv_dims(B, T, c_in, c_out, k, stride);
+    Arena tmp;
+    ConvW c = pack_adhoc(h, tmp, w, bias, c_in, c_out, k, stride);
+    const int To = cdiv(T, stride);
+    ConvArgs a = fwd_conv_args(c, tens(const_cast<float*>(x), T, c_in), tens(y, To, c_out), B, false, 0.f);
+    const int save = h->conv_impl;
+    h->conv_impl = impl;
+    try { launch_conv(h, a, &c.tc_fwd, (cudaStream_t)stream); } catch (...) { h->conv_impl = save; throw; }
+    h->conv_impl = save;
+    h->launches += 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx, int32_t B, int32_t T, int32_t c_in,
+                     int32_t c_out, int32_t k, int32_t stride, int32_t impl, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    check_conv_dims(B, T, c_in, c_out, k, stride);
+    Arena tmp;
+    ConvW c = pack_adhoc(h, tmp, w, nullptr, c_in, c_out, k, stride);
+    const int To = cdiv(T, stride);
+    ConvArgs a = bwd_conv_args(c, tens(const_cast<float*>(dy), To, c_out), tens(dx, T, c_in), B, 0.f);
+    const int save = h->conv_impl;
+    h->conv_impl = impl;
+    try { launch_conv(h, a, &c.tc_bwd, (cudaStream_t)stream); } catch (...) { h->conv_impl = save; throw; }
+    h->conv_impl = save;
+    h->launches += 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond, const float* res, int32_t up, float* out,
+                               float* stats_out, int32_t B, int32_t T, int32_t C, float neg_slope, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!y || !out || B <= 0 || T <= 0 || C <= 0 || up < 1) fail(AVC_ERR_INVALID, "bad argument");
+    if (res && T % up) fail(AVC_ERR_INVALID, "T must be a multiple of up");
+    std::vector<Launch> v;
+    Emitter E{h, &v};
+    ResArgs r = no_res();
+    if (res) r = mk_res(tens(const_cast<float*>(res), T / up, C), up > 1 ? RES_UP : RES_SAME, up);
+    emit_norm_fwd(E, y, B, T, C, cond, 2 * C, nullptr, stats_out, out, r, neg_slope);
+    run_list(v, (cudaStream_t)stream);
+    h->launches += 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, const float* stats, const float* cond, float* gy,
+                               float* gcond, int32_t B, int32_t T, int32_t C, float neg_slope, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!g || !y || !stats || B <= 0 || T <= 0 || C <= 0 || C % kNormCh) fail(AVC_ERR_INVALID, "bad argument");
+    std::vector<Launch> v;
+    Emitter E{h, &v};
+    emit_norm_bwd(E, g, y, stats, cond, 2 * C, gy, gcond, 2 * C, B, T, C, neg_slope);
+    run_list(v, (cudaStream_t)stream);
+    h->launches += 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float* w, float* m, float* v, float* adv, int64_t n,
+                       float eps, int32_t step, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    if (!g_adv || !x || !w || !m || !v || !adv || n <= 0 || n % 4 || step < 1) fail(AVC_ERR_INVALID, "bad argument (n must be a multiple of 4, step >= 1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena tmp;
+    const double t = step;
+    std::vector<float> tab = {(float)(1e-3 / (1.0 - std::pow(0.9, t))), (float)std::sqrt(1.0 - std::pow(0.999, t))};
+    UpdateArgs u{};
+    u.g_adv = g_adv; u.g_bs = n; u.g_rs = (int)0; u.x = x; u.w = w; u.m = m; u.v = v; u.adv = adv; u.adv_bs = n; u.adv_rs = 0;
+    u.B = 1; u.T = 1; u.C = (int)n;   // one row of n channels
+    if (n > (1LL << 30)) fail(AVC_ERR_INVALID, "n too large for the unit-test entry point");
+    u.eps = eps;
+    u.table = reinterpret_cast<float2*>(tmp.upload(tab));
+    u.step = tmp.raw<int>(1);
+    u.done = nullptr;
+    const unsigned g = ew_grid(n / 4, h->sm_count);
+    adam_tanh_update_kernel<<<g, 256, 0, st>>>(u);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int64_t avc_kernel_launches(const avc_handle* h) { return h ? h->launches : -1; }
+int32_t avc_launches_per_iter(const avc_handle* h) { return h ? h->launches_per_iter : -1; }
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+/*
+ * avc_b200.h -- C-ABI of libavc_b200.so: the B200 (sm_100a) implementation of attack-vc's
+ * adversarial perturbation loop.
+ *
+ * The reference (bbbbhrrrr/attack-vc) has no native layer: its hot path is Python calling
+ * PyTorch (attack_utils.py:7-130 driving models.py:121-485).  Each entry point below therefore
+ * cites the reference *Python* interface it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side (this repository ships that binding as
+ * attack_vc_b200/_lib.py + attack_utils.py).
+ *
+ * Conventions
+ *   - every function returns AVC_OK (0) or a negative avc_status; avc_last_error() gives text.
+ *   - all data pointers are DEVICE pointers to fp32 unless a name ends in _host.
+ *   - utterance tensors use the reference's logical layout [B, 80, T] with explicit element
+ *     strides (sb, sc, st), so the CLI's transposed views (attack.py:49-50) need no copy.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls that own temporary device memory (the
+ *     one-shot attacks, avc_attack_end, the forward-only and unit-test entry points) synchronise
+ *     the stream before returning; avc_attack_step only enqueues.  The library never frees caller memory and keeps no global mutable state: all
+ *     state lives in the handle, one handle per (process, device).
+ *   - there is no CPU fallback: without a CUDA device avc_create fails with AVC_ERR_CUDA.
+ */
+#ifndef AVC_B200_H_
+#define AVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct avc_handle avc_handle;
+typedef struct avc_session avc_session;   /* one attack in flight: optimiser state + captured iteration */
+
+typedef enum avc_status {
+  AVC_OK = 0,
+  AVC_ERR_INVALID = -1,     /* bad argument / unsupported hyper-parameter        */
+  AVC_ERR_CUDA = -2,        /* CUDA runtime error (text in avc_last_error)       */
+  AVC_ERR_WEIGHTS = -3,     /* weights missing or wrong shape                    */
+  AVC_ERR_STATE = -4        /* call order violated (e.g. attack before weights)  */
+} avc_status;
+
+#define AVC_MAX_BLOCKS 8
+#define AVC_MAX_BANK 8
+
+/* Hyper-parameters of one encoder (constructor args of ContentEncoder models.py:126-139 and
+ * SpeakerEncoder models.py:218-232).  dropout_rate must be 0 and bank_scale 1. */
+typedef struct avc_encoder_desc {
+  int32_t c_in, c_h, c_out, kernel_size, bank_size, c_bank;
+  int32_t n_conv_blocks, n_dense_blocks;          /* n_dense_blocks = 0 for the content encoder */
+  int32_t subsample[AVC_MAX_BLOCKS];
+  float neg_slope;                                /* 0 = ReLU, 0.01 = "lrelu" (models.py:107-118) */
+} avc_encoder_desc;
+
+/* Decoder constructor args, models.py:351-363.  sn must be false, dropout_rate 0. */
+typedef struct avc_decoder_desc {
+  int32_t c_in, c_cond, c_h, c_out, kernel_size, n_conv_blocks;
+  int32_t upsample[AVC_MAX_BLOCKS];
+  float neg_slope;
+} avc_decoder_desc;
+
+typedef struct avc_model_desc {
+  avc_encoder_desc speaker, content;
+  avc_decoder_desc decoder;
+} avc_model_desc;
+
+/* One tensor of model.state_dict() (models.py:438-452): key, device pointer, PyTorch shape. */
+typedef struct avc_weight_view {
+  const char* name;        /* e.g. "speaker_encoder.conv_bank.3.weight" */
+  const float* data;       /* contiguous fp32, device memory            */
+  int32_t ndim;
+  int64_t shape[4];
+} avc_weight_view;
+
+/* Arguments shared by the three attacks (attack_utils.py:7-14, 51-53, 89-96). */
+typedef struct avc_attack_args {
+  const float* vc_tgt;  int64_t tgt_stride[3];  int32_t B, T_tgt;   /* utterance to defend   */
+  const float* adv_tgt; int64_t adv_stride[3];  int32_t T_adv;      /* adversarial target    */
+  const float* vc_src;  int64_t src_stride[3];  int32_t T_src;      /* NULL for emb_attack   */
+  const float* w0;      int64_t w0_stride[3];   /* initial w ~ N(0,1) (attack_utils.py:30,68,112) */
+  float* adv_out;       int64_t out_stride[3];  /* vc_tgt + eps*tanh(w_final), [B,80,T_tgt]       */
+  float* loss_out;      /* [n_iters] device, per-iteration loss; may be NULL                     */
+  float* grad_out;      /* [B,80,T_tgt] contiguous, dL/dw of the LAST iteration; may be NULL     */
+  float eps;            /* attack.py:95-100                                                      */
+  int32_t n_iters;      /* attack.py:101-106                                                     */
+  double inv_norm;      /* MSELoss normaliser 1/(B_global*D); <=0 means 1/(B*D) of this call.     *
+                         * Sharded callers pass the GLOBAL value (SURVEY §5 sharding hazard).      */
+  int32_t use_graph;    /* 1: capture one iteration into a CUDA graph and replay it               */
+} avc_attack_args;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* replaces: AdaInVC(config["model"]).to(device)  (data_utils.py:220, models.py:438-452) */
+int avc_create(avc_handle** out, const avc_model_desc* desc, int device);
+void avc_destroy(avc_handle* h);
+const char* avc_last_error(const avc_handle* h);   /* h may be NULL: last create() error */
+/* replaces: model.load_state_dict(...) (data_utils.py:221).  Synchronous; copies + repacks. */
+int avc_load_weights(avc_handle* h, const avc_weight_view* tensors, int32_t n);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* replaces: attack_utils.emb_attack (attack_utils.py:51-86) */
+int avc_emb_attack(avc_handle* h, const avc_attack_args* a, void* stream);
+/* replaces: attack_utils.e2e_attack (attack_utils.py:7-48) */
+int avc_e2e_attack(avc_handle* h, const avc_attack_args* a, void* stream);
+/* replaces: attack_utils.fb_attack (attack_utils.py:89-130) */
+int avc_fb_attack(avc_handle* h, const avc_attack_args* a, void* stream);
+
+/* ---- the same attacks as a session, so a caller can interleave iterations with a progress bar
+ * (the reference shows tqdm.trange, attack_utils.py:33,71,115) or time iterations precisely.
+ * begin: validates, computes targets + loop invariants, captures one iteration (kind 0 emb, 1 e2e,
+ * 2 fb; a->n_iters is the MAXIMUM number of iterations).  step: enqueue n more iterations.
+ * end: write adv_out / loss_out / grad_out, synchronise, free the session (always frees). */
+int avc_attack_begin(avc_handle* h, int32_t kind, const avc_attack_args* a, void* stream, avc_session** out);
+int avc_attack_step(avc_session* s, int32_t n, void* stream);
+int avc_attack_end(avc_session* s, void* stream);
+/* kernels launched by one iteration of this session */
+int32_t avc_session_launches(const avc_session* s);
+/* measurement aid for bench.py: run ONE iteration eagerly with CUDA events around every launch.
+ * Arrays hold avc_session_launches() entries: kind (0 conv,1 norm,2 dense tail,3 affine,4 loss,
+ * 5 update,6 layout,7 copy), milliseconds, algorithmic FLOPs and algorithmic HBM bytes. */
+int avc_session_profile(avc_session* s, int32_t cap, int32_t* kind, float* ms, double* flops, double* bytes, void* stream);
+
+/* ---- forward-only model entry points (also used by the parity tests) --- */
+/* replaces: model.speaker_encoder(x) (models.py:327-343).  x [B,80,T] strided -> emb [B,c_out] */
+int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], int32_t B, int32_t T,
+                        float* emb, void* stream);
+/* replaces: model.inference(src, tgt) (models.py:472-485) -> out [B,80,T_out] contiguous,
+ * T_out = avc_decoder_frames(h, T_src). */
+int avc_inference(avc_handle* h, const float* src, const int64_t src_stride[3], int32_t T_src,
+                  const float* tgt, const int64_t tgt_stride[3], int32_t T_tgt, int32_t B,
+                  float* out, void* stream);
+int32_t avc_decoder_frames(const avc_handle* h, int32_t T_src);
+
+/* ---- per-kernel entry points for unit tests (time-major [B,T,C] contiguous tensors) ------- */
+/* replaces: pad_layer(x, nn.Conv1d(k, stride)) (models.py:10-30): reflect pad + conv + bias.
+ * w is PyTorch layout [c_out, c_in, k].  y [B, ceil(T/stride), c_out]. */
+int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* bias, float* y,
+                   int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride,
+                   int32_t impl /*0 auto, 1 simt fp32, 2 tcgen05 3xTF32*/, void* stream);
+/* autograd of the above w.r.t. x: dy [B,T_out,c_out] -> dx [B,T,c_in] */
+int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx,
+                     int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride,
+                     int32_t impl, void* stream);
+/* replaces: act(append_cond(InstanceNorm1d(y), cond)) [+ residual] (models.py:414-431).
+ * cond [B,2C] (mean | std) or NULL; res [B,T/up,C] or NULL; stats_out [B,C,2] (mean, rstd). */
+int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond, const float* res,
+                               int32_t up, float* out, float* stats_out, int32_t B, int32_t T,
+                               int32_t C, float neg_slope, void* stream);
+/* its backward: g [B,T,C] -> gy [B,T,C] (may be NULL), gcond [B,2C] (d mean | d std) */
+int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, const float* stats,
+                               const float* cond, float* gy, float* gcond, int32_t B, int32_t T,
+                               int32_t C, float neg_slope, void* stream);
+/* replaces: adv = x + eps*tanh(w); tanh backward; torch.optim.Adam([w]).step()
+ * (attack_utils.py:40,44-46; torch/optim/adam.py _single_tensor_adam).  step is 1-based. */
+int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float* w, float* m,
+                       float* v, float* adv, int64_t n, float eps, int32_t step, void* stream);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+int64_t avc_kernel_launches(const avc_handle* h);   /* kernels launched (graph nodes x replays) */
+int32_t avc_launches_per_iter(const avc_handle* h); /* kernels in the last captured iteration  */
+const char* avc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVC_B200_H_ */

@@ -1,0 +1,352 @@
+"""CPU oracle for the attack-vc adversarial perturbation loop.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch restatement (functional PyTorch, fp32 or fp64) of the one hot
+path this repository accelerates.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product path
+(``attack_vc_b200`` + ``libavc_b200.so``) never does and has no CPU fallback.
+
+Parity pinning: the reference ships no tests, golden vectors or checkpoints (SURVEY.md
+§4, §8c), and its arithmetic lives in PyTorch (third party, version unpinned by the
+reference; torch 2.11.0 here).  The oracle is therefore pinned by EXECUTING the unmodified
+reference in the build container: ``tests/test_oracle_vs_reference.py`` imports
+``/root/reference/models.py`` + ``attack_utils.py`` and asserts equality, and
+``scripts/make_golden.py`` stores reference outputs under ``tests/golden/`` so the same
+check travels to the GPU box where ``/root/reference`` does not exist.
+
+Reference lines followed (``/root/reference``):
+  pad_layer            models.py:10-30      -> _pad_conv
+  pixel_shuffle_1d     models.py:33-49      -> _pixel_shuffle
+  upsample             models.py:52-63      -> nearest ``repeat_interleave``
+  append_cond          models.py:66-79      -> _adain
+  conv_bank            models.py:82-104     -> _bank
+  get_act              models.py:107-118    -> _act
+  ContentEncoder.fwd   models.py:181-210    -> content_encoder
+  SpeakerEncoder.fwd   models.py:285-343    -> speaker_encoder
+  Decoder.fwd          models.py:403-435    -> decoder
+  AdaInVC.inference    models.py:472-485    -> inference
+  emb/e2e/fb_attack    attack_utils.py:7-130 -> run_attack
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+# --------------------------------------------------------------------------------------
+# Synthetic AdaIN-VC hyper-parameters (the reference reads them from an
+# external config.yaml, data_utils.py:219-220, that is not in its tree).
+# --------------------------------------------------------------------------------------
+SYNTH_CONFIG: Dict[str, Dict] = {
+    "SpeakerEncoder": dict(c_in=80, c_h=128, c_out=128, kernel_size=5, bank_size=8, bank_scale=1,
+                           c_bank=128, n_conv_blocks=6, n_dense_blocks=6,
+                           subsample=[1, 2, 1, 2, 1, 2], act="relu", dropout_rate=0.0),
+    "ContentEncoder": dict(c_in=80, c_h=128, c_out=128, kernel_size=5, bank_size=8, bank_scale=1,
+                           c_bank=128, n_conv_blocks=6, subsample=[1, 2, 1, 2, 1, 2],
+                           act="relu", dropout_rate=0.0),
+    "Decoder": dict(c_in=128, c_cond=128, c_h=128, c_out=80, kernel_size=5, n_conv_blocks=6,
+                    upsample=[2, 1, 2, 1, 2, 1], act="relu", sn=False, dropout_rate=0.0),
+}
+
+
+def _encoder_shapes(prefix: str, c: Dict, dense: bool) -> "OrderedDict[str, tuple]":
+    out: "OrderedDict[str, tuple]" = OrderedDict()
+    ks = list(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"]))
+    for i, k in enumerate(ks):
+        out[f"{prefix}conv_bank.{i}.weight"] = (c["c_bank"], c["c_in"], k)
+        out[f"{prefix}conv_bank.{i}.bias"] = (c["c_bank"],)
+    c_cat = c["c_bank"] * len(ks) + c["c_in"]
+    out[f"{prefix}in_conv_layer.weight"] = (c["c_h"], c_cat, 1)
+    out[f"{prefix}in_conv_layer.bias"] = (c["c_h"],)
+    for name in ("first_conv_layers", "second_conv_layers"):
+        for l in range(c["n_conv_blocks"]):
+            out[f"{prefix}{name}.{l}.weight"] = (c["c_h"], c["c_h"], c["kernel_size"])
+            out[f"{prefix}{name}.{l}.bias"] = (c["c_h"],)
+    if dense:
+        for name in ("first_dense_layers", "second_dense_layers"):
+            for l in range(c["n_dense_blocks"]):
+                out[f"{prefix}{name}.{l}.weight"] = (c["c_h"], c["c_h"])
+                out[f"{prefix}{name}.{l}.bias"] = (c["c_h"],)
+        out[f"{prefix}output_layer.weight"] = (c["c_out"], c["c_h"])
+        out[f"{prefix}output_layer.bias"] = (c["c_out"],)
+    else:
+        for name in ("mean_layer", "std_layer"):
+            out[f"{prefix}{name}.weight"] = (c["c_out"], c["c_h"], 1)
+            out[f"{prefix}{name}.bias"] = (c["c_out"],)
+    return out
+
+
+def param_shapes(cfg: Dict = SYNTH_CONFIG) -> "OrderedDict[str, tuple]":
+    """state_dict key -> shape, in the reference's registration order
+    (models.py:159-179 CE, :258-283 SE, :383-401 DEC, :448-452 AdaInVC)."""
+    out: "OrderedDict[str, tuple]" = OrderedDict()
+    out.update(_encoder_shapes("content_encoder.", cfg["ContentEncoder"], dense=False))
+    out.update(_encoder_shapes("speaker_encoder.", cfg["SpeakerEncoder"], dense=True))
+    d = cfg["Decoder"]
+    p = "decoder."
+    out[p + "in_conv_layer.weight"] = (d["c_h"], d["c_in"], 1)
+    out[p + "in_conv_layer.bias"] = (d["c_h"],)
+    for l in range(d["n_conv_blocks"]):
+        out[f"{p}first_conv_layers.{l}.weight"] = (d["c_h"], d["c_h"], d["kernel_size"])
+        out[f"{p}first_conv_layers.{l}.bias"] = (d["c_h"],)
+    for l in range(d["n_conv_blocks"]):
+        out[f"{p}second_conv_layers.{l}.weight"] = (d["c_h"] * d["upsample"][l], d["c_h"], d["kernel_size"])
+        out[f"{p}second_conv_layers.{l}.bias"] = (d["c_h"] * d["upsample"][l],)
+    for l in range(2 * d["n_conv_blocks"]):
+        out[f"{p}conv_affine_layers.{l}.weight"] = (2 * d["c_h"], d["c_cond"])
+        out[f"{p}conv_affine_layers.{l}.bias"] = (2 * d["c_h"],)
+    out[p + "out_conv_layer.weight"] = (d["c_out"], d["c_h"], 1)
+    out[p + "out_conv_layer.bias"] = (d["c_out"],)
+    return out
+
+
+def make_state_dict(cfg: Dict = SYNTH_CONFIG, seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, Tensor]":
+    """Seeded random-init weights: every tensor ~ U(-1/sqrt(fan_in), +1/sqrt(fan_in)), the
+    bound PyTorch's default Conv1d/Linear init uses.  One generator, tensors in
+    ``param_shapes`` order, always drawn in float64 then cast, so fp32 and fp64 copies agree."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000003 * (seed + 1))
+    sd: "OrderedDict[str, Tensor]" = OrderedDict()
+    shapes = param_shapes(cfg)
+    for key, shape in shapes.items():
+        wshape = shapes[key[: -len("bias")] + "weight"] if key.endswith("bias") else shape
+        fan_in = math.prod(wshape[1:])
+        bound = 1.0 / math.sqrt(fan_in)
+        t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2.0 - 1.0) * bound
+        sd[key] = t.to(dtype)
+    return sd
+
+
+def make_inputs(kind: str, B: int, T: int, seed: int = 1, T_src: Optional[int] = None,
+                T_adv: Optional[int] = None, dtype=torch.float32) -> Dict[str, Tensor]:
+    """Synthetic 80-bin log-mel utterances ~N(0,1) and the initial w0 ~N(0,1)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7919 * (seed + 1))
+    T_src = T if T_src is None else T_src
+    T_adv = T if T_adv is None else T_adv
+    d = {
+        "vc_tgt": torch.randn(B, 80, T, generator=g, dtype=torch.float64).to(dtype),
+        "adv_tgt": torch.randn(B, 80, T_adv, generator=g, dtype=torch.float64).to(dtype),
+        "w0": torch.randn(B, 80, T, generator=g, dtype=torch.float64).to(dtype),
+    }
+    if kind != "emb":
+        d["vc_src"] = torch.randn(B, 80, T_src, generator=g, dtype=torch.float64).to(dtype)
+    return d
+
+
+# --------------------------------------------------------------------------------------
+# Functional model (channels-first [B, C, T], exactly the reference's tensor convention)
+# --------------------------------------------------------------------------------------
+def _act(x: Tensor, act: str) -> Tensor:
+    # get_act, models.py:107-118: "lrelu" -> LeakyReLU() (slope 0.01), anything else ReLU.
+    return F.leaky_relu(x, 0.01) if act == "lrelu" else F.relu(x)
+
+
+def _pad_conv(sd, key: str, x: Tensor, stride: int = 1) -> Tensor:
+    # pad_layer, models.py:23-30: reflect pad (k//2, k//2) for odd k, (k//2, k//2-1) for even k.
+    w, b = sd[key + ".weight"], sd[key + ".bias"]
+    k = w.shape[-1]
+    left, right = k // 2, (k // 2 if k % 2 else k // 2 - 1)
+    if left or right:
+        x = F.pad(x, (left, right), mode="reflect")
+    return F.conv1d(x, w, b, stride=stride)
+
+
+def _bank(sd, prefix: str, x: Tensor, n_bank: int, act: str) -> Tensor:
+    # conv_bank, models.py:98-104: [act(conv_k(x)) for k] + [x] concatenated on channels, x LAST.
+    outs = [_act(_pad_conv(sd, f"{prefix}conv_bank.{i}", x), act) for i in range(n_bank)]
+    return torch.cat(outs + [x], dim=1)
+
+
+def _inorm(x: Tensor) -> Tensor:
+    # nn.InstanceNorm1d(affine=False): per (b, c) over time, biased variance, eps=1e-5,
+    # identical in train and eval (no running stats) -- models.py:176,396.
+    # F.instance_norm is the ATen op the reference's module dispatches to.
+    return F.instance_norm(x, eps=1e-5)
+
+
+def _adain(x: Tensor, cond: Tensor) -> Tensor:
+    # append_cond, models.py:76-79: first half of cond = mean, second half = std.
+    p = cond.shape[1] // 2
+    return x * cond[:, p:, None] + cond[:, :p, None]
+
+
+def _pixel_shuffle(x: Tensor, r: int) -> Tensor:
+    # pixel_shuffle_1d, models.py:44-49: out[b, c, r*t + s] = in[b, r*c + s, t].
+    b, c, t = x.shape
+    return x.reshape(b, c // r, r, t).permute(0, 1, 3, 2).reshape(b, c // r, t * r)
+
+
+def _n_bank(c: Dict) -> int:
+    return len(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"]))
+
+
+def speaker_encoder(sd, x: Tensor, cfg: Dict = SYNTH_CONFIG, prefix: str = "speaker_encoder.") -> Tensor:
+    c = cfg["SpeakerEncoder"]
+    act = c["act"]
+    h = _bank(sd, prefix, x, _n_bank(c), act)                       # models.py:336
+    h = _act(_pad_conv(sd, prefix + "in_conv_layer", h), act)        # :337-338
+    for l in range(c["n_conv_blocks"]):                              # :285-305 (no norm in SE)
+        y = _act(_pad_conv(sd, f"{prefix}first_conv_layers.{l}", h), act)
+        y = _act(_pad_conv(sd, f"{prefix}second_conv_layers.{l}", y, stride=c["subsample"][l]), act)
+        if c["subsample"][l] > 1:
+            h = F.avg_pool1d(h, kernel_size=c["subsample"][l], ceil_mode=True)
+        h = y + h
+    v = h.mean(dim=2)                                                # AdaptiveAvgPool1d(1), :340
+    for l in range(c["n_dense_blocks"]):                             # :307-325
+        y = _act(F.linear(v, sd[f"{prefix}first_dense_layers.{l}.weight"], sd[f"{prefix}first_dense_layers.{l}.bias"]), act)
+        y = _act(F.linear(y, sd[f"{prefix}second_dense_layers.{l}.weight"], sd[f"{prefix}second_dense_layers.{l}.bias"]), act)
+        v = y + v
+    return F.linear(v, sd[prefix + "output_layer.weight"], sd[prefix + "output_layer.bias"])  # :342
+
+
+def content_encoder(sd, x: Tensor, cfg: Dict = SYNTH_CONFIG, prefix: str = "content_encoder."):
+    c = cfg["ContentEncoder"]
+    act = c["act"]
+    h = _bank(sd, prefix, x, _n_bank(c), act)                       # models.py:191
+    h = _act(_inorm(_pad_conv(sd, prefix + "in_conv_layer", h)), act)  # :192-194
+    for l in range(c["n_conv_blocks"]):                              # :196-207
+        y = _act(_inorm(_pad_conv(sd, f"{prefix}first_conv_layers.{l}", h)), act)
+        y = _act(_inorm(_pad_conv(sd, f"{prefix}second_conv_layers.{l}", y, stride=c["subsample"][l])), act)
+        if c["subsample"][l] > 1:
+            h = F.avg_pool1d(h, kernel_size=c["subsample"][l], ceil_mode=True)
+        h = y + h
+    return _pad_conv(sd, prefix + "mean_layer", h), _pad_conv(sd, prefix + "std_layer", h)  # :208-209
+
+
+def decoder(sd, z: Tensor, emb: Tensor, cfg: Dict = SYNTH_CONFIG, prefix: str = "decoder.") -> Tensor:
+    c = cfg["Decoder"]
+    act = c["act"]
+    h = _act(_inorm(_pad_conv(sd, prefix + "in_conv_layer", z)), act)  # models.py:413-415
+    for l in range(c["n_conv_blocks"]):                                # :417-432
+        a0 = F.linear(emb, sd[f"{prefix}conv_affine_layers.{2 * l}.weight"], sd[f"{prefix}conv_affine_layers.{2 * l}.bias"])
+        a1 = F.linear(emb, sd[f"{prefix}conv_affine_layers.{2 * l + 1}.weight"], sd[f"{prefix}conv_affine_layers.{2 * l + 1}.bias"])
+        y = _act(_adain(_inorm(_pad_conv(sd, f"{prefix}first_conv_layers.{l}", h)), a0), act)
+        y = _pad_conv(sd, f"{prefix}second_conv_layers.{l}", y)
+        up = c["upsample"][l]
+        if up > 1:
+            y = _pixel_shuffle(y, up)                                   # shuffle BEFORE the norm, :423-426
+        y = _act(_adain(_inorm(y), a1), act)
+        h = y + (h.repeat_interleave(up, dim=2) if up > 1 else h)      # nearest upsample, :430-431
+    return _pad_conv(sd, prefix + "out_conv_layer", h)                  # :434
+
+
+def inference(sd, src: Tensor, tgt: Tensor, cfg: Dict = SYNTH_CONFIG) -> Tensor:
+    mu, _ = content_encoder(sd, src, cfg)        # models.py:482 (mu only, no sampling)
+    emb = speaker_encoder(sd, tgt, cfg)          # :483
+    return decoder(sd, mu, emb, cfg)             # :484
+
+
+# --------------------------------------------------------------------------------------
+# nn.Module facade with the reference's state_dict keys and attribute names, so the
+# drop-in ``attack_utils`` API can be driven without /root/reference (GPU box).
+# --------------------------------------------------------------------------------------
+class _Node(nn.Module):
+    pass
+
+
+class _SubNet(_Node):
+    def __init__(self, owner: "OracleAdaInVC", which: str):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        self._which = which
+
+    def forward(self, *args):
+        own = self._owner
+        sd = own.live_state()
+        if self._which == "speaker_encoder":
+            return speaker_encoder(sd, args[0], own.cfg)
+        if self._which == "content_encoder":
+            return content_encoder(sd, args[0], own.cfg)
+        return decoder(sd, args[0], args[1], own.cfg)
+
+
+class OracleAdaInVC(nn.Module):
+    """Same public surface as the reference's ``AdaInVC`` (models.py:438-485): attributes
+    ``content_encoder`` / ``speaker_encoder`` / ``decoder`` (callables), ``inference``, and a
+    ``state_dict()`` with identical keys and shapes.  Parameters keep requires_grad=True and
+    the module stays in train mode, as ``load_model`` leaves the reference (data_utils.py:220-221)."""
+
+    def __init__(self, cfg: Dict = SYNTH_CONFIG, seed: int = 0, dtype=torch.float32,
+                 state: Optional[Dict[str, Tensor]] = None):
+        super().__init__()
+        self.cfg = cfg
+        state = make_state_dict(cfg, seed, dtype) if state is None else state
+        self.content_encoder = _SubNet(self, "content_encoder")
+        self.speaker_encoder = _SubNet(self, "speaker_encoder")
+        self.decoder = _SubNet(self, "decoder")
+        for which, key in (("content_encoder", "ContentEncoder"), ("speaker_encoder", "SpeakerEncoder"),
+                           ("decoder", "Decoder")):
+            sub = getattr(self, which)
+            for k, v in cfg[key].items():       # c_in, subsample, upsample, ... like the reference attrs
+                setattr(sub, k, v)
+            sub.act_name = cfg[key]["act"]
+            sub.dropout_layer = nn.Dropout(p=cfg[key]["dropout_rate"])
+        for key, value in state.items():
+            parts = key.split(".")
+            node: nn.Module = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            node.register_parameter(parts[-1], nn.Parameter(value.clone()))
+        self._keys = list(state.keys())
+
+    def live_state(self) -> Dict[str, Tensor]:
+        params = dict(self.named_parameters())
+        return {k: params[k] for k in self._keys}
+
+    def inference(self, src: Tensor, tgt: Tensor) -> Tensor:
+        return inference(self.live_state(), src, tgt, self.cfg)
+
+
+# --------------------------------------------------------------------------------------
+# Attack loops (attack_utils.py:7-130), instrumented: take w0, record loss and w.grad.
+# ``model`` is anything with .speaker_encoder(x) and .inference(src, tgt): the reference's
+# AdaInVC or OracleAdaInVC.  Structure mirrors the reference: Adam([w]) defaults, MSELoss
+# (mean over ALL elements), targets under no_grad, loss = mse(out,tgt) - 0.1*mse(out,org).
+# With a model whose params require grad this also does the reference's unread wgrad work
+# and recomputes the loop-invariant content encoder every iteration, so timing it is a
+# faithful CPU baseline.
+# --------------------------------------------------------------------------------------
+def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_iters: int,
+               w0: Tensor, vc_src: Optional[Tensor] = None, record_grads: Iterable[int] = (),
+               progress=None) -> Dict[str, object]:
+    if kind not in ("emb", "e2e", "fb"):
+        raise NotImplementedError(kind)
+    record = set(record_grads)
+    w = w0.detach().clone().requires_grad_(True)              # attack_utils.py:30,68,112 (w0 injected)
+    opt = torch.optim.Adam([w])                               # :31,69,113  lr 1e-3, betas (.9,.999), eps 1e-8
+    mse = nn.MSELoss()                                        # :32,70,114
+
+    def fwd(x: Tensor) -> Tensor:
+        if kind == "emb":
+            return model.speaker_encoder(x)                   # :79
+        if kind == "e2e":
+            return model.inference(vc_src, x)                 # :41
+        return model.speaker_encoder(model.inference(vc_src, x))  # :123
+
+    with torch.no_grad():                                     # :35-37, 73-75, 117-119
+        org = fwd(vc_tgt)
+        tgt = model.speaker_encoder(adv_tgt) if kind in ("emb", "fb") else model.inference(vc_src, adv_tgt)
+
+    losses: List[float] = []
+    grads: Dict[int, Tensor] = {}
+    it = range(n_iters) if progress is None else progress(range(n_iters))
+    for i in it:
+        adv = vc_tgt + eps * w.tanh()                         # :40,78,122
+        out = fwd(adv)
+        loss = mse(out, tgt) - 0.1 * mse(out, org)            # :43,81,125
+        opt.zero_grad()
+        loss.backward()
+        if i in record:
+            grads[i] = w.grad.detach().clone()
+        losses.append(float(loss.detach()))
+        opt.step()
+    with torch.no_grad():
+        final = vc_tgt + eps * w.tanh()                       # :48,86,130
+    return {"adv": final.detach(), "w": w.detach().clone(), "losses": torch.tensor(losses, dtype=torch.float64),
+            "grads": grads, "org": org.detach(), "tgt": tgt.detach()}

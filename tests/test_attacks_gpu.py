@@ -1,0 +1,155 @@
+"""Loop parity of the three attacks (BASELINE.json north_star): per-iteration loss and gradient
+within 1e-3 relative of the reference, final speaker-embedding cosine >= 0.999, perturbation bound
+exact.  References: the committed golden vectors (reference run) and the oracle run on the host."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3            # north_star tolerance (loss and gradient, relative)
+GOLDEN_CASES = ["emb_T128_it100", "e2e_T64_it20", "fb_T64_it20", "emb_B2_ragged_cli", "e2e_B2_ragged", "fb_B2_ragged"]
+
+
+def cuda(g, k, cli=False):
+    t = torch.from_numpy(g[k]).cuda()
+    if cli:
+        t = t.transpose(1, 2).contiguous().transpose(1, 2)
+    return t
+
+
+def grad_rel(a, b):
+    a, b = a.double().cpu(), torch.as_tensor(b).double()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_attack_vs_golden(engine, golden, name):
+    g = golden(name)
+    kind = name.split("_")[0]
+    cli = name.endswith("cli")
+    n = int(g["n_iters"])
+    eps = float(g["eps"])
+    src = cuda(g, "vc_src", cli) if "vc_src" in g else None
+    x, at, w0 = cuda(g, "vc_tgt", cli), cuda(g, "adv_tgt", cli), cuda(g, "w0", cli)
+    adv, info = engine.attack(kind, x, at, eps, n, vc_src=src, w0=w0, want_loss=True, want_grad=True)
+    losses = info["losses"].cpu().double().numpy()
+    np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
+    # gradient of the last iteration, then of the earlier recorded ones (re-run with fewer iterations)
+    for key in [k for k in g if k.startswith("grad_")]:
+        i = int(key.split("_")[1])
+        if i == n - 1:
+            gi = info["grad"]
+        else:
+            _, inf2 = engine.attack(kind, x, at, eps, i + 1, vc_src=src, w0=w0, want_grad=True)
+            gi = inf2["grad"]
+        assert grad_rel(gi, g[key]) < RTOL, (key, grad_rel(gi, g[key]))
+    # result: same layout as the input, bound respected, close to the reference's result
+    assert adv.shape == x.shape and adv.stride() == x.stride()
+    ptb = (adv - x).abs().max().item()
+    assert ptb <= eps * (1 + 1e-6)
+    assert float((adv.cpu() - torch.from_numpy(g["adv"])).abs().max()) < 5e-5
+    emb = engine.speaker_encoder(adv).cpu().double()
+    ref = torch.from_numpy(g["emb_final"]).double()
+    cos = torch.nn.functional.cosine_similarity(emb, ref, dim=1)
+    assert float(cos.min()) >= 0.999
+
+
+@pytest.mark.parametrize("kind,B,T,T_src,T_adv,n", [
+    ("emb", 3, 256, None, 200, 8), ("e2e", 2, 128, 100, 128, 5), ("fb", 2, 96, 72, 64, 5), ("emb", 1, 17, None, 19, 3)])
+def test_attack_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, T_src, T_adv, n):
+    inp = oracle.make_inputs(kind, B, T, seed=21, T_src=T_src, T_adv=T_adv)
+    o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=inp.get("vc_src"),
+                          record_grads=[n - 1])
+    adv, info = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, n,
+                              vc_src=inp["vc_src"].cuda() if "vc_src" in inp else None, w0=inp["w0"].cuda(),
+                              want_loss=True, want_grad=True)
+    np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL)
+    assert grad_rel(info["grad"], o["grads"][n - 1]) < RTOL
+    assert float((adv.cpu() - o["adv"]).abs().max()) < 5e-5
+
+
+def test_graph_and_eager_agree(engine, oracle):
+    inp = oracle.make_inputs("e2e", 1, 64, seed=8)
+    args = (inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, 6)
+    kw = dict(vc_src=inp["vc_src"].cuda(), w0=inp["w0"].cuda())
+    a = engine.attack("e2e", *args, use_graph=True, **kw)
+    b = engine.attack("e2e", *args, use_graph=False, **kw)
+    assert torch.equal(a, b)
+
+
+def test_batch_sharding_invariance(engine, oracle):
+    """A batch split into shards with the GLOBAL MSE normaliser equals the unsharded call
+    (Adam is not scale invariant at these gradient magnitudes)."""
+    inp = oracle.make_inputs("emb", 4, 128, seed=31)
+    x, at, w0 = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), inp["w0"].cuda()
+    full = engine.attack("emb", x, at, 0.1, 10, w0=w0)
+    inv = 1.0 / (4 * 128)
+    parts = [engine.attack("emb", x[i:i + 2], at[i:i + 2], 0.1, 10, w0=w0[i:i + 2], inv_norm=inv) for i in (0, 2)]
+    assert torch.allclose(torch.cat(parts), full, rtol=0, atol=1e-7)
+    wrong = engine.attack("emb", x[:2], at[:2], 0.1, 10, w0=w0[:2])      # local normaliser: differs
+    assert not torch.allclose(wrong, full[:2], rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind,B,T,n", [("e2e", 1, 256, 20), ("fb", 8, 256, 3), ("emb", 32, 512, 3)])
+def test_full_size_properties(engine, oracle, kind, B, T, n):
+    """BASELINE.json sizes: properties that do not need the oracle (bound, determinism, finite,
+    loss of iteration 0 equals the loss computed from forward-only entry points)."""
+    inp = oracle.make_inputs(kind, B, T, seed=41)
+    x, at, w0 = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), inp["w0"].cuda()
+    src = inp["vc_src"].cuda() if "vc_src" in inp else None
+    a1, info = engine.attack(kind, x, at, 0.1, n, vc_src=src, w0=w0, want_loss=True)
+    a2 = engine.attack(kind, x, at, 0.1, n, vc_src=src, w0=w0)
+    assert torch.equal(a1, a2)                                   # deterministic: no float atomics
+    assert torch.isfinite(a1).all() and torch.isfinite(info["losses"]).all()
+    assert float((a1 - x).abs().max()) <= 0.1 * (1 + 1e-6)
+    adv0 = x + 0.1 * torch.tanh(w0)
+    if kind == "emb":
+        f = engine.speaker_encoder
+        e, t, o = f(adv0), f(at), f(x)
+    elif kind == "e2e":
+        e, t, o = engine.inference(src, adv0), engine.inference(src, at), engine.inference(src, x)
+    else:
+        f = engine.speaker_encoder
+        e, t, o = f(engine.inference(src, adv0)), f(at), f(engine.inference(src, x))
+    loss0 = ((e - t) ** 2).mean() - 0.1 * ((e - o) ** 2).mean()
+    assert abs(float(loss0) - float(info["losses"][0])) <= 1e-4 * abs(float(loss0))
+
+
+def test_dropin_module_signatures(gpu_model, oracle):
+    """attack_utils.{emb,e2e,fb}_attack keep the reference signatures and RNG consumption."""
+    import inspect
+
+    import attack_utils as AU
+    assert list(inspect.signature(AU.emb_attack).parameters) == ["model", "vc_tgt", "adv_tgt", "eps", "n_iters"]
+    assert list(inspect.signature(AU.e2e_attack).parameters) == ["model", "vc_src", "vc_tgt", "adv_tgt", "eps", "n_iters"]
+    assert list(inspect.signature(AU.fb_attack).parameters) == ["model", "vc_src", "vc_tgt", "adv_tgt", "eps", "n_iters"]
+    inp = oracle.make_inputs("fb", 1, 64, seed=2)
+    x, at, src = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), inp["vc_src"].cuda()
+    torch.manual_seed(3)
+    a = AU.emb_attack(gpu_model, x, at, 0.1, 3)
+    torch.manual_seed(3)
+    w0 = torch.zeros_like(x).normal_(0, 1)       # the one draw the reference makes
+    from attack_vc_b200 import engine_for
+    b = engine_for(gpu_model).attack("emb", x, at, 0.1, 3, w0=w0)
+    assert torch.equal(a, b)
+    assert AU.e2e_attack(gpu_model, src, x, at, 0.1, 2).shape == x.shape
+    assert AU.fb_attack(gpu_model, src, x, at, 0.1, 2).shape == x.shape
+
+
+def test_session_matches_one_shot(engine, oracle):
+    """avc_attack_begin/step/end in chunks == the one-shot call; profile() consumes one iteration."""
+    inp = oracle.make_inputs("fb", 1, 64, seed=9)
+    x, at, src, w0 = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), inp["vc_src"].cuda(), inp["w0"].cuda()
+    ref, rinfo = engine.attack("fb", x, at, 0.1, 7, vc_src=src, w0=w0, want_loss=True)
+    s = engine.begin("fb", x, at, 0.1, 7, vc_src=src, w0=w0, want_loss=True)
+    assert s.launches_per_iter > 10
+    s.step(3)
+    prof = s.profile()
+    assert len(prof) == s.launches_per_iter and all(ms >= 0 for _, ms, _, _ in prof)
+    s.step(3)
+    with pytest.raises(ValueError):
+        s.step(1)                      # only 7 iterations were provisioned
+    out, info = s.end()
+    assert torch.equal(out, ref)
+    assert torch.equal(info["losses"], rinfo["losses"])

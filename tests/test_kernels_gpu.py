@@ -1,0 +1,129 @@
+"""Per-kernel parity through the C-ABI unit-test entry points, against PyTorch ops evaluated in
+fp64 on the same GPU (kernels are fp32: tolerance 2e-5 relative to the output scale)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def ref_conv(x_tl, w, b, stride):
+    k = w.shape[-1]
+    pl, pr = k // 2, (k // 2 if k % 2 else k // 2 - 1)
+    x = x_tl.transpose(1, 2)
+    if pl or pr:
+        x = F.pad(x, (pl, pr), mode="reflect")
+    return F.conv1d(x, w, b, stride=stride).transpose(1, 2)
+
+
+CONV_CASES = [
+    # B, T, c_in, c_out, k, stride
+    (1, 256, 128, 128, 5, 1),
+    (1, 256, 128, 128, 5, 2),
+    (2, 131, 128, 128, 5, 2),      # odd T, ceil-mode output length
+    (1, 64, 1104, 128, 1, 1),      # in-conv over the bank concat
+    (1, 32, 128, 256, 5, 1),       # decoder second conv (up=2)
+    (3, 77, 128, 80, 1, 1),        # decoder out-conv, N=80
+    (1, 5, 128, 128, 5, 1),        # shortest legal T for pad 2... (T > pad)
+    (2, 3, 128, 128, 5, 1),
+    (2, 300, 128, 128, 5, 1),      # several time tiles
+    (1, 40, 128, 128, 5, 3),       # stride 3
+] + [(2, 50, 80, 128, k, 1) for k in range(1, 9)]   # conv bank, even kernels pad asymmetrically
+
+
+@pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES)
+def test_conv1d_fwd(engine, B, T, ci, co, k, s):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k)
+    x = torch.randn(B, T, ci, device="cuda", generator=g)
+    w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
+    b = torch.randn(co, device="cuda", generator=g)
+    y = engine.conv1d_fwd(x, w, b, stride=s, impl=1)
+    ref = ref_conv(x.double(), w.double(), b.double(), s)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES)
+def test_conv1d_dgrad(engine, B, T, ci, co, k, s):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 7)
+    x = torch.randn(B, T, ci, device="cuda", generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
+    y = ref_conv(x, w.double(), None, s)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    (dx_ref,) = torch.autograd.grad(y, x, dy.double())
+    dx = engine.conv1d_dgrad(dy, w, T, stride=s, impl=1)
+    assert dx.shape == dx_ref.shape
+    assert rel_err(dx, dx_ref) < 2e-6
+
+
+def ref_norm(y, cond, res, up, slope):
+    x = F.instance_norm(y.transpose(1, 2), eps=1e-5)
+    if cond is not None:
+        C = y.shape[2]
+        x = x * cond[:, C:, None] + cond[:, :C, None]
+    x = F.leaky_relu(x, slope) if slope else F.relu(x)
+    if res is not None:
+        r = res.transpose(1, 2)
+        x = x + (r.repeat_interleave(up, dim=2) if up > 1 else r)
+    return x.transpose(1, 2)
+
+
+@pytest.mark.parametrize("B,T,up,with_cond,with_res,slope", [
+    (1, 256, 1, True, True, 0.0), (2, 64, 2, True, True, 0.0), (3, 33, 1, False, False, 0.0),
+    (2, 100, 2, True, True, 0.01), (1, 7, 1, True, False, 0.0), (4, 512, 1, True, True, 0.0)])
+def test_instnorm_adain_act(engine, B, T, up, with_cond, with_res, slope):
+    C = 128
+    g = torch.Generator(device="cuda").manual_seed(T * 10 + up)
+    y = torch.randn(B, T, C, device="cuda", generator=g) * 2 + 0.5
+    cond = torch.randn(B, 2 * C, device="cuda", generator=g) if with_cond else None
+    res = torch.randn(B, T // up, C, device="cuda", generator=g) if with_res else None
+    if with_res and T % up:
+        pytest.skip("T not a multiple of up")
+    out, stats = engine.instnorm_adain_act_fwd(y, cond, res, up, slope)
+    yd = y.double().requires_grad_(True)
+    cd = cond.double().requires_grad_(True) if with_cond else None
+    ref = ref_norm(yd, cd, res.double() if with_res else None, up, slope)
+    assert rel_err(out, ref) < 5e-6
+    mu = y.double().mean(1)
+    rstd = 1 / torch.sqrt(y.double().var(1, unbiased=False) + 1e-5)
+    assert rel_err(stats[..., 0], mu) < 5e-6 and rel_err(stats[..., 1], rstd) < 5e-6
+    # backward
+    gup = torch.randn(B, T, C, device="cuda", generator=g)
+    grads = torch.autograd.grad(ref, [yd] + ([cd] if with_cond else []), gup.double())
+    gy, gcond = engine.instnorm_adain_act_bwd(gup, y, stats, cond, slope)
+    assert rel_err(gy, grads[0]) < 2e-5
+    if with_cond:
+        assert rel_err(gcond, grads[1]) < 2e-5
+
+
+@pytest.mark.parametrize("step", [1, 2, 10, 1500])
+def test_adam_tanh_step_matches_torch_adam(engine, step):
+    """One fused update == autograd through x + eps*tanh(w) + torch.optim.Adam.step on CPU fp32."""
+    n = 80 * 128
+    g = torch.Generator().manual_seed(step)
+    x = torch.randn(n, generator=g)
+    w = torch.randn(n, generator=g)
+    m = torch.randn(n, generator=g) * 1e-8
+    v = torch.rand(n, generator=g) * 1e-16
+    g_adv = torch.randn(n, generator=g) * 3e-8       # same order as Adam's eps (SURVEY §5 hazard)
+    eps = 0.1
+    wp = w.clone().requires_grad_(True)
+    opt = torch.optim.Adam([wp])
+    adv = x + eps * wp.tanh()
+    adv.backward(g_adv)
+    opt.state[wp] = {"step": torch.tensor(float(step - 1)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+    opt.step()
+    ref_adv = (x + eps * wp.detach().tanh())
+    wd, md, vd = w.cuda(), m.cuda(), v.cuda()
+    adv_d = engine.adam_tanh_step(g_adv.cuda(), x.cuda(), wd, md, vd, eps, step)
+    st = opt.state[wp]
+    assert torch.allclose(wd.cpu(), wp.detach(), rtol=0, atol=2e-7)
+    assert torch.allclose(md.cpu(), st["exp_avg"], rtol=1e-6, atol=1e-20)
+    assert torch.allclose(vd.cpu(), st["exp_avg_sq"], rtol=1e-6, atol=1e-30)
+    assert torch.allclose(adv_d.cpu(), ref_adv, rtol=0, atol=2e-7)
+    # the bound is exact on the perturbation term
+    assert float((eps * wd.tanh()).abs().max()) <= eps

@@ -1,0 +1,62 @@
+"""Oracle == unmodified reference, executed here (build container only; skipped on the GPU box)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import REFERENCE
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref_model(oracle):
+    sys.path.insert(0, REFERENCE)
+    try:
+        import models as RM
+    finally:
+        sys.path.remove(REFERENCE)
+    m = RM.AdaInVC(oracle.SYNTH_CONFIG)
+    m.load_state_dict(oracle.make_state_dict(seed=0), strict=True)   # same keys + shapes as the reference
+    return m
+
+
+def test_state_dict_keys_match_reference(oracle, ref_model, cpu_model):
+    assert list(ref_model.state_dict().keys()) == list(cpu_model.state_dict().keys())
+    for (k, a), (_, b) in zip(ref_model.state_dict().items(), cpu_model.state_dict().items()):
+        assert a.shape == b.shape, k
+        assert torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("B,T,T_src", [(1, 128, 128), (3, 75, 43)])
+def test_forward_bit_exact(oracle, ref_model, cpu_model, B, T, T_src):
+    inp = oracle.make_inputs("e2e", B, T, seed=5, T_src=T_src)
+    with torch.no_grad():
+        assert torch.equal(ref_model.speaker_encoder(inp["vc_tgt"]), cpu_model.speaker_encoder(inp["vc_tgt"]))
+        mu_r, ls_r = ref_model.content_encoder(inp["vc_src"])
+        mu_o, ls_o = cpu_model.content_encoder(inp["vc_src"])
+        assert torch.equal(mu_r, mu_o) and torch.equal(ls_r, ls_o)
+        assert torch.equal(ref_model.inference(inp["vc_src"], inp["vc_tgt"]), cpu_model.inference(inp["vc_src"], inp["vc_tgt"]))
+
+
+@pytest.mark.parametrize("kind", ["emb", "e2e", "fb"])
+def test_attack_loop_bit_exact(oracle, ref_model, cpu_model, kind):
+    sys.path.insert(0, REFERENCE)
+    try:
+        import attack_utils as RA
+    finally:
+        sys.path.remove(REFERENCE)
+    inp = oracle.make_inputs(kind, 1, 48, seed=2)
+    torch.manual_seed(77)
+    w0 = torch.zeros_like(inp["vc_tgt"]).normal_(0, 1)
+    torch.manual_seed(77)
+    n = 4
+    if kind == "emb":
+        r = RA.emb_attack(ref_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n)
+    elif kind == "e2e":
+        r = RA.e2e_attack(ref_model, inp["vc_src"], inp["vc_tgt"], inp["adv_tgt"], 0.1, n)
+    else:
+        r = RA.fb_attack(ref_model, inp["vc_src"], inp["vc_tgt"], inp["adv_tgt"], 0.1, n)
+    o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, w0, vc_src=inp.get("vc_src"))
+    assert torch.equal(r.detach(), o["adv"])
