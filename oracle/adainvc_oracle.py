@@ -28,114 +28,14 @@ Reference lines followed (``/root/reference``):
 """
 from __future__ import annotations
 
-import math
-from collections import OrderedDict
 from typing import Dict, Iterable, List, Optional
 
 import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-# --------------------------------------------------------------------------------------
-# Synthetic AdaIN-VC hyper-parameters (the reference reads them from an
-# external config.yaml, data_utils.py:219-220, that is not in its tree).
-# --------------------------------------------------------------------------------------
-SYNTH_CONFIG: Dict[str, Dict] = {
-    "SpeakerEncoder": dict(c_in=80, c_h=128, c_out=128, kernel_size=5, bank_size=8, bank_scale=1,
-                           c_bank=128, n_conv_blocks=6, n_dense_blocks=6,
-                           subsample=[1, 2, 1, 2, 1, 2], act="relu", dropout_rate=0.0),
-    "ContentEncoder": dict(c_in=80, c_h=128, c_out=128, kernel_size=5, bank_size=8, bank_scale=1,
-                           c_bank=128, n_conv_blocks=6, subsample=[1, 2, 1, 2, 1, 2],
-                           act="relu", dropout_rate=0.0),
-    "Decoder": dict(c_in=128, c_cond=128, c_h=128, c_out=80, kernel_size=5, n_conv_blocks=6,
-                    upsample=[2, 1, 2, 1, 2, 1], act="relu", sn=False, dropout_rate=0.0),
-}
-
-
-def _encoder_shapes(prefix: str, c: Dict, dense: bool) -> "OrderedDict[str, tuple]":
-    out: "OrderedDict[str, tuple]" = OrderedDict()
-    ks = list(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"]))
-    for i, k in enumerate(ks):
-        out[f"{prefix}conv_bank.{i}.weight"] = (c["c_bank"], c["c_in"], k)
-        out[f"{prefix}conv_bank.{i}.bias"] = (c["c_bank"],)
-    c_cat = c["c_bank"] * len(ks) + c["c_in"]
-    out[f"{prefix}in_conv_layer.weight"] = (c["c_h"], c_cat, 1)
-    out[f"{prefix}in_conv_layer.bias"] = (c["c_h"],)
-    for name in ("first_conv_layers", "second_conv_layers"):
-        for l in range(c["n_conv_blocks"]):
-            out[f"{prefix}{name}.{l}.weight"] = (c["c_h"], c["c_h"], c["kernel_size"])
-            out[f"{prefix}{name}.{l}.bias"] = (c["c_h"],)
-    if dense:
-        for name in ("first_dense_layers", "second_dense_layers"):
-            for l in range(c["n_dense_blocks"]):
-                out[f"{prefix}{name}.{l}.weight"] = (c["c_h"], c["c_h"])
-                out[f"{prefix}{name}.{l}.bias"] = (c["c_h"],)
-        out[f"{prefix}output_layer.weight"] = (c["c_out"], c["c_h"])
-        out[f"{prefix}output_layer.bias"] = (c["c_out"],)
-    else:
-        for name in ("mean_layer", "std_layer"):
-            out[f"{prefix}{name}.weight"] = (c["c_out"], c["c_h"], 1)
-            out[f"{prefix}{name}.bias"] = (c["c_out"],)
-    return out
-
-
-def param_shapes(cfg: Dict = SYNTH_CONFIG) -> "OrderedDict[str, tuple]":
-    """state_dict key -> shape, in the reference's registration order
-    (models.py:159-179 CE, :258-283 SE, :383-401 DEC, :448-452 AdaInVC)."""
-    out: "OrderedDict[str, tuple]" = OrderedDict()
-    out.update(_encoder_shapes("content_encoder.", cfg["ContentEncoder"], dense=False))
-    out.update(_encoder_shapes("speaker_encoder.", cfg["SpeakerEncoder"], dense=True))
-    d = cfg["Decoder"]
-    p = "decoder."
-    out[p + "in_conv_layer.weight"] = (d["c_h"], d["c_in"], 1)
-    out[p + "in_conv_layer.bias"] = (d["c_h"],)
-    for l in range(d["n_conv_blocks"]):
-        out[f"{p}first_conv_layers.{l}.weight"] = (d["c_h"], d["c_h"], d["kernel_size"])
-        out[f"{p}first_conv_layers.{l}.bias"] = (d["c_h"],)
-    for l in range(d["n_conv_blocks"]):
-        out[f"{p}second_conv_layers.{l}.weight"] = (d["c_h"] * d["upsample"][l], d["c_h"], d["kernel_size"])
-        out[f"{p}second_conv_layers.{l}.bias"] = (d["c_h"] * d["upsample"][l],)
-    for l in range(2 * d["n_conv_blocks"]):
-        out[f"{p}conv_affine_layers.{l}.weight"] = (2 * d["c_h"], d["c_cond"])
-        out[f"{p}conv_affine_layers.{l}.bias"] = (2 * d["c_h"],)
-    out[p + "out_conv_layer.weight"] = (d["c_out"], d["c_h"], 1)
-    out[p + "out_conv_layer.bias"] = (d["c_out"],)
-    return out
-
-
-def make_state_dict(cfg: Dict = SYNTH_CONFIG, seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, Tensor]":
-    """Seeded random-init weights: every tensor ~ U(-1/sqrt(fan_in), +1/sqrt(fan_in)), the
-    bound PyTorch's default Conv1d/Linear init uses.  One generator, tensors in
-    ``param_shapes`` order, always drawn in float64 then cast, so fp32 and fp64 copies agree."""
-    g = torch.Generator(device="cpu")
-    g.manual_seed(1000003 * (seed + 1))
-    sd: "OrderedDict[str, Tensor]" = OrderedDict()
-    shapes = param_shapes(cfg)
-    for key, shape in shapes.items():
-        wshape = shapes[key[: -len("bias")] + "weight"] if key.endswith("bias") else shape
-        fan_in = math.prod(wshape[1:])
-        bound = 1.0 / math.sqrt(fan_in)
-        t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2.0 - 1.0) * bound
-        sd[key] = t.to(dtype)
-    return sd
-
-
-def make_inputs(kind: str, B: int, T: int, seed: int = 1, T_src: Optional[int] = None,
-                T_adv: Optional[int] = None, dtype=torch.float32) -> Dict[str, Tensor]:
-    """Synthetic 80-bin log-mel utterances ~N(0,1) and the initial w0 ~N(0,1)."""
-    g = torch.Generator(device="cpu")
-    g.manual_seed(7919 * (seed + 1))
-    T_src = T if T_src is None else T_src
-    T_adv = T if T_adv is None else T_adv
-    d = {
-        "vc_tgt": torch.randn(B, 80, T, generator=g, dtype=torch.float64).to(dtype),
-        "adv_tgt": torch.randn(B, 80, T_adv, generator=g, dtype=torch.float64).to(dtype),
-        "w0": torch.randn(B, 80, T, generator=g, dtype=torch.float64).to(dtype),
-    }
-    if kind != "emb":
-        d["vc_src"] = torch.randn(B, 80, T_src, generator=g, dtype=torch.float64).to(dtype)
-    return d
-
+from attack_vc_b200.synthetic import (SYNTH_CONFIG, ParamTree, make_inputs, make_state_dict,  # noqa: F401,E402
+                                      param_shapes)
 
 # --------------------------------------------------------------------------------------
 # Functional model (channels-first [B, C, T], exactly the reference's tensor convention)
@@ -244,11 +144,7 @@ def inference(sd, src: Tensor, tgt: Tensor, cfg: Dict = SYNTH_CONFIG) -> Tensor:
 # nn.Module facade with the reference's state_dict keys and attribute names, so the
 # drop-in ``attack_utils`` API can be driven without /root/reference (GPU box).
 # --------------------------------------------------------------------------------------
-class _Node(nn.Module):
-    pass
-
-
-class _SubNet(_Node):
+class _SubNet(nn.Module):
     def __init__(self, owner: "OracleAdaInVC", which: str):
         super().__init__()
         object.__setattr__(self, "_owner", owner)
@@ -264,7 +160,7 @@ class _SubNet(_Node):
         return decoder(sd, args[0], args[1], own.cfg)
 
 
-class OracleAdaInVC(nn.Module):
+class OracleAdaInVC(ParamTree):
     """Same public surface as the reference's ``AdaInVC`` (models.py:438-485): attributes
     ``content_encoder`` / ``speaker_encoder`` / ``decoder`` (callables), ``inference``, and a
     ``state_dict()`` with identical keys and shapes.  Parameters keep requires_grad=True and
@@ -272,28 +168,7 @@ class OracleAdaInVC(nn.Module):
 
     def __init__(self, cfg: Dict = SYNTH_CONFIG, seed: int = 0, dtype=torch.float32,
                  state: Optional[Dict[str, Tensor]] = None):
-        super().__init__()
-        self.cfg = cfg
-        state = make_state_dict(cfg, seed, dtype) if state is None else state
-        self.content_encoder = _SubNet(self, "content_encoder")
-        self.speaker_encoder = _SubNet(self, "speaker_encoder")
-        self.decoder = _SubNet(self, "decoder")
-        for which, key in (("content_encoder", "ContentEncoder"), ("speaker_encoder", "SpeakerEncoder"),
-                           ("decoder", "Decoder")):
-            sub = getattr(self, which)
-            for k, v in cfg[key].items():       # c_in, subsample, upsample, ... like the reference attrs
-                setattr(sub, k, v)
-            sub.act_name = cfg[key]["act"]
-            sub.dropout_layer = nn.Dropout(p=cfg[key]["dropout_rate"])
-        for key, value in state.items():
-            parts = key.split(".")
-            node: nn.Module = self
-            for p in parts[:-1]:
-                if p not in node._modules:
-                    node.add_module(p, _Node())
-                node = node._modules[p]
-            node.register_parameter(parts[-1], nn.Parameter(value.clone()))
-        self._keys = list(state.keys())
+        super().__init__(cfg, seed, dtype, state, subnet=lambda which: _SubNet(self, which))
 
     def live_state(self) -> Dict[str, Tensor]:
         params = dict(self.named_parameters())
@@ -314,7 +189,7 @@ class OracleAdaInVC(nn.Module):
 # --------------------------------------------------------------------------------------
 def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_iters: int,
                w0: Tensor, vc_src: Optional[Tensor] = None, record_grads: Iterable[int] = (),
-               progress=None) -> Dict[str, object]:
+               progress=None, record_w: bool = False) -> Dict[str, object]:
     if kind not in ("emb", "e2e", "fb"):
         raise NotImplementedError(kind)
     record = set(record_grads)
@@ -335,6 +210,7 @@ def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_
 
     losses: List[float] = []
     grads: Dict[int, Tensor] = {}
+    ws: Dict[int, Tensor] = {}
     it = range(n_iters) if progress is None else progress(range(n_iters))
     for i in it:
         adv = vc_tgt + eps * w.tanh()                         # :40,78,122
@@ -344,9 +220,11 @@ def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_
         loss.backward()
         if i in record:
             grads[i] = w.grad.detach().clone()
+            if record_w:
+                ws[i] = w.detach().clone()      # w BEFORE this iteration's Adam step (teacher forcing)
         losses.append(float(loss.detach()))
         opt.step()
     with torch.no_grad():
         final = vc_tgt + eps * w.tanh()                       # :48,86,130
     return {"adv": final.detach(), "w": w.detach().clone(), "losses": torch.tensor(losses, dtype=torch.float64),
-            "grads": grads, "org": org.detach(), "tgt": tgt.detach()}
+            "grads": grads, "ws": ws, "org": org.detach(), "tgt": tgt.detach()}

@@ -35,15 +35,17 @@ def test_attack_vs_golden(engine, golden, name):
     adv, info = engine.attack(kind, x, at, eps, n, vc_src=src, w0=w0, want_loss=True, want_grad=True)
     losses = info["losses"].cpu().double().numpy()
     np.testing.assert_allclose(losses, g["losses"], rtol=RTOL)
-    # gradient of the last iteration, then of the earlier recorded ones (re-run with fewer iterations)
+    # Gradient parity is teacher-forced: golden holds (w_i, grad_i) pairs of the reference; one
+    # iteration from w_i must reproduce grad_i.  (Comparing free-running trajectories is not a test
+    # of the kernels: the reference itself, 8 threads vs 1 thread, differs by 6.8e-3 at iteration 30
+    # of this very case, whenever a ReLU unit of the dense tail crosses zero -- scripts/make_golden.py.)
     for key in [k for k in g if k.startswith("grad_")]:
         i = int(key.split("_")[1])
-        if i == n - 1:
-            gi = info["grad"]
-        else:
-            _, inf2 = engine.attack(kind, x, at, eps, i + 1, vc_src=src, w0=w0, want_grad=True)
-            gi = inf2["grad"]
-        assert grad_rel(gi, g[key]) < RTOL, (key, grad_rel(gi, g[key]))
+        wi = cuda(g, f"w_{i}", cli)
+        _, inf2 = engine.attack(kind, x, at, eps, 1, vc_src=src, w0=wi, want_grad=True, want_loss=True)
+        assert grad_rel(inf2["grad"], g[key]) < RTOL, (key, grad_rel(inf2["grad"], g[key]))
+        assert abs(float(inf2["losses"][0]) - g["losses"][i]) <= RTOL * abs(g["losses"][i])
+    assert grad_rel(info["grad"], g[f"grad_{n - 1}"]) < 2e-2      # free-running: loose, see above
     # result: same layout as the input, bound respected, close to the reference's result
     assert adv.shape == x.shape and adv.stride() == x.stride()
     ptb = (adv - x).abs().max().item()
@@ -59,14 +61,26 @@ def test_attack_vs_golden(engine, golden, name):
     ("emb", 3, 256, None, 200, 8), ("e2e", 2, 128, 100, 128, 5), ("fb", 2, 96, 72, 64, 5), ("emb", 1, 17, None, 19, 3)])
 def test_attack_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, T_src, T_adv, n):
     inp = oracle.make_inputs(kind, B, T, seed=21, T_src=T_src, T_adv=T_adv)
-    o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=inp.get("vc_src"),
-                          record_grads=[n - 1])
-    adv, info = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, n,
-                              vc_src=inp["vc_src"].cuda() if "vc_src" in inp else None, w0=inp["w0"].cuda(),
+    src = inp.get("vc_src")
+    o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=src,
+                          record_grads=[0, n - 1], record_w=True)
+    gsrc = src.cuda() if src is not None else None
+    adv, info = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, n, vc_src=gsrc, w0=inp["w0"].cuda(),
                               want_loss=True, want_grad=True)
     np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL)
-    assert grad_rel(info["grad"], o["grads"][n - 1]) < RTOL
     assert float((adv.cpu() - o["adv"]).abs().max()) < 5e-5
+    # teacher-forced gradient at the first and last recorded state; an fp64 oracle at the same w
+    # arbitrates should that state sit on a ReLU edge
+    m64 = oracle.OracleAdaInVC(oracle.SYNTH_CONFIG, seed=0, dtype=torch.float64)
+    for i in (0, n - 1):
+        wi = o["ws"][i]
+        _, inf = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, 1, vc_src=gsrc, w0=wi.cuda(), want_grad=True)
+        e32 = grad_rel(inf["grad"], o["grads"][i])
+        if e32 >= RTOL:
+            o64 = oracle.run_attack(kind, m64, inp["vc_tgt"].double(), inp["adv_tgt"].double(), 0.1, 1, wi.double(),
+                                    vc_src=src.double() if src is not None else None, record_grads=[0])
+            e32 = min(e32, grad_rel(inf["grad"], o64["grads"][0]))
+        assert e32 < RTOL, (i, e32)
 
 
 def test_graph_and_eager_agree(engine, oracle):

@@ -122,8 +122,9 @@ def test_adam_tanh_step_matches_torch_adam(engine, step):
     adv_d = engine.adam_tanh_step(g_adv.cuda(), x.cuda(), wd, md, vd, eps, step)
     st = opt.state[wp]
     assert torch.allclose(wd.cpu(), wp.detach(), rtol=0, atol=2e-7)
-    assert torch.allclose(md.cpu(), st["exp_avg"], rtol=1e-6, atol=1e-20)
-    assert torch.allclose(vd.cpu(), st["exp_avg_sq"], rtol=1e-6, atol=1e-30)
+    # m mixes two ~1e-8 terms of either sign: absolute tolerance at 1e-6 of that scale
+    assert torch.allclose(md.cpu(), st["exp_avg"], rtol=1e-5, atol=1e-14)
+    assert torch.allclose(vd.cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-22)
     assert torch.allclose(adv_d.cpu(), ref_adv, rtol=0, atol=2e-7)
     # the bound is exact on the perturbation term
     assert float((eps * wd.tanh()).abs().max()) <= eps
