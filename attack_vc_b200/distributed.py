@@ -1,0 +1,73 @@
+"""Batch sharding of the attack loop over the GPUs of one box.
+
+Utterances are independent (no BatchNorm in AdaIN-VC, InstanceNorm and pooling are per utterance),
+so a batch is split into contiguous slices, one per rank, weights replicated, and NO collective runs
+inside the loop.  The only coupling is the MSE normaliser: ``nn.MSELoss()`` averages over the batch
+too (attack_utils.py:32,70,114), and Adam is not scale invariant at these gradient magnitudes
+(SURVEY §5), so every rank passes the GLOBAL 1/(B_total*D).  After the loop the perturbed utterances
+are all-gathered and the per-iteration loss partial sums all-reduced (NCCL on GPUs; gloo in the CPU
+tests of this host logic).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of n utterances owned by ``rank``; the first n % world ranks get one
+    extra.  Empty slices are legal (world > n)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def global_inv_norm(kind: str, B_total: int, c_emb: int, c_mel: int, T_out: int) -> float:
+    """1 / (number of elements the reference's MSELoss averages over) for the WHOLE batch:
+    emb / fb compare embeddings [B, c_emb]; e2e compares converted mels [B, c_mel, T_out]."""
+    d = c_emb if kind in ("emb", "fb") else c_mel * T_out
+    return 1.0 / (float(B_total) * d)
+
+
+AttackFn = Callable[..., Tuple[Tensor, Dict[str, Optional[Tensor]]]]
+
+
+def sharded_attack(attack: AttackFn, kind: str, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_iters: int,
+                   inv_norm: float, vc_src: Optional[Tensor] = None, w0: Optional[Tensor] = None,
+                   group=None) -> Tuple[Tensor, Tensor]:
+    """Run ``attack`` on this rank's slice of the (replicated) batch and return the full perturbed
+    batch plus the per-iteration loss of the whole batch on every rank.
+
+    ``attack(kind, vc_tgt, adv_tgt, eps, n_iters, vc_src=, w0=, inv_norm=, want_loss=True)`` is
+    ``Engine.attack`` on a GPU; tests inject a CPU stand-in to exercise this plumbing under gloo."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = vc_tgt.shape[0]
+    lo, hi = shard_bounds(B, world, rank)
+    losses = torch.zeros(n_iters, dtype=torch.float32, device=vc_tgt.device)
+    if hi > lo:
+        sl = slice(lo, hi)
+        adv, info = attack(kind, vc_tgt[sl], adv_tgt[sl], eps, n_iters,
+                           vc_src=None if vc_src is None else vc_src[sl], w0=None if w0 is None else w0[sl],
+                           inv_norm=inv_norm, want_loss=True)
+        losses = info["losses"].to(torch.float32)
+    else:
+        adv = vc_tgt[0:0]
+    if world == 1:
+        return adv, losses
+    # gather of perturbed outputs: equal-sized padded slots, then trim (slices differ by at most one)
+    cap = -(-B // world)
+    slot = torch.zeros((cap,) + tuple(vc_tgt.shape[1:]), dtype=vc_tgt.dtype, device=vc_tgt.device)
+    slot[: hi - lo] = adv
+    slots = [torch.empty_like(slot) for _ in range(world)]
+    dist.all_gather(slots, slot, group=group)
+    parts = []
+    for r in range(world):
+        a, b = shard_bounds(B, world, r)
+        parts.append(slots[r][: b - a])
+    # loss statistics: each rank holds the partial sum over its slice, already scaled by the global normaliser
+    dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
+    return torch.cat(parts, dim=0), losses

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- attack iterations/s of the attack-vc perturbation loop on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload e2e|fb|emb]
+
+A *step* is one attack iteration (adv = x + eps*tanh(w); forward; loss; backward; Adam) over one
+batch of synthetic 80-bin mel utterances.  Default workload = BASELINE.json configs[1]: e2e_attack,
+1 utterance of 80 x 256 frames per GPU, random-init AdaIN-VC weights.  Multi-GPU: one process per
+GPU (torchrun), independent utterances per rank, no collective in the loop ("weak" scaling); the
+perturbed outputs and loss curves are gathered with NCCL after the loop.
+
+Numbers in the JSON line
+  value     iterations/s x utterances, inputs resident in HBM, CUDA events around exactly K steps
+            (graph replays of the captured iteration), max over ranks.
+  e2e       same metric through the drop-in public API attack_utils.<kind>_attack(...) with pinned
+            HOST tensors: H2D copies, target/invariant computation, K iterations, D2H of the result
+            all inside the timed region.
+  roofline  conv kernels (the dominant kernel class): algorithmic FLOPs / per-launch CUDA-event time
+            from one eagerly launched iteration, against MEASURED_PEAKS.json.
+  cpu_baseline  the oracle (PyTorch CPU restatement of the reference loop, incl. its wgrad and
+            per-iteration content-encoder work) on this box's host cores, bounded sample.
+`--impl reference` times that CPU loop alone (the reference is Python/PyTorch; /root/reference does
+not travel to the GPU box, the oracle is bit-identical to it -- tests/test_oracle_vs_reference.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")     # the drop-in keeps the reference's progress bar; keep stderr quiet here
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, utterances per GPU, frames, description)
+    "e2e": ("e2e", 1, 256, "BASELINE configs[1]: e2e_attack, ContentEncoder+SpeakerEncoder+Decoder, 80x256, batch 1 per GPU"),
+    "fb": ("fb", 64, 256, "BASELINE configs[2]: fb_attack, 80x256, batch 64 per GPU"),
+    "emb": ("emb", 512, 512, "BASELINE configs[3]: emb_attack, 80x512, 512 utterances per GPU (4096 over 8)"),
+}
+KIND_NAMES = {0: "conv", 1: "norm", 2: "dense_tail", 3: "affine", 4: "loss", 5: "update", 6: "layout", 7: "copy"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            self.thread.join(timeout=1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_loop_rate(kind: str, B: int, T: int, budget_s: float, max_iters: int):
+    """iterations/s of the oracle loop (== reference loop) on the host cores; bounded sample."""
+    from oracle import adainvc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0)
+    inp = O.make_inputs(kind, B, T, seed=1)
+    run = lambda n: O.run_attack(kind, model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=inp.get("vc_src"))
+    run(2)                                  # warm-up (thread pool, mkldnn primitives)
+    t0 = time.perf_counter(); run(3); t3 = time.perf_counter() - t0
+    n = int(max(5, min(max_iters, budget_s / (t3 / 3))))
+    t0 = time.perf_counter(); run(n); dt = time.perf_counter() - t0
+    # run(n) also recomputes the two targets once; that is part of the reference's attack call
+    return n * B / dt, cores, n, dt
+
+
+def reference_arm(args, rank):
+    kind, B, T, desc = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    Bc = min(B, 8)        # batched workloads: CPU sub-batch of 8 utterances
+    rate, cores, n, dt = cpu_loop_rate(kind, Bc, T, budget_s=20.0, max_iters=max(5, args.steps))
+    sample = f"{n} iterations of {kind}_attack, {Bc} utterance(s) of 80x{T}, oracle loop (bit-identical to the reference loop), {dt:.1f} s"
+    line = {
+        "impl": "reference", "metric": "attack iterations/s (x utterances)", "value": rate, "unit": "utterance-iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * Bc / rate, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "attack": kind, "utterances_per_gpu": B, "frames": T, "eps": 0.1},
+        "cpu_baseline": {"value": rate, "unit": "utterance-iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "utterance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="e2e", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the batched side measurements")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; attack_vc_b200 has no CPU fallback (use --impl reference for the CPU loop)")
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from attack_vc_b200 import Engine
+    from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs
+    import attack_utils as AU
+
+    kind, B, T, desc = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+    model = ParamTree(SYNTH_CONFIG, seed=0).to(dev)
+    eng = Engine(model)
+    host = {k: v.pin_memory() for k, v in make_inputs(kind, B, T, seed=1 + rank).items()}
+    inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    src = inp.get("vc_src")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: K graph-replayed iterations, inputs resident, CUDA events on the launch stream ----
+    sess = eng.begin(kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, W + K + 1, vc_src=src, w0=inp["w0"], want_loss=True)
+    launches_per_iter = sess.launches_per_iter
+    sess.step(W)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clk:
+        e0.record()
+        sess.step(K)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = clk.summary()
+    value = K * B * world / (ms / 1e3)
+    prof = sess.profile()                                   # one eager iteration, events around every launch
+    _, info = sess.end()
+    losses = info["losses"][: W + K + 1]
+    if not bool(torch.isfinite(losses).all()):
+        raise SystemExit("bench.py: non-finite loss")
+
+    # ---- roofline of the dominant kernel class (conv) from the per-launch event times ---------------
+    peaks = load_peaks()
+    by_kind = {}
+    for k, t_ms, fl, by in prof:
+        d = by_kind.setdefault(KIND_NAMES.get(k, str(k)), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += t_ms; d["flops"] += fl; d["bytes"] += by
+    tot_ms = sum(d["ms"] for d in by_kind.values()) or 1e-9
+    conv = by_kind.get("conv", {"launches": 1, "ms": 1e-9, "flops": 0.0, "bytes": 0.0})
+    conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": conv_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": conv_tf / peaks["bf16_tflops"], "traffic": None,
+                "kernel": "conv1d implicit GEMM (fwd + dgrad), all launches of one iteration",
+                "launches": conv["launches"], "avg_launch_us": 1e3 * conv["ms"] / conv["launches"],
+                "share_of_step": conv["ms"] / tot_ms, "peak_source": peaks["source"] + ", bf16 dense burst",
+                "algorithmic_gflop_per_step": sum(d["flops"] for d in by_kind.values()) / 1e9}
+    hbm = {}
+    for name in ("norm", "update", "loss"):
+        if name in by_kind and by_kind[name]["ms"] > 0:
+            gbs = by_kind[name]["bytes"] / (by_kind[name]["ms"] / 1e3) / 1e9
+            hbm[name] = {"achieved_gbs": gbs, "frac": gbs / peaks["hbm_gbs"], "launches": by_kind[name]["launches"],
+                         "avg_launch_us": 1e3 * by_kind[name]["ms"] / by_kind[name]["launches"]}
+    breakdown = {k: {"launches": d["launches"], "ms": round(d["ms"], 4)} for k, d in by_kind.items()}
+
+    # ---- e2e: the drop-in public API with pinned host tensors ----------------------------------------
+    fn = {"emb": AU.emb_attack, "e2e": AU.e2e_attack, "fb": AU.fb_attack}[kind]
+
+    def public_call(n):
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "w0"}
+        if kind == "emb":
+            out = fn(model, d["vc_tgt"], d["adv_tgt"], 0.1, n)
+        else:
+            out = fn(model, d["vc_src"], d["vc_tgt"], d["adv_tgt"], 0.1, n)
+        return out.cpu()
+    public_call(3)
+    barrier()
+    t0 = time.perf_counter()
+    res = public_call(K)
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    e2e_value = K * B * world / (e2e_ms / 1e3)
+    h2d = sum(v.numel() * 4 for k, v in host.items() if k != "w0")
+    d2h = res.numel() * 4
+    launches_before = eng.kernel_launches
+
+    # ---- after the loop: gather perturbed outputs + loss curves (NCCL), not timed --------------------
+    if world > 1:
+        outs = [torch.empty_like(res, device=dev) for _ in range(world)]
+        dist.all_gather(outs, res.to(dev))
+        ls = losses.clone()
+        dist.all_reduce(ls)
+
+    line = {
+        "metric": "attack iterations/s (x utterances)", "value": value, "unit": "utterance-iterations/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "attack": kind, "utterances_per_gpu": B, "frames": T, "eps": 0.1,
+                   "defended_utterances_per_s_at_1500_iters": value / 1500.0,
+                   "l2": "not flushed: iteration i+1 consumes iteration i's state and the 19.6 MB of weights stay hot by construction of the attack; the batched side measurements stream activations larger than L2",
+                   "conv_impl": os.environ.get("AVC_CONV_IMPL", "auto")},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "utterance-iterations/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "ms_total": e2e_ms, "api": f"attack_utils.{kind}_attack(model, ..., n_iters={K}) with pinned host tensors"},
+        "gpu_launches": launches_per_iter * K,
+        "launches_per_step": launches_per_iter,
+        "roofline": roofline, "hbm_kernels": hbm, "breakdown_ms": breakdown,
+        "loss_first_last": [float(losses[0]), float(losses[-1])],
+        "kernel_launches_total": launches_before,
+    }
+
+    # ---- side measurements on rank 0 at N=1: batched configs where the rooflines are meaningful ------
+    if world == 1 and not args.no_extra and args.workload == "e2e":
+        extra = {}
+        for name, (k2, B2, T2, n2) in {"emb_B128_T512": ("emb", 128, 512, 6), "fb_B64_T256": ("fb", 64, 256, 6)}.items():
+            try:
+                i2 = {k: v.to(dev) for k, v in make_inputs(k2, B2, T2, seed=9).items()}
+                s2 = eng.begin(k2, i2["vc_tgt"], i2["adv_tgt"], 0.1, 3 + n2 + 1, vc_src=i2.get("vc_src"), w0=i2["w0"])
+                s2.step(3)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                a.record(); s2.step(n2); b.record(); torch.cuda.synchronize(dev)
+                ms2 = a.elapsed_time(b) / n2
+                p2 = s2.profile(); s2.end()
+                cf = sum(f for kk, _, f, _ in p2 if kk == 0); cm = sum(m for kk, m, _, _ in p2 if kk == 0)
+                ent = {"utterance_iterations_per_s": B2 * 1e3 / ms2, "ms_per_step": ms2, "conv_tflops": cf / (cm / 1e3) / 1e12,
+                       "conv_frac_of_bf16_peak": cf / (cm / 1e3) / 1e12 / peaks["bf16_tflops"], "conv_share_of_step": cm / sum(m for _, m, _, _ in p2)}
+                for kk, nm in ((1, "norm"), (5, "update")):
+                    mm = sum(m for q, m, _, _ in p2 if q == kk); bb = sum(bt for q, _, _, bt in p2 if q == kk)
+                    if mm > 0:
+                        ent[nm + "_gbs"] = bb / (mm / 1e3) / 1e9
+                        ent[nm + "_frac_of_hbm_peak"] = ent[nm + "_gbs"] / peaks["hbm_gbs"]
+                extra[name] = ent
+                del i2
+            except Exception as e:   # a side measurement must never take the headline down
+                extra[name] = {"error": str(e)[:200]}
+        line["batched"] = extra
+
+    if world == 1 and not args.no_cpu_baseline:
+        Bc = min(B, 8)
+        rate, cores, n, dt = cpu_loop_rate(kind, Bc, T, budget_s=15.0, max_iters=400)
+        line["cpu_baseline"] = {"value": rate, "unit": "utterance-iterations/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} iterations of {kind}_attack, {Bc} utterance(s) of 80x{T}, oracle loop (bit-identical to the reference loop), {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -189,13 +189,17 @@ class OracleAdaInVC(ParamTree):
 # --------------------------------------------------------------------------------------
 def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_iters: int,
                w0: Tensor, vc_src: Optional[Tensor] = None, record_grads: Iterable[int] = (),
-               progress=None, record_w: bool = False) -> Dict[str, object]:
+               progress=None, record_w: bool = False, inv_norm: Optional[float] = None) -> Dict[str, object]:
     if kind not in ("emb", "e2e", "fb"):
         raise NotImplementedError(kind)
     record = set(record_grads)
     w = w0.detach().clone().requires_grad_(True)              # attack_utils.py:30,68,112 (w0 injected)
     opt = torch.optim.Adam([w])                               # :31,69,113  lr 1e-3, betas (.9,.999), eps 1e-8
     mse = nn.MSELoss()                                        # :32,70,114
+    if inv_norm is not None:
+        # sharded call (attack_vc_b200/distributed.py): same loss, but normalised by the GLOBAL element
+        # count 1/(B_total*D) instead of this slice's -- the only coupling between utterances
+        mse = lambda a, b: (a - b).square().sum() * inv_norm  # noqa: E731
 
     def fwd(x: Tensor) -> Tensor:
         if kind == "emb":
