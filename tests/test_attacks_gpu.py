@@ -45,7 +45,8 @@ def test_attack_vs_golden(engine, golden, name):
         _, inf2 = engine.attack(kind, x, at, eps, 1, vc_src=src, w0=wi, want_grad=True, want_loss=True)
         assert grad_rel(inf2["grad"], g[key]) < RTOL, (key, grad_rel(inf2["grad"], g[key]))
         assert abs(float(inf2["losses"][0]) - g["losses"][i]) <= RTOL * abs(g["losses"][i])
-    assert grad_rel(info["grad"], g[f"grad_{n - 1}"]) < 2e-2      # free-running: loose, see above
+    if f"grad_{n - 1}" in g:
+        assert grad_rel(info["grad"], g[f"grad_{n - 1}"]) < 2e-2      # free-running: loose, see above
     # result: same layout as the input, bound respected, close to the reference's result
     assert adv.shape == x.shape and adv.stride() == x.stride()
     ptb = (adv - x).abs().max().item()
