@@ -51,8 +51,39 @@ struct ConvArgs {
   int zsplit;     // 1: blockIdx.z selects ONE group; its outputs go to channels [z*N, z*N+N) (conv bank)
   int n_groups;
   int win_rows;   // activation-window rows available in smem (zero rows follow)
+  // conv_small_kernel only: first smem window row of every group (all windows are resident at once),
+  // win_off[n_groups] = first zero row; ring = number of weight-slab buffers, slab_floats = size of one
+  int win_off[kMaxGroups + 1];
+  int ring, slab_floats;
   TapGroup g[kMaxGroups];
 };
+
+// Rows of the activation window one output tile [t0, t1) of group G needs (shared by host and device).
+struct WinGeom {
+  int wlo, nrows;                      // first gather position (may be negative) and row count
+  int lt_lo, lt_hi, rt_lo, rt_hi;      // dgrad: output rows that also receive a mirrored (reflect-pad) gradient
+  bool edge;
+};
+__host__ __device__ inline WinGeom win_geom(int bwd, int s, int T_y, const TapGroup& G, int t0, int t1) {
+  const int sv = bwd ? 1 : s;
+  int pmin = t0 * sv, pmax = (t1 - 1) * sv;
+  WinGeom w;
+  w.edge = false; w.lt_lo = 0; w.lt_hi = -1; w.rt_lo = 0; w.rt_hi = -1;
+  if (bwd) {
+    w.lt_lo = t0 > 1 ? t0 : 1; w.lt_hi = (t1 - 1) < G.pl ? (t1 - 1) : G.pl;
+    w.rt_lo = t0 > (T_y - 1 - G.pr) ? t0 : (T_y - 1 - G.pr); w.rt_hi = (t1 - 1) < (T_y - 2) ? (t1 - 1) : (T_y - 2);
+    if (w.lt_lo <= w.lt_hi) { w.edge = true; if (-w.lt_hi < pmin) pmin = -w.lt_hi; if (-w.lt_lo > pmax) pmax = -w.lt_lo; }
+    if (w.rt_lo <= w.rt_hi) {
+      w.edge = true;
+      const int a = 2 * (T_y - 1) - w.rt_hi, b = 2 * (T_y - 1) - w.rt_lo;
+      if (a < pmin) pmin = a;
+      if (b > pmax) pmax = b;
+    }
+  }
+  w.wlo = pmin + G.off0;
+  w.nrows = pmax + G.off0 + G.n_taps - 1 - w.wlo + 1;
+  return w;
+}
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool pred) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -62,6 +93,19 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, b
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+// wait until at most n groups are pending (n is warp-uniform, 0..7)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
+}
 
 template <int RM, int TXN, int TYN, bool EDGE>
 __device__ __forceinline__ void conv_accumulate_slab(float (&acc)[RM][4], const float* __restrict__ S,
@@ -218,6 +262,171 @@ __global__ void __launch_bounds__(TXN* TYN) conv_simt_kernel(const ConvArgs p) {
     if (p.res.mode != RES_NONE) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
     st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
   }
+}
+
+
+// =================================================================================================
+// conv_small_kernel -- the same contraction for SMALL M (batch-1 attacks: M = 32..256 rows).
+// There a layer is latency-bound, not throughput-bound, so the tile is tiny (TM x 32 outputs, one
+// CTA per SM), every group's activation window is resident at once, weight slabs (one tap x <=128
+// channels x 32 columns) stream through a deep cp.async ring issued before anything else, the 8
+// warps split K (16 rows of every slab each) and their partial tiles are summed in a fixed order.
+// =================================================================================================
+constexpr int kSmTN = 32;
+constexpr int kSmWarps = 8;
+
+template <int TM>
+__global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArgs p) {
+  constexpr int RM = TM / 4, NT = 32 * kSmWarps;
+  extern __shared__ __align__(16) float smem[];
+  const int g_lo = p.zsplit ? blockIdx.z : 0;
+  const int g_hi = p.zsplit ? blockIdx.z + 1 : p.n_groups;
+  float* S = smem;                                                    // windows, then kMaxTaps zero rows
+  const int zr = p.win_off[p.n_groups];
+  float* Wr = smem + (size_t)(zr + kMaxTaps) * kSRow;                 // [ring][slab_floats]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = lane & 7, ty = lane >> 3;
+  const int tiles_t = (p.T_y + TM - 1) / TM;
+  const int b = blockIdx.x / tiles_t, t0 = (blockIdx.x % tiles_t) * TM;
+  const int t1 = min(t0 + TM, p.T_y);
+  const int n0 = blockIdx.y * kSmTN;
+  const int Ntot = p.N;
+  const int sv = p.bwd ? 1 : p.s;
+
+  int n_slabs = 0;
+  for (int gi = g_lo; gi < g_hi; ++gi) n_slabs += p.g[gi].n_taps;
+
+  // ---- weight ring: slab q = (group, tap) in issue order ----------------------------------------
+  int is_g = g_lo, is_tap = 0;   // next slab to issue
+  auto issue = [&](int q) {
+    if (q < n_slabs) {
+      const TapGroup& G = p.g[is_g];
+      const float* Wg = G.W + (long long)is_tap * G.wts * Ntot + n0;
+      float* dst = Wr + (size_t)(q % p.ring) * p.slab_floats;
+      for (int idx = tid; idx < G.kc * (kSmTN / 4); idx += NT) {
+        const int k = idx >> 3, n = (idx & 7) << 2;
+        const bool ok = (n0 + n) < Ntot;
+        cp_async16(dst + k * kSmTN + n, ok ? Wg + (long long)k * Ntot + n : G.W, ok);
+      }
+      if (++is_tap == G.n_taps) { is_tap = 0; ++is_g; }
+    }
+    cp_async_commit();
+  };
+  for (int q = 0; q < p.ring - 1; ++q) issue(q);
+
+  // ---- all activation windows -> smem (loads of all groups in flight together) -------------------
+  for (int i = tid; i < kMaxTaps * kSRow; i += NT) S[zr * kSRow + i] = 0.f;
+  for (int gi = g_lo; gi < g_hi; ++gi) {
+    const TapGroup& G = p.g[gi];
+    const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
+    const int woff = p.zsplit ? 0 : p.win_off[gi];
+    if (wg.nrows > (p.zsplit ? zr : p.win_off[gi + 1] - p.win_off[gi])) __trap();   // host sized the window too small
+    const int c4n = G.kc >> 2;
+    const float* Ab = p.A + (long long)b * p.a_bs + G.a_ch_off;
+    const float* Mb = p.Mk ? p.Mk + (long long)b * p.m_bs + G.a_ch_off : nullptr;
+    for (int idx = tid; idx < wg.nrows * c4n; idx += NT) {
+      const int row = idx / c4n, c = (idx - row * c4n) << 2;
+      const int r = wg.wlo + row;
+      int rr; bool ok;
+      if (!p.bwd) {
+        rr = r < 0 ? -r : r;
+        if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
+        ok = rr >= 0 && rr < p.T_a;
+      } else {
+        ok = r >= 0 && (r % p.s) == 0;
+        rr = r / p.s;
+        ok = ok && rr < p.T_a;
+      }
+      float4 v = f4zero();
+      if (ok) {
+        v = ld4(Ab + (long long)rr * p.a_rs + c);
+        if (Mb) v = dact4mul(v, ld4(Mb + (long long)rr * p.m_rs + c), p.slope);
+      }
+      st4(S + (size_t)(woff + row) * kSRow + c, v);
+    }
+  }
+
+  // ---- main loop over slabs ------------------------------------------------------------------------
+  float acc[RM][4];
+#pragma unroll
+  for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  int rb[RM][3];
+  bool edge = false;
+  int cg = g_lo - 1, ctap = 0, cnt = 0;   // group / tap of the slab being consumed
+  const float* Sg = S;
+  int kc = 0;
+  for (int q = 0; q < n_slabs; ++q) {
+    if (cnt == 0) {   // first slab of the next group: per-thread window rows
+      ++cg; ctap = 0;
+      const TapGroup& G = p.g[cg];
+      cnt = G.n_taps; kc = G.kc;
+      const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
+      edge = wg.edge;
+      Sg = S + (size_t)(p.zsplit ? 0 : p.win_off[cg]) * kSRow;
+      const int zrel = zr - (p.zsplit ? 0 : p.win_off[cg]);
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int t = t0 + ty * RM + i;
+        const bool tv = t < t1;
+        rb[i][0] = tv ? t * sv + G.off0 - wg.wlo : zrel;
+        rb[i][1] = (tv && t >= wg.lt_lo && t <= wg.lt_hi) ? -t + G.off0 - wg.wlo : zrel;
+        rb[i][2] = (tv && t >= wg.rt_lo && t <= wg.rt_hi) ? 2 * (p.T_y - 1) - t + G.off0 - wg.wlo : zrel;
+      }
+    }
+    cp_async_wait_dyn(p.ring - 2);
+    __syncthreads();                     // slab q landed for everyone; everyone is done with slab q-1 (and, first time, the windows are visible)
+    issue(q + p.ring - 1);               // refills the buffer slab q-1 used
+    const float* Wsub = Wr + (size_t)(q % p.ring) * p.slab_floats;
+    const int k_lo = warp * 16, k_hi = min(k_lo + 16, kc);
+    for (int k4 = k_lo; k4 < k_hi; k4 += 4) {
+      float4 a[RM];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        a[i] = ld4(Sg + (rb[i][0] + ctap) * kSRow + k4);
+        if (edge) {
+          a[i] = f4add(a[i], ld4(Sg + (rb[i][1] + ctap) * kSRow + k4));
+          a[i] = f4add(a[i], ld4(Sg + (rb[i][2] + ctap) * kSRow + k4));
+        }
+      }
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float4 w = ld4(Wsub + (k4 + qq) * kSmTN + tx * 4);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          const float av = qq == 0 ? a[i].x : qq == 1 ? a[i].y : qq == 2 ? a[i].z : a[i].w;
+          acc[i][0] = fmaf(av, w.x, acc[i][0]);
+          acc[i][1] = fmaf(av, w.y, acc[i][1]);
+          acc[i][2] = fmaf(av, w.z, acc[i][2]);
+          acc[i][3] = fmaf(av, w.w, acc[i][3]);
+        }
+      }
+    }
+    ++ctap; --cnt;
+  }
+  cp_async_wait<0>();
+  __syncthreads();                       // all slabs consumed: the ring becomes the reduction buffer
+
+  // ---- fixed-order sum of the 8 K-slices, then the epilogue ----------------------------------------
+  float* red = Wr;                       // [kSmWarps][TM][kSmTN]
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+    st4(red + ((size_t)warp * TM + ty * RM + i) * kSmTN + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+  __syncthreads();
+  if (tid >= TM * (kSmTN / 4)) return;
+  const int row = tid >> 3, nn = (tid & 7) << 2;
+  const int t = t0 + row, n = n0 + nn;
+  if (t >= t1 || n >= p.N) return;
+  float4 v = ld4(red + (size_t)row * kSmTN + nn);
+#pragma unroll
+  for (int w = 1; w < kSmWarps; ++w) v = f4add(v, ld4(red + ((size_t)w * TM + row) * kSmTN + nn));
+  const int ch = p.zsplit ? blockIdx.z * p.N + n : n;   // output channel
+  if (p.bias) v = f4add(v, ld4(p.bias + ch));
+  if (p.Om) v = dact4mul(v, ld4(p.Om + (long long)b * p.om_bs + (long long)t * p.om_rs + ch), p.slope);
+  if (p.act) v = act4(v, p.slope);
+  if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)t * p.y2_rs + ch, v);
+  if (p.res.mode != RES_NONE) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
+  st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
 }
 
 }  // namespace avc

@@ -326,18 +326,6 @@ struct TailArgs {
   float* gpool;           // [B,128]: d h[b,t,:] for every t (already divided by T_h)
 };
 
-__device__ __forceinline__ void dense128(const float* __restrict__ M, const float* __restrict__ vin,
-                                         float (*part)[128], int tid) {
-  // part[g][n] = sum_{c in slice g} M[c*128+n] * vin[c]
-  const int g = tid >> 7, n = tid & 127;
-  float a = 0.f;
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const int c = g * 16 + q;
-    a = fmaf(M[c * 128 + n], vin[c], a);
-  }
-  part[g][n] = a;
-}
 __device__ __forceinline__ float part_sum(float (*part)[128], int n) {
   float s = 0.f;
 #pragma unroll
@@ -345,7 +333,19 @@ __device__ __forceinline__ float part_sum(float (*part)[128], int n) {
   return s;
 }
 
+__device__ __forceinline__ void cp16(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+
+constexpr int kTailRing = 3;                       // weight matrices in flight (64 KB each)
+constexpr int kTailSmem = kTailRing * 128 * 128 * 4;
+
+// The chain is 13 dependent 128x128 mat-vecs forward and 13 backward for ONE utterance per CTA: pure
+// latency.  The matrices do not depend on the data, so they stream through a 3-deep cp.async ring two
+// layers ahead of the arithmetic.
 __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
+  extern __shared__ __align__(16) float wring[];    // [kTailRing][128*128]
   __shared__ float part[8][128];
   __shared__ float va[2 * kTailMaxDense + 2][128];   // va[0]=pooled v0; block l: va[1+2l]=y1, va[2+2l]=y2; running v in vcur
   __shared__ float vcur[128];
@@ -353,7 +353,48 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
   __shared__ float lred[4];
   const int tid = threadIdx.x, b = blockIdx.x, n = tid & 127;
   const int nsave = 2 * p.n_dense + 1;
+  const int nd = p.n_dense;
   float* acts_b = p.acts + (long long)b * (nsave + p.n_dense) * 128;   // + per-block inputs v_l
+
+  // matrix sequence of this launch: forward Wt1[0],Wt2[0],...,Wto then backward Wo,W2[nd-1],W1[nd-1],...,W2[0],W1[0]
+  const int n_fwd = (p.mode & TAIL_FWD) ? 2 * nd + 1 : 0;
+  const int n_all = n_fwd + ((p.mode & TAIL_BWD) ? 2 * nd + 1 : 0);
+  auto mat_at = [&](int i) -> const float* {
+    if (i < n_fwd) return i == 2 * nd ? p.Wto : ((i & 1) ? p.Wt2[i >> 1] : p.Wt1[i >> 1]);
+    const int j = i - n_fwd;
+    if (j == 0) return p.Wo;
+    const int l = nd - 1 - ((j - 1) >> 1);
+    return ((j - 1) & 1) ? p.W1[l] : p.W2[l];
+  };
+  auto issue = [&](int i) {
+    if (i < n_all) {
+      const float* M = mat_at(i);
+      float* dst = wring + (size_t)(i % kTailRing) * 16384;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cp16(dst + (q * 1024 + tid) * 4, M + (q * 1024 + tid) * 4);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  int seq = 0;
+  // part[g][n] = sum_{c in slice g} M[c*128+n] * vin[c] for the next matrix of the sequence
+  auto dense_step = [&](const float* vin) {
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();                 // matrix `seq` landed for everyone, vin is visible, matrix seq-1 is no longer read
+    issue(seq + 2);
+    const float* M = wring + (size_t)(seq % kTailRing) * 16384;
+    const int g = tid >> 7;
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int c = g * 16 + q;
+      a = fmaf(M[c * 128 + n], vin[c], a);
+    }
+    part[g][n] = a;
+    ++seq;
+    __syncthreads();
+  };
+  issue(0);
+  issue(1);
 
   if (p.mode & TAIL_FWD) {
     // global average pool over time
@@ -365,21 +406,17 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
       part[g][n] = a;
       __syncthreads();
       if (tid < 128) { vcur[n] = part_sum(part, n) / (float)p.T_h; va[0][n] = vcur[n]; }
-      __syncthreads();
     }
     for (int l = 0; l < p.n_dense; ++l) {
-      if (tid < 128) acts_b[(nsave + l) * 128 + n] = vcur[n];     // block input v_l (for nothing but completeness)
-      dense128(p.Wt1[l], vcur, part, tid);
-      __syncthreads();
-      if (tid < 128) va[1 + 2 * l][n] = actf(part_sum(part, n) + p.b1[l][n], p.slope);
-      __syncthreads();
-      dense128(p.Wt2[l], va[1 + 2 * l], part, tid);
-      __syncthreads();
+      dense_step(vcur);
+      if (tid < 128) {
+        acts_b[(nsave + l) * 128 + n] = vcur[n];     // block input v_l (for nothing but completeness)
+        va[1 + 2 * l][n] = actf(part_sum(part, n) + p.b1[l][n], p.slope);
+      }
+      dense_step(va[1 + 2 * l]);
       if (tid < 128) { float y2 = actf(part_sum(part, n) + p.b2[l][n], p.slope); va[2 + 2 * l][n] = y2; vcur[n] = y2 + vcur[n]; }
-      __syncthreads();
     }
-    dense128(p.Wto, vcur, part, tid);
-    __syncthreads();
+    dense_step(vcur);
     if (tid < 128) {
       gt[n] = part_sum(part, n) + p.bo[n];     // embedding
       if (p.emb) p.emb[(long long)b * 128 + n] = gt[n];
@@ -412,25 +449,19 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
       gv[n] = s;
     }
   }
-  __syncthreads();
   // ---- output layer: g_v = Wo^T g_emb  (Wo is [n_out][c]: contraction over n_out) ----------------
-  dense128(p.Wo, gv, part, tid);
-  __syncthreads();
+  dense_step(gv);
   if (tid < 128) gv[n] = part_sum(part, n);
-  __syncthreads();
   for (int l = p.n_dense - 1; l >= 0; --l) {
     // v_{l+1} = y2 + v_l ; y2 = act(W2 y1 + b2) ; y1 = act(W1 v_l + b1)
+    __syncthreads();
     if (tid < 128) gt[n] = gv[n] * dactf(va[2 + 2 * l][n], p.slope);     // d pre-act 2
-    __syncthreads();
-    dense128(p.W2[l], gt, part, tid);
-    __syncthreads();
+    dense_step(gt);
     if (tid < 128) gt[n] = part_sum(part, n) * dactf(va[1 + 2 * l][n], p.slope);   // d pre-act 1
-    __syncthreads();
-    dense128(p.W1[l], gt, part, tid);
-    __syncthreads();
+    dense_step(gt);
     if (tid < 128) gv[n] = gv[n] + part_sum(part, n);
-    __syncthreads();
   }
+  __syncthreads();
   if (tid < 128) p.gpool[(long long)b * 128 + n] = gv[n] / (float)p.T_h;
 }
 

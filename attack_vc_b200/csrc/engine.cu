@@ -6,6 +6,7 @@
 // host (the reference never reads the loss inside the loop either).
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -67,20 +68,26 @@ struct Launch {
   void operator()(cudaStream_t st) const { fn(st); }
 };
 
+constexpr int kUnroll = 16;
+
 struct Plan {
   Arena mem;
+  explicit Plan(SlabPool* pool = nullptr) : mem(pool) {}
   std::vector<Launch> setup;    // once per attack call (targets, loop invariants)
   std::vector<Launch> iter;     // one attack iteration
   std::vector<Launch> finish;   // after the loop
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr, graphU = nullptr;
+  cudaGraphExec_t exec = nullptr;    // one iteration
+  cudaGraphExec_t execU = nullptr;   // kUnroll iterations back to back: 16x fewer launches, shallow launch queue
   int n_iters = 0;      // iterations the Adam table / loss buffer were sized for
   int done_iters = 0;
   bool use_graph = true;
   bool finished = false;
   ~Plan() {
     if (exec) cudaGraphExecDestroy(exec);
+    if (execU) cudaGraphExecDestroy(execU);
     if (graph) cudaGraphDestroy(graph);
+    if (graphU) cudaGraphDestroy(graphU);
   }
 };
 
@@ -91,6 +98,7 @@ struct avc_handle {
   int sm_count = 148;
   avc_model_desc desc{};
   Arena wmem;
+  SlabPool pool;      // activation slabs recycled between attacks (declared before any Plan can die)
   bool have_weights = false;
   EncoderW se, ce;
   DecoderW dec;
@@ -110,6 +118,8 @@ namespace {
 // =================================================================================================
 // conv launch
 // =================================================================================================
+constexpr size_t kSmemMax = 227 * 1024;
+
 template <int RM, int TXN, int TYN>
 void launch_conv_cfg(ConvArgs a, cudaStream_t st) {
   constexpr int TM = RM * TYN, TN = TXN * 4;
@@ -126,27 +136,72 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(conv_simt_kernel<4, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<1, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(conv_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CK(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
   tc_init_attributes();
 }
 
-void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st) {
+// small-M path: every window resident, deep weight ring (conv_simt.cuh: conv_small_kernel)
+template <int TM>
+bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
+  const int tiles_t = (a.T_y + TM - 1) / TM;
+  int rows[kMaxGroups] = {0}, kc_max = 0, slabs_max = 0, slabs_all = 0;
+  for (int g = 0; g < a.n_groups; ++g) {
+    for (int i = 0; i < tiles_t; ++i) {
+      const WinGeom w = win_geom(a.bwd, a.s, a.T_y, a.g[g], i * TM, std::min(i * TM + TM, a.T_y));
+      rows[g] = std::max(rows[g], w.nrows);
+    }
+    kc_max = std::max(kc_max, a.g[g].kc);
+    slabs_max = std::max(slabs_max, a.g[g].n_taps);
+    slabs_all += a.g[g].n_taps;
+  }
+  int off = 0;
+  for (int g = 0; g < a.n_groups; ++g) {
+    a.win_off[g] = a.zsplit ? 0 : off;
+    off = a.zsplit ? std::max(off, rows[g]) : off + rows[g];
+  }
+  a.win_off[a.n_groups] = off;
+  a.slab_floats = kc_max * kSmTN;
+  const size_t win_bytes = (size_t)(off + kMaxTaps) * kSRow * sizeof(float);
+  const size_t slab_bytes = (size_t)a.slab_floats * sizeof(float);
+  const int n_slabs = a.zsplit ? slabs_max : slabs_all;
+  if (win_bytes + 2 * slab_bytes > kSmemMax) return false;
+  int ring = (int)std::min<size_t>((kSmemMax - win_bytes) / slab_bytes, 8);
+  ring = std::max(2, std::min(ring, n_slabs + 1));
+  while ((size_t)ring * slab_bytes < (size_t)kSmWarps * TM * kSmTN * sizeof(float)) ++ring;   // the ring doubles as the split-K reduction buffer
+  const size_t smem = win_bytes + (size_t)ring * slab_bytes;
+  if (smem > kSmemMax) return false;
+  a.ring = ring;
+  dim3 grid(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : 1);
+  conv_small_kernel<TM><<<grid, 32 * kSmWarps, smem, st>>>(a);
+  CK(cudaGetLastError());
+  return true;
+}
+
+void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st, bool allow_small = true) {
   // pick the largest tile that still gives every SM about two CTAs; small-M problems (batch 1)
-  // get the 16x32 tile so the layer spreads over as many SMs as possible
+  // take the latency-oriented kernel
   const long long z = a.zsplit ? a.n_groups : 1;
   auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
-  if (ctas(64, 64) >= 2LL * sm_count) launch_conv_cfg<4, 16, 16>(a, st);
-  else if (ctas(32, 32) >= 2LL * sm_count) launch_conv_cfg<2, 8, 16>(a, st);
-  else launch_conv_cfg<1, 8, 16>(a, st);
+  if (ctas(64, 64) >= 2LL * sm_count) { launch_conv_cfg<4, 16, 16>(a, st); return; }
+  if (ctas(32, 32) >= 2LL * sm_count) { launch_conv_cfg<2, 8, 16>(a, st); return; }
+  static const bool no_small = getenv("AVC_NO_SMALL") != nullptr;
+  if (!no_small && allow_small) {
+    const bool one_wave8 = ctas(8, kSmTN) <= sm_count;
+    if (one_wave8 ? launch_conv_small_cfg<8>(a, st) : launch_conv_small_cfg<16>(a, st)) return;
+  }
+  launch_conv_cfg<1, 8, 16>(a, st);
 }
 
 void launch_conv(avc_handle* h, const ConvArgs& a, const TcPack* tc, cudaStream_t st) {
   int impl = h->conv_impl;
-  if (impl != 1 && tc && tc->ok && tc_eligible(a, *tc, impl == 2)) {
+  if (impl != 1 && impl != 3 && tc && tc->ok && tc_eligible(a, *tc, impl == 2)) {
     launch_conv_tc(a, *tc, h->sm_count, st);
     return;
   }
   if (impl == 2 && tc == nullptr) { /* no tensor-core image for this op: fp32 path */ }
-  launch_conv_simt(a, h->sm_count, st);
+  launch_conv_simt(a, h->sm_count, st, impl != 3);
 }
 
 // fill the channel groups of a plain Conv1d (forward) -- K split into <=128-channel groups
@@ -381,7 +436,7 @@ TailArgs tail_args(const EncoderW& W, const EncActs& A) {
 }
 
 void emit_tail(Emitter& E, const TailArgs& t, int B) {
-  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { se_tail_kernel<<<B, 1024, 0, st>>>(t); CK(cudaGetLastError()); });
+  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { se_tail_kernel<<<B, 1024, kTailSmem, st>>>(t); CK(cudaGetLastError()); });
 }
 
 // speaker-encoder backward from gpool ([B,128], gradient of every pooled row) down to d input
@@ -742,7 +797,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   const float eps = a->eps;
   const EncoderW& SE = h->se;
 
-  std::unique_ptr<Plan> plan_ptr(new Plan());
+  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool));
   Plan& plan = *plan_ptr;
   plan.n_iters = n_iters;
   plan.use_graph = a->use_graph != 0;
@@ -937,23 +992,27 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     h->launches += (long long)plan.setup.size();
     h->launches_per_iter = (int)plan.iter.size();
     if (n_iters > 0 && plan.use_graph) {
-      cudaStream_t cs;
-      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-      if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
-      try {
-        run_list(plan.iter, cs);
-      } catch (...) {
-        cudaGraph_t g = nullptr;
-        cudaStreamEndCapture(cs, &g);
-        if (g) cudaGraphDestroy(g);
+      auto capture = [&](int reps, cudaGraph_t* g, cudaGraphExec_t* x) {
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+        try {
+          for (int r = 0; r < reps; ++r) run_list(plan.iter, cs);
+        } catch (...) {
+          cudaGraph_t bad = nullptr;
+          cudaStreamEndCapture(cs, &bad);
+          if (bad) cudaGraphDestroy(bad);
+          cudaStreamDestroy(cs);
+          throw;
+        }
+        e = cudaStreamEndCapture(cs, g);
         cudaStreamDestroy(cs);
-        throw;
-      }
-      e = cudaStreamEndCapture(cs, &plan.graph);
-      cudaStreamDestroy(cs);
-      if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
-      CK(cudaGraphInstantiate(&plan.exec, plan.graph, 0));
+        if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(x, *g, 0));
+      };
+      capture(1, &plan.graph, &plan.exec);
+      if (n_iters >= 2 * kUnroll) capture(kUnroll, &plan.graphU, &plan.execU);
     }
   } catch (...) {
     cudaDeviceSynchronize();   // nothing may still be running when the arena is released
@@ -968,7 +1027,9 @@ void step_attack(avc_handle* h, Plan& plan, int n, cudaStream_t st) {
     fail(AVC_ERR_INVALID, "session was opened for %d iterations, %d done, %d more requested", plan.n_iters, plan.done_iters, n);
   try {
     if (plan.exec) {
-      for (int i = 0; i < n; ++i) CK(cudaGraphLaunch(plan.exec, st));
+      int left = n;
+      if (plan.execU) for (; left >= kUnroll; left -= kUnroll) CK(cudaGraphLaunch(plan.execU, st));
+      for (; left > 0; --left) CK(cudaGraphLaunch(plan.exec, st));
     } else {
       for (int i = 0; i < n; ++i) run_list(plan.iter, st);
     }
@@ -994,9 +1055,19 @@ void finish_attack(avc_handle* h, Plan& plan, cudaStream_t st) {
 }
 
 void run_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
+  static const bool timing = getenv("AVC_TIMING") != nullptr;   // host-side phase times on stderr
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   std::unique_ptr<Plan> plan = build_attack(h, kind, a, st);
+  const double t1 = now();
   step_attack(h, *plan, a->n_iters, st);
+  const double t2 = now();
   finish_attack(h, *plan, st);
+  const double t3 = now();
+  const double t4 = [&] { if (plan->execU) { cudaGraphExecDestroy(plan->execU); plan->execU = nullptr; } if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; } return now(); }();
+  plan.reset();
+  if (timing) fprintf(stderr, "[avc] graph exec destroy %.2f ms\n", t4 - t3);
+  if (timing) fprintf(stderr, "[avc] attack kind %d: build %.2f ms, enqueue %.2f ms, drain+finish %.2f ms, free %.2f ms\n", (int)kind, t1 - t0, t2 - t1, t3 - t2, now() - t3);
 }
 
 template <class Fn>

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/avc_b200.h"
@@ -32,24 +33,52 @@ struct Fail {
   } while (0)
 
 // ---- device memory owned by the handle / a plan ---------------------------------------------
+// Slabs released by a finished attack are kept by the handle's pool and handed to the next one:
+// cudaFree / cudaMalloc of the 32 MiB slabs cost up to hundreds of ms per attack call otherwise.
+struct SlabPool {
+  std::vector<std::pair<void*, size_t>> free_slabs;
+  size_t held = 0;
+  static constexpr size_t kMaxHeld = 8ull << 30;   // beyond this, released slabs go back to the driver
+  void* take(size_t sz) {
+    for (size_t i = 0; i < free_slabs.size(); ++i)
+      if (free_slabs[i].second == sz) {
+        void* p = free_slabs[i].first;
+        free_slabs.erase(free_slabs.begin() + i);
+        held -= sz;
+        return p;
+      }
+    return nullptr;
+  }
+  void give(void* p, size_t sz) {
+    if (held + sz > kMaxHeld) { cudaFree(p); return; }
+    free_slabs.emplace_back(p, sz);
+    held += sz;
+  }
+  ~SlabPool() {
+    for (auto& s : free_slabs) cudaFree(s.first);
+  }
+};
+
 struct Arena {
   // bump allocator over zero-initialised slabs: one cudaMalloc per 32 MiB instead of one per tensor
   static constexpr size_t kSlab = 32u << 20;
-  std::vector<void*> slabs;
+  std::vector<std::pair<void*, size_t>> slabs;
+  SlabPool* pool = nullptr;
   char* cur = nullptr;
   size_t left = 0;
   size_t bytes = 0;
   Arena() = default;
+  explicit Arena(SlabPool* p) : pool(p) {}
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
   float* f(size_t n) {
     const size_t b = (n * sizeof(float) + 255) / 256 * 256;
     if (b > left) {
-      const size_t sz = b > kSlab ? b : kSlab;
-      void* p = nullptr;
-      CK(cudaMalloc(&p, sz));
+      const size_t sz = b > kSlab ? (b + kSlab - 1) / kSlab * kSlab : kSlab;
+      void* p = pool ? pool->take(sz) : nullptr;
+      if (!p) CK(cudaMalloc(&p, sz));
       CK(cudaMemset(p, 0, sz));
-      slabs.push_back(p);
+      slabs.emplace_back(p, sz);
       bytes += sz;
       if (b > kSlab) return static_cast<float*>(p);   // dedicated slab, keep the current one
       cur = static_cast<char*>(p);
@@ -70,7 +99,9 @@ struct Arena {
     return p;
   }
   ~Arena() {
-    for (void* p : slabs) cudaFree(p);
+    for (auto& s : slabs) {
+      if (pool) pool->give(s.first, s.second); else cudaFree(s.first);
+    }
   }
 };
 

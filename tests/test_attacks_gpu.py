@@ -101,9 +101,12 @@ def test_batch_sharding_invariance(engine, oracle):
     full = engine.attack("emb", x, at, 0.1, 10, w0=w0)
     inv = 1.0 / (4 * 128)
     parts = [engine.attack("emb", x[i:i + 2], at[i:i + 2], 0.1, 10, w0=w0[i:i + 2], inv_norm=inv) for i in (0, 2)]
-    assert torch.allclose(torch.cat(parts), full, rtol=0, atol=1e-7)
-    wrong = engine.attack("emb", x[:2], at[:2], 0.1, 10, w0=w0[:2])      # local normaliser: differs
-    assert not torch.allclose(wrong, full[:2], rtol=0, atol=1e-7)
+    # different batch sizes may take different tile shapes (summation order), so "equal" means fp32 noise
+    err = float((torch.cat(parts) - full).abs().max())
+    assert err < 5e-6, err
+    wrong = engine.attack("emb", x[:2], at[:2], 0.1, 10, w0=w0[:2])      # local normaliser: a different trajectory
+    err_wrong = float((wrong - full[:2]).abs().max())
+    assert err_wrong > 20 * max(err, 1e-7), (err, err_wrong)
 
 
 @pytest.mark.parametrize("kind,B,T,n", [("e2e", 1, 256, 20), ("fb", 8, 256, 3), ("emb", 32, 512, 3)])

@@ -35,27 +35,29 @@ CONV_CASES = [
 ] + [(2, 50, 80, 128, k, 1) for k in range(1, 9)]   # conv bank, even kernels pad asymmetrically
 
 
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES)
-def test_conv1d_fwd(engine, B, T, ci, co, k, s):
+def test_conv1d_fwd(engine, B, T, ci, co, k, s, impl):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k)
     x = torch.randn(B, T, ci, device="cuda", generator=g)
     w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
     b = torch.randn(co, device="cuda", generator=g)
-    y = engine.conv1d_fwd(x, w, b, stride=s, impl=1)
+    y = engine.conv1d_fwd(x, w, b, stride=s, impl=impl)
     ref = ref_conv(x.double(), w.double(), b.double(), s)
     assert y.shape == ref.shape
     assert rel_err(y, ref) < 2e-6
 
 
+@pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES)
-def test_conv1d_dgrad(engine, B, T, ci, co, k, s):
+def test_conv1d_dgrad(engine, B, T, ci, co, k, s, impl):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 7)
     x = torch.randn(B, T, ci, device="cuda", generator=g, dtype=torch.float64, requires_grad=True)
     w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
     y = ref_conv(x, w.double(), None, s)
     dy = torch.randn(y.shape, device="cuda", generator=g)
     (dx_ref,) = torch.autograd.grad(y, x, dy.double())
-    dx = engine.conv1d_dgrad(dy, w, T, stride=s, impl=1)
+    dx = engine.conv1d_dgrad(dy, w, T, stride=s, impl=impl)
     assert dx.shape == dx_ref.shape
     assert rel_err(dx, dx_ref) < 2e-6
 
@@ -121,10 +123,11 @@ def test_adam_tanh_step_matches_torch_adam(engine, step):
     wd, md, vd = w.cuda(), m.cuda(), v.cuda()
     adv_d = engine.adam_tanh_step(g_adv.cuda(), x.cuda(), wd, md, vd, eps, step)
     st = opt.state[wp]
-    assert torch.allclose(wd.cpu(), wp.detach(), rtol=0, atol=2e-7)
+    # one fp32 ulp of |w| (tanhf on CPU and GPU may differ in the last place)
+    assert torch.allclose(wd.cpu(), wp.detach(), rtol=3e-7, atol=1e-7)
     # m mixes two ~1e-8 terms of either sign: absolute tolerance at 1e-6 of that scale
     assert torch.allclose(md.cpu(), st["exp_avg"], rtol=1e-5, atol=1e-14)
     assert torch.allclose(vd.cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-22)
-    assert torch.allclose(adv_d.cpu(), ref_adv, rtol=0, atol=2e-7)
+    assert torch.allclose(adv_d.cpu(), ref_adv, rtol=3e-7, atol=1e-7)
     # the bound is exact on the perturbation term
     assert float((eps * wd.tanh()).abs().max()) <= eps
