@@ -72,6 +72,14 @@ __device__ __forceinline__ float4 res_load4(const ResArgs& r, int b, int t, int 
   }
 }
 
+// Programmatic dependent launch (see launch_k in engine.cu).  launch_dependents: the next kernel of the
+// stream may start its prologue now.  wait: block until every predecessor kernel has completed and its
+// writes are visible -- must precede the first read of anything a predecessor wrote and the first
+// write of anything a predecessor may still read.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(TXN* TYN) conv_simt_kernel(const ConvArgs p) {
   float* S = smem;                                         // [(win_rows + kMaxTaps)][kSRow]
   float* Wb = smem + (size_t)(p.win_rows + kMaxTaps) * kSRow;  // [2][kKSub][TN]
 
+  pdl_enter();
   const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
   const int tiles_t = (p.T_y + TM - 1) / TM;
   const int b = blockIdx.x / tiles_t, t0 = (blockIdx.x % tiles_t) * TM;
@@ -313,7 +314,9 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     }
     cp_async_commit();
   };
+  pdl_launch_dependents();
   for (int q = 0; q < p.ring - 1; ++q) issue(q);
+  pdl_wait();   // weights are loop constants; the windows below are the predecessor's output
 
   // ---- all activation windows -> smem (loads of all groups in flight together) -------------------
   for (int i = tid; i < kMaxTaps * kSRow; i += NT) S[zr * kSRow + i] = 0.f;

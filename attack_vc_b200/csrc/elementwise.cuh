@@ -12,6 +12,7 @@ namespace avc {
 // ---------------------------------------------------------------------------------------------
 __global__ void layout_in_kernel(const float* __restrict__ src, long long sb, long long sc, long long st,
                                  float* __restrict__ dst, long long d_bs, int d_rs, int B, int C, int T) {
+  pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n = (long long)B * T * C;
   if (i >= n) return;
@@ -24,6 +25,7 @@ __global__ void layout_in_kernel(const float* __restrict__ src, long long sb, lo
 __global__ void layout_out_kernel(const float* __restrict__ src, long long s_bs, int s_rs,
                                   float* __restrict__ dst, long long sb, long long sc, long long st,
                                   int B, int C, int T) {
+  pdl_enter();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n = (long long)B * T * C;
   if (i >= n) return;
@@ -67,6 +69,7 @@ __device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[4], int
 }
 
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
+  pdl_enter();
   __shared__ float4 red[kNormTL][4];
   const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
   const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
@@ -130,6 +133,7 @@ struct NormBwdArgs {
 };
 
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) {
+  pdl_enter();
   __shared__ float4 red[kNormTL][4];
   const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
   const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__
                                                        const float* __restrict__ org, float* __restrict__ g,
                                                        long long n4, float inv_norm, float* __restrict__ loss_parts,
                                                        const int* __restrict__ step, int parts_per_step) {
+  pdl_enter();
   __shared__ float wsum[8];
   float acc = 0.f;
   const float k = 2.f * inv_norm;
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(256) mse_grad_kernel(const float* __restrict__
 }
 
 __global__ void loss_sum_kernel(const float* __restrict__ parts, int parts_per_step, int n_iters, float* __restrict__ loss) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_iters) return;
   double s = 0.0;
@@ -239,6 +245,7 @@ struct UpdateArgs {
 };
 
 __global__ void __launch_bounds__(256) adam_tanh_update_kernel(const UpdateArgs p) {
+  pdl_enter();
   const int c4n = p.C >> 2;
   const long long n4 = (long long)p.B * p.T * c4n;
   const int step = *p.step;
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(256) adam_tanh_update_kernel(const UpdateArgs 
 // adv = x + eps*tanh(w) only (initial perturbation and final result, attack_utils.py:40,48)
 __global__ void perturb_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ adv,
                                long long adv_bs, int adv_rs, int B, int T, int C, float eps) {
+  pdl_enter();
   const int c4n = C >> 2;
   const long long n4 = (long long)B * T * c4n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -393,8 +401,10 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
     ++seq;
     __syncthreads();
   };
+  pdl_launch_dependents();
   issue(0);
   issue(1);
+  pdl_wait();   // weights are loop constants; everything below reads the predecessor's output
 
   if (p.mode & TAIL_FWD) {
     // global average pool over time
@@ -486,18 +496,24 @@ __global__ void __launch_bounds__(1024) affine_fwd_kernel(const AffineArgs p) {
   __shared__ float e[128];
   __shared__ float part[4][256];
   const int b = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, n = tid & 255, g = tid >> 8;
+  pdl_launch_dependents();
+  const float* M = p.Wt[l];
+  float wv[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) wv[q] = M[(g * 32 + q) * 256 + n];   // loop constants: fetched before the dependency wait
+  pdl_wait();
   if (tid < 128) e[tid] = p.emb[(long long)b * 128 + tid];
   __syncthreads();
-  const float* M = p.Wt[l];
   float a = 0.f;
-#pragma unroll 8
-  for (int q = 0; q < 32; ++q) { const int c = g * 32 + q; a = fmaf(M[c * 256 + n], e[c], a); }
+#pragma unroll
+  for (int q = 0; q < 32; ++q) a = fmaf(wv[q], e[g * 32 + q], a);
   part[g][n] = a;
   __syncthreads();
   if (tid < 256) p.cond[((long long)b * p.L + l) * 256 + n] = part[0][n] + part[1][n] + part[2][n] + part[3][n] + p.bias[l][n];
 }
 
 __global__ void __launch_bounds__(1024) affine_bwd_kernel(const AffineArgs p) {
+  pdl_enter();
   __shared__ float gc[256];
   __shared__ float part[8][128];
   const int b = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, c = tid & 127, g = tid >> 7;

@@ -29,6 +29,21 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Every kernel of the loop is launched with programmatic dependent launch (PDL): the next kernel's
+// CTAs may become resident while the previous kernel drains, run their data-independent prologue
+// (weight prefetch) and block in griddepcontrol.wait until the predecessor's memory is visible.
+bool g_pdl = getenv("AVC_NO_PDL") == nullptr;
+template <class... KArgs, class... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 // ---- packed weights ----------------------------------------------------------------------------
 struct ConvW {
   int c_in = 0, c_out = 0, k = 0, stride = 1;
@@ -128,8 +143,7 @@ void launch_conv_cfg(ConvArgs a, cudaStream_t st) {
   if (smem > 200 * 1024) fail(AVC_ERR_INVALID, "conv window needs %zu B of shared memory", smem);
   const int tiles_t = (a.T_y + TM - 1) / TM;
   dim3 grid(a.B * tiles_t, (a.N + TN - 1) / TN, a.zsplit ? a.n_groups : 1);
-  conv_simt_kernel<RM, TXN, TYN><<<grid, TXN * TYN, smem, st>>>(a);
-  CK(cudaGetLastError());
+  launch_k(conv_simt_kernel<RM, TXN, TYN>, grid, TXN * TYN, smem, st, a);
 }
 
 void init_kernel_attributes() {
@@ -174,8 +188,7 @@ bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
   if (smem > kSmemMax) return false;
   a.ring = ring;
   dim3 grid(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : 1);
-  conv_small_kernel<TM><<<grid, 32 * kSmWarps, smem, st>>>(a);
-  CK(cudaGetLastError());
+  launch_k(conv_small_kernel<TM>, grid, 32 * kSmWarps, smem, st, a);
   return true;
 }
 
@@ -306,7 +319,7 @@ void emit_norm_fwd(Emitter& E, const float* y, int B, int T, int C, const float*
   n.out = outp; n.res = res; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
   dim3 grid(B, C / kNormCh);
-  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid](cudaStream_t st) { norm_act_fwd_kernel<<<grid, 256, 0, st>>>(n); CK(cudaGetLastError()); });
+  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid](cudaStream_t st) { launch_k(norm_act_fwd_kernel, grid, 256, 0, st, n); });
 }
 
 void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stats, const float* cond, int cond_bs,
@@ -315,7 +328,7 @@ void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stat
   n.g = g; n.y = y; n.stats = stats; n.cond = cond; n.cond_bs = cond_bs; n.gy = gy; n.gcond = gcond; n.gcond_bs = gcond_bs;
   n.T = T; n.C = C; n.slope = slope;
   dim3 grid(B, C / kNormCh);
-  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid](cudaStream_t st) { norm_act_bwd_kernel<<<grid, 256, 0, st>>>(n); CK(cudaGetLastError()); });
+  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid](cudaStream_t st) { launch_k(norm_act_bwd_kernel, grid, 256, 0, st, n); });
 }
 
 // ---- encoder (speaker / content) ------------------------------------------------------------------
@@ -436,7 +449,7 @@ TailArgs tail_args(const EncoderW& W, const EncActs& A) {
 }
 
 void emit_tail(Emitter& E, const TailArgs& t, int B) {
-  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { se_tail_kernel<<<B, 1024, kTailSmem, st>>>(t); CK(cudaGetLastError()); });
+  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { launch_k(se_tail_kernel, B, 1024, kTailSmem, st, t); });
 }
 
 // speaker-encoder backward from gpool ([B,128], gradient of every pooled row) down to d input
@@ -553,7 +566,7 @@ void emit_decoder_fwd(Emitter& E, const DecoderW& W, const DecActs& A, const flo
   const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
   AffineArgs f = affine_args(W, A, emb);
   dim3 ag(A.B, L2);
-  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { affine_fwd_kernel<<<ag, 1024, 0, st>>>(f); CK(cudaGetLastError()); });
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { launch_k(affine_fwd_kernel, ag, 1024, 0, st, f); });
   for (int l = 0; l < A.nb; ++l) {
     const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
     if (l > 0) {
@@ -601,7 +614,7 @@ void emit_decoder_bwd(Emitter& E, const DecoderW& W, const DecActs& A, const Ten
   }
   AffineArgs f = affine_args(W, A, nullptr);
   dim3 ag(A.B, L2);
-  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { affine_bwd_kernel<<<ag, 1024, 0, st>>>(f); CK(cudaGetLastError()); });
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { launch_k(affine_bwd_kernel, ag, 1024, 0, st, f); });
 }
 
 // ---- misc launch helpers ------------------------------------------------------------------------------
@@ -610,8 +623,7 @@ void emit_layout_in(Emitter& E, const float* src, const int64_t s[3], const Tens
   const long long n = (long long)B * dst.T * C;
   const Tens d = dst;
   E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
-    layout_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, sb, sc, st_, d.p, d.bs, d.rs, B, C, d.T);
-    CK(cudaGetLastError());
+    launch_k(layout_in_kernel, (unsigned)((n + 255) / 256), 256, 0, st, src, sb, sc, st_, d.p, d.bs, d.rs, B, C, d.T);
   });
 }
 void emit_layout_out(Emitter& E, const Tens& src, float* dst, const int64_t s[3], int B, int C) {
@@ -619,8 +631,7 @@ void emit_layout_out(Emitter& E, const Tens& src, float* dst, const int64_t s[3]
   const long long n = (long long)B * src.T * C;
   const Tens d = src;
   E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
-    layout_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.p, d.bs, d.rs, dst, sb, sc, st_, B, C, d.T);
-    CK(cudaGetLastError());
+    launch_k(layout_out_kernel, (unsigned)((n + 255) / 256), 256, 0, st, d.p, d.bs, d.rs, dst, sb, sc, st_, B, C, d.T);
   });
 }
 void emit_copy(Emitter& E, float* dst, const float* src, size_t n) {
@@ -846,7 +857,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   };
   auto perturb = [&](Emitter& E) {
     const unsigned g = ew_grid((long long)nel / 4, h->sm_count);
-    E.push(LK_UPDATE, 0, 12.0 * nel, [=](cudaStream_t s_) { perturb_kernel<<<g, 256, 0, s_>>>(x, w, adv.p, adv.bs, adv.rs, B, T, C, eps); CK(cudaGetLastError()); });
+    E.push(LK_UPDATE, 0, 12.0 * nel, [=](cudaStream_t s_) { launch_k(perturb_kernel, g, 256, 0, s_, x, w, adv.p, adv.bs, adv.rs, B, T, C, eps); });
   };
   auto update = [&](Emitter& E, const Tens& gadv) {
     UpdateArgs u{};
@@ -854,7 +865,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     u.adv = adv.p; u.adv_bs = adv.bs; u.adv_rs = adv.rs; u.gw_out = gw; u.B = B; u.T = T; u.C = C; u.eps = eps;
     u.table = table; u.step = step; u.done = done;
     const unsigned g = ew_grid((long long)nel / 4, h->sm_count);
-    E.push(LK_UPDATE, 0, 36.0 * nel, [=](cudaStream_t s_) { adam_tanh_update_kernel<<<g, 256, 0, s_>>>(u); CK(cudaGetLastError()); });
+    E.push(LK_UPDATE, 0, 36.0 * nel, [=](cudaStream_t s_) { launch_k(adam_tanh_update_kernel, g, 256, 0, s_, u); });
   };
 
   if (kind == K_EMB) {
@@ -931,7 +942,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
       {
         const float invn = (float)inv_norm;
         float* lp = loss_parts; int* stp = step; const int pp = parts;
-        I.push(LK_LOSS, 0, 16.0 * nout, [=](cudaStream_t s_) { mse_grad_kernel<<<mg, 256, 0, s_>>>(dout, tgt, org, gout, n4, invn, lp, stp, pp); CK(cudaGetLastError()); });
+        I.push(LK_LOSS, 0, 16.0 * nout, [=](cudaStream_t s_) { launch_k(mse_grad_kernel, mg, 256, 0, s_, dout, tgt, org, gout, n4, invn, lp, stp, pp); });
       }
       emit_decoder_bwd(I, h->dec, dec, tens(gout, T_dec, Cm));
     } else {   // K_FB
@@ -978,7 +989,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   emit_layout_out(F, adv, a->adv_out, a->out_stride, B, C);
   if (a->loss_out && n_iters > 0) {
     float* lp = loss_parts; float* lo = a->loss_out; const int pp = parts;
-    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) { loss_sum_kernel<<<(n_iters + 127) / 128, 128, 0, s_>>>(lp, pp, n_iters, lo); CK(cudaGetLastError()); });
+    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) { launch_k(loss_sum_kernel, (n_iters + 127) / 128, 128, 0, s_, lp, pp, n_iters, lo); });
   }
   if (a->grad_out && n_iters > 0) {
     const int64_t cs[3] = {(int64_t)C * T, (int64_t)T, 1};
@@ -1397,8 +1408,7 @@ int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float*
     u.step = tmp.raw<int>(1);
     u.done = nullptr;
     const unsigned g = ew_grid(n / 4, h->sm_count);
-    adam_tanh_update_kernel<<<g, 256, 0, st>>>(u);
-    CK(cudaGetLastError());
+    launch_k(adam_tanh_update_kernel, g, 256, 0, st, u);
     h->launches += 1;
     CK(cudaStreamSynchronize(st));
   });
