@@ -1,6 +1,36 @@
-// conv_tc.cuh -- tcgen05 / TMEM implicit-GEMM Conv1d (3xTF32 split, fp32 accumulate).  STUB: the
-// tensor-core path is not wired yet; every conv runs on the exact-fp32 SIMT kernel.
+// conv_tc.cuh -- tcgen05 / TMEM implicit-GEMM Conv1d for large M (batched attacks), sm_100a only.
+//
+// Same contraction as conv_simt.cuh (reference pad_layer + nn.Conv1d, models.py:10-30, and its
+// autograd w.r.t. the input), on the 5th-generation tensor cores:
+//
+//   * precision: 3xTF32 split  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulation in TMEM.
+//     One TF32 pass misses the 1e-3 gradient tolerance by 20x, the split is ~2^-21.
+//   * M axis = "virtual rows": utterances laid end to end with a fixed spacing Pv >= valid rows +
+//     taps - 1, so that a conv tap is a pure row shift of ONE shared-memory window even when a
+//     128-row tile spans several (short) utterances.  Rows past an utterance's valid range are dead.
+//   * A operand: loader warps gather the window from global memory (reflect padding / zero padding
+//     and the optional act' mask by index arithmetic), split every value into its TF32 hi / lo parts
+//     and store both planes in the UMMA "interleaved" (no-swizzle, K-major) canonical layout
+//     [k/4][row][4 floats]: core matrices of consecutive 8-row groups are contiguous (SBO = 128 B),
+//     so tap j is the SAME buffer with the descriptor start address advanced by j*16 bytes.
+//   * B operand: weights pre-split and pre-tiled on the host in exactly the shared-memory image of
+//     one (K-block, tap) stage, streamed by one elected thread with cp.async.bulk (TMA engine,
+//     mbarrier complete_tx) through a ring.
+//   * one elected thread issues tcgen05.mma (kind::tf32, M=128, N <= 128); tcgen05.commit frees the
+//     ring slots and signals the drain warps.
+//   * accumulation is CHUNKED: the tensor core accumulates fp32 with truncation, a bias that grows
+//     linearly with the number of MMA steps (measured: -8e-8 relative per K=8 step, 3.3e-6 at K=640).
+//     So every ~20 steps the accumulator (ping-pong halves of TMEM) is handed to eight drain warps,
+//     which add it into fp32 registers with round-to-nearest (tcgen05.ld), and finally apply bias /
+//     act' mask / activation / residual exactly like the CUDA-core kernel.
+//   * dgrad: the transposed conv is evaluated on the EXTENDED row range [-pl, T+pr); the rows outside
+//     [0,T) (gradient of the reflect padding) go to a small side buffer and `tc_fold_kernel` adds them
+//     to their mirror rows -- no atomics, fixed order.
+//
+//   * strided convs: forward = one group per tap residue (parity planes of the input); dgrad = one
+//     pass per output residue.  N > 128 (decoder up-convs, in-conv dgrad) = one pass per 128 columns.
 #pragma once
+#include <cstdint>
 #include <vector>
 
 #include "conv_simt.cuh"
@@ -8,17 +38,519 @@
 
 namespace avc {
 
-struct TcPack {
+constexpr int kTcM = 128;          // rows of one UMMA / one CTA tile
+constexpr int kTcRows = 136;       // window rows per A stage (128 + kMaxTaps)
+constexpr int kTcKB = 32;          // channels per K block (4 UMMA k-steps of 8)
+constexpr int kTcAStages = 2;
+constexpr int kTcBStages = 3;
+constexpr int kTcNMax = 128;       // columns of one pass
+constexpr int kTcThreads = 448;    // warp 0: TMEM + weight producer, 1: MMA issuer, 2-5: loaders, 6-13: drain + epilogue
+constexpr int kTcAPlane = (kTcKB / 4) * kTcRows * 4;   // floats of one hi (or lo) plane of an A stage
+constexpr int kTcChunkSteps = 16;  // MMA k-steps accumulated in TMEM before the drain warps take over
+constexpr int kTcMaxChunks = 12;   // N chunks of one packed conv (1104 = 8 x 128 + 80)
+constexpr int kTcMaxPass = 12;
+
+struct TcPack {                    // weights of ONE conv direction / tap subset, device memory
   bool ok = false;
-  float* img = nullptr;
-  int k = 0, kc = 0, n = 0;
+  int k = 0, kc = 0, n = 0, n_chunks = 0;
+  float* blocks[kTcMaxChunks] = {};   // per N chunk: [kb][tap][plane hi|lo][k/4][cn][4]
+  int cn[kTcMaxChunks] = {};
 };
 
-inline void tc_pack_conv(Arena&, TcPack& p, const std::vector<float>&, int k, int kc, int n) {
-  p.ok = false; p.k = k; p.kc = kc; p.n = n;
+struct TcGroup {
+  const float* Wp;                 // packed blocks of this group (for this pass's N chunk)
+  int a_ch_off, kc, n_taps;
+  int sg, off0;                    // input position of window row u:  sg*u + off0
+};
+
+struct TcPass {
+  int g_begin, g_end;              // groups accumulated by this pass
+  int N, ch_off;                   // columns of this pass and where they go in the output row
+  int so, oo;                      // output index of virtual row u:  so*u + oo
+};
+
+struct TcArgs {
+  const float* A; long long a_bs; int a_rs; int T_a;
+  const float* Mk; long long m_bs; int m_rs; float slope;
+  int bwd;               // 0: reflect gather (forward), 1: zero-padded gather (dgrad)
+  int Pv;                // virtual rows per utterance
+  int T_y;               // main output rows per utterance
+  int halo_l, halo_r;    // dgrad: rows kept on each side for the reflect-pad fold
+  int B; long long Mv;   // B * Pv
+  int side_n;            // columns of one side-buffer row (the whole output width)
+  float* Y; long long y_bs; int y_rs;
+  float* Y2; long long y2_bs; int y2_rs;
+  const float* bias; int act;
+  const float* Om; long long om_bs; int om_rs;
+  ResArgs res;
+  float* side;           // [B][halo_l + halo_r][side_n]
+  int n_pass;
+  int terms;             // 3: 3xTF32 (product), 1: single TF32 pass, 4: + lo*lo (both measurement only)
+  TcPass pass[kTcMaxPass];
+  TcGroup g[kTcMaxPass];
+};
+
+// ---- host: weight packing ----------------------------------------------------------------------
+inline float tf32_hi_host(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xffffe000u;   // round to 10 mantissa bits (ties away), same as the device split
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
 }
-inline bool tc_eligible(const ConvArgs&, const TcPack&, bool) { return false; }
-inline void tc_init_attributes() {}
-inline void launch_conv_tc(const ConvArgs&, const TcPack&, int, cudaStream_t) {}
+
+// img: [k_img][kc][n] (n contiguous) -- the forward or dgrad image pack_conv builds for the CUDA-core
+// path; taps: which taps of the image, in window order, this pack contracts.
+inline void tc_pack_taps(Arena& mem, TcPack& p, const std::vector<float>& img, int kc, int n, const std::vector<int>& taps) {
+  const int k = (int)taps.size();
+  p.ok = false; p.k = k; p.kc = kc; p.n = n; p.n_chunks = 0;
+  if (kc % 8 || n % 8 || k < 1 || k > kMaxTaps) return;
+  const int nch = (n + kTcNMax - 1) / kTcNMax;
+  if (nch > kTcMaxChunks) return;
+  for (int ch = 0; ch < nch; ++ch) {
+    const int cn = std::min(kTcNMax, n - ch * kTcNMax);
+    if (cn != 128 && cn != 80) return;   // drain warps are instantiated for 64 / 40 columns per thread
+  }
+  const int nkb = (kc + kTcKB - 1) / kTcKB;
+  for (int ch = 0; ch < nch; ++ch) {
+    const int n0 = ch * kTcNMax, cn = std::min(kTcNMax, n - n0);
+    std::vector<float> out((size_t)2 * k * kc * cn);
+    size_t o = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int kb0 = kb * kTcKB, kbs = std::min(kTcKB, kc - kb0);
+      for (int t = 0; t < k; ++t)
+        for (int plane = 0; plane < 2; ++plane)
+          for (int c = 0; c < kbs / 4; ++c)
+            for (int nn = 0; nn < cn; ++nn)
+              for (int e = 0; e < 4; ++e) {
+                const float v = img[((size_t)taps[t] * kc + kb0 + 4 * c + e) * n + n0 + nn];
+                const float hi = tf32_hi_host(v);
+                out[o++] = plane == 0 ? hi : tf32_hi_host(v - hi);   // lo pre-rounded (RN): the MMA would truncate it
+              }
+    }
+    p.blocks[ch] = mem.upload(out);
+    p.cn[ch] = cn;
+  }
+  p.n_chunks = nch;
+  p.ok = true;
+}
+
+// ---- device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap, not hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle ("interleaved") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14), LBO>>4 [16,30) = bytes between the two 16-byte K chunks of one MMA,
+// SBO>>4 [32,46) = bytes between consecutive 8-row core matrices, version 1 at [46,48), layout 0.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ float tf32_hi(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// K blocks are visited in (group, kb) order by all roles; a chunk closes after the K block that
+// brings it to kTcChunkSteps MMA k-steps, and after the last K block of the pass.
+struct TcWalk {
+  int gi, kb, nkb, steps;
+  __device__ TcWalk(const TcArgs& p, const TcPass& ps) : gi(ps.g_begin), kb(0), steps(0) { nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB; }
+  // advance past the current K block; returns true when the chunk it belongs to is complete
+  __device__ bool next(const TcArgs& p, const TcPass& ps, bool& done) {
+    const TcGroup& G = p.g[gi];
+    steps += G.n_taps * (min(kTcKB, G.kc - kb * kTcKB) / 8);
+    if (++kb == nkb) {
+      kb = 0;
+      if (++gi < ps.g_end) nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB;
+    }
+    done = gi >= ps.g_end;
+    if (done || steps >= kTcChunkSteps) { steps = 0; return true; }
+    return false;
+  }
+};
+
+template <int NH>   // columns per drain thread (half of the pass width): 64 or 40
+__device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
+                                                   uint32_t acc_empty0, long long v0, int warp, int lane) {
+  const int quad = warp & 3;                    // TMEM lanes this warp may read: [32*quad, 32*quad+32)
+  const int half = (warp - 6) >> 2;             // which half of the columns
+  float acc[NH];
+#pragma unroll
+  for (int i = 0; i < NH; ++i) acc[i] = 0.f;
+  TcWalk w(p, ps);
+  bool done = false;
+  int chunk = 0;
+  while (!done) {
+    if (!w.next(p, ps, done)) continue;
+    const int buf = chunk & 1;
+    mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+    tc_fence_after();
+    const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kTcNMax + half * NH);
+#pragma unroll
+    for (int c0 = 0; c0 < NH; c0 += 8) {
+      uint32_t r[8];
+      tmem_ld8(t0 + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);     // round-to-nearest fp32 adds
+    }
+    tc_fence_before();
+    mbar_arrive(acc_empty0 + 8 * buf);
+    ++chunk;
+  }
+  // ---- epilogue: bias / mask / act / residual -> global ----
+  const int row = quad * 32 + lane;
+  const long long u = v0 + row;
+  const int b = (int)(u / p.Pv);
+  const int o = ps.so * (int)(u - (long long)b * p.Pv) + ps.oo;   // output index inside the utterance
+  const bool main_row = b < p.B && o >= 0 && o < p.T_y;
+  int hrow = -1;                                                    // side-buffer row (dgrad halo)
+  if (b < p.B && p.side) {
+    if (o < 0 && o >= -p.halo_l) hrow = o + p.halo_l;
+    else if (o >= p.T_y && o < p.T_y + p.halo_r) hrow = p.halo_l + (o - p.T_y);
+  }
+  const int chb = ps.ch_off + half * NH;
+  if (main_row) {
+#pragma unroll
+    for (int q = 0; q < NH / 4; ++q) {
+      const int ch = chb + 4 * q;
+      float4 x = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      if (p.bias) x = f4add(x, ld4(p.bias + ch));
+      if (p.Om) x = dact4mul(x, ld4(p.Om + (long long)b * p.om_bs + (long long)o * p.om_rs + ch), p.slope);
+      if (p.act) x = act4(x, p.slope);
+      if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)o * p.y2_rs + ch, x);
+      if (p.res.mode != RES_NONE) x = f4add(x, res_load4(p.res, b, o, p.T_y, ch));
+      st4(p.Y + (long long)b * p.y_bs + (long long)o * p.y_rs + ch, x);
+    }
+  } else if (hrow >= 0) {
+    float* sd = p.side + ((long long)b * (p.halo_l + p.halo_r) + hrow) * p.side_n + chb;
+#pragma unroll
+    for (int q = 0; q < NH / 4; ++q) st4(sd + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TcPass& ps = p.pass[blockIdx.z];
+  const int N = ps.N;
+  constexpr uint32_t b_stage_bytes = 2 * (kTcKB / 4) * kTcNMax * 16;                // hi + lo plane of a full weight stage
+  float* As = reinterpret_cast<float*>(tc_smem);                                     // [kTcAStages][2][kTcAPlane]
+  unsigned char* Bs = tc_smem + (size_t)kTcAStages * 2 * kTcAPlane * 4;              // [kTcBStages][b_stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)kTcBStages * b_stage_bytes);
+  // bars: a_full[2] a_empty[2] b_full[4] b_empty[4] acc_full[2] acc_empty[2]
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8 * s; };
+  auto a_empty = [&](int s) { return bar0 + 8 * (2 + s); };
+  auto b_full = [&](int s) { return bar0 + 8 * (4 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8 * (8 + s); };
+  const uint32_t acc_full0 = bar0 + 8 * 12, acc_empty0 = bar0 + 8 * 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  constexpr uint32_t tmem_cols = 2 * kTcNMax;     // two accumulators, ping-pong
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  const long long v0 = (long long)blockIdx.x * kTcM;
+
+  if (warp == 0) {
+    // ===== weight producer: one elected lane streams (K block, tap) stages with the TMA engine =====
+    if (lane == 0) {
+      int sb = 0; uint32_t pb = 0;
+      for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
+        const TcGroup& G = p.g[gi];
+        const int nkb = (G.kc + kTcKB - 1) / kTcKB;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int kbs = min(kTcKB, G.kc - kb * kTcKB);
+          const uint32_t bytes = 2u * kbs * N * 4u;
+          const float* src = G.Wp + (size_t)kb * G.n_taps * 2 * kTcKB * N;
+          for (int tap = 0; tap < G.n_taps; ++tap) {
+            mbar_wait(b_empty(sb), pb ^ 1);
+            mbar_expect_tx(b_full(sb), bytes);
+            bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src + (size_t)tap * 2 * kbs * N, bytes, b_full(sb));
+            if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+      const uint32_t a_lbo = kTcRows * 16, b_lbo = (uint32_t)N * 16;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      TcWalk w(p, ps);
+      bool done = false;
+      int chunk = 0;
+      uint32_t acc = 0;
+      bool fresh = true;           // first K block of a chunk: wait for the drain warps to release the buffer
+      while (!done) {
+        const TcGroup& G = p.g[w.gi];
+        const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
+        const int buf = chunk & 1;
+        if (fresh) {
+          mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);
+          tc_fence_after();
+          acc = 0; fresh = false;
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
+        mbar_wait(a_full(sa), pa);
+        const uint32_t a_hi = smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lo = a_hi + kTcAPlane * 4;
+        for (int tap = 0; tap < G.n_taps; ++tap) {
+          mbar_wait(b_full(sb), pb);
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(Bs + (size_t)sb * b_stage_bytes), b_lo = b_hi + (uint32_t)(kbs / 4) * N * 16;
+          for (int ks = 0; ks < kbs / 8; ++ks) {
+            const uint32_t ao = tap * 16 + ks * 2 * a_lbo, bo = ks * 2 * b_lbo;
+            const uint64_t dah = tc_desc(a_hi + ao, a_lbo, 128), dal = tc_desc(a_lo + ao, a_lbo, 128);
+            const uint64_t dbh = tc_desc(b_hi + bo, b_lbo, 128), dbl = tc_desc(b_lo + bo, b_lbo, 128);
+            tc_mma_tf32(d_tmem, dah, dbh, idesc, acc);
+            acc = 1;
+            if (p.terms >= 3) {
+              tc_mma_tf32(d_tmem, dal, dbh, idesc, 1);
+              tc_mma_tf32(d_tmem, dah, dbl, idesc, 1);
+            }
+            if (p.terms >= 4) tc_mma_tf32(d_tmem, dal, dbl, idesc, 1);
+          }
+          tc_commit(b_empty(sb));
+          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+        }
+        tc_commit(a_empty(sa));
+        if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+        if (w.next(p, ps, done)) {
+          tc_commit(acc_full0 + 8 * buf);
+          ++chunk; fresh = true;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== loaders (128 threads): window gather + TF32 split =====
+    pdl_wait();
+    const int tl = threadIdx.x - 64;   // 0..127
+    int sa = 0; uint32_t pa = 0;
+    for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
+      const TcGroup& G = p.g[gi];
+      const int nrows = kTcM + G.n_taps - 1;
+      // source rows of my (up to two) window rows
+      const float* src[2]; const float* msk[2]; bool have[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = tl + j * kTcM;
+        have[j] = i < nrows;
+        src[j] = nullptr; msk[j] = nullptr;
+        if (have[j]) {
+          const long long u = v0 + i;
+          const int b = (int)(u / p.Pv);
+          const int pos = G.sg * (int)(u - (long long)b * p.Pv) + G.off0;
+          int rr = pos;
+          if (!p.bwd) {
+            rr = rr < 0 ? -rr : rr;
+            if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
+          }
+          if (b < p.B && rr >= 0 && rr < p.T_a) {
+            src[j] = p.A + (long long)b * p.a_bs + (long long)rr * p.a_rs + G.a_ch_off;
+            if (p.Mk) msk[j] = p.Mk + (long long)b * p.m_bs + (long long)rr * p.m_rs + G.a_ch_off;
+          }
+        }
+      }
+      const int nkb = (G.kc + kTcKB - 1) / kTcKB;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = kb * kTcKB, kbs = min(kTcKB, G.kc - kb0);
+        mbar_wait(a_empty(sa), pa ^ 1);
+        float* hi = As + (size_t)sa * 2 * kTcAPlane;
+        float* lo = hi + kTcAPlane;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (!have[j]) continue;
+          const int i = tl + j * kTcM;
+          float4 v[kTcKB / 4];
+#pragma unroll
+          for (int c = 0; c < kTcKB / 4; ++c) v[c] = (src[j] && 4 * c < kbs) ? ld4(src[j] + kb0 + 4 * c) : f4zero();
+          if (msk[j]) {
+#pragma unroll
+            for (int c = 0; c < kTcKB / 4; ++c)
+              if (4 * c < kbs) v[c] = dact4mul(v[c], ld4(msk[j] + kb0 + 4 * c), p.slope);
+          }
+#pragma unroll
+          for (int c = 0; c < kTcKB / 4; ++c) {
+            if (4 * c >= kbs) break;
+            const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
+            st4(hi + ((size_t)c * kTcRows + i) * 4, h);
+            st4(lo + ((size_t)c * kTcRows + i) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full(sa));
+        if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    // ===== drain warps (256 threads): chunk sums in registers, then the epilogue =====
+    pdl_wait();
+    if (N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane);
+    else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// dgrad: add the extended rows (gradient of the reflect padding) to their mirror rows.
+//   row r' in [1, PL]        += side[PL - r']
+//   row r' in [T-1-PR, T-2]  += side[PL + T - 2 - r']          (both scaled by act'(Om) like the main rows)
+__global__ void tc_fold_kernel(float* __restrict__ Y, long long y_bs, int y_rs, const float* __restrict__ side,
+                               const float* __restrict__ Om, long long om_bs, int om_rs, float slope,
+                               int B, int T, int N, int PL, int PR) {
+  pdl_enter();
+  const int n4 = N >> 2, H = PL + PR;
+  const long long tot = (long long)B * H * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % n4) << 2;
+    const long long bj = i / n4;
+    const int j = (int)(bj % H), b = (int)(bj / H);
+    const int r = j < PL ? j + 1 : T - 1 - PR + (j - PL);
+    if (r < 0 || r >= T) continue;
+    if (j >= PL && r >= 1 && r <= PL) continue;                 // the left-edge thread of this row adds both parts
+    const float* sb = side + (long long)b * H * N + c;
+    float4 a = f4zero();
+    if (r >= 1 && r <= PL) a = f4add(a, ld4(sb + (long long)(PL - r) * N));
+    if (r >= T - 1 - PR && r <= T - 2) a = f4add(a, ld4(sb + (long long)(PL + T - 2 - r) * N));
+    if (Om) a = dact4mul(a, ld4(Om + (long long)b * om_bs + (long long)r * om_rs + c), slope);
+    float* y = Y + (long long)b * y_bs + (long long)r * y_rs + c;
+    st4(y, f4add(ld4(y), a));
+  }
+}
+
+inline size_t tc_smem_bytes() {
+  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 16 * 8 + 16;
+}
+
+// ---- host: the tensor-core view of one conv launch (passes x groups, no tensor pointers yet) --------
+struct TcOp {
+  int n_pass = 0, n_groups = 0;
+  int kmax = 1;          // most taps of any group
+  int sdiv = 1;          // dgrad: virtual rows advance sdiv output rows (conv stride)
+  int n_out = 0;         // total output columns
+  TcPass pass[kTcMaxPass];
+  TcGroup g[kTcMaxPass];
+  bool add_pass(int g_begin, int g_end, int N, int ch_off, int so, int oo) {
+    if (n_pass >= kTcMaxPass) return false;
+    pass[n_pass++] = TcPass{g_begin, g_end, N, ch_off, so, oo};
+    return true;
+  }
+  int add_group(const float* Wp, int a_ch_off, int kc, int n_taps, int sg, int off0) {
+    if (n_groups >= kTcMaxPass) return -1;
+    g[n_groups] = TcGroup{Wp, a_ch_off, kc, n_taps, sg, off0};
+    kmax = std::max(kmax, n_taps);
+    return n_groups++;
+  }
+};
+
+inline bool tc_supported(const ConvArgs& a, const TcOp& op) {
+  if (op.n_pass <= 0 || op.n_groups <= 0) return false;
+  if (a.Y2 && a.bwd) return false;
+  for (int g = 0; g < op.n_groups; ++g)
+    if (!op.g[g].Wp || op.g[g].kc % 8 || op.g[g].a_ch_off % 4 || op.g[g].n_taps < 1 || op.g[g].n_taps > kMaxTaps) return false;
+  for (int q = 0; q < op.n_pass; ++q)
+    if (op.pass[q].N != 128 && op.pass[q].N != 80) return false;
+  if (a.a_rs % 4 || (a.Mk && a.m_rs % 4)) return false;
+  return true;
+}
+
+inline void tc_halo(const ConvArgs& a, int& PL, int& PR) {
+  PL = PR = 0;
+  if (a.bwd) for (int g = 0; g < a.n_groups; ++g) { PL = std::max(PL, a.g[g].pl); PR = std::max(PR, a.g[g].pr); }
+}
+
+// side: scratch of tc_side_floats(a) floats for dgrad (nullptr for forward)
+inline size_t tc_side_floats(const ConvArgs& a) {
+  int PL, PR;
+  tc_halo(a, PL, PR);
+  return (size_t)a.B * (PL + PR) * a.N;
+}
+
+inline TcArgs tc_make_args(const ConvArgs& a, const TcOp& op, float* side, int terms) {
+  TcArgs t{};
+  t.A = a.A; t.a_bs = a.a_bs; t.a_rs = a.a_rs; t.T_a = a.T_a;
+  t.Mk = a.Mk; t.m_bs = a.m_bs; t.m_rs = a.m_rs; t.slope = a.slope;
+  t.bwd = a.bwd;
+  int PL, PR;
+  tc_halo(a, PL, PR);
+  t.T_y = a.T_y; t.halo_l = PL; t.halo_r = PR;
+  const int n_valid = a.bwd ? (a.T_y + PL + PR + op.sdiv - 1) / op.sdiv : a.T_y;
+  t.Pv = n_valid + op.kmax - 1;
+  t.B = a.B; t.Mv = (long long)a.B * t.Pv;
+  t.side_n = a.N;
+  t.Y = a.Y; t.y_bs = a.y_bs; t.y_rs = a.y_rs;
+  t.Y2 = a.Y2; t.y2_bs = a.y2_bs; t.y2_rs = a.y2_rs;
+  t.bias = a.bias; t.act = a.act;
+  t.Om = a.Om; t.om_bs = a.om_bs; t.om_rs = a.om_rs;
+  t.res = a.res;
+  t.side = (PL + PR) > 0 ? side : nullptr;
+  t.n_pass = op.n_pass;
+  t.terms = terms;
+  for (int q = 0; q < op.n_pass; ++q) t.pass[q] = op.pass[q];
+  for (int g = 0; g < op.n_groups; ++g) t.g[g] = op.g[g];
+  return t;
+}
 
 }  // namespace avc

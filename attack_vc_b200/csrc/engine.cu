@@ -50,10 +50,57 @@ struct ConvW {
   float* fwd = nullptr;   // [k][c_in][c_out']      c_out' = pixel-shuffle-permuted output channel
   float* bwd = nullptr;   // [k reversed][c_out'][c_in]
   float* bias = nullptr;  // [c_out']
-  TcPack tc_fwd, tc_bwd;  // tcgen05 operand images (conv_tc.cuh); empty when not eligible
+  TcPack tc_fwd[4], tc_bwd[4];  // tcgen05 operand images per tap residue mod stride (conv_tc.cuh); !ok when not eligible
   int pl() const { return k / 2; }
   int pr() const { return (k % 2) ? k / 2 : k / 2 - 1; }
 };
+
+
+// Tensor-core view of one plain Conv1d (any stride), forward or dgrad -- see conv_tc.cuh.
+//   forward: one group per tap residue e (taps j = s*i + e read input position s*(t+i) + e - pl)
+//   dgrad:   one pass per output residue e (rows p = s*u + e of the padded gradient use taps j = s*i + e)
+// N > 128 is split into passes of 128 columns.
+TcOp tc_op_conv(const ConvW& w, bool bwd) {
+  TcOp op;
+  const int s = w.stride;
+  if (s > 4) return TcOp{};
+  if (!bwd) {
+    op.n_out = w.c_out;
+    for (int e = 0; e < s && e < w.k; ++e) if (!w.tc_fwd[e].ok) return TcOp{};
+    const int nch = w.tc_fwd[0].n_chunks;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int g0 = op.n_groups;
+      for (int e = 0; e < s && e < w.k; ++e)
+        if (op.add_group(w.tc_fwd[e].blocks[ch], 0, w.c_in, w.tc_fwd[e].k, s, e - w.pl()) < 0) return TcOp{};
+      if (!op.add_pass(g0, op.n_groups, w.tc_fwd[0].cn[ch], ch * kTcNMax, 1, 0)) return TcOp{};
+    }
+  } else {
+    op.n_out = w.c_in;
+    op.sdiv = s;
+    for (int e = 0; e < s && e < w.k; ++e) if (!w.tc_bwd[e].ok) return TcOp{};
+    const int nch = w.tc_bwd[0].n_chunks;
+    for (int e = 0; e < s && e < w.k; ++e)
+      for (int ch = 0; ch < nch; ++ch) {
+        const int g0 = op.add_group(w.tc_bwd[e].blocks[ch], 0, w.c_out, w.tc_bwd[e].k, 1, -(w.tc_bwd[e].k - 1));
+        if (g0 < 0 || !op.add_pass(g0, g0 + 1, w.tc_bwd[e].cn[ch], ch * kTcNMax, s, e - w.pl())) return TcOp{};
+      }
+  }
+  return op;
+}
+
+
+// f: forward image [k][c_in][c_out'], r: dgrad image [k reversed][c_out'][c_in] (pack_conv)
+void tc_pack_both(Arena& mem, ConvW& c, const std::vector<float>& f, const std::vector<float>& r) {
+  const int s = c.stride, k = c.k;
+  for (int e = 0; e < s && e < k && e < 4; ++e) {
+    std::vector<int> ft, bt;
+    for (int j = e; j < k; j += s) ft.push_back(j);                 // window order = ascending tap
+    const int ne = (int)ft.size();
+    for (int tp = 0; tp < ne; ++tp) bt.push_back(k - 1 - (s * (ne - 1 - tp) + e));   // image index of W_j^T, j = s*(ne-1-tp)+e
+    tc_pack_taps(mem, c.tc_fwd[e], f, c.c_in, c.c_out, ft);
+    tc_pack_taps(mem, c.tc_bwd[e], r, c.c_out, c.c_in, bt);
+  }
+}
 
 struct EncoderW {
   avc_encoder_desc d{};
@@ -120,7 +167,8 @@ struct avc_handle {
   std::string err;
   long long launches = 0;
   int launches_per_iter = 0;
-  int conv_impl = 0;   // 0 auto, 1 simt, 2 tcgen05 (env AVC_CONV_IMPL overrides)
+  int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only)
+  long long tc_min_rows = 2048;   // auto: GEMM rows from which the tensor-core kernel is used (env AVC_TC_MIN_ROWS)
 };
 
 struct avc_session {
@@ -153,7 +201,7 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(conv_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
-  tc_init_attributes();
+  CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
 }
 
 // small-M path: every window resident, deep weight ring (conv_simt.cuh: conv_small_kernel)
@@ -207,14 +255,29 @@ void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st, bool all
   launch_conv_cfg<1, 8, 16>(a, st);
 }
 
-void launch_conv(avc_handle* h, const ConvArgs& a, const TcPack* tc, cudaStream_t st) {
-  int impl = h->conv_impl;
-  if (impl != 1 && impl != 3 && tc && tc->ok && tc_eligible(a, *tc, impl == 2)) {
-    launch_conv_tc(a, *tc, h->sm_count, st);
-    return;
-  }
-  if (impl == 2 && tc == nullptr) { /* no tensor-core image for this op: fp32 path */ }
-  launch_conv_simt(a, h->sm_count, st, impl != 3);
+void launch_conv(avc_handle* h, const ConvArgs& a, cudaStream_t st) {
+  launch_conv_simt(a, h->sm_count, st, h->conv_impl != 3);
+}
+
+// tensor-core route: decided when the plan is built (the dgrad side buffer comes from the plan's arena)
+bool want_tc(const avc_handle* h, const ConvArgs& a, const TcOp& op) {
+  const int impl = h->conv_impl;
+  if (impl == 1 || impl == 3) return false;
+  if (!tc_supported(a, op)) return false;
+  if (impl == 2 || impl == 4 || impl == 5) return true;
+  return (long long)a.B * (a.T_y + op.kmax - 1) >= h->tc_min_rows;
+}
+
+void launch_conv_tc(const TcArgs& t, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes();
+  dim3 grid((unsigned)((t.Mv + kTcM - 1) / kTcM), 1, t.n_pass);
+  launch_k(conv_tc_kernel, grid, kTcThreads, smem, st, t);
+}
+
+void launch_tc_fold(const TcArgs& t, int sm_count, cudaStream_t st) {
+  const long long n = (long long)t.B * (t.halo_l + t.halo_r) * (t.side_n / 4);
+  const unsigned g = (unsigned)std::max(1LL, std::min((n + 255) / 256, (long long)sm_count * 4));
+  launch_k(tc_fold_kernel, g, 256, 0, st, t.Y, t.y_bs, t.y_rs, (const float*)t.side, t.Om, t.om_bs, t.om_rs, t.slope, t.B, t.T_y, t.side_n, t.halo_l, t.halo_r);
 }
 
 // fill the channel groups of a plain Conv1d (forward) -- K split into <=128-channel groups
@@ -268,19 +331,34 @@ int cdiv(int a, int b) { return (a + b - 1) / b; }
 struct Emitter {
   avc_handle* h;
   std::vector<Launch>* out;
-  void conv(const ConvArgs& a, const TcPack* tc = nullptr) {
+  Arena* mem;   // scratch that must outlive the launches (dgrad side buffers of the tensor-core path)
+  void conv(const ConvArgs& a, const ConvW* cw = nullptr, const TcOp* multi = nullptr) {
     avc_handle* hh = h;
     ConvArgs ac = a;
-    TcPack tcc = tc ? *tc : TcPack{};
-    bool have = tc != nullptr;
     double macs = 0;
     const int g_n = ac.n_groups;
     for (int g = 0; g < g_n; ++g) macs += (double)ac.g[g].kc * ac.g[g].n_taps;
     macs *= (double)ac.B * ac.T_y * ac.N / (ac.bwd ? ac.s : 1);
     const double bytes = 4.0 * ac.B * ((double)ac.T_a * ac.g[0].kc * (ac.zsplit ? 1 : g_n) + (double)ac.T_y * ac.N * (ac.zsplit ? g_n : 1));
     Launch l;
-    l.fn = [hh, ac, tcc, have](cudaStream_t st) { launch_conv(hh, ac, have ? &tcc : nullptr, st); };
     l.kind = LK_CONV; l.flops = 2.0 * macs; l.bytes = bytes;
+    TcOp op = multi ? *multi : (cw ? tc_op_conv(*cw, ac.bwd != 0) : TcOp{});
+    if (want_tc(hh, ac, op)) {
+      const size_t side_n = tc_side_floats(ac);
+      float* side = side_n ? mem->f(side_n) : nullptr;
+      const TcArgs t = tc_make_args(ac, op, side, hh->conv_impl == 4 ? 1 : hh->conv_impl == 5 ? 4 : 3);
+      l.fn = [t](cudaStream_t st) { launch_conv_tc(t, st); };
+      out->push_back(std::move(l));
+      if (t.side) {
+        const int smc = hh->sm_count;
+        Launch f;
+        f.kind = LK_CONV; f.flops = 0; f.bytes = 0;
+        f.fn = [t, smc](cudaStream_t st) { launch_tc_fold(t, smc, st); };
+        out->push_back(std::move(f));
+      }
+      return;
+    }
+    l.fn = [hh, ac](cudaStream_t st) { launch_conv(hh, ac, st); };
     out->push_back(std::move(l));
   }
   void push(int kind, double flops, double bytes, std::function<void(cudaStream_t)> fn) {
@@ -391,17 +469,23 @@ void emit_bank_and_inconv(Emitter& E, const EncoderW& W, const EncActs& A, bool 
     a.slope = slope; a.bwd = 0; a.s = 1; a.T_y = A.T; a.B = A.B;
     a.Y = A.cat; a.y_bs = x.bs; a.y_rs = W.c_cat; a.N = W.d.c_bank; a.bias = W.bank_bias; a.act = 1;
     a.res = no_res(); a.zsplit = 1; a.n_groups = W.n_bank;
+    TcOp op;
+    bool tc_ok = true;
     for (int z = 0; z < W.n_bank; ++z) {
       const ConvW& w = W.bank[z];
       a.g[z] = TapGroup{w.fwd, 0, w.c_in, w.k, -w.pl(), w.pl(), w.pr(), w.c_in};
+      const TcPack& pk = w.tc_fwd[0];
+      const int gi = (pk.ok && pk.n_chunks == 1) ? op.add_group(pk.blocks[0], 0, w.c_in, w.k, 1, -w.pl()) : -1;
+      tc_ok = tc_ok && gi >= 0 && op.add_pass(gi, gi + 1, pk.cn[0], z * W.d.c_bank, 1, 0);   // one pass per bank conv
     }
-    E.conv(a);
+    if (!tc_ok) op = TcOp{};
+    E.conv(a, nullptr, &op);
   }
   {   // 1x1 in-conv over the concatenation (models.py:192 / :337)
     Tens cat{A.cat, x.bs, W.c_cat, A.T};
     Tens outT = tens(content ? A.tmp : A.h0, A.T, W.d.c_h);
     ConvArgs a = fwd_conv_args(W.in_conv, cat, outT, A.B, !content, slope);
-    E.conv(a, &W.in_conv.tc_fwd);
+    E.conv(a, &W.in_conv);
     if (content) emit_norm_fwd(E, A.tmp, A.B, A.T, W.d.c_h, nullptr, 0, nullptr, nullptr, A.h0, no_res(), slope);
   }
 }
@@ -416,17 +500,17 @@ void emit_encoder_blocks_fwd(Emitter& E, const EncoderW& W, const EncActs& A, bo
     ResArgs res = mk_res(in, sub > 1 ? RES_POOL : RES_SAME, sub);
     if (!content) {
       ConvArgs a1 = fwd_conv_args(W.c1[l], in, tens(A.h1[l], Ti, ch), A.B, true, slope);
-      E.conv(a1, &W.c1[l].tc_fwd);
+      E.conv(a1, &W.c1[l]);
       ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.h1[l], Ti, ch), tens(A.hout[l], To, ch), A.B, true, slope);
       a2.Y2 = A.h2[l]; a2.y2_bs = (long long)To * ch; a2.y2_rs = ch;
       a2.res = res;
-      E.conv(a2, &W.c2[l].tc_fwd);
+      E.conv(a2, &W.c2[l]);
     } else {
       ConvArgs a1 = fwd_conv_args(W.c1[l], in, tens(A.tmp, Ti, ch), A.B, false, slope);
-      E.conv(a1, &W.c1[l].tc_fwd);
+      E.conv(a1, &W.c1[l]);
       emit_norm_fwd(E, A.tmp, A.B, Ti, ch, nullptr, 0, nullptr, nullptr, A.h1[l], no_res(), slope);
       ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.h1[l], Ti, ch), tens(A.tmp2, To, ch), A.B, false, slope);
-      E.conv(a2, &W.c2[l].tc_fwd);
+      E.conv(a2, &W.c2[l]);
       emit_norm_fwd(E, A.tmp2, A.B, To, ch, nullptr, 0, nullptr, nullptr, A.hout[l], res, slope);
     }
     hin = A.hout[l];
@@ -466,12 +550,12 @@ void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Ten
     ConvArgs a2 = bwd_conv_args(W.c2[l], gout, gH, A.B, slope);
     a2.Mk = A.h2[l]; a2.m_bs = (long long)To * ch; a2.m_rs = ch;
     a2.Om = A.h1[l]; a2.om_bs = (long long)Ti * ch; a2.om_rs = ch;
-    E.conv(a2, &W.c2[l].tc_bwd);
+    E.conv(a2, &W.c2[l]);
     // through the first conv, plus the skip path (avg-pool backward when sub-sampled)
     Tens gx = tens(pingpong[l & 1], Ti, ch);
     ConvArgs a1 = bwd_conv_args(W.c1[l], gH, gx, A.B, slope);
     a1.res = mk_res(gout, sub > 1 ? RES_POOL_BWD : RES_SAME, sub);
-    E.conv(a1, &W.c1[l].tc_bwd);
+    E.conv(a1, &W.c1[l]);
     gout = gx;
   }
   if (nb == 0) fail(AVC_ERR_INVALID, "n_conv_blocks must be > 0");
@@ -479,7 +563,7 @@ void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Ten
     Tens gcat = tens(A.gcat, A.T, W.c_cat);
     ConvArgs a = bwd_conv_args(W.in_conv, gout, gcat, A.B, slope);
     a.Mk = A.h0; a.m_bs = (long long)A.T * ch; a.m_rs = ch;
-    E.conv(a, &W.in_conv.tc_bwd);
+    E.conv(a, &W.in_conv);
   }
   {   // conv bank: sum of the 8 transposed convs of (gcat_k * act'(cat_k)) + pass-through slice
     ConvArgs a{};
@@ -490,11 +574,20 @@ void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Ten
     Tens pass{A.gcat + W.n_bank * W.d.c_bank, a.a_bs, W.c_cat, A.T};
     a.res = mk_res(pass, RES_SAME, 1);
     a.n_groups = W.n_bank;
+    TcOp op;
+    bool tc_ok = true;
+    int PL = 0;
+    for (int z = 0; z < W.n_bank; ++z) PL = std::max(PL, W.bank[z].pl());
     for (int z = 0; z < W.n_bank; ++z) {
       const ConvW& w = W.bank[z];
       a.g[z] = TapGroup{w.bwd, z * W.d.c_bank, w.c_out, w.k, w.pl() - (w.k - 1), w.pl(), w.pr(), w.c_out};
+      const TcPack& pk = w.tc_bwd[0];
+      tc_ok = tc_ok && pk.ok && pk.n_chunks == 1 &&
+              op.add_group(pk.blocks[0], z * W.d.c_bank, w.c_out, w.k, 1, w.pl() - (w.k - 1) - PL) >= 0;
     }
-    E.conv(a);
+    tc_ok = tc_ok && op.add_pass(0, op.n_groups, W.bank[0].tc_bwd[0].cn[0], 0, 1, -PL);   // one pass sums the 8 transposed convs
+    if (!tc_ok) op = TcOp{};
+    E.conv(a, nullptr, &op);
   }
 }
 
@@ -545,10 +638,10 @@ void emit_decoder_const(Emitter& E, const DecoderW& W, const DecActs& A) {
   const float slope = W.d.neg_slope;
   const int ch = W.d.c_h;
   ConvArgs a = fwd_conv_args(W.in_conv, tens(A.z, A.L, W.d.c_in), tens(A.c0, A.L, ch), A.B, false, slope);
-  E.conv(a, &W.in_conv.tc_fwd);
+  E.conv(a, &W.in_conv);
   emit_norm_fwd(E, A.c0, A.B, A.L, ch, nullptr, 0, nullptr, nullptr, A.h[0], no_res(), slope);
   ConvArgs a1 = fwd_conv_args(W.c1[0], tens(A.h[0], A.L, ch), tens(A.c1[0], A.L, ch), A.B, false, slope);
-  E.conv(a1, &W.c1[0].tc_fwd);
+  E.conv(a1, &W.c1[0]);
   emit_norm_fwd(E, A.c1[0], A.B, A.L, ch, nullptr, 0, nullptr, A.st1[0], nullptr, no_res(), slope);
 }
 
@@ -571,19 +664,19 @@ void emit_decoder_fwd(Emitter& E, const DecoderW& W, const DecActs& A, const flo
     const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
     if (l > 0) {
       ConvArgs a1 = fwd_conv_args(W.c1[l], tens(A.h[l], Ti, ch), tens(A.c1[l], Ti, ch), A.B, false, slope);
-      E.conv(a1, &W.c1[l].tc_fwd);
+      E.conv(a1, &W.c1[l]);
     }
     emit_norm_fwd(E, A.c1[l], A.B, Ti, ch, A.cond + (2 * l) * 2 * ch, cb, l == 0 ? A.st1[0] : nullptr,
                   l == 0 ? nullptr : A.st1[l], A.r1[l], no_res(), slope);
     // second conv: c_h -> c_h*up channels; the packed weights are channel-permuted so that the
     // [Ti, ch*up] result IS the pixel-shuffled [Ti*up, ch] tensor (models.py:33-49)
     ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.r1[l], Ti, ch), Tens{A.c2[l], (long long)Ti * ch * up, ch * up, Ti}, A.B, false, slope);
-    E.conv(a2, &W.c2[l].tc_fwd);
+    E.conv(a2, &W.c2[l]);
     ResArgs res = mk_res(tens(A.h[l], Ti, ch), up > 1 ? RES_UP : RES_SAME, up);
     emit_norm_fwd(E, A.c2[l], A.B, To, ch, A.cond + (2 * l + 1) * 2 * ch, cb, nullptr, A.st2[l], A.h[l + 1], res, slope);
   }
   ConvArgs ao = fwd_conv_args(W.out_conv, tens(A.h[A.nb], A.Td[A.nb], ch), outT, A.B, false, slope);
-  E.conv(ao, &W.out_conv.tc_fwd);
+  E.conv(ao, &W.out_conv);
 }
 
 // decoder backward: gout = dL/d(decoder output) -> gemb_parts [B, 2*nb, 128]
@@ -593,7 +686,7 @@ void emit_decoder_bwd(Emitter& E, const DecoderW& W, const DecActs& A, const Ten
   int cur = 0;
   {
     ConvArgs a = bwd_conv_args(W.out_conv, gout, tens(A.gh[cur], A.Td[A.nb], ch), A.B, slope);
-    E.conv(a, &W.out_conv.tc_bwd);
+    E.conv(a, &W.out_conv);
   }
   for (int l = A.nb - 1; l >= 0; --l) {
     const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
@@ -601,14 +694,14 @@ void emit_decoder_bwd(Emitter& E, const DecoderW& W, const DecActs& A, const Ten
     emit_norm_bwd(E, gh.p, A.c2[l], A.st2[l], A.cond + (2 * l + 1) * 2 * ch, cb, A.gy, A.gcond + (2 * l + 1) * 2 * ch, cb,
                   A.B, To, ch, slope);
     ConvArgs a2 = bwd_conv_args(W.c2[l], Tens{A.gy, (long long)Ti * ch * up, ch * up, Ti}, tens(A.gr1, Ti, ch), A.B, slope);
-    E.conv(a2, &W.c2[l].tc_bwd);
+    E.conv(a2, &W.c2[l]);
     emit_norm_bwd(E, A.gr1, A.c1[l], A.st1[l], A.cond + (2 * l) * 2 * ch, cb, l > 0 ? A.gy : nullptr,
                   A.gcond + (2 * l) * 2 * ch, cb, A.B, Ti, ch, slope);
     if (l > 0) {
       Tens gnext = tens(A.gh[cur ^ 1], Ti, ch);
       ConvArgs a1 = bwd_conv_args(W.c1[l], tens(A.gy, Ti, ch), gnext, A.B, slope);
       a1.res = mk_res(gh, up > 1 ? RES_UP_BWD : RES_SAME, up);
-      E.conv(a1, &W.c1[l].tc_bwd);
+      E.conv(a1, &W.c1[l]);
       cur ^= 1;
     }
   }
@@ -692,8 +785,7 @@ ConvW pack_conv(avc_handle* h, HostW& hw, const std::string& key, int c_in, int 
   c.fwd = h->wmem.upload(f);
   c.bwd = h->wmem.upload(r);
   c.bias = h->wmem.upload(bb);
-  tc_pack_conv(h->wmem, c.tc_fwd, f, k, c_in, c_out);     // B operand images for the tcgen05 path
-  tc_pack_conv(h->wmem, c.tc_bwd, r, k, c_out, c_in);
+  tc_pack_both(h->wmem, c, f, r);     // B operand images for the tcgen05 path
   return c;
 }
 
@@ -813,7 +905,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   plan.n_iters = n_iters;
   plan.use_graph = a->use_graph != 0;
   Arena& m = plan.mem;
-  Emitter S{h, &plan.setup}, I{h, &plan.iter}, F{h, &plan.finish};
+  Emitter S{h, &plan.setup, &plan.mem}, I{h, &plan.iter, &plan.mem}, F{h, &plan.finish, &plan.mem};
 
   // ---- state of the optimiser --------------------------------------------------------------
   const size_t nel = (size_t)B * T * C;
@@ -903,7 +995,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     {
       const int nb = h->ce.d.n_conv_blocks;
       ConvArgs am = fwd_conv_args(h->ce.mean_layer, tens(ce.hout[nb - 1], L, h->ce.d.c_h), tens(dec.z, L, h->ce.d.c_out), B, false, 0.f);
-      S.conv(am, &h->ce.mean_layer.tc_fwd);
+      S.conv(am, &h->ce.mean_layer);
     }
     emit_decoder_const(S, h->dec, dec);
 
@@ -1123,6 +1215,7 @@ int avc_create(avc_handle** out, const avc_model_desc* desc, int device) {
     h->sm_count = p.multiProcessorCount;
     h->desc = *desc;
     if (const char* s = getenv("AVC_CONV_IMPL")) h->conv_impl = atoi(s);
+    if (const char* s = getenv("AVC_TC_MIN_ROWS")) h->tc_min_rows = atoll(s);
     init_kernel_attributes();
     *out = h.release();
   });
@@ -1245,7 +1338,7 @@ int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], 
     if (!x || !emb || B <= 0 || T <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     Plan plan;
-    Emitter S{h, &plan.setup};
+    Emitter S{h, &plan.setup, &plan.mem};
     EncActs A = alloc_encoder(plan.mem, h->se, B, T, false, false);
     emit_layout_in(S, x, stride, A.input(h->se), B, h->desc.speaker.c_in);
     emit_bank_and_inconv(S, h->se, A, false);
@@ -1267,7 +1360,7 @@ int avc_inference(avc_handle* h, const float* src, const int64_t src_stride[3], 
     if (!src || !tgt || !out || B <= 0 || T_src <= 0 || T_tgt <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     Plan plan;
-    Emitter S{h, &plan.setup};
+    Emitter S{h, &plan.setup, &plan.mem};
     const int C = h->desc.speaker.c_in, L = content_frames(h, T_src), T_dec = decoder_frames(h, T_src);
     EncActs ce = alloc_encoder(plan.mem, h->ce, B, T_src, false, true);
     EncActs se = alloc_encoder(plan.mem, h->se, B, T_tgt, false, false);
@@ -1278,7 +1371,7 @@ int avc_inference(avc_handle* h, const float* src, const int64_t src_stride[3], 
     emit_encoder_blocks_fwd(S, h->ce, ce, true);
     const int nb = h->ce.d.n_conv_blocks;
     ConvArgs am = fwd_conv_args(h->ce.mean_layer, tens(ce.hout[nb - 1], L, h->ce.d.c_h), tens(dec.z, L, h->ce.d.c_out), B, false, 0.f);
-    S.conv(am, &h->ce.mean_layer.tc_fwd);
+    S.conv(am, &h->ce.mean_layer);
     emit_decoder_const(S, h->dec, dec);
     emit_layout_in(S, tgt, tgt_stride, se.input(h->se), B, C);
     emit_bank_and_inconv(S, h->se, se, false);
@@ -1311,8 +1404,7 @@ static ConvW pack_adhoc(avc_handle* h, Arena& tmp, const float* w_dev, const flo
         r[((size_t)(k - 1 - j) * c_out + n) * c_in + ci] = v;
       }
   c.fwd = tmp.upload(f); c.bwd = tmp.upload(r); c.bias = tmp.upload(b);
-  tc_pack_conv(tmp, c.tc_fwd, f, k, c_in, c_out);
-  tc_pack_conv(tmp, c.tc_bwd, r, k, c_out, c_in);
+  tc_pack_both(tmp, c, f, r);
   (void)h;
   return c;
 }
@@ -1334,9 +1426,14 @@ int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* b
     ConvArgs a = fwd_conv_args(c, tens(const_cast<float*>(x), T, c_in), tens(y, To, c_out), B, false, 0.f);
     const int save = h->conv_impl;
     h->conv_impl = impl;
-    try { launch_conv(h, a, &c.tc_fwd, (cudaStream_t)stream); } catch (...) { h->conv_impl = save; throw; }
+    std::vector<Launch> v;
+    try {
+      Emitter E{h, &v, &tmp};
+      E.conv(a, &c);
+      run_list(v, (cudaStream_t)stream);
+    } catch (...) { h->conv_impl = save; cudaDeviceSynchronize(); throw; }
     h->conv_impl = save;
-    h->launches += 1;
+    h->launches += (long long)v.size();
     CK(cudaStreamSynchronize((cudaStream_t)stream));
   });
 }
@@ -1352,9 +1449,14 @@ int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx, 
     ConvArgs a = bwd_conv_args(c, tens(const_cast<float*>(dy), To, c_out), tens(dx, T, c_in), B, 0.f);
     const int save = h->conv_impl;
     h->conv_impl = impl;
-    try { launch_conv(h, a, &c.tc_bwd, (cudaStream_t)stream); } catch (...) { h->conv_impl = save; throw; }
+    std::vector<Launch> v;
+    try {
+      Emitter E{h, &v, &tmp};
+      E.conv(a, &c);
+      run_list(v, (cudaStream_t)stream);
+    } catch (...) { h->conv_impl = save; cudaDeviceSynchronize(); throw; }
     h->conv_impl = save;
-    h->launches += 1;
+    h->launches += (long long)v.size();
     CK(cudaStreamSynchronize((cudaStream_t)stream));
   });
 }
@@ -1366,7 +1468,8 @@ int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond,
     if (!y || !out || B <= 0 || T <= 0 || C <= 0 || up < 1) fail(AVC_ERR_INVALID, "bad argument");
     if (res && T % up) fail(AVC_ERR_INVALID, "T must be a multiple of up");
     std::vector<Launch> v;
-    Emitter E{h, &v};
+    Arena scratch;
+    Emitter E{h, &v, &scratch};
     ResArgs r = no_res();
     if (res) r = mk_res(tens(const_cast<float*>(res), T / up, C), up > 1 ? RES_UP : RES_SAME, up);
     emit_norm_fwd(E, y, B, T, C, cond, 2 * C, nullptr, stats_out, out, r, neg_slope);
@@ -1382,7 +1485,8 @@ int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, co
   return guarded(h, [&] {
     if (!g || !y || !stats || B <= 0 || T <= 0 || C <= 0 || C % kNormCh) fail(AVC_ERR_INVALID, "bad argument");
     std::vector<Launch> v;
-    Emitter E{h, &v};
+    Arena scratch;
+    Emitter E{h, &v, &scratch};
     emit_norm_bwd(E, g, y, stats, cond, 2 * C, gy, gcond, 2 * C, B, T, C, neg_slope);
     run_list(v, (cudaStream_t)stream);
     h->launches += 1;

@@ -131,3 +131,46 @@ def test_adam_tanh_step_matches_torch_adam(engine, step):
     assert torch.allclose(adv_d.cpu(), ref_adv, rtol=3e-7, atol=1e-7)
     # the bound is exact on the perturbation term
     assert float((eps * wd.tanh()).abs().max()) <= eps
+
+
+TC_CASES = CONV_CASES + [
+    (64, 256, 128, 128, 5, 1),     # 130 tiles
+    (7, 100, 128, 128, 5, 1),      # tiles straddle utterances
+    (16, 32, 128, 256, 5, 1),      # short utterances, N = 256 (two column passes)
+    (9, 131, 128, 128, 5, 2),      # stride 2, odd T
+    (4, 64, 128, 1104, 1, 1),      # dgrad of this is K=1104; forward N = 1104 -> 9 column passes
+]
+
+
+@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3)])
+@pytest.mark.parametrize("B,T,ci,co,k,s", TC_CASES)
+def test_conv1d_fwd_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
+    """tcgen05 path: 3xTF32 with chunked accumulation (impl 2) must be fp32-grade; a single TF32 pass
+    (impl 4, measurement only) is ~2e-4."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k)
+    x = torch.randn(B, T, ci, device="cuda", generator=g)
+    w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
+    b = torch.randn(co, device="cuda", generator=g)
+    y = engine.conv1d_fwd(x, w, b, stride=s, impl=impl)
+    ref = ref_conv(x.double(), w.double(), b.double(), s)
+    assert y.shape == ref.shape
+    err = rel_err(y, ref)
+    assert err < tol, err
+    y1 = engine.conv1d_fwd(x, w, b, stride=s, impl=1)
+    assert not torch.equal(y, y1), "tensor-core route silently fell back to the CUDA-core kernel"
+
+
+@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3)])
+@pytest.mark.parametrize("B,T,ci,co,k,s", TC_CASES)
+def test_conv1d_dgrad_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 7)
+    x = torch.randn(B, T, ci, device="cuda", generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
+    y = ref_conv(x, w.double(), None, s)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    (dx_ref,) = torch.autograd.grad(y, x, dy.double())
+    dx = engine.conv1d_dgrad(dy, w, T, stride=s, impl=impl)
+    err = rel_err(dx, dx_ref)
+    assert err < tol, err
+    dx1 = engine.conv1d_dgrad(dy, w, T, stride=s, impl=1)
+    assert not torch.equal(dx, dx1), "tensor-core route silently fell back to the CUDA-core kernel"
