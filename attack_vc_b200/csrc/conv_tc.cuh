@@ -86,6 +86,7 @@ struct TcArgs {
   float* side;           // [B][halo_l + halo_r][side_n]
   int n_pass;
   int terms;             // 3: 3xTF32 (product), 1: single TF32 pass, 4: + lo*lo (both measurement only)
+  int dbg;               // bottleneck probes (results are garbage): 1 no weight copies, 2 no window gather, 4 no MMA
   TcPass pass[kTcMaxPass];
   TcGroup g[kTcMaxPass];
 };
@@ -212,9 +213,44 @@ struct TcWalk {
   }
 };
 
+constexpr int kTcScrPitch = 36;    // floats per row of a drain warp's transpose slab (32 + 4: conflict-free float4 rows)
+
+// Columns [C0, C0+SW) of the 32 rows a drain warp owns: registers -> slab (row per lane) -> global
+// (SW/4 lanes per row, so a warp instruction covers 32/(SW/4) rows with contiguous SW*4-byte segments).
+template <int NH, int C0, int SW>
+__device__ __forceinline__ void tc_store_slab(const TcArgs& p, const float (&acc)[NH], float* scratch, int lane,
+                                              int b_own, int o_own, int kind_own, int chb) {
+  constexpr int LPR = SW / 4, RPI = 32 / LPR;
+#pragma unroll
+  for (int q = 0; q < SW / 4; ++q)
+    st4(scratch + lane * kTcScrPitch + 4 * q, make_float4(acc[C0 + 4 * q], acc[C0 + 4 * q + 1], acc[C0 + 4 * q + 2], acc[C0 + 4 * q + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int r = it * RPI + lane / LPR, c4 = lane % LPR;
+    const int b = __shfl_sync(0xffffffffu, b_own, r), o = __shfl_sync(0xffffffffu, o_own, r);
+    const int kind = __shfl_sync(0xffffffffu, kind_own, r);
+    if (kind == 0) continue;
+    float4 x = ld4(scratch + r * kTcScrPitch + 4 * c4);
+    const int ch = chb + C0 + 4 * c4;
+    if (kind == 1) {
+      if (p.bias) x = f4add(x, ld4(p.bias + ch));
+      if (p.Om) x = dact4mul(x, ld4(p.Om + (long long)b * p.om_bs + (long long)o * p.om_rs + ch), p.slope);
+      if (p.act) x = act4(x, p.slope);
+      if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)o * p.y2_rs + ch, x);
+      if (p.res.mode != RES_NONE) x = f4add(x, res_load4(p.res, b, o, p.T_y, ch));
+      st4(p.Y + (long long)b * p.y_bs + (long long)o * p.y_rs + ch, x);
+    } else {
+      const int hrow = o < 0 ? o + p.halo_l : p.halo_l + (o - p.T_y);
+      st4(p.side + ((long long)b * (p.halo_l + p.halo_r) + hrow) * p.side_n + ch, x);
+    }
+  }
+  __syncwarp();
+}
+
 template <int NH>   // columns per drain thread (half of the pass width): 64 or 40
 __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
-                                                   uint32_t acc_empty0, long long v0, int warp, int lane) {
+                                                   uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch) {
   const int quad = warp & 3;                    // TMEM lanes this warp may read: [32*quad, 32*quad+32)
   const int half = (warp - 6) >> 2;             // which half of the columns
   float acc[NH];
@@ -222,7 +258,6 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
   for (int i = 0; i < NH; ++i) acc[i] = 0.f;
   TcWalk w(p, ps);
   bool done = false;
-  int chunk = 0;
   while (!done) {
     if (!w.next(p, ps, done)) continue;
     const int buf = chunk & 1;
@@ -231,6 +266,7 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kTcNMax + half * NH);
 #pragma unroll
     for (int c0 = 0; c0 < NH; c0 += 8) {
+      if (p.dbg & 16) break;
       uint32_t r[8];
       tmem_ld8(t0 + c0, r);
       tmem_ld_wait();
@@ -238,45 +274,33 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
       for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);     // round-to-nearest fp32 adds
     }
     tc_fence_before();
-    mbar_arrive(acc_empty0 + 8 * buf);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
     ++chunk;
   }
-  // ---- epilogue: bias / mask / act / residual -> global ----
+  // ---- epilogue: bias / mask / act / residual -> global (overlaps the next tile's MMAs) ----
+  // Each lane owns one accumulator ROW; rows are 512 B apart in memory, so the tile is transposed
+  // through a per-warp shared-memory slab and written with lanes along the channel axis.
   const int row = quad * 32 + lane;
   const long long u = v0 + row;
-  const int b = (int)(u / p.Pv);
-  const int o = ps.so * (int)(u - (long long)b * p.Pv) + ps.oo;   // output index inside the utterance
-  const bool main_row = b < p.B && o >= 0 && o < p.T_y;
-  int hrow = -1;                                                    // side-buffer row (dgrad halo)
-  if (b < p.B && p.side) {
-    if (o < 0 && o >= -p.halo_l) hrow = o + p.halo_l;
-    else if (o >= p.T_y && o < p.T_y + p.halo_r) hrow = p.halo_l + (o - p.T_y);
+  const int b_own = (int)(u / p.Pv);
+  const int o_own = ps.so * (int)(u - (long long)b_own * p.Pv) + ps.oo;   // output index inside the utterance
+  int kind_own = 0;                                                        // 0 dead, 1 main row, 2 dgrad halo row
+  if (b_own < p.B && !(p.dbg & 8)) {
+    if (o_own >= 0 && o_own < p.T_y) kind_own = 1;
+    else if (p.side && ((o_own < 0 && o_own >= -p.halo_l) || (o_own >= p.T_y && o_own < p.T_y + p.halo_r))) kind_own = 2;
   }
   const int chb = ps.ch_off + half * NH;
-  if (main_row) {
-#pragma unroll
-    for (int q = 0; q < NH / 4; ++q) {
-      const int ch = chb + 4 * q;
-      float4 x = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-      if (p.bias) x = f4add(x, ld4(p.bias + ch));
-      if (p.Om) x = dact4mul(x, ld4(p.Om + (long long)b * p.om_bs + (long long)o * p.om_rs + ch), p.slope);
-      if (p.act) x = act4(x, p.slope);
-      if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)o * p.y2_rs + ch, x);
-      if (p.res.mode != RES_NONE) x = f4add(x, res_load4(p.res, b, o, p.T_y, ch));
-      st4(p.Y + (long long)b * p.y_bs + (long long)o * p.y_rs + ch, x);
-    }
-  } else if (hrow >= 0) {
-    float* sd = p.side + ((long long)b * (p.halo_l + p.halo_r) + hrow) * p.side_n + chb;
-#pragma unroll
-    for (int q = 0; q < NH / 4; ++q) st4(sd + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
-  }
+  tc_store_slab<NH, 0, (NH >= 32 ? 32 : 8)>(p, acc, scratch, lane, b_own, o_own, kind_own, chb);
+  if (NH > 32) tc_store_slab<NH, 32, (NH - 32 >= 32 ? 32 : 8)>(p, acc, scratch, lane, b_own, o_own, kind_own, chb);
 }
 
+// Persistent: gridDim.x CTAs (one per SM) walk the work items (M tile, pass) round-robin; barrier phases,
+// ring positions and the accumulator ping-pong run on across items, so the drain warps' epilogue of one
+// item overlaps the MMAs of the next.
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcPass& ps = p.pass[blockIdx.z];
-  const int N = ps.N;
   constexpr uint32_t b_stage_bytes = 2 * (kTcKB / 4) * kTcNMax * 16;                // hi + lo plane of a full weight stage
   float* As = reinterpret_cast<float*>(tc_smem);                                     // [kTcAStages][2][kTcAPlane]
   unsigned char* Bs = tc_smem + (size_t)kTcAStages * 2 * kTcAPlane * 4;              // [kTcBStages][b_stage_bytes]
@@ -289,11 +313,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   auto b_empty = [&](int s) { return bar0 + 8 * (8 + s); };
   const uint32_t acc_full0 = bar0 + 8 * 12, acc_empty0 = bar0 + 8 * 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* scr_all = reinterpret_cast<float*>(bars + 18);                               // [8 drain warps][32][kTcScrPitch]
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), 128); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t tmem_cols = 2 * kTcNMax;     // two accumulators, ping-pong
@@ -307,24 +332,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
 
-  const long long v0 = (long long)blockIdx.x * kTcM;
+  const int n_mt = (int)((p.Mv + kTcM - 1) / kTcM);
+  const int n_work = n_mt * p.n_pass;              // item w: M tile w / n_pass, pass w % n_pass (passes of a tile share A in L2)
 
   if (warp == 0) {
     // ===== weight producer: one elected lane streams (K block, tap) stages with the TMA engine =====
     if (lane == 0) {
       int sb = 0; uint32_t pb = 0;
-      for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
-        const TcGroup& G = p.g[gi];
-        const int nkb = (G.kc + kTcKB - 1) / kTcKB;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int kbs = min(kTcKB, G.kc - kb * kTcKB);
-          const uint32_t bytes = 2u * kbs * N * 4u;
-          const float* src = G.Wp + (size_t)kb * G.n_taps * 2 * kTcKB * N;
-          for (int tap = 0; tap < G.n_taps; ++tap) {
-            mbar_wait(b_empty(sb), pb ^ 1);
-            mbar_expect_tx(b_full(sb), bytes);
-            bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src + (size_t)tap * 2 * kbs * N, bytes, b_full(sb));
-            if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+      for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+        const TcPass& ps = p.pass[wk % p.n_pass];
+        const int N = ps.N;
+        for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
+          const TcGroup& G = p.g[gi];
+          const int nkb = (G.kc + kTcKB - 1) / kTcKB;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int kbs = min(kTcKB, G.kc - kb * kTcKB);
+            const uint32_t bytes = 2u * kbs * N * 4u;
+            const float* src = G.Wp + (size_t)kb * G.n_taps * 2 * kTcKB * N;
+            for (int tap = 0; tap < G.n_taps; ++tap) {
+              mbar_wait(b_empty(sb), pb ^ 1);
+              if (p.dbg & 1) { mbar_arrive(b_full(sb)); }
+              else {
+                mbar_expect_tx(b_full(sb), bytes);
+                bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src + (size_t)tap * 2 * kbs * N, bytes, b_full(sb));
+              }
+              if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+            }
           }
         }
       }
@@ -332,119 +365,153 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-      const uint32_t a_lbo = kTcRows * 16, b_lbo = (uint32_t)N * 16;
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-      TcWalk w(p, ps);
-      bool done = false;
       int chunk = 0;
-      uint32_t acc = 0;
-      bool fresh = true;           // first K block of a chunk: wait for the drain warps to release the buffer
-      while (!done) {
-        const TcGroup& G = p.g[w.gi];
-        const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
-        const int buf = chunk & 1;
-        if (fresh) {
-          mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);
-          tc_fence_after();
-          acc = 0; fresh = false;
-        }
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
-        mbar_wait(a_full(sa), pa);
-        const uint32_t a_hi = smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lo = a_hi + kTcAPlane * 4;
-        for (int tap = 0; tap < G.n_taps; ++tap) {
-          mbar_wait(b_full(sb), pb);
-          tc_fence_after();
-          const uint32_t b_hi = smem_u32(Bs + (size_t)sb * b_stage_bytes), b_lo = b_hi + (uint32_t)(kbs / 4) * N * 16;
-          for (int ks = 0; ks < kbs / 8; ++ks) {
-            const uint32_t ao = tap * 16 + ks * 2 * a_lbo, bo = ks * 2 * b_lbo;
-            const uint64_t dah = tc_desc(a_hi + ao, a_lbo, 128), dal = tc_desc(a_lo + ao, a_lbo, 128);
-            const uint64_t dbh = tc_desc(b_hi + bo, b_lbo, 128), dbl = tc_desc(b_lo + bo, b_lbo, 128);
-            tc_mma_tf32(d_tmem, dah, dbh, idesc, acc);
-            acc = 1;
-            if (p.terms >= 3) {
-              tc_mma_tf32(d_tmem, dal, dbh, idesc, 1);
-              tc_mma_tf32(d_tmem, dah, dbl, idesc, 1);
-            }
-            if (p.terms >= 4) tc_mma_tf32(d_tmem, dal, dbl, idesc, 1);
+      long long st_a = 0, st_b = 0, st_acc = 0, st_issue = 0, t_begin = clock64(), tq;   // dbg & 32: where the issuer waits
+      const int terms = p.terms;
+      const bool no_mma = (p.dbg & 4) != 0;
+      for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+        const TcPass& ps = p.pass[wk % p.n_pass];
+        const int N = ps.N;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        const uint32_t a_lbo = kTcRows * 16, b_lbo = (uint32_t)N * 16;
+        TcWalk w(p, ps);
+        bool done = false;
+        uint32_t acc = 0;
+        bool fresh = true;           // first K block of a chunk: wait for the drain warps to release the buffer
+        while (!done) {
+          const TcGroup& G = p.g[w.gi];
+          const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
+          const int buf = chunk & 1;
+          if (fresh) {
+            tq = clock64();
+            mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);
+            st_acc += clock64() - tq;
+            tc_fence_after();
+            acc = 0; fresh = false;
           }
-          tc_commit(b_empty(sb));
-          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
-        }
-        tc_commit(a_empty(sa));
-        if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
-        if (w.next(p, ps, done)) {
-          tc_commit(acc_full0 + 8 * buf);
-          ++chunk; fresh = true;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
+          tq = clock64();
+          mbar_wait(a_full(sa), pa);
+          if (st_issue == 0) t_begin = clock64();      // the first window also waits for the predecessor kernel (PDL)
+          else st_a += clock64() - tq;
+          const uint64_t a_desc0 = tc_desc(smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lbo, 128);
+          const uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4), b_ks = (uint64_t)((2 * b_lbo) >> 4);
+          const int nks = no_mma ? 0 : kbs / 8;
+          for (int tap = 0; tap < G.n_taps; ++tap) {
+            tq = clock64();
+            mbar_wait(b_full(sb), pb);
+            st_b += clock64() - tq;
+            tc_fence_after();
+            tq = clock64();
+            // descriptors advance by plain 64-bit adds on the (address >> 4) field: no re-encoding per MMA
+            uint64_t da = a_desc0 + (uint64_t)tap;                                  // tap j = window shifted by j rows of 16 B
+            uint64_t db = tc_desc(smem_u32(Bs + (size_t)sb * b_stage_bytes), b_lbo, 128);
+            const uint64_t b_lo_off = (uint64_t)(((uint32_t)(kbs / 4) * N * 16) >> 4);
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
+              tc_mma_tf32(d_tmem, da, db, idesc, acc);
+              acc = 1;
+              if (terms >= 3) {
+                tc_mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1);
+                tc_mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1);
+              }
+              if (terms >= 4) tc_mma_tf32(d_tmem, da + a_lo_off, db + b_lo_off, idesc, 1);
+              da += a_ks; db += b_ks;
+            }
+            tc_commit(b_empty(sb));
+            st_issue += clock64() - tq;
+            if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(a_empty(sa));
+          if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+          if (w.next(p, ps, done)) {
+            tc_commit(acc_full0 + 8 * buf);
+            ++chunk; fresh = true;
+          }
         }
       }
+      if ((p.dbg & 32) && blockIdx.x == 0)
+        printf("[conv_tc cta0] issuer: total %lld clk, wait a_full %lld, wait b_full %lld, wait acc_empty %lld, issue %lld (items %d)\n",
+               clock64() - t_begin, st_a, st_b, st_acc, st_issue, (n_work + (int)gridDim.x - 1) / (int)gridDim.x);
     }
   } else if (warp < 6) {
     // ===== loaders (128 threads): window gather + TF32 split =====
     pdl_wait();
     const int tl = threadIdx.x - 64;   // 0..127
     int sa = 0; uint32_t pa = 0;
-    for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
-      const TcGroup& G = p.g[gi];
-      const int nrows = kTcM + G.n_taps - 1;
-      // source rows of my (up to two) window rows
-      const float* src[2]; const float* msk[2]; bool have[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = tl + j * kTcM;
-        have[j] = i < nrows;
-        src[j] = nullptr; msk[j] = nullptr;
-        if (have[j]) {
-          const long long u = v0 + i;
-          const int b = (int)(u / p.Pv);
-          const int pos = G.sg * (int)(u - (long long)b * p.Pv) + G.off0;
-          int rr = pos;
-          if (!p.bwd) {
-            rr = rr < 0 ? -rr : rr;
-            if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
-          }
-          if (b < p.B && rr >= 0 && rr < p.T_a) {
-            src[j] = p.A + (long long)b * p.a_bs + (long long)rr * p.a_rs + G.a_ch_off;
-            if (p.Mk) msk[j] = p.Mk + (long long)b * p.m_bs + (long long)rr * p.m_rs + G.a_ch_off;
-          }
-        }
-      }
-      const int nkb = (G.kc + kTcKB - 1) / kTcKB;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int kb0 = kb * kTcKB, kbs = min(kTcKB, G.kc - kb0);
-        mbar_wait(a_empty(sa), pa ^ 1);
-        float* hi = As + (size_t)sa * 2 * kTcAPlane;
-        float* lo = hi + kTcAPlane;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const TcPass& ps = p.pass[wk % p.n_pass];
+      const long long v0 = (long long)(wk / p.n_pass) * kTcM;
+      for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
+        const TcGroup& G = p.g[gi];
+        const int nrows = kTcM + G.n_taps - 1;
+        // source rows of my (up to two) window rows
+        const float* src[2]; const float* msk[2]; bool have[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (!have[j]) continue;
           const int i = tl + j * kTcM;
-          float4 v[kTcKB / 4];
-#pragma unroll
-          for (int c = 0; c < kTcKB / 4; ++c) v[c] = (src[j] && 4 * c < kbs) ? ld4(src[j] + kb0 + 4 * c) : f4zero();
-          if (msk[j]) {
-#pragma unroll
-            for (int c = 0; c < kTcKB / 4; ++c)
-              if (4 * c < kbs) v[c] = dact4mul(v[c], ld4(msk[j] + kb0 + 4 * c), p.slope);
-          }
-#pragma unroll
-          for (int c = 0; c < kTcKB / 4; ++c) {
-            if (4 * c >= kbs) break;
-            const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
-            st4(hi + ((size_t)c * kTcRows + i) * 4, h);
-            st4(lo + ((size_t)c * kTcRows + i) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
+          have[j] = i < nrows;
+          src[j] = nullptr; msk[j] = nullptr;
+          if (have[j]) {
+            const long long u = v0 + i;
+            const int b = (int)(u / p.Pv);
+            const int pos = G.sg * (int)(u - (long long)b * p.Pv) + G.off0;
+            int rr = pos;
+            if (!p.bwd) {
+              rr = rr < 0 ? -rr : rr;
+              if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
+            }
+            if (b < p.B && rr >= 0 && rr < p.T_a) {
+              src[j] = p.A + (long long)b * p.a_bs + (long long)rr * p.a_rs + G.a_ch_off;
+              if (p.Mk) msk[j] = p.Mk + (long long)b * p.m_bs + (long long)rr * p.m_rs + G.a_ch_off;
+            }
           }
         }
-        fence_proxy_async();
-        mbar_arrive(a_full(sa));
-        if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+        const int nkb = (G.kc + kTcKB - 1) / kTcKB;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int kb0 = kb * kTcKB, kbs = min(kTcKB, G.kc - kb0);
+          mbar_wait(a_empty(sa), pa ^ 1);
+          float* hi = As + (size_t)sa * 2 * kTcAPlane;
+          float* lo = hi + kTcAPlane;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!have[j] || (p.dbg & 2)) continue;
+            const int i = tl + j * kTcM;
+            float4 v[kTcKB / 4];
+#pragma unroll
+            for (int c = 0; c < kTcKB / 4; ++c) v[c] = (src[j] && 4 * c < kbs) ? ld4(src[j] + kb0 + 4 * c) : f4zero();
+            if (msk[j]) {
+#pragma unroll
+              for (int c = 0; c < kTcKB / 4; ++c)
+                if (4 * c < kbs) v[c] = dact4mul(v[c], ld4(msk[j] + kb0 + 4 * c), p.slope);
+            }
+#pragma unroll
+            for (int c = 0; c < kTcKB / 4; ++c) {
+              if (4 * c >= kbs) break;
+              const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
+              st4(hi + ((size_t)c * kTcRows + i) * 4, h);
+              st4(lo + ((size_t)c * kTcRows + i) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full(sa));
+          if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+        }
       }
     }
   } else {
     // ===== drain warps (256 threads): chunk sums in registers, then the epilogue =====
     pdl_wait();
-    if (N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane);
-    else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane);
+    int chunk = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const TcPass& ps = p.pass[wk % p.n_pass];
+      const long long v0 = (long long)(wk / p.n_pass) * kTcM;
+      float* scratch = scr_all + (size_t)(warp - 6) * 32 * kTcScrPitch;
+      if (ps.N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch);
+      else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -481,7 +548,7 @@ __global__ void tc_fold_kernel(float* __restrict__ Y, long long y_bs, int y_rs, 
 }
 
 inline size_t tc_smem_bytes() {
-  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 16 * 8 + 16;
+  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 18 * 8 + (size_t)8 * 32 * kTcScrPitch * 4;
 }
 
 // ---- host: the tensor-core view of one conv launch (passes x groups, no tensor pointers yet) --------
@@ -548,6 +615,7 @@ inline TcArgs tc_make_args(const ConvArgs& a, const TcOp& op, float* side, int t
   t.side = (PL + PR) > 0 ? side : nullptr;
   t.n_pass = op.n_pass;
   t.terms = terms;
+  { static const int dbg = getenv("AVC_TC_DBG") ? atoi(getenv("AVC_TC_DBG")) : 0; t.dbg = dbg; }
   for (int q = 0; q < op.n_pass; ++q) t.pass[q] = op.pass[q];
   for (int g = 0; g < op.n_groups; ++g) t.g[g] = op.g[g];
   return t;

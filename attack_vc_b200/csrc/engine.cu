@@ -268,9 +268,10 @@ bool want_tc(const avc_handle* h, const ConvArgs& a, const TcOp& op) {
   return (long long)a.B * (a.T_y + op.kmax - 1) >= h->tc_min_rows;
 }
 
-void launch_conv_tc(const TcArgs& t, cudaStream_t st) {
+void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st) {
   const size_t smem = tc_smem_bytes();
-  dim3 grid((unsigned)((t.Mv + kTcM - 1) / kTcM), 1, t.n_pass);
+  const long long work = ((t.Mv + kTcM - 1) / kTcM) * t.n_pass;
+  dim3 grid((unsigned)std::min<long long>(work, sm_count), 1, 1);   // persistent: one CTA per SM
   launch_k(conv_tc_kernel, grid, kTcThreads, smem, st, t);
 }
 
@@ -347,7 +348,8 @@ struct Emitter {
       const size_t side_n = tc_side_floats(ac);
       float* side = side_n ? mem->f(side_n) : nullptr;
       const TcArgs t = tc_make_args(ac, op, side, hh->conv_impl == 4 ? 1 : hh->conv_impl == 5 ? 4 : 3);
-      l.fn = [t](cudaStream_t st) { launch_conv_tc(t, st); };
+      const int smc0 = hh->sm_count;
+      l.fn = [t, smc0](cudaStream_t st) { launch_conv_tc(t, smc0, st); };
       out->push_back(std::move(l));
       if (t.side) {
         const int smc = hh->sm_count;
