@@ -46,7 +46,8 @@ constexpr int kTcBStages = 3;
 constexpr int kTcNMax = 128;       // columns of one pass
 constexpr int kTcThreads = 448;    // warp 0: TMEM + weight producer, 1: MMA issuer, 2-5: loaders, 6-13: drain + epilogue
 constexpr int kTcAPlane = (kTcKB / 4) * kTcRows * 4;   // floats of one hi (or lo) plane of an A stage
-constexpr int kTcChunkSteps = 16;  // MMA k-steps accumulated in TMEM before the drain warps take over
+constexpr int kTcChunkSteps = 8;   // default MMA k-steps accumulated in TMEM before the drain warps take over
+constexpr int kTcAccBufs = 4;      // accumulator ring in TMEM (4 x 128 columns = all 512): hides the drain hand-off latency
 constexpr int kTcMaxChunks = 12;   // N chunks of one packed conv (1104 = 8 x 128 + 80)
 constexpr int kTcMaxPass = 12;
 
@@ -86,6 +87,7 @@ struct TcArgs {
   float* side;           // [B][halo_l + halo_r][side_n]
   int n_pass;
   int terms;             // 3: 3xTF32 (product), 1: single TF32 pass, 4: + lo*lo (both measurement only)
+  int chunk_steps;       // MMA k-steps accumulated in TMEM before the drain warps take the partial sum (env AVC_TC_CHUNK)
   int dbg;               // bottleneck probes (results are garbage): 1 no weight copies, 2 no window gather, 4 no MMA
   TcPass pass[kTcMaxPass];
   TcGroup g[kTcMaxPass];
@@ -191,24 +193,36 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
-// K blocks are visited in (group, kb) order by all roles; a chunk closes after the K block that
-// brings it to kTcChunkSteps MMA k-steps, and after the last K block of the pass.
+// Weight stages are visited in (group, K block, tap) order by all roles; a chunk closes after the tap
+// that brings it to chunk_steps MMA k-steps, and after the last tap of the pass.
 struct TcWalk {
-  int gi, kb, nkb, steps;
-  __device__ TcWalk(const TcArgs& p, const TcPass& ps) : gi(ps.g_begin), kb(0), steps(0) { nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB; }
-  // advance past the current K block; returns true when the chunk it belongs to is complete
-  __device__ bool next(const TcArgs& p, const TcPass& ps, bool& done) {
+  int gi, kb, tap, nkb, steps;
+  __device__ TcWalk(const TcArgs& p, const TcPass& ps) : gi(ps.g_begin), kb(0), tap(0), steps(0) { nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB; }
+  // advance past the current tap; kb_end: it was the last tap of its K block, done: of the pass;
+  // returns true when the chunk it belongs to is complete
+  __device__ bool next(const TcArgs& p, const TcPass& ps, bool& kb_end, bool& done) {
     const TcGroup& G = p.g[gi];
-    steps += G.n_taps * (min(kTcKB, G.kc - kb * kTcKB) / 8);
-    if (++kb == nkb) {
-      kb = 0;
-      if (++gi < ps.g_end) nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB;
+    steps += min(kTcKB, G.kc - kb * kTcKB) / 8;
+    kb_end = false; done = false;
+    if (++tap == G.n_taps) {
+      tap = 0; kb_end = true;
+      if (++kb == nkb) {
+        kb = 0;
+        if (++gi < ps.g_end) nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB;
+        else done = true;
+      }
     }
-    done = gi >= ps.g_end;
-    if (done || steps >= kTcChunkSteps) { steps = 0; return true; }
+    if (done || steps >= p.chunk_steps) { steps = 0; return true; }
     return false;
   }
 };
@@ -257,21 +271,32 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
 #pragma unroll
   for (int i = 0; i < NH; ++i) acc[i] = 0.f;
   TcWalk w(p, ps);
-  bool done = false;
+  bool done = false, kb_end;
   while (!done) {
-    if (!w.next(p, ps, done)) continue;
-    const int buf = chunk & 1;
-    mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+    if (!w.next(p, ps, kb_end, done)) continue;
+    const int buf = chunk % kTcAccBufs;
+    mbar_wait(acc_full0 + 8 * buf, (chunk / kTcAccBufs) & 1);
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kTcNMax + half * NH);
+    if (!(p.dbg & 16)) {
+      // loads are issued in batches of 32 (or 40) columns before one wait: the TMEM read latency is paid per batch
 #pragma unroll
-    for (int c0 = 0; c0 < NH; c0 += 8) {
-      if (p.dbg & 16) break;
-      uint32_t r[8];
-      tmem_ld8(t0 + c0, r);
-      tmem_ld_wait();
+      for (int c0 = 0; c0 + 32 <= NH; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(t0 + c0, r0);
+        tmem_ld16(t0 + c0 + 16, r1);
+        if (NH - c0 - 32 == 8) {           // NH = 40: the 8-column tail rides along
+          uint32_t r2[8];
+          tmem_ld8(t0 + c0 + 32, r2);
+          tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);     // round-to-nearest fp32 adds
+          for (int i = 0; i < 8; ++i) acc[c0 + 32 + i] += __uint_as_float(r2[i]);
+        } else {
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(r0[i]); acc[c0 + 16 + i] += __uint_as_float(r1[i]); }   // round-to-nearest fp32 adds
+      }
     }
     tc_fence_before();
     __syncwarp();
@@ -305,23 +330,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   float* As = reinterpret_cast<float*>(tc_smem);                                     // [kTcAStages][2][kTcAPlane]
   unsigned char* Bs = tc_smem + (size_t)kTcAStages * 2 * kTcAPlane * 4;              // [kTcBStages][b_stage_bytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)kTcBStages * b_stage_bytes);
-  // bars: a_full[2] a_empty[2] b_full[4] b_empty[4] acc_full[2] acc_empty[2]
+  // bars: a_full[2] a_empty[2] b_full[4] b_empty[4] acc_full[4] acc_empty[4]
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8 * s; };
   auto a_empty = [&](int s) { return bar0 + 8 * (2 + s); };
   auto b_full = [&](int s) { return bar0 + 8 * (4 + s); };
   auto b_empty = [&](int s) { return bar0 + 8 * (8 + s); };
-  const uint32_t acc_full0 = bar0 + 8 * 12, acc_empty0 = bar0 + 8 * 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* scr_all = reinterpret_cast<float*>(bars + 18);                               // [8 drain warps][32][kTcScrPitch]
+  const uint32_t acc_full0 = bar0 + 8 * 12, acc_empty0 = bar0 + 8 * 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* scr_all = reinterpret_cast<float*>(bars + 22);                               // [8 drain warps][32][kTcScrPitch]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 8); }
+    for (int s = 0; s < kTcAccBufs; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  constexpr uint32_t tmem_cols = 2 * kTcNMax;     // two accumulators, ping-pong
+  constexpr uint32_t tmem_cols = kTcAccBufs * kTcNMax;     // accumulator ring
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -378,19 +403,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
         TcWalk w(p, ps);
         bool done = false;
         uint32_t acc = 0;
-        bool fresh = true;           // first K block of a chunk: wait for the drain warps to release the buffer
+        bool fresh = true;           // first tap of a chunk: wait for the drain warps to release the buffer
         while (!done) {
           const TcGroup& G = p.g[w.gi];
           const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
-          const int buf = chunk & 1;
-          if (fresh) {
-            tq = clock64();
-            mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);
-            st_acc += clock64() - tq;
-            tc_fence_after();
-            acc = 0; fresh = false;
-          }
-          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
           tq = clock64();
           mbar_wait(a_full(sa), pa);
           if (st_issue == 0) t_begin = clock64();      // the first window also waits for the predecessor kernel (PDL)
@@ -398,7 +414,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
           const uint64_t a_desc0 = tc_desc(smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lbo, 128);
           const uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4), b_ks = (uint64_t)((2 * b_lbo) >> 4);
           const int nks = no_mma ? 0 : kbs / 8;
-          for (int tap = 0; tap < G.n_taps; ++tap) {
+          bool kb_end = false;
+          while (!kb_end) {
+            const int tap = w.tap;
+            const int buf = chunk % kTcAccBufs;
+            if (fresh) {
+              tq = clock64();
+              mbar_wait(acc_empty0 + 8 * buf, ((chunk / kTcAccBufs) & 1) ^ 1);
+              st_acc += clock64() - tq;
+              tc_fence_after();
+              acc = 0; fresh = false;
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
             tq = clock64();
             mbar_wait(b_full(sb), pb);
             st_b += clock64() - tq;
@@ -422,13 +449,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             tc_commit(b_empty(sb));
             st_issue += clock64() - tq;
             if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+            if (w.next(p, ps, kb_end, done)) {
+              tc_commit(acc_full0 + 8 * buf);
+              ++chunk; fresh = true;
+            }
           }
           tc_commit(a_empty(sa));
           if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
-          if (w.next(p, ps, done)) {
-            tc_commit(acc_full0 + 8 * buf);
-            ++chunk; fresh = true;
-          }
         }
       }
       if ((p.dbg & 32) && blockIdx.x == 0)
@@ -548,7 +575,7 @@ __global__ void tc_fold_kernel(float* __restrict__ Y, long long y_bs, int y_rs, 
 }
 
 inline size_t tc_smem_bytes() {
-  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 18 * 8 + (size_t)8 * 32 * kTcScrPitch * 4;
+  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 22 * 8 + (size_t)8 * 32 * kTcScrPitch * 4;
 }
 
 // ---- host: the tensor-core view of one conv launch (passes x groups, no tensor pointers yet) --------
@@ -615,6 +642,7 @@ inline TcArgs tc_make_args(const ConvArgs& a, const TcOp& op, float* side, int t
   t.side = (PL + PR) > 0 ? side : nullptr;
   t.n_pass = op.n_pass;
   t.terms = terms;
+  { static const int cs = getenv("AVC_TC_CHUNK") ? atoi(getenv("AVC_TC_CHUNK")) : kTcChunkSteps; t.chunk_steps = cs; }
   { static const int dbg = getenv("AVC_TC_DBG") ? atoi(getenv("AVC_TC_DBG")) : 0; t.dbg = dbg; }
   for (int q = 0; q < op.n_pass; ++q) t.pass[q] = op.pass[q];
   for (int g = 0; g < op.n_groups; ++g) t.g[g] = op.g[g];
