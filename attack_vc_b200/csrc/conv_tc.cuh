@@ -464,23 +464,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
     }
   } else if (warp < 6) {
     // ===== loaders (128 threads): window gather + TF32 split =====
+    // Thread tl owns window row tl (8 float4 per K block); the <= 7 rows past 128 are spread one float4
+    // per thread.  The loads of K block kb+1 are issued right after K block kb is stored, so they fly
+    // while the thread waits for the stage to be released.
     pdl_wait();
     const int tl = threadIdx.x - 64;   // 0..127
+    const int er = tl >> 3, ec = tl & 7;   // my share of the extra rows: row 128 + er, chunk ec
     int sa = 0; uint32_t pa = 0;
+    const bool skip = (p.dbg & 2) != 0;
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const TcPass& ps = p.pass[wk % p.n_pass];
       const long long v0 = (long long)(wk / p.n_pass) * kTcM;
       for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
         const TcGroup& G = p.g[gi];
-        const int nrows = kTcM + G.n_taps - 1;
-        // source rows of my (up to two) window rows
-        const float* src[2]; const float* msk[2]; bool have[2];
+        const float* src[2]; const float* msk[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int i = tl + j * kTcM;
-          have[j] = i < nrows;
+          const int i = j == 0 ? tl : kTcM + er;
           src[j] = nullptr; msk[j] = nullptr;
-          if (have[j]) {
+          if (j == 0 || er < G.n_taps - 1) {
             const long long u = v0 + i;
             const int b = (int)(u / p.Pv);
             const int pos = G.sg * (int)(u - (long long)b * p.Pv) + G.off0;
@@ -489,42 +491,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
               rr = rr < 0 ? -rr : rr;
               if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
             }
-            if (b < p.B && rr >= 0 && rr < p.T_a) {
+            if (b < p.B && rr >= 0 && rr < p.T_a && !skip) {
               src[j] = p.A + (long long)b * p.a_bs + (long long)rr * p.a_rs + G.a_ch_off;
               if (p.Mk) msk[j] = p.Mk + (long long)b * p.m_bs + (long long)rr * p.m_rs + G.a_ch_off;
             }
           }
         }
+        const bool have_e = er < G.n_taps - 1;
         const int nkb = (G.kc + kTcKB - 1) / kTcKB;
-        for (int kb = 0; kb < nkb; ++kb) {
+        float4 v[kTcKB / 4], m[kTcKB / 4], ve, me;
+        auto fetch = [&](int kb) {
           const int kb0 = kb * kTcKB, kbs = min(kTcKB, G.kc - kb0);
+#pragma unroll
+          for (int c = 0; c < kTcKB / 4; ++c) v[c] = (src[0] && 4 * c < kbs) ? ld4(src[0] + kb0 + 4 * c) : f4zero();
+          ve = (src[1] && 4 * ec < kbs) ? ld4(src[1] + kb0 + 4 * ec) : f4zero();
+          if (p.Mk) {
+#pragma unroll
+            for (int c = 0; c < kTcKB / 4; ++c) m[c] = (msk[0] && 4 * c < kbs) ? ld4(msk[0] + kb0 + 4 * c) : f4zero();
+            me = (msk[1] && 4 * ec < kbs) ? ld4(msk[1] + kb0 + 4 * ec) : f4zero();
+          }
+        };
+        fetch(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int kbs = min(kTcKB, G.kc - kb * kTcKB);
           mbar_wait(a_empty(sa), pa ^ 1);
           float* hi = As + (size_t)sa * 2 * kTcAPlane;
           float* lo = hi + kTcAPlane;
+          if (p.Mk) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (!have[j] || (p.dbg & 2)) continue;
-            const int i = tl + j * kTcM;
-            float4 v[kTcKB / 4];
+            for (int c = 0; c < kTcKB / 4; ++c) v[c] = dact4mul(v[c], m[c], p.slope);
+            ve = dact4mul(ve, me, p.slope);
+          }
 #pragma unroll
-            for (int c = 0; c < kTcKB / 4; ++c) v[c] = (src[j] && 4 * c < kbs) ? ld4(src[j] + kb0 + 4 * c) : f4zero();
-            if (msk[j]) {
-#pragma unroll
-              for (int c = 0; c < kTcKB / 4; ++c)
-                if (4 * c < kbs) v[c] = dact4mul(v[c], ld4(msk[j] + kb0 + 4 * c), p.slope);
-            }
-#pragma unroll
-            for (int c = 0; c < kTcKB / 4; ++c) {
-              if (4 * c >= kbs) break;
-              const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
-              st4(hi + ((size_t)c * kTcRows + i) * 4, h);
-              st4(lo + ((size_t)c * kTcRows + i) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
-            }
+          for (int c = 0; c < kTcKB / 4; ++c) {
+            if (4 * c >= kbs) break;
+            const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
+            st4(hi + ((size_t)c * kTcRows + tl) * 4, h);
+            st4(lo + ((size_t)c * kTcRows + tl) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
+          }
+          if (have_e && 4 * ec < kbs) {
+            const float4 h = make_float4(tf32_hi(ve.x), tf32_hi(ve.y), tf32_hi(ve.z), tf32_hi(ve.w));
+            st4(hi + ((size_t)ec * kTcRows + kTcM + er) * 4, h);
+            st4(lo + ((size_t)ec * kTcRows + kTcM + er) * 4, make_float4(tf32_hi(ve.x - h.x), tf32_hi(ve.y - h.y), tf32_hi(ve.z - h.z), tf32_hi(ve.w - h.w)));
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(sa));
           if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+          if (kb + 1 < nkb) fetch(kb + 1);
         }
       }
     }

@@ -50,6 +50,18 @@ __global__ void k(long long* out) {
       tc_commit(b0); mbar_wait(b0, ph); ph ^= 1;
       out[o++] = clock64() - t0;
     }
+    // A-operand alignment: start offset (tap shift) and LBO (bytes between the two K chunks)
+    {
+      const uint32_t offs[4] = {0, 16, 64, 0};
+      const uint32_t lbos[4] = {136 * 16, 136 * 16, 136 * 16, 137 * 16};
+      for (int v = 0; v < 4; ++v) {
+        const uint64_t dav = tc_desc(a + offs[v], lbos[v], 128);
+        long long t0 = clock64();
+        for (int i = 0; i < 240; ++i) tc_mma_tf32(tm, dav, db, idesc, 1);
+        tc_commit(b0); mbar_wait(b0, ph); ph ^= 1;
+        out[16 + v] = clock64() - t0;
+      }
+    }
     // same with a tcgen05.commit after every group (to 20 distinct single-use barriers), as the conv kernel does
     {
       long long t0 = clock64();
@@ -66,16 +78,17 @@ __global__ void k(long long* out) {
 }
 
 int main() {
-  long long* out; long long h[16];
-  cudaMalloc(&out, 128);
+  long long* out; long long h[24];
+  cudaMalloc(&out, 256);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 141000);
   for (int rep = 0; rep < 2; ++rep) {
     k<<<1, 128, 141000>>>(out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-    cudaMemcpy(h, out, 120, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, out, 160, cudaMemcpyDeviceToHost);
     const int ns[6] = {1, 3, 12, 36, 120, 480};
     for (int t = 0; t < 6; ++t) printf("n=%3d MMAs: total %6lld clk (issue %5lld) -> %.1f clk/MMA\n", ns[t], h[2 * t], h[2 * t + 1], (double)h[2 * t] / ns[t]);
+    printf("240 MMAs, A start +0/LBO 2176: %lld clk | +16 B: %lld | +64 B: %lld | +0/LBO 2192: %lld\n", h[16], h[17], h[18], h[19]);
     printf("240 MMAs in 20 groups: no fence %lld clk, fence::after_thread_sync per group %lld clk, commit per group %lld clk\n", h[12], h[13], h[14]);
   }
   return 0;
