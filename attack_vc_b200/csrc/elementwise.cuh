@@ -38,12 +38,16 @@ __global__ void layout_out_kernel(const float* __restrict__ src, long long s_bs,
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm1d(affine=False) + AdaIN + act (+ skip)            (models.py:66-79, 176, 396, 414-431)
 //   out[b,t,c] = act( ((y - mu_bc) * rstd_bc) * std_bc + mean_bc ) + skip
-// grid (B, C/16); 256 threads = 4 float4 channel lanes x 64 time lanes.  Statistics are two-pass
-// (mean, then centred sum of squares; biased variance, eps 1e-5) -- the re-reads hit L1/L2, HBM sees
-// each tensor once: 8 B/element forward (+4 with a skip), 12 B/element backward.
+// grid (B, C/32); 256 threads = 8 float4 channel lanes (one full 128-byte line per row) x 32 time
+// lanes.  The CTA's [T, 32] slice is staged in shared memory while the first pass sums it, so the
+// centred second pass and the normalising third pass never go back to HBM: 8 B/element forward
+// (+4 with a skip), 12 B/element backward, each tensor touched exactly once.  Statistics are
+// two-pass (mean, then centred sum of squares; biased variance, eps 1e-5) and every reduction has
+// a fixed order.  Slices longer than the staging capacity fall back to re-reading (L2).
 // ---------------------------------------------------------------------------------------------
-constexpr int kNormCh = 16;
-constexpr int kNormTL = 64;
+constexpr int kNormCh = 32;
+constexpr int kNormTL = 32;
+constexpr int kNormSmemMax = 216 * 1024;
 
 struct NormArgs {
   const float* y; int T; int C;        // [B,T,C] contiguous conv output (already pixel-shuffled)
@@ -53,27 +57,34 @@ struct NormArgs {
   float* out;                          // [B,T,C]
   ResArgs res;
   float slope;
+  int stage;                           // 1: the slice fits the dynamic shared memory of this launch
 };
 
-__device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[4], int lane_c, int lane_t) {
-  // reduce over the 64 time lanes for each of the 4 float4 channel lanes; result broadcast
-  red[lane_t][lane_c] = v;
-  __syncthreads();
-  for (int s = kNormTL / 2; s > 0; s >>= 1) {
-    if (lane_t < s) red[lane_t][lane_c] = f4add(red[lane_t][lane_c], red[lane_t + s][lane_c]);
-    __syncthreads();
+// sum over the 32 time lanes for each of the 8 float4 channel lanes; result broadcast to all threads
+__device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[8], int lane_c) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
   }
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < 8) red[warp][lane_c] = v;
+  __syncthreads();
   float4 r = red[0][lane_c];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = f4add(r, red[w][lane_c]);
   __syncthreads();
   return r;
 }
 
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
+  extern __shared__ __align__(16) float4 ntile[];   // [T][8] when p.stage
+  __shared__ float4 red[8][8];
   pdl_enter();
-  __shared__ float4 red[kNormTL][4];
-  const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
-  const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
+  const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
+  const int b = blockIdx.x, c = blockIdx.y * kNormCh + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
+  const bool staged = p.stage && !p.stats_in;
   float4 mu, rstd;
   if (p.stats_in) {
     const float* s = p.stats_in + ((long long)b * p.C + c) * 2;
@@ -82,17 +93,21 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
     rstd = make_float4(s0.y, s0.w, s1.y, s1.w);
   } else {
     float4 sum = f4zero();
-    for (int t = lane_t; t < p.T; t += kNormTL) sum = f4add(sum, ld4(yb + (long long)t * p.C));
-    sum = block_reduce_t(sum, red, lane_c, lane_t);
+    for (int t = lane_t; t < p.T; t += kNormTL) {
+      const float4 v = ld4(yb + (long long)t * p.C);
+      if (staged) ntile[t * 8 + lane_c] = v;
+      sum = f4add(sum, v);
+    }
+    sum = block_reduce_t(sum, red, lane_c);
     const float invT = 1.f / (float)p.T;
     mu = f4scale(sum, invT);
     float4 sq = f4zero();
     for (int t = lane_t; t < p.T; t += kNormTL) {
-      float4 v = ld4(yb + (long long)t * p.C);
+      const float4 v = staged ? ntile[t * 8 + lane_c] : ld4(yb + (long long)t * p.C);
       float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
       sq.x = fmaf(dx, dx, sq.x); sq.y = fmaf(dy, dy, sq.y); sq.z = fmaf(dz, dz, sq.z); sq.w = fmaf(dw, dw, sq.w);
     }
-    sq = block_reduce_t(sq, red, lane_c, lane_t);
+    sq = block_reduce_t(sq, red, lane_c);
     rstd = make_float4(rsqrtf(sq.x * invT + 1e-5f), rsqrtf(sq.y * invT + 1e-5f),
                        rsqrtf(sq.z * invT + 1e-5f), rsqrtf(sq.w * invT + 1e-5f));
   }
@@ -109,7 +124,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
   }
   float* ob = p.out + (long long)b * p.T * p.C + c;
   for (int t = lane_t; t < p.T; t += kNormTL) {
-    float4 v = ld4(yb + (long long)t * p.C);
+    const float4 v = staged ? ntile[t * 8 + lane_c] : ld4(yb + (long long)t * p.C);
     float4 a;
     a.x = fmaf((v.x - mu.x) * rstd.x, cs.x, cm.x);
     a.y = fmaf((v.y - mu.y) * rstd.y, cs.y, cm.y);
@@ -130,13 +145,15 @@ struct NormBwdArgs {
   float* gcond; int gcond_bs;   // row b: d mean at [0,C), d std at [C,2C); nullptr for plain InstanceNorm
   int T; int C;
   float slope;
+  int stage;            // 1: y and g slices both fit the dynamic shared memory of this launch
 };
 
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) {
+  extern __shared__ __align__(16) float4 ntile[];   // [T][8][2] (xhat, ga) when p.stage
+  __shared__ float4 red[8][8];
   pdl_enter();
-  __shared__ float4 red[kNormTL][4];
-  const int b = blockIdx.x, c = blockIdx.y * kNormCh + (threadIdx.x & 3) * 4;
-  const int lane_c = threadIdx.x & 3, lane_t = threadIdx.x >> 2;
+  const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
+  const int b = blockIdx.x, c = blockIdx.y * kNormCh + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
   const float* gb = p.g + (long long)b * p.T * p.C + c;
   const float* s = p.stats + ((long long)b * p.C + c) * 2;
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
     cm = ld4(p.cond + (long long)b * p.cond_bs + c);
     cs = ld4(p.cond + (long long)b * p.cond_bs + p.C + c);
   }
+  const bool staged = p.stage && p.gy;
   // pass 1: S1 = sum_t ga, S2 = sum_t ga * xhat,  ga = g * act'(a)
   float4 S1 = f4zero(), S2 = f4zero();
   for (int t = lane_t; t < p.T; t += kNormTL) {
@@ -154,11 +172,12 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
     const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
     const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
     const float4 ga = dact4mul(g, a, p.slope);
+    if (staged) { ntile[(t * 8 + lane_c) * 2] = xh; ntile[(t * 8 + lane_c) * 2 + 1] = ga; }
     S1 = f4add(S1, ga);
     S2.x = fmaf(ga.x, xh.x, S2.x); S2.y = fmaf(ga.y, xh.y, S2.y); S2.z = fmaf(ga.z, xh.z, S2.z); S2.w = fmaf(ga.w, xh.w, S2.w);
   }
-  S1 = block_reduce_t(S1, red, lane_c, lane_t);
-  S2 = block_reduce_t(S2, red, lane_c, lane_t);
+  S1 = block_reduce_t(S1, red, lane_c);
+  S2 = block_reduce_t(S2, red, lane_c);
   if (p.gcond && lane_t == 0) {
     st4(p.gcond + (long long)b * p.gcond_bs + c, S1);
     st4(p.gcond + (long long)b * p.gcond_bs + p.C + c, S2);
@@ -170,10 +189,15 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
   const float4 k = make_float4(rstd.x * cs.x, rstd.y * cs.y, rstd.z * cs.z, rstd.w * cs.w);
   float* ob = p.gy + (long long)b * p.T * p.C + c;
   for (int t = lane_t; t < p.T; t += kNormTL) {
-    const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
-    const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
-    const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
-    const float4 ga = dact4mul(g, a, p.slope);
+    float4 xh, ga;
+    if (staged) {
+      xh = ntile[(t * 8 + lane_c) * 2]; ga = ntile[(t * 8 + lane_c) * 2 + 1];
+    } else {
+      const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
+      xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
+      const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
+      ga = dact4mul(g, a, p.slope);
+    }
     float4 o;
     o.x = k.x * (ga.x - m1.x - xh.x * m2.x);
     o.y = k.y * (ga.y - m1.y - xh.y * m2.y);

@@ -201,6 +201,8 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(conv_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
+  CK(cudaFuncSetAttribute(norm_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
 }
 
@@ -399,7 +401,10 @@ void emit_norm_fwd(Emitter& E, const float* y, int B, int T, int C, const float*
   n.out = outp; n.res = res; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
   dim3 grid(B, C / kNormCh);
-  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid](cudaStream_t st) { launch_k(norm_act_fwd_kernel, grid, 256, 0, st, n); });
+  const size_t smem = (size_t)T * kNormCh * sizeof(float);
+  n.stage = smem <= (size_t)kNormSmemMax ? 1 : 0;
+  const size_t dyn = n.stage ? smem : 0;
+  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid, dyn](cudaStream_t st) { launch_k(norm_act_fwd_kernel, grid, 256, dyn, st, n); });
 }
 
 void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stats, const float* cond, int cond_bs,
@@ -407,8 +412,12 @@ void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stat
   NormBwdArgs n{};
   n.g = g; n.y = y; n.stats = stats; n.cond = cond; n.cond_bs = cond_bs; n.gy = gy; n.gcond = gcond; n.gcond_bs = gcond_bs;
   n.T = T; n.C = C; n.slope = slope;
+  if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
   dim3 grid(B, C / kNormCh);
-  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid](cudaStream_t st) { launch_k(norm_act_bwd_kernel, grid, 256, 0, st, n); });
+  const size_t smem = (size_t)T * kNormCh * sizeof(float) * 2;
+  n.stage = (gy && smem <= (size_t)kNormSmemMax) ? 1 : 0;
+  const size_t dyn = n.stage ? smem : 0;
+  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid, dyn](cudaStream_t st) { launch_k(norm_act_bwd_kernel, grid, 256, dyn, st, n); });
 }
 
 // ---- encoder (speaker / content) ------------------------------------------------------------------
