@@ -164,8 +164,20 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("AVC_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; the contract is ONE
+        # JSON line there, so stdout is pointed at stderr until the communicator exists.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from attack_vc_b200 import Engine
     from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs
