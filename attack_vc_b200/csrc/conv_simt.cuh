@@ -299,18 +299,22 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   for (int gi = g_lo; gi < g_hi; ++gi) n_slabs += p.g[gi].n_taps;
 
   // ---- weight ring: slab q = (group, tap) in issue order ----------------------------------------
-  int is_g = g_lo, is_tap = 0;   // next slab to issue
+  // thread constants of the copy: 16-byte column chunk wn of K rows wk, wk + 32, ...
+  const int wk = tid >> 3, wn = (tid & 7) << 2;
+  const bool wok = (n0 + wn) < Ntot;
+  int is_g = g_lo, is_tap = 0, is_slot = 0;   // next slab to issue and the ring slot it goes to
   auto issue = [&](int q) {
     if (q < n_slabs) {
       const TapGroup& G = p.g[is_g];
-      const float* Wg = G.W + (long long)is_tap * G.wts * Ntot + n0;
-      float* dst = Wr + (size_t)(q % p.ring) * p.slab_floats;
-      for (int idx = tid; idx < G.kc * (kSmTN / 4); idx += NT) {
-        const int k = idx >> 3, n = (idx & 7) << 2;
-        const bool ok = (n0 + n) < Ntot;
-        cp_async16(dst + k * kSmTN + n, ok ? Wg + (long long)k * Ntot + n : G.W, ok);
+      const float* src = wok ? G.W + ((long long)is_tap * G.wts + wk) * Ntot + n0 + wn : G.W;
+      float* dst = Wr + (size_t)is_slot * p.slab_floats + wk * kSmTN + wn;
+      const long long sstep = wok ? 32LL * Ntot : 0;
+      for (int k = wk; k < G.kc; k += 32) {
+        cp_async16(dst, src, wok);
+        src += sstep; dst += 32 * kSmTN;
       }
       if (++is_tap == G.n_taps) { is_tap = 0; ++is_g; }
+      if (++is_slot == p.ring) is_slot = 0;
     }
     cp_async_commit();
   };
@@ -328,8 +332,11 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     const int c4n = G.kc >> 2;
     const float* Ab = p.A + (long long)b * p.a_bs + G.a_ch_off;
     const float* Mb = p.Mk ? p.Mk + (long long)b * p.m_bs + G.a_ch_off : nullptr;
-    for (int idx = tid; idx < wg.nrows * c4n; idx += NT) {
-      const int row = idx / c4n, c = (idx - row * c4n) << 2;
+    const int drow = NT / c4n, dcol = NT - drow * c4n;   // idx += NT without a division per element
+    int row = tid / c4n, col = tid - row * c4n;
+    for (int idx = tid; idx < wg.nrows * c4n; idx += NT, row += drow, col += dcol) {
+      if (col >= c4n) { col -= c4n; ++row; }
+      const int c = col << 2;
       const int r = wg.wlo + row;
       int rr; bool ok;
       if (!p.bwd) {
@@ -357,6 +364,7 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   int rb[RM][3];
   bool edge = false;
   int cg = g_lo - 1, ctap = 0, cnt = 0;   // group / tap of the slab being consumed
+  int c_slot = 0;                          // ring slot of the slab being consumed
   const float* Sg = S;
   int kc = 0;
   for (int q = 0; q < n_slabs; ++q) {
@@ -380,7 +388,8 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     cp_async_wait_dyn(p.ring - 2);
     __syncthreads();                     // slab q landed for everyone; everyone is done with slab q-1 (and, first time, the windows are visible)
     issue(q + p.ring - 1);               // refills the buffer slab q-1 used
-    const float* Wsub = Wr + (size_t)(q % p.ring) * p.slab_floats;
+    const float* Wsub = Wr + (size_t)c_slot * p.slab_floats;
+    if (++c_slot == p.ring) c_slot = 0;
     const int k_lo = warp * 16, k_hi = min(k_lo + 16, kc);
     for (int k4 = k_lo; k4 < k_hi; k4 += 4) {
       float4 a[RM];
