@@ -48,6 +48,8 @@ EXPORTS = [
     "avc_conv1d_dgrad", "avc_instnorm_adain_act_fwd", "avc_instnorm_adain_act_bwd", "avc_adam_tanh_step",
     "avc_kernel_launches", "avc_launches_per_iter", "avc_version",
     "avc_attack_begin", "avc_attack_step", "avc_attack_end", "avc_session_launches", "avc_session_profile",
+    "avc_pm_create", "avc_pm_destroy", "avc_pm_last_error", "avc_pm_load_weights", "avc_pm_out_shape", "avc_pm_forward",
+    "avc_pm_train_step", "avc_pm_kernel_launches",
 ]
 
 _lib = None
@@ -93,6 +95,17 @@ def load() -> C.CDLL:
     lib.avc_kernel_launches.restype = i64
     lib.avc_launches_per_iter.argtypes = [vp]
     lib.avc_launches_per_iter.restype = i32
+    lib.avc_pm_create.argtypes = [P(vp), C.c_int]
+    lib.avc_pm_destroy.argtypes = [vp]
+    lib.avc_pm_destroy.restype = None
+    lib.avc_pm_last_error.argtypes = [vp]
+    lib.avc_pm_last_error.restype = C.c_char_p
+    lib.avc_pm_load_weights.argtypes = [vp, P(WeightView), i32]
+    lib.avc_pm_out_shape.argtypes = [i32, i32, P(i32), P(i32)]
+    lib.avc_pm_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.avc_pm_train_step.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, P(WeightView), i32, vp]
+    lib.avc_pm_kernel_launches.argtypes = [vp]
+    lib.avc_pm_kernel_launches.restype = i64
     lib.avc_version.argtypes = []
     lib.avc_version.restype = C.c_char_p
     _lib = lib

@@ -1,0 +1,850 @@
+// predictive.cu -- VSMask PredictiveModel (reference models/predictive_model.py:6-110)
+// on B200: eval forward, training forward (BatchNorm batch statistics) and the full backward
+// (dgrad + wgrad + BatchNorm / PReLU / bias gradients) of   loss = mean(out^2)   (BASELINE config 5).
+//
+// Layout: NHWC fp32 (the [B,1,F,T] input and output of the reference are NHWC with C = 1 as they are).
+// All reductions are two-stage with a fixed order (no float atomics).  Round-1 status: direct
+// CUDA-core kernels, correct and measured, not yet tuned (see DESIGN.md "Row P").
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/avc_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+using namespace avc;
+
+namespace {
+
+thread_local std::string g_pm_create_error;
+
+// ---- generic 3x3 gather convolution ---------------------------------------------------------------
+// y[b,oh,ow,co] = epi( sum_{kh,kw,ci} x[b, ih(oh,kh), iw(ow,kw), ci] * w[kh][kw][ci][co] )
+enum PmMode : int {
+  PM_REFLECT = 0,   // ih = reflect(oh*sh + kh - 1)                     Conv2d after ReflectionPad2d(1)
+  PM_TRANSPOSED = 1,// ih = (oh - kh)/sh when divisible and in range     ConvTranspose2d forward; conv dgrad on padded coords
+  PM_PLAIN = 2      // ih = oh*sh + kh                                   ConvTranspose2d dgrad
+};
+struct PmConv {
+  const float* x; int Hi, Wi, Ci;
+  const float* w;                 // [9][Ci][Cop], Cop = Co rounded up to 4
+  const float* bias;              // [Cop] or nullptr
+  const float* scale; const float* shift;   // [Cop] or nullptr: v = v*scale + shift (folded eval BatchNorm)
+  const float* dmask;             // optional tensor shaped like y: v *= dmask > 0 ? 1 : mslope (backward through LeakyReLU)
+  float mslope;
+  float* y; int Ho, Wo, Co, Cop;
+  int B, mode, sh, sw;
+  float slope; int act;           // 0 none, 1 x>0?x:slope*x, 2 the same then tanh
+};
+
+__device__ __forceinline__ int pm_src(int o, int k, int n_in, int s, int mode) {
+  if (mode == PM_REFLECT) {
+    int i = o * s + k - 1;
+    i = i < 0 ? -i : i;
+    if (i >= n_in) i = 2 * (n_in - 1) - i;
+    return i;
+  }
+  if (mode == PM_TRANSPOSED) {
+    const int t = o - k;
+    if (t < 0 || t % s) return -1;
+    const int i = t / s;
+    return i < n_in ? i : -1;
+  }
+  return o * s + k;
+}
+
+template <bool CI1>
+__global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
+  const int co = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  const long long pg = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  const int wg = (p.Wo + 3) / 4;
+  const long long npg = (long long)p.B * p.Ho * wg;
+  if (pg >= npg || co >= p.Cop) return;
+  const int ow0 = (int)(pg % wg) * 4;
+  const long long t = pg / wg;
+  const int oh = (int)(t % p.Ho), b = (int)(t / p.Ho);
+  float acc[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = pm_src(oh, kh, p.Hi, p.sh, p.mode);
+    if (ih < 0 || ih >= p.Hi) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      int iw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        iw[q] = (ow0 + q < p.Wo) ? pm_src(ow0 + q, kw, p.Wi, p.sw, p.mode) : -1;
+        if (iw[q] >= p.Wi) iw[q] = -1;
+      }
+      const float* wt = p.w + (size_t)(kh * 3 + kw) * p.Ci * p.Cop + co;
+      const float* xr = p.x + ((long long)(b * p.Hi + ih) * p.Wi) * p.Ci;
+      if (CI1) {
+        const float4 w4 = ld4(wt);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = iw[q] >= 0 ? xr[iw[q]] : 0.f;
+          acc[q][0] = fmaf(a, w4.x, acc[q][0]); acc[q][1] = fmaf(a, w4.y, acc[q][1]);
+          acc[q][2] = fmaf(a, w4.z, acc[q][2]); acc[q][3] = fmaf(a, w4.w, acc[q][3]);
+        }
+      } else {
+        for (int ci = 0; ci < p.Ci; ci += 4) {
+          float4 a[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a[q] = iw[q] >= 0 ? ld4(xr + (long long)iw[q] * p.Ci + ci) : f4zero();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 w4 = ld4(wt + (size_t)(ci + c) * p.Cop);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float av = c == 0 ? a[q].x : c == 1 ? a[q].y : c == 2 ? a[q].z : a[q].w;
+              acc[q][0] = fmaf(av, w4.x, acc[q][0]); acc[q][1] = fmaf(av, w4.y, acc[q][1]);
+              acc[q][2] = fmaf(av, w4.z, acc[q][2]); acc[q][3] = fmaf(av, w4.w, acc[q][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
+  float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (ow0 + q >= p.Wo) continue;
+    float v[4] = {fmaf(acc[q][0] + bias.x, sc.x, sf.x), fmaf(acc[q][1] + bias.y, sc.y, sf.y),
+                  fmaf(acc[q][2] + bias.z, sc.z, sf.z), fmaf(acc[q][3] + bias.w, sc.w, sf.w)};
+    const long long o = ((long long)(b * p.Ho + oh) * p.Wo + ow0 + q) * p.Co + co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (co + j >= p.Co) continue;
+      float x = v[j];
+      if (p.dmask) x *= p.dmask[o + j] > 0.f ? 1.f : p.mslope;
+      if (p.act) x = x > 0.f ? x : x * p.slope;
+      if (p.act == 2) x = tanhf(x);
+      p.y[o + j] = x;
+    }
+  }
+}
+
+// ---- per-channel reductions over the N = B*H*W pixels of an NHWC tensor --------------------------------
+// stage 1: grid (G, 1); thread = (channel float4 lane, row lane); partial[G][4 quantities][C]
+//   kind 0 (BatchNorm forward): q0 = sum y, q1 = sum y^2
+//   kind 1 (BatchNorm/PReLU backward): with yn = y*scale+shift, gyn = gz * (yn > 0 ? 1 : a), xh = (y-mean)*rstd:
+//                                      q0 = sum gyn, q1 = sum gyn*xh, q2 = sum gz*yn*[yn <= 0]  (PReLU slope gradient)
+//   kind 2 (bias gradient): q0 = sum g
+struct PmReduce {
+  const float* y; const float* g; long long N; int C;
+  const float* scale; const float* shift; const float* mean; const float* rstd; float a;
+  int kind;
+  float* partial;   // [G][3][C]
+};
+__global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
+  extern __shared__ float4 pm_red[];   // [rowlanes][3][C4]
+  const int C4 = p.C >> 2;
+  const int cl = threadIdx.x % C4, rl = threadIdx.x / C4, RL = blockDim.x / C4;
+  float4 q0 = f4zero(), q1 = f4zero(), q2 = f4zero();
+  if (rl < RL) {
+    const long long per = (p.N + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = min(p.N, lo + per);
+    float4 sc = f4zero(), sf = f4zero(), mu = f4zero(), rs = f4zero();
+    if (p.kind == 1) { sc = ld4(p.scale + 4 * cl); sf = ld4(p.shift + 4 * cl); mu = ld4(p.mean + 4 * cl); rs = ld4(p.rstd + 4 * cl); }
+    for (long long i = lo + rl; i < hi; i += RL) {
+      if (p.kind == 0) {
+        const float4 v = ld4(p.y + i * p.C + 4 * cl);
+        q0 = f4add(q0, v);
+        q1.x = fmaf(v.x, v.x, q1.x); q1.y = fmaf(v.y, v.y, q1.y); q1.z = fmaf(v.z, v.z, q1.z); q1.w = fmaf(v.w, v.w, q1.w);
+      } else if (p.kind == 1) {
+        const float4 v = ld4(p.y + i * p.C + 4 * cl), gz = ld4(p.g + i * p.C + 4 * cl);
+        const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gz.x, gz.y, gz.z, gz.w};
+        const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, f4[4] = {sf.x, sf.y, sf.z, sf.w}, m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w};
+        float o0[4], o1[4], o2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float yn = fmaf(vv[j], s4[j], f4[j]);
+          const float gyn = gg[j] * (yn > 0.f ? 1.f : p.a);
+          const float xh = (vv[j] - m4[j]) * r4[j];
+          o0[j] = gyn; o1[j] = gyn * xh; o2[j] = yn > 0.f ? 0.f : gg[j] * yn;
+        }
+        q0 = f4add(q0, make_float4(o0[0], o0[1], o0[2], o0[3]));
+        q1 = f4add(q1, make_float4(o1[0], o1[1], o1[2], o1[3]));
+        q2 = f4add(q2, make_float4(o2[0], o2[1], o2[2], o2[3]));
+      } else {
+        q0 = f4add(q0, ld4(p.g + i * p.C + 4 * cl));
+      }
+    }
+    pm_red[(rl * 3 + 0) * C4 + cl] = q0; pm_red[(rl * 3 + 1) * C4 + cl] = q1; pm_red[(rl * 3 + 2) * C4 + cl] = q2;
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 0; k < 3; ++k) {
+      float4 s = f4zero();
+      for (int r = 0; r < RL; ++r) s = f4add(s, pm_red[(r * 3 + k) * C4 + cl]);
+      st4(p.partial + ((size_t)blockIdx.x * 3 + k) * p.C + 4 * cl, s);
+    }
+  }
+}
+
+// stage 2 of the BatchNorm forward statistics: mean / biased variance -> scale, shift, saved mean / rstd,
+// and PyTorch's running-statistics update (momentum 0.1, unbiased variance).
+__global__ void pm_bn_finalize_kernel(const float* partial, int G, int C, long long N, const float* gamma, const float* beta,
+                                      float* scale, float* shift, float* mean, float* rstd,
+                                      const float* run_mean, const float* run_var, float* new_mean, float* new_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int g = 0; g < G; ++g) { s += partial[((size_t)g * 3 + 0) * C + c]; ss += partial[((size_t)g * 3 + 1) * C + c]; }
+  const double m = s / (double)N;
+  double var = ss / (double)N - m * m;
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + 1e-5));
+  mean[c] = (float)m; rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc; shift[c] = beta[c] - (float)m * sc;
+  if (new_mean) {
+    const double unb = N > 1 ? var * (double)N / (double)(N - 1) : var;
+    new_mean[c] = (float)(0.9 * run_mean[c] + 0.1 * m);
+    new_var[c] = (float)(0.9 * run_var[c] + 0.1 * unb);
+  }
+}
+
+// generic stage 2: out[k][c] = sum_g partial[g][k][c] (fixed order), k < 3
+__global__ void pm_sum_partials_kernel(const float* partial, int G, int C, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * C) return;
+  const int k = i / C, c = i - k * C;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += partial[((size_t)g * 3 + k) * C + c];
+  out[i] = (float)s;
+}
+
+// z = prelu(y*scale + shift)
+__global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const float* shift, float a, float* z, long long n4, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    const float4 v = ld4(y + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
+    float4 o = make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w));
+    st4(z + i * 4, act4(o, a));
+  }
+}
+
+// BatchNorm (training) + PReLU backward, elementwise part:
+//   gy = gamma*rstd * (gyn - sum_gyn/N - xh * sum_gyn_xh/N),  gyn = gz * prelu'(yn)
+__global__ void pm_bn_bwd_kernel(const float* y, const float* gz, const float* scale, const float* shift, const float* mean,
+                                 const float* rstd, const float* sums /*[3][C]*/, float a, float invN, float* gy, long long n4, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    const float4 v = ld4(y + i * 4), g = ld4(gz + i * 4), sc = ld4(scale + c), sf = ld4(shift + c), mu = ld4(mean + c), rs = ld4(rstd + c);
+    const float4 s0 = ld4(sums + c), s1 = ld4(sums + C + c);
+    const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w}, s4[4] = {sc.x, sc.y, sc.z, sc.w}, f4[4] = {sf.x, sf.y, sf.z, sf.w};
+    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w}, a0[4] = {s0.x, s0.y, s0.z, s0.w}, a1[4] = {s1.x, s1.y, s1.z, s1.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yn = fmaf(vv[j], s4[j], f4[j]);
+      const float gyn = gg[j] * (yn > 0.f ? 1.f : a);
+      const float xh = (vv[j] - m4[j]) * r4[j];
+      o[j] = s4[j] * (gyn - a0[j] * invN - xh * a1[j] * invN);     // scale = gamma*rstd
+    }
+    st4(gy + i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// loss = mean(out^2): g_pre = 2*out/N * (1 - out^2) * leaky'(out)   (tanh and LeakyReLU(0.2) of the last block)
+// plus per-CTA partial sums of out^2.  out has C = 1, so plain scalars.
+__global__ void __launch_bounds__(256) pm_loss_bwd_kernel(const float* out, float* gpre, long long n, float inv_n, float* partial) {
+  __shared__ float ws[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = out[i];
+    acc = fmaf(o, o, acc);
+    if (gpre) gpre[i] = 2.f * o * inv_n * (1.f - o * o) * (o > 0.f ? 1.f : 0.2f);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += ws[i];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void pm_loss_final_kernel(const float* partial, int G, float inv_n, float* loss) {
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += partial[g];
+  *loss = (float)(s * inv_n);
+}
+
+// sum of all n elements of v: per-CTA partials, then pm_sum_n_kernel
+__global__ void __launch_bounds__(256) pm_sum_all_kernel(const float* v, long long n, float* partial) {
+  __shared__ float ws[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += ws[i];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void pm_sum_n_kernel(const float* v, int n, float* out) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += v[i];
+  *out = (float)s;
+}
+
+// fold the gradient w.r.t. the reflect-padded input ([B,H+2,W+2,C]) back onto the input ([B,H,W,C])
+__global__ void pm_fold_kernel(const float* gxp, float* gx, int B, int H, int W, int C) {
+  const long long n4 = (long long)B * H * W * (C >> 2);
+  const int C4 = C >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long long t = i / C4;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H), b = (int)(t / H);
+    float4 s = f4zero();
+    // padded row 0 mirrors input row 1, padded row H+1 mirrors input row H-2 (both when H == 3)
+    for (int a = 0; a < 3; ++a) {
+      int ph;
+      if (a == 0) ph = h + 1; else if (a == 1) { if (h != 1) continue; ph = 0; } else { if (h != H - 2) continue; ph = H + 1; }
+      for (int e = 0; e < 3; ++e) {
+        int pw;
+        if (e == 0) pw = w + 1; else if (e == 1) { if (w != 1) continue; pw = 0; } else { if (w != W - 2) continue; pw = W + 1; }
+        s = f4add(s, ld4(gxp + ((long long)(b * (H + 2) + ph) * (W + 2) + pw) * C + c));
+      }
+    }
+    st4(gx + i * 4, s);
+  }
+}
+// C = 1 variant (gradient w.r.t. the model input)
+__global__ void pm_fold1_kernel(const float* gxp, float* gx, int B, int H, int W) {
+  const long long n = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H), b = (int)(t / H);
+    float s = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      int ph;
+      if (a == 0) ph = h + 1; else if (a == 1) { if (h != 1) continue; ph = 0; } else { if (h != H - 2) continue; ph = H + 1; }
+      for (int e = 0; e < 3; ++e) {
+        int pw;
+        if (e == 0) pw = w + 1; else if (e == 1) { if (w != 1) continue; pw = 0; } else { if (w != W - 2) continue; pw = W + 1; }
+        s += gxp[(long long)(b * (H + 2) + ph) * (W + 2) + pw];
+      }
+    }
+    gx[i] = s;
+  }
+}
+
+// ---- weight gradient -----------------------------------------------------------------------------------
+// gw[tap][ci][co] = sum over base pixels of A[pixA(base,tap)][ci] * G[pixG(base,tap)][co]
+//   down conv (amode PM_REFLECT): base = output pixel (oh,ow); A = block input at reflect(oh*sh+kh-1, ...); G = gy at base
+//   conv-transpose (amode PM_PLAIN): base = input pixel (ih,iw); A = x at base; G = gpre at (2ih+kh, 2iw+kw)
+// grid (S pixel slices, ci tiles of 32, 9 taps x co tiles of 32); thread = (ci lane 0..31, co float4 lane 0..7)
+struct PmWgrad {
+  const float* A; int Ha, Wa, Ci;
+  const float* G; int Hg, Wg, Co;
+  int B, Hb, Wb;        // base pixel grid
+  int up;               // 0 down conv, 1 conv-transpose
+  int sh, sw;
+  float* partial;       // [S][9][Ci][Cop]
+  int Cop;
+};
+__global__ void __launch_bounds__(256) pm_wgrad_kernel(const PmWgrad p) {
+  const int cil = threadIdx.x >> 3, co4 = threadIdx.x & 7;
+  const int ci = blockIdx.y * 32 + cil;
+  const int cot = blockIdx.z % ((p.Cop + 31) / 32), tap = blockIdx.z / ((p.Cop + 31) / 32);
+  const int co = cot * 32 + co4 * 4;
+  const int kh = tap / 3, kw = tap % 3;
+  const long long N = (long long)p.B * p.Hb * p.Wb;
+  const long long per = (N + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per, hi = min(N, lo + per);
+  float4 acc = f4zero();
+  const bool active = ci < p.Ci && co < p.Cop;
+  for (long long i = lo; i < hi; ++i) {
+    const int wb = (int)(i % p.Wb);
+    const long long t = i / p.Wb;
+    const int hb = (int)(t % p.Hb), b = (int)(t / p.Hb);
+    int ha, wa, hg, wg;
+    if (!p.up) {
+      ha = pm_src(hb, kh, p.Ha, p.sh, PM_REFLECT); wa = pm_src(wb, kw, p.Wa, p.sw, PM_REFLECT);
+      hg = hb; wg = wb;
+    } else {
+      ha = hb; wa = wb; hg = 2 * hb + kh; wg = 2 * wb + kw;
+    }
+    if (!active) continue;
+    const float a = p.A[((long long)(b * p.Ha + ha) * p.Wa + wa) * p.Ci + ci];
+    const float* gp = p.G + ((long long)(b * p.Hg + hg) * p.Wg + wg) * p.Co + co;
+    float4 g;
+    if (co + 3 < p.Co) g = ld4(gp);
+    else g = make_float4(co < p.Co ? gp[0] : 0.f, co + 1 < p.Co ? gp[1] : 0.f, co + 2 < p.Co ? gp[2] : 0.f, 0.f);
+    acc.x = fmaf(a, g.x, acc.x); acc.y = fmaf(a, g.y, acc.y); acc.z = fmaf(a, g.z, acc.z); acc.w = fmaf(a, g.w, acc.w);
+  }
+  if (active) st4(p.partial + (((size_t)blockIdx.x * 9 + tap) * p.Ci + ci) * p.Cop + co, acc);
+}
+// gw_out (PyTorch layout) = sum_s partial[s]; down: out[co][ci][kh][kw]; up: out[ci][co][kh][kw]
+__global__ void pm_wgrad_final_kernel(const float* partial, int S, int Ci, int Co, int Cop, int up, float* out) {
+  const long long n = 9LL * Ci * Co;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    long long t = i / Co;
+    const int ci = (int)(t % Ci), tap = (int)(t / Ci);
+    double s = 0.0;
+    for (int k = 0; k < S; ++k) s += partial[(((size_t)k * 9 + tap) * Ci + ci) * Cop + co];
+    const long long o = up ? ((long long)ci * Co + co) * 9 + tap : ((long long)co * Ci + ci) * 9 + tap;
+    out[o] = (float)s;
+  }
+}
+
+// ---- model ---------------------------------------------------------------------------------------------
+struct DownSpec { int ci, co, sh, sw; };
+struct UpSpec { int ci, co; };
+const DownSpec kDown[7] = {{1, 32, 1, 2}, {32, 64, 2, 2}, {64, 128, 2, 2}, {128, 256, 2, 2}, {256, 256, 2, 2}, {256, 512, 2, 2}, {512, 512, 2, 2}};
+const UpSpec kUp[5] = {{512, 256}, {256, 128}, {128, 64}, {64, 32}, {32, 1}};
+
+int pad4(int c) { return (c + 3) / 4 * 4; }
+
+struct DownW {
+  float *w = nullptr, *wt = nullptr;    // [9][ci][cop], transposed [9][co][cip]
+  float *bias = nullptr, *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
+  float *escale = nullptr, *eshift = nullptr;   // folded eval BatchNorm (+ conv bias)
+  float a = 0.25f;
+};
+struct UpW {
+  float *w = nullptr, *wt = nullptr, *bias = nullptr;
+};
+
+}  // namespace
+
+struct avc_pm_handle {
+  int device = 0, sm_count = 148;
+  Arena wmem;
+  SlabPool pool;
+  bool have_weights = false;
+  DownW down[7];
+  UpW up[5];
+  std::string err;
+  long long launches = 0;
+};
+
+namespace {
+
+template <class Fn>
+int pm_guarded(avc_pm_handle* h, Fn&& fn) {
+  try {
+    if (h) CK(cudaSetDevice(h->device));
+    fn();
+    return AVC_OK;
+  } catch (const Fail& f) {
+    if (h) h->err = f.msg; else g_pm_create_error = f.msg;
+    return f.code;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what(); else g_pm_create_error = e.what();
+    return AVC_ERR_INVALID;
+  }
+}
+
+void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
+  const int lanes = std::min(c.Cop / 4, 32);
+  dim3 block(lanes, 256 / lanes);
+  const long long npg = (long long)c.B * c.Ho * ((c.Wo + 3) / 4);
+  dim3 grid((unsigned)((npg + block.y - 1) / block.y), (unsigned)((c.Cop / 4 + lanes - 1) / lanes));
+  if (c.Ci == 1) pm_conv_kernel<true><<<grid, block, 0, st>>>(c);
+  else {
+    if (c.Ci % 4) fail(AVC_ERR_INVALID, "predictive conv: c_in %d not a multiple of 4", c.Ci);
+    pm_conv_kernel<false><<<grid, block, 0, st>>>(c);
+  }
+  CK(cudaGetLastError());
+  h->launches++;
+}
+
+int reduce_slices(long long N) { return (int)std::max<long long>(1, std::min<long long>(592, N / 256)); }
+
+// stage 1 + (for kind != 0) stage 2 of a per-channel reduction; returns G
+int launch_pm_reduce(avc_pm_handle* h, PmReduce r, cudaStream_t st) {
+  const int G = reduce_slices(r.N);
+  const int C4 = r.C / 4, RL = 256 / C4;
+  if (r.C % 4 || C4 > 256 || RL < 1) fail(AVC_ERR_INVALID, "predictive reduce: bad channel count %d", r.C);
+  const size_t smem = (size_t)RL * 3 * C4 * sizeof(float4);
+  pm_reduce_kernel<<<G, RL * C4, smem, st>>>(r);
+  CK(cudaGetLastError());
+  h->launches++;
+  return G;
+}
+
+unsigned ew_grid(long long n, int sm) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sm * 8)); }
+
+struct HostSD {
+  std::map<std::string, std::vector<float>> t;
+  std::map<std::string, std::vector<int64_t>> shape;
+  const std::vector<float>& get(const std::string& k, std::initializer_list<int64_t> want) {
+    auto it = t.find(k);
+    if (it == t.end()) fail(AVC_ERR_WEIGHTS, "missing weight '%s'", k.c_str());
+    if (shape[k] != std::vector<int64_t>(want)) fail(AVC_ERR_WEIGHTS, "weight '%s' has an unexpected shape", k.c_str());
+    return it->second;
+  }
+};
+
+// activations of one forward pass (kept for the backward)
+struct PmActs {
+  int B = 0, H[8]{}, W[8]{};        // down: spatial size after block l is H[l+1], W[l+1]; H[0], W[0] = input
+  int Hu[6]{}, Wu[6]{};             // up: Hu[0] = H[7]
+  const float* x = nullptr;
+  float* y[7]{};                    // conv outputs (pre-BatchNorm), training only
+  float* z[7]{};                    // block outputs
+  float *scale[7]{}, *shift[7]{}, *mean[7]{}, *rstd[7]{};
+  float* u[5]{};                    // up block outputs (u[4] = model output when out == nullptr)
+};
+
+void pm_shapes(PmActs& A, int B, int H, int W) {
+  A.B = B; A.H[0] = H; A.W[0] = W;
+  for (int l = 0; l < 7; ++l) {
+    if (A.H[l] < 2 || A.W[l] < 2) fail(AVC_ERR_INVALID, "predictive model: %dx%d is too small for ReflectionPad2d(1) at block %d", A.H[l], A.W[l], l);
+    A.H[l + 1] = (A.H[l] + 2 - 3) / kDown[l].sh + 1;
+    A.W[l + 1] = (A.W[l] + 2 - 3) / kDown[l].sw + 1;
+  }
+  A.Hu[0] = A.H[7]; A.Wu[0] = A.W[7];
+  for (int i = 0; i < 5; ++i) { A.Hu[i + 1] = (A.Hu[i] - 1) * 2 + 3; A.Wu[i + 1] = (A.Wu[i] - 1) * 2 + 3; }
+}
+
+// forward; training: batch statistics, conv outputs kept.  new_stats (optional): [7] pairs of device pointers
+void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* out, bool training,
+                float* const* new_mean, float* const* new_var, cudaStream_t st) {
+  A.x = x;
+  const float* in = x;
+  for (int l = 0; l < 7; ++l) {
+    const DownSpec& s = kDown[l];
+    const DownW& w = h->down[l];
+    const long long npix = (long long)A.B * A.H[l + 1] * A.W[l + 1];
+    A.z[l] = mem.f((size_t)npix * s.co);
+    PmConv c{};
+    c.x = in; c.Hi = A.H[l]; c.Wi = A.W[l]; c.Ci = s.ci;
+    c.w = w.w; c.Ho = A.H[l + 1]; c.Wo = A.W[l + 1]; c.Co = s.co; c.Cop = pad4(s.co);
+    c.B = A.B; c.mode = PM_REFLECT; c.sh = s.sh; c.sw = s.sw;
+    if (!training) {
+      c.scale = w.escale; c.shift = w.eshift; c.slope = w.a; c.act = 1; c.y = A.z[l];
+      launch_pm_conv(h, c, st);
+    } else {
+      A.y[l] = mem.f((size_t)npix * s.co);
+      A.scale[l] = mem.f(s.co); A.shift[l] = mem.f(s.co); A.mean[l] = mem.f(s.co); A.rstd[l] = mem.f(s.co);
+      c.bias = w.bias; c.y = A.y[l];
+      launch_pm_conv(h, c, st);
+      PmReduce r{};
+      r.y = A.y[l]; r.N = npix; r.C = s.co; r.kind = 0;
+      r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
+      const int G = launch_pm_reduce(h, r, st);
+      pm_bn_finalize_kernel<<<(s.co + 127) / 128, 128, 0, st>>>(r.partial, G, s.co, npix, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
+                                                               A.rstd[l], w.rmean, w.rvar, new_mean ? new_mean[l] : nullptr, new_var ? new_var[l] : nullptr);
+      CK(cudaGetLastError());
+      const long long n4 = npix * s.co / 4;
+      pm_affine_prelu_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a, A.z[l], n4, s.co);
+      CK(cudaGetLastError());
+      h->launches += 2;
+    }
+    in = A.z[l];
+  }
+  for (int i = 0; i < 5; ++i) {
+    const UpSpec& s = kUp[i];
+    const UpW& w = h->up[i];
+    const long long npix = (long long)A.B * A.Hu[i + 1] * A.Wu[i + 1];
+    A.u[i] = (i == 4 && out) ? out : mem.f((size_t)npix * s.co);
+    PmConv c{};
+    c.x = in; c.Hi = A.Hu[i]; c.Wi = A.Wu[i]; c.Ci = s.ci;
+    c.w = w.w; c.bias = w.bias; c.y = A.u[i]; c.Ho = A.Hu[i + 1]; c.Wo = A.Wu[i + 1]; c.Co = s.co; c.Cop = pad4(s.co);
+    c.B = A.B; c.mode = PM_TRANSPOSED; c.sh = 2; c.sw = 2; c.slope = 0.2f; c.act = i == 4 ? 2 : 1;
+    launch_pm_conv(h, c, st);
+    in = A.u[i];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int avc_pm_create(avc_pm_handle** out, int device) {
+  if (!out) { g_pm_create_error = "null argument"; return AVC_ERR_INVALID; }
+  *out = nullptr;
+  return pm_guarded(nullptr, [&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) fail(AVC_ERR_CUDA, "no CUDA device available (%s); libavc_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= n) fail(AVC_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp p{};
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) fail(AVC_ERR_CUDA, "device %d is sm_%d%d; libavc_b200 is built for sm_100a only", device, p.major, p.minor);
+    auto h = std::make_unique<avc_pm_handle>();
+    h->device = device; h->sm_count = p.multiProcessorCount;
+    CK(cudaFuncSetAttribute(pm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    *out = h.release();
+  });
+}
+
+void avc_pm_destroy(avc_pm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+const char* avc_pm_last_error(const avc_pm_handle* h) { return h ? h->err.c_str() : g_pm_create_error.c_str(); }
+
+int64_t avc_pm_kernel_launches(const avc_pm_handle* h) { return h ? h->launches : -1; }
+
+int avc_pm_load_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_t n) {
+  if (!h) return AVC_ERR_INVALID;
+  return pm_guarded(h, [&] {
+    if (!tensors || n <= 0) fail(AVC_ERR_INVALID, "no tensors");
+    if (h->have_weights) fail(AVC_ERR_STATE, "weights already loaded; create a new handle");
+    HostSD sd;
+    for (int i = 0; i < n; ++i) {
+      const avc_weight_view& v = tensors[i];
+      if (!v.name || !v.data || v.ndim < 0 || v.ndim > 4) fail(AVC_ERR_WEIGHTS, "bad weight view %d", i);
+      size_t cnt = 1;
+      std::vector<int64_t> shp;
+      for (int d = 0; d < v.ndim; ++d) { cnt *= (size_t)v.shape[d]; shp.push_back(v.shape[d]); }
+      std::vector<float> host(cnt);
+      CK(cudaMemcpy(host.data(), v.data, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+      sd.t[v.name] = std::move(host);
+      sd.shape[v.name] = shp;
+    }
+    for (int l = 0; l < 7; ++l) {
+      const DownSpec& s = kDown[l];
+      const std::string p = "down_blocks." + std::to_string(l) + ".conv.";
+      const auto& w = sd.get(p + "1.weight", {s.co, s.ci, 3, 3});
+      const auto& b = sd.get(p + "1.bias", {s.co});
+      const auto& g = sd.get(p + "2.weight", {s.co});
+      const auto& be = sd.get(p + "2.bias", {s.co});
+      const auto& rm = sd.get(p + "2.running_mean", {s.co});
+      const auto& rv = sd.get(p + "2.running_var", {s.co});
+      const auto& a = sd.get(p + "3.weight", {1});
+      const int cop = pad4(s.co), cip = pad4(s.ci);
+      std::vector<float> wp((size_t)9 * s.ci * cop, 0.f), wt((size_t)9 * s.co * cip, 0.f), es(cop, 0.f), ef(cop, 0.f), bp(cop, 0.f), gp(cop, 0.f), bep(cop, 0.f);
+      for (int co = 0; co < s.co; ++co)
+        for (int ci = 0; ci < s.ci; ++ci)
+          for (int t = 0; t < 9; ++t) {
+            const float v = w[((size_t)co * s.ci + ci) * 9 + t];
+            wp[((size_t)t * s.ci + ci) * cop + co] = v;
+            wt[((size_t)t * s.co + co) * cip + ci] = v;
+          }
+      for (int c = 0; c < s.co; ++c) {
+        const float sc = g[c] / std::sqrt(rv[c] + 1e-5f);
+        es[c] = sc; ef[c] = (b[c] - rm[c]) * sc + be[c];
+        bp[c] = b[c]; gp[c] = g[c]; bep[c] = be[c];
+      }
+      DownW& d = h->down[l];
+      d.w = h->wmem.upload(wp); d.wt = h->wmem.upload(wt); d.bias = h->wmem.upload(bp);
+      d.gamma = h->wmem.upload(gp); d.beta = h->wmem.upload(bep);
+      std::vector<float> rmp(cop, 0.f), rvp(cop, 1.f);
+      std::copy(rm.begin(), rm.end(), rmp.begin()); std::copy(rv.begin(), rv.end(), rvp.begin());
+      d.rmean = h->wmem.upload(rmp); d.rvar = h->wmem.upload(rvp);
+      d.escale = h->wmem.upload(es); d.eshift = h->wmem.upload(ef);
+      d.a = a[0];
+    }
+    for (int i = 0; i < 5; ++i) {
+      const UpSpec& s = kUp[i];
+      const std::string p = "up_blocks." + std::to_string(i) + ".conv_transpose.0.";
+      const auto& w = sd.get(p + "weight", {s.ci, s.co, 3, 3});
+      const auto& b = sd.get(p + "bias", {s.co});
+      const int cop = pad4(s.co), cip = pad4(s.ci);
+      std::vector<float> wp((size_t)9 * s.ci * cop, 0.f), wt((size_t)9 * s.co * cip, 0.f), bp(cop, 0.f);
+      for (int ci = 0; ci < s.ci; ++ci)
+        for (int co = 0; co < s.co; ++co)
+          for (int t = 0; t < 9; ++t) {
+            const float v = w[((size_t)ci * s.co + co) * 9 + t];
+            wp[((size_t)t * s.ci + ci) * cop + co] = v;
+            wt[((size_t)t * s.co + co) * cip + ci] = v;
+          }
+      std::copy(b.begin(), b.end(), bp.begin());
+      UpW& u = h->up[i];
+      u.w = h->wmem.upload(wp); u.wt = h->wmem.upload(wt); u.bias = h->wmem.upload(bp);
+    }
+    CK(cudaDeviceSynchronize());
+    h->have_weights = true;
+  });
+}
+
+int avc_pm_out_shape(int32_t H, int32_t W, int32_t* Ho, int32_t* Wo) {
+  if (!Ho || !Wo || H < 2 || W < 2) return AVC_ERR_INVALID;
+  try {
+    PmActs A;
+    pm_shapes(A, 1, H, W);
+    *Ho = A.Hu[5]; *Wo = A.Wu[5];
+    return AVC_OK;
+  } catch (...) {
+    return AVC_ERR_INVALID;
+  }
+}
+
+int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t training, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return pm_guarded(h, [&] {
+    if (!h->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
+    if (!x || !out || B <= 0) fail(AVC_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena mem(&h->pool);
+    PmActs A;
+    pm_shapes(A, B, H, W);
+    CK(cudaDeviceSynchronize());
+    pm_forward(h, mem, A, x, out, training != 0, nullptr, nullptr, st);
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+// One training forward/backward of loss = mean(out^2).  grads: views named like the state_dict entries
+// (weights, biases, BatchNorm weight/bias, PReLU weight), each `data` a device buffer of the PyTorch shape
+// that receives the gradient; unknown names are an error, missing ones are simply not written.
+// new_stats: optional views "down_blocks.l.conv.2.running_mean|running_var" receiving the updated statistics.
+int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, int32_t W, float* out, float* loss,
+                      float* grad_x, const avc_weight_view* grads, int32_t n_grads, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return pm_guarded(h, [&] {
+    if (!h->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
+    if (!x || B <= 0 || !loss) fail(AVC_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::map<std::string, float*> gout;
+    for (int i = 0; i < n_grads; ++i) {
+      if (!grads[i].name || !grads[i].data) fail(AVC_ERR_INVALID, "bad gradient view %d", i);
+      gout[grads[i].name] = const_cast<float*>(grads[i].data);
+    }
+    auto want = [&](const std::string& k) -> float* { auto it = gout.find(k); return it == gout.end() ? nullptr : it->second; };
+    Arena mem(&h->pool);
+    PmActs A;
+    pm_shapes(A, B, H, W);
+    float* nm[7]; float* nv[7];
+    for (int l = 0; l < 7; ++l) {
+      const std::string p = "down_blocks." + std::to_string(l) + ".conv.2.";
+      nm[l] = want(p + "running_mean"); nv[l] = want(p + "running_var");
+      if ((nm[l] == nullptr) != (nv[l] == nullptr)) fail(AVC_ERR_INVALID, "running_mean and running_var outputs must come together");
+    }
+    CK(cudaDeviceSynchronize());
+    pm_forward(h, mem, A, x, out, true, nm, nv, st);
+    const float* o = A.u[4];
+    const long long n_out = (long long)B * A.Hu[5] * A.Wu[5];
+    // ---- loss and gradient w.r.t. the last block's pre-activation ----
+    float* g = mem.f((size_t)n_out);
+    const int LG = (int)ew_grid(n_out, h->sm_count);
+    float* lpart = mem.f(LG);
+    pm_loss_bwd_kernel<<<LG, 256, 0, st>>>(o, g, n_out, 1.f / (float)n_out, lpart);
+    CK(cudaGetLastError());
+    pm_loss_final_kernel<<<1, 1, 0, st>>>(lpart, LG, 1.f / (float)n_out, loss);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst) {
+      if (!dst) return;
+      PmWgrad q{};
+      q.A = Ain; q.Ha = Ha; q.Wa = Wa; q.Ci = Ci; q.G = G; q.Hg = Hg; q.Wg = Wg; q.Co = Co;
+      q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
+      const long long N = (long long)B * Hb * Wb;
+      const int S = (int)std::max<long long>(1, std::min<long long>(64, N / 512));
+      q.partial = mem.f((size_t)S * 9 * Ci * q.Cop);
+      dim3 grid(S, (Ci + 31) / 32, 9 * ((q.Cop + 31) / 32));
+      pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
+      CK(cudaGetLastError());
+      pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(q.partial, S, Ci, Co, q.Cop, up, dst);
+      CK(cudaGetLastError());
+      h->launches += 2;
+    };
+    auto bias_grad = [&](const float* G, long long N, int C, float* dst) {
+      if (!dst) return;
+      if (C % 4) {   // single output channel (last block): sum of every element
+        if (C != 1) fail(AVC_ERR_INVALID, "bias gradient: unsupported channel count %d", C);
+        const int G2 = (int)ew_grid(N, h->sm_count);
+        float* part = mem.f(G2);
+        pm_sum_all_kernel<<<G2, 256, 0, st>>>(G, N, part);
+        CK(cudaGetLastError());
+        pm_sum_n_kernel<<<1, 1, 0, st>>>(part, G2, dst);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        return;
+      }
+      PmReduce r{};
+      r.g = G; r.N = N; r.C = C; r.kind = 2; r.partial = mem.f((size_t)reduce_slices(N) * 3 * C);
+      const int Gs = launch_pm_reduce(h, r, st);
+      float* s3 = mem.f(3 * (size_t)C);
+      pm_sum_partials_kernel<<<(3 * C + 127) / 128, 128, 0, st>>>(r.partial, Gs, C, s3);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(dst, s3, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      h->launches += 1;
+    };
+    // ---- up blocks, last to first: g = gradient w.r.t. block i's pre-activation ----
+    for (int i = 4; i >= 0; --i) {
+      const UpSpec& s = kUp[i];
+      const std::string p = "up_blocks." + std::to_string(i) + ".conv_transpose.0.";
+      const float* xin = i > 0 ? A.u[i - 1] : A.z[6];
+      const long long npix = (long long)B * A.Hu[i + 1] * A.Wu[i + 1];
+      bias_grad(g, npix, s.co, want(p + "bias"));
+      wgrad(xin, A.Hu[i], A.Wu[i], s.ci, g, A.Hu[i + 1], A.Wu[i + 1], s.co, A.Hu[i], A.Wu[i], 1, 2, 2, want(p + "weight"));
+      // dgrad: gx[ih,iw,ci] = sum_{kh,kw,co} g[2ih+kh, 2iw+kw, co] * W[ci][co][kh][kw]; then through the previous LeakyReLU
+      float* gx = mem.f((size_t)B * A.Hu[i] * A.Wu[i] * s.ci);
+      PmConv c{};
+      c.x = g; c.Hi = A.Hu[i + 1]; c.Wi = A.Wu[i + 1]; c.Ci = s.co;
+      c.w = h->up[i].wt; c.y = gx; c.Ho = A.Hu[i]; c.Wo = A.Wu[i]; c.Co = s.ci; c.Cop = pad4(s.ci);
+      c.B = B; c.mode = PM_PLAIN; c.sh = 2; c.sw = 2;
+      if (i > 0) { c.dmask = A.u[i - 1]; c.mslope = 0.2f; }
+      launch_pm_conv(h, c, st);
+      g = gx;
+    }
+    // ---- down blocks, last to first: g = gradient w.r.t. block l's output z_l ----
+    for (int l = 6; l >= 0; --l) {
+      const DownSpec& s = kDown[l];
+      const DownW& w = h->down[l];
+      const std::string p = "down_blocks." + std::to_string(l) + ".conv.";
+      const long long npix = (long long)B * A.H[l + 1] * A.W[l + 1];
+      PmReduce r{};
+      r.y = A.y[l]; r.g = g; r.N = npix; r.C = s.co; r.kind = 1;
+      r.scale = A.scale[l]; r.shift = A.shift[l]; r.mean = A.mean[l]; r.rstd = A.rstd[l]; r.a = w.a;
+      r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
+      const int Gs = launch_pm_reduce(h, r, st);
+      float* sums = mem.f(3 * (size_t)s.co);
+      pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, Gs, s.co, sums);
+      CK(cudaGetLastError());
+      if (float* d = want(p + "2.bias")) CK(cudaMemcpyAsync(d, sums, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (float* d = want(p + "2.weight")) CK(cudaMemcpyAsync(d, sums + s.co, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (float* d = want(p + "3.weight")) {   // PReLU slope: sum over channels of q2 (fixed order)
+        pm_sum_n_kernel<<<1, 1, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
+        CK(cudaGetLastError());
+      }
+      float* gy = mem.f((size_t)npix * s.co);
+      const long long n4 = npix * s.co / 4;
+      pm_bn_bwd_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], g, A.scale[l], A.shift[l], A.mean[l], A.rstd[l], sums, w.a,
+                                                              1.f / (float)npix, gy, n4, s.co);
+      CK(cudaGetLastError());
+      h->launches += 2;
+      bias_grad(gy, npix, s.co, want(p + "1.bias"));
+      const float* xin = l > 0 ? A.z[l - 1] : A.x;
+      wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"));
+      if (l == 0 && !grad_x) break;
+      // dgrad on the padded coordinates, then fold the reflect padding back
+      const int Hp = A.H[l] + 2, Wp = A.W[l] + 2;
+      const int cip = pad4(s.ci);
+      float* gxp = mem.f((size_t)B * Hp * Wp * cip);
+      PmConv c{};
+      c.x = gy; c.Hi = A.H[l + 1]; c.Wi = A.W[l + 1]; c.Ci = s.co;
+      c.w = w.wt; c.y = gxp; c.Ho = Hp; c.Wo = Wp; c.Co = s.ci; c.Cop = cip;
+      c.B = B; c.mode = PM_TRANSPOSED; c.sh = s.sh; c.sw = s.sw;
+      launch_pm_conv(h, c, st);
+      if (l > 0) {
+        float* gx = mem.f((size_t)B * A.H[l] * A.W[l] * s.ci);
+        pm_fold_kernel<<<ew_grid((long long)B * A.H[l] * A.W[l] * s.ci / 4, h->sm_count), 256, 0, st>>>(gxp, gx, B, A.H[l], A.W[l], s.ci);
+        CK(cudaGetLastError());
+        g = gx;
+      } else {
+        pm_fold1_kernel<<<ew_grid((long long)B * A.H[0] * A.W[0], h->sm_count), 256, 0, st>>>(gxp, grad_x, B, A.H[0], A.W[0]);
+        CK(cudaGetLastError());
+      }
+      h->launches += 1;
+    }
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

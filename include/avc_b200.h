@@ -153,6 +153,29 @@ int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, co
 int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float* w, float* m,
                        float* v, float* adv, int64_t n, float eps, int32_t step, void* stream);
 
+/* ---- VSMask PredictiveModel (reference models/predictive_model.py:53-110) ------------
+ * Own handle: the model is independent of AdaIN-VC.  x is the reference's [B,1,F,T] tensor (contiguous),
+ * out [B,1,F',T'] with (F',T') = avc_pm_out_shape(F,T) -- (95,63) for the (80,100) windows of vsmask.py. */
+typedef struct avc_pm_handle avc_pm_handle;
+/* replaces: PredictiveModel() (predictive_model.py:54-85) */
+int avc_pm_create(avc_pm_handle** out, int device);
+void avc_pm_destroy(avc_pm_handle* h);
+const char* avc_pm_last_error(const avc_pm_handle* h);
+/* replaces: load_state_dict (vsmask.py:27-30): the 69 tensors of PredictiveModel.state_dict() by name */
+int avc_pm_load_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_t n);
+int avc_pm_out_shape(int32_t F, int32_t T, int32_t* F_out, int32_t* T_out);
+/* replaces: PredictiveModel.forward (predictive_model.py:87-110); training != 0 uses BatchNorm batch
+ * statistics like model.train() (train_predictive.py:64), 0 the running statistics (vsmask.py:30). */
+int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int32_t F, int32_t T, int32_t training, void* stream);
+/* replaces: model.train(); out = model(x); loss = out.square().mean(); loss.backward()  (BASELINE config 5:
+ * "predictive_model forward/backward").  out (may be NULL) receives the forward result, loss one float,
+ * grad_x (may be NULL) d loss / d x; grads[i].name is a state_dict key, grads[i].data the device buffer of
+ * that tensor's shape that receives its gradient ("...running_mean"/"...running_var" receive the updated
+ * running statistics instead). */
+int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t F, int32_t T, float* out, float* loss,
+                      float* grad_x, const avc_weight_view* grads, int32_t n_grads, void* stream);
+int64_t avc_pm_kernel_launches(const avc_pm_handle* h);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 int64_t avc_kernel_launches(const avc_handle* h);   /* kernels launched (graph nodes x replays) */
 int32_t avc_launches_per_iter(const avc_handle* h); /* kernels in the last captured iteration  */

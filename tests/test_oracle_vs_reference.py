@@ -60,3 +60,35 @@ def test_attack_loop_bit_exact(oracle, ref_model, cpu_model, kind):
         r = RA.fb_attack(ref_model, inp["vc_src"], inp["vc_tgt"], inp["adv_tgt"], 0.1, n)
     o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, w0, vc_src=inp.get("vc_src"))
     assert torch.equal(r.detach(), o["adv"])
+
+
+def _ref_predictive():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_predictive_model", os.path.join(REFERENCE, "models", "predictive_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)          # by file path: models.py shadows the models/ directory
+    return m.PredictiveModel()
+
+
+def test_predictive_oracle_bit_exact():
+    from oracle import predictive_oracle as P
+    pm = _ref_predictive()
+    sd = P.pm_make_state_dict(0)
+    assert list(pm.state_dict().keys()) == list(sd.keys())
+    pm.load_state_dict(sd, strict=True)
+    x = torch.randn(3, 1, 80, 100, generator=torch.Generator().manual_seed(5))
+    pm.eval()
+    with torch.no_grad():
+        assert torch.equal(pm(x), P.pm_forward(sd, x, training=False))
+    pm.train()
+    xin = x.clone().requires_grad_(True)
+    out = pm(xin)
+    loss = out.square().mean()
+    loss.backward()
+    t = P.pm_train_step(sd, x)
+    assert torch.equal(out.detach(), t["out"]) and torch.equal(loss.detach(), t["loss"])
+    for n, prm in pm.named_parameters():
+        assert torch.equal(prm.grad, t["grads"][n]), n
+    assert torch.equal(xin.grad, t["grad_x"])
+    for k, v in t["new_stats"].items():
+        assert torch.equal(pm.state_dict()[k], v), k

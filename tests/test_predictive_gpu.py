@@ -1,0 +1,77 @@
+"""VSMask PredictiveModel on the B200 path vs the oracle (bit-identical to the reference
+module, tests/test_oracle_vs_reference.py) on the same seeded weights and inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def pm():
+    from oracle import predictive_oracle as P
+    from attack_vc_b200.predictive import PredictiveEngine
+    sd = P.pm_make_state_dict(0)
+    eng = PredictiveEngine({k: v.cuda() for k, v in sd.items()})
+    return P, sd, eng
+
+
+@pytest.mark.parametrize("B,F,T", [(2, 80, 100), (1, 80, 100), (3, 64, 77), (5, 80, 131)])
+def test_eval_forward(pm, B, F, T):
+    P, sd, eng = pm
+    x = torch.randn(B, 1, F, T, generator=torch.Generator().manual_seed(B * 100 + T))
+    ref = P.pm_forward(sd, x, training=False)
+    out = eng.forward(x.cuda(), training=False)
+    assert out.shape == ref.shape == (B, 1) + P.pm_out_shape(F, T)
+    assert rel(out, ref) < 2e-5
+    assert float(out.abs().max()) <= 1.0
+
+
+@pytest.mark.parametrize("B,F,T", [(4, 80, 100), (2, 64, 77)])
+def test_training_forward_uses_batch_statistics(pm, B, F, T):
+    P, sd, eng = pm
+    x = torch.randn(B, 1, F, T, generator=torch.Generator().manual_seed(7))
+    ref = P.pm_forward(sd, x, training=True)
+    out = eng.forward(x.cuda(), training=True)
+    assert rel(out, ref) < 5e-5
+    assert rel(out, P.pm_forward(sd, x, training=False)) > 1e-2      # the two modes really differ
+
+
+@pytest.mark.parametrize("B,F,T", [(4, 80, 100), (3, 64, 77)])
+def test_train_step_gradients(pm, B, F, T):
+    """loss = out.square().mean(): every parameter gradient (wgrad, biases, BatchNorm, PReLU), d loss / d x and
+    the running-statistics update, against autograd through the oracle."""
+    P, sd, eng = pm
+    x = torch.randn(B, 1, F, T, generator=torch.Generator().manual_seed(11))
+    ref = P.pm_train_step(sd, x)
+    got = eng.train_step(x.cuda(), want_grad_x=True)
+    assert abs(float(got["loss"]) - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    assert rel(got["out"], ref["out"]) < 5e-5
+    assert rel(got["grad_x"], ref["grad_x"]) < 2e-3
+    worst = ("", 0.0)
+    for k, g in ref["grads"].items():
+        if k.endswith("conv.1.bias"):
+            # Conv2d bias under training-mode BatchNorm: the true gradient is 0, both sides hold rounding noise
+            assert float(got["grads"][k].abs().max()) < 1e-6 + 1e-3 * float(ref["grads"]["down_blocks.0.conv.2.bias"].abs().max())
+            continue
+        e = rel(got["grads"][k], g)
+        if e > worst[1]:
+            worst = (k, e)
+    assert worst[1] < 2e-3, worst
+    for k, v in ref["new_stats"].items():
+        assert rel(got["new_stats"][k], v) < 1e-5, k
+
+
+def test_errors(pm):
+    P, sd, eng = pm
+    from attack_vc_b200 import AvcError
+    with pytest.raises(AvcError):
+        eng.forward(torch.randn(1, 1, 80, 100))                  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        eng.forward(torch.randn(1, 2, 80, 100, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.forward(torch.randn(1, 1, 80, 1, device="cuda"))     # too small for ReflectionPad2d(1)
