@@ -348,7 +348,7 @@ __global__ void pm_fold1_kernel(const float* gxp, float* gx, int B, int H, int W
 // gw[tap][ci][co] = sum over base pixels of A[pixA(base,tap)][ci] * G[pixG(base,tap)][co]
 //   down conv (amode PM_REFLECT): base = output pixel (oh,ow); A = block input at reflect(oh*sh+kh-1, ...); G = gy at base
 //   conv-transpose (amode PM_PLAIN): base = input pixel (ih,iw); A = x at base; G = gpre at (2ih+kh, 2iw+kw)
-// grid (S pixel slices, ci tiles of 32, 9 taps x co tiles of 32); thread = (ci lane 0..31, co float4 lane 0..7)
+// grid (S pixel slices, ci tiles of 64, 9 taps x co tiles of 64)
 struct PmWgrad {
   const float* A; int Ha, Wa, Ci;
   const float* G; int Hg, Wg, Co;
@@ -358,37 +358,66 @@ struct PmWgrad {
   float* partial;       // [S][9][Ci][Cop]
   int Cop;
 };
+// 64 x 64 tile of gw[tap] per CTA, the pixel axis (the GEMM K) staged 16 pixels at a time in shared memory
+// and split over gridDim.x slices; thread = 4 ci x 4 co.
+constexpr int kWgKC = 16, kWgT = 64, kWgPitch = kWgT + 4;
 __global__ void __launch_bounds__(256) pm_wgrad_kernel(const PmWgrad p) {
-  const int cil = threadIdx.x >> 3, co4 = threadIdx.x & 7;
-  const int ci = blockIdx.y * 32 + cil;
-  const int cot = blockIdx.z % ((p.Cop + 31) / 32), tap = blockIdx.z / ((p.Cop + 31) / 32);
-  const int co = cot * 32 + co4 * 4;
+  __shared__ __align__(16) float As[kWgKC][kWgPitch];
+  __shared__ __align__(16) float Gs[kWgKC][kWgPitch];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int n_cot = (p.Cop + kWgT - 1) / kWgT;
+  const int cot = blockIdx.z % n_cot, tap = blockIdx.z / n_cot;
+  const int ci0 = blockIdx.y * kWgT, co0 = cot * kWgT;
   const int kh = tap / 3, kw = tap % 3;
   const long long N = (long long)p.B * p.Hb * p.Wb;
-  const long long per = (N + gridDim.x - 1) / gridDim.x;
+  const long long per = ((N + gridDim.x - 1) / gridDim.x + kWgKC - 1) / kWgKC * kWgKC;
   const long long lo = (long long)blockIdx.x * per, hi = min(N, lo + per);
-  float4 acc = f4zero();
-  const bool active = ci < p.Ci && co < p.Cop;
-  for (long long i = lo; i < hi; ++i) {
-    const int wb = (int)(i % p.Wb);
-    const long long t = i / p.Wb;
-    const int hb = (int)(t % p.Hb), b = (int)(t / p.Hb);
-    int ha, wa, hg, wg;
-    if (!p.up) {
-      ha = pm_src(hb, kh, p.Ha, p.sh, PM_REFLECT); wa = pm_src(wb, kw, p.Wa, p.sw, PM_REFLECT);
-      hg = hb; wg = wb;
-    } else {
-      ha = hb; wa = wb; hg = 2 * hb + kh; wg = 2 * wb + kw;
+  // loader role: pixel lk = tid / 16 of the chunk, channels 4*(tid % 16) .. +3
+  const int lk = tid >> 4, lc = (tid & 15) << 2;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+  for (long long base = lo; base < hi; base += kWgKC) {
+    const long long i = base + lk;
+    float4 av = f4zero(), gv = f4zero();
+    if (i < hi) {
+      const int wb = (int)(i % p.Wb);
+      const long long t = i / p.Wb;
+      const int hb = (int)(t % p.Hb), b = (int)(t / p.Hb);
+      int ha, wa, hg, wg;
+      if (!p.up) {
+        ha = pm_src(hb, kh, p.Ha, p.sh, PM_REFLECT); wa = pm_src(wb, kw, p.Wa, p.sw, PM_REFLECT);
+        hg = hb; wg = wb;
+      } else {
+        ha = hb; wa = wb; hg = 2 * hb + kh; wg = 2 * wb + kw;
+      }
+      const float* ap = p.A + ((long long)(b * p.Ha + ha) * p.Wa + wa) * p.Ci + ci0 + lc;
+      const float* gp = p.G + ((long long)(b * p.Hg + hg) * p.Wg + wg) * p.Co + co0 + lc;
+      if (ci0 + lc + 3 < p.Ci && (p.Ci & 3) == 0) av = ld4(ap);
+      else av = make_float4(ci0 + lc < p.Ci ? ap[0] : 0.f, ci0 + lc + 1 < p.Ci ? ap[1] : 0.f, ci0 + lc + 2 < p.Ci ? ap[2] : 0.f, ci0 + lc + 3 < p.Ci ? ap[3] : 0.f);
+      if (co0 + lc + 3 < p.Co && (p.Co & 3) == 0) gv = ld4(gp);
+      else gv = make_float4(co0 + lc < p.Co ? gp[0] : 0.f, co0 + lc + 1 < p.Co ? gp[1] : 0.f, co0 + lc + 2 < p.Co ? gp[2] : 0.f, co0 + lc + 3 < p.Co ? gp[3] : 0.f);
     }
-    if (!active) continue;
-    const float a = p.A[((long long)(b * p.Ha + ha) * p.Wa + wa) * p.Ci + ci];
-    const float* gp = p.G + ((long long)(b * p.Hg + hg) * p.Wg + wg) * p.Co + co;
-    float4 g;
-    if (co + 3 < p.Co) g = ld4(gp);
-    else g = make_float4(co < p.Co ? gp[0] : 0.f, co + 1 < p.Co ? gp[1] : 0.f, co + 2 < p.Co ? gp[2] : 0.f, 0.f);
-    acc.x = fmaf(a, g.x, acc.x); acc.y = fmaf(a, g.y, acc.y); acc.z = fmaf(a, g.z, acc.z); acc.w = fmaf(a, g.w, acc.w);
+    __syncthreads();                 // the previous chunk has been consumed
+    st4(&As[lk][lc], av);
+    st4(&Gs[lk][lc], gv);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kWgKC; ++k) {
+      const float4 a4 = ld4(&As[k][ty * 4]), g4 = ld4(&Gs[k][tx * 4]);
+      const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        acc[a][0] = fmaf(aa[a], g4.x, acc[a][0]); acc[a][1] = fmaf(aa[a], g4.y, acc[a][1]);
+        acc[a][2] = fmaf(aa[a], g4.z, acc[a][2]); acc[a][3] = fmaf(aa[a], g4.w, acc[a][3]);
+      }
+    }
   }
-  if (active) st4(p.partial + (((size_t)blockIdx.x * 9 + tap) * p.Ci + ci) * p.Cop + co, acc);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int ci = ci0 + ty * 4 + a, co = co0 + tx * 4;
+    if (ci < p.Ci && co < p.Cop) st4(p.partial + (((size_t)blockIdx.x * 9 + tap) * p.Ci + ci) * p.Cop + co, make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]));
+  }
 }
 // gw_out (PyTorch layout) = sum_s partial[s]; down: out[co][ci][kh][kw]; up: out[ci][co][kh][kw]
 __global__ void pm_wgrad_final_kernel(const float* partial, int S, int Ci, int Co, int Cop, int up, float* out) {
@@ -744,9 +773,10 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
       q.A = Ain; q.Ha = Ha; q.Wa = Wa; q.Ci = Ci; q.G = G; q.Hg = Hg; q.Wg = Wg; q.Co = Co;
       q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
       const long long N = (long long)B * Hb * Wb;
-      const int S = (int)std::max<long long>(1, std::min<long long>(64, N / 512));
+      const int tiles = 9 * ((Ci + kWgT - 1) / kWgT) * ((q.Cop + kWgT - 1) / kWgT);
+      const int S = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, (2LL * h->sm_count + tiles - 1) / tiles), N / (4 * kWgKC) + 1));
       q.partial = mem.f((size_t)S * 9 * Ci * q.Cop);
-      dim3 grid(S, (Ci + 31) / 32, 9 * ((q.Cop + 31) / 32));
+      dim3 grid(S, (Ci + kWgT - 1) / kWgT, 9 * ((q.Cop + kWgT - 1) / kWgT));
       pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
       CK(cudaGetLastError());
       pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(q.partial, S, Ci, Co, q.Cop, up, dst);

@@ -44,6 +44,7 @@ WORKLOADS = {
     "e2e": ("e2e", 1, 256, "BASELINE configs[1]: e2e_attack, ContentEncoder+SpeakerEncoder+Decoder, 80x256, batch 1 per GPU"),
     "fb": ("fb", 64, 256, "BASELINE configs[2]: fb_attack, 80x256, batch 64 per GPU"),
     "emb": ("emb", 512, 512, "BASELINE configs[3]: emb_attack, 80x512, 512 utterances per GPU (4096 over 8)"),
+    "pm": ("pm", 256, 100, "BASELINE configs[4]: VSMask predictive_model forward/backward, 80x100 windows, batch 256 per GPU"),
 }
 KIND_NAMES = {0: "conv", 1: "norm", 2: "dense_tail", 3: "affine", 4: "loss", 5: "update", 6: "layout", 7: "copy"}
 
@@ -121,6 +122,124 @@ def cpu_loop_rate(kind: str, B: int, T: int, budget_s: float, max_iters: int):
     return n * B / dt, cores, n, dt
 
 
+PM_GFLOP_FWD, PM_GFLOP_FWD_BWD = 0.2045, 0.6111        # per 80x100 window, SURVEY 8d
+
+
+def pm_cpu_rate(B: int, budget_s: float):
+    """windows/s of the oracle training step (== reference module + autograd) on the host cores."""
+    from oracle import predictive_oracle as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = P.pm_make_state_dict(0)
+    x = torch.randn(B, 1, 80, 100, generator=torch.Generator().manual_seed(3))
+    P.pm_train_step(sd, x)
+    t0 = time.perf_counter(); P.pm_train_step(sd, x); t1 = time.perf_counter() - t0
+    n = int(max(2, min(50, budget_s / t1)))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        P.pm_train_step(sd, x)
+    dt = time.perf_counter() - t0
+    return n * B / dt, cores, n, dt
+
+
+def pm_arm(args, rank, world, local):
+    """BASELINE configs[4]: one step = model.train(); out = model(x); out.square().mean().backward() on a
+    batch of 80x100 windows.  Multi-GPU: independent replicas with local BatchNorm statistics."""
+    import torch.distributed as dist
+    _, B, T, desc = WORKLOADS["pm"]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rate, cores, n, dt = pm_cpu_rate(32, 20.0)
+        line = {"impl": "reference", "metric": "predictive_model windows/s (train forward+backward)", "value": rate, "unit": "windows/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 32 / rate, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "windows_per_gpu": B, "window": "1x80x100"},
+                "cpu_baseline": {"value": rate, "unit": "windows/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference module), {dt:.1f} s"},
+                "e2e": {"value": rate, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    from oracle.predictive_oracle import pm_make_state_dict   # weights only (seeded synthetic init)
+    from attack_vc_b200.predictive import PredictiveEngine
+    eng = PredictiveEngine({k: v.to(dev) for k, v in pm_make_state_dict(0).items()})
+    K, W = args.steps, max(args.warmup, 3)
+    host = torch.randn(B, 1, 80, T, generator=torch.Generator().manual_seed(3 + rank)).pin_memory()
+    x = host.to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def mx(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+    for _ in range(W):
+        eng.train_step(x)
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            r = eng.train_step(x)
+        e1.record()
+        sync_all()
+    ms = mx(e0.elapsed_time(e1))
+    launches = eng.kernel_launches - l0
+    value = K * B * world / (ms / 1e3)
+    # eval forward alone
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.forward(x); torch.cuda.synchronize(dev); a.record()
+    for _ in range(max(3, K)):
+        eng.forward(x)
+    b.record(); torch.cuda.synchronize(dev)
+    fwd_rate = max(3, K) * B * 1e3 / a.elapsed_time(b)
+    # e2e: pinned host windows -> device, training step, loss back to the host, every step
+    sync_all(); t0 = time.perf_counter()
+    for _ in range(K):
+        r = eng.train_step(host.to(dev, non_blocking=True)); lv = float(r["loss"].cpu())
+    e2e_ms = mx(1e3 * (time.perf_counter() - t0))
+    peaks = load_peaks()
+    tf = value / world * PM_GFLOP_FWD_BWD / 1e3
+    line = {"metric": "predictive_model windows/s (train forward+backward)", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "windows_per_gpu": B, "window": "1x80x100", "loss": "out.square().mean()",
+                       "batchnorm": "batch statistics per GPU (replicas; no cross-GPU statistics all-reduce)",
+                       "eval_forward_windows_per_s_per_gpu": fwd_rate, "l2": "activations of one step (2.6 GB at batch 256) exceed L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": K * B * world / (e2e_ms / 1e3), "unit": "windows/s", "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4,
+                    "api": "PredictiveEngine.train_step(pinned host windows) + loss.cpu() per step"},
+            "gpu_launches": launches, "launches_per_step": launches / K,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
+                         "traffic": None, "kernel": "whole step (direct fp32 CUDA-core conv2d / conv-transpose / wgrad kernels, round-1 untuned)",
+                         "algorithmic_gflop_per_window": PM_GFLOP_FWD_BWD, "peak_source": peaks["source"] + ", bf16 dense burst"},
+            "loss": lv}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, n, dt = pm_cpu_rate(32, 15.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "windows/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference module), {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def reference_arm(args, rank):
     kind, B, T, desc = WORKLOADS[args.workload]
     if rank != 0:
@@ -153,6 +272,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "pm":
+        if args.impl != "reference" and not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; attack_vc_b200 has no CPU fallback (use --impl reference for the CPU loop)")
+        pm_arm(args, rank, world, local)
+        return
     if args.impl == "reference":
         reference_arm(args, rank)
         return
