@@ -390,27 +390,34 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     issue(q + p.ring - 1);               // refills the buffer slab q-1 used
     const float* Wsub = Wr + (size_t)c_slot * p.slab_floats;
     if (++c_slot == p.ring) c_slot = 0;
-    const int k_lo = warp * 16, k_hi = min(k_lo + 16, kc);
-    for (int k4 = k_lo; k4 < k_hi; k4 += 4) {
-      float4 a[RM];
+    const int k_lo = warp * 16;
+    if (k_lo < kc) {     // kc is a multiple of 16: a warp has all 16 of its K rows or none
+      // all 24 shared-memory loads of the slab are issued before the first FMA: with two warps per
+      // scheduler the loop is bound by load latency, not by bandwidth
+      float4 a[4][RM], w[16];
 #pragma unroll
-      for (int i = 0; i < RM; ++i) {
-        a[i] = ld4(Sg + (rb[i][0] + ctap) * kSRow + k4);
-        if (edge) {
-          a[i] = f4add(a[i], ld4(Sg + (rb[i][1] + ctap) * kSRow + k4));
-          a[i] = f4add(a[i], ld4(Sg + (rb[i][2] + ctap) * kSRow + k4));
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          a[j][i] = ld4(Sg + (rb[i][0] + ctap) * kSRow + k_lo + 4 * j);
+          if (edge) {
+            a[j][i] = f4add(a[j][i], ld4(Sg + (rb[i][1] + ctap) * kSRow + k_lo + 4 * j));
+            a[j][i] = f4add(a[j][i], ld4(Sg + (rb[i][2] + ctap) * kSRow + k_lo + 4 * j));
+          }
         }
       }
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const float4 w = ld4(Wsub + (k4 + qq) * kSmTN + tx * 4);
+      for (int k = 0; k < 16; ++k) w[k] = ld4(Wsub + (k_lo + k) * kSmTN + tx * 4);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
-          const float av = qq == 0 ? a[i].x : qq == 1 ? a[i].y : qq == 2 ? a[i].z : a[i].w;
-          acc[i][0] = fmaf(av, w.x, acc[i][0]);
-          acc[i][1] = fmaf(av, w.y, acc[i][1]);
-          acc[i][2] = fmaf(av, w.z, acc[i][2]);
-          acc[i][3] = fmaf(av, w.w, acc[i][3]);
+          const float4 av4 = a[k >> 2][i];
+          const float av = (k & 3) == 0 ? av4.x : (k & 3) == 1 ? av4.y : (k & 3) == 2 ? av4.z : av4.w;
+          acc[i][0] = fmaf(av, w[k].x, acc[i][0]);
+          acc[i][1] = fmaf(av, w[k].y, acc[i][1]);
+          acc[i][2] = fmaf(av, w[k].z, acc[i][2]);
+          acc[i][3] = fmaf(av, w[k].w, acc[i][3]);
         }
       }
     }
