@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   bool edge = false;
   int cg = g_lo - 1, ctap = 0, cnt = 0;   // group / tap of the slab being consumed
   int c_slot = 0;                          // ring slot of the slab being consumed
+  const bool all_resident = n_slabs <= p.ring - 1;   // the prologue already requested every slab: no ring traffic, no per-slab barrier
   const float* Sg = S;
   int kc = 0;
   for (int q = 0; q < n_slabs; ++q) {
@@ -385,9 +386,14 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
         rb[i][2] = (tv && t >= wg.rt_lo && t <= wg.rt_hi) ? 2 * (p.T_y - 1) - t + G.off0 - wg.wlo : zrel;
       }
     }
-    cp_async_wait_dyn(p.ring - 2);
-    __syncthreads();                     // slab q landed for everyone; everyone is done with slab q-1 (and, first time, the windows are visible)
-    issue(q + p.ring - 1);               // refills the buffer slab q-1 used
+    if (!all_resident) {
+      cp_async_wait_dyn(p.ring - 2);
+      __syncthreads();                   // slab q landed for everyone; everyone is done with slab q-1 (and, first time, the windows are visible)
+      issue(q + p.ring - 1);             // refills the buffer slab q-1 used
+    } else if (q == 0) {
+      cp_async_wait<0>();                // every slab was requested before the dependency wait: one barrier for the whole loop
+      __syncthreads();
+    }
     const float* Wsub = Wr + (size_t)c_slot * p.slab_floats;
     if (++c_slot == p.ring) c_slot = 0;
     const int k_lo = warp * 16;
