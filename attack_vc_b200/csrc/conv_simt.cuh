@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(TXN* TYN) conv_simt_kernel(const ConvArgs p) {
 // warps split K (16 rows of every slab each) and their partial tiles are summed in a fixed order.
 // =================================================================================================
 constexpr int kSmTN = 32;
-constexpr int kSmWarps = 8;
+constexpr int kSmWarps = 16;        // K slices per slab: warp w contracts rows [kSmKW*w, kSmKW*(w+1))
+constexpr int kSmKW = 128 / kSmWarps;
 
 template <int TM>
 __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArgs p) {
@@ -308,10 +309,11 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
       const TapGroup& G = p.g[is_g];
       const float* src = wok ? G.W + ((long long)is_tap * G.wts + wk) * Ntot + n0 + wn : G.W;
       float* dst = Wr + (size_t)is_slot * p.slab_floats + wk * kSmTN + wn;
-      const long long sstep = wok ? 32LL * Ntot : 0;
-      for (int k = wk; k < G.kc; k += 32) {
+      constexpr int kRows = NT / 8;          // K rows covered per pass of the CTA
+      const long long sstep = wok ? (long long)kRows * Ntot : 0;
+      for (int k = wk; k < G.kc; k += kRows) {
         cp_async16(dst, src, wok);
-        src += sstep; dst += 32 * kSmTN;
+        src += sstep; dst += kRows * kSmTN;
       }
       if (++is_tap == G.n_taps) { is_tap = 0; ++is_g; }
       if (++is_slot == p.ring) is_slot = 0;
@@ -396,13 +398,13 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     }
     const float* Wsub = Wr + (size_t)c_slot * p.slab_floats;
     if (++c_slot == p.ring) c_slot = 0;
-    const int k_lo = warp * 16;
-    if (k_lo < kc) {     // kc is a multiple of 16: a warp has all 16 of its K rows or none
-      // all 24 shared-memory loads of the slab are issued before the first FMA: with two warps per
+    const int k_lo = warp * kSmKW;
+    if (k_lo < kc) {     // kc is a multiple of kSmKW: a warp has all of its K rows or none
+      // all shared-memory loads of the slab are issued before the first FMA: with few warps per
       // scheduler the loop is bound by load latency, not by bandwidth
-      float4 a[4][RM], w[16];
+      float4 a[kSmKW / 4][RM], w[kSmKW];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kSmKW / 4; ++j) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
           a[j][i] = ld4(Sg + (rb[i][0] + ctap) * kSRow + k_lo + 4 * j);
@@ -413,9 +415,9 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
         }
       }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) w[k] = ld4(Wsub + (k_lo + k) * kSmTN + tx * 4);
+      for (int k = 0; k < kSmKW; ++k) w[k] = ld4(Wsub + (k_lo + k) * kSmTN + tx * 4);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
+      for (int k = 0; k < kSmKW; ++k) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
           const float4 av4 = a[k >> 2][i];

@@ -216,7 +216,7 @@ bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
       const WinGeom w = win_geom(a.bwd, a.s, a.T_y, a.g[g], i * TM, std::min(i * TM + TM, a.T_y));
       rows[g] = std::max(rows[g], w.nrows);
     }
-    if (a.g[g].kc % 16) return false;   // the kernel gives every warp a whole 16-row K slice
+    if (a.g[g].kc % kSmKW) return false;   // the kernel gives every warp a whole K slice
     kc_max = std::max(kc_max, a.g[g].kc);
     slabs_max = std::max(slabs_max, a.g[g].n_taps);
     slabs_all += a.g[g].n_taps;
