@@ -93,7 +93,17 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
     rstd = make_float4(s0.y, s0.w, s1.y, s1.w);
   } else {
     float4 sum = f4zero();
-    for (int t = lane_t; t < p.T; t += kNormTL) {
+    int t = lane_t;
+    for (; t + 3 * kNormTL < p.T; t += 4 * kNormTL) {      // four independent 16-byte loads in flight per thread
+      const float4 v0 = ld4(yb + (long long)t * p.C), v1 = ld4(yb + (long long)(t + kNormTL) * p.C);
+      const float4 v2 = ld4(yb + (long long)(t + 2 * kNormTL) * p.C), v3 = ld4(yb + (long long)(t + 3 * kNormTL) * p.C);
+      if (staged) {
+        ntile[t * 8 + lane_c] = v0; ntile[(t + kNormTL) * 8 + lane_c] = v1;
+        ntile[(t + 2 * kNormTL) * 8 + lane_c] = v2; ntile[(t + 3 * kNormTL) * 8 + lane_c] = v3;
+      }
+      sum = f4add(f4add(sum, v0), f4add(v1, f4add(v2, v3)));
+    }
+    for (; t < p.T; t += kNormTL) {
       const float4 v = ld4(yb + (long long)t * p.C);
       if (staged) ntile[t * 8 + lane_c] = v;
       sum = f4add(sum, v);
@@ -123,6 +133,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
     cs = ld4(p.cond + (long long)b * p.cond_bs + p.C + c);
   }
   float* ob = p.out + (long long)b * p.T * p.C + c;
+#pragma unroll 4
   for (int t = lane_t; t < p.T; t += kNormTL) {
     const float4 v = staged ? ntile[t * 8 + lane_c] : ld4(yb + (long long)t * p.C);
     float4 a;
@@ -167,6 +178,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
   const bool staged = p.stage && p.gy;
   // pass 1: S1 = sum_t ga, S2 = sum_t ga * xhat,  ga = g * act'(a)
   float4 S1 = f4zero(), S2 = f4zero();
+#pragma unroll 4
   for (int t = lane_t; t < p.T; t += kNormTL) {
     const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
     const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
@@ -188,6 +200,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
   const float4 m1 = f4scale(S1, invT), m2 = f4scale(S2, invT);
   const float4 k = make_float4(rstd.x * cs.x, rstd.y * cs.y, rstd.z * cs.z, rstd.w * cs.w);
   float* ob = p.gy + (long long)b * p.T * p.C + c;
+#pragma unroll 4
   for (int t = lane_t; t < p.T; t += kNormTL) {
     float4 xh, ga;
     if (staged) {
