@@ -169,6 +169,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp (the same one every time): tcgen05.mma / commit are issued by it while the
+// whole warp runs the surrounding loop, so addresses and descriptors stay in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -388,8 +395,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop (waits included), one elected lane issues =====
+    {
+      const bool leader = elect_one();
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int chunk = 0;
       long long st_a = 0, st_b = 0, st_acc = 0, st_issue = 0, t_begin = clock64(), tq;   // dbg & 32: where the issuer waits
@@ -437,28 +445,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             const uint64_t b_lo_off = (uint64_t)(((uint32_t)(kbs / 4) * N * 16) >> 4);
 #pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
-              tc_mma_tf32(d_tmem, da, db, idesc, acc);
-              acc = 1;
-              if (terms >= 3) {
-                tc_mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1);
-                tc_mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1);
+              if (leader) {
+                tc_mma_tf32(d_tmem, da, db, idesc, acc);
+                if (terms >= 3) {
+                  tc_mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1);
+                  tc_mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1);
+                }
+                if (terms >= 4) tc_mma_tf32(d_tmem, da + a_lo_off, db + b_lo_off, idesc, 1);
               }
-              if (terms >= 4) tc_mma_tf32(d_tmem, da + a_lo_off, db + b_lo_off, idesc, 1);
+              acc = 1;
               da += a_ks; db += b_ks;
             }
-            tc_commit(b_empty(sb));
+            if (leader) tc_commit(b_empty(sb));
+            __syncwarp();
             st_issue += clock64() - tq;
             if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
             if (w.next(p, ps, kb_end, done)) {
-              tc_commit(acc_full0 + 8 * buf);
+              if (leader) tc_commit(acc_full0 + 8 * buf);
               ++chunk; fresh = true;
             }
           }
-          tc_commit(a_empty(sa));
+          if (leader) tc_commit(a_empty(sa));
           if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
         }
       }
-      if ((p.dbg & 32) && blockIdx.x == 0)
+      if ((p.dbg & 32) && blockIdx.x == 0 && lane == 0)
         printf("[conv_tc cta0] issuer: total %lld clk, wait a_full %lld, wait b_full %lld, wait acc_empty %lld, issue %lld (items %d)\n",
                clock64() - t_begin, st_a, st_b, st_acc, st_issue, (n_work + (int)gridDim.x - 1) / (int)gridDim.x);
     }
