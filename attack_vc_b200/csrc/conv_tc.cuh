@@ -154,12 +154,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded wait: a protocol bug must trap, not hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if ((spin & 1023u) == 1023u) {          // the clock is only consulted now and then: try_wait itself suspends the thread
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000LL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -400,7 +404,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
       const bool leader = elect_one();
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int chunk = 0;
-      long long st_a = 0, st_b = 0, st_acc = 0, st_issue = 0, t_begin = clock64(), tq;   // dbg & 32: where the issuer waits
+#ifdef AVC_TC_PROFILE
+      long long st_a = 0, st_b = 0, st_acc = 0, st_issue = 0, t_begin = clock64(), tq;   // where the issuer waits (build with -DAVC_TC_PROFILE, run with AVC_TC_DBG=32)
+#define TCP(x) x
+#else
+#define TCP(x)
+#endif
       const int terms = p.terms;
       const bool no_mma = (p.dbg & 4) != 0;
       for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
@@ -415,10 +424,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
         while (!done) {
           const TcGroup& G = p.g[w.gi];
           const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
-          tq = clock64();
+          TCP(tq = clock64();)
           mbar_wait(a_full(sa), pa);
-          if (st_issue == 0) t_begin = clock64();      // the first window also waits for the predecessor kernel (PDL)
-          else st_a += clock64() - tq;
+          TCP(if (st_issue == 0) t_begin = clock64(); else st_a += clock64() - tq;)   // the first window also waits for the predecessor kernel (PDL)
           const uint64_t a_desc0 = tc_desc(smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lbo, 128);
           const uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4), b_ks = (uint64_t)((2 * b_lbo) >> 4);
           const int nks = no_mma ? 0 : kbs / 8;
@@ -427,18 +435,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             const int tap = w.tap;
             const int buf = chunk % kTcAccBufs;
             if (fresh) {
-              tq = clock64();
+              TCP(tq = clock64();)
               mbar_wait(acc_empty0 + 8 * buf, ((chunk / kTcAccBufs) & 1) ^ 1);
-              st_acc += clock64() - tq;
+              TCP(st_acc += clock64() - tq;)
               tc_fence_after();
               acc = 0; fresh = false;
             }
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
-            tq = clock64();
+            TCP(tq = clock64();)
             mbar_wait(b_full(sb), pb);
-            st_b += clock64() - tq;
+            TCP(st_b += clock64() - tq;)
             tc_fence_after();
-            tq = clock64();
+            TCP(tq = clock64();)
             // descriptors advance by plain 64-bit adds on the (address >> 4) field: no re-encoding per MMA
             uint64_t da = a_desc0 + (uint64_t)tap;                                  // tap j = window shifted by j rows of 16 B
             uint64_t db = tc_desc(smem_u32(Bs + (size_t)sb * b_stage_bytes), b_lbo, 128);
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             }
             if (leader) tc_commit(b_empty(sb));
             __syncwarp();
-            st_issue += clock64() - tq;
+            TCP(st_issue += clock64() - tq;)
             if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
             if (w.next(p, ps, kb_end, done)) {
               if (leader) tc_commit(acc_full0 + 8 * buf);
@@ -469,9 +477,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
           if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
         }
       }
+#ifdef AVC_TC_PROFILE
       if ((p.dbg & 32) && blockIdx.x == 0 && lane == 0)
         printf("[conv_tc cta0] issuer: total %lld clk, wait a_full %lld, wait b_full %lld, wait acc_empty %lld, issue %lld (items %d)\n",
                clock64() - t_begin, st_a, st_b, st_acc, st_issue, (n_work + (int)gridDim.x - 1) / (int)gridDim.x);
+#endif
+#undef TCP
     }
   } else if (warp < 6) {
     // ===== loaders (128 threads): window gather + TF32 split =====
