@@ -30,6 +30,18 @@ class WeightView(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
 
 
+class HeaderArgs(C.Structure):
+    _fields_ = [
+        ("source", C.c_void_p), ("src_stride", C.c_int64 * 3), ("B", C.c_int32), ("T", C.c_int32),
+        ("target", C.c_void_p), ("tgt_stride", C.c_int64 * 3), ("T_tgt", C.c_int32),
+        ("header0", C.c_void_p), ("hdr_stride", C.c_int64 * 2),
+        ("header_out", C.c_void_p), ("out_stride", C.c_int64 * 2),
+        ("loss_out", C.c_void_p), ("grad_out", C.c_void_p),
+        ("eps", C.c_float), ("lam", C.c_float), ("lr", C.c_float), ("n_iters", C.c_int32),
+        ("inv_norm", C.c_double), ("use_graph", C.c_int32),
+    ]
+
+
 class AttackArgs(C.Structure):
     _fields_ = [
         ("vc_tgt", C.c_void_p), ("tgt_stride", C.c_int64 * 3), ("B", C.c_int32), ("T_tgt", C.c_int32),
@@ -48,6 +60,7 @@ EXPORTS = [
     "avc_conv1d_dgrad", "avc_instnorm_adain_act_fwd", "avc_instnorm_adain_act_bwd", "avc_adam_tanh_step",
     "avc_kernel_launches", "avc_launches_per_iter", "avc_version",
     "avc_attack_begin", "avc_attack_step", "avc_attack_end", "avc_session_launches", "avc_session_profile",
+    "avc_header_optimize", "avc_header_begin", "avc_header_step", "avc_header_grad_buffer",
     "avc_pm_create", "avc_pm_destroy", "avc_pm_last_error", "avc_pm_load_weights", "avc_pm_out_shape", "avc_pm_forward",
     "avc_pm_train_step", "avc_pm_kernel_launches",
 ]
@@ -95,6 +108,11 @@ def load() -> C.CDLL:
     lib.avc_kernel_launches.restype = i64
     lib.avc_launches_per_iter.argtypes = [vp]
     lib.avc_launches_per_iter.restype = i32
+    lib.avc_header_optimize.argtypes = [vp, P(HeaderArgs), vp]
+    lib.avc_header_begin.argtypes = [vp, P(HeaderArgs), vp, P(vp)]
+    lib.avc_header_step.argtypes = [vp, i32, i32, vp]
+    lib.avc_header_grad_buffer.argtypes = [vp, P(i64)]
+    lib.avc_header_grad_buffer.restype = vp
     lib.avc_pm_create.argtypes = [P(vp), C.c_int]
     lib.avc_pm_destroy.argtypes = [vp]
     lib.avc_pm_destroy.restype = None

@@ -346,6 +346,105 @@ __global__ void perturb_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Universal perturbation header (reference models/header_model.py:25-68): ONE perturbation h [T, C]
+// shared by the whole batch.
+//   perturb:  adv[b,t,c] = clamp(x[b,t,c] + h[t,c], -1, 1)                           (:42-45)
+//   grad:     g_h[t,c]   = sum_b g_adv[b,t,c] * [-1 <= x + h <= 1]                   (clamp backward; fixed order over b)
+//   apply:    Adam(lr) on h with g_h (torch/optim/adam.py), h = clamp(h, -eps, eps)  (:59-65), then the next adv
+// grad and apply are separate kernels because a sharded batch all-reduces g_h between them.
+// ---------------------------------------------------------------------------------------------
+__global__ void header_perturb_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ adv,
+                                      long long adv_bs, int adv_rs, int B, int T, int C) {
+  pdl_enter();
+  const int c4n = C >> 2;
+  const long long n4 = (long long)B * T * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const long long bt = i / c4n;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float4 xv = ld4(x + i * 4), hv = ld4(h + ((long long)t * C + c));
+    st4(adv + (long long)b * adv_bs + (long long)t * adv_rs + c,
+        make_float4(fminf(fmaxf(xv.x + hv.x, -1.f), 1.f), fminf(fmaxf(xv.y + hv.y, -1.f), 1.f),
+                    fminf(fmaxf(xv.z + hv.z, -1.f), 1.f), fminf(fmaxf(xv.w + hv.w, -1.f), 1.f)));
+  }
+}
+
+__global__ void header_grad_kernel(const float* __restrict__ g_adv, long long g_bs, int g_rs, const float* __restrict__ x,
+                                   const float* __restrict__ h, float* __restrict__ gh, int B, int T, int C) {
+  pdl_enter();
+  const int c4n = C >> 2;
+  const long long n4 = (long long)T * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const int t = (int)(i / c4n);
+    const float4 hv = ld4(h + i * 4);
+    float4 s = f4zero();
+    for (int b = 0; b < B; ++b) {
+      const float4 xv = ld4(x + ((long long)b * T + t) * C + c);
+      const float4 g = ld4(g_adv + (long long)b * g_bs + (long long)t * g_rs + c);
+      const float p0 = xv.x + hv.x, p1 = xv.y + hv.y, p2 = xv.z + hv.z, p3 = xv.w + hv.w;
+      s.x += (p0 >= -1.f && p0 <= 1.f) ? g.x : 0.f;
+      s.y += (p1 >= -1.f && p1 <= 1.f) ? g.y : 0.f;
+      s.z += (p2 >= -1.f && p2 <= 1.f) ? g.z : 0.f;
+      s.w += (p3 >= -1.f && p3 <= 1.f) ? g.w : 0.f;
+    }
+    st4(gh + i * 4, s);
+  }
+}
+
+struct HeaderApplyArgs {
+  const float* gh; float* h; float* m; float* v;     // [T, C]
+  const float* x; float* adv; long long adv_bs; int adv_rs;
+  int B, T, C;
+  float eps;
+  const float2* table;   // [n_iters] (lr/(1-b1^t), sqrt(1-b2^t))
+  int* step; unsigned int* done;
+};
+__global__ void __launch_bounds__(256) header_apply_kernel(const HeaderApplyArgs p) {
+  pdl_enter();
+  const int c4n = p.C >> 2;
+  const long long n4 = (long long)p.T * c4n;
+  const int step = *p.step;
+  const float2 tab = p.table[step];
+  const float step_size = tab.x, bc2s = tab.y;
+  const float b1w = (float)(1.0 - 0.9), b2 = 0.999f, b2w = (float)(1.0 - 0.999);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) << 2;
+    const int t = (int)(i / c4n);
+    const float4 g = ld4(p.gh + i * 4);
+    float4 h = ld4(p.h + i * 4), m = ld4(p.m + i * 4), v = ld4(p.v + i * 4);
+    float ga[4] = {g.x, g.y, g.z, g.w}, ha[4] = {h.x, h.y, h.z, h.w}, ma[4] = {m.x, m.y, m.z, m.w}, va[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ma[j] = ma[j] + (ga[j] - ma[j]) * b1w;
+      va[j] = va[j] * b2 + (b2w * ga[j]) * ga[j];
+      const float denom = sqrtf(va[j]) / bc2s + 1e-8f;
+      ha[j] = ha[j] + (-step_size * ma[j]) / denom;
+      ha[j] = fminf(fmaxf(ha[j], -p.eps), p.eps);
+    }
+    st4(p.h + i * 4, make_float4(ha[0], ha[1], ha[2], ha[3]));
+    st4(p.m + i * 4, make_float4(ma[0], ma[1], ma[2], ma[3]));
+    st4(p.v + i * 4, make_float4(va[0], va[1], va[2], va[3]));
+    for (int b = 0; b < p.B; ++b) {
+      const float4 xv = ld4(p.x + ((long long)b * p.T + t) * p.C + c);
+      st4(p.adv + (long long)b * p.adv_bs + (long long)t * p.adv_rs + c,
+          make_float4(fminf(fmaxf(xv.x + ha[0], -1.f), 1.f), fminf(fmaxf(xv.y + ha[1], -1.f), 1.f),
+                      fminf(fmaxf(xv.z + ha[2], -1.f), 1.f), fminf(fmaxf(xv.w + ha[3], -1.f), 1.f)));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && p.done) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *p.done = 0u;
+      *p.step = step + 1;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Speaker-encoder tail: AdaptiveAvgPool1d(1) -> 6 residual dense blocks -> output Linear
 // (models.py:307-325, 340-342), the emb/fb loss (attack_utils.py:81,125) and the whole backward of
 // the tail, one CTA (1024 threads = 8 K-slices x 128 outputs) per utterance.  Requires c_h = c_out = 128.
@@ -366,6 +465,7 @@ struct TailArgs {
   float* emb;             // [B,128] output embedding (TAIL_FWD)
   const float* tgt; const float* org;   // [B,128] (TAIL_LOSS)
   float inv_norm;
+  float lam;              // weight of the 'away from the original' term: 0.1 in the attacks (attack_utils.py:43,81,125), lambda_param in header_model.py:56
   float* loss_parts; const int* step; int parts_per_step;
   const float* gemb; int gemb_parts;    // TAIL_BWD without TAIL_LOSS: d emb = sum_p gemb[b][p][128]
   float* gpool;           // [B,128]: d h[b,t,:] for every t (already divided by T_h)
@@ -481,8 +581,8 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
     float lp = 0.f;
     if (tid < 128) {
       const float e = gt[n], d = e - p.tgt[(long long)b * 128 + n], o = e - p.org[(long long)b * 128 + n];
-      lp = d * d - 0.1f * (o * o);
-      gv[n] = 2.f * p.inv_norm * (d - 0.1f * o);
+      lp = d * d - p.lam * (o * o);
+      gv[n] = 2.f * p.inv_norm * (d - p.lam * o);
       lp = warp_sum(lp);
       if ((tid & 31) == 0) lred[tid >> 5] = lp;
     }

@@ -137,10 +137,13 @@ struct Plan {
   explicit Plan(SlabPool* pool = nullptr) : mem(pool) {}
   std::vector<Launch> setup;    // once per attack call (targets, loop invariants)
   std::vector<Launch> iter;     // one attack iteration
+  std::vector<Launch> iter2;    // header optimisation only: the apply half of an iteration (after the gradient all-reduce)
+  float* gh = nullptr; long long gh_n = 0;   // header optimisation: this rank's partial gradient [T,C]
   std::vector<Launch> finish;   // after the loop
   cudaGraph_t graph = nullptr, graphU = nullptr;
   cudaGraphExec_t exec = nullptr;    // one iteration
   cudaGraphExec_t execU = nullptr;   // kUnroll iterations back to back: 16x fewer launches, shallow launch queue
+  cudaGraph_t graph2 = nullptr; cudaGraphExec_t exec2 = nullptr;   // header optimisation: apply half
   int n_iters = 0;      // iterations the Adam table / loss buffer were sized for
   int done_iters = 0;
   bool use_graph = true;
@@ -148,6 +151,8 @@ struct Plan {
   ~Plan() {
     if (exec) cudaGraphExecDestroy(exec);
     if (execU) cudaGraphExecDestroy(execU);
+    if (exec2) cudaGraphExecDestroy(exec2);
+    if (graph2) cudaGraphDestroy(graph2);
     if (graph) cudaGraphDestroy(graph);
     if (graphU) cudaGraphDestroy(graphU);
   }
@@ -954,7 +959,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     emit_bank_and_inconv(E, SE, A, false);
     emit_encoder_blocks_fwd(E, SE, A, false);
     TailArgs t = tail_args(SE, A);
-    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm;
+    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm; t.lam = 0.1f;
     t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
     if (emb_dst) t.emb = emb_dst;
     emit_tail(E, t, A.B);
@@ -1136,6 +1141,143 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   return plan_ptr;
 }
 
+// ---- universal perturbation header (reference models/header_model.py:25-68) --------
+// speaker_encoder = this handle's AdaIN-VC SpeakerEncoder on mel.squeeze(1); source/target embeddings are loop
+// invariants (the reference recomputes them every iteration, :48-49).  iter = forward, loss, backward and the
+// batch-summed header gradient; iter2 = Adam + projection + next perturbed batch.
+std::unique_ptr<Plan> build_header(avc_handle* h, const avc_header_args* a, cudaStream_t st) {
+  if (!h->have_weights) fail(AVC_ERR_STATE, "avc_load_weights must be called before avc_header_*");
+  if (!a || !a->source || !a->target || !a->header0 || !a->header_out) fail(AVC_ERR_INVALID, "null tensor argument");
+  if (a->B <= 0 || a->T <= 0 || a->T_tgt <= 0 || a->n_iters < 0 || a->lr <= 0.f) fail(AVC_ERR_INVALID, "bad B/T/n_iters/lr");
+  const int B = a->B, T = a->T, C = h->desc.speaker.c_in, n_iters = a->n_iters;
+  const EncoderW& SE = h->se;
+  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool));
+  Plan& plan = *plan_ptr;
+  plan.n_iters = n_iters;
+  plan.use_graph = a->use_graph != 0;
+  Arena& m = plan.mem;
+  Emitter S{h, &plan.setup, &plan.mem}, I{h, &plan.iter, &plan.mem}, F{h, &plan.finish, &plan.mem};
+  const size_t nel = (size_t)B * T * C, nh = (size_t)T * C;
+  float* x = m.f(nel);
+  float* hdr = m.f(nh);
+  float* mm = m.f(nh);
+  float* vv = m.f(nh);
+  float* gh = m.f(nh);
+  plan.gh = gh; plan.gh_n = (long long)nh;
+  int* step = m.raw<int>(1);
+  unsigned int* done = m.raw<unsigned int>(1);
+  std::vector<float> tab((size_t)std::max(n_iters, 1) * 2);
+  for (int i = 0; i < n_iters; ++i) {
+    const double t = i + 1;
+    tab[2 * i] = (float)((double)a->lr / (1.0 - std::pow(0.9, t)));
+    tab[2 * i + 1] = (float)std::sqrt(1.0 - std::pow(0.999, t));
+  }
+  float2* table = reinterpret_cast<float2*>(m.upload(tab));
+  EncActs se1 = alloc_encoder(m, SE, B, T, true, false);
+  const Tens adv = se1.input(SE);
+  emit_layout_in(S, a->source, a->src_stride, tens(x, T, C), B, C);
+  const int64_t hs[3] = {0, a->hdr_stride[0], a->hdr_stride[1]};
+  emit_layout_in(S, a->header0, hs, tens(hdr, T, C), 1, C);
+  const double inv_norm = a->inv_norm > 0 ? a->inv_norm : 1.0 / ((double)B * SE.d.c_out);
+  const int parts = B;
+  float* loss_parts = m.f((size_t)std::max(n_iters, 1) * parts);
+  float* org = m.f((size_t)B * 128);
+  float* tgt = m.f((size_t)B * 128);
+  auto se_forward = [&](Emitter& E, const EncActs& A, int tail_mode, const float* tgt_e, const float* org_e, float* emb_dst) {
+    emit_bank_and_inconv(E, SE, A, false);
+    emit_encoder_blocks_fwd(E, SE, A, false);
+    TailArgs t = tail_args(SE, A);
+    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm; t.lam = a->lambda;
+    t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+    if (emb_dst) t.emb = emb_dst;
+    emit_tail(E, t, A.B);
+  };
+  // loop invariants: embeddings of the clean source and of the target (header_model.py:48-49)
+  emit_layout_in(S, a->source, a->src_stride, adv, B, C);
+  se_forward(S, se1, TAIL_FWD, nullptr, nullptr, org);
+  if (a->T_tgt == T) {
+    emit_layout_in(S, a->target, a->tgt_stride, adv, B, C);
+    se_forward(S, se1, TAIL_FWD, nullptr, nullptr, tgt);
+  } else {
+    EncActs seT = alloc_encoder(m, SE, B, a->T_tgt, false, false);
+    emit_layout_in(S, a->target, a->tgt_stride, seT.input(SE), B, C);
+    se_forward(S, seT, TAIL_FWD, nullptr, nullptr, tgt);
+  }
+  const unsigned gp = ew_grid((long long)nel / 4, h->sm_count), gt = ew_grid((long long)nh / 4, h->sm_count);
+  S.push(LK_UPDATE, 0, 8.0 * nel, [=](cudaStream_t s_) { launch_k(header_perturb_kernel, gp, 256, 0, s_, (const float*)x, (const float*)hdr, adv.p, adv.bs, adv.rs, B, T, C); });
+  // iteration, gradient half
+  se_forward(I, se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
+  Tens gin = tens(se1.gin, T, C);
+  emit_speaker_bwd(I, SE, se1, gin);
+  I.push(LK_UPDATE, 0, 8.0 * nel, [=](cudaStream_t s_) { launch_k(header_grad_kernel, gt, 256, 0, s_, (const float*)gin.p, gin.bs, gin.rs, (const float*)x, (const float*)hdr, gh, B, T, C); });
+  // iteration, apply half
+  {
+    HeaderApplyArgs u{};
+    u.gh = gh; u.h = hdr; u.m = mm; u.v = vv; u.x = x; u.adv = adv.p; u.adv_bs = adv.bs; u.adv_rs = adv.rs;
+    u.B = B; u.T = T; u.C = C; u.eps = a->eps; u.table = table; u.step = step; u.done = done;
+    Emitter I2{h, &plan.iter2, &plan.mem};
+    I2.push(LK_UPDATE, 0, 8.0 * nel + 28.0 * nh, [=](cudaStream_t s_) { launch_k(header_apply_kernel, gt, 256, 0, s_, u); });
+  }
+  // finish: header, loss curve, last gradient
+  {
+    const int64_t os[3] = {0, a->out_stride[0], a->out_stride[1]};
+    emit_layout_out(F, tens(hdr, T, C), a->header_out, os, 1, C);
+  }
+  if (a->loss_out && n_iters > 0) {
+    float* lp = loss_parts; float* lo = a->loss_out; const int pp = parts;
+    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) { launch_k(loss_sum_kernel, (n_iters + 127) / 128, 128, 0, s_, (const float*)lp, pp, n_iters, lo); });
+  }
+  if (a->grad_out && n_iters > 0) {
+    const int64_t cs[3] = {0, (int64_t)T, 1};
+    emit_layout_out(F, tens(gh, T, C), a->grad_out, cs, 1, C);
+  }
+  CK(cudaDeviceSynchronize());
+  try {
+    run_list(plan.setup, st);
+    h->launches += (long long)plan.setup.size();
+    h->launches_per_iter = (int)(plan.iter.size() + plan.iter2.size());
+    if (n_iters > 0 && plan.use_graph) {
+      auto capture = [&](const std::vector<Launch>& v, cudaGraph_t* g, cudaGraphExec_t* xg) {
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+        try { run_list(v, cs); } catch (...) { cudaGraph_t bad = nullptr; cudaStreamEndCapture(cs, &bad); if (bad) cudaGraphDestroy(bad); cudaStreamDestroy(cs); throw; }
+        e = cudaStreamEndCapture(cs, g);
+        cudaStreamDestroy(cs);
+        if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(xg, *g, 0));
+      };
+      capture(plan.iter, &plan.graph, &plan.exec);
+      capture(plan.iter2, &plan.graph2, &plan.exec2);
+    }
+  } catch (...) {
+    cudaDeviceSynchronize();
+    throw;
+  }
+  return plan_ptr;
+}
+
+// phase 0: n whole iterations; 1: the gradient half of ONE iteration; 2: the apply half of ONE iteration
+void step_header(avc_handle* h, Plan& plan, int n, int phase, cudaStream_t st) {
+  if (plan.finished) fail(AVC_ERR_STATE, "session already finished");
+  if (plan.iter2.empty()) fail(AVC_ERR_STATE, "not a header-optimisation session");
+  if (phase < 0 || phase > 2 || n < 0) fail(AVC_ERR_INVALID, "bad phase / count");
+  const int iters = phase == 0 ? n : (phase == 2 ? 1 : 0);
+  if (plan.done_iters + iters > plan.n_iters) fail(AVC_ERR_INVALID, "session was opened for %d iterations, %d done", plan.n_iters, plan.done_iters);
+  auto half = [&](const std::vector<Launch>& v, cudaGraphExec_t x) { if (x) CK(cudaGraphLaunch(x, st)); else run_list(v, st); };
+  try {
+    if (phase == 0) for (int i = 0; i < n; ++i) { half(plan.iter, plan.exec); half(plan.iter2, plan.exec2); }
+    else if (phase == 1) half(plan.iter, plan.exec);
+    else half(plan.iter2, plan.exec2);
+  } catch (...) {
+    cudaDeviceSynchronize();
+    throw;
+  }
+  plan.done_iters += iters;
+  h->launches += (long long)(phase == 0 ? (plan.iter.size() + plan.iter2.size()) * n : (phase == 1 ? plan.iter.size() : plan.iter2.size()));
+}
+
 void step_attack(avc_handle* h, Plan& plan, int n, cudaStream_t st) {
   if (plan.finished) fail(AVC_ERR_STATE, "attack session already finished");
   if (n < 0 || plan.done_iters + n > plan.n_iters)
@@ -1303,6 +1445,35 @@ int avc_attack_end(avc_session* s, void* stream) {
   cudaDeviceSynchronize();
   delete s;
   return rc;
+}
+
+int avc_header_begin(avc_handle* h, const avc_header_args* a, void* stream, avc_session** out) {
+  if (!h || !out) return AVC_ERR_INVALID;
+  *out = nullptr;
+  return guarded(h, [&] {
+    std::unique_ptr<Plan> plan = build_header(h, a, (cudaStream_t)stream);
+    *out = new avc_session{h, std::move(plan)};
+  });
+}
+
+int avc_header_step(avc_session* s, int32_t n, int32_t phase, void* stream) {
+  if (!s) return AVC_ERR_INVALID;
+  return guarded(s->h, [&] { step_header(s->h, *s->plan, n, phase, (cudaStream_t)stream); });
+}
+
+float* avc_header_grad_buffer(avc_session* s, int64_t* n) {
+  if (!s || !s->plan->gh) return nullptr;
+  if (n) *n = s->plan->gh_n;
+  return s->plan->gh;
+}
+
+int avc_header_optimize(avc_handle* h, const avc_header_args* a, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    std::unique_ptr<Plan> plan = build_header(h, a, (cudaStream_t)stream);
+    step_header(h, *plan, a->n_iters, 0, (cudaStream_t)stream);
+    finish_attack(h, *plan, (cudaStream_t)stream);
+  });
 }
 
 int32_t avc_session_launches(const avc_session* s) { return s ? (int32_t)s->plan->iter.size() : -1; }

@@ -71,3 +71,30 @@ def sharded_attack(attack: AttackFn, kind: str, vc_tgt: Tensor, adv_tgt: Tensor,
     # loss statistics: each rank holds the partial sum over its slice, already scaled by the global normaliser
     dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
     return torch.cat(parts, dim=0), losses
+
+
+def sharded_header_optimize(engine, source_mel: Tensor, target_mel: Tensor, num_iterations: int, epsilon: float = 0.1,
+                            lambda_param: float = 0.5, lr: float = 1e-3, header0: Optional[Tensor] = None, group=None):
+    """UniversalPerturbationHeader.optimize (models/header_model.py:25-68) with the batch sharded over the ranks.
+    The header is shared by ALL utterances, so this is the one workload with a per-iteration collective: every
+    rank runs forward/backward on its slice, the partial header gradients (80*T floats, 32 KB) are all-reduced,
+    then every rank applies the same Adam step.  ``engine`` is an ``Engine`` (or a stand-in with ``header_begin``)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = source_mel.shape[0]
+    lo, hi = shard_bounds(B, world, rank)
+    if hi <= lo:
+        raise ValueError("sharded_header_optimize needs at least one utterance per rank")
+    inv = 1.0 / (float(B) * 128)
+    sess = engine.header_begin(source_mel[lo:hi], target_mel[lo:hi], num_iterations, epsilon, lambda_param, lr,
+                               header0=header0, inv_norm=inv, want_loss=True)
+    for _ in range(int(num_iterations)):
+        sess.grad_half()
+        if world > 1:
+            dist.all_reduce(sess.grad, op=dist.ReduceOp.SUM, group=group)
+        sess.apply_half()
+    header, info = sess.end()
+    losses = info["losses"].clone()
+    if world > 1:
+        dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
+    return header, losses

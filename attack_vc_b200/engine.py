@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from . import _lib
-from ._lib import AttackArgs, DecoderDesc, EncoderDesc, ModelDesc, WeightView
+from ._lib import AttackArgs, DecoderDesc, EncoderDesc, HeaderArgs, ModelDesc, WeightView
 
 
 class AvcError(RuntimeError):
@@ -252,6 +252,63 @@ class Engine:
             self._check(self._lib.avc_attack_begin(self._h, k, C.byref(a), self._stream(), C.byref(sp)))
         return AttackSession(self, sp, keep, int(n_iters))
 
+    # ---- universal perturbation header (models/header_model.py:25-68) ---------------------------------
+    def _header_args(self, source, target, eps, lam, lr, n_iters, header0, inv_norm, want_loss, want_grad, use_graph):
+        if source.dim() == 4:          # the reference's [B,1,80,T] -> the speaker encoder's [B,80,T] (a view)
+            source = source.squeeze(1)
+        if target.dim() == 4:
+            target = target.squeeze(1)
+        source, target = self._utt(source, "source_mel"), self._utt(target, "target_mel")
+        B, _, T = source.shape
+        if target.shape[0] != B:
+            raise ValueError("batch sizes of source_mel / target_mel differ")
+        if header0 is None:
+            header0 = torch.zeros(self.c_in, T, device=self.device, dtype=torch.float32)   # header_model.py:22
+        header0 = header0.reshape(self.c_in, -1)
+        if header0.shape[1] != T or header0.device != self.device or header0.dtype != torch.float32:
+            raise ValueError(f"header must be float32 [80, {T}] on {self.device}")
+        n_iters = int(n_iters)
+        out = torch.empty(self.c_in, T, device=self.device, dtype=torch.float32)
+        loss = torch.zeros(max(n_iters, 1), device=self.device, dtype=torch.float32) if want_loss else None
+        grad = torch.zeros(self.c_in, T, device=self.device, dtype=torch.float32) if want_grad else None
+        a = HeaderArgs()
+        a.source, a.src_stride, a.B, a.T = source.data_ptr(), _strides3(source), B, T
+        a.target, a.tgt_stride, a.T_tgt = target.data_ptr(), _strides3(target), target.shape[2]
+        a.header0, a.hdr_stride = header0.data_ptr(), (C.c_int64 * 2)(*[int(v) for v in header0.stride()])
+        a.header_out, a.out_stride = out.data_ptr(), (C.c_int64 * 2)(*[int(v) for v in out.stride()])
+        a.loss_out = loss.data_ptr() if loss is not None else None
+        a.grad_out = grad.data_ptr() if grad is not None else None
+        a.eps, a.lam, a.lr, a.n_iters = float(eps), float(lam), float(lr), n_iters
+        a.inv_norm = float(inv_norm) if inv_norm is not None else 0.0
+        a.use_graph = 1 if use_graph else 0
+        return a, (source, target, header0, out, loss, grad)
+
+    def header_optimize(self, source_mel: Tensor, target_mel: Tensor, num_iterations: int = 1000, epsilon: float = 0.1,
+                        lambda_param: float = 0.5, lr: float = 1e-3, header0: Optional[Tensor] = None,
+                        inv_norm: Optional[float] = None, want_loss: bool = False, want_grad: bool = False, use_graph: bool = True):
+        """UniversalPerturbationHeader.optimize with this model's speaker encoder and Adam([header], lr)
+        (header_model.py:25-68, train_header.py:46,77-81).  Returns the optimised header [1,1,80,T]
+        (and an info dict when want_loss / want_grad)."""
+        with torch.cuda.device(self.device):
+            a, keep = self._header_args(source_mel, target_mel, epsilon, lambda_param, lr, num_iterations, header0, inv_norm,
+                                        want_loss, want_grad, use_graph)
+            self._check(self._lib.avc_header_optimize(self._h, C.byref(a), self._stream()))
+        _, _, _, out, loss, grad = keep
+        hdr = out.reshape(1, 1, self.c_in, -1)
+        if want_loss or want_grad:
+            return hdr, {"losses": loss[:int(num_iterations)] if loss is not None else None, "grad": grad}
+        return hdr
+
+    def header_begin(self, source_mel: Tensor, target_mel: Tensor, num_iterations: int, epsilon: float = 0.1,
+                     lambda_param: float = 0.5, lr: float = 1e-3, header0: Optional[Tensor] = None,
+                     inv_norm: Optional[float] = None, want_loss: bool = False, use_graph: bool = True) -> "HeaderSession":
+        with torch.cuda.device(self.device):
+            a, keep = self._header_args(source_mel, target_mel, epsilon, lambda_param, lr, num_iterations, header0, inv_norm,
+                                        want_loss, False, use_graph)
+            sp = C.c_void_p()
+            self._check(self._lib.avc_header_begin(self._h, C.byref(a), self._stream(), C.byref(sp)))
+        return HeaderSession(self, sp, keep, int(num_iterations))
+
     def speaker_encoder(self, x: Tensor) -> Tensor:
         x = self._utt(x, "x")
         with torch.cuda.device(self.device):
@@ -347,6 +404,50 @@ class AttackSession:
         self.eng._check(self.eng._lib.avc_attack_end(s, self.eng._stream()))
         _, _, _, w0, out, loss, grad = self._keep
         return out, {"losses": loss, "grad": grad, "w0": w0}
+
+    def __del__(self):
+        try:
+            if self._s is not None:
+                self.eng._lib.avc_attack_end(self._s, self.eng._stream())
+                self._s = None
+        except Exception:
+            pass
+
+
+class _DevMem:
+    """CUDA array interface over a raw device pointer owned by the library (lives as long as the session)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class HeaderSession:
+    """avc_header_begin / avc_header_step / avc_attack_end.  ``step(n)`` runs whole iterations; a sharded
+    caller alternates ``grad_half()``, an all-reduce of ``grad`` and ``apply_half()``."""
+
+    def __init__(self, eng: Engine, sp, keep, n_iters: int):
+        self.eng, self._s, self._keep, self.n_iters = eng, sp, keep, n_iters
+        n = C.c_int64()
+        ptr = eng._lib.avc_header_grad_buffer(sp, C.byref(n))
+        self.grad = torch.as_tensor(_DevMem(int(ptr), int(n.value)), device=eng.device)   # [T*80] time-major partial gradient
+
+    def step(self, n: int = 1) -> None:
+        self.eng._check(self.eng._lib.avc_header_step(self._s, int(n), 0, self.eng._stream()))
+
+    def grad_half(self) -> None:
+        self.eng._check(self.eng._lib.avc_header_step(self._s, 1, 1, self.eng._stream()))
+
+    def apply_half(self) -> None:
+        self.eng._check(self.eng._lib.avc_header_step(self._s, 1, 2, self.eng._stream()))
+
+    def end(self):
+        if self._s is None:
+            raise AvcError("session already ended")
+        s, self._s = self._s, None
+        self.grad = None
+        self.eng._check(self.eng._lib.avc_attack_end(s, self.eng._stream()))
+        _, _, _, out, loss, _ = self._keep
+        return out.reshape(1, 1, self.eng.c_in, -1), {"losses": loss}
 
     def __del__(self):
         try:

@@ -118,6 +118,31 @@ int32_t avc_session_launches(const avc_session* s);
  * 5 update,6 layout,7 copy), milliseconds, algorithmic FLOPs and algorithmic HBM bytes. */
 int avc_session_profile(avc_session* s, int32_t cap, int32_t* kind, float* ms, double* flops, double* bytes, void* stream);
 
+/* ---- universal perturbation header -------------------------------------------------
+ * replaces: UniversalPerturbationHeader.optimize(source_mel, target_mel, speaker_encoder, Adam([header], lr), ...)
+ * (models/header_model.py:25-68) with speaker_encoder = this handle's AdaIN-VC SpeakerEncoder applied to
+ * mel.squeeze(1).  ONE perturbation [80,T] is shared by the batch: perturbed = clamp(source + header, -1, 1),
+ * loss = mse(e, e_target) - lambda * mse(e, e_source), Adam step, header = clamp(header, -eps, eps). */
+typedef struct avc_header_args {
+  const float* source; int64_t src_stride[3]; int32_t B, T;     /* [B,80,T] (the reference's [B,1,80,T] squeezed) */
+  const float* target; int64_t tgt_stride[3]; int32_t T_tgt;
+  const float* header0; int64_t hdr_stride[2];                   /* [80,T] initial header (zeros, header_model.py:22) */
+  float* header_out;    int64_t out_stride[2];                   /* [80,T] */
+  float* loss_out;                                               /* [n_iters] or NULL */
+  float* grad_out;                                               /* [80,T] contiguous, d loss / d header of the last iteration, or NULL */
+  float eps, lambda, lr;                                         /* train_header.py:120-125: 0.1, 0.5, 1e-3 */
+  int32_t n_iters;
+  double inv_norm;                                               /* 1/(B_global*128); <= 0: this call's batch */
+  int32_t use_graph;
+} avc_header_args;
+int avc_header_optimize(avc_handle* h, const avc_header_args* a, void* stream);
+/* session form (ended with avc_attack_end).  phase 0: n whole iterations.  Sharded batches run phase 1 (forward,
+ * backward, this rank's partial header gradient), all-reduce avc_header_grad_buffer() over the ranks, then phase 2
+ * (Adam + projection + next perturbed batch) -- the one per-iteration collective of this workload. */
+int avc_header_begin(avc_handle* h, const avc_header_args* a, void* stream, avc_session** out);
+int avc_header_step(avc_session* s, int32_t n, int32_t phase, void* stream);
+float* avc_header_grad_buffer(avc_session* s, int64_t* n_floats);
+
 /* ---- forward-only model entry points (also used by the parity tests) --- */
 /* replaces: model.speaker_encoder(x) (models.py:327-343).  x [B,80,T] strided -> emb [B,c_out] */
 int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], int32_t B, int32_t T,

@@ -232,3 +232,32 @@ def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_
         final = vc_tgt + eps * w.tanh()                       # :48,86,130
     return {"adv": final.detach(), "w": w.detach().clone(), "losses": torch.tensor(losses, dtype=torch.float64),
             "grads": grads, "ws": ws, "org": org.detach(), "tgt": tgt.detach()}
+
+
+def run_header(model, source_mel: Tensor, target_mel: Tensor, num_iterations: int, epsilon: float = 0.1,
+               lambda_param: float = 0.5, lr: float = 1e-3, header0: Optional[Tensor] = None,
+               inv_norm: Optional[float] = None) -> Dict[str, object]:
+    """UniversalPerturbationHeader.optimize (models/header_model.py:25-68) driven as train_header.py:46,77-81
+    does (Adam([header], lr)), with speaker_encoder = model.speaker_encoder on mel.squeeze(1).
+    source_mel / target_mel: [B,1,80,T].  Records the loss of every iteration and the last header gradient."""
+    header = (torch.zeros((1, 1) + tuple(source_mel.shape[2:]), dtype=source_mel.dtype) if header0 is None
+              else header0.detach().clone().reshape((1, 1) + tuple(source_mel.shape[2:]))).requires_grad_(True)   # :22-23
+    opt = torch.optim.Adam([header], lr=lr)
+    enc = lambda m: model.speaker_encoder(m.squeeze(1))
+    mse = F.mse_loss if inv_norm is None else (lambda a, b: (a - b).square().sum() * inv_norm)
+    losses: List[float] = []
+    grad = None
+    for _ in range(num_iterations):
+        perturbed = torch.clamp(source_mel + header, -1.0, 1.0)            # :42-45
+        with torch.no_grad():
+            e_src, e_tgt = enc(source_mel), enc(target_mel)                # :48-49 (recomputed every iteration there)
+        e = enc(perturbed)                                                 # :50
+        loss = mse(e, e_tgt) - lambda_param * mse(e, e_src)                # :53-56
+        opt.zero_grad()
+        loss.backward()
+        grad = header.grad.detach().clone()
+        opt.step()                                                         # :59-61
+        with torch.no_grad():
+            header.data = torch.clamp(header.data, -epsilon, epsilon)      # :64-65
+        losses.append(float(loss.detach()))
+    return {"header": header.detach().clone(), "losses": torch.tensor(losses, dtype=torch.float64), "grad": grad}

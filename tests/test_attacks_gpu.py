@@ -204,3 +204,95 @@ def test_tensor_core_plans_vs_host_oracle(engine, oracle, cpu_model, kind, B, T,
     with torch.no_grad():
         ref = cpu_model.speaker_encoder(o["adv"]).double()
     assert float(torch.nn.functional.cosine_similarity(emb, ref, dim=1).min()) >= 0.999
+
+
+# ---- universal perturbation header (models/header_model.py:25-68) --------------------------------
+@pytest.mark.parametrize("B,T,T_tgt,n,eps", [(3, 100, 100, 6, 0.003), (1, 64, 90, 4, 0.1), (20, 128, 128, 3, 0.1)])
+def test_header_optimize_vs_host_oracle(engine, oracle, cpu_model, B, T, T_tgt, n, eps):
+    inp = oracle.make_inputs("emb", B, T, seed=31, T_adv=T_tgt)
+    src, tgt = inp["vc_tgt"].unsqueeze(1) * 0.6, inp["adv_tgt"].unsqueeze(1) * 0.6
+    o = oracle.run_header(cpu_model, src, tgt, n, epsilon=eps)
+    # teacher-forced gradient of the first iteration (header 0) and of iteration n-1 from the oracle's header
+    o1 = oracle.run_header(cpu_model, src, tgt, 1, epsilon=eps)
+    _, i1 = engine.header_optimize(src.cuda(), tgt.cuda(), 1, epsilon=eps, want_loss=True, want_grad=True)
+    assert grad_rel(i1["grad"], o1["grad"][0, 0]) < RTOL
+    hdr, info = engine.header_optimize(src.cuda(), tgt.cuda(), n, epsilon=eps, want_loss=True)
+    assert hdr.shape == (1, 1, 80, T)
+    np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL, atol=1e-9)
+    assert float(hdr.abs().max()) <= float(np.float32(eps))          # the bound is applied in fp32 like torch.clamp
+    err = (hdr.cpu() - o["header"]).abs()
+    # Adam at |g| ~ 1e-7 normalises the step: elements whose gradient sits near zero may differ by a whole
+    # lr-sized step between two fp32 implementations; everything else must agree to fp32 noise
+    assert float(err.median()) < 1e-6
+    assert float((err > 1e-4).float().mean()) < 0.02
+    assert float(err.max()) <= 2e-3 * n + 1e-6
+
+
+def test_header_session_phases_match_one_shot(engine, oracle):
+    inp = oracle.make_inputs("emb", 4, 96, seed=8)
+    src, tgt = (inp["vc_tgt"] * 0.6).cuda(), (inp["adv_tgt"] * 0.6).cuda()
+    n = 5
+    ref, rinfo = engine.header_optimize(src, tgt, n, epsilon=0.004, want_loss=True)
+    eager = engine.header_optimize(src, tgt, n, epsilon=0.004, use_graph=False)
+    assert torch.equal(ref, eager)
+    s = engine.header_begin(src, tgt, n, epsilon=0.004, want_loss=True)
+    s.step(2)
+    for _ in range(n - 2):
+        s.grad_half()
+        assert float(s.grad.abs().max()) > 0
+        s.apply_half()
+    out, info = s.end()
+    assert torch.equal(out, ref)
+    assert torch.equal(info["losses"], rinfo["losses"])
+
+
+def test_header_sharded_gradient_sum(engine, oracle):
+    """Two half-batch sessions whose gradient buffers are summed by hand == the whole-batch optimisation
+    (what sharded_header_optimize does with an NCCL all-reduce)."""
+    inp = oracle.make_inputs("emb", 6, 80, seed=9)
+    src, tgt = (inp["vc_tgt"] * 0.6).cuda(), (inp["adv_tgt"] * 0.6).cuda()
+    n, inv = 4, 1.0 / (6 * 128)
+    full = engine.header_optimize(src, tgt, n, epsilon=0.003)
+    a = engine.header_begin(src[:3], tgt[:3], n, epsilon=0.003, inv_norm=inv)
+    b = engine.header_begin(src[3:], tgt[3:], n, epsilon=0.003, inv_norm=inv)
+    for _ in range(n):
+        a.grad_half(); b.grad_half()
+        tot = a.grad + b.grad
+        a.grad.copy_(tot); b.grad.copy_(tot)
+        a.apply_half(); b.apply_half()
+    ha, _ = a.end()
+    hb, _ = b.end()
+    assert torch.equal(ha, hb)
+    err = (ha - full).abs()
+    assert float(err.median()) < 1e-6 and float((err > 1e-4).float().mean()) < 0.02
+
+
+def test_header_dropin_class(gpu_model, cpu_model, oracle, tmp_path):
+    """attack_vc_b200.header_model.UniversalPerturbationHeader keeps the reference's surface
+    (models/header_model.py:7-103) and is driven exactly as train_header.py:39-46,77-85 drives it."""
+    from attack_vc_b200.header_model import UniversalPerturbationHeader
+    inp = oracle.make_inputs("emb", 2, 100, seed=12)
+    src, tgt = inp["vc_tgt"].unsqueeze(1) * 0.6, inp["adv_tgt"].unsqueeze(1) * 0.6
+    H = UniversalPerturbationHeader(mel_bins=80, time_length=100, device="cuda")
+    opt = torch.optim.Adam([H.header], lr=1e-3)
+    H.optimize(src.cuda(), tgt.cuda(), gpu_model, opt, num_iterations=4, epsilon=0.1, lambda_param=0.5)
+    o = oracle.run_header(cpu_model, src, tgt, 4)
+    assert H.header.shape == (1, 1, 80, 100) and H.header.requires_grad
+    assert float((H.header.detach().cpu() - o["header"]).abs().median()) < 1e-6
+    # a second call continues from the stored header (fresh Adam moments, as a new optimizer would)
+    H.optimize(src.cuda(), tgt.cuda(), gpu_model, torch.optim.Adam([H.header], lr=1e-3), num_iterations=1)
+    assert float(H.header.detach().abs().max()) > float(o["header"].abs().max())
+    long = torch.randn(2, 1, 80, 150, device="cuda")
+    out = H.apply_header(long)
+    assert torch.equal(out[..., 100:], long[..., 100:].clamp(-1, 1))
+    assert torch.equal(out[..., :100], (long[..., :100] + H.header.detach()).clamp(-1, 1))
+    short = torch.randn(1, 1, 80, 60, device="cuda")
+    assert torch.equal(H.apply_header(short), (short + H.header.detach()[..., :60]).clamp(-1, 1))
+    H.save(str(tmp_path / "h.pt"))
+    G = UniversalPerturbationHeader(80, 100, device="cuda")
+    G.load(str(tmp_path / "h.pt"))
+    assert torch.equal(G.header, H.header) and G.header.requires_grad
+    with pytest.raises(TypeError):
+        H.optimize(src.cuda(), tgt.cuda(), lambda m: m, opt, num_iterations=1)
+    with pytest.raises(TypeError):
+        H.optimize(src.cuda(), tgt.cuda(), gpu_model, torch.optim.SGD([H.header], lr=1e-3), num_iterations=1)

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from attack_vc_b200.distributed import global_inv_norm, shard_bounds, sharded_attack
+from attack_vc_b200.distributed import global_inv_norm, shard_bounds, sharded_attack, sharded_header_optimize
 
 
 def test_shard_bounds_cover_batch():
@@ -82,3 +82,83 @@ def test_sharded_equals_unsharded_gloo(kind):
     assert adv.shape == full_adv.shape
     assert torch.allclose(adv, full_adv, rtol=0, atol=2e-6)
     assert torch.allclose(losses, info["losses"], rtol=1e-4, atol=0)
+
+
+class _CpuHeaderSession:
+    """Stand-in for HeaderSession (grad_half / all-reduce on .grad / apply_half) built from torch autograd, to
+    exercise the per-iteration all-reduce plumbing under gloo."""
+
+    def __init__(self, model, src, tgt, n, eps, lam, lr, header0, inv_norm):
+        T = src.shape[-1]
+        self.model, self.src, self.tgt, self.eps, self.lam, self.inv = model, src, tgt, eps, lam, inv_norm
+        self.h = (torch.zeros(1, 1, 80, T) if header0 is None else header0.clone().reshape(1, 1, 80, T)).requires_grad_(True)
+        self.opt = torch.optim.Adam([self.h], lr=lr)
+        self.grad = torch.zeros(T * 80)
+        self.losses = []
+
+    def grad_half(self):
+        enc = lambda m: self.model.speaker_encoder(m.squeeze(1))
+        with torch.no_grad():
+            e_s, e_t = enc(self.src), enc(self.tgt)
+        e = enc(torch.clamp(self.src + self.h, -1.0, 1.0))
+        loss = ((e - e_t).square().sum() - self.lam * (e - e_s).square().sum()) * self.inv
+        self.opt.zero_grad()
+        loss.backward()
+        self.losses.append(float(loss))
+        self.grad.copy_(self.h.grad[0, 0].t().reshape(-1))        # time-major like the device buffer
+
+    def apply_half(self):
+        T = self.h.shape[-1]
+        self.h.grad = self.grad.reshape(T, 80).t().reshape(1, 1, 80, T).clone()
+        self.opt.step()
+        with torch.no_grad():
+            self.h.data = torch.clamp(self.h.data, -self.eps, self.eps)
+
+    def end(self):
+        return self.h.detach().clone(), {"losses": torch.tensor(self.losses)}
+
+
+class _CpuHeaderEngine:
+    def __init__(self, model):
+        self.model = model
+
+    def header_begin(self, src, tgt, n, eps, lam, lr, header0=None, inv_norm=None, want_loss=True):
+        return _CpuHeaderSession(self.model, src, tgt, n, eps, lam, lr, header0, inv_norm)
+
+
+def _header_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import adainvc_oracle as O
+        inp = O.make_inputs("emb", 3, 40, seed=21)
+        src, tgt = inp["vc_tgt"].unsqueeze(1) * 0.6, inp["adv_tgt"].unsqueeze(1) * 0.6
+        eng = _CpuHeaderEngine(O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0))
+        hdr, losses = sharded_header_optimize(eng, src, tgt, 3, epsilon=0.002, lambda_param=0.5, lr=1e-3)
+        if rank == 0:
+            q.put((hdr.numpy().copy(), losses.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_header_equals_unsharded_gloo():
+    """Header gradients summed over 2 ranks + the same Adam step on every rank == the reference's single-process
+    optimize over the whole batch (models/header_model.py:25-68)."""
+    from oracle import adainvc_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_header_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    hdr, losses = (torch.from_numpy(a) for a in q.get(timeout=300))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    inp = O.make_inputs("emb", 3, 40, seed=21)
+    src, tgt = inp["vc_tgt"].unsqueeze(1) * 0.6, inp["adv_tgt"].unsqueeze(1) * 0.6
+    o = O.run_header(O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0), src, tgt, 3, epsilon=0.002)
+    assert torch.allclose(hdr, o["header"], rtol=0, atol=2e-6)
+    assert torch.allclose(losses.double(), o["losses"], rtol=1e-4, atol=1e-9)

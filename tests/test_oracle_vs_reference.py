@@ -62,6 +62,25 @@ def test_attack_loop_bit_exact(oracle, ref_model, cpu_model, kind):
     assert torch.equal(r.detach(), o["adv"])
 
 
+def test_header_optimize_bit_exact(oracle, ref_model, cpu_model):
+    """oracle.run_header == UniversalPerturbationHeader.optimize (models/header_model.py:25-68) with the AdaIN-VC
+    speaker encoder and Adam([header], lr=1e-3) as train_header.py builds it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_header_model", os.path.join(REFERENCE, "models", "header_model.py"))
+    hm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(hm)
+    inp = oracle.make_inputs("emb", 3, 100, seed=4)
+    src, tgt = inp["vc_tgt"].unsqueeze(1) * 0.6, inp["adv_tgt"].unsqueeze(1) * 0.6      # some |x| > 1: the clamp is live
+    assert float(src.abs().max()) > 1.0
+    H = hm.UniversalPerturbationHeader(80, 100, device="cpu")
+    opt = torch.optim.Adam([H.header], lr=1e-3)
+    H.optimize(src, tgt, lambda m: ref_model.speaker_encoder(m.squeeze(1)), opt, num_iterations=5, epsilon=0.003,
+               lambda_param=0.5)
+    o = oracle.run_header(cpu_model, src, tgt, 5, epsilon=0.003)
+    assert torch.equal(H.header.detach(), o["header"])
+    assert float(o["header"].abs().max()) == pytest.approx(0.003, rel=1e-6)             # the eps clamp is live too
+
+
 def _ref_predictive():
     import importlib.util
     spec = importlib.util.spec_from_file_location("ref_predictive_model", os.path.join(REFERENCE, "models", "predictive_model.py"))
