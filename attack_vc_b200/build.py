@@ -38,7 +38,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libavc_b200.so cannot be built and there is no CPU fallback")
-    cmd = [nvcc, *NVCC_FLAGS, *map(str, sources()), "-o", str(LIB)]
+    extra = os.environ.get("AVC_NVCC_EXTRA", "").split()      # experiments only (e.g. -DAVC_SMALL_MINB=2)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *map(str, sources()), "-o", str(LIB)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -35,6 +35,32 @@ struct TapGroup {
   int wts;          // rows between consecutive taps in W (>= kc; the full K of the packed image)
 };
 
+// Folding of the decoder's InstanceNorm/AdaIN/activation kernels into the small-M conv kernel (batch-1 attacks, where
+// every separate launch is ~6 us of dependent latency).  The PRODUCER conv writes, next to its raw output, per-tile
+// partial statistics; the CONSUMER conv finalises them (fixed order) and applies the normalisation while it loads
+// its activation window.  Same arithmetic per element as norm_act_fwd_kernel / norm_act_bwd_kernel.
+struct FoldPro {
+  int mode;             // 0 none; 1 window = act(AdaIN(IN(A))) [+ res]; 2 window = d/dy of that, A = upstream gradient
+  int C, T;             // channels / rows of the normalised tensor (window channel n -> n % C)
+  const float* part;    // [B][n_part][C][2] producer partials: mode 1 (sum, M2 about the tile mean), mode 2 (S1, S2)
+  int n_part, part_tm, part_up, part_T;   // every partial covers part_tm rows (part_T % part_tm == 0 or the host does not fold)
+  const float* stats;   // finalised [B][C][2] (mean, rstd): mode 1 when n_part == 0, mode 2 always
+  float* stats_out;     // mode 1: finalised statistics for the backward pass
+  const float* cond; int cond_bs;   // AdaIN mean at [0,C), std at [C,2C) of row b
+  const float* y;       // mode 2: raw conv output saved by the forward pass, indexed like A
+  float* gcond; int gcond_bs;       // mode 2: d mean / d std
+  ResArgs res;          // mode 1: skip connection added after the activation
+  float* out;           // mode 1: optional materialised [B][T][C] result (own rows of the column-tile-0 CTAs)
+};
+struct FoldEpi {
+  int mode;             // 0 none; 1 partial statistics of the output; 2 partial S1 = sum ga, S2 = sum ga*xhat
+  int C;
+  float* part; int n_part;
+  const float* y; const float* stats; const float* cond; int cond_bs;   // mode 2 (y indexed like Y)
+};
+constexpr int kFoldPC = 6 * 128;
+constexpr int kFoldMaxPart = 64;   // most partials one normalisation may be split into (conv_small_kernel keeps them in registers)   // per-channel constants in shared memory (floats)
+
 struct ConvArgs {
   const float* A; long long a_bs; int a_rs; int T_a;     // operand rows per utterance
   const float* Mk; long long m_bs; int m_rs;             // optional: a *= act'(Mk) on load
@@ -55,6 +81,10 @@ struct ConvArgs {
   // win_off[n_groups] = first zero row; ring = number of weight-slab buffers, slab_floats = size of one
   int win_off[kMaxGroups + 1];
   int ring, slab_floats;
+  int e_rows, e_off[kMaxGroups];   // dgrad: rows behind the zero rows holding the pre-summed operands of reflect-edge output rows (0: sum in the loop)
+  int f_stage, f_s2, f_epi;   // float offsets of the fold regions behind the weight ring (conv_small_kernel)
+  FoldPro pro;
+  FoldEpi epi;
   TapGroup g[kMaxGroups];
 };
 
@@ -277,15 +307,30 @@ constexpr int kSmTN = 32;
 constexpr int kSmWarps = 16;        // K slices per slab: warp w contracts rows [kSmKW*w, kSmKW*(w+1))
 constexpr int kSmKW = 128 / kSmWarps;
 
+#ifdef AVC_SMALL_PROFILE
+// debug build only: per-launch phase stamps of CTA 0 (globaltimer ns at entry/exit, SM clock in between)
+__device__ unsigned long long g_small_prof[8192][12];
+__device__ unsigned int g_small_prof_n;
+#define SMALL_STAMP(i) do { if (prof_slot < 8192u && threadIdx.x == 0) g_small_prof[prof_slot][i] = clock64(); } while (0)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#else
+#define SMALL_STAMP(i) do {} while (0)
+#endif
+#ifndef AVC_SMALL_MINB
+#define AVC_SMALL_MINB 1
+#endif
+// n % C for the few wraps the folded decoder has (n < 2C with pixel shuffle x2): no integer division
+__device__ __forceinline__ int fold_ch(int n, int C) { while (n >= C) n -= C; return n; }
+
 template <int TM>
-__global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArgs p) {
+__global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kernel(const ConvArgs p) {
   constexpr int RM = TM / 4, NT = 32 * kSmWarps;
   extern __shared__ __align__(16) float smem[];
   const int g_lo = p.zsplit ? blockIdx.z : 0;
   const int g_hi = p.zsplit ? blockIdx.z + 1 : p.n_groups;
   float* S = smem;                                                    // windows, then kMaxTaps zero rows
   const int zr = p.win_off[p.n_groups];
-  float* Wr = smem + (size_t)(zr + kMaxTaps) * kSRow;                 // [ring][slab_floats]
+  float* Wr = smem + (size_t)(zr + kMaxTaps + p.e_rows) * kSRow;      // [ring][slab_floats]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = lane & 7, ty = lane >> 3;
@@ -298,6 +343,14 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
 
   int n_slabs = 0;
   for (int gi = g_lo; gi < g_hi; ++gi) n_slabs += p.g[gi].n_taps;
+#ifdef AVC_SMALL_PROFILE
+  unsigned prof_slot = 0xffffffffu;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    prof_slot = atomicAdd(&g_small_prof_n, 1u);
+    if (prof_slot < 8192u) { g_small_prof[prof_slot][0] = gtimer(); g_small_prof[prof_slot][7] = ((unsigned long long)gridDim.x << 32) | (gridDim.y << 16) | (p.pro.mode << 4) | p.epi.mode; }
+  }
+  SMALL_STAMP(1);
+#endif
 
   // ---- weight ring: slab q = (group, tap) in issue order ----------------------------------------
   // thread constants of the copy: 16-byte column chunk wn of K rows wk, wk + 32, ...
@@ -321,44 +374,223 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
     cp_async_commit();
   };
   pdl_launch_dependents();
-  for (int q = 0; q < p.ring - 1; ++q) issue(q);
+  const bool all_resident = n_slabs <= p.ring;   // every slab has its own buffer: no refills, no per-slab barrier
+  const int n_pre = all_resident ? n_slabs : p.ring - 1;
+  for (int q = 0; q < n_pre; ++q) issue(q);
   pdl_wait();   // weights are loop constants; the windows below are the predecessor's output
+  SMALL_STAMP(2);
 
-  // ---- all activation windows -> smem (loads of all groups in flight together) -------------------
+  // ---- activation windows -> smem (loads of all groups in flight together) --------------------------
+  // Folded normalisation (FoldPro / FoldEpi): EVERY global read this CTA needs -- producer partials, raw window,
+  // the second operand of the transform (skip connection or saved conv output), the epilogue's operands -- is issued
+  // here as one batch of cp.async, so the fold adds no extra L2 round trip to the dependent chain of the iteration.
+  float* PC = Wr + (size_t)p.ring * p.slab_floats;                    // [6][128]: mu, rstd, std, mean, m1, m2
+  float* stage = PC + p.f_stage;                                      // [n_part][C][2] producer partials
+  float* S2 = PC + p.f_s2;                                            // second-operand window, same geometry as S
+  float* EP = PC + p.f_epi;                                           // epilogue operands: y tile [TM][32], stats [64], mean [32], std [32]
+  const int fmode = p.pro.mode;
+  const bool second = fmode == 2 || (fmode == 1 && p.pro.res.mode != RES_NONE);
   for (int i = tid; i < kMaxTaps * kSRow; i += NT) S[zr * kSRow + i] = 0.f;
-  for (int gi = g_lo; gi < g_hi; ++gi) {
-    const TapGroup& G = p.g[gi];
-    const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
-    const int woff = p.zsplit ? 0 : p.win_off[gi];
-    if (wg.nrows > (p.zsplit ? zr : p.win_off[gi + 1] - p.win_off[gi])) __trap();   // host sized the window too small
-    const int c4n = G.kc >> 2;
-    const float* Ab = p.A + (long long)b * p.a_bs + G.a_ch_off;
-    const float* Mb = p.Mk ? p.Mk + (long long)b * p.m_bs + G.a_ch_off : nullptr;
-    const int drow = NT / c4n, dcol = NT - drow * c4n;   // idx += NT without a division per element
-    int row = tid / c4n, col = tid - row * c4n;
-    for (int idx = tid; idx < wg.nrows * c4n; idx += NT, row += drow, col += dcol) {
-      if (col >= c4n) { col -= c4n; ++row; }
-      const int c = col << 2;
-      const int r = wg.wlo + row;
-      int rr; bool ok;
-      if (!p.bwd) {
-        rr = r < 0 ? -r : r;
-        if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
-        ok = rr >= 0 && rr < p.T_a;
-      } else {
-        ok = r >= 0 && (r % p.s) == 0;
-        rr = r / p.s;
-        ok = ok && rr < p.T_a;
+  // walk(fn): fn(G, smem float offset of the element, c, r, rr, ok) for every float4 of every window
+  auto walk = [&](auto&& fn) {
+    for (int gi = g_lo; gi < g_hi; ++gi) {
+      const TapGroup& G = p.g[gi];
+      const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
+      const int woff = p.zsplit ? 0 : p.win_off[gi];
+      if (wg.nrows > (p.zsplit ? zr : p.win_off[gi + 1] - p.win_off[gi])) __trap();   // host sized the window too small
+      const int c4n = G.kc >> 2;
+      // idx += NT without a division per element (and none at all for the usual 128-channel group)
+      int drow, row;
+      if (c4n == 32) { drow = NT / 32; row = tid >> 5; } else { drow = NT / c4n; row = tid / c4n; }
+      const int dcol = NT - drow * c4n;
+      int col = tid - row * c4n;
+      for (int idx = tid; idx < wg.nrows * c4n; idx += NT, row += drow, col += dcol) {
+        if (col >= c4n) { col -= c4n; ++row; }
+        const int c = col << 2;
+        const int r = wg.wlo + row;
+        int rr; bool ok;
+        if (!p.bwd) {
+          rr = r < 0 ? -r : r;
+          if (rr >= p.T_a) rr = 2 * (p.T_a - 1) - rr;
+          ok = rr >= 0 && rr < p.T_a;
+        } else if (p.s == 1) {
+          rr = r;
+          ok = r >= 0 && r < p.T_a;
+        } else {
+          ok = r >= 0 && (r % p.s) == 0;
+          rr = r / p.s;
+          ok = ok && rr < p.T_a;
+        }
+        fn(G, (woff + row) * kSRow + c, c, r, rr, ok);
       }
+    }
+  };
+  if (!fmode) {
+    walk([&](const TapGroup& G, int so, int c, int r, int rr, bool ok) {
       float4 v = f4zero();
       if (ok) {
-        v = ld4(Ab + (long long)rr * p.a_rs + c);
-        if (Mb) v = dact4mul(v, ld4(Mb + (long long)rr * p.m_rs + c), p.slope);
+        v = ld4(p.A + (long long)b * p.a_bs + G.a_ch_off + (long long)rr * p.a_rs + c);
+        if (p.Mk) v = dact4mul(v, ld4(p.Mk + (long long)b * p.m_bs + G.a_ch_off + (long long)rr * p.m_rs + c), p.slope);
       }
-      st4(S + (size_t)(woff + row) * kSRow + c, v);
+      st4(S + so, v);
+    });
+  } else {
+    const FoldPro& f = p.pro;
+    const int nfl = f.n_part * f.C * 2;
+    const float* src = f.part + (long long)b * nfl;
+    for (int i = tid * 4; i < nfl; i += NT * 4) cp_async16(stage + i, src + i, true);
+    walk([&](const TapGroup& G, int so, int c, int r, int rr, bool ok) {
+      const float* a = p.A + (long long)b * p.a_bs + G.a_ch_off + (long long)rr * p.a_rs + c;
+      cp_async16(S + so, ok ? a : p.A, ok);
+      if (second) {
+        const float* q;
+        if (fmode == 2) q = f.y + (long long)b * p.a_bs + G.a_ch_off + (long long)rr * p.a_rs + c;
+        else q = f.res.R + (long long)b * f.res.bs + (long long)(f.res.mode == RES_UP ? (f.res.rf == 2 ? rr >> 1 : rr / f.res.rf) : rr) * f.res.rs + fold_ch(G.a_ch_off + c, f.C);
+        cp_async16(S2 + so, ok ? q : p.A, ok);
+      }
+    });
+  }
+  if (p.epi.mode == 2) {
+    const FoldEpi& e = p.epi;
+    const int cc0 = fold_ch(n0, e.C);
+    if (tid < TM * 8) {
+      const int er = tid >> 3, en = (tid & 7) << 2;
+      const bool eok = t0 + er < t1 && n0 + en < p.N;
+      cp_async16(EP + er * kSmTN + en, eok ? e.y + (long long)b * p.y_bs + (long long)(t0 + er) * p.y_rs + n0 + en : e.y, eok);
+    } else if (tid < TM * 8 + 16) {
+      const int j = tid - TM * 8;
+      cp_async16(EP + TM * kSmTN + j * 4, e.stats + ((long long)b * e.C + cc0) * 2 + j * 4, true);
+    } else if (tid < TM * 8 + 32) {
+      const int j = tid - TM * 8 - 16;      // 0..7 mean, 8..15 std
+      if (e.cond) cp_async16(EP + TM * kSmTN + 64 + j * 4, e.cond + (long long)b * e.cond_bs + (j >> 3) * e.C + cc0 + (j & 7) * 4, true);
+      else st4(EP + TM * kSmTN + 64 + j * 4, j < 8 ? f4zero() : make_float4(1.f, 1.f, 1.f, 1.f));
     }
   }
+  if (fmode) {
+    const FoldPro& f = p.pro;
+    // finalised statistics / AdaIN row of channel c (4 threads per channel, sub = partial residue class)
+    const int c = tid >> 2, sub = tid & 3;
+    const bool cv = c < f.C;
+    float mu = 0.f, rstd = 0.f, cs = 1.f, cm = 0.f;
+    if (cv) {
+      if (f.mode == 2 || f.n_part == 0) {
+        mu = f.stats[((long long)b * f.C + c) * 2];
+        rstd = f.stats[((long long)b * f.C + c) * 2 + 1];
+      }
+      if (f.cond) { cs = f.cond[(long long)b * f.cond_bs + f.C + c]; cm = f.cond[(long long)b * f.cond_bs + c]; }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    SMALL_STAMP(10);
+    __syncthreads();
+    SMALL_STAMP(8);
+    // fixed-order reduction of the partials: residue classes q = sub (mod 4) summed in order, then ((0+1)+(2+3))
+    auto quad = [](float v) {
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      return v;
+    };
+    const int cq = cv ? c : 0;
+    const float invT = __frcp_rn((float)f.T);
+    // partial q of this channel: st2[q * C]; this thread sums q = sub, sub+4, ...  (every partial covers part_tm rows:
+    // the host folds only when the producer's tiles are not ragged)
+    const float2* st2 = reinterpret_cast<const float2*>(stage) + cq + sub * f.C;
+    const int qstep = 4 * f.C, n_it = (f.n_part - sub + 3) >> 2;
+    if (f.mode == 1 && f.n_part > 0) {
+      const float cnt = (float)f.part_tm, inv_cnt = __frcp_rn(cnt);
+      float sum = 0.f;
+#pragma unroll 2
+      for (int i = 0; i < n_it; ++i) sum += st2[i * qstep].x;
+      mu = quad(sum) * invT;
+      float m2 = 0.f;
+#pragma unroll 2
+      for (int i = 0; i < n_it; ++i) {
+        const float2 pq = st2[i * qstep];
+        const float d = fmaf(pq.x, inv_cnt, -mu);
+        m2 += fmaf(cnt * d, d, pq.y);
+      }
+      rstd = rsqrtf(quad(m2) * invT + 1e-5f);
+      if (cv && sub == 0 && f.stats_out && blockIdx.y == 0 && t0 == 0) {
+        f.stats_out[((long long)b * f.C + c) * 2] = mu;
+        f.stats_out[((long long)b * f.C + c) * 2 + 1] = rstd;
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+    if (f.mode == 2) {
+#pragma unroll 2
+      for (int i = 0; i < n_it; ++i) { const float2 pq = st2[i * qstep]; s1 += pq.x; s2 += pq.y; }
+      s1 = quad(s1); s2 = quad(s2);
+      if (cv && sub == 0 && f.gcond && blockIdx.y == 0 && t0 == 0) {
+        f.gcond[(long long)b * f.gcond_bs + c] = s1;
+        f.gcond[(long long)b * f.gcond_bs + f.C + c] = s2;
+      }
+    }
+    if (cv && sub == 0) {
+      PC[c] = mu; PC[128 + c] = rstd; PC[256 + c] = cs; PC[384 + c] = cm;
+      PC[512 + c] = s1 * invT; PC[640 + c] = s2 * invT;
+    }
+    SMALL_STAMP(9);
+    __syncthreads();
+    SMALL_STAMP(11);
+    // transform the raw windows in place
+    walk([&](const TapGroup& G, int so, int cch, int r, int rr, bool ok) {
+      if (!ok) return;
+      const int cc = fold_ch(G.a_ch_off + cch, f.C);
+      float4 v = ld4(S + so);
+      const float4 mu4 = ld4(PC + cc), rs = ld4(PC + 128 + cc), cs4 = ld4(PC + 256 + cc), cm4 = ld4(PC + 384 + cc);
+      if (fmode == 1) {
+        float4 a;
+        a.x = fmaf((v.x - mu4.x) * rs.x, cs4.x, cm4.x); a.y = fmaf((v.y - mu4.y) * rs.y, cs4.y, cm4.y);
+        a.z = fmaf((v.z - mu4.z) * rs.z, cs4.z, cm4.z); a.w = fmaf((v.w - mu4.w) * rs.w, cs4.w, cm4.w);
+        v = act4(a, p.slope);
+        if (second) v = f4add(v, ld4(S2 + so));
+        if (f.out && blockIdx.y == 0 && r >= t0 && r < t1) st4(f.out + ((long long)b * f.T + rr) * f.C + cc, v);
+      } else {
+        const float4 yv = ld4(S2 + so);
+        const float4 m1 = ld4(PC + 512 + cc), m2 = ld4(PC + 640 + cc);
+        const float4 xh = make_float4((yv.x - mu4.x) * rs.x, (yv.y - mu4.y) * rs.y, (yv.z - mu4.z) * rs.z, (yv.w - mu4.w) * rs.w);
+        const float4 a = make_float4(fmaf(xh.x, cs4.x, cm4.x), fmaf(xh.y, cs4.y, cm4.y), fmaf(xh.z, cs4.z, cm4.z), fmaf(xh.w, cs4.w, cm4.w));
+        const float4 ga = dact4mul(v, a, p.slope);
+        v.x = rs.x * cs4.x * (ga.x - m1.x - xh.x * m2.x); v.y = rs.y * cs4.y * (ga.y - m1.y - xh.y * m2.y);
+        v.z = rs.z * cs4.z * (ga.z - m1.z - xh.z * m2.z); v.w = rs.w * cs4.w * (ga.w - m1.w - xh.w * m2.w);
+      }
+      st4(S + so, v);
+    });
+  } else if (p.epi.mode == 2) {
+    cp_async_commit();     // the epilogue operands ride in their own group, older than every ring refill
+  }
 
+  // ---- dgrad tiles that touch a reflect-padded border: an output row t there also receives the gradient of the mirrored
+  // positions.  Sum its 2-3 operand rows ONCE per tap into extra rows, so the main loop reads one operand row per output row.
+  if (p.e_rows && p.bwd) {
+    bool any = false;
+    for (int gi = g_lo; gi < g_hi; ++gi) any = any || win_geom(p.bwd, p.s, p.T_y, p.g[gi], t0, t1).edge;
+    if (any) {
+      __syncthreads();       // windows complete
+      for (int gi = g_lo; gi < g_hi; ++gi) {
+        const TapGroup& G = p.g[gi];
+        const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
+        if (!wg.edge) continue;
+        const int nl = max(0, wg.lt_hi - wg.lt_lo + 1), nr = max(0, wg.rt_hi - wg.rt_lo + 1);
+        const float* Sg0 = S + (size_t)p.win_off[gi] * kSRow;
+        float* Eg = S + (size_t)p.e_off[gi] * kSRow;
+        const int c4n = G.kc >> 2, n_pair = (nl + nr) * G.n_taps;
+        // thread -> (16-byte column, first (row, tap) pair); no integer division (each thread has one or two pairs)
+        int c4, pair, dpair;
+        if (c4n == 32) { c4 = tid & 31; pair = tid >> 5; dpair = NT / 32; }
+        else { c4 = tid % c4n; pair = tid / c4n; dpair = NT / c4n; if (dpair == 0) __trap(); }
+        for (; pair < n_pair; pair += dpair) {
+          int j = 0, tap = pair;
+          while (tap >= G.n_taps) { tap -= G.n_taps; ++j; }
+          const int t = j < nl ? wg.lt_lo + j : wg.rt_lo + (j - nl);
+          const int r0 = t + G.off0 - wg.wlo + tap;
+          const int r1 = (j < nl ? -t : 2 * (p.T_y - 1) - t) + G.off0 - wg.wlo + tap;
+          st4(Eg + (size_t)pair * kSRow + c4 * 4, f4add(ld4(Sg0 + (size_t)r0 * kSRow + c4 * 4), ld4(Sg0 + (size_t)r1 * kSRow + c4 * 4)));
+        }
+      }
+    }
+  }
+  SMALL_STAMP(3);
   // ---- main loop over slabs ------------------------------------------------------------------------
   float acc[RM][4];
 #pragma unroll
@@ -367,7 +599,6 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   bool edge = false;
   int cg = g_lo - 1, ctap = 0, cnt = 0;   // group / tap of the slab being consumed
   int c_slot = 0;                          // ring slot of the slab being consumed
-  const bool all_resident = n_slabs <= p.ring - 1;   // the prologue already requested every slab: no ring traffic, no per-slab barrier
   const float* Sg = S;
   int kc = 0;
   for (int q = 0; q < n_slabs; ++q) {
@@ -376,16 +607,22 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
       const TapGroup& G = p.g[cg];
       cnt = G.n_taps; kc = G.kc;
       const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
-      edge = wg.edge;
-      Sg = S + (size_t)(p.zsplit ? 0 : p.win_off[cg]) * kSRow;
-      const int zrel = zr - (p.zsplit ? 0 : p.win_off[cg]);
+      const bool pre = p.e_rows && p.bwd;      // mirrored operands were pre-summed above
+      edge = wg.edge && !pre;
+      const int wbase = p.zsplit ? 0 : p.win_off[cg];
+      Sg = S + (size_t)wbase * kSRow;
+      const int zrel = zr - wbase;
+      const int nl = max(0, wg.lt_hi - wg.lt_lo + 1);
 #pragma unroll
       for (int i = 0; i < RM; ++i) {
         const int t = t0 + ty * RM + i;
         const bool tv = t < t1;
+        const bool lt = tv && t >= wg.lt_lo && t <= wg.lt_hi, rt = tv && t >= wg.rt_lo && t <= wg.rt_hi;
         rb[i][0] = tv ? t * sv + G.off0 - wg.wlo : zrel;
-        rb[i][1] = (tv && t >= wg.lt_lo && t <= wg.lt_hi) ? -t + G.off0 - wg.wlo : zrel;
-        rb[i][2] = (tv && t >= wg.rt_lo && t <= wg.rt_hi) ? 2 * (p.T_y - 1) - t + G.off0 - wg.wlo : zrel;
+        rb[i][1] = lt ? -t + G.off0 - wg.wlo : zrel;
+        rb[i][2] = rt ? 2 * (p.T_y - 1) - t + G.off0 - wg.wlo : zrel;
+        if (pre && lt) rb[i][0] = p.e_off[cg] - wbase + (t - wg.lt_lo) * G.n_taps;
+        if (pre && rt) rb[i][0] = p.e_off[cg] - wbase + (nl + t - wg.rt_lo) * G.n_taps;
       }
     }
     if (!all_resident) {
@@ -433,6 +670,7 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   }
   cp_async_wait<0>();
   __syncthreads();                       // all slabs consumed: the ring becomes the reduction buffer
+  SMALL_STAMP(4);
 
   // ---- fixed-order sum of the 8 K-slices, then the epilogue ----------------------------------------
   float* red = Wr;                       // [kSmWarps][TM][kSmTN]
@@ -440,20 +678,65 @@ __global__ void __launch_bounds__(32 * kSmWarps) conv_small_kernel(const ConvArg
   for (int i = 0; i < RM; ++i)
     st4(red + ((size_t)warp * TM + ty * RM + i) * kSmTN + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
   __syncthreads();
-  if (tid >= TM * (kSmTN / 4)) return;
   const int row = tid >> 3, nn = (tid & 7) << 2;
   const int t = t0 + row, n = n0 + nn;
-  if (t >= t1 || n >= p.N) return;
-  float4 v = ld4(red + (size_t)row * kSmTN + nn);
-#pragma unroll
-  for (int w = 1; w < kSmWarps; ++w) v = f4add(v, ld4(red + ((size_t)w * TM + row) * kSmTN + nn));
+  const bool active = tid < TM * (kSmTN / 4) && t < t1 && n < p.N;
+#ifndef AVC_SMALL_PROFILE
+  if (!active && !p.epi.mode) return;
+#endif
   const int ch = p.zsplit ? blockIdx.z * p.N + n : n;   // output channel
-  if (p.bias) v = f4add(v, ld4(p.bias + ch));
-  if (p.Om) v = dact4mul(v, ld4(p.Om + (long long)b * p.om_bs + (long long)t * p.om_rs + ch), p.slope);
-  if (p.act) v = act4(v, p.slope);
-  if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)t * p.y2_rs + ch, v);
-  if (p.res.mode != RES_NONE) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
-  st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
+  float4 v = f4zero();
+  if (active) {
+    v = ld4(red + (size_t)row * kSmTN + nn);
+#pragma unroll
+    for (int w = 1; w < kSmWarps; ++w) v = f4add(v, ld4(red + ((size_t)w * TM + row) * kSmTN + nn));
+    if (p.bias) v = f4add(v, ld4(p.bias + ch));
+    if (p.Om) v = dact4mul(v, ld4(p.Om + (long long)b * p.om_bs + (long long)t * p.om_rs + ch), p.slope);
+    if (p.act) v = act4(v, p.slope);
+    if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)t * p.y2_rs + ch, v);
+    if (p.res.mode != RES_NONE) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
+    st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
+  }
+#ifdef AVC_SMALL_PROFILE
+  SMALL_STAMP(5);
+  if (prof_slot < 8192u && threadIdx.x == 0) g_small_prof[prof_slot][6] = gtimer();
+#endif
+  if (!p.epi.mode) return;
+  // ---- folded normalisation: per-tile partial sums over the rows of this tile, one thread per column ----
+  const FoldEpi& e = p.epi;
+  float* tile = S;                       // [2][TM][kSmTN]; the windows are dead
+  float4 e1 = v, e2 = f4zero();
+  if (e.mode == 2 && active) {
+    const float* EPc = Wr + (size_t)p.ring * p.slab_floats + p.f_epi;
+    const float4 s0 = ld4(EPc + TM * kSmTN + nn * 2), s1 = ld4(EPc + TM * kSmTN + nn * 2 + 4);
+    const float4 mu = make_float4(s0.x, s0.z, s1.x, s1.z), rs = make_float4(s0.y, s0.w, s1.y, s1.w);
+    const float4 cm = ld4(EPc + TM * kSmTN + 64 + nn), cs = ld4(EPc + TM * kSmTN + 96 + nn);
+    const float4 yv = ld4(EPc + row * kSmTN + nn);
+    const float4 xh = make_float4((yv.x - mu.x) * rs.x, (yv.y - mu.y) * rs.y, (yv.z - mu.z) * rs.z, (yv.w - mu.w) * rs.w);
+    const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
+    e1 = dact4mul(v, a, p.slope);
+    e2 = make_float4(e1.x * xh.x, e1.y * xh.y, e1.z * xh.z, e1.w * xh.w);
+  }
+  if (tid < TM * (kSmTN / 4)) {
+    st4(tile + row * kSmTN + nn, e1);
+    st4(tile + (TM + row) * kSmTN + nn, e2);
+  }
+  __syncthreads();
+  if (tid < kSmTN && n0 + tid < p.N) {
+    const int rows = t1 - t0, col = n0 + tid;
+    const int half = col >= e.C ? 1 : 0;                    // N is C or 2C (pixel shuffle x2)
+    const int q = (t0 / TM) * (p.N > e.C ? 2 : 1) + half;
+    float* dst = e.part + (((long long)b * e.n_part + q) * e.C + (col - half * e.C)) * 2;
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < rows; ++r) s1 += tile[r * kSmTN + tid];
+    if (e.mode == 1) {
+      const float m = s1 * __frcp_rn((float)rows);
+      for (int r = 0; r < rows; ++r) { const float d = tile[r * kSmTN + tid] - m; s2 = fmaf(d, d, s2); }
+    } else {
+      for (int r = 0; r < rows; ++r) s2 += tile[(TM + r) * kSmTN + tid];
+    }
+    dst[0] = s1; dst[1] = s2;
+  }
 }
 
 }  // namespace avc

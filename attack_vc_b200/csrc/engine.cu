@@ -213,7 +213,7 @@ void init_kernel_attributes() {
 
 // small-M path: every window resident, deep weight ring (conv_simt.cuh: conv_small_kernel)
 template <int TM>
-bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
+bool small_cfg(ConvArgs& a, dim3& grid, size_t& smem) {
   const int tiles_t = (a.T_y + TM - 1) / TM;
   int rows[kMaxGroups] = {0}, kc_max = 0, slabs_max = 0, slabs_all = 0;
   for (int g = 0; g < a.n_groups; ++g) {
@@ -233,33 +233,83 @@ bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
   }
   a.win_off[a.n_groups] = off;
   a.slab_floats = kc_max * kSmTN;
-  const size_t win_bytes = (size_t)(off + kMaxTaps) * kSRow * sizeof(float);
+  // dgrad: rows for the pre-summed operands of reflect-edge output rows (conv_small_kernel); skipped when a tile's left and
+  // right border rows overlap (tiny T) or the rows would take too much shared memory -- the kernel then sums inside the loop
+  a.e_rows = 0;
+  static const bool no_edge_pre = getenv("AVC_NO_EDGE_PRE") != nullptr;
+  if (a.bwd && !a.zsplit && !no_edge_pre) {
+    int e_tot = 0; bool ok = true;
+    for (int g = 0; g < a.n_groups && ok; ++g) {
+      int need = 0;
+      for (int i = 0; i < tiles_t; ++i) {
+        const WinGeom w = win_geom(a.bwd, a.s, a.T_y, a.g[g], i * TM, std::min(i * TM + TM, a.T_y));
+        const int nl = std::max(0, w.lt_hi - w.lt_lo + 1), nr = std::max(0, w.rt_hi - w.rt_lo + 1);
+        if (nl && nr && w.lt_hi >= w.rt_lo) ok = false;
+        need = std::max(need, (nl + nr) * a.g[g].n_taps);
+      }
+      a.e_off[g] = off + kMaxTaps + e_tot;
+      e_tot += need;
+    }
+    if (ok && e_tot > 0 && (size_t)e_tot * kSRow * sizeof(float) <= 32 * 1024) a.e_rows = e_tot;
+  }
+  const size_t win_bytes = (size_t)(off + kMaxTaps + a.e_rows) * kSRow * sizeof(float);
   const size_t slab_bytes = (size_t)a.slab_floats * sizeof(float);
+  // fold regions behind the ring: constants | staged partials | second-operand window | epilogue operands
+  size_t fold_floats = 0;
+  a.f_stage = a.f_s2 = a.f_epi = 0;
+  if (a.pro.mode) {
+    a.f_stage = kFoldPC;
+    a.f_s2 = a.f_stage + a.pro.n_part * a.pro.C * 2;
+    const bool second = a.pro.mode == 2 || a.pro.res.mode != RES_NONE;
+    fold_floats = (size_t)a.f_s2 + (second ? (size_t)off * kSRow : 0);
+  }
+  if (a.epi.mode == 2) { a.f_epi = (int)fold_floats; fold_floats += (size_t)TM * kSmTN + 128; }
+  const size_t fold_bytes = fold_floats * sizeof(float);
+  const size_t avail = kSmemMax - fold_bytes;
   const int n_slabs = a.zsplit ? slabs_max : slabs_all;
-  if (win_bytes + 2 * slab_bytes > kSmemMax) return false;
-  int ring = (int)std::min<size_t>((kSmemMax - win_bytes) / slab_bytes, 8);
-  ring = std::max(2, std::min(ring, n_slabs + 1));
+  if (win_bytes + 2 * slab_bytes > avail) return false;
+  // a ring that holds every slab (n_slabs + 1 buffers) needs no refills and no per-slab barrier; else at most 8 buffers
+  int ring = (int)((avail - win_bytes) / slab_bytes);
+  if (ring < n_slabs) ring = std::min(ring, 8);
+  ring = std::max(2, std::min(ring, n_slabs));
   while ((size_t)ring * slab_bytes < (size_t)kSmWarps * TM * kSmTN * sizeof(float)) ++ring;   // the ring doubles as the split-K reduction buffer
-  const size_t smem = win_bytes + (size_t)ring * slab_bytes;
+  smem = win_bytes + (size_t)ring * slab_bytes + fold_bytes;
   if (smem > kSmemMax) return false;
   a.ring = ring;
-  dim3 grid(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : 1);
+  grid = dim3(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : 1);
+  return true;
+}
+template <int TM>
+bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
+  dim3 grid; size_t smem = 0;
+  if (!small_cfg<TM>(a, grid, smem)) return false;
   launch_k(conv_small_kernel<TM>, grid, 32 * kSmWarps, smem, st, a);
   return true;
+}
+
+// tile height the small-M kernel would run this conv with; 0: one of the generic tiles takes it
+int small_tm(const ConvArgs& a, int sm_count, bool allow_small = true) {
+  const long long z = a.zsplit ? a.n_groups : 1;
+  auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
+  if (ctas(64, 64) >= 2LL * sm_count || ctas(32, 32) >= 2LL * sm_count) return 0;
+  static const bool no_small = getenv("AVC_NO_SMALL") != nullptr;
+  if (no_small || !allow_small) return 0;
+  ConvArgs t = a; dim3 g; size_t sm = 0;
+  if (ctas(8, kSmTN) <= sm_count) return small_cfg<8>(t, g, sm) ? 8 : 0;
+  return small_cfg<16>(t, g, sm) ? 16 : 0;
 }
 
 void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st, bool allow_small = true) {
   // pick the largest tile that still gives every SM about two CTAs; small-M problems (batch 1)
   // take the latency-oriented kernel
+  const int tm = small_tm(a, sm_count, allow_small);
+  if (tm == 8 && launch_conv_small_cfg<8>(a, st)) return;
+  if (tm == 16 && launch_conv_small_cfg<16>(a, st)) return;
+  if (a.pro.mode || a.epi.mode) fail(AVC_ERR_STATE, "folded normalisation planned for a conv the small-M kernel cannot run");
   const long long z = a.zsplit ? a.n_groups : 1;
   auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
   if (ctas(64, 64) >= 2LL * sm_count) { launch_conv_cfg<4, 16, 16>(a, st); return; }
   if (ctas(32, 32) >= 2LL * sm_count) { launch_conv_cfg<2, 8, 16>(a, st); return; }
-  static const bool no_small = getenv("AVC_NO_SMALL") != nullptr;
-  if (!no_small && allow_small) {
-    const bool one_wave8 = ctas(8, kSmTN) <= sm_count;
-    if (one_wave8 ? launch_conv_small_cfg<8>(a, st) : launch_conv_small_cfg<16>(a, st)) return;
-  }
   launch_conv_cfg<1, 8, 16>(a, st);
 }
 
@@ -370,6 +420,12 @@ struct Emitter {
     }
     l.fn = [hh, ac](cudaStream_t st) { launch_conv(hh, ac, st); };
     out->push_back(std::move(l));
+  }
+  // tile height if this conv runs on the small-M CUDA-core kernel (the only one that folds normalisations), else 0
+  int small_tm_of(const ConvArgs& a, const ConvW* cw) const {
+    if (h->conv_impl != 0 && h->conv_impl != 1) return 0;
+    if (cw && want_tc(h, a, tc_op_conv(*cw, a.bwd != 0))) return 0;
+    return small_tm(a, h->sm_count, true);
   }
   void push(int kind, double flops, double bytes, std::function<void(cudaStream_t)> fn) {
     Launch l;
@@ -671,7 +727,91 @@ AffineArgs affine_args(const DecoderW& W, const DecActs& A, const float* emb) {
 }
 
 // emb-dependent part of the decoder forward (models.py:417-434); `outT` receives the [B,T,c_out] mel
+// ---- folded decoder (batch-1 plans): no separate normalisation launches --------------------------------
+// A normalisation whose application is deferred into the window load of the next conv (conv_simt.cuh: FoldPro).
+struct PendingNorm {
+  float* y; int T;                 // raw conv output viewed [B][T][ch]
+  const float* cond;               // AdaIN row of this layer
+  const float* stats; float* stats_out;
+  float* part; int n_part, tm, up, part_T;
+  ResArgs res; float* out;
+};
+
+bool fold_enabled(const DecoderW& W) {
+  static const bool off = getenv("AVC_NO_FOLD") != nullptr;
+  return !off && W.d.c_h <= 128 && W.d.c_h % 32 == 0;
+}
+
+// consumer side: conv reads act(AdaIN(IN(P.y))) [+res] through its window
+void fold_fwd_in(ConvArgs& a, const PendingNorm& P, int ch, int cb) {
+  a.A = P.y; a.a_bs = (long long)P.T * ch; a.a_rs = ch; a.T_a = P.T;
+  FoldPro& f = a.pro;
+  f.mode = 1; f.C = ch; f.T = P.T; f.part = P.part; f.n_part = P.n_part; f.part_tm = P.tm; f.part_up = P.up; f.part_T = P.part_T;
+  f.stats = P.stats; f.stats_out = P.stats_out; f.cond = P.cond; f.cond_bs = cb; f.res = P.res; f.out = P.out;
+}
+// producer side: conv also writes the per-tile partial statistics of its output
+float* fold_fwd_out(Emitter& E, ConvArgs& a, int tm, int ch, int* n_part) {
+  const int np = cdiv(a.T_y, tm) * (a.N / ch);
+  if (np > kFoldMaxPart || a.T_y % tm) { *n_part = 0; return nullptr; }   // ragged tiles: the consumer assumes equal row counts
+  float* part = E.mem->f((size_t)a.B * np * ch * 2);
+  a.epi.mode = 1; a.epi.C = ch; a.epi.part = part; a.epi.n_part = np;
+  *n_part = np;
+  return part;
+}
+
+bool emit_decoder_fwd_folded(Emitter& E, const DecoderW& W, const DecActs& A, const float* emb, const Tens& outT) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
+  if (!fold_enabled(W)) return false;
+  AffineArgs f = affine_args(W, A, emb);
+  dim3 ag(A.B, L2);
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { launch_k(affine_fwd_kernel, ag, 1024, 0, st, f); });
+  PendingNorm P{};
+  P.y = A.c1[0]; P.T = A.Td[0]; P.cond = A.cond; P.stats = A.st1[0]; P.res = no_res();   // c1[0] and its statistics are loop constants
+  for (int l = 0; l < A.nb; ++l) {
+    const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
+    if (up != 1 && up != 2) return false;
+    if (l > 0) {
+      ConvArgs a1 = fwd_conv_args(W.c1[l], tens(A.h[l], Ti, ch), tens(A.c1[l], Ti, ch), A.B, false, slope);
+      fold_fwd_in(a1, P, ch, cb);
+      const int tm = E.small_tm_of(a1, &W.c1[l]);
+      if (!tm || a1.s != 1) return false;
+      PendingNorm Q{};
+      Q.part = fold_fwd_out(E, a1, tm, ch, &Q.n_part);
+      if (!Q.part) return false;
+      Q.y = A.c1[l]; Q.T = Ti; Q.cond = A.cond + (2 * l) * 2 * ch; Q.stats_out = A.st1[l]; Q.tm = tm; Q.up = 1; Q.part_T = Ti; Q.res = no_res();
+      E.conv(a1, &W.c1[l]);
+      P = Q;
+    }
+    ConvArgs a2 = fwd_conv_args(W.c2[l], tens(A.r1[l], Ti, ch), Tens{A.c2[l], (long long)Ti * ch * up, ch * up, Ti}, A.B, false, slope);
+    fold_fwd_in(a2, P, ch, cb);
+    const int tm2 = E.small_tm_of(a2, &W.c2[l]);
+    if (!tm2 || a2.s != 1 || a2.N != ch * up) return false;
+    PendingNorm Q{};
+    Q.part = fold_fwd_out(E, a2, tm2, ch, &Q.n_part);
+    if (!Q.part) return false;
+    Q.y = A.c2[l]; Q.T = To; Q.cond = A.cond + (2 * l + 1) * 2 * ch; Q.stats_out = A.st2[l]; Q.tm = tm2; Q.up = up; Q.part_T = Ti;
+    Q.res = mk_res(tens(A.h[l], Ti, ch), up > 1 ? RES_UP : RES_SAME, up);
+    Q.out = l + 1 < A.nb ? A.h[l + 1] : nullptr;      // h[l+1] is read again as the skip connection of block l+1
+    E.conv(a2, &W.c2[l]);
+    P = Q;
+  }
+  ConvArgs ao = fwd_conv_args(W.out_conv, tens(A.h[A.nb], A.Td[A.nb], ch), outT, A.B, false, slope);
+  fold_fwd_in(ao, P, ch, cb);
+  if (!E.small_tm_of(ao, &W.out_conv) || ao.s != 1) return false;
+  E.conv(ao, &W.out_conv);
+  return true;
+}
+
+void emit_decoder_fwd_plain(Emitter& E, const DecoderW& W, const DecActs& A, const float* emb, const Tens& outT);
 void emit_decoder_fwd(Emitter& E, const DecoderW& W, const DecActs& A, const float* emb, const Tens& outT) {
+  const size_t mark = E.out->size();
+  if (emit_decoder_fwd_folded(E, W, A, emb, outT)) return;
+  E.out->resize(mark);
+  emit_decoder_fwd_plain(E, W, A, emb, outT);
+}
+
+void emit_decoder_fwd_plain(Emitter& E, const DecoderW& W, const DecActs& A, const float* emb, const Tens& outT) {
   const float slope = W.d.neg_slope;
   const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
   AffineArgs f = affine_args(W, A, emb);
@@ -697,7 +837,78 @@ void emit_decoder_fwd(Emitter& E, const DecoderW& W, const DecActs& A, const flo
 }
 
 // decoder backward: gout = dL/d(decoder output) -> gemb_parts [B, 2*nb, 128]
+// producer side (backward): the dgrad conv also writes per-tile S1/S2 of the normalisation its output flows into
+bool fold_bwd_out(Emitter& E, ConvArgs& a, const ConvW* cw, const float* y, const float* stats, const float* cond, int ch, int cb,
+                  float** part, int* n_part) {
+  const int tm = E.small_tm_of(a, cw);
+  if (!tm || a.N != ch) return false;
+  const int np = cdiv(a.T_y, tm);
+  if (np > kFoldMaxPart) return false;
+  *part = E.mem->f((size_t)a.B * np * ch * 2);
+  *n_part = np;
+  a.epi.mode = 2; a.epi.C = ch; a.epi.part = *part; a.epi.n_part = np; a.epi.y = y; a.epi.stats = stats; a.epi.cond = cond; a.epi.cond_bs = cb;
+  return true;
+}
+void fold_bwd_in(ConvArgs& a, const float* part, int n_part, int T, const float* y, const float* stats, const float* cond,
+                 float* gcond, int ch, int cb) {
+  FoldPro& f = a.pro;
+  f.mode = 2; f.C = ch; f.T = T; f.part = part; f.n_part = n_part; f.stats = stats; f.cond = cond; f.cond_bs = cb; f.y = y;
+  f.gcond = gcond; f.gcond_bs = cb; f.res = no_res();
+}
+
+bool emit_decoder_bwd_folded(Emitter& E, const DecoderW& W, const DecActs& A, const Tens& gout) {
+  const float slope = W.d.neg_slope;
+  const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
+  if (!fold_enabled(W)) return false;
+  int cur = 0;
+  float* part = nullptr; int n_part = 0;
+  {
+    ConvArgs a = bwd_conv_args(W.out_conv, gout, tens(A.gh[cur], A.Td[A.nb], ch), A.B, slope);
+    if (!fold_bwd_out(E, a, &W.out_conv, A.c2[A.nb - 1], A.st2[A.nb - 1], A.cond + (2 * (A.nb - 1) + 1) * 2 * ch, ch, cb, &part, &n_part)) return false;
+    E.conv(a, &W.out_conv);
+  }
+  for (int l = A.nb - 1; l >= 0; --l) {
+    const int Ti = A.Td[l], To = A.Td[l + 1], up = W.d.upsample[l];
+    Tens gh = tens(A.gh[cur], To, ch);
+    // dgrad of conv2: its window is d/d(c2[l]) of act(AdaIN(IN(c2[l]))) applied to gh, viewed [Ti, ch*up]
+    ConvArgs a2 = bwd_conv_args(W.c2[l], Tens{gh.p, (long long)Ti * ch * up, ch * up, Ti}, tens(A.gr1, Ti, ch), A.B, slope);
+    fold_bwd_in(a2, part, n_part, To, A.c2[l], A.st2[l], A.cond + (2 * l + 1) * 2 * ch, A.gcond + (2 * l + 1) * 2 * ch, ch, cb);
+    if (a2.s != 1) return false;
+    if (l > 0) {
+      if (!fold_bwd_out(E, a2, &W.c2[l], A.c1[l], A.st1[l], A.cond + (2 * l) * 2 * ch, ch, cb, &part, &n_part)) return false;
+    } else if (!E.small_tm_of(a2, &W.c2[l])) {
+      return false;
+    }
+    E.conv(a2, &W.c2[l]);
+    if (l > 0) {
+      Tens gnext = tens(A.gh[cur ^ 1], Ti, ch);
+      ConvArgs a1 = bwd_conv_args(W.c1[l], tens(A.gr1, Ti, ch), gnext, A.B, slope);
+      a1.res = mk_res(gh, up > 1 ? RES_UP_BWD : RES_SAME, up);
+      fold_bwd_in(a1, part, n_part, Ti, A.c1[l], A.st1[l], A.cond + (2 * l) * 2 * ch, A.gcond + (2 * l) * 2 * ch, ch, cb);
+      if (a1.s != 1) return false;
+      if (!fold_bwd_out(E, a1, &W.c1[l], A.c2[l - 1], A.st2[l - 1], A.cond + (2 * (l - 1) + 1) * 2 * ch, ch, cb, &part, &n_part)) return false;
+      E.conv(a1, &W.c1[l]);
+      cur ^= 1;
+    } else {
+      // first AdaIN of the decoder: c1[0] is a loop constant, only d cond is needed
+      emit_norm_bwd(E, A.gr1, A.c1[0], A.st1[0], A.cond, cb, nullptr, A.gcond, cb, A.B, Ti, ch, slope);
+    }
+  }
+  AffineArgs f = affine_args(W, A, nullptr);
+  dim3 ag(A.B, L2);
+  E.push(LK_AFFINE, 2.0 * A.B * L2 * 256 * 128, 0, [f, ag](cudaStream_t st) { launch_k(affine_bwd_kernel, ag, 1024, 0, st, f); });
+  return true;
+}
+
+void emit_decoder_bwd_plain(Emitter& E, const DecoderW& W, const DecActs& A, const Tens& gout);
 void emit_decoder_bwd(Emitter& E, const DecoderW& W, const DecActs& A, const Tens& gout) {
+  const size_t mark = E.out->size();
+  if (emit_decoder_bwd_folded(E, W, A, gout)) return;
+  E.out->resize(mark);
+  emit_decoder_bwd_plain(E, W, A, gout);
+}
+
+void emit_decoder_bwd_plain(Emitter& E, const DecoderW& W, const DecActs& A, const Tens& gout) {
   const float slope = W.d.neg_slope;
   const int ch = W.d.c_h, L2 = 2 * A.nb, cb = L2 * 2 * ch;
   int cur = 0;
@@ -1701,6 +1912,19 @@ int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float*
   });
 }
 
+#ifdef AVC_SMALL_PROFILE
+// debug build only (not part of the C-ABI): copy out and reset the conv_small phase stamps
+extern "C" int avc_debug_small_profile(unsigned long long* out, int cap) {
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_small_prof_n, sizeof(n));
+  const int m = (int)std::min<unsigned>(std::min<unsigned>(n, 8192u), (unsigned)cap);
+  if (m > 0) cudaMemcpyFromSymbol(out, g_small_prof, (size_t)m * 12 * sizeof(unsigned long long));
+  n = 0;
+  cudaMemcpyToSymbol(g_small_prof_n, &n, sizeof(n));
+  return m;
+}
+#endif
 int64_t avc_kernel_launches(const avc_handle* h) { return h ? h->launches : -1; }
 int32_t avc_launches_per_iter(const avc_handle* h) { return h ? h->launches_per_iter : -1; }
 
