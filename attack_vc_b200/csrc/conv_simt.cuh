@@ -22,6 +22,7 @@ namespace avc {
 
 constexpr int kMaxGroups = 10;
 constexpr int kMaxTaps = 8;
+constexpr int kMaxZk = 3;
 constexpr int kKSub = 32;        // K rows of a weight slab staged per pipeline step
 constexpr int kSRow = 128 + 4;   // smem row pitch of the activation window (floats)
 
@@ -81,6 +82,10 @@ struct ConvArgs {
   // win_off[n_groups] = first zero row; ring = number of weight-slab buffers, slab_floats = size of one
   int win_off[kMaxGroups + 1];
   int ring, slab_floats;
+  // K split over blockIdx.z (conv_small_kernel): CTA z contracts groups [zk_lo[z], zk_hi[z]) only; z = 0 writes Y (with bias /
+  // residual), z > 0 writes the contiguous [B][T_y][N] partial y_part[z-1]; the consumer adds the partials in order
+  int zk, zk_lo[kMaxZk], zk_hi[kMaxZk];
+  float* y_part[kMaxZk - 1];
   int e_rows, e_off[kMaxGroups];   // dgrad: rows behind the zero rows holding the pre-summed operands of reflect-edge output rows (0: sum in the loop)
   int f_stage, f_s2, f_epi;   // float offsets of the fold regions behind the weight ring (conv_small_kernel)
   FoldPro pro;
@@ -326,8 +331,8 @@ template <int TM>
 __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kernel(const ConvArgs p) {
   constexpr int RM = TM / 4, NT = 32 * kSmWarps;
   extern __shared__ __align__(16) float smem[];
-  const int g_lo = p.zsplit ? blockIdx.z : 0;
-  const int g_hi = p.zsplit ? blockIdx.z + 1 : p.n_groups;
+  const int g_lo = p.zk > 1 ? p.zk_lo[blockIdx.z] : p.zsplit ? blockIdx.z : 0;
+  const int g_hi = p.zk > 1 ? p.zk_hi[blockIdx.z] : p.zsplit ? blockIdx.z + 1 : p.n_groups;
   float* S = smem;                                                    // windows, then kMaxTaps zero rows
   const int zr = p.win_off[p.n_groups];
   float* Wr = smem + (size_t)(zr + kMaxTaps + p.e_rows) * kSRow;      // [ring][slab_floats]
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
       const TapGroup& G = p.g[gi];
       const WinGeom wg = win_geom(p.bwd, p.s, p.T_y, G, t0, t1);
       const int woff = p.zsplit ? 0 : p.win_off[gi];
-      if (wg.nrows > (p.zsplit ? zr : p.win_off[gi + 1] - p.win_off[gi])) __trap();   // host sized the window too small
+      if (woff + wg.nrows > zr) __trap();   // host sized the window too small
       const int c4n = G.kc >> 2;
       // idx += NT without a division per element (and none at all for the usual 128-channel group)
       int drow, row;
@@ -425,7 +430,14 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
       }
     }
   };
-  if (!fmode) {
+  if (!fmode && !p.Mk) {
+    // nothing to do to the operand on the way in: asynchronous copies, all in flight at once (they join the first weight
+    // group the main loop waits for)
+    walk([&](const TapGroup& G, int so, int c, int r, int rr, bool ok) {
+      cp_async16(S + so, ok ? p.A + (long long)b * p.a_bs + G.a_ch_off + (long long)rr * p.a_rs + c : p.A, ok);
+    });
+    cp_async_commit();
+  } else if (!fmode) {
     walk([&](const TapGroup& G, int so, int c, int r, int rr, bool ok) {
       float4 v = f4zero();
       if (ok) {
@@ -566,6 +578,7 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
     bool any = false;
     for (int gi = g_lo; gi < g_hi; ++gi) any = any || win_geom(p.bwd, p.s, p.T_y, p.g[gi], t0, t1).edge;
     if (any) {
+      cp_async_wait<0>();
       __syncthreads();       // windows complete
       for (int gi = g_lo; gi < g_hi; ++gi) {
         const TapGroup& G = p.g[gi];
@@ -626,7 +639,8 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
       }
     }
     if (!all_resident) {
-      cp_async_wait_dyn(p.ring - 2);
+      if (q == 0) cp_async_wait<0>();    // the activation windows may ride in the youngest group
+      else cp_async_wait_dyn(p.ring - 2);
       __syncthreads();                   // slab q landed for everyone; everyone is done with slab q-1 (and, first time, the windows are visible)
       issue(q + p.ring - 1);             // refills the buffer slab q-1 used
     } else if (q == 0) {
@@ -690,12 +704,14 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
     v = ld4(red + (size_t)row * kSmTN + nn);
 #pragma unroll
     for (int w = 1; w < kSmWarps; ++w) v = f4add(v, ld4(red + ((size_t)w * TM + row) * kSmTN + nn));
-    if (p.bias) v = f4add(v, ld4(p.bias + ch));
+    const bool first = p.zk <= 1 || blockIdx.z == 0;
+    if (p.bias && first) v = f4add(v, ld4(p.bias + ch));
     if (p.Om) v = dact4mul(v, ld4(p.Om + (long long)b * p.om_bs + (long long)t * p.om_rs + ch), p.slope);
     if (p.act) v = act4(v, p.slope);
     if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)t * p.y2_rs + ch, v);
-    if (p.res.mode != RES_NONE) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
-    st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
+    if (p.res.mode != RES_NONE && first) v = f4add(v, res_load4(p.res, b, t, p.T_y, ch));
+    if (first) st4(p.Y + (long long)b * p.y_bs + (long long)t * p.y_rs + ch, v);
+    else st4(p.y_part[blockIdx.z - 1] + ((long long)b * p.T_y + t) * p.N + ch, v);
   }
 #ifdef AVC_SMALL_PROFILE
   SMALL_STAMP(5);

@@ -270,6 +270,7 @@ __global__ void loss_sum_kernel(const float* __restrict__ parts, int parts_per_s
 // ---------------------------------------------------------------------------------------------
 struct UpdateArgs {
   const float* g_adv; long long g_bs; int g_rs;   // [B,T,C] gradient w.r.t. adv
+  const float* g_part[2]; int n_gpart;             // contiguous [B,T,C] partials added to g_adv in order (K-split bank dgrad)
   const float* x;                                  // [B,T,C] contiguous
   float* w; float* m; float* v;                    // contiguous
   float* adv; long long adv_bs; int adv_rs;        // may live inside the bank "cat" buffer
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(256) adam_tanh_update_kernel(const UpdateArgs 
     const long long bt = i / c4n;
     const int t = (int)(bt % p.T), b = (int)(bt / p.T);
     const long long lin = i * 4;
-    const float4 g = ld4(p.g_adv + (long long)b * p.g_bs + (long long)t * p.g_rs + c);
+    float4 g = ld4(p.g_adv + (long long)b * p.g_bs + (long long)t * p.g_rs + c);
+    for (int q = 0; q < p.n_gpart; ++q) g = f4add(g, ld4(p.g_part[q] + lin));
     float4 w = ld4(p.w + lin), m = ld4(p.m + lin), v = ld4(p.v + lin);
     const float4 x = ld4(p.x + lin);
     float gw[4], wa[4] = {w.x, w.y, w.z, w.w}, ma[4] = {m.x, m.y, m.z, m.w}, va[4] = {v.x, v.y, v.z, v.w};
@@ -369,7 +371,8 @@ __global__ void header_perturb_kernel(const float* __restrict__ x, const float* 
   }
 }
 
-__global__ void header_grad_kernel(const float* __restrict__ g_adv, long long g_bs, int g_rs, const float* __restrict__ x,
+__global__ void header_grad_kernel(const float* __restrict__ g_adv, long long g_bs, int g_rs, const float* __restrict__ gp0,
+                                   const float* __restrict__ gp1, const float* __restrict__ x,
                                    const float* __restrict__ h, float* __restrict__ gh, int B, int T, int C) {
   pdl_enter();
   const int c4n = C >> 2;
@@ -381,7 +384,9 @@ __global__ void header_grad_kernel(const float* __restrict__ g_adv, long long g_
     float4 s = f4zero();
     for (int b = 0; b < B; ++b) {
       const float4 xv = ld4(x + ((long long)b * T + t) * C + c);
-      const float4 g = ld4(g_adv + (long long)b * g_bs + (long long)t * g_rs + c);
+      float4 g = ld4(g_adv + (long long)b * g_bs + (long long)t * g_rs + c);
+      if (gp0) g = f4add(g, ld4(gp0 + ((long long)b * T + t) * C + c));     // K-split partials of the bank dgrad, in order
+      if (gp1) g = f4add(g, ld4(gp1 + ((long long)b * T + t) * C + c));
       const float p0 = xv.x + hv.x, p1 = xv.y + hv.y, p2 = xv.z + hv.z, p3 = xv.w + hv.w;
       s.x += (p0 >= -1.f && p0 <= 1.f) ? g.x : 0.f;
       s.y += (p1 >= -1.f && p1 <= 1.f) ? g.y : 0.f;

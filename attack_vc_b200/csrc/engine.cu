@@ -226,10 +226,20 @@ bool small_cfg(ConvArgs& a, dim3& grid, size_t& smem) {
     slabs_max = std::max(slabs_max, a.g[g].n_taps);
     slabs_all += a.g[g].n_taps;
   }
-  int off = 0;
-  for (int g = 0; g < a.n_groups; ++g) {
-    a.win_off[g] = a.zsplit ? 0 : off;
-    off = a.zsplit ? std::max(off, rows[g]) : off + rows[g];
+  // window rows: every group of a CTA is resident at once; with a z split (conv bank forward: one group per z; K split:
+  // a range of groups per z) the offsets restart for every z and the region is sized for the largest
+  const int n_rng = a.zk > 1 ? a.zk : 1;
+  int off = 0, slabs_rng = 0;
+  for (int r = 0; r < n_rng; ++r) {
+    const int lo = a.zk > 1 ? a.zk_lo[r] : 0, hi = a.zk > 1 ? a.zk_hi[r] : a.n_groups;
+    int o = 0, sl = 0;
+    for (int g = lo; g < hi; ++g) {
+      a.win_off[g] = a.zsplit ? 0 : o;
+      o = a.zsplit ? std::max(o, rows[g]) : o + rows[g];
+      sl += a.g[g].n_taps;
+    }
+    off = std::max(off, o);
+    slabs_rng = std::max(slabs_rng, sl);
   }
   a.win_off[a.n_groups] = off;
   a.slab_floats = kc_max * kSmTN;
@@ -238,19 +248,24 @@ bool small_cfg(ConvArgs& a, dim3& grid, size_t& smem) {
   a.e_rows = 0;
   static const bool no_edge_pre = getenv("AVC_NO_EDGE_PRE") != nullptr;
   if (a.bwd && !a.zsplit && !no_edge_pre) {
-    int e_tot = 0; bool ok = true;
-    for (int g = 0; g < a.n_groups && ok; ++g) {
-      int need = 0;
-      for (int i = 0; i < tiles_t; ++i) {
-        const WinGeom w = win_geom(a.bwd, a.s, a.T_y, a.g[g], i * TM, std::min(i * TM + TM, a.T_y));
-        const int nl = std::max(0, w.lt_hi - w.lt_lo + 1), nr = std::max(0, w.rt_hi - w.rt_lo + 1);
-        if (nl && nr && w.lt_hi >= w.rt_lo) ok = false;
-        need = std::max(need, (nl + nr) * a.g[g].n_taps);
+    int e_max = 0; bool ok = true;
+    for (int r = 0; r < n_rng && ok; ++r) {
+      const int lo = a.zk > 1 ? a.zk_lo[r] : 0, hi = a.zk > 1 ? a.zk_hi[r] : a.n_groups;
+      int e_tot = 0;
+      for (int g = lo; g < hi && ok; ++g) {
+        int need = 0;
+        for (int i = 0; i < tiles_t; ++i) {
+          const WinGeom w = win_geom(a.bwd, a.s, a.T_y, a.g[g], i * TM, std::min(i * TM + TM, a.T_y));
+          const int nl = std::max(0, w.lt_hi - w.lt_lo + 1), nr = std::max(0, w.rt_hi - w.rt_lo + 1);
+          if (nl && nr && w.lt_hi >= w.rt_lo) ok = false;
+          need = std::max(need, (nl + nr) * a.g[g].n_taps);
+        }
+        a.e_off[g] = off + kMaxTaps + e_tot;
+        e_tot += need;
       }
-      a.e_off[g] = off + kMaxTaps + e_tot;
-      e_tot += need;
+      e_max = std::max(e_max, e_tot);
     }
-    if (ok && e_tot > 0 && (size_t)e_tot * kSRow * sizeof(float) <= 32 * 1024) a.e_rows = e_tot;
+    if (ok && e_max > 0 && (size_t)e_max * kSRow * sizeof(float) <= 56 * 1024) a.e_rows = e_max;
   }
   const size_t win_bytes = (size_t)(off + kMaxTaps + a.e_rows) * kSRow * sizeof(float);
   const size_t slab_bytes = (size_t)a.slab_floats * sizeof(float);
@@ -266,7 +281,7 @@ bool small_cfg(ConvArgs& a, dim3& grid, size_t& smem) {
   if (a.epi.mode == 2) { a.f_epi = (int)fold_floats; fold_floats += (size_t)TM * kSmTN + 128; }
   const size_t fold_bytes = fold_floats * sizeof(float);
   const size_t avail = kSmemMax - fold_bytes;
-  const int n_slabs = a.zsplit ? slabs_max : slabs_all;
+  const int n_slabs = a.zsplit ? slabs_max : a.zk > 1 ? slabs_rng : slabs_all;
   if (win_bytes + 2 * slab_bytes > avail) return false;
   // a ring that holds every slab (n_slabs + 1 buffers) needs no refills and no per-slab barrier; else at most 8 buffers
   int ring = (int)((avail - win_bytes) / slab_bytes);
@@ -276,7 +291,7 @@ bool small_cfg(ConvArgs& a, dim3& grid, size_t& smem) {
   smem = win_bytes + (size_t)ring * slab_bytes + fold_bytes;
   if (smem > kSmemMax) return false;
   a.ring = ring;
-  grid = dim3(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : 1);
+  grid = dim3(a.B * tiles_t, (a.N + kSmTN - 1) / kSmTN, a.zsplit ? a.n_groups : a.zk > 1 ? a.zk : 1);
   return true;
 }
 template <int TM>
@@ -289,7 +304,7 @@ bool launch_conv_small_cfg(ConvArgs a, cudaStream_t st) {
 
 // tile height the small-M kernel would run this conv with; 0: one of the generic tiles takes it
 int small_tm(const ConvArgs& a, int sm_count, bool allow_small = true) {
-  const long long z = a.zsplit ? a.n_groups : 1;
+  const long long z = a.zsplit ? a.n_groups : a.zk > 1 ? a.zk : 1;
   auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
   if (ctas(64, 64) >= 2LL * sm_count || ctas(32, 32) >= 2LL * sm_count) return 0;
   static const bool no_small = getenv("AVC_NO_SMALL") != nullptr;
@@ -305,7 +320,7 @@ void launch_conv_simt(const ConvArgs& a, int sm_count, cudaStream_t st, bool all
   const int tm = small_tm(a, sm_count, allow_small);
   if (tm == 8 && launch_conv_small_cfg<8>(a, st)) return;
   if (tm == 16 && launch_conv_small_cfg<16>(a, st)) return;
-  if (a.pro.mode || a.epi.mode) fail(AVC_ERR_STATE, "folded normalisation planned for a conv the small-M kernel cannot run");
+  if (a.pro.mode || a.epi.mode || a.zk > 1) fail(AVC_ERR_STATE, "folded normalisation / K split planned for a conv the small-M kernel cannot run");
   const long long z = a.zsplit ? a.n_groups : 1;
   auto ctas = [&](int TM, int TN) { return (long long)a.B * ((a.T_y + TM - 1) / TM) * ((a.N + TN - 1) / TN) * z; };
   if (ctas(64, 64) >= 2LL * sm_count) { launch_conv_cfg<4, 16, 16>(a, st); return; }
@@ -610,7 +625,11 @@ void emit_tail(Emitter& E, const TailArgs& t, int B) {
 }
 
 // speaker-encoder backward from gpool ([B,128], gradient of every pooled row) down to d input
-void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Tens& gin) {
+// partial input gradients of a K-split conv-bank dgrad (small-M plans): the consumer adds p[0..n) to gin, in order
+struct GradParts { const float* p[kMaxZk - 1] = {nullptr, nullptr}; int n = 0; };
+
+// `parts` non-null: the caller's consumer of gin can add partials, so the bank dgrad may split its K over blockIdx.z
+void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Tens& gin, GradParts* parts = nullptr) {
   const float slope = W.d.neg_slope;
   const int ch = W.d.c_h, nb = W.d.n_conv_blocks;
   Tens gout{A.gpool, (long long)ch, 0, A.Tl[nb]};   // broadcast over time (row stride 0)
@@ -660,6 +679,36 @@ void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Ten
     }
     tc_ok = tc_ok && op.add_pass(0, op.n_groups, W.bank[0].tc_bwd[0].cn[0], 0, 1, -PL);   // one pass sums the 8 transposed convs
     if (!tc_ok) op = TcOp{};
+    static const bool no_zk = getenv("AVC_NO_KSPLIT") != nullptr;
+    if (parts && !no_zk && W.n_bank >= kMaxZk && !want_tc(E.h, a, op) && E.small_tm_of(a, nullptr)) {
+      // batch-1 plans: this conv contracts K = sum_k k*c_bank (36 weight slabs for the 8-kernel bank), four times the longest
+      // other layer, on too few CTAs.  Split K into kMaxZk balanced ranges of whole groups (longest-processing-time first).
+      ConvArgs sp = a;
+      int order[kMaxGroups], bin_of[kMaxGroups], load[kMaxZk] = {0};
+      for (int z = 0; z < W.n_bank; ++z) order[z] = z;
+      std::sort(order, order + W.n_bank, [&](int x, int y) { return a.g[x].n_taps > a.g[y].n_taps; });
+      for (int i = 0; i < W.n_bank; ++i) {
+        int best = 0;
+        for (int q = 1; q < kMaxZk; ++q) if (load[q] < load[best]) best = q;
+        bin_of[order[i]] = best; load[best] += a.g[order[i]].n_taps;
+      }
+      int n = 0;
+      for (int q = 0; q < kMaxZk; ++q) {
+        sp.zk_lo[q] = n;
+        for (int i = 0; i < W.n_bank; ++i) if (bin_of[order[i]] == q) sp.g[n++] = a.g[order[i]];
+        sp.zk_hi[q] = n;
+      }
+      sp.zk = kMaxZk;
+      if (E.small_tm_of(sp, nullptr)) {
+        for (int q = 0; q + 1 < kMaxZk; ++q) {
+          sp.y_part[q] = E.mem->f((size_t)A.B * A.T * W.d.c_in);
+          parts->p[q] = sp.y_part[q];
+        }
+        parts->n = kMaxZk - 1;
+        E.conv(sp, nullptr, nullptr);
+        return;
+      }
+    }
     E.conv(a, nullptr, &op);
   }
 }
@@ -1179,8 +1228,10 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     const unsigned g = ew_grid((long long)nel / 4, h->sm_count);
     E.push(LK_UPDATE, 0, 12.0 * nel, [=](cudaStream_t s_) { launch_k(perturb_kernel, g, 256, 0, s_, x, w, adv.p, adv.bs, adv.rs, B, T, C, eps); });
   };
-  auto update = [&](Emitter& E, const Tens& gadv) {
+  auto update = [&](Emitter& E, const Tens& gadv, const GradParts& gp) {
     UpdateArgs u{};
+    u.n_gpart = gp.n;
+    for (int q = 0; q < gp.n; ++q) u.g_part[q] = gp.p[q];
     u.g_adv = gadv.p; u.g_bs = gadv.bs; u.g_rs = gadv.rs; u.x = x; u.w = w; u.m = mm; u.v = vv;
     u.adv = adv.p; u.adv_bs = adv.bs; u.adv_rs = adv.rs; u.gw_out = gw; u.B = B; u.T = T; u.C = C; u.eps = eps;
     u.table = table; u.step = step; u.done = done;
@@ -1208,8 +1259,9 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     // iteration (attack_utils.py:77-84)
     se_forward(I, se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
     Tens gin = tens(se1.gin, T, C);
-    emit_speaker_bwd(I, SE, se1, gin);
-    update(I, gin);
+    GradParts gp;
+    emit_speaker_bwd(I, SE, se1, gin, &gp);
+    update(I, gin, gp);
   } else {
     const int T_src = a->T_src;
     if (T_src <= 0) fail(AVC_ERR_INVALID, "bad T_src");
@@ -1301,8 +1353,9 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
       emit_tail(I, t, B);
     }
     Tens gin = tens(se1.gin, T, C);
-    emit_speaker_bwd(I, SE, se1, gin);
-    update(I, gin);
+    GradParts gp;
+    emit_speaker_bwd(I, SE, se1, gin, &gp);
+    update(I, gin, gp);
   }
 
   // ---- finish: result, loss curve, last gradient -----------------------------------------------
@@ -1419,8 +1472,9 @@ std::unique_ptr<Plan> build_header(avc_handle* h, const avc_header_args* a, cuda
   // iteration, gradient half
   se_forward(I, se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
   Tens gin = tens(se1.gin, T, C);
-  emit_speaker_bwd(I, SE, se1, gin);
-  I.push(LK_UPDATE, 0, 8.0 * nel, [=](cudaStream_t s_) { launch_k(header_grad_kernel, gt, 256, 0, s_, (const float*)gin.p, gin.bs, gin.rs, (const float*)x, (const float*)hdr, gh, B, T, C); });
+  GradParts gparts;
+  emit_speaker_bwd(I, SE, se1, gin, &gparts);
+  I.push(LK_UPDATE, 0, 8.0 * nel, [=](cudaStream_t s_) { launch_k(header_grad_kernel, gt, 256, 0, s_, (const float*)gin.p, gin.bs, gin.rs, gparts.p[0], gparts.p[1], (const float*)x, (const float*)hdr, gh, B, T, C); });
   // iteration, apply half
   {
     HeaderApplyArgs u{};
