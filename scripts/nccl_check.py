@@ -1,0 +1,61 @@
+"""2-GPU check of the sharded paths over NCCL (run under torchrun, one rank per GPU):
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/nccl_check.py
+1. sharded_attack (emb, e2e): batch sliced over the ranks, global MSE normaliser, all_gather of the perturbed
+   utterances + all_reduce of the loss curves == the unsharded call on one GPU.
+2. sharded_header_optimize: per-iteration all_reduce of the 80*T header gradient == the unsharded optimisation."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from attack_vc_b200 import Engine  # noqa: E402
+from attack_vc_b200.distributed import global_inv_norm, sharded_attack, sharded_header_optimize  # noqa: E402
+from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    out = os.dup(1)
+    os.dup2(2, 1)                       # NCCL prints its banner on stdout
+    dist.init_process_group("nccl")
+    os.dup2(out, 1)
+    eng = Engine(ParamTree(SYNTH_CONFIG, seed=0).to("cuda"))
+    ok = True
+    for kind, B, T, n in (("emb", 7, 128, 6), ("e2e", 4, 128, 4)):
+        inp = {k: v.cuda() for k, v in make_inputs(kind, B, T, seed=17).items()}
+        T_out = T if kind != "e2e" else int(eng._lib.avc_decoder_frames(eng._h, T))
+        inv = global_inv_norm(kind, B, 128, 80, T_out)
+        adv, losses = sharded_attack(eng.attack, kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inv, vc_src=inp.get("vc_src"), w0=inp["w0"])
+        full, info = eng.attack(kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, vc_src=inp.get("vc_src"), w0=inp["w0"], want_loss=True)
+        err = float((adv - full).abs().max())
+        lerr = float(((losses - info["losses"]).abs() / info["losses"].abs()).max())
+        good = err < 5e-6 and lerr < 1e-4
+        ok &= good
+        if rank == 0:
+            print(f"sharded_attack {kind} B={B} over {world} GPUs: max |adv - unsharded| {err:.2e}, loss rel err {lerr:.2e} -> {'PASS' if good else 'FAIL'}")
+    B, T, n = 10, 100, 8
+    inp = make_inputs("emb", B, T, seed=23)
+    src, tgt = (inp["vc_tgt"] * 0.6).cuda(), (inp["adv_tgt"] * 0.6).cuda()
+    hdr, losses = sharded_header_optimize(eng, src, tgt, n, epsilon=0.004)
+    full, info = eng.header_optimize(src, tgt, n, epsilon=0.004, want_loss=True)
+    err = (hdr - full).abs()
+    lerr = float(((losses - info["losses"]).abs() / info["losses"].abs()).max())
+    good = float(err.median()) < 1e-6 and float((err > 1e-4).float().mean()) < 0.02 and lerr < 1e-3
+    ok &= good
+    same = [torch.empty_like(hdr) for _ in range(world)]
+    dist.all_gather(same, hdr.contiguous())
+    ident = all(torch.equal(same[0], s) for s in same)
+    ok &= ident
+    if rank == 0:
+        print(f"sharded_header_optimize B={B} over {world} GPUs: median |h - unsharded| {float(err.median()):.2e}, "
+              f"frac > 1e-4 {float((err > 1e-4).float().mean()):.4f}, loss rel err {lerr:.2e}, identical on all ranks {ident} -> {'PASS' if good and ident else 'FAIL'}")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
