@@ -361,20 +361,30 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
   // thread constants of the copy: 16-byte column chunk wn of K rows wk, wk + 32, ...
   const int wk = tid >> 3, wn = (tid & 7) << 2;
   const bool wok = (n0 + wn) < Ntot;
-  int is_g = g_lo, is_tap = 0, is_slot = 0;   // next slab to issue and the ring slot it goes to
+  // Issue state kept as running pointers: the kernel is instruction-issue bound, and 7 slabs x ~70 instructions of
+  // 64-bit index arithmetic per thread used to cost as much as the main loop.  Per slab now: two copies, three adds.
+  constexpr int kRows = NT / 8;                  // K rows covered per pass of the CTA
+  int is_g = g_lo, is_left = 0, is_slot = 0;     // group of the next slab, taps left in it, ring slot it goes to
+  int is_kc = 0;
+  const float* is_src = nullptr;                 // row wk of the next slab, this thread's 16-byte column
+  long long is_tap_step = 0, is_row_step = 0;
+  float* is_dst = Wr + wk * kSmTN + wn;
+  auto issue_group = [&]() {
+    const TapGroup& G = p.g[is_g];
+    is_left = G.n_taps; is_kc = G.kc;
+    is_src = wok ? G.W + (long long)wk * Ntot + n0 + wn : G.W;
+    is_tap_step = wok ? (long long)G.wts * Ntot : 0;
+    is_row_step = wok ? (long long)kRows * Ntot : 0;
+  };
+  if (n_slabs > 0) issue_group();
   auto issue = [&](int q) {
     if (q < n_slabs) {
-      const TapGroup& G = p.g[is_g];
-      const float* src = wok ? G.W + ((long long)is_tap * G.wts + wk) * Ntot + n0 + wn : G.W;
-      float* dst = Wr + (size_t)is_slot * p.slab_floats + wk * kSmTN + wn;
-      constexpr int kRows = NT / 8;          // K rows covered per pass of the CTA
-      const long long sstep = wok ? (long long)kRows * Ntot : 0;
-      for (int k = wk; k < G.kc; k += kRows) {
-        cp_async16(dst, src, wok);
-        src += sstep; dst += kRows * kSmTN;
-      }
-      if (++is_tap == G.n_taps) { is_tap = 0; ++is_g; }
-      if (++is_slot == p.ring) is_slot = 0;
+      if (wk < is_kc) cp_async16(is_dst, is_src, wok);
+      if (wk + kRows < is_kc) cp_async16(is_dst + kRows * kSmTN, is_src + is_row_step, wok);
+      is_src += is_tap_step;
+      is_dst += p.slab_floats;
+      if (++is_slot == p.ring) { is_slot = 0; is_dst -= (size_t)p.ring * p.slab_floats; }
+      if (--is_left == 0 && ++is_g < g_hi) issue_group();
     }
     cp_async_commit();
   };
@@ -614,6 +624,11 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
   int c_slot = 0;                          // ring slot of the slab being consumed
   const float* Sg = S;
   int kc = 0;
+  const int k_lo = warp * kSmKW;
+  // running pointers (the loop is instruction-issue bound): operand rows of this thread at the current tap, and the
+  // weight rows of this warp's K slice in the current ring slot
+  const float* ap[RM];
+  const float* wp = Wr + k_lo * kSmTN + tx * 4;
   for (int q = 0; q < n_slabs; ++q) {
     if (cnt == 0) {   // first slab of the next group: per-thread window rows
       ++cg; ctap = 0;
@@ -636,6 +651,7 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
         rb[i][2] = rt ? 2 * (p.T_y - 1) - t + G.off0 - wg.wlo : zrel;
         if (pre && lt) rb[i][0] = p.e_off[cg] - wbase + (t - wg.lt_lo) * G.n_taps;
         if (pre && rt) rb[i][0] = p.e_off[cg] - wbase + (nl + t - wg.rt_lo) * G.n_taps;
+        ap[i] = Sg + rb[i][0] * kSRow + k_lo;
       }
     }
     if (!all_resident) {
@@ -647,18 +663,14 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
       cp_async_wait<0>();                // every slab was requested before the dependency wait: one barrier for the whole loop
       __syncthreads();
     }
-    const float* Wsub = Wr + (size_t)c_slot * p.slab_floats;
-    if (++c_slot == p.ring) c_slot = 0;
-    const int k_lo = warp * kSmKW;
     if (k_lo < kc) {     // kc is a multiple of kSmKW: a warp has all of its K rows or none
-      // all shared-memory loads of the slab are issued before the first FMA: with few warps per
-      // scheduler the loop is bound by load latency, not by bandwidth
+      // all shared-memory loads of the slab are issued before the first FMA
       float4 a[kSmKW / 4][RM], w[kSmKW];
 #pragma unroll
       for (int j = 0; j < kSmKW / 4; ++j) {
 #pragma unroll
         for (int i = 0; i < RM; ++i) {
-          a[j][i] = ld4(Sg + (rb[i][0] + ctap) * kSRow + k_lo + 4 * j);
+          a[j][i] = ld4(ap[i] + 4 * j);
           if (edge) {
             a[j][i] = f4add(a[j][i], ld4(Sg + (rb[i][1] + ctap) * kSRow + k_lo + 4 * j));
             a[j][i] = f4add(a[j][i], ld4(Sg + (rb[i][2] + ctap) * kSRow + k_lo + 4 * j));
@@ -666,7 +678,7 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
         }
       }
 #pragma unroll
-      for (int k = 0; k < kSmKW; ++k) w[k] = ld4(Wsub + (k_lo + k) * kSmTN + tx * 4);
+      for (int k = 0; k < kSmKW; ++k) w[k] = ld4(wp + k * kSmTN);
 #pragma unroll
       for (int k = 0; k < kSmKW; ++k) {
 #pragma unroll
@@ -680,6 +692,10 @@ __global__ void __launch_bounds__(32 * kSmWarps, AVC_SMALL_MINB) conv_small_kern
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < RM; ++i) ap[i] += kSRow;
+    wp += p.slab_floats;
+    if (++c_slot == p.ring) { c_slot = 0; wp -= (size_t)p.ring * p.slab_floats; }
     ++ctap; --cnt;
   }
   cp_async_wait<0>();
