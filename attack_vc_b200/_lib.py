@@ -4,8 +4,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libavc_b200.so"
+# AVC_LIB selects another build of the same library (instrumented / experimental builds made by scripts/); never a fallback
+LIB_PATH = Path(os.environ["AVC_LIB"]).resolve() if os.environ.get("AVC_LIB") else _HERE / "libavc_b200.so"
 
 AVC_MAX_BLOCKS = 8
 

@@ -151,19 +151,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU box.
+// Bounded wait: a protocol bug must trap, not hang the GPU box (2^28 failed try_waits, each of which
+// suspends the thread for a while, is seconds; a kernel runs for well under a millisecond).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
-    if ((spin & 1023u) == 1023u) {          // the clock is only consulted now and then: try_wait itself suspends the thread
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 20000000000LL) __trap();
-    }
+    if (spin == (1u << 28)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -240,53 +236,135 @@ struct TcWalk {
 
 constexpr int kTcScrPitch = 36;    // floats per row of a drain warp's transpose slab (32 + 4: conflict-free float4 rows)
 
-// Columns [C0, C0+SW) of the 32 rows a drain warp owns: registers -> slab (row per lane) -> global
-// (SW/4 lanes per row, so a warp instruction covers 32/(SW/4) rows with contiguous SW*4-byte segments).
+// ---- epilogue ------------------------------------------------------------------------------------
+// Each drain lane owns one accumulator ROW; rows are 512 B apart in memory, so the tile is transposed
+// through a per-warp shared-memory slab and written with lanes along the channel axis.  Everything that
+// depends on the row (utterance, output row, which rows of the skip tensor it reads, their weight) is
+// worked out ONCE by the lane that owns the row and handed to the storing lanes with shuffles, and the
+// row loop is a real loop: the whole kernel has to stay a few tens of KB of code (the first version
+// unrolled 16 row groups x 5 skip modes per tile, 370 KB of SASS, and the drain warps spent 10-20k clk
+// per tile fetching instructions).
+struct TcRow {
+  int kind;      // 0 dead, 1 main row, 2 dgrad halo row
+  int b, o;      // utterance, output row (kind 2: row of the side buffer)
+  int t0, t1;    // rows of the skip tensor (t1 < 0: one row only)
+  float rs;      // skip value = (R[t0] + R[t1]) * rs
+};
+
+__device__ __forceinline__ TcRow tc_row_info(const TcArgs& p, const TcPass& ps, long long u) {
+  TcRow r;
+  r.b = (int)(u / p.Pv);
+  r.o = ps.so * (int)(u - (long long)r.b * p.Pv) + ps.oo;
+  r.kind = 0; r.t0 = 0; r.t1 = -1; r.rs = 1.f;
+  if (r.b < p.B && !(p.dbg & 8)) {
+    if (r.o >= 0 && r.o < p.T_y) r.kind = 1;
+    else if (p.side && ((r.o < 0 && r.o >= -p.halo_l) || (r.o >= p.T_y && r.o < p.T_y + p.halo_r))) {
+      r.kind = 2;
+      r.o = r.o < 0 ? r.o + p.halo_l : p.halo_l + (r.o - p.T_y);
+    }
+  }
+  if (r.kind == 1) {
+    const int rf = p.res.rf, t = r.o;
+    switch (p.res.mode) {   // res_load4 (common.cuh) with the loads separated from the index arithmetic; rf <= 2 (tc_supported)
+      case RES_SAME: r.t0 = t; break;
+      case RES_POOL: { const int lo = t * rf, n = min(rf, p.res.T_r - lo); r.t0 = lo; r.t1 = n > 1 ? lo + 1 : -1; r.rs = 1.f / (float)n; break; }
+      case RES_POOL_BWD: { const int q = rf > 1 ? t >> 1 : t; r.t0 = q; r.rs = 1.f / (float)min(rf, p.T_y - q * rf); break; }
+      case RES_UP: r.t0 = rf > 1 ? t >> 1 : t; break;
+      case RES_UP_BWD: r.t0 = t * rf; r.t1 = rf > 1 ? t * rf + 1 : -1; break;
+      default: break;
+    }
+  }
+  return r;
+}
+
+#ifndef AVC_TC_EPI_BATCH
+#define AVC_TC_EPI_BATCH 4
+#endif
+// Columns [chb, chb+SW) of the 32 rows a drain warp owns, slab -> global.  SW/4 lanes per row, so a warp
+// instruction covers 32/(SW/4) rows with contiguous SW*4-byte segments.  Rows go in batches of NB: all the
+// global loads of a batch (act' mask, skip rows) are in flight before the first one is consumed.
+template <int SW>
+__device__ __forceinline__ void tc_slab_to_global(const TcArgs& p, const float* scratch, int lane, const TcRow& own, int chb) {
+  constexpr int LPR = SW / 4, RPI = 32 / LPR, ITS = 32 / RPI;
+  constexpr int NB = ITS < AVC_TC_EPI_BATCH ? ITS : AVC_TC_EPI_BATCH;
+  const int c4 = lane % LPR, ch = chb + 4 * c4, rsub = lane / LPR;
+  const float4 bias = p.bias ? ld4(p.bias + ch) : f4zero();
+  const bool has_res = p.res.mode != RES_NONE;
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITS; it0 += NB) {
+    int kq[NB], bq[NB], oq[NB];
+    float4 om[NB], ra[NB], rb[NB];
+    float rsc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = (it0 + j) * RPI + rsub;
+      kq[j] = __shfl_sync(0xffffffffu, own.kind, r);
+      bq[j] = __shfl_sync(0xffffffffu, own.b, r);
+      oq[j] = __shfl_sync(0xffffffffu, own.o, r);
+      om[j] = f4zero(); ra[j] = f4zero(); rb[j] = f4zero(); rsc[j] = 1.f;
+      if (p.Om && kq[j] == 1) om[j] = ld4(p.Om + (long long)bq[j] * p.om_bs + (long long)oq[j] * p.om_rs + ch);
+      if (has_res) {
+        const int t0 = __shfl_sync(0xffffffffu, own.t0, r), t1 = __shfl_sync(0xffffffffu, own.t1, r);
+        rsc[j] = __shfl_sync(0xffffffffu, own.rs, r);
+        if (kq[j] == 1) {
+          const float* rbase = p.res.R + (long long)bq[j] * p.res.bs + ch;
+          ra[j] = ld4(rbase + (long long)t0 * p.res.rs);
+          if (t1 >= 0) rb[j] = ld4(rbase + (long long)t1 * p.res.rs);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (kq[j] == 0) continue;
+      const int r = (it0 + j) * RPI + rsub;
+      float4 x = ld4(scratch + r * kTcScrPitch + 4 * c4);
+      if (kq[j] == 1) {
+        if (p.bias) x = f4add(x, bias);
+        if (p.Om) x = dact4mul(x, om[j], p.slope);
+        if (p.act) x = act4(x, p.slope);
+        if (p.Y2) st4(p.Y2 + (long long)bq[j] * p.y2_bs + (long long)oq[j] * p.y2_rs + ch, x);
+        if (has_res) x = f4add(x, f4scale(f4add(ra[j], rb[j]), rsc[j]));
+        st4(p.Y + (long long)bq[j] * p.y_bs + (long long)oq[j] * p.y_rs + ch, x);
+      } else {
+        st4(p.side + ((long long)bq[j] * (p.halo_l + p.halo_r) + oq[j]) * p.side_n + ch, x);
+      }
+    }
+  }
+}
+
+// registers -> slab: lane's row, columns [C0, C0+SW)
 template <int NH, int C0, int SW>
-__device__ __forceinline__ void tc_store_slab(const TcArgs& p, const float (&acc)[NH], float* scratch, int lane,
-                                              int b_own, int o_own, int kind_own, int chb) {
-  constexpr int LPR = SW / 4, RPI = 32 / LPR;
+__device__ __forceinline__ void tc_acc_to_slab(const float (&acc)[NH], float* scratch, int lane) {
 #pragma unroll
   for (int q = 0; q < SW / 4; ++q)
     st4(scratch + lane * kTcScrPitch + 4 * q, make_float4(acc[C0 + 4 * q], acc[C0 + 4 * q + 1], acc[C0 + 4 * q + 2], acc[C0 + 4 * q + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 32 / RPI; ++it) {
-    const int r = it * RPI + lane / LPR, c4 = lane % LPR;
-    const int b = __shfl_sync(0xffffffffu, b_own, r), o = __shfl_sync(0xffffffffu, o_own, r);
-    const int kind = __shfl_sync(0xffffffffu, kind_own, r);
-    if (kind == 0) continue;
-    float4 x = ld4(scratch + r * kTcScrPitch + 4 * c4);
-    const int ch = chb + C0 + 4 * c4;
-    if (kind == 1) {
-      if (p.bias) x = f4add(x, ld4(p.bias + ch));
-      if (p.Om) x = dact4mul(x, ld4(p.Om + (long long)b * p.om_bs + (long long)o * p.om_rs + ch), p.slope);
-      if (p.act) x = act4(x, p.slope);
-      if (p.Y2) st4(p.Y2 + (long long)b * p.y2_bs + (long long)o * p.y2_rs + ch, x);
-      if (p.res.mode != RES_NONE) x = f4add(x, res_load4(p.res, b, o, p.T_y, ch));
-      st4(p.Y + (long long)b * p.y_bs + (long long)o * p.y_rs + ch, x);
-    } else {
-      const int hrow = o < 0 ? o + p.halo_l : p.halo_l + (o - p.T_y);
-      st4(p.side + ((long long)b * (p.halo_l + p.halo_r) + hrow) * p.side_n + ch, x);
-    }
-  }
-  __syncwarp();
 }
 
+struct TcDrainProf { long long wait, ld, epi; };
+#ifdef AVC_TC_PROFILE
+#define TCD(x) x
+#else
+#define TCD(x)
+#endif
 template <int NH>   // columns per drain thread (half of the pass width): 64 or 40
 __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
-                                                   uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch) {
+                                                   uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch,
+                                                   TcDrainProf& dp) {
+  TCD(long long dq;)
   const int quad = warp & 3;                    // TMEM lanes this warp may read: [32*quad, 32*quad+32)
   const int half = (warp - 6) >> 2;             // which half of the columns
   float acc[NH];
 #pragma unroll
   for (int i = 0; i < NH; ++i) acc[i] = 0.f;
+  const TcRow own = tc_row_info(p, ps, v0 + quad * 32 + lane);   // worked out while the first chunk's MMAs run
   TcWalk w(p, ps);
   bool done = false, kb_end;
   while (!done) {
     if (!w.next(p, ps, kb_end, done)) continue;
     const int buf = chunk % kTcAccBufs;
+    TCD(dq = clock64();)
     mbar_wait(acc_full0 + 8 * buf, (chunk / kTcAccBufs) & 1);
+    TCD(dp.wait += clock64() - dq; dq = clock64();)
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kTcNMax + half * NH);
     if (!(p.dbg & 16)) {
@@ -312,23 +390,24 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+    TCD(dp.ld += clock64() - dq;)
     ++chunk;
   }
+  TCD(dq = clock64();)
   // ---- epilogue: bias / mask / act / residual -> global (overlaps the next tile's MMAs) ----
-  // Each lane owns one accumulator ROW; rows are 512 B apart in memory, so the tile is transposed
-  // through a per-warp shared-memory slab and written with lanes along the channel axis.
-  const int row = quad * 32 + lane;
-  const long long u = v0 + row;
-  const int b_own = (int)(u / p.Pv);
-  const int o_own = ps.so * (int)(u - (long long)b_own * p.Pv) + ps.oo;   // output index inside the utterance
-  int kind_own = 0;                                                        // 0 dead, 1 main row, 2 dgrad halo row
-  if (b_own < p.B && !(p.dbg & 8)) {
-    if (o_own >= 0 && o_own < p.T_y) kind_own = 1;
-    else if (p.side && ((o_own < 0 && o_own >= -p.halo_l) || (o_own >= p.T_y && o_own < p.T_y + p.halo_r))) kind_own = 2;
-  }
   const int chb = ps.ch_off + half * NH;
-  tc_store_slab<NH, 0, (NH >= 32 ? 32 : 8)>(p, acc, scratch, lane, b_own, o_own, kind_own, chb);
-  if (NH > 32) tc_store_slab<NH, 32, (NH - 32 >= 32 ? 32 : 8)>(p, acc, scratch, lane, b_own, o_own, kind_own, chb);
+  constexpr int SW0 = NH >= 32 ? 32 : 8, SW1 = NH - 32 >= 32 ? 32 : 8;
+  tc_acc_to_slab<NH, 0, SW0>(acc, scratch, lane);
+  __syncwarp();
+  tc_slab_to_global<SW0>(p, scratch, lane, own, chb);
+  if (NH > 32) {
+    __syncwarp();
+    tc_acc_to_slab<NH, 32, SW1>(acc, scratch, lane);
+    __syncwarp();
+    tc_slab_to_global<SW1>(p, scratch, lane, own, chb + 32);
+  }
+  __syncwarp();
+  TCD(dp.epi += clock64() - dq;)
 }
 
 // Persistent: gridDim.x CTAs (one per SM) walk the work items (M tile, pass) round-robin; barrier phases,
@@ -494,10 +573,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
     const int er = tl >> 3, ec = tl & 7;   // my share of the extra rows: row 128 + er, chunk ec
     int sa = 0; uint32_t pa = 0;
     const bool skip = (p.dbg & 2) != 0;
+#ifdef AVC_TC_PROFILE
+    long long l_setup = 0, l_wait = 0, l_store = 0, l_fetch = 0, l_t0 = clock64(), lq;
+#define TCL(x) x
+#else
+#define TCL(x)
+#endif
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const TcPass& ps = p.pass[wk % p.n_pass];
       const long long v0 = (long long)(wk / p.n_pass) * kTcM;
       for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
+        TCL(lq = clock64();)
         const TcGroup& G = p.g[gi];
         const float* src[2]; const float* msk[2];
 #pragma unroll
@@ -534,9 +620,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
           }
         };
         fetch(0);
+        TCL(l_setup += clock64() - lq;)
         for (int kb = 0; kb < nkb; ++kb) {
           const int kbs = min(kTcKB, G.kc - kb * kTcKB);
+          TCL(lq = clock64();)
           mbar_wait(a_empty(sa), pa ^ 1);
+          TCL(l_wait += clock64() - lq; lq = clock64();)
           float* hi = As + (size_t)sa * 2 * kTcAPlane;
           float* lo = hi + kTcAPlane;
           if (p.Mk) {
@@ -559,22 +648,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full(sa));
+          TCL(l_store += clock64() - lq; lq = clock64();)
           if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
           if (kb + 1 < nkb) fetch(kb + 1);
+          TCL(l_fetch += clock64() - lq;)
         }
       }
     }
+#ifdef AVC_TC_PROFILE
+    if ((p.dbg & 32) && blockIdx.x == 0 && tl == 0)
+      printf("[conv_tc cta0] loader: total %lld clk, setup %lld, wait a_empty %lld, split+store %lld, fetch issue %lld\n",
+             clock64() - l_t0, l_setup, l_wait, l_store, l_fetch);
+#endif
+#undef TCL
   } else {
     // ===== drain warps (256 threads): chunk sums in registers, then the epilogue =====
     pdl_wait();
     int chunk = 0;
+    TcDrainProf dp{0, 0, 0};
+    TCD(const long long d_t0 = clock64();)
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const TcPass& ps = p.pass[wk % p.n_pass];
       const long long v0 = (long long)(wk / p.n_pass) * kTcM;
       float* scratch = scr_all + (size_t)(warp - 6) * 32 * kTcScrPitch;
-      if (ps.N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch);
-      else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch);
+      if (ps.N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
+      else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
     }
+#ifdef AVC_TC_PROFILE
+    if ((p.dbg & 32) && blockIdx.x == 0 && warp == 6 && lane == 0)
+      printf("[conv_tc cta0] drain: total %lld clk, wait acc_full %lld, tmem ld+add %lld, epilogue %lld (chunks %d)\n",
+             clock64() - d_t0, dp.wait, dp.ld, dp.epi, chunk);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -638,6 +742,7 @@ struct TcOp {
 inline bool tc_supported(const ConvArgs& a, const TcOp& op) {
   if (op.n_pass <= 0 || op.n_groups <= 0) return false;
   if (a.Y2 && a.bwd) return false;
+  if (a.res.mode != RES_NONE && (a.res.rf < 1 || a.res.rf > 2)) return false;   // the epilogue reads at most two skip rows per output row
   for (int g = 0; g < op.n_groups; ++g)
     if (!op.g[g].Wp || op.g[g].kc % 8 || op.g[g].a_ch_off % 4 || op.g[g].n_taps < 1 || op.g[g].n_taps > kMaxTaps) return false;
   for (int q = 0; q < op.n_pass; ++q)
