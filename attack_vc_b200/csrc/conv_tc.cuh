@@ -46,10 +46,14 @@ constexpr int kTcBStages = 3;
 constexpr int kTcNMax = 128;       // columns of one pass
 constexpr int kTcThreads = 448;    // warp 0: TMEM + weight producer, 1: MMA issuer, 2-5: loaders, 6-13: drain + epilogue
 constexpr int kTcAPlane = (kTcKB / 4) * kTcRows * 4;   // floats of one hi (or lo) plane of an A stage
-constexpr int kTcChunkSteps = 8;   // default MMA k-steps accumulated in TMEM before the drain warps take over
+constexpr int kTcChunkSteps = 12;  // default MMA k-steps (2 MMAs each) accumulated in TMEM before the drain warps take over: 24 accumulate operations, see DESIGN.md
 constexpr int kTcAccBufs = 4;      // accumulator ring in TMEM (4 x 128 columns = all 512): hides the drain hand-off latency
 constexpr int kTcMaxChunks = 12;   // N chunks of one packed conv (1104 = 8 x 128 + 80)
 constexpr int kTcMaxPass = 12;
+#ifndef AVC_TC_PF_DIST
+#define AVC_TC_PF_DIST 3
+#endif
+constexpr int kTcPfDist = AVC_TC_PF_DIST;   // K blocks of window rows prefetched into L2 ahead of the loaders' register fetch
 
 struct TcPack {                    // weights of ONE conv direction / tap subset, device memory
   bool ok = false;
@@ -68,6 +72,18 @@ struct TcPass {
   int g_begin, g_end;              // groups accumulated by this pass
   int N, ch_off;                   // columns of this pass and where they go in the output row
   int so, oo;                      // output index of virtual row u:  so*u + oo
+  int s_begin, s_end;              // its weight stages in TcArgs::st (tc_build_stages)
+  int n_chunks;                    // accumulator hand-offs to the drain warps
+};
+
+// One weight stage = one (K block, tap) of one group.  The table is worked out on the host and travels in the
+// kernel parameters (constant bank: the producer and the MMA issuer read it with uniform loads), so no role
+// re-derives the (group, K block, tap, chunk) walk on the device.
+constexpr int kTcMaxStages = 192;
+enum : unsigned { kTcKbFirst = 1, kTcKbLast = 2, kTcChunkFirst = 4, kTcChunkLast = 8 };
+struct TcStage {
+  uint32_t w_off;                  // float offset of its hi|lo weight block from the group's Wp
+  uint8_t gi, tap, nks, flags;     // group, window shift (rows), MMA k-steps, kTc* flags
 };
 
 struct TcArgs {
@@ -91,6 +107,7 @@ struct TcArgs {
   int dbg;               // bottleneck probes (results are garbage): 1 no weight copies, 2 no window gather, 4 no MMA
   TcPass pass[kTcMaxPass];
   TcGroup g[kTcMaxPass];
+  TcStage st[kTcMaxStages];
 };
 
 // ---- host: weight packing ----------------------------------------------------------------------
@@ -101,6 +118,13 @@ inline float tf32_hi_host(float v) {
   float r;
   memcpy(&r, &u, 4);
   return r;
+}
+
+inline uint16_t bf16_rn_host(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);   // round to nearest even on the top 16 bits (finite inputs)
+  return (uint16_t)(u >> 16);
 }
 
 // img: [k_img][kc][n] (n contiguous) -- the forward or dgrad image pack_conv builds for the CUDA-core
@@ -119,18 +143,27 @@ inline void tc_pack_taps(Arena& mem, TcPack& p, const std::vector<float>& img, i
   for (int ch = 0; ch < nch; ++ch) {
     const int n0 = ch * kTcNMax, cn = std::min(kTcNMax, n - n0);
     std::vector<float> out((size_t)2 * k * kc * cn);
+    uint16_t* out16 = reinterpret_cast<uint16_t*>(out.data());
     size_t o = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int kb0 = kb * kTcKB, kbs = std::min(kTcKB, kc - kb0);
-      for (int t = 0; t < k; ++t)
-        for (int plane = 0; plane < 2; ++plane)
-          for (int c = 0; c < kbs / 4; ++c)
+      for (int t = 0; t < k; ++t) {
+        // plane 0: TF32 hi parts, [k/4][n][4 floats]
+        for (int c = 0; c < kbs / 4; ++c)
+          for (int nn = 0; nn < cn; ++nn)
+            for (int e = 0; e < 4; ++e)
+              out[o++] = tf32_hi_host(img[((size_t)taps[t] * kc + kb0 + 4 * c + e) * n + n0 + nn]);
+        // plane 1: per MMA k-step of 8 channels two 16-byte K chunks per column: bf16(hi[0..8)), bf16(lo[0..8))
+        for (int ks = 0; ks < kbs / 8; ++ks)
+          for (int j = 0; j < 2; ++j)
             for (int nn = 0; nn < cn; ++nn)
-              for (int e = 0; e < 4; ++e) {
-                const float v = img[((size_t)taps[t] * kc + kb0 + 4 * c + e) * n + n0 + nn];
+              for (int e = 0; e < 8; ++e) {
+                const float v = img[((size_t)taps[t] * kc + kb0 + 8 * ks + e) * n + n0 + nn];
                 const float hi = tf32_hi_host(v);
-                out[o++] = plane == 0 ? hi : tf32_hi_host(v - hi);   // lo pre-rounded (RN): the MMA would truncate it
+                out16[2 * o + ((size_t)(2 * ks + j) * cn + nn) * 8 + e] = bf16_rn_host(j == 0 ? hi : v - hi);
               }
+        o += (size_t)kbs * cn;
+      }
     }
     p.blocks[ch] = mem.upload(out);
     p.cn[ch] = cn;
@@ -166,6 +199,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// bring one 128-byte line into L2 ahead of use (no register, no dependency): the gathers and the epilogue operands
+// stream from HBM, and one K block / one row batch in flight per SM is far too little to cover its latency
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -185,6 +221,12 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {   // always accumulates
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 // K-major, no swizzle ("interleaved") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14), LBO>>4 [16,30) = bytes between the two 16-byte K chunks of one MMA,
 // SBO>>4 [32,46) = bytes between consecutive 8-row core matrices, version 1 at [46,48), layout 0.
@@ -194,6 +236,18 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 }
 __device__ __forceinline__ float tf32_hi(float v) {
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ uint32_t bf16x2(float lo, float hi) {   // lo -> bits [0,16), hi -> bits [16,32), round to nearest even
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_bf16x8(float* dst, float4 a, float4 b) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(bf16x2(a.x, a.y), bf16x2(a.z, a.w), bf16x2(b.x, b.y), bf16x2(b.z, b.w));
+}
+__device__ __forceinline__ void st_bf16x4(float* dst, float4 a) {
+  *reinterpret_cast<uint2*>(dst) = make_uint2(bf16x2(a.x, a.y), bf16x2(a.z, a.w));
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -209,30 +263,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-
-// Weight stages are visited in (group, K block, tap) order by all roles; a chunk closes after the tap
-// that brings it to chunk_steps MMA k-steps, and after the last tap of the pass.
-struct TcWalk {
-  int gi, kb, tap, nkb, steps;
-  __device__ TcWalk(const TcArgs& p, const TcPass& ps) : gi(ps.g_begin), kb(0), tap(0), steps(0) { nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB; }
-  // advance past the current tap; kb_end: it was the last tap of its K block, done: of the pass;
-  // returns true when the chunk it belongs to is complete
-  __device__ bool next(const TcArgs& p, const TcPass& ps, bool& kb_end, bool& done) {
-    const TcGroup& G = p.g[gi];
-    steps += min(kTcKB, G.kc - kb * kTcKB) / 8;
-    kb_end = false; done = false;
-    if (++tap == G.n_taps) {
-      tap = 0; kb_end = true;
-      if (++kb == nkb) {
-        kb = 0;
-        if (++gi < ps.g_end) nkb = (p.g[gi].kc + kTcKB - 1) / kTcKB;
-        else done = true;
-      }
-    }
-    if (done || steps >= p.chunk_steps) { steps = 0; return true; }
-    return false;
-  }
-};
 
 constexpr int kTcScrPitch = 36;    // floats per row of a drain warp's transpose slab (32 + 4: conflict-free float4 rows)
 
@@ -283,12 +313,13 @@ __device__ __forceinline__ TcRow tc_row_info(const TcArgs& p, const TcPass& ps, 
 // Columns [chb, chb+SW) of the 32 rows a drain warp owns, slab -> global.  SW/4 lanes per row, so a warp
 // instruction covers 32/(SW/4) rows with contiguous SW*4-byte segments.  Rows go in batches of NB: all the
 // global loads of a batch (act' mask, skip rows) are in flight before the first one is consumed.
-template <int SW>
-__device__ __forceinline__ void tc_slab_to_global(const TcArgs& p, const float* scratch, int lane, const TcRow& own, int chb) {
-  constexpr int LPR = SW / 4, RPI = 32 / LPR, ITS = 32 / RPI;
+// ncol: valid columns of the slab (a pass of N = 80 fills 64 + 16 of the two 64-column halves).
+__device__ __forceinline__ void tc_slab_to_global(const TcArgs& p, const float* scratch, int lane, const TcRow& own, int chb, int ncol) {
+  constexpr int SW = 32, LPR = SW / 4, RPI = 32 / LPR, ITS = 32 / RPI;
   constexpr int NB = ITS < AVC_TC_EPI_BATCH ? ITS : AVC_TC_EPI_BATCH;
   const int c4 = lane % LPR, ch = chb + 4 * c4, rsub = lane / LPR;
-  const float4 bias = p.bias ? ld4(p.bias + ch) : f4zero();
+  const bool col_ok = 4 * c4 < ncol;
+  const float4 bias = (p.bias && col_ok) ? ld4(p.bias + ch) : f4zero();
   const bool has_res = p.res.mode != RES_NONE;
 #pragma unroll 1
   for (int it0 = 0; it0 < ITS; it0 += NB) {
@@ -299,6 +330,7 @@ __device__ __forceinline__ void tc_slab_to_global(const TcArgs& p, const float* 
     for (int j = 0; j < NB; ++j) {
       const int r = (it0 + j) * RPI + rsub;
       kq[j] = __shfl_sync(0xffffffffu, own.kind, r);
+      if (!col_ok) kq[j] = 0;
       bq[j] = __shfl_sync(0xffffffffu, own.b, r);
       oq[j] = __shfl_sync(0xffffffffu, own.o, r);
       om[j] = f4zero(); ra[j] = f4zero(); rb[j] = f4zero(); rsc[j] = 1.f;
@@ -332,11 +364,11 @@ __device__ __forceinline__ void tc_slab_to_global(const TcArgs& p, const float* 
   }
 }
 
-// registers -> slab: lane's row, columns [C0, C0+SW)
-template <int NH, int C0, int SW>
+// registers -> slab: lane's row, columns [C0, C0+32)
+template <int NH, int C0>
 __device__ __forceinline__ void tc_acc_to_slab(const float (&acc)[NH], float* scratch, int lane) {
 #pragma unroll
-  for (int q = 0; q < SW / 4; ++q)
+  for (int q = 0; q < 8; ++q)
     st4(scratch + lane * kTcScrPitch + 4 * q, make_float4(acc[C0 + 4 * q], acc[C0 + 4 * q + 1], acc[C0 + 4 * q + 2], acc[C0 + 4 * q + 3]));
 }
 
@@ -346,21 +378,33 @@ struct TcDrainProf { long long wait, ld, epi; };
 #else
 #define TCD(x)
 #endif
-template <int NH>   // columns per drain thread (half of the pass width): 64 or 40
+constexpr int kTcNH = 64;   // accumulator columns per drain thread (half of a 128-column pass; N = 80: 64 + 16)
 __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
                                                    uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch,
                                                    TcDrainProf& dp) {
   TCD(long long dq;)
+  constexpr int NH = kTcNH;
   const int quad = warp & 3;                    // TMEM lanes this warp may read: [32*quad, 32*quad+32)
   const int half = (warp - 6) >> 2;             // which half of the columns
+  const int ncol = min(NH, ps.N - half * NH);   // valid columns of this half
   float acc[NH];
 #pragma unroll
   for (int i = 0; i < NH; ++i) acc[i] = 0.f;
   const TcRow own = tc_row_info(p, ps, v0 + quad * 32 + lane);   // worked out while the first chunk's MMAs run
-  TcWalk w(p, ps);
-  bool done = false, kb_end;
-  while (!done) {
-    if (!w.next(p, ps, kb_end, done)) continue;
+  if (own.kind == 1 && kTcPfDist > 0) {   // the epilogue's operands for this lane's row: into L2 now, read ~20k clk later
+    const int c0 = ps.ch_off + half * NH;
+    if (p.Om) {
+      const float* q = p.Om + (long long)own.b * p.om_bs + (long long)own.o * p.om_rs + c0;
+      prefetch_l2(q); if (ncol > 32) prefetch_l2(q + 32);
+    }
+    if (p.res.mode != RES_NONE) {
+      const float* q = p.res.R + (long long)own.b * p.res.bs + c0;
+      prefetch_l2(q + (long long)own.t0 * p.res.rs); if (ncol > 32) prefetch_l2(q + (long long)own.t0 * p.res.rs + 32);
+      if (own.t1 >= 0) { prefetch_l2(q + (long long)own.t1 * p.res.rs); if (ncol > 32) prefetch_l2(q + (long long)own.t1 * p.res.rs + 32); }
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < ps.n_chunks; ++c) {
     const int buf = chunk % kTcAccBufs;
     TCD(dq = clock64();)
     mbar_wait(acc_full0 + 8 * buf, (chunk / kTcAccBufs) & 1);
@@ -368,23 +412,17 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kTcNMax + half * NH);
     if (!(p.dbg & 16)) {
-      // loads are issued in batches of 32 (or 40) columns before one wait: the TMEM read latency is paid per batch
+      // loads are issued in batches of 32 columns before one wait: the TMEM read latency is paid per batch
 #pragma unroll
-      for (int c0 = 0; c0 + 32 <= NH; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(t0 + c0, r0);
-        tmem_ld16(t0 + c0 + 16, r1);
-        if (NH - c0 - 32 == 8) {           // NH = 40: the 8-column tail rides along
-          uint32_t r2[8];
-          tmem_ld8(t0 + c0 + 32, r2);
+      for (int c0 = 0; c0 < NH; c0 += 32) {
+        if (c0 < ncol) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(t0 + c0, r0);
+          tmem_ld16(t0 + c0 + 16, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[c0 + 32 + i] += __uint_as_float(r2[i]);
-        } else {
-          tmem_ld_wait();
+          for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(r0[i]); acc[c0 + 16 + i] += __uint_as_float(r1[i]); }   // round-to-nearest fp32 adds
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(r0[i]); acc[c0 + 16 + i] += __uint_as_float(r1[i]); }   // round-to-nearest fp32 adds
       }
     }
     tc_fence_before();
@@ -396,15 +434,14 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
   TCD(dq = clock64();)
   // ---- epilogue: bias / mask / act / residual -> global (overlaps the next tile's MMAs) ----
   const int chb = ps.ch_off + half * NH;
-  constexpr int SW0 = NH >= 32 ? 32 : 8, SW1 = NH - 32 >= 32 ? 32 : 8;
-  tc_acc_to_slab<NH, 0, SW0>(acc, scratch, lane);
+  tc_acc_to_slab<NH, 0>(acc, scratch, lane);
   __syncwarp();
-  tc_slab_to_global<SW0>(p, scratch, lane, own, chb);
-  if (NH > 32) {
+  tc_slab_to_global(p, scratch, lane, own, chb, ncol);
+  if (ncol > 32) {
     __syncwarp();
-    tc_acc_to_slab<NH, 32, SW1>(acc, scratch, lane);
+    tc_acc_to_slab<NH, 32>(acc, scratch, lane);
     __syncwarp();
-    tc_slab_to_global<SW1>(p, scratch, lane, own, chb + 32);
+    tc_slab_to_global(p, scratch, lane, own, chb + 32, ncol - 32);
   }
   __syncwarp();
   TCD(dp.epi += clock64() - dq;)
@@ -451,34 +488,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   const int n_work = n_mt * p.n_pass;              // item w: M tile w / n_pass, pass w % n_pass (passes of a tile share A in L2)
 
   if (warp == 0) {
-    // ===== weight producer: one elected lane streams (K block, tap) stages with the TMA engine =====
+    // ===== weight producer: one elected lane streams the stages of the table with the TMA engine =====
     if (lane == 0) {
       int sb = 0; uint32_t pb = 0;
       for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
         const TcPass& ps = p.pass[wk % p.n_pass];
-        const int N = ps.N;
-        for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
-          const TcGroup& G = p.g[gi];
-          const int nkb = (G.kc + kTcKB - 1) / kTcKB;
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int kbs = min(kTcKB, G.kc - kb * kTcKB);
-            const uint32_t bytes = 2u * kbs * N * 4u;
-            const float* src = G.Wp + (size_t)kb * G.n_taps * 2 * kTcKB * N;
-            for (int tap = 0; tap < G.n_taps; ++tap) {
-              mbar_wait(b_empty(sb), pb ^ 1);
-              if (p.dbg & 1) { mbar_arrive(b_full(sb)); }
-              else {
-                mbar_expect_tx(b_full(sb), bytes);
-                bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src + (size_t)tap * 2 * kbs * N, bytes, b_full(sb));
-              }
-              if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
-            }
+        const uint32_t N = (uint32_t)ps.N;
+#pragma unroll 1
+        for (int s = ps.s_begin; s < ps.s_end; ++s) {
+          const TcStage e = p.st[s];
+          const uint32_t bytes = 64u * e.nks * N;                      // 2 planes x (8 nks) channels x N x 4 bytes
+          const float* src = p.g[e.gi].Wp + e.w_off;
+          mbar_wait(b_empty(sb), pb ^ 1);
+          if (p.dbg & 1) { mbar_arrive(b_full(sb)); }
+          else {
+            mbar_expect_tx(b_full(sb), bytes);
+            bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src, bytes, b_full(sb));
           }
+          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: the whole warp walks the loop (waits included), one elected lane issues =====
+    // ===== MMA issuer: the whole warp walks the stage table (waits included), one elected lane issues =====
     {
       const bool leader = elect_one();
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
@@ -491,69 +523,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
 #endif
       const int terms = p.terms;
       const bool no_mma = (p.dbg & 4) != 0;
+      const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+      constexpr uint32_t a_lbo = kTcRows * 16;
+      constexpr uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4);
       for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
         const TcPass& ps = p.pass[wk % p.n_pass];
-        const int N = ps.N;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-        const uint32_t a_lbo = kTcRows * 16, b_lbo = (uint32_t)N * 16;
-        TcWalk w(p, ps);
-        bool done = false;
-        uint32_t acc = 0;
-        bool fresh = true;           // first tap of a chunk: wait for the drain warps to release the buffer
-        while (!done) {
-          const TcGroup& G = p.g[w.gi];
-          const int kbs = min(kTcKB, G.kc - w.kb * kTcKB);
-          TCP(tq = clock64();)
-          mbar_wait(a_full(sa), pa);
-          TCP(if (st_issue == 0) t_begin = clock64(); else st_a += clock64() - tq;)   // the first window also waits for the predecessor kernel (PDL)
-          const uint64_t a_desc0 = tc_desc(smem_u32(As + (size_t)sa * 2 * kTcAPlane), a_lbo, 128);
-          const uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4), b_ks = (uint64_t)((2 * b_lbo) >> 4);
-          const int nks = no_mma ? 0 : kbs / 8;
-          bool kb_end = false;
-          while (!kb_end) {
-            const int tap = w.tap;
-            const int buf = chunk % kTcAccBufs;
-            if (fresh) {
-              TCP(tq = clock64();)
-              mbar_wait(acc_empty0 + 8 * buf, ((chunk / kTcAccBufs) & 1) ^ 1);
-              TCP(st_acc += clock64() - tq;)
-              tc_fence_after();
-              acc = 0; fresh = false;
-            }
-            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
+        const uint32_t N = (uint32_t)ps.N;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);   // TF32 x TF32 -> fp32
+        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);  // BF16 x BF16 -> fp32, K = 16
+        const uint32_t b_lbo = N * 16;
+        const uint64_t b_ks = (uint64_t)((2 * b_lbo) >> 4);
+        uint64_t a_desc0 = 0;
+        uint32_t d_tmem = 0, acc = 0;
+#pragma unroll 1
+        for (int s = ps.s_begin; s < ps.s_end; ++s) {
+          const TcStage e = p.st[s];
+          if (e.flags & kTcKbFirst) {
             TCP(tq = clock64();)
-            mbar_wait(b_full(sb), pb);
-            TCP(st_b += clock64() - tq;)
-            tc_fence_after();
-            TCP(tq = clock64();)
-            // descriptors advance by plain 64-bit adds on the (address >> 4) field: no re-encoding per MMA
-            uint64_t da = a_desc0 + (uint64_t)tap;                                  // tap j = window shifted by j rows of 16 B
-            uint64_t db = tc_desc(smem_u32(Bs + (size_t)sb * b_stage_bytes), b_lbo, 128);
-            const uint64_t b_lo_off = (uint64_t)(((uint32_t)(kbs / 4) * N * 16) >> 4);
-#pragma unroll 4
-            for (int ks = 0; ks < nks; ++ks) {
-              if (leader) {
-                tc_mma_tf32(d_tmem, da, db, idesc, acc);
-                if (terms >= 3) {
-                  tc_mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1);
-                  tc_mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1);
-                }
-                if (terms >= 4) tc_mma_tf32(d_tmem, da + a_lo_off, db + b_lo_off, idesc, 1);
-              }
-              acc = 1;
-              da += a_ks; db += b_ks;
-            }
-            if (leader) tc_commit(b_empty(sb));
-            __syncwarp();
-            TCP(st_issue += clock64() - tq;)
-            if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
-            if (w.next(p, ps, kb_end, done)) {
-              if (leader) tc_commit(acc_full0 + 8 * buf);
-              ++chunk; fresh = true;
-            }
+            mbar_wait(a_full(sa), pa);
+            TCP(if (st_issue == 0) t_begin = clock64(); else st_a += clock64() - tq;)   // the first window also waits for the predecessor kernel (PDL)
+            a_desc0 = tc_desc(a_base + (uint32_t)sa * (2 * kTcAPlane * 4), a_lbo, 128);
           }
-          if (leader) tc_commit(a_empty(sa));
-          if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
+          if (e.flags & kTcChunkFirst) {     // first stage of a chunk: wait for the drain warps to release the buffer
+            const int buf = chunk % kTcAccBufs;
+            TCP(tq = clock64();)
+            mbar_wait(acc_empty0 + 8 * buf, ((chunk / kTcAccBufs) & 1) ^ 1);
+            TCP(st_acc += clock64() - tq;)
+            d_tmem = tmem_base + (uint32_t)(buf * kTcNMax);
+            acc = 0;
+          }
+          TCP(tq = clock64();)
+          mbar_wait(b_full(sb), pb);
+          TCP(st_b += clock64() - tq;)
+          tc_fence_after();
+          TCP(tq = clock64();)
+          // descriptors advance by plain 64-bit adds on the (address >> 4) field: no re-encoding per MMA
+          uint64_t da = a_desc0 + (uint64_t)e.tap;                                  // tap j = window shifted by j rows of 16 B
+          uint64_t db = tc_desc(b_base + (uint32_t)sb * b_stage_bytes, b_lbo, 128);
+          const uint64_t b_lo_off = (uint64_t)(2u * e.nks * N);                    // (kbs / 4) * N * 16 bytes >> 4
+          const int nks = no_mma ? 0 : e.nks;
+#pragma unroll 4
+          for (int ks = 0; ks < nks; ++ks) {
+            if (leader) {
+              tc_mma_tf32(d_tmem, da, db, idesc, acc);                                          // a_hi * b_hi
+              if (terms >= 2) tc_mma_bf16(d_tmem, da + a_lo_off, db + b_lo_off, idesc16);      // a_lo * b_hi + a_hi * b_lo
+            }
+            acc = 1;
+            da += a_ks; db += b_ks;
+          }
+          if (leader) {
+            tc_commit(b_empty(sb));
+            if (e.flags & kTcChunkLast) tc_commit(acc_full0 + 8 * (chunk % kTcAccBufs));
+            if (e.flags & kTcKbLast) tc_commit(a_empty(sa));
+          }
+          __syncwarp();
+          TCP(st_issue += clock64() - tq;)
+          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+          if (e.flags & kTcChunkLast) ++chunk;
+          if (e.flags & kTcKbLast) { if (++sa == kTcAStages) { sa = 0; pa ^= 1; } }
         }
       }
 #ifdef AVC_TC_PROFILE
@@ -619,39 +646,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             me = (msk[1] && 4 * ec < kbs) ? ld4(msk[1] + kb0 + 4 * ec) : f4zero();
           }
         };
-        fetch(0);
+        // L2 prefetch runs kTcPfDist K blocks ahead of the register fetch (one 128-byte line per row and K block)
+        auto prefetch = [&](int kb) {
+          if (kb >= nkb) return;
+          const int kb0 = kb * kTcKB;
+          if (src[0]) { prefetch_l2(src[0] + kb0); if (msk[0]) prefetch_l2(msk[0] + kb0); }
+          if (ec == 0 && src[1]) { prefetch_l2(src[1] + kb0); if (msk[1]) prefetch_l2(msk[1] + kb0); }
+        };
+#pragma unroll 1
+        for (int d = 1; d <= kTcPfDist; ++d) prefetch(d);
         TCL(l_setup += clock64() - lq;)
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int kbs = min(kTcKB, G.kc - kb * kTcKB);
-          TCL(lq = clock64();)
-          mbar_wait(a_empty(sa), pa ^ 1);
-          TCL(l_wait += clock64() - lq; lq = clock64();)
-          float* hi = As + (size_t)sa * 2 * kTcAPlane;
-          float* lo = hi + kTcAPlane;
-          if (p.Mk) {
+        // kb = -1 only fetches K block 0; afterwards: store K block kb, then issue the loads of kb + 1 so that they
+        // fly while this thread waits for the next stage to be released (one fetch site: code size matters here)
+#pragma unroll 1
+        for (int kb = -1; kb < nkb; ++kb) {
+          if (kb >= 0) {
+            const int kbs = min(kTcKB, G.kc - kb * kTcKB);
+            TCL(lq = clock64();)
+            mbar_wait(a_empty(sa), pa ^ 1);
+            TCL(l_wait += clock64() - lq; lq = clock64();)
+            float* hi = As + (size_t)sa * 2 * kTcAPlane;
+            float* lo = hi + kTcAPlane;
+            if (p.Mk) {
 #pragma unroll
-            for (int c = 0; c < kTcKB / 4; ++c) v[c] = dact4mul(v[c], m[c], p.slope);
-            ve = dact4mul(ve, me, p.slope);
-          }
+              for (int c = 0; c < kTcKB / 4; ++c) v[c] = dact4mul(v[c], m[c], p.slope);
+              ve = dact4mul(ve, me, p.slope);
+            }
+            // plane 0: TF32 hi parts [k/4][row][4 floats]; plane 1: per k-step of 8 channels two 16-byte K chunks per row,
+            // bf16(lo[0..8)) then bf16(hi[0..8)) -- the K = 16 operand of the correction MMA (pairs with the weights' hi|lo chunks)
 #pragma unroll
-          for (int c = 0; c < kTcKB / 4; ++c) {
-            if (4 * c >= kbs) break;
-            const float4 h = make_float4(tf32_hi(v[c].x), tf32_hi(v[c].y), tf32_hi(v[c].z), tf32_hi(v[c].w));
-            st4(hi + ((size_t)c * kTcRows + tl) * 4, h);
-            st4(lo + ((size_t)c * kTcRows + tl) * 4, make_float4(tf32_hi(v[c].x - h.x), tf32_hi(v[c].y - h.y), tf32_hi(v[c].z - h.z), tf32_hi(v[c].w - h.w)));
+            for (int ks = 0; ks < kTcKB / 8; ++ks) {
+              if (8 * ks >= kbs) break;
+              const float4 a = v[2 * ks], b = v[2 * ks + 1];
+              const float4 ha = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+              const float4 hb = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
+              st4(hi + ((size_t)(2 * ks) * kTcRows + tl) * 4, ha);
+              st4(hi + ((size_t)(2 * ks + 1) * kTcRows + tl) * 4, hb);
+              st_bf16x8(lo + ((size_t)(2 * ks) * kTcRows + tl) * 4, f4sub(a, ha), f4sub(b, hb));
+              st_bf16x8(lo + ((size_t)(2 * ks + 1) * kTcRows + tl) * 4, ha, hb);
+            }
+            if (have_e && 4 * ec < kbs) {   // extra rows: this thread holds 4 of the 8 channels of its k-step
+              const float4 h = make_float4(tf32_hi(ve.x), tf32_hi(ve.y), tf32_hi(ve.z), tf32_hi(ve.w));
+              st4(hi + ((size_t)ec * kTcRows + kTcM + er) * 4, h);
+              float* q = lo + ((size_t)(ec & ~1) * kTcRows + kTcM + er) * 4 + 2 * (ec & 1);
+              st_bf16x4(q, f4sub(ve, h));
+              st_bf16x4(q + (size_t)kTcRows * 4, h);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(sa));
+            TCL(l_store += clock64() - lq; lq = clock64();)
+            if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
           }
-          if (have_e && 4 * ec < kbs) {
-            const float4 h = make_float4(tf32_hi(ve.x), tf32_hi(ve.y), tf32_hi(ve.z), tf32_hi(ve.w));
-            st4(hi + ((size_t)ec * kTcRows + kTcM + er) * 4, h);
-            st4(lo + ((size_t)ec * kTcRows + kTcM + er) * 4, make_float4(tf32_hi(ve.x - h.x), tf32_hi(ve.y - h.y), tf32_hi(ve.z - h.z), tf32_hi(ve.w - h.w)));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_full(sa));
-          TCL(l_store += clock64() - lq; lq = clock64();)
-          if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
           if (kb + 1 < nkb) fetch(kb + 1);
-          TCL(l_fetch += clock64() - lq;)
+          prefetch(kb + 1 + kTcPfDist);
+          TCL(if (kb >= 0) l_fetch += clock64() - lq;)
         }
       }
     }
@@ -671,8 +720,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
       const TcPass& ps = p.pass[wk % p.n_pass];
       const long long v0 = (long long)(wk / p.n_pass) * kTcM;
       float* scratch = scr_all + (size_t)(warp - 6) * 32 * kTcScrPitch;
-      if (ps.N == 128) tc_drain_and_store<64>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
-      else tc_drain_and_store<40>(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
+      tc_drain_and_store(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
     }
 #ifdef AVC_TC_PROFILE
     if ((p.dbg & 32) && blockIdx.x == 0 && warp == 6 && lane == 0)
@@ -739,8 +787,16 @@ struct TcOp {
   }
 };
 
+inline int tc_stage_count(const TcOp& op) {
+  int n = 0;
+  for (int q = 0; q < op.n_pass; ++q)
+    for (int g = op.pass[q].g_begin; g < op.pass[q].g_end; ++g) n += ((op.g[g].kc + kTcKB - 1) / kTcKB) * op.g[g].n_taps;
+  return n;
+}
+
 inline bool tc_supported(const ConvArgs& a, const TcOp& op) {
   if (op.n_pass <= 0 || op.n_groups <= 0) return false;
+  if (tc_stage_count(op) > kTcMaxStages) return false;
   if (a.Y2 && a.bwd) return false;
   if (a.res.mode != RES_NONE && (a.res.rf < 1 || a.res.rf > 2)) return false;   // the epilogue reads at most two skip rows per output row
   for (int g = 0; g < op.n_groups; ++g)
@@ -785,8 +841,38 @@ inline TcArgs tc_make_args(const ConvArgs& a, const TcOp& op, float* side, int t
   t.terms = terms;
   { static const int cs = getenv("AVC_TC_CHUNK") ? atoi(getenv("AVC_TC_CHUNK")) : kTcChunkSteps; t.chunk_steps = cs; }
   { static const int dbg = getenv("AVC_TC_DBG") ? atoi(getenv("AVC_TC_DBG")) : 0; t.dbg = dbg; }
-  for (int q = 0; q < op.n_pass; ++q) t.pass[q] = op.pass[q];
   for (int g = 0; g < op.n_groups; ++g) t.g[g] = op.g[g];
+  // stage table: (group, K block, tap) in the order every role visits them; an accumulation chunk closes after the
+  // tap that brings it to chunk_steps MMA k-steps and after the last tap of the pass
+  int ns = 0;
+  for (int q = 0; q < op.n_pass; ++q) {
+    TcPass ps = op.pass[q];
+    ps.s_begin = ns; ps.n_chunks = 0;
+    int steps = 0;
+    for (int g = ps.g_begin; g < ps.g_end; ++g) {
+      const TcGroup& G = op.g[g];
+      const int nkb = (G.kc + kTcKB - 1) / kTcKB;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int kbs = std::min(kTcKB, G.kc - kb * kTcKB);
+        for (int tap = 0; tap < G.n_taps; ++tap) {
+          if (ns >= kTcMaxStages) fail(AVC_ERR_STATE, "conv_tc: stage table overflow (tc_supported should have refused this conv)");
+          TcStage& e = t.st[ns++];
+          e.w_off = (uint32_t)((size_t)kb * G.n_taps * 2 * kTcKB * ps.N + (size_t)tap * 2 * kbs * ps.N);
+          e.gi = (uint8_t)g; e.tap = (uint8_t)tap; e.nks = (uint8_t)(kbs / 8);
+          unsigned fl = 0;
+          if (tap == 0) fl |= kTcKbFirst;
+          if (tap == G.n_taps - 1) fl |= kTcKbLast;
+          if (steps == 0) fl |= kTcChunkFirst;
+          steps += kbs / 8;
+          const bool last = g == ps.g_end - 1 && kb == nkb - 1 && tap == G.n_taps - 1;
+          if (last || steps >= t.chunk_steps) { fl |= kTcChunkLast; steps = 0; ++ps.n_chunks; }
+          e.flags = (uint8_t)fl;
+        }
+      }
+    }
+    ps.s_end = ns;
+    t.pass[q] = ps;
+  }
   return t;
 }
 
