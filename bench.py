@@ -433,7 +433,8 @@ def main():
     # ---- side measurements on rank 0 at N=1: batched configs where the rooflines are meaningful ------
     if world == 1 and not args.no_extra and args.workload == "e2e":
         extra = {}
-        for name, (k2, B2, T2, n2) in {"emb_B128_T512": ("emb", 128, 512, 6), "fb_B64_T256": ("fb", 64, 256, 6)}.items():
+        for name, (k2, B2, T2, n2) in {"emb_B128_T512": ("emb", 128, 512, 6), "fb_B64_T256": ("fb", 64, 256, 6),
+                                      "emb_B512_T512_cfg4_per_gpu": ("emb", 512, 512, 4)}.items():
             try:
                 i2 = {k: v.to(dev) for k, v in make_inputs(k2, B2, T2, seed=9).items()}
                 s2 = eng.begin(k2, i2["vc_tgt"], i2["adv_tgt"], 0.1, 3 + n2 + 1, vc_src=i2.get("vc_src"), w0=i2["w0"])
@@ -447,9 +448,10 @@ def main():
                 tf = cf / (cm / 1e3) / 1e12
                 ent = {"utterance_iterations_per_s": B2 * 1e3 / ms2, "ms_per_step": ms2, "conv_tflops": tf,
                        "conv_frac_of_bf16_peak": tf / peaks["bf16_tflops"],
-                       # tcgen05 path: 3xTF32 = 3 tensor passes per algorithmic FLOP, TF32 peak = bf16 peak / 2
-                       "conv_tensor_pipe_frac_of_tf32_peak_3x": 3 * tf / (peaks["bf16_tflops"] / 2),
-                       "conv_kernel": "conv_tc_kernel (tcgen05 kind::tf32, 3xTF32 split, chunked fp32 accumulation)",
+                       # tcgen05 path: per 8 input channels one TF32 MMA (hi*hi) and one BF16 K=16 MMA (lo*hi + hi*lo), each as long
+                       # as a single-pass TF32 MMA: the tensor pipe executes 2x the algorithmic FLOPs at the TF32 rate (= bf16 peak / 2)
+                       "conv_tensor_pipe_busy_frac": 2 * tf / (peaks["bf16_tflops"] / 2),
+                       "conv_kernel": "conv_tc_kernel (tcgen05: kind::tf32 hi*hi + kind::f16 bf16 correction, chunked fp32 accumulation)",
                        "conv_share_of_step": cm / sum(m for _, m, _, _ in p2)}
                 for kk, nm in ((1, "norm"), (5, "update")):
                     mm = sum(m for q, m, _, _ in p2 if q == kk); bb = sum(bt for q, _, _, bt in p2 if q == kk)
