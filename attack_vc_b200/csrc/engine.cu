@@ -21,6 +21,7 @@
 #include "host_util.h"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_wgrad.cuh"
 #include "elementwise.cuh"
 
 using namespace avc;
@@ -1906,6 +1907,41 @@ int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx, 
     h->conv_impl = save;
     h->launches += (long long)v.size();
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+  });
+}
+
+int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias, int32_t B, int32_t T,
+                     int32_t c_in, int32_t c_out, int32_t k, int32_t stride, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return guarded(h, [&] {
+    check_conv_dims(B, T, c_in, c_out, k, stride);
+    if (!x || !dy || !dw) fail(AVC_ERR_INVALID, "conv1d_wgrad: null tensor");
+    const int To = cdiv(T, stride);
+    const long long rows = (long long)B * To;
+    WgradArgs a{};
+    a.x = x; a.T = T; a.c_in = c_in; a.dy = dy; a.To = To; a.c_out = c_out;
+    a.B = B; a.k = k; a.stride = stride; a.pl = k / 2;
+    const int tiles = cdiv(c_out, kWgTile) * cdiv(c_in, kWgTile) * k;
+    // enough row splits for ~3 CTAs per SM, at least 64 rows each
+    int splits = std::max(1, std::min<int>((int)((rows + 63) / 64), cdiv(3 * h->sm_count, tiles)));
+    a.rows_per_split = (int)((rows + splits - 1) / splits);
+    a.rows_per_split = cdiv(a.rows_per_split, kWgRows) * kWgRows;
+    splits = (int)((rows + a.rows_per_split - 1) / a.rows_per_split);
+    a.splits = splits;
+    Arena tmp(&h->pool);   // partial tiles: a slab recycled through the handle's pool (no cudaMalloc per call)
+    a.partial = tmp.f((size_t)splits * k * c_out * c_in);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(cdiv(c_out, kWgTile), cdiv(c_in, kWgTile), k * splits);
+    conv_wgrad_kernel<<<grid, 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    conv_wgrad_final_kernel<<<ew_grid((long long)k * c_out * c_in, h->sm_count), 256, 0, st>>>(a.partial, splits, k, c_out, c_in, dw);
+    CK(cudaGetLastError());
+    if (dbias) {
+      conv_bgrad_kernel<<<cdiv(c_out, 32), 256, 0, st>>>(dy, rows, c_out, dbias);
+      CK(cudaGetLastError());
+    }
+    h->launches += dbias ? 3 : 2;
+    CK(cudaStreamSynchronize(st));
   });
 }
 

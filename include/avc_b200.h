@@ -164,6 +164,11 @@ int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* b
 int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx,
                      int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride,
                      int32_t impl, void* stream);
+/* autograd of the above w.r.t. the parameters: x [B,T,c_in], dy [B,T_out,c_out] -> dw [c_out,c_in,k] (PyTorch
+ * layout), dbias [c_out] or NULL.  Replaces the param.grad side effect of loss.backward() (attack_utils.py:45,83,127),
+ * which the attack itself never reads (SURVEY.md §8 "wgrad note"): opt-in, not part of an attack iteration. */
+int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias,
+                     int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride, void* stream);
 /* replaces: act(append_cond(InstanceNorm1d(y), cond)) [+ residual] (models.py:414-431).
  * cond [B,2C] (mean | std) or NULL; res [B,T/up,C] or NULL; stats_out [B,C,2] (mean, rstd). */
 int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond, const float* res,

@@ -48,6 +48,24 @@ def test_conv1d_fwd(engine, B, T, ci, co, k, s, impl):
     assert rel_err(y, ref) < 2e-6
 
 
+@pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES + [(16, 512, 128, 128, 5, 1), (8, 256, 80, 128, 8, 1)])
+def test_conv1d_wgrad(engine, B, T, ci, co, k, s):
+    """d/dW, d/db of pad_layer + Conv1d against fp64 autograd (the param.grad the reference's loss.backward() fills)."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 13)
+    x = torch.randn(B, T, ci, device="cuda", generator=g)
+    w = (torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5).double().requires_grad_(True)
+    b = torch.randn(co, device="cuda", generator=g).double().requires_grad_(True)
+    y = ref_conv(x.double(), w, b, s)
+    dy = torch.randn(y.shape, device="cuda", generator=g)
+    dw_ref, db_ref = torch.autograd.grad(y, (w, b), dy.double())
+    dw, db = engine.conv1d_wgrad(x, dy, k, stride=s)
+    assert dw.shape == dw_ref.shape and db.shape == db_ref.shape
+    assert rel_err(dw, dw_ref) < 2e-6
+    assert rel_err(db, db_ref) < 2e-6
+    dw2, _ = engine.conv1d_wgrad(x, dy, k, stride=s, bias=False)
+    assert torch.equal(dw, dw2)          # fixed summation order: bit-reproducible
+
+
 @pytest.mark.parametrize("impl", [1, 3])
 @pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES)
 def test_conv1d_dgrad(engine, B, T, ci, co, k, s, impl):
