@@ -142,27 +142,38 @@ inline void tc_pack_taps(Arena& mem, TcPack& p, const std::vector<float>& img, i
   const int nkb = (kc + kTcKB - 1) / kTcKB;
   for (int ch = 0; ch < nch; ++ch) {
     const int n0 = ch * kTcNMax, cn = std::min(kTcNMax, n - n0);
-    std::vector<float> out((size_t)2 * k * kc * cn);
+    // two images back to back: [0] whole stages for the single-CTA kernel, [1] the same stages split into column halves
+    // for the CTA-pair kernel ([half][plane][k/4][cn/2][16 B], each CTA streams its half)
+    const size_t img_floats = (size_t)2 * k * kc * cn;
+    std::vector<float> out(2 * img_floats);
     uint16_t* out16 = reinterpret_cast<uint16_t*>(out.data());
     size_t o = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int kb0 = kb * kTcKB, kbs = std::min(kTcKB, kc - kb0);
       for (int t = 0; t < k; ++t) {
+        auto wv = [&](int c, int nn) { return img[((size_t)taps[t] * kc + kb0 + c) * n + n0 + nn]; };
         // plane 0: TF32 hi parts, [k/4][n][4 floats]
         for (int c = 0; c < kbs / 4; ++c)
           for (int nn = 0; nn < cn; ++nn)
-            for (int e = 0; e < 4; ++e)
-              out[o++] = tf32_hi_host(img[((size_t)taps[t] * kc + kb0 + 4 * c + e) * n + n0 + nn]);
+            for (int e = 0; e < 4; ++e) {
+              const float hi = tf32_hi_host(wv(4 * c + e, nn));
+              out[o + ((size_t)c * cn + nn) * 4 + e] = hi;
+              const int h = nn / (cn / 2), nh = nn % (cn / 2);
+              out[img_floats + o + (size_t)h * kbs * cn + ((size_t)c * (cn / 2) + nh) * 4 + e] = hi;
+            }
         // plane 1: per MMA k-step of 8 channels two 16-byte K chunks per column: bf16(hi[0..8)), bf16(lo[0..8))
         for (int ks = 0; ks < kbs / 8; ++ks)
           for (int j = 0; j < 2; ++j)
             for (int nn = 0; nn < cn; ++nn)
               for (int e = 0; e < 8; ++e) {
-                const float v = img[((size_t)taps[t] * kc + kb0 + 8 * ks + e) * n + n0 + nn];
+                const float v = wv(8 * ks + e, nn);
                 const float hi = tf32_hi_host(v);
-                out16[2 * o + ((size_t)(2 * ks + j) * cn + nn) * 8 + e] = bf16_rn_host(j == 0 ? hi : v - hi);
+                const uint16_t q = bf16_rn_host(j == 0 ? hi : v - hi);
+                out16[2 * (o + (size_t)kbs * cn) + ((size_t)(2 * ks + j) * cn + nn) * 8 + e] = q;
+                const int h = nn / (cn / 2), nh = nn % (cn / 2);
+                out16[2 * (img_floats + o + (size_t)h * kbs * cn + (size_t)kbs * cn / 2) + ((size_t)(2 * ks + j) * (cn / 2) + nh) * 8 + e] = q;
               }
-        o += (size_t)kbs * cn;
+        o += (size_t)2 * kbs * cn;
       }
     }
     p.blocks[ch] = mem.upload(out);
@@ -227,6 +238,33 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: the even CTA of a 2-CTA cluster issues M = 256 MMAs for both ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(bar), "r"(rank) : "memory");
+}
+// completion of all prior MMAs of the pair -> the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
 // K-major, no swizzle ("interleaved") shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14), LBO>>4 [16,30) = bytes between the two 16-byte K chunks of one MMA,
 // SBO>>4 [32,46) = bytes between consecutive 8-row core matrices, version 1 at [46,48), layout 0.
@@ -264,6 +302,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
+constexpr int kTcBarSlots = 38;    // 8-byte slots of the barrier block (36 barriers + the TMEM address)
 constexpr int kTcScrPitch = 36;    // floats per row of a drain warp's transpose slab (32 + 4: conflict-free float4 rows)
 
 // ---- epilogue ------------------------------------------------------------------------------------
@@ -381,7 +420,7 @@ struct TcDrainProf { long long wait, ld, epi; };
 constexpr int kTcNH = 64;   // accumulator columns per drain thread (half of a 128-column pass; N = 80: 64 + 16)
 __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
                                                    uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch,
-                                                   TcDrainProf& dp) {
+                                                   TcDrainProf& dp, int leader_rank = -1) {   // >= 0: acc_empty lives in that CTA of the pair
   TCD(long long dq;)
   constexpr int NH = kTcNH;
   const int quad = warp & 3;                    // TMEM lanes this warp may read: [32*quad, 32*quad+32)
@@ -427,7 +466,7 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+    if (lane == 0) { if (leader_rank >= 0) mbar_arrive_cta(acc_empty0 + 8 * buf, (uint32_t)leader_rank); else mbar_arrive(acc_empty0 + 8 * buf); }
     TCD(dp.ld += clock64() - dq;)
     ++chunk;
   }
@@ -450,33 +489,52 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
 // Persistent: gridDim.x CTAs (one per SM) walk the work items (M tile, pass) round-robin; barrier phases,
 // ring positions and the accumulator ping-pong run on across items, so the drain warps' epilogue of one
 // item overlaps the MMAs of the next.
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) {
+//
+// PAIR = true: the kernel is launched as clusters of two CTAs (one TPC).  The two CTAs work on M tiles 2i and 2i+1 of
+// the same pass; the even CTA (the leader) issues cta_group::2 MMAs with M = 256 for both.  Each CTA gathers its own
+// window, keeps its own accumulators and runs its own epilogue, but holds only HALF of every weight stage (N/2
+// columns): the tensor cores of both SMs read it across the pair.  Per MMA a CTA's shared memory delivers 4 KB of A
+// and 2 KB of B instead of 4 + 4, and the bulk copies write 16 KB per stage instead of 32 -- shared-memory bandwidth
+// is what bounds the single-CTA kernel.  Cross-CTA protocol: the peer's loader and drain warps arrive on
+// the LEADER's a_full / acc_empty barriers; the peer's warp 1 forwards "my weight half has landed" to the leader's
+// b_fwd barrier; the leader's commits are multicast to the same barrier in both CTAs.
+template <bool PAIR>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel_t(const TcArgs p) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t b_stage_bytes = 2 * (kTcKB / 4) * kTcNMax * 16;                // hi + lo plane of a full weight stage
+  constexpr int NBS = PAIR ? 2 * kTcBStages : kTcBStages;                            // weight ring depth (half-size stages in a pair)
+  constexpr uint32_t b_stage_bytes = 2 * (kTcKB / 4) * kTcNMax * 16 / (PAIR ? 2 : 1);   // both planes of a full weight stage (pair: of its half)
   float* As = reinterpret_cast<float*>(tc_smem);                                     // [kTcAStages][2][kTcAPlane]
-  unsigned char* Bs = tc_smem + (size_t)kTcAStages * 2 * kTcAPlane * 4;              // [kTcBStages][b_stage_bytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)kTcBStages * b_stage_bytes);
-  // bars: a_full[2] a_empty[2] b_full[4] b_empty[4] acc_full[4] acc_empty[4]
+  unsigned char* Bs = tc_smem + (size_t)kTcAStages * 2 * kTcAPlane * 4;              // [NBS][b_stage_bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16);
+  // bars: a_full[2] a_empty[2] b_full[8] b_empty[8] b_fwd[8] acc_full[4] acc_empty[4]
   const uint32_t bar0 = smem_u32(bars);
   auto a_full = [&](int s) { return bar0 + 8 * s; };
   auto a_empty = [&](int s) { return bar0 + 8 * (2 + s); };
   auto b_full = [&](int s) { return bar0 + 8 * (4 + s); };
-  auto b_empty = [&](int s) { return bar0 + 8 * (8 + s); };
-  const uint32_t acc_full0 = bar0 + 8 * 12, acc_empty0 = bar0 + 8 * 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* scr_all = reinterpret_cast<float*>(bars + 22);                               // [8 drain warps][32][kTcScrPitch]
+  auto b_empty = [&](int s) { return bar0 + 8 * (12 + s); };
+  auto b_fwd = [&](int s) { return bar0 + 8 * (20 + s); };
+  const uint32_t acc_full0 = bar0 + 8 * 28, acc_empty0 = bar0 + 8 * 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  float* scr_all = reinterpret_cast<float*>(bars + kTcBarSlots);                      // [8 drain warps][32][kTcScrPitch]
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;                               // 0: leader
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), 4); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < kTcAccBufs; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, 8); }
+    for (int s = 0; s < kTcAStages; ++s) { mbar_init(a_full(s), PAIR ? 8 : 4); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < 8; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); mbar_init(b_fwd(s), 1); }
+    for (int s = 0; s < kTcAccBufs; ++s) { mbar_init(acc_full0 + 8 * s, 1); mbar_init(acc_empty0 + 8 * s, PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t tmem_cols = kTcAccBufs * kTcNMax;     // accumulator ring
+  if (PAIR) cluster_sync_all();                            // both CTAs' barriers exist before anyone arrives remotely
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -485,28 +543,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   pdl_launch_dependents();
 
   const int n_mt = (int)((p.Mv + kTcM - 1) / kTcM);
-  const int n_work = n_mt * p.n_pass;              // item w: M tile w / n_pass, pass w % n_pass (passes of a tile share A in L2)
+  // item w: M tile (pair: tile pair) w / n_pass, pass w % n_pass (passes of a tile share A in L2)
+  const int n_work = (PAIR ? (n_mt + 1) / 2 : n_mt) * p.n_pass;
+  const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_row0 = [&](int wk) { return (long long)(PAIR ? 2 * (wk / p.n_pass) + (int)rank : wk / p.n_pass) * kTcM; };   // a tile past the end is all dead rows
 
   if (warp == 0) {
     // ===== weight producer: one elected lane streams the stages of the table with the TMA engine =====
     if (lane == 0) {
       int sb = 0; uint32_t pb = 0;
-      for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      for (int wk = w_first; wk < n_work; wk += w_step) {
         const TcPass& ps = p.pass[wk % p.n_pass];
         const uint32_t N = (uint32_t)ps.N;
 #pragma unroll 1
         for (int s = ps.s_begin; s < ps.s_end; ++s) {
           const TcStage e = p.st[s];
-          const uint32_t bytes = 64u * e.nks * N;                      // 2 planes x (8 nks) channels x N x 4 bytes
-          const float* src = p.g[e.gi].Wp + e.w_off;
+          const uint32_t bytes = (PAIR ? 32u : 64u) * e.nks * N;      // 2 planes x (8 nks) channels x N (pair: N/2) x 4 bytes
+          const TcGroup& G = p.g[e.gi];
+          // pair image: after the single-CTA image (2 * taps * channels * N floats), each stage as [half][plane][k/4][N/2][4]
+          const float* src = G.Wp + e.w_off + (PAIR ? (size_t)2 * G.n_taps * G.kc * N + rank * (bytes >> 2) : (size_t)0);
           mbar_wait(b_empty(sb), pb ^ 1);
           if (p.dbg & 1) { mbar_arrive(b_full(sb)); }
           else {
             mbar_expect_tx(b_full(sb), bytes);
             bulk_g2s(smem_u32(Bs + (size_t)sb * b_stage_bytes), src, bytes, b_full(sb));
           }
-          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+          if (++sb == NBS) { sb = 0; pb ^= 1; }
         }
+      }
+    }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===== peer CTA: forward "my half of weight stage s has landed" to the leader's b_fwd barrier =====
+    int sb = 0; uint32_t pb = 0;
+    for (int wk = w_first; wk < n_work; wk += w_step) {
+      const TcPass& ps = p.pass[wk % p.n_pass];
+#pragma unroll 1
+      for (int s = ps.s_begin; s < ps.s_end; ++s) {
+        mbar_wait(b_full(sb), pb);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(b_fwd(sb), 0);
+        if (++sb == NBS) { sb = 0; pb ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -526,12 +602,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
       const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
       constexpr uint32_t a_lbo = kTcRows * 16;
       constexpr uint64_t a_lo_off = (uint64_t)((kTcAPlane * 4) >> 4), a_ks = (uint64_t)((2 * a_lbo) >> 4);
-      for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      for (int wk = w_first; wk < n_work; wk += w_step) {
         const TcPass& ps = p.pass[wk % p.n_pass];
         const uint32_t N = (uint32_t)ps.N;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);   // TF32 x TF32 -> fp32
-        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);  // BF16 x BF16 -> fp32, K = 16
-        const uint32_t b_lbo = N * 16;
+        constexpr uint32_t m_field = (uint32_t)((PAIR ? 2 * kTcM : kTcM) >> 4) << 24;                                // M = 256 across the pair
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | m_field;   // TF32 x TF32 -> fp32
+        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | m_field;  // BF16 x BF16 -> fp32, K = 16
+        const uint32_t b_lbo = (PAIR ? N / 2 : N) * 16;                                                               // this CTA's columns of the stage
         const uint64_t b_ks = (uint64_t)((2 * b_lbo) >> 4);
         uint64_t a_desc0 = 0;
         uint32_t d_tmem = 0, acc = 0;
@@ -554,31 +631,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
           }
           TCP(tq = clock64();)
           mbar_wait(b_full(sb), pb);
+          if (PAIR) mbar_wait(b_fwd(sb), pb);          // ... and the peer's half
           TCP(st_b += clock64() - tq;)
           tc_fence_after();
           TCP(tq = clock64();)
           // descriptors advance by plain 64-bit adds on the (address >> 4) field: no re-encoding per MMA
           uint64_t da = a_desc0 + (uint64_t)e.tap;                                  // tap j = window shifted by j rows of 16 B
           uint64_t db = tc_desc(b_base + (uint32_t)sb * b_stage_bytes, b_lbo, 128);
-          const uint64_t b_lo_off = (uint64_t)(2u * e.nks * N);                    // (kbs / 4) * N * 16 bytes >> 4
+          const uint64_t b_lo_off = (uint64_t)((PAIR ? 1u : 2u) * e.nks * N);      // (kbs / 4) * N (pair: N/2) * 16 bytes >> 4
           const int nks = no_mma ? 0 : e.nks;
+          // all TF32 MMAs of the stage, then all BF16 correction MMAs (same accumulator, order is free): alternating the
+          // MMA kind instruction by instruction cost ~12 clk per MMA
 #pragma unroll 4
           for (int ks = 0; ks < nks; ++ks) {
             if (leader) {
-              tc_mma_tf32(d_tmem, da, db, idesc, acc);                                          // a_hi * b_hi
-              if (terms >= 2) tc_mma_bf16(d_tmem, da + a_lo_off, db + b_lo_off, idesc16);      // a_lo * b_hi + a_hi * b_lo
+              if (PAIR) tc_mma2_tf32(d_tmem, da, db, idesc, acc);
+              else tc_mma_tf32(d_tmem, da, db, idesc, acc);                                       // a_hi * b_hi
             }
             acc = 1;
             da += a_ks; db += b_ks;
           }
+          if (terms >= 2) {
+            da = a_desc0 + (uint64_t)e.tap + a_lo_off;
+            db = tc_desc(b_base + (uint32_t)sb * b_stage_bytes, b_lbo, 128) + b_lo_off;
+#pragma unroll 4
+            for (int ks = 0; ks < nks; ++ks) {
+              if (leader) {
+                if (PAIR) tc_mma2_bf16(d_tmem, da, db, idesc16);
+                else tc_mma_bf16(d_tmem, da, db, idesc16);                                        // a_lo * b_hi + a_hi * b_lo
+              }
+              da += a_ks; db += b_ks;
+            }
+          }
           if (leader) {
-            tc_commit(b_empty(sb));
-            if (e.flags & kTcChunkLast) tc_commit(acc_full0 + 8 * (chunk % kTcAccBufs));
-            if (e.flags & kTcKbLast) tc_commit(a_empty(sa));
+            if (PAIR) {
+              tc_commit2(b_empty(sb));
+              if (e.flags & kTcChunkLast) tc_commit2(acc_full0 + 8 * (chunk % kTcAccBufs));
+              if (e.flags & kTcKbLast) tc_commit2(a_empty(sa));
+            } else {
+              tc_commit(b_empty(sb));
+              if (e.flags & kTcChunkLast) tc_commit(acc_full0 + 8 * (chunk % kTcAccBufs));
+              if (e.flags & kTcKbLast) tc_commit(a_empty(sa));
+            }
           }
           __syncwarp();
           TCP(st_issue += clock64() - tq;)
-          if (++sb == kTcBStages) { sb = 0; pb ^= 1; }
+          if (++sb == NBS) { sb = 0; pb ^= 1; }
           if (e.flags & kTcChunkLast) ++chunk;
           if (e.flags & kTcKbLast) { if (++sa == kTcAStages) { sa = 0; pa ^= 1; } }
         }
@@ -606,9 +704,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
 #else
 #define TCL(x)
 #endif
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    for (int wk = w_first; wk < n_work; wk += w_step) {
       const TcPass& ps = p.pass[wk % p.n_pass];
-      const long long v0 = (long long)(wk / p.n_pass) * kTcM;
+      const long long v0 = tile_row0(wk);
       for (int gi = ps.g_begin; gi < ps.g_end; ++gi) {
         TCL(lq = clock64();)
         const TcGroup& G = p.g[gi];
@@ -694,7 +792,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(sa));
+            if (lane == 0) { if (PAIR) mbar_arrive_cta(a_full(sa), 0); else mbar_arrive(a_full(sa)); }
             TCL(l_store += clock64() - lq; lq = clock64();)
             if (++sa == kTcAStages) { sa = 0; pa ^= 1; }
           }
@@ -716,11 +814,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
     int chunk = 0;
     TcDrainProf dp{0, 0, 0};
     TCD(const long long d_t0 = clock64();)
-    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+    for (int wk = w_first; wk < n_work; wk += w_step) {
       const TcPass& ps = p.pass[wk % p.n_pass];
-      const long long v0 = (long long)(wk / p.n_pass) * kTcM;
+      const long long v0 = tile_row0(wk);
       float* scratch = scr_all + (size_t)(warp - 6) * 32 * kTcScrPitch;
-      tc_drain_and_store(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp);
+      tc_drain_and_store(p, ps, tmem_base, acc_full0, acc_empty0, v0, warp, lane, chunk, scratch, dp, PAIR ? 0 : -1);
     }
 #ifdef AVC_TC_PROFILE
     if ((p.dbg & 32) && blockIdx.x == 0 && warp == 6 && lane == 0)
@@ -730,9 +828,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const TcArgs p) 
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the leader's MMAs write the peer's TMEM and read its shared memory: leave together
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -763,7 +863,7 @@ __global__ void tc_fold_kernel(float* __restrict__ Y, long long y_bs, int y_rs, 
 }
 
 inline size_t tc_smem_bytes() {
-  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + 22 * 8 + (size_t)8 * 32 * kTcScrPitch * 4;
+  return (size_t)kTcAStages * 2 * kTcAPlane * 4 + (size_t)kTcBStages * 2 * (kTcKB / 4) * kTcNMax * 16 + kTcBarSlots * 8 + (size_t)8 * 32 * kTcScrPitch * 4;
 }
 
 // ---- host: the tensor-core view of one conv launch (passes x groups, no tensor pointers yet) --------

@@ -44,6 +44,19 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
   CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
+// the same as a grid of 2-CTA clusters (CTA pairs on one TPC: the tcgen05 cta_group::2 kernel)
+template <class... KArgs, class... Args>
+void launch_k_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
+  CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
 
 // ---- packed weights ----------------------------------------------------------------------------
 struct ConvW {
@@ -209,7 +222,8 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
   CK(cudaFuncSetAttribute(norm_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(norm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
-  CK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CK(cudaFuncSetAttribute(conv_tc_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CK(cudaFuncSetAttribute(conv_tc_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
 }
 
 // small-M path: every window resident, deep weight ring (conv_simt.cuh: conv_small_kernel)
@@ -344,9 +358,17 @@ bool want_tc(const avc_handle* h, const ConvArgs& a, const TcOp& op) {
 
 void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st) {
   const size_t smem = tc_smem_bytes();
-  const long long work = ((t.Mv + kTcM - 1) / kTcM) * t.n_pass;
+  const long long n_mt = (t.Mv + kTcM - 1) / kTcM;
+  static const int pair_env = getenv("AVC_TC_PAIR") ? atoi(getenv("AVC_TC_PAIR")) : 0;
+  if (pair_env && n_mt >= 2) {   // CTA pairs: two M tiles of one pass per cluster, persistent over (tile pair, pass) items
+    const long long work = ((n_mt + 1) / 2) * t.n_pass;
+    dim3 grid(2u * (unsigned)std::min<long long>(work, sm_count / 2), 1, 1);
+    launch_k_pair(conv_tc_kernel_t<true>, grid, kTcThreads, smem, st, t);
+    return;
+  }
+  const long long work = n_mt * t.n_pass;
   dim3 grid((unsigned)std::min<long long>(work, sm_count), 1, 1);   // persistent: one CTA per SM
-  launch_k(conv_tc_kernel, grid, kTcThreads, smem, st, t);
+  launch_k(conv_tc_kernel_t<false>, grid, kTcThreads, smem, st, t);
 }
 
 void launch_tc_fold(const TcArgs& t, int sm_count, cudaStream_t st) {
