@@ -411,13 +411,75 @@ __device__ __forceinline__ void tc_acc_to_slab(const float (&acc)[NH], float* sc
     st4(scratch + lane * kTcScrPitch + 4 * q, make_float4(acc[C0 + 4 * q], acc[C0 + 4 * q + 1], acc[C0 + 4 * q + 2], acc[C0 + 4 * q + 3]));
 }
 
+constexpr int kTcNH = 64;   // accumulator columns per drain thread (half of a 128-column pass; N = 80: 64 + 16)
+#ifndef AVC_TC_DIRECT_EPI
+#define AVC_TC_DIRECT_EPI 0
+#endif
+constexpr bool kTcDirectEpi = AVC_TC_DIRECT_EPI != 0;
+// Direct epilogue: every drain lane writes the 64 columns of ITS row straight from its accumulator registers, 16 bytes
+// per store.  A warp store touches 32 rows x 16 B (two stores fill a 32-byte sector), which the memory system takes
+// at 32 lines per instruction -- but it is ~250 instructions per tile and thread where the transposing version
+// (per-warp shared-memory slab, shuffled row descriptors, 64-bit address arithmetic per row group) needs ~1900, and
+// the drain warps' instruction stream, not the memory system, is what made the epilogue (~10k clk per tile) longer
+// than the accumulator ring lets the MMA issuer run ahead.
+template <int NQ>   // float4 columns per batch: the batch's mask / skip loads are in flight before the first is consumed
+__device__ __forceinline__ void tc_store_row_batches(const TcArgs& p, const float (&acc)[kTcNH], float* yp, float* y2p,
+                                                     const float* g0p, const float* g1p, float rs, int chb, int ncol) {
+  const bool has_om = p.Om != nullptr, has_res = p.res.mode != RES_NONE;
+#pragma unroll
+  for (int q0 = 0; q0 < kTcNH / 4; q0 += NQ) {
+    if (4 * q0 < ncol) {
+      float4 ga[NQ], gb[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        if (g0p) ga[i] = ld4(g0p + 4 * (q0 + i));
+        if (g1p) gb[i] = ld4(g1p + 4 * (q0 + i));
+      }
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int c = 4 * (q0 + i);
+        if (c < ncol) {
+          float4 x = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+          if (p.bias) x = f4add(x, ld4(p.bias + chb + c));          // same address in every lane: one transaction
+          if (has_om) x = dact4mul(x, ga[i], p.slope);
+          if (p.act) x = act4(x, p.slope);
+          if (y2p) st4(y2p + c, x);
+          if (has_res) x = f4add(x, f4scale(g1p ? f4add(ga[i], gb[i]) : ga[i], rs));
+          st4(yp + c, x);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_store_row_direct(const TcArgs& p, const float (&acc)[kTcNH], const TcRow& own, int chb, int ncol) {
+  if (own.kind == 0) return;
+  if (own.kind == 2) {       // dgrad halo row -> side buffer (own.o is its row there)
+    float* sp = p.side + ((long long)own.b * (p.halo_l + p.halo_r) + own.o) * p.side_n + chb;
+#pragma unroll
+    for (int c = 0; c < kTcNH; c += 4)
+      if (c < ncol) st4(sp + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+    return;
+  }
+  float* yp = p.Y + (long long)own.b * p.y_bs + (long long)own.o * p.y_rs + chb;
+  float* y2p = p.Y2 ? p.Y2 + (long long)own.b * p.y2_bs + (long long)own.o * p.y2_rs + chb : nullptr;
+  if (p.Om) {
+    tc_store_row_batches<4>(p, acc, yp, y2p, p.Om + (long long)own.b * p.om_bs + (long long)own.o * p.om_rs + chb, nullptr, 1.f, chb, ncol);
+  } else if (p.res.mode != RES_NONE) {
+    const float* rb = p.res.R + (long long)own.b * p.res.bs + chb;
+    tc_store_row_batches<2>(p, acc, yp, y2p, rb + (long long)own.t0 * p.res.rs, own.t1 >= 0 ? rb + (long long)own.t1 * p.res.rs : nullptr,
+                            own.rs, chb, ncol);
+  } else {
+    tc_store_row_batches<4>(p, acc, yp, y2p, nullptr, nullptr, 1.f, chb, ncol);
+  }
+}
+
 struct TcDrainProf { long long wait, ld, epi; };
 #ifdef AVC_TC_PROFILE
 #define TCD(x) x
 #else
 #define TCD(x)
 #endif
-constexpr int kTcNH = 64;   // accumulator columns per drain thread (half of a 128-column pass; N = 80: 64 + 16)
 __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass& ps, uint32_t tmem_base, uint32_t acc_full0,
                                                    uint32_t acc_empty0, long long v0, int warp, int lane, int& chunk, float* scratch,
                                                    TcDrainProf& dp, int leader_rank = -1) {   // >= 0: acc_empty lives in that CTA of the pair
@@ -473,16 +535,19 @@ __device__ __forceinline__ void tc_drain_and_store(const TcArgs& p, const TcPass
   TCD(dq = clock64();)
   // ---- epilogue: bias / mask / act / residual -> global (overlaps the next tile's MMAs) ----
   const int chb = ps.ch_off + half * NH;
-  tc_acc_to_slab<NH, 0>(acc, scratch, lane);
-  __syncwarp();
-  tc_slab_to_global(p, scratch, lane, own, chb, ncol);
-  if (ncol > 32) {
+  if (kTcDirectEpi) tc_store_row_direct(p, acc, own, chb, ncol);
+  else {
+    tc_acc_to_slab<NH, 0>(acc, scratch, lane);
     __syncwarp();
-    tc_acc_to_slab<NH, 32>(acc, scratch, lane);
+    tc_slab_to_global(p, scratch, lane, own, chb, ncol);
+    if (ncol > 32) {
+      __syncwarp();
+      tc_acc_to_slab<NH, 32>(acc, scratch, lane);
+      __syncwarp();
+      tc_slab_to_global(p, scratch, lane, own, chb + 32, ncol - 32);
+    }
     __syncwarp();
-    tc_slab_to_global(p, scratch, lane, own, chb + 32, ncol - 32);
   }
-  __syncwarp();
   TCD(dp.epi += clock64() - dq;)
 }
 
@@ -899,6 +964,7 @@ inline bool tc_supported(const ConvArgs& a, const TcOp& op) {
   if (tc_stage_count(op) > kTcMaxStages) return false;
   if (a.Y2 && a.bwd) return false;
   if (a.res.mode != RES_NONE && (a.res.rf < 1 || a.res.rf > 2)) return false;   // the epilogue reads at most two skip rows per output row
+  if (a.Om && a.res.mode != RES_NONE) return false;                              // one set of operand registers serves either
   for (int g = 0; g < op.n_groups; ++g)
     if (!op.g[g].Wp || op.g[g].kc % 8 || op.g[g].a_ch_off % 4 || op.g[g].n_taps < 1 || op.g[g].n_taps > kMaxTaps) return false;
   for (int q = 0; q < op.n_pass; ++q)
