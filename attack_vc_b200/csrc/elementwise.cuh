@@ -483,17 +483,12 @@ __device__ __forceinline__ float part_sum(float (*part)[128], int n) {
   return s;
 }
 
-__device__ __forceinline__ void cp16(float* smem_dst, const float* gsrc) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
-}
-
 constexpr int kTailRing = 3;                       // weight matrices in flight (64 KB each)
 constexpr int kTailSmem = kTailRing * 128 * 128 * 4;
 
 // The chain is 13 dependent 128x128 mat-vecs forward and 13 backward for ONE utterance per CTA: pure
-// latency.  The matrices do not depend on the data, so they stream through a 3-deep cp.async ring two
-// layers ahead of the arithmetic.
+// latency.  The matrices do not depend on the data, so they stream through a 3-deep ring of bulk copies two
+// layers ahead of the arithmetic (the first two and the biases before the dependency wait).
 __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
   extern __shared__ __align__(16) float wring[];    // [kTailRing][128*128]
   __shared__ float part[8][128];
@@ -501,6 +496,8 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
   __shared__ float vcur[128];
   __shared__ float gv[128], gt[128];
   __shared__ float lred[4];
+  __shared__ __align__(8) uint64_t tbar[kTailRing];   // "matrix i has landed in ring slot i % kTailRing"
+  __shared__ float bsm[2 * kTailMaxDense + 1][128];   // biases (loop constants): fetched before the dependency wait, not one L2 round trip per layer
   const int tid = threadIdx.x, b = blockIdx.x, n = tid & 127;
   const int nsave = 2 * p.n_dense + 1;
   const int nd = p.n_dense;
@@ -516,19 +513,22 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
     const int l = nd - 1 - ((j - 1) >> 1);
     return ((j - 1) & 1) ? p.W1[l] : p.W2[l];
   };
+  // one elected thread streams each 64 KB matrix with two bulk copies (TMA engine, mbarrier complete_tx): per-thread
+  // cp.async moved a matrix into this one SM in ~3k clk, which was the whole cost of a layer at batch 1
   auto issue = [&](int i) {
-    if (i < n_all) {
+    if (i < n_all && tid == 0) {
       const float* M = mat_at(i);
-      float* dst = wring + (size_t)(i % kTailRing) * 16384;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) cp16(dst + (q * 1024 + tid) * 4, M + (q * 1024 + tid) * 4);
+      const uint32_t bar = smem_u32(&tbar[i % kTailRing]);
+      const uint32_t dst = smem_u32(wring + (size_t)(i % kTailRing) * 16384);
+      mbar_expect_tx(bar, 65536u);
+      bulk_g2s(dst, M, 32768u, bar);
+      bulk_g2s(dst + 32768u, M + 8192, 32768u, bar);
     }
-    asm volatile("cp.async.commit_group;\n" ::);
   };
   int seq = 0;
   // part[g][n] = sum_{c in slice g} M[c*128+n] * vin[c] for the next matrix of the sequence
   auto dense_step = [&](const float* vin) {
-    asm volatile("cp.async.wait_group 1;\n" ::);
+    mbar_wait(smem_u32(&tbar[seq % kTailRing]), (uint32_t)(seq / kTailRing) & 1u);
     __syncthreads();                 // matrix `seq` landed for everyone, vin is visible, matrix seq-1 is no longer read
     issue(seq + 2);
     const float* M = wring + (size_t)(seq % kTailRing) * 16384;
@@ -544,8 +544,25 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
     __syncthreads();
   };
   pdl_launch_dependents();
+  if (tid == 0) {
+    for (int i = 0; i < kTailRing; ++i) mbar_init(smem_u32(&tbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   issue(0);
   issue(1);
+  if ((p.mode & TAIL_FWD) && tid < 128) {
+    float bl[2 * kTailMaxDense + 1];
+#pragma unroll
+    for (int l = 0; l < kTailMaxDense; ++l) {     // all loads in flight before the first store
+      bl[2 * l] = l < p.n_dense ? p.b1[l][n] : 0.f;
+      bl[2 * l + 1] = l < p.n_dense ? p.b2[l][n] : 0.f;
+    }
+    bl[2 * kTailMaxDense] = p.bo[n];
+#pragma unroll
+    for (int i = 0; i < 2 * kTailMaxDense; ++i) bsm[i][n] = bl[i];
+    bsm[2 * p.n_dense][n] = bl[2 * kTailMaxDense];
+  }
   pdl_wait();   // weights are loop constants; everything below reads the predecessor's output
 
   if (p.mode & TAIL_FWD) {
@@ -563,14 +580,14 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
       dense_step(vcur);
       if (tid < 128) {
         acts_b[(nsave + l) * 128 + n] = vcur[n];     // block input v_l (for nothing but completeness)
-        va[1 + 2 * l][n] = actf(part_sum(part, n) + p.b1[l][n], p.slope);
+        va[1 + 2 * l][n] = actf(part_sum(part, n) + bsm[2 * l][n], p.slope);
       }
       dense_step(va[1 + 2 * l]);
-      if (tid < 128) { float y2 = actf(part_sum(part, n) + p.b2[l][n], p.slope); va[2 + 2 * l][n] = y2; vcur[n] = y2 + vcur[n]; }
+      if (tid < 128) { float y2 = actf(part_sum(part, n) + bsm[2 * l + 1][n], p.slope); va[2 + 2 * l][n] = y2; vcur[n] = y2 + vcur[n]; }
     }
     dense_step(vcur);
     if (tid < 128) {
-      gt[n] = part_sum(part, n) + p.bo[n];     // embedding
+      gt[n] = part_sum(part, n) + bsm[2 * p.n_dense][n];     // embedding
       if (p.emb) p.emb[(long long)b * 128 + n] = gt[n];
     }
     if (tid < 128) for (int i = 0; i < nsave; ++i) acts_b[i * 128 + n] = va[i][n];
