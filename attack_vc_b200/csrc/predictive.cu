@@ -132,6 +132,94 @@ __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
   }
 }
 
+// ---- the same convolution as a shared-memory tiled implicit GEMM (Ci % 16 == 0, Cop >= 32) ------------------------
+// M = output pixels, N = Cop, K = taps x Ci.  64 pixels x 64 channels per CTA, 4 x 4 per thread, K in slabs of 16
+// channels of one tap.  For PM_TRANSPOSED the pixels are enumerated by residue class (oh % sh, ow % sw): a class
+// meets only the taps with kh = oh (mod sh), kw = ow (mod sw), so a CTA (one class, blockIdx.z) loops over its valid
+// taps only -- the direct kernel multiplied through the structural zeros of the stride-2 transposed convs (4x).
+constexpr int kPmTM = 64, kPmTN = 64, kPmTK = 16, kPmPitch = 68;
+
+__global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
+  __shared__ __align__(16) float sA[kPmTK][kPmPitch];
+  __shared__ __align__(16) float sW[kPmTK][kPmPitch];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int co0 = blockIdx.y * kPmTN;
+  const bool tr = p.mode == PM_TRANSPOSED;
+  const int csh = tr ? p.sh : 1, csw = tr ? p.sw : 1;
+  const int ph = (int)blockIdx.z / csw, pw = (int)blockIdx.z % csw;      // residue class of this CTA
+  const int Hc = (p.Ho - ph + csh - 1) / csh, Wc = (p.Wo - pw + csw - 1) / csw;
+  const long long npix = (long long)p.B * Hc * Wc;
+  const long long pix0 = (long long)blockIdx.x * kPmTM;
+  if (pix0 >= npix) return;
+  // the pixel this thread LOADS for (tid / 4) and the 4 pixels it ACCUMULATES (4 * ty + q)
+  auto decode = [&](long long pix, int& b, int& oh, int& ow) {
+    if (pix >= npix) { b = -1; oh = ow = 0; return; }
+    const int wq = (int)(pix % Wc);
+    const long long t = pix / Wc;
+    ow = wq * csw + pw; oh = (int)(t % Hc) * csh + ph; b = (int)(t / Hc);
+  };
+  int lb, loh, low;
+  decode(pix0 + (tid >> 2), lb, loh, low);
+  const int lci = (tid & 3) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    if (tr && (kh % csh) != (ph % csh)) continue;                      // (oh - kh) % sh != 0 for the whole class
+    for (int kw = 0; kw < 3; ++kw) {
+      if (tr && (kw % csw) != (pw % csw)) continue;
+      long long xoff = -1;
+      if (lb >= 0) {
+        const int ih = pm_src(loh, kh, p.Hi, p.sh, p.mode), iw = pm_src(low, kw, p.Wi, p.sw, p.mode);
+        if (ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) xoff = (((long long)lb * p.Hi + ih) * p.Wi + iw) * p.Ci;
+      }
+      const float* wt = p.w + (size_t)(kh * 3 + kw) * p.Ci * p.Cop;
+      for (int ci0 = 0; ci0 < p.Ci; ci0 += kPmTK) {
+        const float4 a = xoff >= 0 ? ld4(p.x + xoff + ci0 + lci) : f4zero();
+        const int wr = tid >> 4, wc = (tid & 15) * 4;
+        const float4 w4 = (co0 + wc < p.Cop) ? ld4(wt + (size_t)(ci0 + wr) * p.Cop + co0 + wc) : f4zero();
+        __syncthreads();
+        sA[lci][tid >> 2] = a.x; sA[lci + 1][tid >> 2] = a.y; sA[lci + 2][tid >> 2] = a.z; sA[lci + 3][tid >> 2] = a.w;
+        st4(&sW[wr][wc], w4);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kPmTK; ++kk) {
+          const float4 av = ld4(&sA[kk][ty * 4]), bv = ld4(&sW[kk][tx * 4]);
+          const float aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[q][0] = fmaf(aa[q], bv.x, acc[q][0]); acc[q][1] = fmaf(aa[q], bv.y, acc[q][1]);
+            acc[q][2] = fmaf(aa[q], bv.z, acc[q][2]); acc[q][3] = fmaf(aa[q], bv.w, acc[q][3]);
+          }
+        }
+      }
+    }
+  }
+  const int co = co0 + tx * 4;
+  if (co >= p.Cop) return;
+  const float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
+  const float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int b, oh, ow;
+    decode(pix0 + ty * 4 + q, b, oh, ow);
+    if (b < 0) continue;
+    float v[4] = {fmaf(acc[q][0] + bias.x, sc.x, sf.x), fmaf(acc[q][1] + bias.y, sc.y, sf.y),
+                  fmaf(acc[q][2] + bias.z, sc.z, sf.z), fmaf(acc[q][3] + bias.w, sc.w, sf.w)};
+    const long long o = (((long long)b * p.Ho + oh) * p.Wo + ow) * p.Co + co;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (co + j >= p.Co) continue;
+      float x = v[j];
+      if (p.dmask) x *= p.dmask[o + j] > 0.f ? 1.f : p.mslope;
+      if (p.act) x = x > 0.f ? x : x * p.slope;
+      if (p.act == 2) x = tanhf(x);
+      p.y[o + j] = x;
+    }
+  }
+}
+
 // ---- per-channel reductions over the N = B*H*W pixels of an NHWC tensor --------------------------------
 // stage 1: grid (G, 1); thread = (channel float4 lane, row lane); partial[G][4 quantities][C]
 //   kind 0 (BatchNorm forward): q0 = sum y, q1 = sum y^2
@@ -482,6 +570,16 @@ int pm_guarded(avc_pm_handle* h, Fn&& fn) {
 }
 
 void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
+  static const bool no_tiled = getenv("AVC_PM_NO_TILED") != nullptr;
+  if (!no_tiled && c.Ci % kPmTK == 0 && c.Cop >= 32) {
+    const int csh = c.mode == PM_TRANSPOSED ? c.sh : 1, csw = c.mode == PM_TRANSPOSED ? c.sw : 1;
+    const long long npix = (long long)c.B * ((c.Ho + csh - 1) / csh) * ((c.Wo + csw - 1) / csw);   // the largest class
+    dim3 grid((unsigned)((npix + kPmTM - 1) / kPmTM), (unsigned)((c.Cop + kPmTN - 1) / kPmTN), (unsigned)(csh * csw));
+    pm_conv_tiled_kernel<<<grid, 256, 0, st>>>(c);
+    CK(cudaGetLastError());
+    h->launches++;
+    return;
+  }
   const int lanes = std::min(c.Cop / 4, 32);
   dim3 block(lanes, 256 / lanes);
   const long long npg = (long long)c.B * c.Ho * ((c.Wo + 3) / 4);
