@@ -164,34 +164,51 @@ __global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
   float acc[4][4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
-  for (int kh = 0; kh < 3; ++kh) {
-    if (tr && (kh % csh) != (ph % csh)) continue;                      // (oh - kh) % sh != 0 for the whole class
-    for (int kw = 0; kw < 3; ++kw) {
-      if (tr && (kw % csw) != (pw % csw)) continue;
-      long long xoff = -1;
-      if (lb >= 0) {
-        const int ih = pm_src(loh, kh, p.Hi, p.sh, p.mode), iw = pm_src(low, kw, p.Wi, p.sw, p.mode);
-        if (ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) xoff = (((long long)lb * p.Hi + ih) * p.Wi + iw) * p.Ci;
-      }
-      const float* wt = p.w + (size_t)(kh * 3 + kw) * p.Ci * p.Cop;
-      for (int ci0 = 0; ci0 < p.Ci; ci0 += kPmTK) {
-        const float4 a = xoff >= 0 ? ld4(p.x + xoff + ci0 + lci) : f4zero();
-        const int wr = tid >> 4, wc = (tid & 15) * 4;
-        const float4 w4 = (co0 + wc < p.Cop) ? ld4(wt + (size_t)(ci0 + wr) * p.Cop + co0 + wc) : f4zero();
-        __syncthreads();
-        sA[lci][tid >> 2] = a.x; sA[lci + 1][tid >> 2] = a.y; sA[lci + 2][tid >> 2] = a.z; sA[lci + 3][tid >> 2] = a.w;
-        st4(&sW[wr][wc], w4);
-        __syncthreads();
+  // valid taps of this class as a bit mask; the K slabs (tap, 16 channels) form one sequence whose next slab is
+  // loaded into registers while the current one is multiplied out of shared memory
+  unsigned tmask = 0;
+  for (int t9 = 0; t9 < 9; ++t9)
+    if (!tr || ((t9 / 3) % csh == ph % csh && (t9 % 3) % csw == pw % csw)) tmask |= 1u << t9;   // (oh - kh) % sh == 0 for the whole class
+  const int wr = tid >> 4, wc = (tid & 15) * 4;
+  long long xoff = -1;
+  const float* wt = p.w;
+  auto setup_tap = [&](int t9) {
+    const int kh = t9 / 3, kw = t9 % 3;
+    xoff = -1;
+    if (lb >= 0) {
+      const int ih = pm_src(loh, kh, p.Hi, p.sh, p.mode), iw = pm_src(low, kw, p.Wi, p.sw, p.mode);
+      if (ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) xoff = (((long long)lb * p.Hi + ih) * p.Wi + iw) * p.Ci;
+    }
+    wt = p.w + (size_t)t9 * p.Ci * p.Cop;
+  };
+  int ci0 = 0;
+  float4 a = f4zero(), w4 = f4zero();
+  auto load_slab = [&]() {
+    a = xoff >= 0 ? ld4(p.x + xoff + ci0 + lci) : f4zero();
+    w4 = (co0 + wc < p.Cop) ? ld4(wt + (size_t)(ci0 + wr) * p.Cop + co0 + wc) : f4zero();
+  };
+  bool more = tmask != 0;
+  if (more) { setup_tap(__ffs(tmask) - 1); tmask &= tmask - 1; load_slab(); }
+  while (more) {
+    __syncthreads();
+    sA[lci][tid >> 2] = a.x; sA[lci + 1][tid >> 2] = a.y; sA[lci + 2][tid >> 2] = a.z; sA[lci + 3][tid >> 2] = a.w;
+    st4(&sW[wr][wc], w4);
+    __syncthreads();
+    ci0 += kPmTK;
+    if (ci0 >= p.Ci) {
+      ci0 = 0;
+      more = tmask != 0;
+      if (more) { setup_tap(__ffs(tmask) - 1); tmask &= tmask - 1; }
+    }
+    if (more) load_slab();
 #pragma unroll
-        for (int kk = 0; kk < kPmTK; ++kk) {
-          const float4 av = ld4(&sA[kk][ty * 4]), bv = ld4(&sW[kk][tx * 4]);
-          const float aa[4] = {av.x, av.y, av.z, av.w};
+    for (int kk = 0; kk < kPmTK; ++kk) {
+      const float4 av = ld4(&sA[kk][ty * 4]), bv = ld4(&sW[kk][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[q][0] = fmaf(aa[q], bv.x, acc[q][0]); acc[q][1] = fmaf(aa[q], bv.y, acc[q][1]);
-            acc[q][2] = fmaf(aa[q], bv.z, acc[q][2]); acc[q][3] = fmaf(aa[q], bv.w, acc[q][3]);
-          }
-        }
+      for (int q = 0; q < 4; ++q) {
+        acc[q][0] = fmaf(aa[q], bv.x, acc[q][0]); acc[q][1] = fmaf(aa[q], bv.y, acc[q][1]);
+        acc[q][2] = fmaf(aa[q], bv.z, acc[q][2]); acc[q][3] = fmaf(aa[q], bv.w, acc[q][3]);
       }
     }
   }
@@ -465,9 +482,10 @@ __global__ void __launch_bounds__(256) pm_wgrad_kernel(const PmWgrad p) {
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-  for (long long base = lo; base < hi; base += kWgKC) {
+  float4 av = f4zero(), gv = f4zero();
+  auto load_chunk = [&](long long base) {
     const long long i = base + lk;
-    float4 av = f4zero(), gv = f4zero();
+    av = f4zero(); gv = f4zero();
     if (i < hi) {
       const int wb = (int)(i % p.Wb);
       const long long t = i / p.Wb;
@@ -486,10 +504,14 @@ __global__ void __launch_bounds__(256) pm_wgrad_kernel(const PmWgrad p) {
       if (co0 + lc + 3 < p.Co && (p.Co & 3) == 0) gv = ld4(gp);
       else gv = make_float4(co0 + lc < p.Co ? gp[0] : 0.f, co0 + lc + 1 < p.Co ? gp[1] : 0.f, co0 + lc + 2 < p.Co ? gp[2] : 0.f, co0 + lc + 3 < p.Co ? gp[3] : 0.f);
     }
+  };
+  if (lo < hi) load_chunk(lo);
+  for (long long base = lo; base < hi; base += kWgKC) {
     __syncthreads();                 // the previous chunk has been consumed
     st4(&As[lk][lc], av);
     st4(&Gs[lk][lc], gv);
     __syncthreads();
+    if (base + kWgKC < hi) load_chunk(base + kWgKC);   // the next chunk's loads fly while this one is multiplied
 #pragma unroll
     for (int k = 0; k < kWgKC; ++k) {
       const float4 a4 = ld4(&As[k][ty * 4]), g4 = ld4(&Gs[k][tx * 4]);
