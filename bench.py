@@ -462,6 +462,31 @@ def main():
                 del i2
             except Exception as e:   # a side measurement must never take the headline down
                 extra[name] = {"error": str(e)[:200]}
+        # HBM-bound kernels at a size where the HBM roofline applies (268 MB per tensor, >> L2), through the C-ABI unit
+        # entry points (which synchronise the stream: a few us of host time ride along).  SURVEY §8d bytes per element.
+        try:
+            Bn, Tn, Cn = 2048, 256, 128
+            gen = torch.Generator(device="cpu").manual_seed(0)
+            yn = torch.randn(Bn, Tn, Cn, generator=gen).to(dev); cn = torch.randn(Bn, 2 * Cn, generator=gen).to(dev)
+            gn = torch.randn(Bn, Tn, Cn, generator=gen).to(dev)
+            _, stn = eng.instnorm_adain_act_fwd(yn, cn, None, 1, 0.0)
+
+            def med_ms(fn, reps=9):
+                fn(); ts = []
+                for _ in range(reps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b.record(); torch.cuda.synchronize(dev); ts.append(a.elapsed_time(b))
+                return sorted(ts)[len(ts) // 2]
+            nel = Bn * Tn * Cn
+            for nm, byt, fn in (("norm_fwd", 8, lambda: eng.instnorm_adain_act_fwd(yn, cn, None, 1, 0.0)),
+                                ("norm_fwd_skip", 12, lambda: eng.instnorm_adain_act_fwd(yn, cn, gn, 1, 0.0)),
+                                ("norm_bwd", 12, lambda: eng.instnorm_adain_act_bwd(gn, yn, stn, cn, 0.0))):
+                msn = med_ms(fn)
+                extra[f"{nm}_{Bn}x{Tn}x{Cn}"] = {"ms": msn, "gbs": byt * nel / msn / 1e6, "frac_of_hbm_peak": byt * nel / msn / 1e6 / peaks["hbm_gbs"],
+                                                  "bytes_per_element": byt}
+            del yn, cn, gn, stn
+        except Exception as e:
+            extra["norm_hbm_size"] = {"error": str(e)[:200]}
         line["batched"] = extra
 
     if world == 1 and not args.no_cpu_baseline:
