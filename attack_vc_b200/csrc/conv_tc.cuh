@@ -3,14 +3,16 @@
 // Same contraction as conv_simt.cuh (reference pad_layer + nn.Conv1d, models.py:10-30, and its
 // autograd w.r.t. the input), on the 5th-generation tensor cores:
 //
-//   * precision: 3xTF32 split  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulation in TMEM.
-//     One TF32 pass misses the 1e-3 gradient tolerance by 20x, the split is ~2^-21.
+//   * precision: every value is split a = a_hi + a_lo (a_hi = tf32(a)); per 8 input channels one kind::tf32 MMA
+//     D += A_hi*B_hi and ONE kind::f16 BF16 MMA with K = 16 whose rows are [bf16(a_lo) | bf16(a_hi)] x [bf16(b_hi) ;
+//     bf16(b_lo)], i.e. D += A_lo*B_hi + A_hi*B_lo, fp32 accumulation in TMEM.  One TF32 pass misses the 1e-3 gradient
+//     tolerance by 20x; this split is ~2^-19 per product and measures 5e-7 per conv.
 //   * M axis = "virtual rows": utterances laid end to end with a fixed spacing Pv >= valid rows +
 //     taps - 1, so that a conv tap is a pure row shift of ONE shared-memory window even when a
 //     128-row tile spans several (short) utterances.  Rows past an utterance's valid range are dead.
 //   * A operand: loader warps gather the window from global memory (reflect padding / zero padding
-//     and the optional act' mask by index arithmetic), split every value into its TF32 hi / lo parts
-//     and store both planes in the UMMA "interleaved" (no-swizzle, K-major) canonical layout
+//     and the optional act' mask by index arithmetic), split every value and store the TF32 plane and the
+//     bf16-pair plane in the UMMA "interleaved" (no-swizzle, K-major) canonical layout
 //     [k/4][row][4 floats]: core matrices of consecutive 8-row groups are contiguous (SBO = 128 B),
 //     so tap j is the SAME buffer with the descriptor start address advanced by j*16 bytes.
 //   * B operand: weights pre-split and pre-tiled on the host in exactly the shared-memory image of
@@ -20,9 +22,10 @@
 //     ring slots and signals the drain warps.
 //   * accumulation is CHUNKED: the tensor core accumulates fp32 with truncation, a bias that grows
 //     linearly with the number of MMA steps (measured: -8e-8 relative per K=8 step, 3.3e-6 at K=640).
-//     So every ~20 steps the accumulator (ping-pong halves of TMEM) is handed to eight drain warps,
-//     which add it into fp32 registers with round-to-nearest (tcgen05.ld), and finally apply bias /
+//     So every 12 k-steps (24 MMAs) the accumulator (a ring of four 128-column TMEM buffers) is handed to eight
+//     drain warps, which add it into fp32 registers with round-to-nearest (tcgen05.ld), and finally apply bias /
 //     act' mask / activation / residual exactly like the CUDA-core kernel.
+//   * the (pass, group, K block, tap, chunk) walk is a host-built table in the kernel parameters (TcStage).
 //   * dgrad: the transposed conv is evaluated on the EXTENDED row range [-pl, T+pr); the rows outside
 //     [0,T) (gradient of the reflect padding) go to a small side buffer and `tc_fold_kernel` adds them
 //     to their mirror rows -- no atomics, fixed order.
@@ -102,7 +105,7 @@ struct TcArgs {
   ResArgs res;
   float* side;           // [B][halo_l + halo_r][side_n]
   int n_pass;
-  int terms;             // 3: 3xTF32 (product), 1: single TF32 pass, 4: + lo*lo (both measurement only)
+  int terms;             // >= 2: TF32 hi*hi + BF16 correction MMA (product), 1: single TF32 pass (measurement only)
   int chunk_steps;       // MMA k-steps accumulated in TMEM before the drain warps take the partial sum (env AVC_TC_CHUNK)
   int dbg;               // bottleneck probes (results are garbage): 1 no weight copies, 2 no window gather, 4 no MMA
   TcPass pass[kTcMaxPass];

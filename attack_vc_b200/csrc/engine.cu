@@ -186,7 +186,7 @@ struct avc_handle {
   std::string err;
   long long launches = 0;
   int launches_per_iter = 0;
-  int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only)
+  int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction), 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only)
   long long tc_min_rows = 2048;   // auto: GEMM rows from which the tensor-core kernel is used (env AVC_TC_MIN_ROWS)
 };
 

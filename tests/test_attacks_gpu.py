@@ -176,7 +176,7 @@ def test_session_matches_one_shot(engine, oracle):
 @pytest.mark.parametrize("kind,B,T,n", [("emb", 10, 256, 4), ("fb", 12, 192, 3), ("e2e", 12, 192, 3)])
 def test_tensor_core_plans_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, n):
     """Batches large enough for the tcgen05 route (>= 2048 GEMM rows: every conv of the plan runs on
-    the tensor cores with the 3xTF32 split).  Tolerances as north_star states them: every loss within
+    the tensor cores with the TF32 + BF16-correction split).  Tolerances as north_star states them: every loss within
     1e-3 (measured ~1e-5), gradient within 1e-3 per utterance.  A piecewise-linear network has states
     where one ReLU unit of the 128-wide dense tail sits within rounding distance of zero; there ANY two
     fp32 implementations disagree by ~2e-3 (the reference itself does between 1 and 8 threads,

@@ -163,7 +163,7 @@ TC_CASES = CONV_CASES + [
 @pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3)])
 @pytest.mark.parametrize("B,T,ci,co,k,s", TC_CASES)
 def test_conv1d_fwd_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
-    """tcgen05 path: 3xTF32 with chunked accumulation (impl 2) must be fp32-grade; a single TF32 pass
+    """tcgen05 path: TF32 hi*hi + BF16 correction MMA with chunked accumulation (impl 2) must be fp32-grade; a single TF32 pass
     (impl 4, measurement only) is ~2e-4."""
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k)
     x = torch.randn(B, T, ci, device="cuda", generator=g)
