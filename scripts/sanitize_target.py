@@ -17,3 +17,8 @@ pm = PredictiveEngine({k: v.to(dev) for k, v in pm_make_state_dict(0).items()})
 r = pm.train_step(torch.randn(2, 1, 80, 100, device=dev), want_grad_x=True)
 torch.cuda.synchronize()
 print("pm ok", float(r["loss"]))
+x = torch.randn(3, 70, 128, device=dev); dy = torch.randn(3, 35, 80, device=dev)
+dw, db = eng.conv1d_wgrad(x, dy, 5, stride=2)
+torch.cuda.synchronize()
+print("wgrad ok", bool(torch.isfinite(dw).all()))
+
