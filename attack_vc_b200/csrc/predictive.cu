@@ -137,62 +137,78 @@ __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
 // channels of one tap.  For PM_TRANSPOSED the pixels are enumerated by residue class (oh % sh, ow % sw): a class
 // meets only the taps with kh = oh (mod sh), kw = ow (mod sw), so a CTA (one class, blockIdx.z) loops over its valid
 // taps only -- the direct kernel multiplied through the structural zeros of the stride-2 transposed convs (4x).
-constexpr int kPmTM = 64, kPmTN = 64, kPmTK = 16, kPmPitch = 68;
+constexpr int kPmTK = 16;
 
+// MP x NP outputs per thread, 16 x 16 threads: tile = 16*MP pixels x 16*NP channels (64 x 64, 128 x 64 or 128 x 128)
+template <int MP, int NP>
 __global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
-  __shared__ __align__(16) float sA[kPmTK][kPmPitch];
-  __shared__ __align__(16) float sW[kPmTK][kPmPitch];
+  constexpr int TM = 16 * MP, TN = 16 * NP, LA = TM / 64, LW = TN / 64;   // float4 loads per thread and slab
+  __shared__ __align__(16) float sA[kPmTK][TM + 4];
+  __shared__ __align__(16) float sW[kPmTK][TN + 4];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int co0 = blockIdx.y * kPmTN;
+  const int co0 = blockIdx.y * TN;
   const bool tr = p.mode == PM_TRANSPOSED;
   const int csh = tr ? p.sh : 1, csw = tr ? p.sw : 1;
   const int ph = (int)blockIdx.z / csw, pw = (int)blockIdx.z % csw;      // residue class of this CTA
   const int Hc = (p.Ho - ph + csh - 1) / csh, Wc = (p.Wo - pw + csw - 1) / csw;
   const long long npix = (long long)p.B * Hc * Wc;
-  const long long pix0 = (long long)blockIdx.x * kPmTM;
+  const long long pix0 = (long long)blockIdx.x * TM;
   if (pix0 >= npix) return;
-  // the pixel this thread LOADS for (tid / 4) and the 4 pixels it ACCUMULATES (4 * ty + q)
   auto decode = [&](long long pix, int& b, int& oh, int& ow) {
     if (pix >= npix) { b = -1; oh = ow = 0; return; }
     const int wq = (int)(pix % Wc);
     const long long t = pix / Wc;
     ow = wq * csw + pw; oh = (int)(t % Hc) * csh + ph; b = (int)(t / Hc);
   };
-  int lb, loh, low;
-  decode(pix0 + (tid >> 2), lb, loh, low);
-  const int lci = (tid & 3) * 4;
-  float acc[4][4];
+  // the pixels this thread LOADS: (tid / 4) + 64 * j; the pixels it ACCUMULATES: MP * ty + q
+  int lb[LA], loh[LA], low[LA];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+  for (int j = 0; j < LA; ++j) decode(pix0 + (tid >> 2) + 64 * j, lb[j], loh[j], low[j]);
+  const int lci = (tid & 3) * 4;
+  float acc[MP][NP];
+#pragma unroll
+  for (int q = 0; q < MP; ++q)
+#pragma unroll
+    for (int r = 0; r < NP; ++r) acc[q][r] = 0.f;
   // valid taps of this class as a bit mask; the K slabs (tap, 16 channels) form one sequence whose next slab is
   // loaded into registers while the current one is multiplied out of shared memory
   unsigned tmask = 0;
   for (int t9 = 0; t9 < 9; ++t9)
     if (!tr || ((t9 / 3) % csh == ph % csh && (t9 % 3) % csw == pw % csw)) tmask |= 1u << t9;   // (oh - kh) % sh == 0 for the whole class
   const int wr = tid >> 4, wc = (tid & 15) * 4;
-  long long xoff = -1;
+  long long xoff[LA];
   const float* wt = p.w;
   auto setup_tap = [&](int t9) {
     const int kh = t9 / 3, kw = t9 % 3;
-    xoff = -1;
-    if (lb >= 0) {
-      const int ih = pm_src(loh, kh, p.Hi, p.sh, p.mode), iw = pm_src(low, kw, p.Wi, p.sw, p.mode);
-      if (ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) xoff = (((long long)lb * p.Hi + ih) * p.Wi + iw) * p.Ci;
+#pragma unroll
+    for (int j = 0; j < LA; ++j) {
+      xoff[j] = -1;
+      if (lb[j] >= 0) {
+        const int ih = pm_src(loh[j], kh, p.Hi, p.sh, p.mode), iw = pm_src(low[j], kw, p.Wi, p.sw, p.mode);
+        if (ih >= 0 && ih < p.Hi && iw >= 0 && iw < p.Wi) xoff[j] = (((long long)lb[j] * p.Hi + ih) * p.Wi + iw) * p.Ci;
+      }
     }
     wt = p.w + (size_t)t9 * p.Ci * p.Cop;
   };
   int ci0 = 0;
-  float4 a = f4zero(), w4 = f4zero();
+  float4 a[LA], w4[LW];
   auto load_slab = [&]() {
-    a = xoff >= 0 ? ld4(p.x + xoff + ci0 + lci) : f4zero();
-    w4 = (co0 + wc < p.Cop) ? ld4(wt + (size_t)(ci0 + wr) * p.Cop + co0 + wc) : f4zero();
+#pragma unroll
+    for (int j = 0; j < LA; ++j) a[j] = xoff[j] >= 0 ? ld4(p.x + xoff[j] + ci0 + lci) : f4zero();
+#pragma unroll
+    for (int j = 0; j < LW; ++j) w4[j] = (co0 + wc + 64 * j < p.Cop) ? ld4(wt + (size_t)(ci0 + wr) * p.Cop + co0 + wc + 64 * j) : f4zero();
   };
   bool more = tmask != 0;
   if (more) { setup_tap(__ffs(tmask) - 1); tmask &= tmask - 1; load_slab(); }
   while (more) {
     __syncthreads();
-    sA[lci][tid >> 2] = a.x; sA[lci + 1][tid >> 2] = a.y; sA[lci + 2][tid >> 2] = a.z; sA[lci + 3][tid >> 2] = a.w;
-    st4(&sW[wr][wc], w4);
+#pragma unroll
+    for (int j = 0; j < LA; ++j) {
+      const int px = (tid >> 2) + 64 * j;
+      sA[lci][px] = a[j].x; sA[lci + 1][px] = a[j].y; sA[lci + 2][px] = a[j].z; sA[lci + 3][px] = a[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < LW; ++j) st4(&sW[wr][wc + 64 * j], w4[j]);
     __syncthreads();
     ci0 += kPmTK;
     if (ci0 >= p.Ci) {
@@ -203,36 +219,41 @@ __global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
     if (more) load_slab();
 #pragma unroll
     for (int kk = 0; kk < kPmTK; ++kk) {
-      const float4 av = ld4(&sA[kk][ty * 4]), bv = ld4(&sW[kk][tx * 4]);
-      const float aa[4] = {av.x, av.y, av.z, av.w};
+      float aa[MP], bb[NP];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        acc[q][0] = fmaf(aa[q], bv.x, acc[q][0]); acc[q][1] = fmaf(aa[q], bv.y, acc[q][1]);
-        acc[q][2] = fmaf(aa[q], bv.z, acc[q][2]); acc[q][3] = fmaf(aa[q], bv.w, acc[q][3]);
-      }
+      for (int q = 0; q < MP; q += 4) { const float4 v = ld4(&sA[kk][ty * MP + q]); aa[q] = v.x; aa[q + 1] = v.y; aa[q + 2] = v.z; aa[q + 3] = v.w; }
+#pragma unroll
+      for (int r = 0; r < NP; r += 4) { const float4 v = ld4(&sW[kk][tx * NP + r]); bb[r] = v.x; bb[r + 1] = v.y; bb[r + 2] = v.z; bb[r + 3] = v.w; }
+#pragma unroll
+      for (int q = 0; q < MP; ++q)
+#pragma unroll
+        for (int r = 0; r < NP; ++r) acc[q][r] = fmaf(aa[q], bb[r], acc[q][r]);
     }
   }
-  const int co = co0 + tx * 4;
-  if (co >= p.Cop) return;
-  const float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
-  const float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
-  const float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    int b, oh, ow;
-    decode(pix0 + ty * 4 + q, b, oh, ow);
-    if (b < 0) continue;
-    float v[4] = {fmaf(acc[q][0] + bias.x, sc.x, sf.x), fmaf(acc[q][1] + bias.y, sc.y, sf.y),
-                  fmaf(acc[q][2] + bias.z, sc.z, sf.z), fmaf(acc[q][3] + bias.w, sc.w, sf.w)};
-    const long long o = (((long long)b * p.Ho + oh) * p.Wo + ow) * p.Co + co;
+  for (int r0 = 0; r0 < NP; r0 += 4) {
+    const int co = co0 + tx * NP + r0;
+    if (co >= p.Cop) continue;
+    const float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
+    const float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (co + j >= p.Co) continue;
-      float x = v[j];
-      if (p.dmask) x *= p.dmask[o + j] > 0.f ? 1.f : p.mslope;
-      if (p.act) x = x > 0.f ? x : x * p.slope;
-      if (p.act == 2) x = tanhf(x);
-      p.y[o + j] = x;
+    for (int q = 0; q < MP; ++q) {
+      int b, oh, ow;
+      decode(pix0 + ty * MP + q, b, oh, ow);
+      if (b < 0) continue;
+      float v[4] = {fmaf(acc[q][r0] + bias.x, sc.x, sf.x), fmaf(acc[q][r0 + 1] + bias.y, sc.y, sf.y),
+                    fmaf(acc[q][r0 + 2] + bias.z, sc.z, sf.z), fmaf(acc[q][r0 + 3] + bias.w, sc.w, sf.w)};
+      const long long o = (((long long)b * p.Ho + oh) * p.Wo + ow) * p.Co + co;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (co + j >= p.Co) continue;
+        float x = v[j];
+        if (p.dmask) x *= p.dmask[o + j] > 0.f ? 1.f : p.mslope;
+        if (p.act) x = x > 0.f ? x : x * p.slope;
+        if (p.act == 2) x = tanhf(x);
+        p.y[o + j] = x;
+      }
     }
   }
 }
@@ -596,8 +617,21 @@ void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
   if (!no_tiled && c.Ci % kPmTK == 0 && c.Cop >= 32) {
     const int csh = c.mode == PM_TRANSPOSED ? c.sh : 1, csw = c.mode == PM_TRANSPOSED ? c.sw : 1;
     const long long npix = (long long)c.B * ((c.Ho + csh - 1) / csh) * ((c.Wo + csw - 1) / csw);   // the largest class
-    dim3 grid((unsigned)((npix + kPmTM - 1) / kPmTM), (unsigned)((c.Cop + kPmTN - 1) / kPmTN), (unsigned)(csh * csw));
-    pm_conv_tiled_kernel<<<grid, 256, 0, st>>>(c);
+    static const int force = getenv("AVC_PM_TILE") ? atoi(getenv("AVC_PM_TILE")) : 0;   // 1: 64x64, 2: 128x64, 3: 128x128
+    auto ctas = [&](int TM, int TN) { return ((npix + TM - 1) / TM) * ((c.Cop + TN - 1) / TN) * csh * csw; };
+    // the largest tile that still fills the machine about twice
+    int tile = c.Cop >= 128 && ctas(128, 128) >= 2LL * h->sm_count ? 3 : ctas(128, 64) >= 2LL * h->sm_count ? 2 : 1;
+    if (force) tile = force;
+    if (tile == 3) {
+      dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((c.Cop + 127) / 128), (unsigned)(csh * csw));
+      pm_conv_tiled_kernel<8, 8><<<grid, 256, 0, st>>>(c);
+    } else if (tile == 2) {
+      dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((c.Cop + 63) / 64), (unsigned)(csh * csw));
+      pm_conv_tiled_kernel<8, 4><<<grid, 256, 0, st>>>(c);
+    } else {
+      dim3 grid((unsigned)((npix + 63) / 64), (unsigned)((c.Cop + 63) / 64), (unsigned)(csh * csw));
+      pm_conv_tiled_kernel<4, 4><<<grid, 256, 0, st>>>(c);
+    }
     CK(cudaGetLastError());
     h->launches++;
     return;
