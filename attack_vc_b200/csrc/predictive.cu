@@ -928,7 +928,8 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
       q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
       const long long N = (long long)B * Hb * Wb;
       const int tiles = 9 * ((Ci + kWgT - 1) / kWgT) * ((q.Cop + kWgT - 1) / kWgT);
-      const int S = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, (2LL * h->sm_count + tiles - 1) / tiles), N / (4 * kWgKC) + 1));
+      static const int oversub = getenv("AVC_PM_WG_CTAS") ? atoi(getenv("AVC_PM_WG_CTAS")) : 8;   // pixel-axis slices: CTAs per SM aimed at
+      const int S = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, ((long long)oversub * h->sm_count + tiles - 1) / tiles), N / (4 * kWgKC) + 1));
       q.partial = mem.f((size_t)S * 9 * Ci * q.Cop);
       dim3 grid(S, (Ci + kWgT - 1) / kWgT, 9 * ((q.Cop + kWgT - 1) / kWgT));
       pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
