@@ -94,14 +94,15 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
   } else {
     float4 sum = f4zero();
     int t = lane_t;
-    for (; t + 3 * kNormTL < p.T; t += 4 * kNormTL) {      // four independent 16-byte loads in flight per thread
-      const float4 v0 = ld4(yb + (long long)t * p.C), v1 = ld4(yb + (long long)(t + kNormTL) * p.C);
-      const float4 v2 = ld4(yb + (long long)(t + 2 * kNormTL) * p.C), v3 = ld4(yb + (long long)(t + 3 * kNormTL) * p.C);
-      if (staged) {
-        ntile[t * 8 + lane_c] = v0; ntile[(t + kNormTL) * 8 + lane_c] = v1;
-        ntile[(t + 2 * kNormTL) * 8 + lane_c] = v2; ntile[(t + 3 * kNormTL) * 8 + lane_c] = v3;
+    for (; t + 7 * kNormTL < p.T; t += 8 * kNormTL) {      // eight independent 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ld4(yb + (long long)(t + j * kNormTL) * p.C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (staged) ntile[(t + j * kNormTL) * 8 + lane_c] = v[j];
+        sum = f4add(sum, v[j]);
       }
-      sum = f4add(f4add(sum, v0), f4add(v1, f4add(v2, v3)));
     }
     for (; t < p.T; t += kNormTL) {
       const float4 v = ld4(yb + (long long)t * p.C);
