@@ -636,6 +636,170 @@ __global__ void __launch_bounds__(1024) se_tail_kernel(const TailArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same tail for SMALL batches (B * 8 <= SMs): one CLUSTER of 8 CTAs per utterance.  At batch 1 the kernel above is
+// one SM pulling 13-26 matrices of 64 KB through its L2 port (~12 us net per launch).  Here CTA r of the cluster owns rows
+// [16r, 16r+16) of every matrix (8 KB, contiguous in both the forward [c][n] and the backward [n][c] images: the split
+// is over the CONTRACTION index either way), keeps all its slices resident in shared memory (one bulk-copy burst before
+// the dependency wait), multiplies its 16 inputs into a 128-wide partial vector, and the partials are reduce-scattered
+// through distributed shared memory: thread n stores its partial into CTA n/16, which sums the 8 partials of its 16
+// outputs in CTA order -- the same 8 x 16 summation tree as se_tail_kernel, so the results are bit-identical.
+// One cluster barrier per layer; the receive buffer is double-buffered.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTclN = 8, kTclS = 16;                 // CTAs per utterance, vector elements per CTA
+constexpr int kTclMatBytes = kTclS * 128 * 4;        // one matrix slice
+__device__ __forceinline__ void st_cluster_f32(float* local, uint32_t rank, float v) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}"
+               ::"r"(smem_u32(local)), "r"(rank), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128) se_tail_cluster_kernel(const TailArgs p) {
+  extern __shared__ __align__(16) float wsl[];          // [n_all][16][128] this CTA's matrix slices
+  __shared__ float recv[2][kTclN][kTclS];
+  __shared__ float va[2 * kTailMaxDense + 2][kTclS];
+  __shared__ float bsm[2 * kTailMaxDense + 1][kTclS];
+  __shared__ float vcur[kTclS], gv[kTclS], gt[kTclS];
+  __shared__ float red[8][kTclS];
+  __shared__ float lossbuf[kTclN];
+  __shared__ __align__(8) uint64_t wbar;
+  const int tid = threadIdx.x, j = tid & 15;
+  const uint32_t r = cluster_ctarank();
+  const int b = blockIdx.x / kTclN;
+  const int nd = p.n_dense, nsave = 2 * nd + 1;
+  const int c0 = (int)r * kTclS;                        // my slice of every 128-vector
+  float* acts_b = p.acts + (long long)b * (nsave + nd) * 128;
+  const int n_fwd = (p.mode & TAIL_FWD) ? 2 * nd + 1 : 0;
+  const int n_all = n_fwd + ((p.mode & TAIL_BWD) ? 2 * nd + 1 : 0);
+  auto mat_at = [&](int i) -> const float* {
+    if (i < n_fwd) return i == 2 * nd ? p.Wto : ((i & 1) ? p.Wt2[i >> 1] : p.Wt1[i >> 1]);
+    const int q = i - n_fwd;
+    if (q == 0) return p.Wo;
+    const int l = nd - 1 - ((q - 1) >> 1);
+    return ((q - 1) & 1) ? p.W1[l] : p.W2[l];
+  };
+  pdl_launch_dependents();
+  if (tid == 0) {
+    mbar_init(smem_u32(&wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(smem_u32(&wbar), (uint32_t)n_all * kTclMatBytes);
+    for (int i = 0; i < n_all; ++i)
+      bulk_g2s(smem_u32(wsl + (size_t)i * kTclS * 128), mat_at(i) + (size_t)c0 * 128, kTclMatBytes, smem_u32(&wbar));
+  }
+  if ((p.mode & TAIL_FWD) && tid < kTclS) {
+    float bl[2 * kTailMaxDense + 1];
+#pragma unroll
+    for (int l = 0; l < kTailMaxDense; ++l) {     // all loads in flight before the first store
+      bl[2 * l] = l < nd ? p.b1[l][c0 + j] : 0.f;
+      bl[2 * l + 1] = l < nd ? p.b2[l][c0 + j] : 0.f;
+    }
+    bl[2 * kTailMaxDense] = p.bo[c0 + j];
+#pragma unroll
+    for (int i = 0; i < 2 * kTailMaxDense; ++i) bsm[i][j] = bl[i];
+    bsm[2 * nd][j] = bl[2 * kTailMaxDense];
+  }
+  cluster_sync_all();      // every CTA of the cluster is running (its shared memory may be written) and the barrier is initialised
+  pdl_wait();              // weights and biases are loop constants; everything below reads the predecessor's output
+  mbar_wait(smem_u32(&wbar), 0);
+  int seq = 0, buf = 0;
+  // out[n] (n in my slice, returned to threads tid < 16) = sum_c M[c][n] vin[c]: my 16 rows times my 16 inputs -> a
+  // 128-wide partial, element n stored into CTA n/16; after the cluster barrier the 8 partials are summed in CTA order
+  auto dense_step = [&](const float* vin) -> float {
+    const float* M = wsl + (size_t)seq * kTclS * 128;
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < kTclS; ++q) a = fmaf(M[q * 128 + tid], vin[q], a);
+    st_cluster_f32(&recv[buf][r][tid & 15], (uint32_t)(tid >> 4), a);
+    cluster_sync_all();
+    float y = 0.f;
+    if (tid < kTclS) {
+#pragma unroll
+      for (int g = 0; g < kTclN; ++g) y += recv[buf][g][j];
+    }
+    ++seq; buf ^= 1;
+    return y;
+  };
+
+  if (p.mode & TAIL_FWD) {
+    {   // global average pool over time of my 16 channels (8 time lanes, summed in lane order)
+      const int g = tid >> 4;
+      float a = 0.f;
+      const float* hb = p.h + (long long)b * p.h_bs + c0 + j;
+      for (int t = g; t < p.T_h; t += 8) a += hb[(long long)t * p.h_rs];
+      red[g][j] = a;
+      __syncthreads();
+      if (tid < kTclS) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int g2 = 0; g2 < 8; ++g2) s2 += red[g2][j];
+        vcur[j] = s2 / (float)p.T_h; va[0][j] = vcur[j];
+      }
+      __syncthreads();
+    }
+    for (int l = 0; l < nd; ++l) {
+      float y = dense_step(vcur);
+      if (tid < kTclS) {
+        acts_b[(nsave + l) * 128 + c0 + j] = vcur[j];
+        va[1 + 2 * l][j] = actf(y + bsm[2 * l][j], p.slope);
+      }
+      __syncthreads();
+      y = dense_step(va[1 + 2 * l]);
+      if (tid < kTclS) { const float y2 = actf(y + bsm[2 * l + 1][j], p.slope); va[2 + 2 * l][j] = y2; vcur[j] = y2 + vcur[j]; }
+      __syncthreads();
+    }
+    const float y = dense_step(vcur);
+    if (tid < kTclS) {
+      gt[j] = y + bsm[2 * nd][j];     // embedding
+      if (p.emb) p.emb[(long long)b * 128 + c0 + j] = gt[j];
+      for (int i = 0; i < nsave; ++i) acts_b[i * 128 + c0 + j] = va[i][j];
+    }
+    __syncthreads();
+  } else {
+    if (tid < kTclS) for (int i = 0; i < nsave; ++i) va[i][j] = acts_b[i * 128 + c0 + j];
+    __syncthreads();
+  }
+  if (p.mode & TAIL_BWD) {
+    // ---- d emb ----
+    if (p.mode & TAIL_LOSS) {
+      float lp = 0.f;
+      if (tid < kTclS) {
+        const float e = gt[j], d = e - p.tgt[(long long)b * 128 + c0 + j], o = e - p.org[(long long)b * 128 + c0 + j];
+        lp = d * d - p.lam * (o * o);
+        gv[j] = 2.f * p.inv_norm * (d - p.lam * o);
+      }
+      if (tid < 32) {
+        lp = warp_sum(lp);
+        if (tid == 0) st_cluster_f32(&lossbuf[r], 0u, lp);     // summed by CTA 0 after the next cluster barrier
+      }
+    } else if (tid < kTclS) {
+      float s2 = 0.f;
+      for (int q = 0; q < p.gemb_parts; ++q) s2 += p.gemb[((long long)b * p.gemb_parts + q) * 128 + c0 + j];
+      gv[j] = s2;
+    }
+    __syncthreads();
+    // ---- output layer: g_v = Wo^T g_emb (contraction over the rows of Wo: my slice of g_emb times my rows) ----
+    float y = dense_step(gv);
+    if ((p.mode & TAIL_LOSS) && r == 0 && tid == 0 && p.loss_parts) {
+      float s2 = 0.f;
+      for (int g = 0; g < kTclN; ++g) s2 += lossbuf[g];
+      p.loss_parts[(long long)(*p.step) * p.parts_per_step + b] = s2 * p.inv_norm;
+    }
+    if (tid < kTclS) gv[j] = y;
+    for (int l = nd - 1; l >= 0; --l) {
+      __syncthreads();
+      if (tid < kTclS) gt[j] = gv[j] * dactf(va[2 + 2 * l][j], p.slope);     // d pre-act 2
+      __syncthreads();
+      y = dense_step(gt);
+      if (tid < kTclS) gt[j] = y * dactf(va[1 + 2 * l][j], p.slope);          // d pre-act 1
+      __syncthreads();
+      y = dense_step(gt);
+      if (tid < kTclS) gv[j] = gv[j] + y;
+    }
+    __syncthreads();
+    if (tid < kTclS) p.gpool[(long long)b * 128 + c0 + j] = gv[j] / (float)p.T_h;
+  }
+  cluster_sync_all();      // nobody leaves while a peer may still store into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------
 // AdaIN affine layers: cond_l = Linear_l(emb), l < 2*n_blocks  (models.py:397-399, 420, 427)
 // forward grid (B, L): 256 outputs per CTA.  backward grid (B, L): partial d emb per layer, summed
 // (fixed order) by the tail kernel.

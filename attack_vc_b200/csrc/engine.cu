@@ -44,14 +44,14 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
   CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
-// the same as a grid of 2-CTA clusters (CTA pairs on one TPC: the tcgen05 cta_group::2 kernel)
+// the same as a grid of clusters of `csize` CTAs (2: CTA pairs on one TPC for the tcgen05 cta_group::2 kernel)
 template <class... KArgs, class... Args>
-void launch_k_pair(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+void launch_k_cluster(unsigned csize, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
@@ -220,6 +220,7 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(conv_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
+  CK(cudaFuncSetAttribute(se_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * kTailMaxDense + 1) * kTclMatBytes > (int)kSmemMax - 4096 ? (int)kSmemMax - 4096 : 2 * (2 * kTailMaxDense + 1) * kTclMatBytes));
   CK(cudaFuncSetAttribute(norm_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(norm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -363,7 +364,7 @@ void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st) {
   if (pair_env && n_mt >= 2) {   // CTA pairs: two M tiles of one pass per cluster, persistent over (tile pair, pass) items
     const long long work = ((n_mt + 1) / 2) * t.n_pass;
     dim3 grid(2u * (unsigned)std::min<long long>(work, sm_count / 2), 1, 1);
-    launch_k_pair(conv_tc_kernel_t<true>, grid, kTcThreads, smem, st, t);
+    launch_k_cluster(2, conv_tc_kernel_t<true>, grid, kTcThreads, smem, st, t);
     return;
   }
   const long long work = n_mt * t.n_pass;
@@ -644,7 +645,15 @@ TailArgs tail_args(const EncoderW& W, const EncActs& A) {
 }
 
 void emit_tail(Emitter& E, const TailArgs& t, int B) {
-  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B](cudaStream_t st) { launch_k(se_tail_kernel, B, 1024, kTailSmem, st, t); });
+  // small batches: a cluster of 8 CTAs per utterance with the matrix slices resident (se_tail_cluster_kernel)
+  const int n_mats = (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0));
+  const size_t csm = (size_t)n_mats * kTclMatBytes;
+  static const bool no_cluster = getenv("AVC_NO_TAIL_CLUSTER") != nullptr;
+  const bool cluster = !no_cluster && B * kTclN <= E.h->sm_count && csm + 4096 <= kSmemMax;
+  E.push(LK_TAIL, 2.0 * B * 128 * 128 * (2 * t.n_dense + 1) * (((t.mode & TAIL_FWD) ? 1 : 0) + ((t.mode & TAIL_BWD) ? 1 : 0)), 0, [t, B, cluster, csm](cudaStream_t st) {
+    if (cluster) launch_k_cluster(kTclN, se_tail_cluster_kernel, B * kTclN, 128, csm, st, t);
+    else launch_k(se_tail_kernel, B, 1024, kTailSmem, st, t);
+  });
 }
 
 // speaker-encoder backward from gpool ([B,128], gradient of every pooled row) down to d input
