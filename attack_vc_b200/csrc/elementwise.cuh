@@ -837,16 +837,20 @@ __global__ void __launch_bounds__(1024) affine_fwd_kernel(const AffineArgs p) {
 }
 
 __global__ void __launch_bounds__(1024) affine_bwd_kernel(const AffineArgs p) {
-  pdl_enter();
   __shared__ float gc[256];
   __shared__ float part[8][128];
   const int b = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, c = tid & 127, g = tid >> 7;
+  pdl_launch_dependents();
+  const float* M = p.W[l];   // [n][c]
+  float wv[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) wv[q] = M[(g * 32 + q) * 128 + c];   // loop constants: fetched before the dependency wait
+  pdl_wait();
   if (tid < 256) gc[tid] = p.gcond[((long long)b * p.L + l) * 256 + tid];
   __syncthreads();
-  const float* M = p.W[l];   // [n][c]
   float a = 0.f;
-#pragma unroll 8
-  for (int q = 0; q < 32; ++q) { const int nn = g * 32 + q; a = fmaf(M[nn * 128 + c], gc[nn], a); }
+#pragma unroll
+  for (int q = 0; q < 32; ++q) a = fmaf(wv[q], gc[g * 32 + q], a);
   part[g][c] = a;
   __syncthreads();
   if (tid < 128) {
