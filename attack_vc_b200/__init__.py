@@ -4,6 +4,6 @@ Only the hot path lives here: ``csrc/`` (CUDA kernels + the C-ABI of include/avc
 host-side mirror of the reference's attack interface (``engine.Engine``; the drop-in module is the
 top-level ``attack_utils.py``).  Importing this package never falls back to PyTorch math: if
 ``libavc_b200.so`` is missing, using it raises."""
-from .engine import AvcError, Engine, engine_for  # noqa: F401
+from .engine import AvcError, Engine, engine_for, invalidate_engine  # noqa: F401
 
-__all__ = ["Engine", "AvcError", "engine_for"]
+__all__ = ["Engine", "AvcError", "engine_for", "invalidate_engine"]

@@ -80,6 +80,13 @@ def load() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m attack_vc_b200.build` "
             "(attack_vc_b200 has no CPU or PyTorch fallback)")
+    if not os.environ.get("AVC_LIB") and (_HERE / "csrc").is_dir():
+        # the binary must be the one these sources build (content hash baked into avc_version()): rebuild, or fail loudly
+        from . import build as _build
+        if _build.built_hash(LIB_PATH) != _build.source_hash():
+            _build.build_library(force=True)
+            if _build.built_hash(LIB_PATH) != _build.source_hash():
+                raise RuntimeError(f"{LIB_PATH} was not built from the sources in {_HERE / 'csrc'} and could not be rebuilt")
     lib = C.CDLL(str(LIB_PATH))
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     P = C.POINTER

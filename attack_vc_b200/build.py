@@ -19,16 +19,38 @@ NVCC_FLAGS = [
 ]
 
 
+VERSION_PREFIX = b"avc_b200 0.2 (sm_100a) src "
+
+
 def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
+def source_hash() -> str:
+    """sha256 over every file the library is compiled from (names + bytes) and the compiler flags."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))) + [HERE.parent / "include" / "avc_b200.h"]
+    for d in deps:
+        h.update(d.name.encode() + b"\0" + d.read_bytes() + b"\0")
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("AVC_NVCC_EXTRA", "").split()).encode())
+    return h.hexdigest()[:16]
+
+
+def built_hash(lib: Path = LIB):
+    """The source hash baked into a built library (the tail of avc_version()), read from its bytes: no dlopen."""
+    if not lib.exists():
+        return None
+    data = lib.read_bytes()
+    i = data.find(VERSION_PREFIX)
+    if i < 0:
+        return None
+    return data[i + len(VERSION_PREFIX): i + len(VERSION_PREFIX) + 16].decode(errors="replace")
+
+
 def _stale() -> bool:
-    if not LIB.exists():
-        return True
-    t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "avc_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    # content, not mtime: a checkout that reorders timestamps must not leave a stale binary in use
+    return built_hash() != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
@@ -39,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libavc_b200.so cannot be built and there is no CPU fallback")
     extra = os.environ.get("AVC_NVCC_EXTRA", "").split()      # experiments only (e.g. -DAVC_SMALL_MINB=2)
-    cmd = [nvcc, *NVCC_FLAGS, *extra, *map(str, sources()), "-o", str(LIB)]
+    cmd = [nvcc, *NVCC_FLAGS, *extra, f'-DAVC_SRC_HASH="{source_hash()}"', *map(str, sources()), "-o", str(LIB)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -146,9 +146,43 @@ struct Launch {
 
 constexpr int kUnroll = 16;
 
+// Caller tensors of one attack call.  Setup / finish launches read them through the plan at LAUNCH time, so a cached
+// plan (same shapes, eps, normaliser) is rebound to the next call's tensors without rebuilding or re-capturing.
+struct IoBind {
+  const float* vc_tgt = nullptr;  int64_t tgt_stride[3] = {0, 0, 0};
+  const float* adv_tgt = nullptr; int64_t adv_stride[3] = {0, 0, 0};
+  const float* vc_src = nullptr;  int64_t src_stride[3] = {0, 0, 0};
+  const float* w0 = nullptr;      int64_t w0_stride[3] = {0, 0, 0};
+  float* adv_out = nullptr;       int64_t out_stride[3] = {0, 0, 0};
+  float* loss_out = nullptr;
+  float* grad_out = nullptr;
+  int n_iters = 0;                 // iterations of THIS call (<= Plan::n_iters, the provisioned capacity)
+  void bind(const avc_attack_args& a) {
+    vc_tgt = a.vc_tgt; adv_tgt = a.adv_tgt; vc_src = a.vc_src; w0 = a.w0; adv_out = a.adv_out;
+    loss_out = a.loss_out; grad_out = a.grad_out; n_iters = a.n_iters;
+    for (int i = 0; i < 3; ++i) {
+      tgt_stride[i] = a.tgt_stride[i]; adv_stride[i] = a.adv_stride[i]; src_stride[i] = a.src_stride[i];
+      w0_stride[i] = a.w0_stride[i]; out_stride[i] = a.out_stride[i];
+    }
+  }
+};
+
+struct PlanKey {
+  int kind = -1, B = 0, T_tgt = 0, T_adv = 0, T_src = 0, use_graph = 0, has_grad = 0, conv_impl = 0;
+  long long tc_min_rows = 0;
+  float eps = 0.f;
+  double inv_norm = 0.0;
+  bool operator==(const PlanKey& o) const {
+    return kind == o.kind && B == o.B && T_tgt == o.T_tgt && T_adv == o.T_adv && T_src == o.T_src && use_graph == o.use_graph &&
+           has_grad == o.has_grad && conv_impl == o.conv_impl && tc_min_rows == o.tc_min_rows && eps == o.eps && inv_norm == o.inv_norm;
+  }
+};
+
 struct Plan {
   Arena mem;
-  explicit Plan(SlabPool* pool = nullptr) : mem(pool) {}
+  IoBind io;
+  PlanKey key;
+  Plan(SlabPool* pool, cudaStream_t st) : mem(pool, st) {}
   std::vector<Launch> setup;    // once per attack call (targets, loop invariants)
   std::vector<Launch> iter;     // one attack iteration
   std::vector<Launch> iter2;    // header optimisation only: the apply half of an iteration (after the gradient all-reduce)
@@ -188,6 +222,10 @@ struct avc_handle {
   int launches_per_iter = 0;
   int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction), 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only)
   long long tc_min_rows = 2048;   // auto: GEMM rows from which the tensor-core kernel is used (env AVC_TC_MIN_ROWS)
+  // Finished attack plans (buffers, launch lists, instantiated graphs) kept for the next call of the same shape: building
+  // and capturing a plan costs ~1 ms, as much as a few iterations at batch 1.  Small plans only, a handful of them.
+  std::vector<std::unique_ptr<Plan>> plan_cache;
+  long long plan_cache_hits = 0;
 };
 
 struct avc_session {
@@ -543,10 +581,11 @@ EncActs alloc_encoder(Arena& m, const EncoderW& W, int B, int T, bool need_bwd, 
   const int ch = W.d.c_h;
   A.Tl[0] = T;
   for (int l = 0; l < W.d.n_conv_blocks; ++l) A.Tl[l + 1] = cdiv(A.Tl[l], W.d.subsample[l]);
-  const int Tlast = A.Tl[W.d.n_conv_blocks];
-  // reflect padding needs pad < length at every level (PyTorch raises otherwise)
-  if (T <= W.d.bank_size / 2 || Tlast <= W.d.kernel_size / 2)
-    fail(AVC_ERR_INVALID, "utterance of %d frames is too short for reflect padding", T);
+  // reflect padding needs pad < length for every conv INPUT (PyTorch raises otherwise, models.py:23-28): the bank sees T,
+  // both convs of block l see Tl[l]; the length after the last sub-sampling only feeds the pooling
+  bool too_short = T <= W.d.bank_size / 2;
+  for (int l = 0; l < W.d.n_conv_blocks; ++l) too_short = too_short || A.Tl[l] <= W.d.kernel_size / 2;
+  if (too_short) fail(AVC_ERR_INVALID, "utterance of %d frames is too short for reflect padding", T);
   A.cat = m.f((size_t)B * T * W.c_cat);
   A.h0 = m.f((size_t)B * T * ch);
   for (int l = 0; l < W.d.n_conv_blocks; ++l) {
@@ -1036,6 +1075,22 @@ void emit_layout_out(Emitter& E, const Tens& src, float* dst, const int64_t s[3]
     launch_k(layout_out_kernel, (unsigned)((n + 255) / 256), 256, 0, st, d.p, d.bs, d.rs, dst, sb, sc, st_, B, C, d.T);
   });
 }
+// the same with the caller's tensor read through the plan at launch time (IoBind): cached plans are rebound, not rebuilt
+void emit_layout_in_io(Emitter& E, const float* const* src, const int64_t* s, const Tens& dst, int B, int C) {
+  const long long n = (long long)B * dst.T * C;
+  const Tens d = dst;
+  E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
+    launch_k(layout_in_kernel, (unsigned)((n + 255) / 256), 256, 0, st, *src, (long long)s[0], (long long)s[1], (long long)s[2], d.p, d.bs, d.rs, B, C, d.T);
+  });
+}
+void emit_layout_out_io(Emitter& E, const Tens& src, float* const* dst, const int64_t* s, int B, int C) {
+  const long long n = (long long)B * src.T * C;
+  const Tens d = src;
+  E.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t st) {
+    if (!*dst) return;
+    launch_k(layout_out_kernel, (unsigned)((n + 255) / 256), 256, 0, st, d.p, d.bs, d.rs, *dst, (long long)s[0], (long long)s[1], (long long)s[2], B, C, d.T);
+  });
+}
 void emit_copy(Emitter& E, float* dst, const float* src, size_t n) {
   E.push(LK_COPY, 0, 8.0 * n, [=](cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
 }
@@ -1200,19 +1255,44 @@ void check_strides(const int64_t s[3], const char* nm) {
   (void)s; (void)nm;   // any strides are legal; element (b,c,t) = base[b*s0 + c*s1 + t*s2]
 }
 
+// capture `reps` back-to-back iterations of the plan into a graph and instantiate it
+void capture_iters(Plan& plan, int reps, cudaGraph_t* g, cudaGraphExec_t* x) {
+  cudaStream_t cs;
+  CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
+  try {
+    for (int r = 0; r < reps; ++r) run_list(plan.iter, cs);
+  } catch (...) {
+    cudaGraph_t bad = nullptr;
+    cudaStreamEndCapture(cs, &bad);
+    if (bad) cudaGraphDestroy(bad);
+    cudaStreamDestroy(cs);
+    throw;
+  }
+  e = cudaStreamEndCapture(cs, g);
+  cudaStreamDestroy(cs);
+  if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
+  CK(cudaGraphInstantiate(x, *g, 0));
+}
+
 std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
   if (!h->have_weights) fail(AVC_ERR_STATE, "avc_load_weights must be called before an attack");
   if (!a || !a->vc_tgt || !a->adv_tgt || !a->w0 || !a->adv_out) fail(AVC_ERR_INVALID, "null tensor argument");
   if (kind != K_EMB && !a->vc_src) fail(AVC_ERR_INVALID, "vc_src is required for e2e and fb attacks");
   if (a->B <= 0 || a->T_tgt <= 0 || a->T_adv <= 0 || a->n_iters < 0) fail(AVC_ERR_INVALID, "bad B/T/n_iters");
-  const int B = a->B, T = a->T_tgt, C = h->desc.speaker.c_in, n_iters = a->n_iters;
+  const int B = a->B, T = a->T_tgt, C = h->desc.speaker.c_in;
+  // provisioned iterations (Adam table, loss buffer): rounded up so that a cached plan serves later calls of the same shape
+  const int n_iters = a->n_iters <= 64 ? 64 : (a->n_iters + 511) / 512 * 512;
   const float eps = a->eps;
   const EncoderW& SE = h->se;
 
-  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool));
+  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool, st));
   Plan& plan = *plan_ptr;
   plan.n_iters = n_iters;
   plan.use_graph = a->use_graph != 0;
+  plan.io.bind(*a);
+  IoBind* io = &plan.io;
   Arena& m = plan.mem;
   Emitter S{h, &plan.setup, &plan.mem}, I{h, &plan.iter, &plan.mem}, F{h, &plan.finish, &plan.mem};
 
@@ -1237,8 +1317,15 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   EncActs se1 = alloc_encoder(m, SE, B, T, true, false);
   const Tens adv = se1.input(SE);   // the perturbed utterance lives in the bank concat buffer
   Tens xT = tens(x, T, C), wT = tens(w, T, C);
-  emit_layout_in(S, a->vc_tgt, a->tgt_stride, xT, B, C);
-  emit_layout_in(S, a->w0, a->w0_stride, wT, B, C);
+  {   // a (possibly reused) plan starts from a fresh optimiser: m = v = 0, step 0
+    float* mz = mm; float* vz = vv; int* sz = step; unsigned int* dz = done;
+    S.push(LK_COPY, 0, 8.0 * nel, [=](cudaStream_t s_) {
+      CK(cudaMemsetAsync(mz, 0, nel * sizeof(float), s_)); CK(cudaMemsetAsync(vz, 0, nel * sizeof(float), s_));
+      CK(cudaMemsetAsync(sz, 0, sizeof(int), s_)); CK(cudaMemsetAsync(dz, 0, sizeof(unsigned int), s_));
+    });
+  }
+  emit_layout_in_io(S, &io->vc_tgt, io->tgt_stride, xT, B, C);
+  emit_layout_in_io(S, &io->w0, io->w0_stride, wT, B, C);
 
   float* org = nullptr;   // targets
   float* tgt = nullptr;
@@ -1277,14 +1364,14 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     org = m.f((size_t)B * 128);
     tgt = m.f((size_t)B * 128);
     // targets (attack_utils.py:73-75)
-    emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+    emit_layout_in_io(S, &io->vc_tgt, io->tgt_stride, adv, B, C);
     se_forward(S, se1, TAIL_FWD, nullptr, nullptr, org);
     if (a->T_adv == T) {
-      emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+      emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, adv, B, C);
       se_forward(S, se1, TAIL_FWD, nullptr, nullptr, tgt);
     } else {
       EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
-      emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+      emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, seT.input(SE), B, C);
       se_forward(S, seT, TAIL_FWD, nullptr, nullptr, tgt);
     }
     perturb(S);
@@ -1301,7 +1388,7 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
     // content code (loop invariant; the reference recomputes it every iteration, models.py:482)
     EncActs ce = alloc_encoder(m, h->ce, B, T_src, false, true);
     DecActs dec = alloc_decoder(m, h->dec, B, L, true);
-    emit_layout_in(S, a->vc_src, a->src_stride, ce.input(h->ce), B, C);
+    emit_layout_in_io(S, &io->vc_src, io->src_stride, ce.input(h->ce), B, C);
     emit_bank_and_inconv(S, h->ce, ce, true);
     emit_encoder_blocks_fwd(S, h->ce, ce, true);
     {
@@ -1324,17 +1411,17 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
       parts = (int)mg;
       loss_parts = m.f((size_t)std::max(n_iters, 1) * parts);
       // targets (attack_utils.py:35-37)
-      emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+      emit_layout_in_io(S, &io->vc_tgt, io->tgt_stride, adv, B, C);
       se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
       emit_decoder_fwd(S, h->dec, dec, se1.emb, doutT);
       emit_copy(S, org, dout, nout);
       if (a->T_adv == T) {
-        emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+        emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, adv, B, C);
         se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
         emit_decoder_fwd(S, h->dec, dec, se1.emb, doutT);
       } else {
         EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
-        emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+        emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, seT.input(SE), B, C);
         se_forward(S, seT, TAIL_FWD, nullptr, nullptr, nullptr);
         emit_decoder_fwd(S, h->dec, dec, seT.emb, doutT);
       }
@@ -1357,16 +1444,16 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
       EncActs se2 = alloc_encoder(m, SE, B, T_dec, true, false);   // speaker encoder on the converted utterance
       const Tens conv_out = se2.input(SE);
       // targets (attack_utils.py:117-119)
-      emit_layout_in(S, a->vc_tgt, a->tgt_stride, adv, B, C);
+      emit_layout_in_io(S, &io->vc_tgt, io->tgt_stride, adv, B, C);
       se_forward(S, se1, TAIL_FWD, nullptr, nullptr, nullptr);
       emit_decoder_fwd(S, h->dec, dec, se1.emb, conv_out);
       se_forward(S, se2, TAIL_FWD, nullptr, nullptr, org);
       if (a->T_adv == T) {
-        emit_layout_in(S, a->adv_tgt, a->adv_stride, adv, B, C);
+        emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, adv, B, C);
         se_forward(S, se1, TAIL_FWD, nullptr, nullptr, tgt);
       } else {
         EncActs seT = alloc_encoder(m, SE, B, a->T_adv, false, false);
-        emit_layout_in(S, a->adv_tgt, a->adv_stride, seT.input(SE), B, C);
+        emit_layout_in_io(S, &io->adv_tgt, io->adv_stride, seT.input(SE), B, C);
         se_forward(S, seT, TAIL_FWD, nullptr, nullptr, tgt);
       }
       perturb(S);
@@ -1391,45 +1478,31 @@ std::unique_ptr<Plan> build_attack(avc_handle* h, AttackKind kind, const avc_att
   }
 
   // ---- finish: result, loss curve, last gradient -----------------------------------------------
-  emit_layout_out(F, adv, a->adv_out, a->out_stride, B, C);
-  if (a->loss_out && n_iters > 0) {
-    float* lp = loss_parts; float* lo = a->loss_out; const int pp = parts;
-    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) { launch_k(loss_sum_kernel, (n_iters + 127) / 128, 128, 0, s_, lp, pp, n_iters, lo); });
+  emit_layout_out_io(F, adv, &io->adv_out, io->out_stride, B, C);
+  {
+    float* lp = loss_parts; const int pp = parts;
+    F.push(LK_LOSS, 0, 4.0 * pp * n_iters, [=](cudaStream_t s_) {
+      const int n = io->n_iters;
+      if (io->loss_out && n > 0) launch_k(loss_sum_kernel, (n + 127) / 128, 128, 0, s_, (const float*)lp, pp, n, io->loss_out);
+    });
   }
-  if (a->grad_out && n_iters > 0) {
-    const int64_t cs[3] = {(int64_t)C * T, (int64_t)T, 1};
-    emit_layout_out(F, tens(gw, T, C), a->grad_out, cs, B, C);
+  if (gw) {
+    const long long cs0 = (long long)C * T, cs1 = T;
+    const Tens g = tens(gw, T, C);
+    const long long n = (long long)B * T * C;
+    F.push(LK_LAYOUT, 0, 8.0 * n, [=](cudaStream_t s_) {
+      if (io->grad_out && io->n_iters > 0)
+        launch_k(layout_out_kernel, (unsigned)((n + 255) / 256), 256, 0, s_, g.p, g.bs, g.rs, io->grad_out, cs0, cs1, 1LL, B, C, g.T);
+    });
   }
 
   // ---- setup: targets, loop invariants, initial perturbation; then capture one iteration -----------
-  CK(cudaDeviceSynchronize());   // arena memsets / uploads were issued on the legacy stream
+  // (arena zero fills / uploads are ordered on `st`: no device-wide synchronisation needed before the first launch)
   try {
     run_list(plan.setup, st);
     h->launches += (long long)plan.setup.size();
     h->launches_per_iter = (int)plan.iter.size();
-    if (n_iters > 0 && plan.use_graph) {
-      auto capture = [&](int reps, cudaGraph_t* g, cudaGraphExec_t* x) {
-        cudaStream_t cs;
-        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-        if (e != cudaSuccess) { cudaStreamDestroy(cs); fail(AVC_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e)); }
-        try {
-          for (int r = 0; r < reps; ++r) run_list(plan.iter, cs);
-        } catch (...) {
-          cudaGraph_t bad = nullptr;
-          cudaStreamEndCapture(cs, &bad);
-          if (bad) cudaGraphDestroy(bad);
-          cudaStreamDestroy(cs);
-          throw;
-        }
-        e = cudaStreamEndCapture(cs, g);
-        cudaStreamDestroy(cs);
-        if (e != cudaSuccess) fail(AVC_ERR_CUDA, "end capture: %s", cudaGetErrorString(e));
-        CK(cudaGraphInstantiate(x, *g, 0));
-      };
-      capture(1, &plan.graph, &plan.exec);
-      if (n_iters >= 2 * kUnroll) capture(kUnroll, &plan.graphU, &plan.execU);
-    }
+    if (plan.use_graph) capture_iters(plan, 1, &plan.graph, &plan.exec);
   } catch (...) {
     cudaDeviceSynchronize();   // nothing may still be running when the arena is released
     throw;
@@ -1447,7 +1520,7 @@ std::unique_ptr<Plan> build_header(avc_handle* h, const avc_header_args* a, cuda
   if (a->B <= 0 || a->T <= 0 || a->T_tgt <= 0 || a->n_iters < 0 || a->lr <= 0.f) fail(AVC_ERR_INVALID, "bad B/T/n_iters/lr");
   const int B = a->B, T = a->T, C = h->desc.speaker.c_in, n_iters = a->n_iters;
   const EncoderW& SE = h->se;
-  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool));
+  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool, st));
   Plan& plan = *plan_ptr;
   plan.n_iters = n_iters;
   plan.use_graph = a->use_graph != 0;
@@ -1577,8 +1650,10 @@ void step_header(avc_handle* h, Plan& plan, int n, int phase, cudaStream_t st) {
 
 void step_attack(avc_handle* h, Plan& plan, int n, cudaStream_t st) {
   if (plan.finished) fail(AVC_ERR_STATE, "attack session already finished");
-  if (n < 0 || plan.done_iters + n > plan.n_iters)
-    fail(AVC_ERR_INVALID, "session was opened for %d iterations, %d done, %d more requested", plan.n_iters, plan.done_iters, n);
+  if (n < 0 || plan.done_iters + n > plan.io.n_iters)
+    fail(AVC_ERR_INVALID, "session was opened for %d iterations, %d done, %d more requested", plan.io.n_iters, plan.done_iters, n);
+  // kUnroll iterations per graph launch, captured the first time a call is long enough to profit from it
+  if (plan.exec && !plan.execU && n >= 2 * kUnroll) capture_iters(plan, kUnroll, &plan.graphU, &plan.execU);
   try {
     if (plan.exec) {
       int left = n;
@@ -1608,26 +1683,81 @@ void finish_attack(avc_handle* h, Plan& plan, cudaStream_t st) {
   }
 }
 
+// ---- plan cache ------------------------------------------------------------------------------------------
+PlanKey make_key(const avc_handle* h, int kind, const avc_attack_args* a) {
+  PlanKey k;
+  if (!a) return k;
+  k.kind = kind; k.B = a->B; k.T_tgt = a->T_tgt; k.T_adv = a->T_adv; k.T_src = kind == K_EMB ? 0 : a->T_src;
+  k.use_graph = a->use_graph != 0; k.has_grad = a->grad_out != nullptr; k.conv_impl = h->conv_impl; k.tc_min_rows = h->tc_min_rows;
+  k.eps = a->eps; k.inv_norm = a->inv_norm > 0 ? a->inv_norm : 0.0;
+  return k;
+}
+constexpr size_t kPlanCacheMaxBytes = 512ull << 20;   // batch-1 .. batch-32 plans; the multi-GB batched plans are rebuilt
+constexpr size_t kPlanCacheEntries = 4;
+
+std::unique_ptr<Plan> take_cached(avc_handle* h, const PlanKey& key, int n_iters) {
+  static const bool off = getenv("AVC_NO_PLAN_CACHE") != nullptr;
+  if (off) return nullptr;
+  for (size_t i = 0; i < h->plan_cache.size(); ++i)
+    if (h->plan_cache[i]->key == key && h->plan_cache[i]->n_iters >= n_iters) {
+      std::unique_ptr<Plan> p = std::move(h->plan_cache[i]);
+      h->plan_cache.erase(h->plan_cache.begin() + i);
+      ++h->plan_cache_hits;
+      return p;
+    }
+  return nullptr;
+}
+void put_cached(avc_handle* h, std::unique_ptr<Plan> plan) {
+  if (!plan || plan->key.kind < 0 || plan->mem.bytes > kPlanCacheMaxBytes) return;   // dropped: buffers go back to the slab pool
+  for (auto& q : h->plan_cache) if (q->key == plan->key && q->n_iters >= plan->n_iters) return;
+  h->plan_cache.push_back(std::move(plan));
+  if (h->plan_cache.size() > kPlanCacheEntries) h->plan_cache.erase(h->plan_cache.begin());
+}
+
+// a plan ready to iterate: a cached one rebound to this call's tensors (its setup re-run), else a new one
+std::unique_ptr<Plan> acquire_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
+  const PlanKey key = make_key(h, (int)kind, a);
+  std::unique_ptr<Plan> plan = a ? take_cached(h, key, a->n_iters) : nullptr;
+  if (plan) {
+    if (!a->vc_tgt || !a->adv_tgt || !a->w0 || !a->adv_out || (kind != K_EMB && !a->vc_src)) fail(AVC_ERR_INVALID, "null tensor argument");
+    plan->io.bind(*a);
+    plan->done_iters = 0;
+    plan->finished = false;
+    try {
+      run_list(plan->setup, st);
+    } catch (...) {
+      cudaDeviceSynchronize();
+      throw;
+    }
+    h->launches += (long long)plan->setup.size();
+    h->launches_per_iter = (int)plan->iter.size();
+    return plan;
+  }
+  plan = build_attack(h, kind, a, st);
+  plan->key = key;
+  return plan;
+}
+
 void run_attack(avc_handle* h, AttackKind kind, const avc_attack_args* a, cudaStream_t st) {
   static const bool timing = getenv("AVC_TIMING") != nullptr;   // host-side phase times on stderr
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
-  std::unique_ptr<Plan> plan = build_attack(h, kind, a, st);
+  const long long hits0 = h->plan_cache_hits;
+  std::unique_ptr<Plan> plan = acquire_attack(h, kind, a, st);
   const double t1 = now();
   step_attack(h, *plan, a->n_iters, st);
   const double t2 = now();
   finish_attack(h, *plan, st);
   const double t3 = now();
-  const double t4 = [&] { if (plan->execU) { cudaGraphExecDestroy(plan->execU); plan->execU = nullptr; } if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; } return now(); }();
-  plan.reset();
-  if (timing) fprintf(stderr, "[avc] graph exec destroy %.2f ms\n", t4 - t3);
-  if (timing) fprintf(stderr, "[avc] attack kind %d: build %.2f ms, enqueue %.2f ms, drain+finish %.2f ms, free %.2f ms\n", (int)kind, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+  put_cached(h, std::move(plan));
+  if (timing) fprintf(stderr, "[avc] attack kind %d: %s %.2f ms, enqueue %.2f ms, drain+finish %.2f ms, release %.2f ms\n", (int)kind,
+                      h->plan_cache_hits > hits0 ? "rebind" : "build", t1 - t0, t2 - t1, t3 - t2, now() - t3);
 }
 
 template <class Fn>
 int guarded(avc_handle* h, Fn&& fn) {
   try {
-    if (h) CK(cudaSetDevice(h->device));
+    DeviceGuard dg(h ? h->device : -1);
     fn();
     return AVC_OK;
   } catch (const Fail& f) {
@@ -1646,7 +1776,11 @@ int guarded(avc_handle* h, Fn&& fn) {
 // =================================================================================================
 extern "C" {
 
-const char* avc_version(void) { return "avc_b200 0.1 (sm_100a)"; }
+#ifndef AVC_SRC_HASH
+#define AVC_SRC_HASH "unhashed-build!!"
+#endif
+// "... src <16 hex digits>": sha256 prefix of the sources this binary was compiled from (attack_vc_b200/build.py)
+const char* avc_version(void) { return "avc_b200 0.2 (sm_100a) src " AVC_SRC_HASH; }
 
 int avc_create(avc_handle** out, const avc_model_desc* desc, int device) {
   if (!out || !desc) { g_create_error = "null argument"; return AVC_ERR_INVALID; }
@@ -1657,7 +1791,7 @@ int avc_create(avc_handle** out, const avc_model_desc* desc, int device) {
     if (e != cudaSuccess || n == 0) fail(AVC_ERR_CUDA, "no CUDA device available (%s); libavc_b200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= n) fail(AVC_ERR_INVALID, "device %d out of range (%d devices)", device, n);
     validate_desc(*desc);
-    CK(cudaSetDevice(device));
+    DeviceGuard dg(device);
     cudaDeviceProp p{};
     CK(cudaGetDeviceProperties(&p, device));
     if (p.major < 10) fail(AVC_ERR_CUDA, "device %d is sm_%d%d; libavc_b200 is built for sm_100a only", device, p.major, p.minor);
@@ -1674,7 +1808,7 @@ int avc_create(avc_handle** out, const avc_model_desc* desc, int device) {
 
 void avc_destroy(avc_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   delete h;
 }
@@ -1724,7 +1858,7 @@ int avc_attack_begin(avc_handle* h, int32_t kind, const avc_attack_args* a, void
   *out = nullptr;
   return guarded(h, [&] {
     if (kind < 0 || kind > 2) fail(AVC_ERR_INVALID, "kind must be 0 (emb), 1 (e2e) or 2 (fb)");
-    std::unique_ptr<Plan> plan = build_attack(h, (AttackKind)kind, a, (cudaStream_t)stream);
+    std::unique_ptr<Plan> plan = acquire_attack(h, (AttackKind)kind, a, (cudaStream_t)stream);
     avc_session* s = new avc_session{h, std::move(plan)};
     *out = s;
   });
@@ -1738,8 +1872,9 @@ int avc_attack_step(avc_session* s, int32_t n, void* stream) {
 int avc_attack_end(avc_session* s, void* stream) {
   if (!s) return AVC_ERR_INVALID;
   int rc = guarded(s->h, [&] { finish_attack(s->h, *s->plan, (cudaStream_t)stream); });
-  cudaSetDevice(s->h->device);
+  DeviceGuard dg(s->h->device);
   cudaDeviceSynchronize();
+  if (rc == AVC_OK) put_cached(s->h, std::move(s->plan));   // idle now: the next call of this shape rebinds it
   delete s;
   return rc;
 }
@@ -1783,7 +1918,7 @@ int avc_session_profile(avc_session* s, int32_t cap, int32_t* kind, float* ms, d
     Plan& plan = *s->plan;
     const int n = (int)plan.iter.size();
     if (cap < n || !kind || !ms || !flops || !bytes) fail(AVC_ERR_INVALID, "profile arrays must hold %d entries", n);
-    if (plan.finished || plan.done_iters + 1 > plan.n_iters) fail(AVC_ERR_STATE, "no iteration left to profile");
+    if (plan.finished || plan.done_iters + 1 > (plan.key.kind >= 0 ? plan.io.n_iters : plan.n_iters)) fail(AVC_ERR_STATE, "no iteration left to profile");
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CK(cudaEventCreate(&e));
@@ -1817,7 +1952,7 @@ int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], 
     if (!h->have_weights) fail(AVC_ERR_STATE, "weights not loaded");
     if (!x || !emb || B <= 0 || T <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    Plan plan;
+    Plan plan(&h->pool, st);           // zero fills / uploads ordered on the caller's stream (it may be non-blocking)
     Emitter S{h, &plan.setup, &plan.mem};
     EncActs A = alloc_encoder(plan.mem, h->se, B, T, false, false);
     emit_layout_in(S, x, stride, A.input(h->se), B, h->desc.speaker.c_in);
@@ -1839,7 +1974,7 @@ int avc_inference(avc_handle* h, const float* src, const int64_t src_stride[3], 
     if (!h->have_weights) fail(AVC_ERR_STATE, "weights not loaded");
     if (!src || !tgt || !out || B <= 0 || T_src <= 0 || T_tgt <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    Plan plan;
+    Plan plan(&h->pool, st);
     Emitter S{h, &plan.setup, &plan.mem};
     const int C = h->desc.speaker.c_in, L = content_frames(h, T_src), T_dec = decoder_frames(h, T_src);
     EncActs ce = alloc_encoder(plan.mem, h->ce, B, T_src, false, true);
@@ -1900,7 +2035,7 @@ int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* b
   if (!h) return AVC_ERR_INVALID;
   return guarded(h, [&] {
     check_conv_dims(B, T, c_in, c_out, k, stride);
-    Arena tmp;
+    Arena tmp(nullptr, (cudaStream_t)stream);
     ConvW c = pack_adhoc(h, tmp, w, bias, c_in, c_out, k, stride);
     const int To = cdiv(T, stride);
     ConvArgs a = fwd_conv_args(c, tens(const_cast<float*>(x), T, c_in), tens(y, To, c_out), B, false, 0.f);
@@ -1923,7 +2058,7 @@ int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx, 
   if (!h) return AVC_ERR_INVALID;
   return guarded(h, [&] {
     check_conv_dims(B, T, c_in, c_out, k, stride);
-    Arena tmp;
+    Arena tmp(nullptr, (cudaStream_t)stream);
     ConvW c = pack_adhoc(h, tmp, w, nullptr, c_in, c_out, k, stride);
     const int To = cdiv(T, stride);
     ConvArgs a = bwd_conv_args(c, tens(const_cast<float*>(dy), To, c_out), tens(dx, T, c_in), B, 0.f);
@@ -1959,7 +2094,7 @@ int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, 
     a.rows_per_split = cdiv(a.rows_per_split, kWgRows) * kWgRows;
     splits = (int)((rows + a.rows_per_split - 1) / a.rows_per_split);
     a.splits = splits;
-    Arena tmp(&h->pool);   // partial tiles: a slab recycled through the handle's pool (no cudaMalloc per call)
+    Arena tmp(&h->pool, (cudaStream_t)stream);   // partial tiles: a slab recycled through the handle's pool (no cudaMalloc per call)
     a.partial = tmp.f((size_t)splits * k * c_out * c_in);
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(cdiv(c_out, kWgTile), cdiv(c_in, kWgTile), k * splits);
@@ -1983,7 +2118,7 @@ int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond,
     if (!y || !out || B <= 0 || T <= 0 || C <= 0 || up < 1) fail(AVC_ERR_INVALID, "bad argument");
     if (res && T % up) fail(AVC_ERR_INVALID, "T must be a multiple of up");
     std::vector<Launch> v;
-    Arena scratch;
+    Arena scratch(nullptr, (cudaStream_t)stream);
     Emitter E{h, &v, &scratch};
     ResArgs r = no_res();
     if (res) r = mk_res(tens(const_cast<float*>(res), T / up, C), up > 1 ? RES_UP : RES_SAME, up);
@@ -2000,7 +2135,7 @@ int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, co
   return guarded(h, [&] {
     if (!g || !y || !stats || B <= 0 || T <= 0 || C <= 0 || C % kNormCh) fail(AVC_ERR_INVALID, "bad argument");
     std::vector<Launch> v;
-    Arena scratch;
+    Arena scratch(nullptr, (cudaStream_t)stream);
     Emitter E{h, &v, &scratch};
     emit_norm_bwd(E, g, y, stats, cond, 2 * C, gy, gcond, 2 * C, B, T, C, neg_slope);
     run_list(v, (cudaStream_t)stream);
@@ -2015,7 +2150,7 @@ int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float*
   return guarded(h, [&] {
     if (!g_adv || !x || !w || !m || !v || !adv || n <= 0 || n % 4 || step < 1) fail(AVC_ERR_INVALID, "bad argument (n must be a multiple of 4, step >= 1)");
     cudaStream_t st = (cudaStream_t)stream;
-    Arena tmp;
+    Arena tmp(nullptr, st);
     const double t = step;
     std::vector<float> tab = {(float)(1e-3 / (1.0 - std::pow(0.9, t))), (float)std::sqrt(1.0 - std::pow(0.999, t))};
     UpdateArgs u{};

@@ -32,13 +32,25 @@ struct Fail {
     if (e_ != cudaSuccess) fail(AVC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// the library works on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {          // dev < 0: nothing to do
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---- device memory owned by the handle / a plan ---------------------------------------------
 // Slabs released by a finished attack are kept by the handle's pool and handed to the next one:
 // cudaFree / cudaMalloc of the 32 MiB slabs cost up to hundreds of ms per attack call otherwise.
 struct SlabPool {
   std::vector<std::pair<void*, size_t>> free_slabs;
   size_t held = 0;
-  static constexpr size_t kMaxHeld = 8ull << 30;   // beyond this, released slabs go back to the driver
+  static constexpr size_t kMaxHeld = 6ull << 30;   // beyond this, released slabs go back to the driver
   void* take(size_t sz) {
     for (size_t i = 0; i < free_slabs.size(); ++i)
       if (free_slabs[i].second == sz) {
@@ -67,8 +79,14 @@ struct Arena {
   char* cur = nullptr;
   size_t left = 0;
   size_t bytes = 0;
+  // Stream the zero fills and uploads are ordered on.  With `ordered` set they are issued asynchronously on the
+  // CALLER's stream, so kernels launched there afterwards see them even when that stream is non-blocking (a
+  // torch.cuda.Stream): the legacy default stream the plain cudaMemset / cudaMemcpy run on does not order against it.
+  cudaStream_t stream = nullptr;
+  bool ordered = false;
   Arena() = default;
   explicit Arena(SlabPool* p) : pool(p) {}
+  Arena(SlabPool* p, cudaStream_t st) : pool(p), stream(st), ordered(true) {}
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
   float* f(size_t n) {
@@ -77,7 +95,7 @@ struct Arena {
       const size_t sz = b > kSlab ? (b + kSlab - 1) / kSlab * kSlab : kSlab;
       void* p = pool ? pool->take(sz) : nullptr;
       if (!p) CK(cudaMalloc(&p, sz));
-      CK(cudaMemset(p, 0, sz));
+      if (ordered) CK(cudaMemsetAsync(p, 0, sz, stream)); else CK(cudaMemset(p, 0, sz));
       slabs.emplace_back(p, sz);
       bytes += sz;
       if (b > kSlab) return static_cast<float*>(p);   // dedicated slab, keep the current one
@@ -95,7 +113,9 @@ struct Arena {
   }
   float* upload(const std::vector<float>& v) {
     float* p = f(v.size());
-    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // pageable source: the async form stages the bytes before it returns, the device copy is ordered on `stream`
+    if (ordered) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    else CK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     return p;
   }
   ~Arena() {

@@ -600,7 +600,7 @@ namespace {
 template <class Fn>
 int pm_guarded(avc_pm_handle* h, Fn&& fn) {
   try {
-    if (h) CK(cudaSetDevice(h->device));
+    DeviceGuard dg(h ? h->device : -1);
     fn();
     return AVC_OK;
   } catch (const Fail& f) {
@@ -760,7 +760,7 @@ int avc_pm_create(avc_pm_handle** out, int device) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) fail(AVC_ERR_CUDA, "no CUDA device available (%s); libavc_b200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= n) fail(AVC_ERR_INVALID, "device %d out of range (%d devices)", device, n);
-    CK(cudaSetDevice(device));
+    DeviceGuard dg(device);
     cudaDeviceProp p{};
     CK(cudaGetDeviceProperties(&p, device));
     if (p.major < 10) fail(AVC_ERR_CUDA, "device %d is sm_%d%d; libavc_b200 is built for sm_100a only", device, p.major, p.minor);
@@ -773,7 +773,7 @@ int avc_pm_create(avc_pm_handle** out, int device) {
 
 void avc_pm_destroy(avc_pm_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard dg(h->device);
   cudaDeviceSynchronize();
   delete h;
 }
@@ -873,10 +873,9 @@ int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int3
     if (!h->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
     if (!x || !out || B <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    Arena mem(&h->pool);
+    Arena mem(&h->pool, st);           // zero fills ordered on the caller's stream: no device-wide synchronisation per call
     PmActs A;
     pm_shapes(A, B, H, W);
-    CK(cudaDeviceSynchronize());
     pm_forward(h, mem, A, x, out, training != 0, nullptr, nullptr, st);
     CK(cudaStreamSynchronize(st));
   });
@@ -899,7 +898,7 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
       gout[grads[i].name] = const_cast<float*>(grads[i].data);
     }
     auto want = [&](const std::string& k) -> float* { auto it = gout.find(k); return it == gout.end() ? nullptr : it->second; };
-    Arena mem(&h->pool);
+    Arena mem(&h->pool, st);
     PmActs A;
     pm_shapes(A, B, H, W);
     float* nm[7]; float* nv[7];
@@ -908,7 +907,6 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
       nm[l] = want(p + "running_mean"); nv[l] = want(p + "running_var");
       if ((nm[l] == nullptr) != (nv[l] == nullptr)) fail(AVC_ERR_INVALID, "running_mean and running_var outputs must come together");
     }
-    CK(cudaDeviceSynchronize());
     pm_forward(h, mem, A, x, out, true, nm, nv, st);
     const float* o = A.u[4];
     const long long n_out = (long long)B * A.Hu[5] * A.Wu[5];

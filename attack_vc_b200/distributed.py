@@ -56,21 +56,39 @@ def sharded_attack(attack: AttackFn, kind: str, vc_tgt: Tensor, adv_tgt: Tensor,
         losses = info["losses"].to(torch.float32)
     else:
         adv = vc_tgt[0:0]
+    return gather_shards(adv, losses, B, group=group)
+
+
+def gather_shards(adv_local: Tensor, losses_local: Tensor, B_total: int, group=None) -> Tuple[Tensor, Tensor]:
+    """The one collective step of a sharded attack, run AFTER the loop: all_gather of the perturbed utterances
+    (equal-sized padded slots; slices differ by at most one utterance) and all_reduce(sum) of the per-iteration loss
+    partial sums (each already scaled by the global normaliser).  NCCL over NVLink on GPUs, gloo in the CPU tests."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return adv, losses
-    # gather of perturbed outputs: equal-sized padded slots, then trim (slices differ by at most one)
-    cap = -(-B // world)
-    slot = torch.zeros((cap,) + tuple(vc_tgt.shape[1:]), dtype=vc_tgt.dtype, device=vc_tgt.device)
-    slot[: hi - lo] = adv
-    slots = [torch.empty_like(slot) for _ in range(world)]
-    dist.all_gather(slots, slot, group=group)
+        return adv_local, losses_local
+    cap = -(-B_total // world)
+    slot = torch.zeros((cap,) + tuple(adv_local.shape[1:]), dtype=adv_local.dtype, device=adv_local.device)
+    slot[: adv_local.shape[0]] = adv_local
+    full = torch.empty((world * cap,) + tuple(adv_local.shape[1:]), dtype=adv_local.dtype, device=adv_local.device)
+    dist.all_gather(list(full.chunk(world)), slot, group=group)     # views of one buffer: no copy after the collective
     parts = []
     for r in range(world):
-        a, b = shard_bounds(B, world, r)
-        parts.append(slots[r][: b - a])
-    # loss statistics: each rank holds the partial sum over its slice, already scaled by the global normaliser
+        a, b = shard_bounds(B_total, world, r)
+        parts.append(full[r * cap: r * cap + (b - a)])
+    losses = losses_local.to(torch.float32).clone()
     dist.all_reduce(losses, op=dist.ReduceOp.SUM, group=group)
-    return torch.cat(parts, dim=0), losses
+    return (torch.cat(parts, dim=0) if B_total % world else full), losses
+
+
+def sharded_attack_shards(attack: AttackFn, kind: str, vc_tgt_local: Tensor, adv_tgt_local: Tensor, eps: float, n_iters: int,
+                          B_total: int, inv_norm: float, vc_src_local: Optional[Tensor] = None,
+                          w0_local: Optional[Tensor] = None, group=None) -> Tuple[Tensor, Tensor]:
+    """``sharded_attack`` for callers that already hold only THEIR slice (rows ``shard_bounds(B_total, world, rank)`` of
+    the global batch): nothing is replicated -- BASELINE configs[3] is 3 x 671 MB of inputs in total, 84 MB per rank.
+    Returns the full perturbed batch and the whole-batch loss curve on every rank."""
+    adv, info = attack(kind, vc_tgt_local, adv_tgt_local, eps, n_iters, vc_src=vc_src_local, w0=w0_local,
+                       inv_norm=inv_norm, want_loss=True)
+    return gather_shards(adv, info["losses"], B_total, group=group)
 
 
 def sharded_header_optimize(engine, source_mel: Tensor, target_mel: Tensor, num_iterations: int, epsilon: float = 0.1,

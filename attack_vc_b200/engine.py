@@ -124,28 +124,32 @@ class Engine:
         self.desc = desc
         self.c_in = int(desc.speaker.c_in)
         self.c_emb = int(desc.speaker.c_out)
+        self._sessions = 0            # open AttackSession / HeaderSession objects: close() refuses while any is alive
         h = C.c_void_p()
-        rc = self._lib.avc_create(C.byref(h), C.byref(desc), self.device.index)
-        if rc != 0:
-            raise AvcError(f"avc_create failed ({rc}): {self._lib.avc_last_error(None).decode()}")
-        self._h = h
-        keep = []
-        views = (WeightView * len(sd))()
-        for i, (k, v) in enumerate(sd.items()):
-            t = v.to(device=self.device, dtype=torch.float32).contiguous()
-            keep.append(t)
-            views[i].name = k.encode()
-            views[i].data = t.data_ptr()
-            views[i].ndim = t.dim()
-            for j, s in enumerate(t.shape):
-                views[i].shape[j] = int(s)
-        torch.cuda.synchronize(self.device)
-        self._check(self._lib.avc_load_weights(self._h, views, len(sd)))
-        del keep
+        with torch.cuda.device(self.device):
+            rc = self._lib.avc_create(C.byref(h), C.byref(desc), self.device.index)
+            if rc != 0:
+                raise AvcError(f"avc_create failed ({rc}): {self._lib.avc_last_error(None).decode()}")
+            self._h = h
+            keep = []
+            views = (WeightView * len(sd))()
+            for i, (k, v) in enumerate(sd.items()):
+                t = v.to(device=self.device, dtype=torch.float32).contiguous()
+                keep.append(t)
+                views[i].name = k.encode()
+                views[i].data = t.data_ptr()
+                views[i].ndim = t.dim()
+                for j, s in enumerate(t.shape):
+                    views[i].shape[j] = int(s)
+            torch.cuda.synchronize(self.device)
+            self._check(self._lib.avc_load_weights(self._h, views, len(sd)))
+            del keep
 
     # ------------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_sessions", 0) > 0:
+                raise AvcError(f"Engine.close(): {self._sessions} attack session(s) still open; end() them first")
             self._lib.avc_destroy(self._h)
             self._h = None
 
@@ -393,6 +397,7 @@ class AttackSession:
 
     def __init__(self, eng: Engine, sp, keep, n_iters: int):
         self.eng, self._s, self._keep, self.n_iters = eng, sp, keep, n_iters
+        eng._sessions += 1
 
     @property
     def launches_per_iter(self) -> int:
@@ -414,6 +419,7 @@ class AttackSession:
         if self._s is None:
             raise AvcError("session already ended")
         s, self._s = self._s, None
+        self.eng._sessions -= 1
         self.eng._check(self.eng._lib.avc_attack_end(s, self.eng._stream()))
         _, _, _, w0, out, loss, grad = self._keep
         return out, {"losses": loss, "grad": grad, "w0": w0}
@@ -421,6 +427,7 @@ class AttackSession:
     def __del__(self):
         try:
             if self._s is not None:
+                self.eng._sessions -= 1
                 self.eng._lib.avc_attack_end(self._s, self.eng._stream())
                 self._s = None
         except Exception:
@@ -440,6 +447,7 @@ class HeaderSession:
 
     def __init__(self, eng: Engine, sp, keep, n_iters: int):
         self.eng, self._s, self._keep, self.n_iters = eng, sp, keep, n_iters
+        eng._sessions += 1
         n = C.c_int64()
         ptr = eng._lib.avc_header_grad_buffer(sp, C.byref(n))
         self.grad = torch.as_tensor(_DevMem(int(ptr), int(n.value)), device=eng.device)   # [T*80] time-major partial gradient
@@ -458,6 +466,7 @@ class HeaderSession:
             raise AvcError("session already ended")
         s, self._s = self._s, None
         self.grad = None
+        self.eng._sessions -= 1
         self.eng._check(self.eng._lib.avc_attack_end(s, self.eng._stream()))
         _, _, _, out, loss, _ = self._keep
         return out.reshape(1, 1, self.eng.c_in, -1), {"losses": loss}
@@ -465,23 +474,49 @@ class HeaderSession:
     def __del__(self):
         try:
             if self._s is not None:
+                self.eng._sessions -= 1
                 self.eng._lib.avc_attack_end(self._s, self.eng._stream())
                 self._s = None
         except Exception:
             pass
 
 
-_ENGINES: Dict[int, Tuple[Tuple, Engine]] = {}
+import weakref  # noqa: E402
+
+_ENGINES: "weakref.WeakKeyDictionary[nn.Module, Tuple[Tuple, Engine]]" = weakref.WeakKeyDictionary()
+
+
+def _fingerprint(model: nn.Module) -> Tuple:
+    """(storage pointer, autograd version, a content probe) per parameter.  The probe -- the sum of up to 64 evenly spaced
+    elements, computed on the device and fetched in ONE transfer -- also catches in-place edits through ``p.data``, which do
+    not bump ``_version``.  Edits that keep all probed elements unchanged need ``invalidate_engine(model)``."""
+    ps = list(model.parameters())
+    if not ps:
+        return ()
+    with torch.no_grad():
+        probes = torch.stack([p.detach().reshape(-1)[:: max(1, p.numel() // 64)][:64].double().sum() for p in ps])
+    vals = probes.cpu().tolist()
+    return tuple((p.data_ptr(), p._version, v) for p, v in zip(ps, vals))
+
+
+def invalidate_engine(model: nn.Module) -> None:
+    """Drop the cached engine of ``model`` (call after editing its weights in a way the fingerprint cannot see)."""
+    hit = _ENGINES.pop(model, None)
+    if hit is not None and hit[1]._sessions == 0:
+        hit[1].close()
 
 
 def engine_for(model: nn.Module) -> Engine:
-    """Engine cache: one per model object, rebuilt when a parameter was modified or moved."""
-    sig = tuple((p.data_ptr(), p._version) for p in model.parameters())
-    hit = _ENGINES.get(id(model))
+    """Engine cache: one per LIVE model object (weak keys: a collected model releases its engine, and a new model that
+    happens to reuse its id() or its allocator pointers can never be handed the old engine); rebuilt when a parameter
+    was modified, replaced or moved."""
+    sig = _fingerprint(model)
+    hit = _ENGINES.get(model)
     if hit is not None and hit[0] == sig:
         return hit[1]
-    if hit is not None:
-        hit[1].close()
+    if hit is not None and hit[1]._sessions == 0:
+        hit[1].close()             # with sessions still open the old handle stays alive until they end (Engine.__del__)
     eng = Engine(model)
-    _ENGINES[id(model)] = (sig, eng)
+    _ENGINES[model] = (sig, eng)
+    weakref.finalize(model, lambda e=eng: e._sessions == 0 and e.close())
     return eng

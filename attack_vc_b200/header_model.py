@@ -47,6 +47,12 @@ class UniversalPerturbationHeader:
         """header_model.py:25-68: num_iterations Adam steps on the shared header, clamped to +-epsilon."""
         eng = engine_for(self._resolve_model(speaker_encoder))
         lr = self._adam_lr(optimizer)
+        # The fused loop starts Adam from m = v = 0, step 0 and does not write the moments back: a caller that continues with
+        # an optimizer that already stepped (chunked optimisation) would silently get another trajectory than the reference,
+        # whose moments and bias-correction step live in the optimizer.  train_header.py:77-81 calls optimize() once.
+        if any(int(st.get("step", 0)) > 0 for st in optimizer.state.values()):
+            raise RuntimeError("UniversalPerturbationHeader.optimize: the Adam optimizer has already stepped; the B200 path "
+                               "restarts the moments on every call -- pass a fresh torch.optim.Adam([header.header], lr)")
         new = eng.header_optimize(source_mel, target_mel, num_iterations, epsilon, lambda_param, lr,
                                   header0=self.header.detach()[0, 0])
         with torch.no_grad():

@@ -144,3 +144,64 @@ class ParamTree(nn.Module):
                 node = node._modules[p]
             node.register_parameter(parts[-1], nn.Parameter(value.clone()))
         self._keys = list(state.keys())
+
+
+# ---- VSMask PredictiveModel: architecture table and seeded synthetic weights ----
+# (c_in, c_out, (stride_h, stride_w)) -- models/predictive_model.py:65-73 and :76-82
+PM_DOWN = [(1, 32, (1, 2)), (32, 64, (2, 2)), (64, 128, (2, 2)), (128, 256, (2, 2)), (256, 256, (2, 2)),
+           (256, 512, (2, 2)), (512, 512, (2, 2))]
+PM_UP = [(512, 256), (256, 128), (128, 64), (64, 32), (32, 1)]
+
+
+def pm_param_shapes() -> "OrderedDict[str, tuple]":
+    """state_dict keys/shapes in the reference's registration order (num_batches_tracked included)."""
+    out: "OrderedDict[str, tuple]" = OrderedDict()
+    for i, (ci, co, _) in enumerate(PM_DOWN):
+        p = f"down_blocks.{i}.conv."
+        out[p + "1.weight"] = (co, ci, 3, 3)
+        out[p + "1.bias"] = (co,)
+        out[p + "2.weight"] = (co,)
+        out[p + "2.bias"] = (co,)
+        out[p + "2.running_mean"] = (co,)
+        out[p + "2.running_var"] = (co,)
+        out[p + "2.num_batches_tracked"] = ()
+        out[p + "3.weight"] = (1,)
+    for i, (ci, co) in enumerate(PM_UP):
+        p = f"up_blocks.{i}.conv_transpose.0."
+        out[p + "weight"] = (ci, co, 3, 3)
+        out[p + "bias"] = (co,)
+    return out
+
+
+def pm_make_state_dict(seed: int = 0, dtype=torch.float32) -> "OrderedDict[str, Tensor]":
+    """Seeded synthetic weights.  Conv / ConvTranspose: U(+-1/sqrt(fan_in)) like PyTorch's default;
+    BatchNorm affine, running statistics and the PReLU slope are randomised too (the defaults 1/0/0/1/0.25
+    would leave those code paths untested)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(424243 * (seed + 1))
+    sd: "OrderedDict[str, Tensor]" = OrderedDict()
+    u = lambda shape, lo, hi: (torch.rand(shape, generator=g, dtype=torch.float64) * (hi - lo) + lo)
+    for key, shape in pm_param_shapes().items():
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+            continue
+        if ".conv.2." in key:
+            if key.endswith("running_var"):
+                t = u(shape, 0.5, 1.5)
+            elif key.endswith("running_mean"):
+                t = u(shape, -0.2, 0.2)
+            elif key.endswith("weight"):
+                t = u(shape, 0.8, 1.2)
+            else:
+                t = u(shape, -0.1, 0.1)
+        elif ".conv.3." in key:
+            t = u(shape, 0.1, 0.4)
+        else:
+            wkey = key[: -len("bias")] + "weight" if key.endswith("bias") else key
+            wshape = pm_param_shapes()[wkey]
+            # Conv2d fan_in = c_in*9; ConvTranspose2d weight is [c_in, c_out, 3, 3] and PyTorch uses size(1)*9
+            fan_in = wshape[1] * 9
+            b = 1.0 / math.sqrt(fan_in)
+            t = u(shape, -b, b)
+        sd[key] = t.to(dtype)
+    return sd

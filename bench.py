@@ -122,6 +122,77 @@ def cpu_loop_rate(kind: str, B: int, T: int, budget_s: float, max_iters: int):
     return n * B / dt, cores, n, dt
 
 
+def gpu_eager_baseline(kind: str, B: int, T: int, dev, budget_s: float = 8.0):
+    """The "library bar" (BASELINE.md 3.5): the SAME loop as the reference (oracle loop == reference loop)
+    run by PyTorch eager on this B200 -- cuDNN / cuBLAS fp32 kernels, TF32 off -- with resident inputs.  Also tried once
+    inside a CUDA graph (capturable Adam), which removes eager's launch overhead.  Checker / baseline code only."""
+    from oracle import adainvc_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {"what": "oracle loop (== reference loop) on cuda, PyTorch eager fp32, allow_tf32 = False", "torch": torch.__version__}
+    try:
+        model = O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0).to(dev)
+        inp = {k: v.to(dev) for k, v in O.make_inputs(kind, B, T, seed=1).items()}
+        run = lambda n: O.run_attack(kind, model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=inp.get("vc_src"))
+        run(3); torch.cuda.synchronize(dev)
+        t0 = time.perf_counter(); run(5); torch.cuda.synchronize(dev); t5 = (time.perf_counter() - t0) / 5
+        n = int(max(10, min(300, budget_s / max(t5, 1e-4))))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev); e0.record(); r = run(n); e1.record(); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / n
+        out.update({"value": B * 1e3 / ms, "unit": "utterance-iterations/s", "ms_per_step": ms, "iterations": n,
+                    "loss_last": float(r["losses"][-1])})
+        try:   # kernels per iteration: difference of two profiled runs of different length
+            from torch.profiler import ProfilerActivity, profile
+
+            def kernels(k):
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    run(k); torch.cuda.synchronize(dev)
+                return sum(1 for ev in prof.events() if str(ev.device_type).endswith("CUDA"))
+            out["launches_per_iter"] = (kernels(4) - kernels(2)) / 2.0
+        except Exception as e:
+            out["launches_per_iter"] = None; out["launches_error"] = str(e)[:120]
+        try:   # the same iteration captured into a CUDA graph (whole-network capture, capturable Adam)
+            x, at, src = inp["vc_tgt"], inp["adv_tgt"], inp.get("vc_src")
+            mse = torch.nn.MSELoss()
+            fwd = {"emb": lambda a: model.speaker_encoder(a), "e2e": lambda a: model.inference(src, a),
+                   "fb": lambda a: model.speaker_encoder(model.inference(src, a))}[kind]
+            with torch.no_grad():
+                org = fwd(x); tgt = model.speaker_encoder(at) if kind in ("emb", "fb") else model.inference(src, at)
+            w = inp["w0"].clone().requires_grad_(True)
+            opt = torch.optim.Adam([w], capturable=True)
+
+            side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    opt.zero_grad(set_to_none=True)
+                    o = fwd(x + 0.1 * w.tanh()); loss = mse(o, tgt) - 0.1 * mse(o, org); loss.backward(); opt.step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            for prm in model.parameters():
+                prm.grad = None
+            with torch.cuda.graph(g):
+                o = fwd(x + 0.1 * w.tanh()); loss = mse(o, tgt) - 0.1 * mse(o, org); loss.backward(); opt.step()
+            for _ in range(3):
+                g.replay()
+            ng = int(max(20, min(2000, budget_s / 2 / max(ms / 1e3 / 4, 1e-5))))
+            torch.cuda.synchronize(dev); e0.record()
+            for _ in range(ng):
+                g.replay()
+            e1.record(); torch.cuda.synchronize(dev)
+            msg = e0.elapsed_time(e1) / ng
+            out["cuda_graph"] = {"value": B * 1e3 / msg, "ms_per_step": msg, "iterations": ng, "loss": float(loss)}
+        except Exception as e:
+            out["cuda_graph"] = {"error": str(e)[:200]}
+    except Exception as e:
+        out["error"] = str(e)[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    return out
+
+
 PM_GFLOP_FWD, PM_GFLOP_FWD_BWD = 0.2045, 0.6111        # per 80x100 window, SURVEY 8d
 
 
@@ -170,7 +241,7 @@ def pm_arm(args, rank, world, local):
             dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize(dev)
         finally:
             sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
-    from oracle.predictive_oracle import pm_make_state_dict   # weights only (seeded synthetic init)
+    from attack_vc_b200.synthetic import pm_make_state_dict
     from attack_vc_b200.predictive import PredictiveEngine
     eng = PredictiveEngine({k: v.to(dev) for k, v in pm_make_state_dict(0).items()})
     K, W = args.steps, max(args.warmup, 3)
@@ -255,6 +326,8 @@ def reference_arm(args, rank):
         "cpu_baseline": {"value": rate, "unit": "utterance-iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "utterance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "ONE CPU process on rank 0 with all host cores, whatever --gpus says (the reference has no multi-process path): "
+                "at N > 1 this is not N reference processes -- compare the N-GPU value with N x this only with that in mind",
     }
     print(json.dumps(line), flush=True)
 
@@ -405,27 +478,51 @@ def main():
     d2h = res.numel() * 4
     launches_before = eng.kernel_launches
 
-    # ---- after the loop: gather perturbed outputs + loss curves (NCCL), not timed --------------------
-    if world > 1:
-        outs = [torch.empty_like(res, device=dev) for _ in range(world)]
-        dist.all_gather(outs, res.to(dev))
-        ls = losses.clone()
-        dist.all_reduce(ls)
+    # ---- N > 1: the path that really shards -- BASELINE configs[3], emb_attack on 512 utterances of 80x512 per GPU
+    # (4096 over 8) with the GLOBAL MSE normaliser, every rank holding only its own slice, and the one exchange step of
+    # the workload (NCCL all_gather of the perturbed utterances + all_reduce of the loss curves) INSIDE the timed region.
+    sharded = None
+    if world > 1 and not args.no_extra:
+        from attack_vc_b200.distributed import gather_shards, global_inv_norm
+        Bs, Ts, ns = 512, 512, 6
+        shard = {k: v.to(dev) for k, v in make_inputs("emb", Bs, Ts, seed=100 + rank).items()}
+        inv = global_inv_norm("emb", Bs * world, 128, 80, Ts)
+        s2 = eng.begin("emb", shard["vc_tgt"], shard["adv_tgt"], 0.1, 3 + ns, w0=shard["w0"], inv_norm=inv, want_loss=True)
+        s2.step(3)
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        barrier()
+        ea.record()
+        s2.step(ns)
+        eb.record()
+        adv_l, inf2 = s2.end()
+        adv_all, loss_all = gather_shards(adv_l, inf2["losses"], Bs * world)
+        ec.record()
+        barrier()
+        ms_it = max_over_ranks(ea.elapsed_time(eb)) / ns
+        ms_x = max_over_ranks(eb.elapsed_time(ec))
+        sharded = {"workload": "BASELINE configs[3]: emb_attack, 80x512, 512 utterances per GPU, global 1/(B_total*128) normaliser",
+                   "utterances_total": Bs * world, "iterations_timed": ns, "ms_per_iteration": ms_it,
+                   "utterance_iterations_per_s": Bs * world * 1e3 / ms_it,
+                   "exchange_ms": ms_x, "exchange": "finish kernels + NCCL all_gather_into_tensor of %.0f MB per rank + all_reduce of the loss curve" % (adv_l.numel() * 4 / 1e6),
+                   "defended_utterances_per_s_at_1500_iters": Bs * world / ((1500 * ms_it + ms_x) / 1e3),
+                   "gathered_shape": list(adv_all.shape), "loss_first_last": [float(loss_all[0]), float(loss_all[3 + ns - 1])],
+                   "algorithmic_tflops": 2.0728e-3 * Bs * world / (ms_it / 1e3)}
+        del shard, adv_all, adv_l
 
     line = {
         "metric": "attack iterations/s (x utterances)", "value": value, "unit": "utterance-iterations/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "attack": kind, "utterances_per_gpu": B, "frames": T, "eps": 0.1,
-                   "defended_utterances_per_s_at_1500_iters": value / 1500.0,
+        "config": {"workload": desc, "attack": kind, "utterances_per_gpu": B, "frames": T, "eps": 0.1},
+        "detail": {"defended_utterances_per_s_at_1500_iters": value / 1500.0,
                    "l2": "not flushed: iteration i+1 consumes iteration i's state and the 19.6 MB of weights stay hot by construction of the attack; the batched side measurements stream activations larger than L2",
-                   "conv_impl": os.environ.get("AVC_CONV_IMPL", "auto")},
+                   "conv_impl": os.environ.get("AVC_CONV_IMPL", "auto"), "library": eng._lib.avc_version().decode()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "utterance-iterations/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "ms_total": e2e_ms, "api": f"attack_utils.{kind}_attack(model, ..., n_iters={K}) with pinned host tensors"},
         "gpu_launches": launches_per_iter * K,
         "launches_per_step": launches_per_iter,
-        "roofline": roofline, "hbm_kernels": hbm, "breakdown_ms": breakdown,
+        "roofline": roofline, "hbm_kernels": hbm, "breakdown_ms": breakdown, "sharded": sharded,
         "loss_first_last": [float(losses[0]), float(losses[-1])],
         "kernel_launches_total": launches_before,
     }
@@ -490,6 +587,7 @@ def main():
         line["batched"] = extra
 
     if world == 1 and not args.no_cpu_baseline:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(kind, min(B, 64), T, dev)
         Bc = min(B, 8)
         rate, cores, n, dt = cpu_loop_rate(kind, Bc, T, budget_s=15.0, max_iters=400)
         line["cpu_baseline"] = {"value": rate, "unit": "utterance-iterations/s", "cores": cores, "kind": "port",

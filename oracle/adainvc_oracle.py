@@ -40,8 +40,39 @@ from attack_vc_b200.synthetic import (SYNTH_CONFIG, ParamTree, make_inputs, make
 # --------------------------------------------------------------------------------------
 # Functional model (channels-first [B, C, T], exactly the reference's tensor convention)
 # --------------------------------------------------------------------------------------
+class ActProbe:
+    """Test instrument for the kink arbiter (tests/test_attacks_gpu.py).  While active it numbers every activation call
+    whose input depends on the attacked tensor (autograd recording, input requires grad), records the pre-activations
+    and can force chosen units onto their other branch.  The network is piecewise linear: where a ReLU unit sits within
+    rounding distance of zero, two correct implementations may legitimately take different branches, and each branch
+    has its own exact gradient.  Never active outside tests."""
+    active: Optional["ActProbe"] = None
+
+    def __init__(self, flip: Optional[Dict] = None, record: bool = True):
+        self.flip = flip or {}          # {call index: BoolTensor (shape of the pre-activation)}: units forced to the other branch
+        self.pre: Dict[int, Tensor] = {}
+        self.record = record
+        self.n = 0
+
+    def __enter__(self):
+        ActProbe.active = self
+        return self
+
+    def __exit__(self, *exc):
+        ActProbe.active = None
+
+
 def _act(x: Tensor, act: str) -> Tensor:
     # get_act, models.py:107-118: "lrelu" -> LeakyReLU() (slope 0.01), anything else ReLU.
+    probe = ActProbe.active
+    if probe is not None and torch.is_grad_enabled() and x.requires_grad:
+        i = probe.n
+        probe.n += 1
+        if probe.record:
+            probe.pre[i] = x.detach().clone()
+        if i in probe.flip:
+            on = (x.detach() > 0) ^ probe.flip[i]
+            return torch.where(on, x, x * (0.01 if act == "lrelu" else 0.0))
     return F.leaky_relu(x, 0.01) if act == "lrelu" else F.relu(x)
 
 
@@ -226,11 +257,12 @@ def run_attack(kind: str, model, vc_tgt: Tensor, adv_tgt: Tensor, eps: float, n_
             grads[i] = w.grad.detach().clone()
             if record_w:
                 ws[i] = w.detach().clone()      # w BEFORE this iteration's Adam step (teacher forcing)
-        losses.append(float(loss.detach()))
+        losses.append(loss.detach())                          # no .item(): the reference never reads the loss in the loop either
         opt.step()
     with torch.no_grad():
         final = vc_tgt + eps * w.tanh()                       # :48,86,130
-    return {"adv": final.detach(), "w": w.detach().clone(), "losses": torch.tensor(losses, dtype=torch.float64),
+    return {"adv": final.detach(), "w": w.detach().clone(),
+            "losses": torch.stack(losses).double().cpu() if losses else torch.zeros(0, dtype=torch.float64),
             "grads": grads, "ws": ws, "org": org.detach(), "tgt": tgt.detach()}
 
 

@@ -52,7 +52,7 @@ class Spy:
         torch.optim.Adam.step = self._orig
 
 
-def case(name, kind, B, T, n_iters, record, T_src=None, T_adv=None, cli_layout=False):
+def case(name, kind, B, T, n_iters, record, T_src=None, T_adv=None, cli_layout=False, skip_edges=False):
     ref = RM.AdaInVC(O.SYNTH_CONFIG)
     ref.load_state_dict(O.make_state_dict(seed=0), strict=True)
     inp = O.make_inputs(kind, B, T, seed=1, T_src=T_src, T_adv=T_adv)
@@ -95,9 +95,13 @@ def case(name, kind, B, T, n_iters, record, T_src=None, T_adv=None, cli_layout=F
         g64 = o64["grads"][0]
         edge = float((spy.grads[i].double() - g64).norm() / g64.norm())
         print(f"  {name}: iteration {i}: reference fp32 vs fp64 at the same w: {edge:.2e}")
-        assert edge < 1e-4, f"{name}: iteration {i} sits on a ReLU edge ({edge:.2e}); record another one"
+        if edge >= 1e-4:
+            assert skip_edges, f"{name}: iteration {i} sits on a ReLU edge ({edge:.2e}); record another one"
+            print(f"  {name}: iteration {i} sits on a ReLU edge: not recorded")
+            continue
         d[f"grad_{i}"] = spy.grads[i].numpy()
         d[f"w_{i}"] = wi.numpy()
+    assert sum(k.startswith("grad_") for k in d) >= 2, f"{name}: fewer than two usable teacher-forcing points"
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
     print(name, "loss0", float(o["losses"][0]), "lossN", float(o["losses"][-1]), "max|adv-x|", float((adv.detach() - inp["vc_tgt"]).abs().max()))
@@ -117,11 +121,25 @@ def model_vectors():
     print("model_fwd", emb.shape, mu.shape, out.shape)
 
 
+CASES = {
+    "emb_T128_it100": lambda: case("emb_T128_it100", "emb", 1, 128, 100, (0, 1, 10, 99)),                      # BASELINE config 1
+    "e2e_T64_it20": lambda: case("e2e_T64_it20", "e2e", 1, 64, 20, (0, 1, 19)),
+    "fb_T64_it20": lambda: case("fb_T64_it20", "fb", 1, 64, 20, (0, 1, 19)),
+    "emb_B2_ragged_cli": lambda: case("emb_B2_ragged_cli", "emb", 2, 75, 6, (0, 5), T_adv=131, cli_layout=True),   # odd T, T_adv != T, CLI strides
+    "e2e_B2_ragged": lambda: case("e2e_B2_ragged", "e2e", 2, 64, 4, (0, 3), T_src=43, T_adv=90),
+    "fb_B2_ragged": lambda: case("fb_B2_ragged", "fb", 2, 50, 4, (0, 2), T_src=61, T_adv=33),
+    # BASELINE config 2 at its own size and length: e2e, 1 utterance of 80x256, 1500 iterations (~7 min of CPU here).
+    # The reference's own 8-thread vs 1-thread runs of this case end 9.3e-5 apart (max |adv|) with per-iteration
+    # losses within 1.5e-5 relative: the trajectory is stable, so the GPU test compares all 1500 losses and the result.
+    # Late in the run the optimiser parks ReLU units near zero (iteration 700: fp32 vs fp64 gradient 1.7e-2 apart), so
+    # several candidate iterations are recorded and those on an edge are dropped.
+    "e2e_T256_it1500": lambda: case("e2e_T256_it1500", "e2e", 1, 256, 1500, (0, 100, 300, 700, 1100, 1400, 1499), skip_edges=True),
+}
+
 if __name__ == "__main__":
-    model_vectors()
-    case("emb_T128_it100", "emb", 1, 128, 100, (0, 1, 10, 99))                      # BASELINE config 1
-    case("e2e_T64_it20", "e2e", 1, 64, 20, (0, 1, 19))
-    case("fb_T64_it20", "fb", 1, 64, 20, (0, 1, 19))
-    case("emb_B2_ragged_cli", "emb", 2, 75, 6, (0, 5), T_adv=131, cli_layout=True)   # odd T, T_adv != T, CLI strides
-    case("e2e_B2_ragged", "e2e", 2, 64, 4, (0, 3), T_src=43, T_adv=90)
-    case("fb_B2_ragged", "fb", 2, 50, 4, (0, 2), T_src=61, T_adv=33)
+    want = sys.argv[1:] or ["model_fwd"] + list(CASES)
+    for name in want:
+        if name == "model_fwd":
+            model_vectors()
+        else:
+            CASES[name]()

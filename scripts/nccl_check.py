@@ -11,7 +11,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from attack_vc_b200 import Engine  # noqa: E402
-from attack_vc_b200.distributed import global_inv_norm, sharded_attack, sharded_header_optimize  # noqa: E402
+from attack_vc_b200.distributed import (global_inv_norm, shard_bounds, sharded_attack, sharded_attack_shards,  # noqa: E402
+                                        sharded_header_optimize)
 from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs  # noqa: E402
 
 
@@ -30,9 +31,12 @@ def main():
         inv = global_inv_norm(kind, B, 128, 80, T_out)
         adv, losses = sharded_attack(eng.attack, kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inv, vc_src=inp.get("vc_src"), w0=inp["w0"])
         full, info = eng.attack(kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, vc_src=inp.get("vc_src"), w0=inp["w0"], want_loss=True)
+        lo, hi = shard_bounds(B, world, rank)                    # the same with every rank holding only its slice
+        adv2, losses2 = sharded_attack_shards(eng.attack, kind, inp["vc_tgt"][lo:hi], inp["adv_tgt"][lo:hi], 0.1, n, B, inv,
+                                              vc_src_local=None if inp.get("vc_src") is None else inp["vc_src"][lo:hi], w0_local=inp["w0"][lo:hi])
         err = float((adv - full).abs().max())
         lerr = float(((losses - info["losses"]).abs() / info["losses"].abs()).max())
-        good = err < 5e-6 and lerr < 1e-4
+        good = err < 5e-6 and lerr < 1e-4 and torch.equal(adv, adv2) and torch.equal(losses, losses2)
         ok &= good
         if rank == 0:
             print(f"sharded_attack {kind} B={B} over {world} GPUs: max |adv - unsharded| {err:.2e}, loss rel err {lerr:.2e} -> {'PASS' if good else 'FAIL'}")

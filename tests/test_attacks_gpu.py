@@ -8,7 +8,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-3            # north_star tolerance (loss and gradient, relative)
-GOLDEN_CASES = ["emb_T128_it100", "e2e_T64_it20", "fb_T64_it20", "emb_B2_ragged_cli", "e2e_B2_ragged", "fb_B2_ragged"]
+GOLDEN_CASES = ["emb_T128_it100", "e2e_T64_it20", "fb_T64_it20", "emb_B2_ragged_cli", "e2e_B2_ragged", "fb_B2_ragged",
+                "e2e_T256_it1500"]          # the last one is BASELINE configs[1] at its own size and length
+# max |adv - reference adv| allowed.  Short runs: fp32 noise.  1500 iterations: the reference's own 8-thread vs
+# 1-thread runs end 9.3e-5 apart (scripts/make_golden.py), so 5e-4 (0.5 % of eps) is ~5x its noise floor.
+ADV_ATOL = {"e2e_T256_it1500": 5e-4}
 
 
 def cuda(g, k, cli=False):
@@ -23,8 +27,73 @@ def grad_rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
+def norm_d(kind, B, T_dec):
+    """elements the reference's MSELoss averages over (attack_utils.py:32,70,114)"""
+    return B * 128 if kind in ("emb", "fb") else B * 80 * T_dec
+
+
+KINK_WINDOW = 2e-5     # |pre-activation| / rms of its layer below which a ReLU unit counts as "on a kink"
+KINK_MAX = 64          # more candidates than this and the arbiter refuses (the window would prove nothing)
+
+
+def assert_grads_per_utterance(oracle, kind, inp, wi, g_gpu, g_ref32, inv_norm, tag=""):
+    """north_star: gradient within 1e-3 relative -- asked of EVERY utterance.  An utterance that misses the fp32 oracle
+    goes to the arbiter, which must PROVE the miss is a ReLU kink and nothing else:
+      1. an fp64 evaluation at the same w (the fp32 oracle may be the side that flipped), else
+      2. the network is piecewise linear and each linear piece has an exact gradient.  The arbiter lists the ReLU units
+         (convs, bank, dense tail, decoder) whose fp64 pre-activation lies within KINK_WINDOW of zero -- the only units
+         fp32 rounding can flip --, measures what each flip does to the fp64 gradient, picks the subset that explains
+         the kernel's gradient (least squares, rounded to flip / no flip) and RE-EVALUATES the fp64 gradient with exactly
+         those units on their other branch: the kernel must match that exact gradient to 1e-3.
+    One flipped unit of a layer with N units moves the gradient by ~1/sqrt(N) (1e-3..2e-2 here), which is why ANY two
+    fp32 implementations -- the reference at 1 vs 8 threads included, scripts/make_golden.py -- disagree in such states.
+    Returns how many utterances needed the arbiter."""
+    g, r = g_gpu.cpu().double(), g_ref32.double()
+    per = ((g - r).flatten(1).norm(dim=1) / r.flatten(1).norm(dim=1))
+    bad = [int(i) for i in torch.nonzero(per >= RTOL).flatten()]
+    if not bad:
+        return 0
+    m64 = oracle.OracleAdaInVC(oracle.SYNTH_CONFIG, seed=0, dtype=torch.float64)
+    for prm in m64.parameters():
+        prm.requires_grad_(False)          # only activations that depend on w are probed (the content encoder is not)
+    src = inp.get("vc_src")
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    for u in bad:
+        args = (kind, m64, inp["vc_tgt"][u:u + 1].double(), inp["adv_tgt"][u:u + 1].double(), 0.1, 1, wi[u:u + 1].double())
+        kw = dict(vc_src=src[u:u + 1].double() if src is not None else None, record_grads=[0], inv_norm=inv_norm)
+
+        def grad64(flip=None):
+            with oracle.ActProbe(flip, record=flip is None) as probe:
+                return oracle.run_attack(*args, **kw)["grads"][0][0], probe
+        g64, probe = grad64()
+        e64 = rel(g[u], g64)
+        if e64 < RTOL:
+            continue
+        cands = []
+        for i, pre in probe.pre.items():
+            thr = KINK_WINDOW * float(pre.pow(2).mean().sqrt())
+            cands += [(i, tuple(int(v) for v in ix)) for ix in torch.nonzero(pre.abs() < thr)]
+        assert 0 < len(cands) <= KINK_MAX, (tag, u, float(per[u]), e64, f"{len(cands)} ReLU units within {KINK_WINDOW} of zero")
+
+        def flip_of(sel):
+            f = {}
+            for i, ix in sel:
+                f.setdefault(i, torch.zeros_like(probe.pre[i], dtype=torch.bool))[ix] = True
+            return f
+        deltas = torch.stack([(grad64(flip_of([c]))[0] - g64).flatten() for c in cands], dim=1)      # [n, n_cands]
+        coef = torch.linalg.lstsq(deltas, (g[u] - g64).flatten().unsqueeze(1)).solution.flatten()
+        sel = [c for c, k in zip(cands, coef) if k > 0.5]
+        assert sel, (tag, u, float(per[u]), e64, "no flip explains the difference", coef.tolist())
+        e_sel = rel(g[u], grad64(flip_of(sel))[0])
+        dist = [float(probe.pre[i][ix].abs() / probe.pre[i].pow(2).mean().sqrt()) for i, ix in sel]
+        print(f"{tag}: utterance {u}: {float(per[u]):.1e} from the fp32 oracle, {e64:.1e} from fp64, {len(cands)} unit(s) on a kink; "
+              f"with {len(sel)} of them (|pre|/rms {', '.join(f'{d:.1e}' for d in dist)}) on the other branch: {e_sel:.1e}")
+        assert e_sel < RTOL, (tag, u, float(per[u]), e64, e_sel, sel, coef.tolist())
+    return len(bad)
+
+
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_attack_vs_golden(engine, golden, name):
+def test_attack_vs_golden(engine, golden, oracle, name):
     g = golden(name)
     kind = name.split("_")[0]
     cli = name.endswith("cli")
@@ -43,7 +112,14 @@ def test_attack_vs_golden(engine, golden, name):
         i = int(key.split("_")[1])
         wi = cuda(g, f"w_{i}", cli)
         _, inf2 = engine.attack(kind, x, at, eps, 1, vc_src=src, w0=wi, want_grad=True, want_loss=True)
-        assert grad_rel(inf2["grad"], g[key]) < RTOL, (key, grad_rel(inf2["grad"], g[key]))
+        if grad_rel(inf2["grad"], g[key]) >= RTOL:      # must be a proven ReLU kink (the golden itself is off every edge in fp64)
+            B = x.shape[0]
+            T_dec = int(engine._lib.avc_decoder_frames(engine._h, src.shape[2])) if src is not None else 0
+            host = {"vc_tgt": x.cpu(), "adv_tgt": at.cpu()}
+            if src is not None:
+                host["vc_src"] = src.cpu()
+            assert_grads_per_utterance(oracle, kind, host, wi.cpu(), inf2["grad"], torch.from_numpy(g[key]), 1.0 / norm_d(kind, B, T_dec),
+                                       tag=f"{name} {key}")
         assert abs(float(inf2["losses"][0]) - g["losses"][i]) <= RTOL * abs(g["losses"][i])
     if f"grad_{n - 1}" in g:
         assert grad_rel(info["grad"], g[f"grad_{n - 1}"]) < 2e-2      # free-running: loose, see above
@@ -51,7 +127,7 @@ def test_attack_vs_golden(engine, golden, name):
     assert adv.shape == x.shape and adv.stride() == x.stride()
     ptb = (adv - x).abs().max().item()
     assert ptb <= eps * (1 + 1e-6)
-    assert float((adv.cpu() - torch.from_numpy(g["adv"])).abs().max()) < 5e-5
+    assert float((adv.cpu() - torch.from_numpy(g["adv"])).abs().max()) < ADV_ATOL.get(name, 5e-5)
     emb = engine.speaker_encoder(adv).cpu().double()
     ref = torch.from_numpy(g["emb_final"]).double()
     cos = torch.nn.functional.cosine_similarity(emb, ref, dim=1)
@@ -59,7 +135,8 @@ def test_attack_vs_golden(engine, golden, name):
 
 
 @pytest.mark.parametrize("kind,B,T,T_src,T_adv,n", [
-    ("emb", 3, 256, None, 200, 8), ("e2e", 2, 128, 100, 128, 5), ("fb", 2, 96, 72, 64, 5), ("emb", 1, 17, None, 19, 3)])
+    ("emb", 3, 256, None, 200, 8), ("e2e", 2, 128, 100, 128, 5), ("fb", 2, 96, 72, 64, 5), ("emb", 1, 17, None, 19, 3),
+    ("emb", 2, 16, None, 16, 3)])        # T=16: the last block's convs see 4 frames > pad 2 (legal in the reference)
 def test_attack_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, T_src, T_adv, n):
     inp = oracle.make_inputs(kind, B, T, seed=21, T_src=T_src, T_adv=T_adv)
     src = inp.get("vc_src")
@@ -70,18 +147,62 @@ def test_attack_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, T_src, T_a
                               want_loss=True, want_grad=True)
     np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL)
     assert float((adv.cpu() - o["adv"]).abs().max()) < 5e-5
-    # teacher-forced gradient at the first and last recorded state; an fp64 oracle at the same w
-    # arbitrates should that state sit on a ReLU edge
-    m64 = oracle.OracleAdaInVC(oracle.SYNTH_CONFIG, seed=0, dtype=torch.float64)
+    # teacher-forced gradient at the first and last recorded state, every utterance; the kink arbiter (fp64 oracle,
+    # proven ReLU flips only) takes the ones that miss
+    T_dec = int(engine._lib.avc_decoder_frames(engine._h, src.shape[2])) if src is not None else 0
+    inv = 1.0 / norm_d(kind, B, T_dec)
     for i in (0, n - 1):
         wi = o["ws"][i]
         _, inf = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, 1, vc_src=gsrc, w0=wi.cuda(), want_grad=True)
-        e32 = grad_rel(inf["grad"], o["grads"][i])
-        if e32 >= RTOL:
-            o64 = oracle.run_attack(kind, m64, inp["vc_tgt"].double(), inp["adv_tgt"].double(), 0.1, 1, wi.double(),
-                                    vc_src=src.double() if src is not None else None, record_grads=[0])
-            e32 = min(e32, grad_rel(inf["grad"], o64["grads"][0]))
-        assert e32 < RTOL, (i, e32)
+        assert_grads_per_utterance(oracle, kind, inp, wi, inf["grad"], o["grads"][i], inv, tag=f"{kind} B{B} T{T} it{i}")
+
+
+def test_too_short_matches_reference_boundary(engine, oracle):
+    """Reflect padding needs pad < length for every conv input: T=8 leaves 2 frames for the last block (pad 2) -> error,
+    as in the reference (PyTorch raises); T=16 is legal (covered above)."""
+    inp = oracle.make_inputs("emb", 1, 8, seed=3)
+    with pytest.raises(ValueError):
+        engine.attack("emb", inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, 1, w0=inp["w0"].cuda())
+
+
+def test_non_default_stream(engine, oracle, cpu_model):
+    """Every entry point orders its own zero fills / uploads on the CALLER's stream, so a non-blocking
+    torch.cuda.Stream works (the legacy default stream does not order against it)."""
+    inp = oracle.make_inputs("e2e", 2, 64, seed=19)
+    x, at, src, w0 = (inp[k].cuda() for k in ("vc_tgt", "adv_tgt", "vc_src", "w0"))
+    ref_emb = engine.speaker_encoder(x)
+    ref_out = engine.inference(src, x)
+    ref_adv = engine.attack("e2e", x, at, 0.1, 4, vc_src=src, w0=w0)
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(st):
+            emb = engine.speaker_encoder(x)
+            out = engine.inference(src, x)
+            adv = engine.attack("e2e", x, at, 0.1, 4, vc_src=src, w0=w0)
+        st.synchronize()
+        assert torch.equal(emb, ref_emb) and torch.equal(out, ref_out) and torch.equal(adv, ref_adv)
+
+
+def test_plan_cache_rebinds_tensors(engine, oracle):
+    """A second call of the same shape reuses the cached plan (buffers, launch lists, instantiated graphs) rebound to
+    the new tensors: results equal a cold engine's, for different inputs, iteration counts and output layouts."""
+    a = oracle.make_inputs("e2e", 1, 64, seed=51)
+    b = oracle.make_inputs("e2e", 1, 64, seed=52)
+    r = []
+    for inp, n in ((a, 5), (b, 9), (a, 5)):
+        x, at, src, w0 = (inp[k].cuda() for k in ("vc_tgt", "adv_tgt", "vc_src", "w0"))
+        adv, info = engine.attack("e2e", x, at, 0.1, n, vc_src=src, w0=w0, want_loss=True)
+        r.append((adv.clone(), info["losses"].clone()))
+    assert torch.equal(r[0][0], r[2][0]) and torch.equal(r[0][1], r[2][1])        # Adam state was reset in between
+    assert not torch.equal(r[0][0], r[1][0])
+    x, at, src, w0 = (b[k].cuda() for k in ("vc_tgt", "adv_tgt", "vc_src", "w0"))
+    xt = x.transpose(1, 2).contiguous().transpose(1, 2)                          # CLI layout through the same cached plan
+    adv_t = engine.attack("e2e", xt, at, 0.1, 9, vc_src=src, w0=w0)
+    assert adv_t.stride() == xt.stride() and torch.equal(adv_t, r[1][0])
+    # a longer call than the cached plan was provisioned for rebuilds it (and still agrees on the common prefix)
+    _, long_info = engine.attack("e2e", x, at, 0.1, 70, vc_src=src, w0=w0, want_loss=True)
+    assert torch.equal(long_info["losses"][:9], r[1][1])
 
 
 def test_graph_and_eager_agree(engine, oracle):
@@ -173,16 +294,15 @@ def test_session_matches_one_shot(engine, oracle):
     assert torch.equal(info["losses"], rinfo["losses"])
 
 
-@pytest.mark.parametrize("kind,B,T,n", [("emb", 10, 256, 4), ("fb", 12, 192, 3), ("e2e", 12, 192, 3)])
+@pytest.mark.parametrize("kind,B,T,n", [("emb", 10, 256, 4), ("fb", 12, 192, 3), ("e2e", 12, 192, 3),
+                                        ("fb", 64, 256, 3)])          # the last one is BASELINE configs[2] at its own size
 def test_tensor_core_plans_vs_host_oracle(engine, oracle, cpu_model, kind, B, T, n):
-    """Batches large enough for the tcgen05 route (>= 2048 GEMM rows: every conv of the plan runs on
-    the tensor cores with the TF32 + BF16-correction split).  Tolerances as north_star states them: every loss within
-    1e-3 (measured ~1e-5), gradient within 1e-3 per utterance.  A piecewise-linear network has states
-    where one ReLU unit of the 128-wide dense tail sits within rounding distance of zero; there ANY two
-    fp32 implementations disagree by ~2e-3 (the reference itself does between 1 and 8 threads,
-    scripts/make_golden.py).  In the e2e / fb attacks the whole gradient passes through that 128-wide
-    bottleneck, so one flipped unit moves an utterance's gradient by 1e-3..1e-2.  The test therefore asks:
-    median utterance < 1e-4, at least 75 % of the utterances < 1e-3, none above 2e-2."""
+    """Batches large enough for the tcgen05 route (>= 2048 GEMM rows: every conv of the plan runs on the tensor cores
+    with the TF32 + BF16-correction split).  Tolerances as north_star states them: every loss within 1e-3 (measured
+    ~1e-5), EVERY utterance's teacher-forced gradient within 1e-3 of the fp32 oracle or, failing that, of an fp64
+    evaluation at the same w (assert_grads_per_utterance: a piecewise-linear network has states where one ReLU unit of
+    the 128-wide dense tail sits within rounding distance of zero, and there the fp32 ORACLE is as likely the side that
+    flipped as the kernel -- the reference itself differs by 6.8e-3 between 1 and 8 threads, scripts/make_golden.py)."""
     inp = oracle.make_inputs(kind, B, T, seed=77)
     src = inp.get("vc_src")
     o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=src,
@@ -193,13 +313,66 @@ def test_tensor_core_plans_vs_host_oracle(engine, oracle, cpu_model, kind, B, T,
     np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL)
     assert float((adv.cpu() - o["adv"]).abs().max()) < 5e-5
     assert float((adv.cpu() - inp["vc_tgt"]).abs().max()) <= 0.1 * (1 + 1e-6)
+    inv = 1.0 / norm_d(kind, B, T)
+    arbitrated = 0
     for i in (0, n - 1):
         wi = o["ws"][i]
         _, inf = engine.attack(kind, inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), 0.1, 1, vc_src=gsrc, w0=wi.cuda(), want_grad=True)
-        g, r = inf["grad"].cpu().double(), o["grads"][i].double()
-        per_utt = ((g - r).flatten(1).norm(dim=1) / r.flatten(1).norm(dim=1))
-        assert float(per_utt.median()) < 1e-4, per_utt
-        assert int((per_utt >= RTOL).sum()) <= len(per_utt) // 4 and float(per_utt.max()) < 2e-2, per_utt
+        arbitrated += assert_grads_per_utterance(oracle, kind, inp, wi, inf["grad"], o["grads"][i], inv, tag=f"{kind} B{B} it{i}")
+    print(f"tensor-core plan {kind} B={B} T={T}: {arbitrated} of {2 * B} utterance gradients needed the fp64 arbiter")
+    emb = engine.speaker_encoder(adv).cpu().double()
+    with torch.no_grad():
+        ref = cpu_model.speaker_encoder(o["adv"]).double()
+    assert float(torch.nn.functional.cosine_similarity(emb, ref, dim=1).min()) >= 0.999
+
+
+def test_cfg4_per_gpu_shard_vs_oracle_subbatch(engine, oracle, cpu_model):
+    """BASELINE configs[3] as one GPU of eight sees it: emb_attack on 512 utterances of 80x512 with the GLOBAL MSE
+    normaliser 1/(4096*128).  Utterances are independent given that constant, so the oracle runs a 32-utterance
+    sub-batch (spread over the shard) with the same normaliser: results, teacher-forced gradients (fp64-arbitrated per
+    utterance) and final-embedding cosine of those 32 must match the B=512 tcgen05 plan."""
+    B, T, n = 512, 512, 3
+    inv = 1.0 / (4096 * 128)
+    inp = oracle.make_inputs("emb", B, T, seed=404)
+    idx = torch.arange(0, B, 16)                                         # 32 utterances across the shard
+    sub = {k: v[idx] for k, v in inp.items()}
+    o = oracle.run_attack("emb", cpu_model, sub["vc_tgt"], sub["adv_tgt"], 0.1, n, sub["w0"], record_grads=[0, n - 1],
+                          record_w=True, inv_norm=inv)
+    x, at = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda()
+    adv, info = engine.attack("emb", x, at, 0.1, n, w0=inp["w0"].cuda(), inv_norm=inv, want_loss=True)
+    assert torch.isfinite(info["losses"]).all()
+    assert float((adv.cpu()[idx] - o["adv"]).abs().max()) < 5e-5
+    assert float((adv - x).abs().max()) <= 0.1 * (1 + 1e-6)
+    arbitrated = 0
+    for i in (0, n - 1):
+        w_all = inp["w0"].clone()
+        w_all[idx] = o["ws"][i]
+        _, inf = engine.attack("emb", x, at, 0.1, 1, w0=w_all.cuda(), inv_norm=inv, want_grad=True)
+        arbitrated += assert_grads_per_utterance(oracle, "emb", sub, o["ws"][i], inf["grad"][idx.cuda()], o["grads"][i], inv, tag=f"cfg4 it{i}")
+    print(f"cfg4 shard: {arbitrated} of 64 utterance gradients needed the fp64 arbiter")
+    emb = engine.speaker_encoder(adv[idx.cuda()]).cpu().double()
+    with torch.no_grad():
+        ref = cpu_model.speaker_encoder(o["adv"]).double()
+    assert float(torch.nn.functional.cosine_similarity(emb, ref, dim=1).min()) >= 0.999
+
+
+def test_cfg2_free_running_vs_host_oracle(engine, oracle, cpu_model):
+    """BASELINE configs[1] at its own size against the HOST oracle run on this box (the committed golden
+    e2e_T256_it1500 pins the same case against the reference run in the build container): 60 free-running iterations
+    of per-iteration loss, teacher-forced gradients at 3 iterations, result, cosine, bound."""
+    inp = oracle.make_inputs("e2e", 1, 256, seed=1)
+    n = 60
+    o = oracle.run_attack("e2e", cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=inp["vc_src"],
+                          record_grads=[0, 30, n - 1], record_w=True)
+    x, at, src = inp["vc_tgt"].cuda(), inp["adv_tgt"].cuda(), inp["vc_src"].cuda()
+    adv, info = engine.attack("e2e", x, at, 0.1, n, vc_src=src, w0=inp["w0"].cuda(), want_loss=True)
+    np.testing.assert_allclose(info["losses"].cpu().double().numpy(), o["losses"].numpy(), rtol=RTOL)
+    assert float((adv.cpu() - o["adv"]).abs().max()) < 5e-5
+    assert float((adv - x).abs().max()) <= 0.1 * (1 + 1e-6)
+    inv = 1.0 / norm_d("e2e", 1, 256)
+    for i in (0, 30, n - 1):
+        _, inf = engine.attack("e2e", x, at, 0.1, 1, vc_src=src, w0=o["ws"][i].cuda(), want_grad=True)
+        assert_grads_per_utterance(oracle, "e2e", inp, o["ws"][i], inf["grad"], o["grads"][i], inv, tag=f"cfg2 it{i}")
     emb = engine.speaker_encoder(adv).cpu().double()
     with torch.no_grad():
         ref = cpu_model.speaker_encoder(o["adv"]).double()

@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from attack_vc_b200.distributed import global_inv_norm, shard_bounds, sharded_attack, sharded_header_optimize
+from attack_vc_b200.distributed import (global_inv_norm, shard_bounds, sharded_attack, sharded_attack_shards,
+                                        sharded_header_optimize)
 
 
 def test_shard_bounds_cover_batch():
@@ -48,6 +49,12 @@ def _worker(rank, world, port, kind, q):
         inv = global_inv_norm(kind, B, 128, 80, T_out)
         adv, losses = sharded_attack(_oracle_attack, kind, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inv,
                                      vc_src=inp.get("vc_src"), w0=inp["w0"])
+        # the pre-sliced form (every rank holds only its slice -- what bench.py's sharded leg uses) must agree bit for bit
+        lo, hi = shard_bounds(B, world, rank)
+        loc = {k: v[lo:hi] for k, v in inp.items()}
+        adv2, losses2 = sharded_attack_shards(_oracle_attack, kind, loc["vc_tgt"], loc["adv_tgt"], 0.1, n, B, inv,
+                                              vc_src_local=loc.get("vc_src"), w0_local=loc["w0"])
+        assert torch.equal(adv, adv2) and torch.equal(losses, losses2)
         if rank == 0:
             q.put((adv.numpy().copy(), losses.numpy().copy()))
     finally:
