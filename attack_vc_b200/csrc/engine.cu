@@ -21,6 +21,7 @@
 #include "host_util.h"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "conv_wgrad.cuh"
 #include "elementwise.cuh"
 
@@ -220,7 +221,8 @@ struct avc_handle {
   std::string err;
   long long launches = 0;
   int launches_per_iter = 0;
-  int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction), 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only)
+  int conv_impl = 0;   // 0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction), 3 CUDA cores without the small-M kernel, 4 tcgen05 single TF32 pass (measurement only),
+                       // 6 tcgen05 with the role-swapped N = 256 kernel forced, 7 tcgen05 with the N = 128 kernel forced
   long long tc_min_rows = 2048;   // auto: GEMM rows from which the tensor-core kernel is used (env AVC_TC_MIN_ROWS)
   // Finished attack plans (buffers, launch lists, instantiated graphs) kept for the next call of the same shape: building
   // and capturing a plan costs ~1 ms, as much as a few iterations at batch 1.  Small plans only, a handful of them.
@@ -263,6 +265,7 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(norm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
 }
 
 // small-M path: every window resident, deep weight ring (conv_simt.cuh: conv_small_kernel)
@@ -391,11 +394,27 @@ bool want_tc(const avc_handle* h, const ConvArgs& a, const TcOp& op) {
   const int impl = h->conv_impl;
   if (impl == 1 || impl == 3) return false;
   if (!tc_supported(a, op)) return false;
-  if (impl == 2 || impl == 4 || impl == 5) return true;
+  if (impl == 2 || impl == 4 || impl == 5 || impl == 6 || impl == 7) return true;
   return (long long)a.B * (a.T_y + op.kmax - 1) >= h->tc_min_rows;
 }
 
-void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st) {
+// which tcgen05 kernel: the role-swapped N = 256 kernel (conv_tc2.cuh) whenever the N = 128 kernel would need more than one
+// wave of 128-row tiles; below that a 256-row tile only halves the SMs in use.  tc2: 0 auto, 1 never, 2 always (impl 6)
+bool use_tc2(const TcArgs& t, int sm_count, int tc2) {
+  static const int env = getenv("AVC_TC2") ? atoi(getenv("AVC_TC2")) : 0;
+  const int mode = tc2 ? tc2 : env;
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  return ((t.Mv + kTcM - 1) / kTcM) * t.n_pass > sm_count;
+}
+
+void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st, int tc2 = 0) {
+  if (use_tc2(t, sm_count, tc2)) {
+    const long long work = ((t.Mv + kT2N - 1) / kT2N) * t.n_pass;
+    dim3 grid((unsigned)std::min<long long>(work, sm_count), 1, 1);   // persistent: one CTA per SM
+    launch_k(conv_tc2_kernel, grid, kT2Threads, tc2_smem_bytes(), st, t);
+    return;
+  }
   const size_t smem = tc_smem_bytes();
   const long long n_mt = (t.Mv + kTcM - 1) / kTcM;
   static const int pair_env = getenv("AVC_TC_PAIR") ? atoi(getenv("AVC_TC_PAIR")) : 0;
@@ -484,7 +503,8 @@ struct Emitter {
       float* side = side_n ? mem->f(side_n) : nullptr;
       const TcArgs t = tc_make_args(ac, op, side, hh->conv_impl == 4 ? 1 : hh->conv_impl == 5 ? 4 : 3);
       const int smc0 = hh->sm_count;
-      l.fn = [t, smc0](cudaStream_t st) { launch_conv_tc(t, smc0, st); };
+      const int tc2 = hh->conv_impl == 6 ? 2 : hh->conv_impl == 7 ? 1 : 0;      // 6: N = 256 kernel everywhere, 7: N = 128 kernel everywhere
+      l.fn = [t, smc0, tc2](cudaStream_t st) { launch_conv_tc(t, smc0, st, tc2); };
       out->push_back(std::move(l));
       if (t.side) {
         const int smc = hh->sm_count;

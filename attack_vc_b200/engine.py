@@ -487,16 +487,16 @@ _ENGINES: "weakref.WeakKeyDictionary[nn.Module, Tuple[Tuple, Engine]]" = weakref
 
 
 def _fingerprint(model: nn.Module) -> Tuple:
-    """(storage pointer, autograd version, a content probe) per parameter.  The probe -- the sum of up to 64 evenly spaced
-    elements, computed on the device and fetched in ONE transfer -- also catches in-place edits through ``p.data``, which do
-    not bump ``_version``.  Edits that keep all probed elements unchanged need ``invalidate_engine(model)``."""
-    ps = list(model.parameters())
+    """(storage pointer, autograd version, 2-norm) per parameter.  The norms -- ONE multi-tensor kernel over all
+    parameters and ONE device-to-host transfer, ~0.1 ms for the 4.9 M parameters of AdaIN-VC -- also catch in-place
+    edits through ``p.data``, which do not bump ``_version``.  An edit that preserves every tensor's norm needs
+    ``invalidate_engine(model)``."""
+    ps = [p.detach() for p in model.parameters()]
     if not ps:
         return ()
     with torch.no_grad():
-        probes = torch.stack([p.detach().reshape(-1)[:: max(1, p.numel() // 64)][:64].double().sum() for p in ps])
-    vals = probes.cpu().tolist()
-    return tuple((p.data_ptr(), p._version, v) for p, v in zip(ps, vals))
+        norms = torch.stack(torch._foreach_norm(ps)).double().cpu().tolist()
+    return tuple((p.data_ptr(), p._version, v) for p, v in zip(ps, norms))
 
 
 def invalidate_engine(model: nn.Module) -> None:

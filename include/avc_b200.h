@@ -159,7 +159,8 @@ int32_t avc_decoder_frames(const avc_handle* h, int32_t T_src);
  * w is PyTorch layout [c_out, c_in, k].  y [B, ceil(T/stride), c_out]. */
 int avc_conv1d_fwd(avc_handle* h, const float* x, const float* w, const float* bias, float* y,
                    int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride,
-                   int32_t impl /*0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction MMA), 3 fp32 CUDA cores without the small-M kernel*/, void* stream);
+                   int32_t impl /*0 auto, 1 fp32 CUDA cores, 2 tcgen05 (TF32 + BF16 correction MMA; kernel picked by size), 3 fp32 CUDA cores without the small-M kernel,
+                                   6 tcgen05 role-swapped N=256 kernel, 7 tcgen05 N=128 kernel*/, void* stream);
 /* autograd of the above w.r.t. x: dy [B,T_out,c_out] -> dx [B,T,c_in] */
 int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx,
                      int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride,

@@ -160,11 +160,12 @@ TC_CASES = CONV_CASES + [
 ]
 
 
-@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3)])
+@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3), (6, 3e-6), (7, 3e-6)])
 @pytest.mark.parametrize("B,T,ci,co,k,s", TC_CASES)
 def test_conv1d_fwd_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
-    """tcgen05 path: TF32 hi*hi + BF16 correction MMA with chunked accumulation (impl 2) must be fp32-grade; a single TF32 pass
-    (impl 4, measurement only) is ~2e-4."""
+    """tcgen05 path: TF32 hi*hi + BF16 correction MMA with chunked accumulation must be fp32-grade -- impl 2 (kernel picked by
+    size), 6 (role-swapped N = 256 kernel, conv_tc2.cuh) and 7 (N = 128 kernel, conv_tc.cuh); a single TF32 pass (impl 4,
+    measurement only) is ~2e-4."""
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k)
     x = torch.randn(B, T, ci, device="cuda", generator=g)
     w = torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5
@@ -178,7 +179,7 @@ def test_conv1d_fwd_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
     assert not torch.equal(y, y1), "tensor-core route silently fell back to the CUDA-core kernel"
 
 
-@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3)])
+@pytest.mark.parametrize("impl,tol", [(2, 3e-6), (4, 3e-3), (6, 3e-6), (7, 3e-6)])
 @pytest.mark.parametrize("B,T,ci,co,k,s", TC_CASES)
 def test_conv1d_dgrad_tensor_core(engine, B, T, ci, co, k, s, impl, tol):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 7)
