@@ -19,8 +19,10 @@
 //   warp 0      weight producer: one bulk copy (TMA engine, mbarrier complete_tx) per 16 KB plane of a stage, ring of 5
 //   warp 1      MMA issuer
 //   warps 2-7   window loaders (192 threads): (row, k-step) units of 32 B, row pointers in a shared-memory table
-//   warps 8-15  drain (TMEM -> fp32 chunk sums in registers) + epilogue; setmaxnreg gives them 168 registers, the rest 88
+//   warps 8-15  drain (TMEM -> fp32 chunk sums in registers) + epilogue; setmaxnreg gives them 160 registers, the rest 96
 #pragma once
+#include <type_traits>
+
 #include "conv_tc.cuh"
 
 namespace avc {
@@ -36,62 +38,110 @@ constexpr int kT2WPlaneBytes = (kTcKB / 4) * kTcNMax * 16;        // 16 KB
 constexpr int kT2AccBufs = 2;                                     // 2 x 256 TMEM columns
 
 inline size_t tc2_smem_bytes() {
-  return (size_t)kT2XStages * 2 * kT2XPlane * 4 + (size_t)kT2WSlots * kT2WPlaneBytes + 32 * 8 + (size_t)2 * kT2Rows * 8 + (size_t)kT2N * (16 + 4);
+  return (size_t)kT2XStages * 2 * kT2XPlane * 4 + (size_t)kT2WSlots * kT2WPlaneBytes + 32 * 8 + (size_t)2 * kT2Rows * 8 + (size_t)kT2N * 5 * 4;
 }
 
 // ---- epilogue ------------------------------------------------------------------------------------
 // Row descriptors: everything that depends on the virtual row (utterance, output row, skip rows and their weight) is worked out
-// ONCE per tile, one row per drain thread, and kept in shared memory as element offsets; the epilogue reads a row's descriptor
-// with one broadcast LDS.128.  (Every lane of every drain warp needs every row's addresses: computing them per lane would cost
-// a 64-bit division per row and lane.)
-struct T2Desc { int yoff, y2off, g0, g1; };   // yoff: -1 dead row, <= -2: dgrad halo row at side offset -2 - yoff; g0/g1: -1 = none
+// ONCE per tile, one row per drain thread, and kept in shared memory as element offsets (five arrays of kT2N words); the epilogue
+// reads them with broadcast LDS.  (Every lane of every drain warp needs every row's addresses: computing them per lane would
+// cost a 64-bit division per row and lane.)  The epilogue itself is branch-free straight-line code -- predicated stores, the
+// operand loads of eight rows in flight before the first is consumed: the first version branched per row (dead / halo / main)
+// and ran one row at a time behind an LDS -> branch -> STG chain, 25-60k clk per tile (profiles/r02b_conv_tc2_roles.txt).
+constexpr int kT2DescWords = 5;     // yoff | y2off | g0 | g1 | rs
+// yoff: -1 dead row, <= -2: dgrad halo row at side-buffer offset -2 - yoff; g0 / g1: -1 = none
 
-__device__ __forceinline__ void t2_make_desc(const TcArgs& p, const TcPass& ps, long long u, T2Desc& d, float& rs) {
+__device__ __forceinline__ void t2_make_desc(const TcArgs& p, const TcPass& ps, long long u, int* __restrict__ tab, int row) {
   const TcRow r = tc_row_info(p, ps, u);
-  d.yoff = -1; d.y2off = 0; d.g0 = -1; d.g1 = -1; rs = r.rs;
-  if (r.kind == 2) d.yoff = -2 - (int)(((long long)r.b * (p.halo_l + p.halo_r) + r.o) * p.side_n);
-  if (r.kind != 1) return;
-  d.yoff = (int)((long long)r.b * p.y_bs + (long long)r.o * p.y_rs);
-  if (p.Y2) d.y2off = (int)((long long)r.b * p.y2_bs + (long long)r.o * p.y2_rs);
-  if (p.Om) d.g0 = (int)((long long)r.b * p.om_bs + (long long)r.o * p.om_rs);
-  else if (p.res.mode != RES_NONE) {
-    d.g0 = (int)((long long)r.b * p.res.bs + (long long)r.t0 * p.res.rs);
-    if (r.t1 >= 0) d.g1 = (int)((long long)r.b * p.res.bs + (long long)r.t1 * p.res.rs);
+  int yoff = -1, y2off = 0, g0 = -1, g1 = -1;
+  if (r.kind == 2) yoff = -2 - (int)(((long long)r.b * (p.halo_l + p.halo_r) + r.o) * p.side_n);
+  if (r.kind == 1) {
+    yoff = (int)((long long)r.b * p.y_bs + (long long)r.o * p.y_rs);
+    if (p.Y2) y2off = (int)((long long)r.b * p.y2_bs + (long long)r.o * p.y2_rs);
+    if (p.Om) g0 = (int)((long long)r.b * p.om_bs + (long long)r.o * p.om_rs);
+    else if (p.res.mode != RES_NONE) {
+      g0 = (int)((long long)r.b * p.res.bs + (long long)r.t0 * p.res.rs);
+      if (r.t1 >= 0) g1 = (int)((long long)r.b * p.res.bs + (long long)r.t1 * p.res.rs);
+    }
   }
+  tab[row] = yoff; tab[kT2N + row] = y2off; tab[2 * kT2N + row] = g0; tab[3 * kT2N + row] = g1; tab[4 * kT2N + row] = __float_as_int(r.rs);
 }
 
+// plain (non-volatile) shared loads: the descriptors are read-only while an epilogue runs, so the compiler may batch and hoist
+// them; `base` is produced by a volatile asm AFTER the barrier that publishes the table, which keeps them below it
+__device__ __forceinline__ int t2_lds(uint32_t addr) { int v; asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+// predicated store without a branch around the arithmetic that feeds it: rows stay independent instruction streams
+__device__ __forceinline__ void t2_st_if(float* ptr, float v, bool ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(ptr), "f"(v), "r"((int)ok));
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // MODE: 0 plain, 1 act' mask on the output (Om), 2 one skip row (RES_SAME / RES_UP / RES_POOL_BWD), 3 two skip rows (RES_POOL / RES_UP_BWD)
-template <int MODE>
-__device__ __forceinline__ void t2_epilogue(const TcArgs& p, const float (&acc)[128], const T2Desc* __restrict__ desc,
-                                            const float* __restrict__ rsv, int c, bool c_ok) {
+// HALO: dgrad launches whose extended rows go to the side buffer.
+// The finished sums are read back from TMEM eight rows at a time in a ROLLED loop (t_sum: this warp's 32 lanes x 128 columns):
+// a fully unrolled epilogue over 128 accumulator registers is 28 KB of straight-line code per variant that every drain warp
+// executes exactly once per tile, and it ran at the speed of instruction fetch (10-58k clk per tile, profiles/r02b_conv_tc2_roles.txt).
+template <int MODE, bool HALO>
+__device__ __forceinline__ void t2_epilogue(const TcArgs& p, uint32_t t_sum, uint32_t tab, int c, bool c_ok) {
   const float bias = (p.bias && c_ok) ? p.bias[c] : 0.f;
-  const float* __restrict__ G = MODE == 1 ? p.Om : p.res.R;
-  constexpr int NB = 8;                      // rows whose operand loads are in flight before the first is consumed
-#pragma unroll
+  const float* G = MODE == 1 ? p.Om : p.res.R;
+  float* const Y = p.Y + c;
+  float* const Y2 = p.Y2 ? p.Y2 + c : nullptr;
+  float* const S = HALO ? p.side + c : nullptr;
+  const bool act = p.act != 0, has_y2 = p.Y2 != nullptr;
+  const float slope = p.slope;
+  // rows whose operand loads are in flight before the first is consumed: the sums wait in TMEM, so the registers are free
+  // for 32 (two-operand modes: 16) rows of operands -- 8 drain warps x 32 loads cover the ~1k clk of an L2 / HBM round trip
+  constexpr int NB = MODE == 3 ? 16 : 32;
+#pragma unroll 1
   for (int r0 = 0; r0 < 128; r0 += NB) {
+    uint32_t v[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j += 16) tmem_ld16(t_sum + r0 + j, *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
     float ga[NB], gb[NB];
     if (MODE >= 1) {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        const int4 d = *reinterpret_cast<const int4*>(desc + r0 + j);
+        const int g0 = t2_lds(tab + 4 * (2 * kT2N + r0 + j));
         ga[j] = 0.f; gb[j] = 0.f;
-        if (c_ok && d.z >= 0) ga[j] = G[d.z + c];
-        if (MODE == 3 && c_ok && d.w >= 0) gb[j] = G[d.w + c];
+        if (c_ok && g0 >= 0) ga[j] = G[g0 + c];
+        if (MODE == 3) {
+          const int g1 = t2_lds(tab + 4 * (3 * kT2N + r0 + j));
+          if (c_ok && g1 >= 0) gb[j] = G[g1 + c];
+        }
       }
     }
+    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      const int4 d = *reinterpret_cast<const int4*>(desc + r0 + j);
-      if (!c_ok || d.x == -1) continue;
-      float x = acc[r0 + j];
-      if (d.x < -1) { p.side[(-2 - d.x) + c] = x; continue; }
-      x += bias;
-      if (MODE == 1) x *= (ga[j] > 0.f ? 1.f : p.slope);
-      if (p.act) x = x > 0.f ? x : x * p.slope;
-      if (p.Y2) p.Y2[d.y + c] = x;
-      if (MODE == 2) x += ga[j] * rsv[r0 + j];
-      if (MODE == 3) x += (ga[j] + gb[j]) * rsv[r0 + j];
-      p.Y[d.x + c] = x;
+      const int yo = t2_lds(tab + 4 * (r0 + j));
+      const float raw = __uint_as_float(v[j]);
+      float x = raw + bias;
+      if (MODE == 1) x *= (ga[j] > 0.f ? 1.f : slope);
+      x = (act && !(x > 0.f)) ? x * slope : x;
+      const bool main_row = c_ok && yo >= 0;
+      if (MODE >= 2) {
+        if (has_y2) t2_st_if(Y2 + t2_lds(tab + 4 * (kT2N + r0 + j)), x, main_row);
+        const float rs = __int_as_float(t2_lds(tab + 4 * (4 * kT2N + r0 + j)));
+        x += (MODE == 3 ? ga[j] + gb[j] : ga[j]) * rs;
+      }
+      if (HALO) {
+        const bool halo_row = c_ok && yo < -1;
+        t2_st_if(halo_row ? S + (-2 - yo) : Y + yo, halo_row ? raw : x, main_row || halo_row);
+      } else {
+        t2_st_if(Y + yo, x, main_row);
+      }
     }
   }
 }
@@ -103,8 +153,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
   unsigned char* Ws = t2_smem + (size_t)kT2XStages * 2 * kT2XPlane * 4;                        // [5 slots][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ws + (size_t)kT2WSlots * kT2WPlaneBytes);
   long long* rowtab = reinterpret_cast<long long*>(bars + 32);                                 // [2][kT2Rows]: element offsets of the window rows (A, mask)
-  T2Desc* desc = reinterpret_cast<T2Desc*>(rowtab + 2 * kT2Rows);                               // [kT2N] output row descriptors of the current tile
-  float* rsv = reinterpret_cast<float*>(desc + kT2N);                                          // [kT2N] skip-row weights
+  int* desc = reinterpret_cast<int*>(rowtab + 2 * kT2Rows);                                   // [kT2DescWords][kT2N] output row descriptors of the current tile
   const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](int s) { return bar0 + 8 * s; };
   auto x_empty = [&](int s) { return bar0 + 8 * (2 + s); };
@@ -134,7 +183,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
   const int w_first = (int)blockIdx.x, w_step = (int)gridDim.x;
 
   if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (warp == 0) {
       // ===== weight producer =====
       if (lane == 0) {
@@ -163,6 +212,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
       int sx = 0, sw = 0; uint32_t px = 0, pw = 0;
       int chunk = 0;
       const int terms = p.terms;
+#ifdef AVC_TC_PROFILE
+      long long st_x = 0, st_w = 0, st_acc = 0, st_issue = 0, t_begin = clock64(), tq;   // build with -DAVC_TC_PROFILE, run with AVC_TC_DBG=32
+#define T2P(x) x
+#else
+#define T2P(x)
+#endif
       const uint32_t x_base = smem_u32(Xs), w_base = smem_u32(Ws);
       constexpr uint32_t x_lbo = kT2Rows * 16;
       constexpr uint64_t x_ks = (uint64_t)((2 * x_lbo) >> 4), x_lo_off = (uint64_t)((kT2XPlane * 4) >> 4);
@@ -179,18 +234,24 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
         for (int s = ps.s_begin; s < ps.s_end; ++s) {
           const TcStage e = p.st[s];
           if (e.flags & kTcKbFirst) {
+            T2P(tq = clock64();)
             mbar_wait(x_full(sx), px);
+            T2P(if (st_issue == 0) t_begin = clock64(); else st_x += clock64() - tq;)
             x_desc0 = tc_desc(x_base + (uint32_t)sx * (2 * kT2XPlane * 4), x_lbo, 128);
           }
           if (e.flags & kTcChunkFirst) {
             const int buf = chunk % kT2AccBufs;
+            T2P(tq = clock64();)
             mbar_wait(acc_empty0 + 8 * buf, ((chunk / kT2AccBufs) & 1) ^ 1);
+            T2P(st_acc += clock64() - tq;)
             d_tmem = tmem_base + (uint32_t)(buf * kT2N);
             acc = 0;
           }
           const int nks = e.nks;
           // plane 0: kind::tf32  D^T += W_hi * X_hi^T
+          T2P(tq = clock64();)
           mbar_wait(w_full(sw), pw);
+          T2P(st_w += clock64() - tq; tq = clock64();)
           tc_fence_after();
           {
             uint64_t dw = tc_desc(w_base + (uint32_t)sw * kT2WPlaneBytes, w_lbo, 128);
@@ -205,7 +266,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
             if (++sw == kT2WSlots) { sw = 0; pw ^= 1; }
           }
           // plane 1: kind::f16 (bf16, K = 16)  D^T += [W_hi | W_lo] * [X_lo | X_hi]^T
+          T2P(st_issue += clock64() - tq; tq = clock64();)
           mbar_wait(w_full(sw), pw);
+          T2P(st_w += clock64() - tq; tq = clock64();)
           tc_fence_after();
           {
             uint64_t dw = tc_desc(w_base + (uint32_t)sw * kT2WPlaneBytes, w_lbo, 128);
@@ -225,10 +288,16 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
             if (++sw == kT2WSlots) { sw = 0; pw ^= 1; }
           }
           __syncwarp();
+          T2P(st_issue += clock64() - tq;)
           if (e.flags & kTcChunkLast) ++chunk;
           if (e.flags & kTcKbLast) { if (++sx == kT2XStages) { sx = 0; px ^= 1; } }
         }
       }
+#ifdef AVC_TC_PROFILE
+      if ((p.dbg & 32) && blockIdx.x == 0 && lane == 0)
+        printf("[conv_tc2 cta0] issuer: total %lld clk, wait x_full %lld, wait w_full %lld, wait acc_empty %lld, issue %lld (items %d)\n",
+               clock64() - t_begin, st_x, st_w, st_acc, st_issue, (n_work + (int)gridDim.x - 1) / (int)gridDim.x);
+#endif
     } else {
       // ===== window loaders (192 threads) =====
       // unit q of a K block = (row q / 4, k-step q % 4): four consecutive lanes read the 128 contiguous bytes of one row's
@@ -236,6 +305,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
       pdl_wait();
       const int tl = threadIdx.x - 64;                    // 0..191
       int sx = 0; uint32_t px = 0;
+#ifdef AVC_TC_PROFILE
+      long long l_wait = 0, l_tab = 0, l_t0 = clock64(), lq;
+#endif
       for (int wk = w_first; wk < n_work; wk += w_step) {
         const TcPass& ps = p.pass[wk % p.n_pass];
         const long long v0 = (long long)(wk / p.n_pass) * kT2N;
@@ -243,6 +315,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
           const TcGroup& G = p.g[gi];
           const int n_rows = kT2N + G.n_taps - 1;
           // row table: element offset of every window row in A (and in the mask tensor), -1 = zeros
+          T2P(lq = clock64();)
           asm volatile("bar.sync 1, %0;" ::"r"(kT2Loaders) : "memory");          // the previous group's readers are done
           for (int i = tl; i < n_rows; i += kT2Loaders) {
             const long long u = v0 + i;
@@ -258,6 +331,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
             rowtab[kT2Rows + i] = (ok && p.Mk) ? (long long)b * p.m_bs + (long long)rr * p.m_rs + G.a_ch_off : -1;
           }
           asm volatile("bar.sync 1, %0;" ::"r"(kT2Loaders) : "memory");
+          T2P(l_tab += clock64() - lq;)
           const int nkb = (G.kc + kTcKB - 1) / kTcKB;
           const int n_units = n_rows * 4;
           const bool masked = p.Mk != nullptr;
@@ -279,32 +353,35 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
             float* hi = Xs + (size_t)sx * 2 * kT2XPlane;
             float* lo = hi + kT2XPlane;
             bool waited = false;
-#pragma unroll 1
-            for (int q0 = tl; q0 < n_units; q0 += 3 * kT2Loaders) {
-              float4 va[3], vb[3], ma[3], mb[3];
+            // NU units per round: every load of a round is in flight before the first is consumed (and, for the first round,
+            // before the thread waits for the stage to be released)
+            auto round = [&](auto nu_tag, int q0) {
+              constexpr int NU = decltype(nu_tag)::value;
+              float4 va[NU], vb[NU], ma[NU > 3 ? 1 : NU], mb[NU > 3 ? 1 : NU];
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
+              for (int j = 0; j < NU; ++j) {
                 const int q = q0 + j * kT2Loaders;
-                va[j] = f4zero(); vb[j] = f4zero(); ma[j] = f4zero(); mb[j] = f4zero();
+                va[j] = f4zero(); vb[j] = f4zero();
+                if (NU <= 3) { ma[j] = f4zero(); mb[j] = f4zero(); }
                 if (q < n_units) {
                   const int ks = q & 3;
                   const long long o = rowtab[q >> 2];
                   if (o >= 0 && 8 * ks < kbs) {
                     const float* src = p.A + o + kb0 + 8 * ks;
                     va[j] = ld4(src); vb[j] = ld4(src + 4);
-                    if (masked) { const float* ms = p.Mk + rowtab[kT2Rows + (q >> 2)] + kb0 + 8 * ks; ma[j] = ld4(ms); mb[j] = ld4(ms + 4); }
+                    if (NU <= 3) { const float* ms = p.Mk + rowtab[kT2Rows + (q >> 2)] + kb0 + 8 * ks; ma[j] = ld4(ms); mb[j] = ld4(ms + 4); }
                   }
                 }
               }
-              if (!waited) { mbar_wait(x_empty(sx), px ^ 1); waited = true; }     // the first loads fly while the stage is released
+              if (!waited) { T2P(lq = clock64();) mbar_wait(x_empty(sx), px ^ 1); waited = true; T2P(l_wait += clock64() - lq;) }
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
+              for (int j = 0; j < NU; ++j) {
                 const int q = q0 + j * kT2Loaders;
                 if (q < n_units) {
                   const int ks = q & 3, row = q >> 2;
                   if (8 * ks < kbs) {
                     float4 a = va[j], b = vb[j];
-                    if (masked) { a = dact4mul(a, ma[j], p.slope); b = dact4mul(b, mb[j], p.slope); }
+                    if (NU <= 3) { a = dact4mul(a, ma[j], p.slope); b = dact4mul(b, mb[j], p.slope); }
                     const float4 ha = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
                     const float4 hb = make_float4(tf32_hi(b.x), tf32_hi(b.y), tf32_hi(b.z), tf32_hi(b.w));
                     st4(hi + ((size_t)(2 * ks) * kT2Rows + row) * 4, ha);
@@ -314,6 +391,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
                   }
                 }
               }
+            };
+            if (masked) {
+#pragma unroll 1
+              for (int q0 = tl; q0 < n_units; q0 += 3 * kT2Loaders) round(std::integral_constant<int, 3>{}, q0);
+            } else {
+#pragma unroll 1
+              for (int q0 = tl; q0 < n_units; q0 += 6 * kT2Loaders) round(std::integral_constant<int, 6>{}, q0);
             }
             if (!waited) mbar_wait(x_empty(sx), px ^ 1);
             fence_proxy_async();
@@ -323,18 +407,26 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
           }
         }
       }
+#ifdef AVC_TC_PROFILE
+      if ((p.dbg & 32) && blockIdx.x == 0 && tl == 0)
+        printf("[conv_tc2 cta0] loader: total %lld clk, row tables %lld, wait x_empty %lld\n", clock64() - l_t0, l_tab, l_wait);
+#endif
     }
   } else {
     // ===== drain warps (256 threads): chunk sums in registers, then the epilogue straight from registers =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     pdl_wait();
     const int quad = warp & 3, half = (warp - 8) >> 2;
     const int dt = threadIdx.x - 256;                   // 0..255: the tile row whose descriptor this thread works out
     int chunk = 0;
+#ifdef AVC_TC_PROFILE
+    long long d_wait = 0, d_ld = 0, d_epi = 0, d_desc = 0, d_t0 = clock64(), dq;
+#endif
     int mode = 0;
     if (p.Om) mode = 1;
     else if (p.res.mode == RES_POOL || p.res.mode == RES_UP_BWD) mode = 3;
     else if (p.res.mode != RES_NONE) mode = 2;
+    if (p.side) mode += 4;
     for (int wk = w_first; wk < n_work; wk += w_step) {
       const TcPass& ps = p.pass[wk % p.n_pass];
       const long long v0 = (long long)(wk / p.n_pass) * kT2N;
@@ -342,30 +434,38 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
       const bool c_ok = cl < ps.N;
       const bool q_ok = quad * 32 < ps.N;               // this warp's lanes hold any valid channel at all
       // ---- row descriptors of this tile (while the first chunk's MMAs run) ----
+      T2P(dq = clock64();)
       asm volatile("bar.sync 2, 256;" ::: "memory");    // the previous tile's epilogue has read its descriptors
       {
-        T2Desc d; float rs;
-        t2_make_desc(p, ps, v0 + dt, d, rs);
-        desc[dt] = d; rsv[dt] = rs;
-        if (kTcPfDist > 0 && d.yoff >= 0) {             // the epilogue's operands for this row: into L2 now, read ~20k clk later
+        t2_make_desc(p, ps, v0 + dt, desc, dt);
+        const int g0 = desc[2 * kT2N + dt], g1 = desc[3 * kT2N + dt];
+        if (kTcPfDist > 0 && g0 >= 0) {                 // the epilogue's operands for this row: into L2 now, read ~20k clk later
           const float* G = p.Om ? p.Om : p.res.R;
           for (int c0 = 0; c0 < ps.N; c0 += 32) {
-            if (d.g0 >= 0) prefetch_l2(G + d.g0 + ps.ch_off + c0);
-            if (d.g1 >= 0) prefetch_l2(G + d.g1 + ps.ch_off + c0);
+            prefetch_l2(G + g0 + ps.ch_off + c0);
+            if (g1 >= 0) prefetch_l2(G + g1 + ps.ch_off + c0);
           }
         }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
+      uint32_t tab;
+      asm volatile("mov.u32 %0, %1;" : "=r"(tab) : "r"(smem_u32(desc) + (uint32_t)(half * 128 * 4)) : "memory");   // descriptor loads stay below the barrier
+      T2P(d_desc += clock64() - dq;)
       float acc[128];
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      uint32_t t_sum = 0;
+      int last_buf = 0;
 #pragma unroll 1
       for (int cc = 0; cc < ps.n_chunks; ++cc) {
         const int buf = chunk % kT2AccBufs;
+        const bool last = cc == ps.n_chunks - 1;
+        T2P(dq = clock64();)
         mbar_wait(acc_full0 + 8 * buf, (chunk / kT2AccBufs) & 1);
+        T2P(d_wait += clock64() - dq; dq = clock64();)
         tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kT2N + half * 128);
         if (q_ok) {
-          const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kT2N + half * 128);
 #pragma unroll
           for (int c0 = 0; c0 < 128; c0 += 32) {
             uint32_t r0[16], r1[16];
@@ -374,24 +474,41 @@ __global__ void __launch_bounds__(kT2Threads, 1) conv_tc2_kernel(const TcArgs p)
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(r0[i]); acc[c0 + 16 + i] += __uint_as_float(r1[i]); }
+            if (last) { tmem_st16(t0 + c0, &acc[c0]); tmem_st16(t0 + c0 + 16, &acc[c0 + 16]); }     // the finished sums go back in place
           }
         }
+        ++chunk;
+        if (last) { t_sum = t0; last_buf = buf; break; }       // this buffer is released after the epilogue has read it
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-        ++chunk;
+        T2P(d_ld += clock64() - dq;)
       }
-      if (!q_ok) continue;
-      const int c = ps.ch_off + cl;
-      const T2Desc* dh = desc + half * 128;
-      const float* rh = rsv + half * 128;
-      switch (mode) {      // one specialised straight-line epilogue per launch stays hot in the instruction cache
-        case 0: t2_epilogue<0>(p, acc, dh, rh, c, c_ok); break;
-        case 1: t2_epilogue<1>(p, acc, dh, rh, c, c_ok); break;
-        case 2: t2_epilogue<2>(p, acc, dh, rh, c, c_ok); break;
-        default: t2_epilogue<3>(p, acc, dh, rh, c, c_ok); break;
+      T2P(dq = clock64();)
+      if (q_ok) {
+        tmem_st_wait();
+        const int c = ps.ch_off + cl;
+        switch (mode) {      // one specialised epilogue per launch
+          case 0: t2_epilogue<0, false>(p, t_sum, tab, c, c_ok); break;
+          case 1: t2_epilogue<1, false>(p, t_sum, tab, c, c_ok); break;
+          case 2: t2_epilogue<2, false>(p, t_sum, tab, c, c_ok); break;
+          case 3: t2_epilogue<3, false>(p, t_sum, tab, c, c_ok); break;
+          case 4: t2_epilogue<0, true>(p, t_sum, tab, c, c_ok); break;
+          case 5: t2_epilogue<1, true>(p, t_sum, tab, c, c_ok); break;
+          case 6: t2_epilogue<2, true>(p, t_sum, tab, c, c_ok); break;
+          default: t2_epilogue<3, true>(p, t_sum, tab, c, c_ok); break;
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty0 + 8 * last_buf);
+      T2P(d_epi += clock64() - dq;)
     }
+#ifdef AVC_TC_PROFILE
+    if ((p.dbg & 32) && blockIdx.x == 0 && warp == 8 && lane == 0)
+      printf("[conv_tc2 cta0] drain: total %lld clk, descriptors %lld, wait acc_full %lld, tmem ld+add %lld, epilogue %lld (chunks %d, mode %d)\n",
+             clock64() - d_t0, d_desc, d_wait, d_ld, d_epi, chunk, mode);
+#endif
   }
   tc_fence_before();
   __syncthreads();

@@ -405,7 +405,19 @@ bool use_tc2(const TcArgs& t, int sm_count, int tc2) {
   const int mode = tc2 ? tc2 : env;
   if (mode == 1) return false;
   if (mode == 2) return true;
-  return ((t.Mv + kTcM - 1) / kTcM) * t.n_pass > sm_count;
+  // measured per launch at emb 128 / 512 x 80x512 (profiles/r02b_*): the N = 256 kernel wins where its 128-clk MMAs and
+  // register epilogue count -- multi-tap convs with more than one wave of 128-row tiles; the N = 128 kernel keeps 1-tap convs
+  // (window-loader bound either way, and its smaller tile balances better), N = 80 outputs (M is padded to 128 after the
+  // swap) and dgrads whose epilogue reads an act' mask (two operand streams per tile against one accumulator hand-off)
+  if (((t.Mv + kTcM - 1) / kTcM) * t.n_pass <= sm_count) return false;
+  int kmax = 1;
+  for (int q = 0; q < t.n_pass; ++q) {
+    if (t.pass[q].N != kTcNMax) return false;
+    for (int g = t.pass[q].g_begin; g < t.pass[q].g_end; ++g) kmax = std::max(kmax, t.g[g].n_taps);
+  }
+  if (kmax < 2) return false;
+  if (t.bwd && t.Om) return false;
+  return true;
 }
 
 void launch_conv_tc(const TcArgs& t, int sm_count, cudaStream_t st, int tc2 = 0) {
