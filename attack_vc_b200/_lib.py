@@ -45,6 +45,29 @@ class HeaderArgs(C.Structure):
     ]
 
 
+class SpkGradArgs(C.Structure):
+    _fields_ = [
+        ("perturbed", C.c_void_p), ("p_stride", C.c_int64 * 3), ("B", C.c_int32), ("T", C.c_int32),
+        ("source", C.c_void_p), ("s_stride", C.c_int64 * 3),
+        ("target", C.c_void_p), ("t_stride", C.c_int64 * 3), ("T_tgt", C.c_int32),
+        ("grad_out", C.c_void_p), ("g_stride", C.c_int64 * 3),
+        ("loss_out", C.c_void_p),
+        ("lam", C.c_float), ("inv_norm", C.c_double), ("use_graph", C.c_int32),
+    ]
+
+
+class PmTrainerArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("F", C.c_int32), ("T", C.c_int32), ("future_steps", C.c_int32),
+        ("eps1", C.c_float), ("eps2", C.c_float), ("eps3", C.c_float), ("lam", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("inv_norm", C.c_double),
+    ]
+
+
+# int (*avc_allreduce_fn)(void* ctx, float* comm, int64_t n_floats, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
 class AttackArgs(C.Structure):
     _fields_ = [
         ("vc_tgt", C.c_void_p), ("tgt_stride", C.c_int64 * 3), ("B", C.c_int32), ("T_tgt", C.c_int32),
@@ -66,6 +89,9 @@ EXPORTS = [
     "avc_header_optimize", "avc_header_begin", "avc_header_step", "avc_header_grad_buffer",
     "avc_pm_create", "avc_pm_destroy", "avc_pm_last_error", "avc_pm_load_weights", "avc_pm_out_shape", "avc_pm_forward",
     "avc_pm_train_step", "avc_pm_kernel_launches",
+    "avc_spk_grad_begin", "avc_spk_grad_step",
+    "avc_pm_set_allreduce", "avc_pm_param_count", "avc_pm_trainer_begin", "avc_pm_trainer_step", "avc_pm_trainer_grads",
+    "avc_pm_trainer_end", "avc_pm_export_weights",
 ]
 
 _lib = None
@@ -135,6 +161,16 @@ def load() -> C.CDLL:
     lib.avc_pm_train_step.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, P(WeightView), i32, vp]
     lib.avc_pm_kernel_launches.argtypes = [vp]
     lib.avc_pm_kernel_launches.restype = i64
+    lib.avc_spk_grad_begin.argtypes = [vp, P(SpkGradArgs), vp, P(vp)]
+    lib.avc_spk_grad_step.argtypes = [vp, vp]
+    lib.avc_pm_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp, vp, i64, i32]
+    lib.avc_pm_param_count.argtypes = [vp]
+    lib.avc_pm_param_count.restype = i64
+    lib.avc_pm_trainer_begin.argtypes = [vp, vp, P(PmTrainerArgs), vp, P(vp)]
+    lib.avc_pm_trainer_step.argtypes = [vp, vp, vp, f32, vp, vp]
+    lib.avc_pm_trainer_grads.argtypes = [vp, P(WeightView), i32, vp]
+    lib.avc_pm_trainer_end.argtypes = [vp]
+    lib.avc_pm_export_weights.argtypes = [vp, P(WeightView), i32, vp]
     lib.avc_version.argtypes = []
     lib.avc_version.restype = C.c_char_p
     _lib = lib

@@ -398,6 +398,25 @@ __global__ void header_grad_kernel(const float* __restrict__ g_adv, long long g_
   }
 }
 
+// d loss / d input of the speaker encoder, written in the reference's [B, C, T] layout with caller strides
+// (train_predictive.py:113-123 as a gradient service: loss.backward() down to perturbed_mels).  gp0 / gp1: K-split
+// partials of the bank dgrad (small-M plans), added in a fixed order.
+__global__ void spk_grad_out_kernel(const float* __restrict__ g_in, long long g_bs, int g_rs, const float* __restrict__ gp0,
+                                    const float* __restrict__ gp1, float* __restrict__ dst, long long sb, long long sc, long long st,
+                                    int B, int T, int C) {
+  pdl_enter();
+  const long long n = (long long)B * T * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long bt = i / C;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    float g = g_in[(long long)b * g_bs + (long long)t * g_rs + c];
+    if (gp0) g += gp0[i];
+    if (gp1) g += gp1[i];
+    dst[b * sb + c * sc + t * st] = g;
+  }
+}
+
 struct HeaderApplyArgs {
   const float* gh; float* h; float* m; float* v;     // [T, C]
   const float* x; float* adv; long long adv_bs; int adv_rs;

@@ -1660,6 +1660,75 @@ std::unique_ptr<Plan> build_header(avc_handle* h, const avc_header_args* a, cuda
   return plan_ptr;
 }
 
+// ---- speaker-embedding loss gradient service (reference train_predictive.py:113-123) -------
+// iter = embeddings of the clean source and of the target (forward only), then forward / loss / backward of the perturbed
+// batch and the input gradient in the caller's layout.  Every launch reads the caller's buffers at run time: one
+// captured graph serves every training step.
+std::unique_ptr<Plan> build_spkgrad(avc_handle* h, const avc_spk_grad_args* a, cudaStream_t st) {
+  if (!h->have_weights) fail(AVC_ERR_STATE, "avc_load_weights must be called before avc_spk_grad_*");
+  if (!a || !a->perturbed || !a->source || !a->target || !a->grad_out) fail(AVC_ERR_INVALID, "null tensor argument");
+  if (a->B <= 0 || a->T <= 0 || a->T_tgt <= 0) fail(AVC_ERR_INVALID, "bad B/T");
+  check_strides(a->p_stride, "perturbed"); check_strides(a->s_stride, "source"); check_strides(a->t_stride, "target");
+  check_strides(a->g_stride, "grad_out");
+  const int B = a->B, T = a->T, C = h->desc.speaker.c_in;
+  const EncoderW& SE = h->se;
+  std::unique_ptr<Plan> plan_ptr(new Plan(&h->pool, st));
+  Plan& plan = *plan_ptr;
+  plan.n_iters = 1 << 30;
+  plan.io.n_iters = 1 << 30;
+  plan.use_graph = a->use_graph != 0;
+  Arena& m = plan.mem;
+  Emitter I{h, &plan.iter, &plan.mem};
+  const size_t nel = (size_t)B * T * C;
+  int* step = m.raw<int>(1);              // stays 0: one loss slot per utterance, overwritten every step
+  const double inv_norm = a->inv_norm > 0 ? a->inv_norm : 1.0 / ((double)B * SE.d.c_out);
+  const int parts = B;
+  float* loss_parts = m.f((size_t)parts);
+  float* org = m.f((size_t)B * 128);
+  float* tgt = m.f((size_t)B * 128);
+  EncActs se1 = alloc_encoder(m, SE, B, T, true, false);
+  const Tens adv = se1.input(SE);
+  const float lam = a->lambda;
+  auto se_forward = [&](const EncActs& A, int tail_mode, const float* tgt_e, const float* org_e, float* emb_dst) {
+    emit_bank_and_inconv(I, SE, A, false);
+    emit_encoder_blocks_fwd(I, SE, A, false);
+    TailArgs t = tail_args(SE, A);
+    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm; t.lam = lam;
+    t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+    if (emb_dst) t.emb = emb_dst;
+    emit_tail(I, t, A.B);
+  };
+  emit_layout_in(I, a->source, a->s_stride, adv, B, C);
+  se_forward(se1, TAIL_FWD, nullptr, nullptr, org);
+  if (a->T_tgt == T) {
+    emit_layout_in(I, a->target, a->t_stride, adv, B, C);
+    se_forward(se1, TAIL_FWD, nullptr, nullptr, tgt);
+  } else {
+    EncActs seT = alloc_encoder(m, SE, B, a->T_tgt, false, false);
+    emit_layout_in(I, a->target, a->t_stride, seT.input(SE), B, C);
+    se_forward(seT, TAIL_FWD, nullptr, nullptr, tgt);
+  }
+  emit_layout_in(I, a->perturbed, a->p_stride, adv, B, C);
+  se_forward(se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
+  Tens gin = tens(se1.gin, T, C);
+  GradParts gparts;
+  emit_speaker_bwd(I, SE, se1, gin, &gparts);
+  {
+    const unsigned g = ew_grid((long long)nel, h->sm_count);
+    float* dst = a->grad_out;
+    const long long sb = a->g_stride[0], sc = a->g_stride[1], stt = a->g_stride[2];
+    I.push(LK_LAYOUT, 0, 8.0 * nel, [=](cudaStream_t s_) { launch_k(spk_grad_out_kernel, g, 256, 0, s_, (const float*)gin.p, gin.bs, gin.rs, gparts.p[0], gparts.p[1], dst, sb, sc, stt, B, T, C); });
+  }
+  if (a->loss_out) {
+    float* lo = a->loss_out;
+    I.push(LK_LOSS, 0, 4.0 * parts, [=](cudaStream_t s_) { launch_k(loss_sum_kernel, 1, 128, 0, s_, (const float*)loss_parts, parts, 1, lo); });
+  }
+  CK(cudaStreamSynchronize(st));
+  h->launches_per_iter = (int)plan.iter.size();
+  if (plan.use_graph) capture_iters(plan, 1, &plan.graph, &plan.exec);
+  return plan_ptr;
+}
+
 // phase 0: n whole iterations; 1: the gradient half of ONE iteration; 2: the apply half of ONE iteration
 void step_header(avc_handle* h, Plan& plan, int n, int phase, cudaStream_t st) {
   if (plan.finished) fail(AVC_ERR_STATE, "session already finished");
@@ -1923,6 +1992,23 @@ int avc_header_begin(avc_handle* h, const avc_header_args* a, void* stream, avc_
 int avc_header_step(avc_session* s, int32_t n, int32_t phase, void* stream) {
   if (!s) return AVC_ERR_INVALID;
   return guarded(s->h, [&] { step_header(s->h, *s->plan, n, phase, (cudaStream_t)stream); });
+}
+
+int avc_spk_grad_begin(avc_handle* h, const avc_spk_grad_args* a, void* stream, avc_session** out) {
+  if (!h || !out) return AVC_ERR_INVALID;
+  *out = nullptr;
+  return guarded(h, [&] {
+    std::unique_ptr<Plan> plan = build_spkgrad(h, a, (cudaStream_t)stream);
+    *out = new avc_session{h, std::move(plan)};
+  });
+}
+
+int avc_spk_grad_step(avc_session* s, void* stream) {
+  if (!s) return AVC_ERR_INVALID;
+  return guarded(s->h, [&] {
+    if (!s->plan->iter2.empty() || !s->plan->setup.empty()) fail(AVC_ERR_STATE, "not a speaker-gradient session");
+    step_attack(s->h, *s->plan, 1, (cudaStream_t)stream);
+  });
 }
 
 float* avc_header_grad_buffer(avc_session* s, int64_t* n) {

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
 //   kind 2 (bias gradient): q0 = sum g
 struct PmReduce {
   const float* y; const float* g; long long N; int C;
-  const float* scale; const float* shift; const float* mean; const float* rstd; float a;
+  const float* scale; const float* shift; const float* mean; const float* rstd; const float* a;   // a: the PReLU slope (device: the trainer's Adam step updates it)
   int kind;
   float* partial;   // [G][3][C]
 };
@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
     const long long per = (p.N + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per, hi = min(p.N, lo + per);
     float4 sc = f4zero(), sf = f4zero(), mu = f4zero(), rs = f4zero();
+    const float pa = p.kind == 1 ? *p.a : 0.f;
     if (p.kind == 1) { sc = ld4(p.scale + 4 * cl); sf = ld4(p.shift + 4 * cl); mu = ld4(p.mean + 4 * cl); rs = ld4(p.rstd + 4 * cl); }
     for (long long i = lo + rl; i < hi; i += RL) {
       if (p.kind == 0) {
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float yn = fmaf(vv[j], s4[j], f4[j]);
-          const float gyn = gg[j] * (yn > 0.f ? 1.f : p.a);
+          const float gyn = gg[j] * (yn > 0.f ? 1.f : pa);
           const float xh = (vv[j] - m4[j]) * r4[j];
           o0[j] = gyn; o1[j] = gyn * xh; o2[j] = yn > 0.f ? 0.f : gg[j] * yn;
         }
@@ -350,7 +351,8 @@ __global__ void pm_sum_partials_kernel(const float* partial, int G, int C, float
 }
 
 // z = prelu(y*scale + shift)
-__global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const float* shift, float a, float* z, long long n4, int C) {
+__global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const float* shift, const float* ap, float* z, long long n4, int C) {
+  const float a = *ap;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
     const float4 v = ld4(y + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
@@ -362,7 +364,8 @@ __global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const
 // BatchNorm (training) + PReLU backward, elementwise part:
 //   gy = gamma*rstd * (gyn - sum_gyn/N - xh * sum_gyn_xh/N),  gyn = gz * prelu'(yn)
 __global__ void pm_bn_bwd_kernel(const float* y, const float* gz, const float* scale, const float* shift, const float* mean,
-                                 const float* rstd, const float* sums /*[3][C]*/, float a, float invN, float* gy, long long n4, int C) {
+                                 const float* rstd, const float* sums /*[3][C]*/, const float* ap, float invN, float* gy, long long n4, int C) {
+  const float a = *ap;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
     const float4 v = ld4(y + i * 4), g = ld4(gz + i * 4), sc = ld4(scale + c), sf = ld4(shift + c), mu = ld4(mean + c), rs = ld4(rstd + c);
@@ -576,13 +579,24 @@ struct DownW {
   float *w = nullptr, *wt = nullptr;    // [9][ci][cop], transposed [9][co][cip]
   float *bias = nullptr, *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
   float *escale = nullptr, *eshift = nullptr;   // folded eval BatchNorm (+ conv bias)
-  float a = 0.25f;
+  float a = 0.25f;          // host copy for the eval conv epilogue (refreshed from a_dev after training steps)
+  float* a_dev = nullptr;   // the PReLU slope on the device
 };
 struct UpW {
   float *w = nullptr, *wt = nullptr, *bias = nullptr;
 };
 
 }  // namespace
+
+// one tensor of model.parameters() inside the flat PyTorch-layout parameter buffer, and the packed images derived from it
+struct PmParam {
+  std::string name;
+  long long off = 0, n = 0;
+  int kind = 0;            // 0: vector copied to d0 (bias / BatchNorm weight / BatchNorm bias / PReLU slope), 1: Conv2d weight [co][ci][3][3], 2: ConvTranspose2d weight [ci][co][3][3]
+  int ci = 0, co = 0;
+  float *d0 = nullptr, *d1 = nullptr;   // kind 1/2: d0 = forward image [9][ci][cop], d1 = transposed image [9][co][cip]
+};
+struct PmParamDev { long long off, n; int kind, ci, co, cop, cip; float* d0; float* d1; };
 
 struct avc_pm_handle {
   int device = 0, sm_count = 148;
@@ -593,6 +607,19 @@ struct avc_pm_handle {
   UpW up[5];
   std::string err;
   long long launches = 0;
+  // training state: every parameter in PyTorch layout in ONE buffer (the trainer's Adam step walks it and rewrites the
+  // packed images in the same pass)
+  std::vector<PmParam> params;
+  long long n_params = 0;
+  float* P = nullptr;
+  PmParamDev* pdev = nullptr;
+  bool eval_stale = false;       // escale / eshift / host PReLU slopes are older than the parameters
+  // data-parallel training: sums that couple the ranks go through the caller's all-reduce
+  avc_allreduce_fn ar = nullptr;
+  void* ar_ctx = nullptr;
+  float* comm = nullptr;
+  long long comm_cap = 0;
+  int world = 1;
 };
 
 namespace {
@@ -663,6 +690,14 @@ int launch_pm_reduce(avc_pm_handle* h, PmReduce r, cudaStream_t st) {
   return G;
 }
 
+// sum comm[0..n) over the ranks, ordered on `st` (the callback enqueues the collective there)
+void pm_allreduce(avc_pm_handle* h, long long n, cudaStream_t st) {
+  if (h->world <= 1) return;
+  if (!h->ar || n > h->comm_cap) fail(AVC_ERR_STATE, "all-reduce of %lld floats requested but the registered buffer holds %lld", n, h->comm_cap);
+  const int rc = h->ar(h->ar_ctx, h->comm, (int64_t)n, (void*)st);
+  if (rc != 0) fail(AVC_ERR_STATE, "the caller's all-reduce callback failed (%d)", rc);
+}
+
 unsigned ew_grid(long long n, int sm) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sm * 8)); }
 
 struct HostSD {
@@ -723,12 +758,22 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
       PmReduce r{};
       r.y = A.y[l]; r.N = npix; r.C = s.co; r.kind = 0;
       r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
-      const int G = launch_pm_reduce(h, r, st);
-      pm_bn_finalize_kernel<<<(s.co + 127) / 128, 128, 0, st>>>(r.partial, G, s.co, npix, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
+      int G = launch_pm_reduce(h, r, st);
+      const float* part = r.partial;
+      long long n_stat = npix;
+      if (h->world > 1) {
+        // one BatchNorm over the GLOBAL batch (a single-device batch of world x B windows): sum, sum of squares across ranks
+        pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, G, s.co, h->comm);
+        CK(cudaGetLastError());
+        h->launches++;
+        pm_allreduce(h, 3LL * s.co, st);
+        part = h->comm; G = 1; n_stat = npix * h->world;
+      }
+      pm_bn_finalize_kernel<<<(s.co + 127) / 128, 128, 0, st>>>(part, G, s.co, n_stat, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
                                                                A.rstd[l], w.rmean, w.rvar, new_mean ? new_mean[l] : nullptr, new_var ? new_var[l] : nullptr);
       CK(cudaGetLastError());
       const long long n4 = npix * s.co / 4;
-      pm_affine_prelu_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a, A.z[l], n4, s.co);
+      pm_affine_prelu_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, A.z[l], n4, s.co);
       CK(cudaGetLastError());
       h->launches += 2;
     }
@@ -748,7 +793,253 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
   }
 }
 
+// backward of one training forward pass.  g: gradient w.r.t. the LAST up block's pre-activation [B,Hu5,Wu5] (consumed).
+// want(key) -> device buffer of that parameter's gradient (PyTorch shape) or nullptr.
+template <class Want>
+void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want, float* grad_x, cudaStream_t st) {
+  const int B = A.B;
+  auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst) {
+    if (!dst) return;
+    PmWgrad q{};
+    q.A = Ain; q.Ha = Ha; q.Wa = Wa; q.Ci = Ci; q.G = G; q.Hg = Hg; q.Wg = Wg; q.Co = Co;
+    q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
+    const long long N = (long long)B * Hb * Wb;
+    const int tiles = 9 * ((Ci + kWgT - 1) / kWgT) * ((q.Cop + kWgT - 1) / kWgT);
+    static const int oversub = getenv("AVC_PM_WG_CTAS") ? atoi(getenv("AVC_PM_WG_CTAS")) : 8;   // pixel-axis slices: CTAs per SM aimed at
+    const int S = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, ((long long)oversub * h->sm_count + tiles - 1) / tiles), N / (4 * kWgKC) + 1));
+    q.partial = mem.f((size_t)S * 9 * Ci * q.Cop);
+    dim3 grid(S, (Ci + kWgT - 1) / kWgT, 9 * ((q.Cop + kWgT - 1) / kWgT));
+    pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
+    CK(cudaGetLastError());
+    pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(q.partial, S, Ci, Co, q.Cop, up, dst);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  };
+  auto bias_grad = [&](const float* G, long long N, int C, float* dst) {
+    if (!dst) return;
+    if (C % 4) {   // single output channel (last block): sum of every element
+      if (C != 1) fail(AVC_ERR_INVALID, "bias gradient: unsupported channel count %d", C);
+      const int G2 = (int)ew_grid(N, h->sm_count);
+      float* part = mem.f(G2);
+      pm_sum_all_kernel<<<G2, 256, 0, st>>>(G, N, part);
+      CK(cudaGetLastError());
+      pm_sum_n_kernel<<<1, 1, 0, st>>>(part, G2, dst);
+      CK(cudaGetLastError());
+      h->launches += 2;
+      return;
+    }
+    PmReduce r{};
+    r.g = G; r.N = N; r.C = C; r.kind = 2; r.partial = mem.f((size_t)reduce_slices(N) * 3 * C);
+    const int Gs = launch_pm_reduce(h, r, st);
+    float* s3 = mem.f(3 * (size_t)C);
+    pm_sum_partials_kernel<<<(3 * C + 127) / 128, 128, 0, st>>>(r.partial, Gs, C, s3);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, s3, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    h->launches += 1;
+  };
+  // ---- up blocks, last to first: g = gradient w.r.t. block i's pre-activation ----
+  for (int i = 4; i >= 0; --i) {
+    const UpSpec& s = kUp[i];
+    const std::string p = "up_blocks." + std::to_string(i) + ".conv_transpose.0.";
+    const float* xin = i > 0 ? A.u[i - 1] : A.z[6];
+    const long long npix = (long long)B * A.Hu[i + 1] * A.Wu[i + 1];
+    bias_grad(g, npix, s.co, want(p + "bias"));
+    wgrad(xin, A.Hu[i], A.Wu[i], s.ci, g, A.Hu[i + 1], A.Wu[i + 1], s.co, A.Hu[i], A.Wu[i], 1, 2, 2, want(p + "weight"));
+    // dgrad: gx[ih,iw,ci] = sum_{kh,kw,co} g[2ih+kh, 2iw+kw, co] * W[ci][co][kh][kw]; then through the previous LeakyReLU
+    float* gx = mem.f((size_t)B * A.Hu[i] * A.Wu[i] * s.ci);
+    PmConv c{};
+    c.x = g; c.Hi = A.Hu[i + 1]; c.Wi = A.Wu[i + 1]; c.Ci = s.co;
+    c.w = h->up[i].wt; c.y = gx; c.Ho = A.Hu[i]; c.Wo = A.Wu[i]; c.Co = s.ci; c.Cop = pad4(s.ci);
+    c.B = B; c.mode = PM_PLAIN; c.sh = 2; c.sw = 2;
+    if (i > 0) { c.dmask = A.u[i - 1]; c.mslope = 0.2f; }
+    launch_pm_conv(h, c, st);
+    g = gx;
+  }
+  // ---- down blocks, last to first: g = gradient w.r.t. block l's output z_l ----
+  for (int l = 6; l >= 0; --l) {
+    const DownSpec& s = kDown[l];
+    const DownW& w = h->down[l];
+    const std::string p = "down_blocks." + std::to_string(l) + ".conv.";
+    const long long npix = (long long)B * A.H[l + 1] * A.W[l + 1];
+    PmReduce r{};
+    r.y = A.y[l]; r.g = g; r.N = npix; r.C = s.co; r.kind = 1;
+    r.scale = A.scale[l]; r.shift = A.shift[l]; r.mean = A.mean[l]; r.rstd = A.rstd[l]; r.a = w.a_dev;
+    r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
+    const int Gs = launch_pm_reduce(h, r, st);
+    float* sums = mem.f(3 * (size_t)s.co);
+    pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, Gs, s.co, sums);
+    CK(cudaGetLastError());
+    // this rank's sums are its share of the BatchNorm / PReLU parameter gradients; d x needs the sums over the GLOBAL batch
+    const float* gsums = sums;
+    long long n_stat = npix;
+    if (h->world > 1) {
+      CK(cudaMemcpyAsync(h->comm, sums, 3 * (size_t)s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      pm_allreduce(h, 3LL * s.co, st);
+      float* gs = mem.f(3 * (size_t)s.co);
+      CK(cudaMemcpyAsync(gs, h->comm, 3 * (size_t)s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      gsums = gs; n_stat = npix * h->world;
+    }
+    if (float* d = want(p + "2.bias")) CK(cudaMemcpyAsync(d, sums, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (float* d = want(p + "2.weight")) CK(cudaMemcpyAsync(d, sums + s.co, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (float* d = want(p + "3.weight")) {   // PReLU slope: sum over channels of q2 (fixed order)
+      pm_sum_n_kernel<<<1, 1, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
+      CK(cudaGetLastError());
+    }
+    float* gy = mem.f((size_t)npix * s.co);
+    const long long n4 = npix * s.co / 4;
+    pm_bn_bwd_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], g, A.scale[l], A.shift[l], A.mean[l], A.rstd[l], gsums, w.a_dev,
+                                                            1.f / (float)n_stat, gy, n4, s.co);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    bias_grad(gy, npix, s.co, want(p + "1.bias"));
+    const float* xin = l > 0 ? A.z[l - 1] : A.x;
+    wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"));
+    if (l == 0 && !grad_x) break;
+    // dgrad on the padded coordinates, then fold the reflect padding back
+    const int Hp = A.H[l] + 2, Wp = A.W[l] + 2;
+    const int cip = pad4(s.ci);
+    float* gxp = mem.f((size_t)B * Hp * Wp * cip);
+    PmConv c{};
+    c.x = gy; c.Hi = A.H[l + 1]; c.Wi = A.W[l + 1]; c.Ci = s.co;
+    c.w = w.wt; c.y = gxp; c.Ho = Hp; c.Wo = Wp; c.Co = s.ci; c.Cop = cip;
+    c.B = B; c.mode = PM_TRANSPOSED; c.sh = s.sh; c.sw = s.sw;
+    launch_pm_conv(h, c, st);
+    if (l > 0) {
+      float* gx = mem.f((size_t)B * A.H[l] * A.W[l] * s.ci);
+      pm_fold_kernel<<<ew_grid((long long)B * A.H[l] * A.W[l] * s.ci / 4, h->sm_count), 256, 0, st>>>(gxp, gx, B, A.H[l], A.W[l], s.ci);
+      CK(cudaGetLastError());
+      g = gx;
+    } else {
+      pm_fold1_kernel<<<ew_grid((long long)B * A.H[0] * A.W[0], h->sm_count), 256, 0, st>>>(gxp, grad_x, B, A.H[0], A.W[0]);
+      CK(cudaGetLastError());
+    }
+    h->launches += 1;
+  }
+}
+
+// ---- VSMask training step glue (train_predictive.py:95-111, utils/audio.py:77-116) ------------------------------------
+struct VsmaskArgs {
+  const float* src;        // [B,F,T]   source mel windows (the reference's [B,1,F,T])
+  const float* pert;       // [B,Fp,Tp] model output
+  int B, F, T, Fp, Tp;
+  int fs, fe;              // future_steps, min(fs + Tp, T)
+  int lo_end, hi_start;    // int(F*0.3), int(F*0.7)
+  float e1, e2, e3;
+};
+// the value the reference clamps: perturbed_mels - source_mels with perturbed_mels = source (+ prediction on [fs,fe)),
+// rounded exactly as the reference rounds it ((s + p) - s in fp32, not p)
+__device__ __forceinline__ float vsmask_delta(const VsmaskArgs& a, int b, int f, int t, float s) {
+  if (t < a.fs || t >= a.fe) return 0.f;
+  const float pm = s + a.pert[((long long)b * a.Fp + f) * a.Tp + (t - a.fs)];
+  return pm - s;
+}
+__device__ __forceinline__ float vsmask_eps(const VsmaskArgs& a, int f) { return f < a.lo_end ? a.e1 : (f < a.hi_start ? a.e2 : a.e3); }
+
+__global__ void vsmask_apply_kernel(const VsmaskArgs a, float* __restrict__ perturbed) {
+  const long long n = (long long)a.B * a.F * a.T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % a.T);
+    const long long bf = i / a.T;
+    const int f = (int)(bf % a.F), b = (int)(bf / a.F);
+    const float s = a.src[i];
+    const float d = vsmask_delta(a, b, f, t, s), e = vsmask_eps(a, f);
+    perturbed[i] = s + fminf(fmaxf(d, -e), e);
+  }
+}
+// d loss / d (last block's pre-activation) from d loss / d perturbed: the crop and the clamp mask (gradient passes where
+// -eps <= delta <= eps, torch.clamp's backward), then tanh and LeakyReLU(0.2) of the last up block (predictive_model.py:47,108)
+__global__ void vsmask_grad_kernel(const VsmaskArgs a, const float* __restrict__ gmel /*[B,F,T]*/, float* __restrict__ gpre /*[B,Fp,Tp]*/) {
+  const long long n = (long long)a.B * a.Fp * a.Tp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tp = (int)(i % a.Tp);
+    const long long bf = i / a.Tp;
+    const int f = (int)(bf % a.Fp), b = (int)(bf / a.Fp);
+    const int t = a.fs + tp;
+    float g = 0.f;
+    if (f < a.F && t < a.fe) {
+      const long long j = ((long long)b * a.F + f) * a.T + t;
+      const float d = vsmask_delta(a, b, f, t, a.src[j]), e = vsmask_eps(a, f);
+      if (d >= -e && d <= e) g = gmel[j];
+    }
+    const float o = a.pert[i];
+    gpre[i] = g * (1.f - o * o) * (o > 0.f ? 1.f : 0.2f);
+  }
+}
+
+// ---- Adam over every parameter + refresh of the packed images, one pass (torch/optim/adam.py, defaults of :57) --------
+struct PmAdamArgs {
+  float* P; const float* G; float* M; float* V;
+  const PmParamDev* tab; int n_tab; long long n;
+  float step_size, bc2s, b1w, b2, b2w, eps;     // lr/(1-b1^t), sqrt(1-b2^t), 1-b1, b2, 1-b2, eps
+};
+__global__ void __launch_bounds__(256) pm_adam_kernel(const PmAdamArgs a) {
+  __shared__ long long offs[64];
+  for (int i = threadIdx.x; i < a.n_tab; i += blockDim.x) offs[i] = a.tab[i].off;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = a.G[i];
+    float m = a.M[i], v = a.V[i], p = a.P[i];
+    m = m + (g - m) * a.b1w;
+    v = v * a.b2 + (a.b2w * g) * g;
+    const float denom = sqrtf(v) / a.bc2s + a.eps;
+    p = p + (-a.step_size * m) / denom;
+    a.M[i] = m; a.V[i] = v; a.P[i] = p;
+    int lo = 0, hi = a.n_tab - 1;                      // the tensor this element belongs to
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offs[mid] <= i) lo = mid; else hi = mid - 1; }
+    const PmParamDev d = a.tab[lo];
+    const long long r = i - d.off;
+    if (d.kind == 0) { d.d0[r] = p; continue; }
+    const int tap = (int)(r % 9);
+    const long long q = r / 9;
+    int ci, co;
+    if (d.kind == 1) { ci = (int)(q % d.ci); co = (int)(q / d.ci); } else { co = (int)(q % d.co); ci = (int)(q / d.co); }
+    d.d0[((long long)tap * d.ci + ci) * d.cop + co] = p;
+    d.d1[((long long)tap * d.co + co) * d.cip + ci] = p;
+  }
+}
+
+// folded eval BatchNorm of every down block from the current parameters and running statistics (one CTA per block)
+struct PmRefoldArgs { const float* bias[7]; const float* gamma[7]; const float* beta[7]; const float* rmean[7]; const float* rvar[7]; float* escale[7]; float* eshift[7]; int co[7]; };
+__global__ void pm_refold_kernel(const PmRefoldArgs a) {
+  const int l = blockIdx.x;
+  for (int c = threadIdx.x; c < a.co[l]; c += blockDim.x) {
+    const float sc = a.gamma[l][c] / sqrtf(a.rvar[l][c] + 1e-5f);
+    a.escale[l][c] = sc;
+    a.eshift[l][c] = (a.bias[l][c] - a.rmean[l][c]) * sc + a.beta[l][c];
+  }
+}
+
+// eval-mode constants follow the parameters lazily: a training step only marks them stale
+void pm_refresh_eval(avc_pm_handle* h, cudaStream_t st) {
+  if (!h->eval_stale) return;
+  PmRefoldArgs r{};
+  for (int l = 0; l < 7; ++l) {
+    const DownW& w = h->down[l];
+    r.bias[l] = w.bias; r.gamma[l] = w.gamma; r.beta[l] = w.beta; r.rmean[l] = w.rmean; r.rvar[l] = w.rvar;
+    r.escale[l] = w.escale; r.eshift[l] = w.eshift; r.co[l] = kDown[l].co;
+  }
+  pm_refold_kernel<<<7, 256, 0, st>>>(r);
+  CK(cudaGetLastError());
+  h->launches++;
+  for (int l = 0; l < 7; ++l) CK(cudaMemcpyAsync(&h->down[l].a, h->down[l].a_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->eval_stale = false;
+}
+
 }  // namespace
+
+struct avc_pm_trainer {
+  avc_pm_handle* pm = nullptr;
+  avc_handle* se = nullptr;
+  avc_pm_trainer_args a{};
+  avc_session* spk = nullptr;             // speaker-embedding loss gradient service on `se`
+  std::unique_ptr<Arena> mem;             // persistent buffers of the trainer
+  float *G = nullptr, *M = nullptr, *V = nullptr;     // [n_params] gradient, Adam moments
+  float *src = nullptr, *tgt = nullptr, *perturbed = nullptr, *gmel = nullptr;   // [B,F,T]
+  float* loss = nullptr;
+  int Fp = 0, Tp = 0;
+  long long step = 0;
+};
 
 extern "C" {
 
@@ -831,6 +1122,7 @@ int avc_pm_load_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_
       d.rmean = h->wmem.upload(rmp); d.rvar = h->wmem.upload(rvp);
       d.escale = h->wmem.upload(es); d.eshift = h->wmem.upload(ef);
       d.a = a[0];
+      d.a_dev = h->wmem.upload(std::vector<float>(1, a[0]));
     }
     for (int i = 0; i < 5; ++i) {
       const UpSpec& s = kUp[i];
@@ -849,6 +1141,40 @@ int avc_pm_load_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_
       std::copy(b.begin(), b.end(), bp.begin());
       UpW& u = h->up[i];
       u.w = h->wmem.upload(wp); u.wt = h->wmem.upload(wt); u.bias = h->wmem.upload(bp);
+    }
+    // flat PyTorch-layout copy of every parameter, in state_dict order (trainer / export)
+    {
+      std::vector<float> flat;
+      auto add = [&](const std::string& name, const std::vector<float>& v, int kind, int ci, int co, float* d0, float* d1) {
+        PmParam q;
+        q.name = name; q.off = (long long)flat.size(); q.n = (long long)v.size(); q.kind = kind; q.ci = ci; q.co = co; q.d0 = d0; q.d1 = d1;
+        flat.insert(flat.end(), v.begin(), v.end());
+        h->params.push_back(q);
+      };
+      for (int l = 0; l < 7; ++l) {
+        const DownSpec& sp = kDown[l];
+        const std::string p = "down_blocks." + std::to_string(l) + ".conv.";
+        DownW& d = h->down[l];
+        add(p + "1.weight", sd.t[p + "1.weight"], 1, sp.ci, sp.co, d.w, d.wt);
+        add(p + "1.bias", sd.t[p + "1.bias"], 0, 0, 0, d.bias, nullptr);
+        add(p + "2.weight", sd.t[p + "2.weight"], 0, 0, 0, d.gamma, nullptr);
+        add(p + "2.bias", sd.t[p + "2.bias"], 0, 0, 0, d.beta, nullptr);
+        add(p + "3.weight", sd.t[p + "3.weight"], 0, 0, 0, d.a_dev, nullptr);
+      }
+      for (int i = 0; i < 5; ++i) {
+        const UpSpec& sp = kUp[i];
+        const std::string p = "up_blocks." + std::to_string(i) + ".conv_transpose.0.";
+        UpW& u = h->up[i];
+        add(p + "weight", sd.t[p + "weight"], 2, sp.ci, sp.co, u.w, u.wt);
+        add(p + "bias", sd.t[p + "bias"], 0, 0, 0, u.bias, nullptr);
+      }
+      h->n_params = (long long)flat.size();
+      h->P = h->wmem.upload(flat);
+      std::vector<PmParamDev> tab;
+      for (const PmParam& q : h->params) tab.push_back(PmParamDev{q.off, q.n, q.kind, q.ci, q.co, pad4(q.co), pad4(q.ci), q.d0, q.d1});
+      if (tab.size() > 64) fail(AVC_ERR_INVALID, "parameter table too large");
+      h->pdev = h->wmem.raw<PmParamDev>(tab.size());
+      CK(cudaMemcpy(h->pdev, tab.data(), tab.size() * sizeof(PmParamDev), cudaMemcpyHostToDevice));
     }
     CK(cudaDeviceSynchronize());
     h->have_weights = true;
@@ -876,6 +1202,7 @@ int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int3
     Arena mem(&h->pool, st);           // zero fills ordered on the caller's stream: no device-wide synchronisation per call
     PmActs A;
     pm_shapes(A, B, H, W);
+    if (!training) pm_refresh_eval(h, st);
     pm_forward(h, mem, A, x, out, training != 0, nullptr, nullptr, st);
     CK(cudaStreamSynchronize(st));
   });
@@ -885,6 +1212,8 @@ int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int3
 // (weights, biases, BatchNorm weight/bias, PReLU weight), each `data` a device buffer of the PyTorch shape
 // that receives the gradient; unknown names are an error, missing ones are simply not written.
 // new_stats: optional views "down_blocks.l.conv.2.running_mean|running_var" receiving the updated statistics.
+// With avc_pm_set_allreduce(world > 1): BatchNorm runs over the global batch, the loss is this rank's share of the
+// global mean and the gradients are this rank's share (the caller sums them over the ranks).
 int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, int32_t W, float* out, float* loss,
                       float* grad_x, const avc_weight_view* grads, int32_t n_grads, void* stream) {
   if (!h) return AVC_ERR_INVALID;
@@ -910,124 +1239,186 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
     pm_forward(h, mem, A, x, out, true, nm, nv, st);
     const float* o = A.u[4];
     const long long n_out = (long long)B * A.Hu[5] * A.Wu[5];
+    const float inv_n = 1.f / (float)(n_out * h->world);
     // ---- loss and gradient w.r.t. the last block's pre-activation ----
     float* g = mem.f((size_t)n_out);
     const int LG = (int)ew_grid(n_out, h->sm_count);
     float* lpart = mem.f(LG);
-    pm_loss_bwd_kernel<<<LG, 256, 0, st>>>(o, g, n_out, 1.f / (float)n_out, lpart);
+    pm_loss_bwd_kernel<<<LG, 256, 0, st>>>(o, g, n_out, inv_n, lpart);
     CK(cudaGetLastError());
-    pm_loss_final_kernel<<<1, 1, 0, st>>>(lpart, LG, 1.f / (float)n_out, loss);
+    pm_loss_final_kernel<<<1, 1, 0, st>>>(lpart, LG, inv_n, loss);
     CK(cudaGetLastError());
     h->launches += 2;
-    auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst) {
-      if (!dst) return;
-      PmWgrad q{};
-      q.A = Ain; q.Ha = Ha; q.Wa = Wa; q.Ci = Ci; q.G = G; q.Hg = Hg; q.Wg = Wg; q.Co = Co;
-      q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
-      const long long N = (long long)B * Hb * Wb;
-      const int tiles = 9 * ((Ci + kWgT - 1) / kWgT) * ((q.Cop + kWgT - 1) / kWgT);
-      static const int oversub = getenv("AVC_PM_WG_CTAS") ? atoi(getenv("AVC_PM_WG_CTAS")) : 8;   // pixel-axis slices: CTAs per SM aimed at
-      const int S = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(256, ((long long)oversub * h->sm_count + tiles - 1) / tiles), N / (4 * kWgKC) + 1));
-      q.partial = mem.f((size_t)S * 9 * Ci * q.Cop);
-      dim3 grid(S, (Ci + kWgT - 1) / kWgT, 9 * ((q.Cop + kWgT - 1) / kWgT));
-      pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
-      CK(cudaGetLastError());
-      pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(q.partial, S, Ci, Co, q.Cop, up, dst);
-      CK(cudaGetLastError());
-      h->launches += 2;
-    };
-    auto bias_grad = [&](const float* G, long long N, int C, float* dst) {
-      if (!dst) return;
-      if (C % 4) {   // single output channel (last block): sum of every element
-        if (C != 1) fail(AVC_ERR_INVALID, "bias gradient: unsupported channel count %d", C);
-        const int G2 = (int)ew_grid(N, h->sm_count);
-        float* part = mem.f(G2);
-        pm_sum_all_kernel<<<G2, 256, 0, st>>>(G, N, part);
-        CK(cudaGetLastError());
-        pm_sum_n_kernel<<<1, 1, 0, st>>>(part, G2, dst);
-        CK(cudaGetLastError());
-        h->launches += 2;
-        return;
-      }
-      PmReduce r{};
-      r.g = G; r.N = N; r.C = C; r.kind = 2; r.partial = mem.f((size_t)reduce_slices(N) * 3 * C);
-      const int Gs = launch_pm_reduce(h, r, st);
-      float* s3 = mem.f(3 * (size_t)C);
-      pm_sum_partials_kernel<<<(3 * C + 127) / 128, 128, 0, st>>>(r.partial, Gs, C, s3);
-      CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(dst, s3, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      h->launches += 1;
-    };
-    // ---- up blocks, last to first: g = gradient w.r.t. block i's pre-activation ----
-    for (int i = 4; i >= 0; --i) {
-      const UpSpec& s = kUp[i];
-      const std::string p = "up_blocks." + std::to_string(i) + ".conv_transpose.0.";
-      const float* xin = i > 0 ? A.u[i - 1] : A.z[6];
-      const long long npix = (long long)B * A.Hu[i + 1] * A.Wu[i + 1];
-      bias_grad(g, npix, s.co, want(p + "bias"));
-      wgrad(xin, A.Hu[i], A.Wu[i], s.ci, g, A.Hu[i + 1], A.Wu[i + 1], s.co, A.Hu[i], A.Wu[i], 1, 2, 2, want(p + "weight"));
-      // dgrad: gx[ih,iw,ci] = sum_{kh,kw,co} g[2ih+kh, 2iw+kw, co] * W[ci][co][kh][kw]; then through the previous LeakyReLU
-      float* gx = mem.f((size_t)B * A.Hu[i] * A.Wu[i] * s.ci);
-      PmConv c{};
-      c.x = g; c.Hi = A.Hu[i + 1]; c.Wi = A.Wu[i + 1]; c.Ci = s.co;
-      c.w = h->up[i].wt; c.y = gx; c.Ho = A.Hu[i]; c.Wo = A.Wu[i]; c.Co = s.ci; c.Cop = pad4(s.ci);
-      c.B = B; c.mode = PM_PLAIN; c.sh = 2; c.sw = 2;
-      if (i > 0) { c.dmask = A.u[i - 1]; c.mslope = 0.2f; }
-      launch_pm_conv(h, c, st);
-      g = gx;
+    pm_backward(h, mem, A, g, want, grad_x, st);
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int avc_pm_set_allreduce(avc_pm_handle* h, avc_allreduce_fn fn, void* ctx, float* comm, int64_t comm_floats, int32_t world_size) {
+  if (!h) return AVC_ERR_INVALID;
+  return pm_guarded(h, [&] {
+    if (world_size < 1) fail(AVC_ERR_INVALID, "world_size %d", world_size);
+    if (world_size > 1 && (!fn || !comm || comm_floats < 3 * 512)) fail(AVC_ERR_INVALID, "a callback and a buffer of at least 1536 floats are needed for world_size > 1");
+    h->ar = world_size > 1 ? fn : nullptr; h->ar_ctx = ctx; h->comm = comm; h->comm_cap = comm_floats; h->world = world_size;
+  });
+}
+
+int64_t avc_pm_param_count(const avc_pm_handle* h) { return h ? h->n_params : -1; }
+
+int avc_pm_export_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_t n, void* stream) {
+  if (!h) return AVC_ERR_INVALID;
+  return pm_guarded(h, [&] {
+    if (!h->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
+    if (!tensors || n <= 0) fail(AVC_ERR_INVALID, "no tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::map<std::string, std::pair<const float*, long long>> src;
+    for (const PmParam& q : h->params) src[q.name] = {h->P + q.off, q.n};
+    for (int l = 0; l < 7; ++l) {
+      const std::string p = "down_blocks." + std::to_string(l) + ".conv.2.";
+      src[p + "running_mean"] = {h->down[l].rmean, kDown[l].co};
+      src[p + "running_var"] = {h->down[l].rvar, kDown[l].co};
     }
-    // ---- down blocks, last to first: g = gradient w.r.t. block l's output z_l ----
-    for (int l = 6; l >= 0; --l) {
-      const DownSpec& s = kDown[l];
-      const DownW& w = h->down[l];
-      const std::string p = "down_blocks." + std::to_string(l) + ".conv.";
-      const long long npix = (long long)B * A.H[l + 1] * A.W[l + 1];
-      PmReduce r{};
-      r.y = A.y[l]; r.g = g; r.N = npix; r.C = s.co; r.kind = 1;
-      r.scale = A.scale[l]; r.shift = A.shift[l]; r.mean = A.mean[l]; r.rstd = A.rstd[l]; r.a = w.a;
-      r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
-      const int Gs = launch_pm_reduce(h, r, st);
-      float* sums = mem.f(3 * (size_t)s.co);
-      pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, Gs, s.co, sums);
-      CK(cudaGetLastError());
-      if (float* d = want(p + "2.bias")) CK(cudaMemcpyAsync(d, sums, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      if (float* d = want(p + "2.weight")) CK(cudaMemcpyAsync(d, sums + s.co, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      if (float* d = want(p + "3.weight")) {   // PReLU slope: sum over channels of q2 (fixed order)
-        pm_sum_n_kernel<<<1, 1, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
-        CK(cudaGetLastError());
-      }
-      float* gy = mem.f((size_t)npix * s.co);
-      const long long n4 = npix * s.co / 4;
-      pm_bn_bwd_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], g, A.scale[l], A.shift[l], A.mean[l], A.rstd[l], sums, w.a,
-                                                              1.f / (float)npix, gy, n4, s.co);
-      CK(cudaGetLastError());
-      h->launches += 2;
-      bias_grad(gy, npix, s.co, want(p + "1.bias"));
-      const float* xin = l > 0 ? A.z[l - 1] : A.x;
-      wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"));
-      if (l == 0 && !grad_x) break;
-      // dgrad on the padded coordinates, then fold the reflect padding back
-      const int Hp = A.H[l] + 2, Wp = A.W[l] + 2;
-      const int cip = pad4(s.ci);
-      float* gxp = mem.f((size_t)B * Hp * Wp * cip);
-      PmConv c{};
-      c.x = gy; c.Hi = A.H[l + 1]; c.Wi = A.W[l + 1]; c.Ci = s.co;
-      c.w = w.wt; c.y = gxp; c.Ho = Hp; c.Wo = Wp; c.Co = s.ci; c.Cop = cip;
-      c.B = B; c.mode = PM_TRANSPOSED; c.sh = s.sh; c.sw = s.sw;
-      launch_pm_conv(h, c, st);
-      if (l > 0) {
-        float* gx = mem.f((size_t)B * A.H[l] * A.W[l] * s.ci);
-        pm_fold_kernel<<<ew_grid((long long)B * A.H[l] * A.W[l] * s.ci / 4, h->sm_count), 256, 0, st>>>(gxp, gx, B, A.H[l], A.W[l], s.ci);
-        CK(cudaGetLastError());
-        g = gx;
-      } else {
-        pm_fold1_kernel<<<ew_grid((long long)B * A.H[0] * A.W[0], h->sm_count), 256, 0, st>>>(gxp, grad_x, B, A.H[0], A.W[0]);
-        CK(cudaGetLastError());
-      }
-      h->launches += 1;
+    for (int i = 0; i < n; ++i) {
+      const avc_weight_view& v = tensors[i];
+      if (!v.name || !v.data) fail(AVC_ERR_INVALID, "bad view %d", i);
+      auto it = src.find(v.name);
+      if (it == src.end()) fail(AVC_ERR_WEIGHTS, "unknown tensor '%s'", v.name);
+      long long cnt = 1;
+      for (int d = 0; d < v.ndim; ++d) cnt *= v.shape[d];
+      if (cnt != it->second.second) fail(AVC_ERR_WEIGHTS, "tensor '%s' has %lld elements, expected %lld", v.name, cnt, it->second.second);
+      CK(cudaMemcpyAsync(const_cast<float*>(v.data), it->second.first, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     CK(cudaStreamSynchronize(st));
   });
+}
+
+int avc_pm_trainer_begin(avc_pm_handle* pm, avc_handle* se, const avc_pm_trainer_args* a, void* stream, avc_pm_trainer** out) {
+  if (!pm || !out) return AVC_ERR_INVALID;
+  *out = nullptr;
+  return pm_guarded(pm, [&] {
+    if (!pm->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
+    if (!se || !a) fail(AVC_ERR_INVALID, "null argument");
+    if (a->B <= 0 || a->F < 2 || a->T < 2 || a->future_steps < 0) fail(AVC_ERR_INVALID, "bad B/F/T/future_steps");
+    if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->adam_eps > 0.f)) fail(AVC_ERR_INVALID, "bad Adam constants");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::unique_ptr<avc_pm_trainer> t(new avc_pm_trainer());
+    t->pm = pm; t->se = se; t->a = *a;
+    PmActs A;
+    pm_shapes(A, a->B, a->F, a->T);
+    t->Fp = A.Hu[5]; t->Tp = A.Wu[5];
+    if (t->Fp < a->F) fail(AVC_ERR_INVALID, "the prediction has %d mel rows, fewer than the %d of the input", t->Fp, a->F);
+    if (a->future_steps >= a->T) fail(AVC_ERR_INVALID, "future_steps %d leaves nothing to perturb in %d frames (the reference skips such batches, train_predictive.py:98)", a->future_steps, a->T);
+    t->mem.reset(new Arena(&pm->pool, st));
+    Arena& m = *t->mem;
+    const size_t np = (size_t)pm->n_params, nel = (size_t)a->B * a->F * a->T;
+    t->G = m.f(np); t->M = m.f(np); t->V = m.f(np);
+    t->src = nullptr; t->tgt = nullptr;
+    t->perturbed = m.f(nel); t->gmel = m.f(nel); t->loss = m.f(1);
+    t->src = m.f(nel); t->tgt = m.f(nel);
+    // speaker-embedding loss service: reads the trainer's three mel buffers every step, writes d loss / d perturbed
+    avc_spk_grad_args g{};
+    const int64_t cs[3] = {(int64_t)a->F * a->T, (int64_t)a->T, 1};
+    g.perturbed = t->perturbed; g.source = t->src; g.target = t->tgt; g.grad_out = t->gmel; g.loss_out = t->loss;
+    for (int i = 0; i < 3; ++i) { g.p_stride[i] = cs[i]; g.s_stride[i] = cs[i]; g.t_stride[i] = cs[i]; g.g_stride[i] = cs[i]; }
+    g.B = a->B; g.T = a->T; g.T_tgt = a->T; g.lambda = a->lambda; g.inv_norm = a->inv_norm; g.use_graph = 1;
+    const int rc = avc_spk_grad_begin(se, &g, stream, &t->spk);
+    if (rc != AVC_OK) fail(rc, "speaker encoder: %s", avc_last_error(se));
+    *out = t.release();
+  });
+}
+
+int avc_pm_trainer_step(avc_pm_trainer* t, const float* source, const float* target, float lr, float* loss_out, void* stream) {
+  if (!t) return AVC_ERR_INVALID;
+  avc_pm_handle* h = t->pm;
+  return pm_guarded(h, [&] {
+    if (!source || !target || !(lr > 0.f)) fail(AVC_ERR_INVALID, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const avc_pm_trainer_args& a = t->a;
+    const size_t nel = (size_t)a.B * a.F * a.T;
+    CK(cudaMemcpyAsync(t->src, source, nel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(t->tgt, target, nel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    Arena mem(&h->pool, st);
+    PmActs A;
+    pm_shapes(A, a.B, a.F, a.T);
+    // model.train(); predicted_perturbation = model(source_mels): running statistics updated in place (:64,92)
+    float* nm[7]; float* nv[7];
+    for (int l = 0; l < 7; ++l) { nm[l] = h->down[l].rmean; nv[l] = h->down[l].rvar; }
+    pm_forward(h, mem, A, t->src, nullptr, true, nm, nv, st);
+    VsmaskArgs v{};
+    v.src = t->src; v.pert = A.u[4]; v.B = a.B; v.F = a.F; v.T = a.T; v.Fp = t->Fp; v.Tp = t->Tp;
+    v.fs = a.future_steps; v.fe = std::min(a.future_steps + t->Tp, a.T);
+    v.lo_end = (int)(a.F * 0.3); v.hi_start = (int)(a.F * 0.7);     // utils/audio.py:96-97
+    v.e1 = a.eps1; v.e2 = a.eps2; v.e3 = a.eps3;
+    vsmask_apply_kernel<<<ew_grid((long long)nel, h->sm_count), 256, 0, st>>>(v, t->perturbed);
+    CK(cudaGetLastError());
+    h->launches++;
+    // three speaker-encoder forwards, the loss, backward to perturbed_mels (:113-123)
+    int rc = avc_spk_grad_step(t->spk, stream);
+    if (rc != AVC_OK) fail(rc, "speaker encoder: %s", avc_last_error(t->se));
+    if (loss_out) CK(cudaMemcpyAsync(loss_out, t->loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const long long n_out = (long long)a.B * t->Fp * t->Tp;
+    float* g = mem.f((size_t)n_out);
+    vsmask_grad_kernel<<<ew_grid(n_out, h->sm_count), 256, 0, st>>>(v, t->gmel, g);
+    CK(cudaGetLastError());
+    h->launches++;
+    // optimizer.zero_grad(); loss.backward()
+    std::map<std::string, float*> gout;
+    for (const PmParam& q : h->params) gout[q.name] = t->G + q.off;
+    auto want = [&](const std::string& k) -> float* { auto it = gout.find(k); return it == gout.end() ? nullptr : it->second; };
+    pm_backward(h, mem, A, g, want, nullptr, st);
+    if (h->world > 1) {
+      // data parallel: the parameter gradients of the global batch are the sum of the ranks' shares
+      if (h->n_params > h->comm_cap) fail(AVC_ERR_STATE, "the all-reduce buffer holds %lld floats, the gradient has %lld", h->comm_cap, h->n_params);
+      CK(cudaMemcpyAsync(h->comm, t->G, (size_t)h->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      pm_allreduce(h, h->n_params, st);
+      CK(cudaMemcpyAsync(t->G, h->comm, (size_t)h->n_params * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    // optimizer.step(): bias corrections in fp64 on the host like torch/optim/adam.py
+    t->step += 1;
+    PmAdamArgs ad{};
+    ad.P = h->P; ad.G = t->G; ad.M = t->M; ad.V = t->V; ad.tab = h->pdev; ad.n_tab = (int)h->params.size(); ad.n = h->n_params;
+    ad.step_size = (float)((double)lr / (1.0 - std::pow((double)a.beta1, (double)t->step)));
+    ad.bc2s = (float)std::sqrt(1.0 - std::pow((double)a.beta2, (double)t->step));
+    ad.b1w = 1.f - a.beta1; ad.b2 = a.beta2; ad.b2w = 1.f - a.beta2; ad.eps = a.adam_eps;
+    pm_adam_kernel<<<ew_grid(h->n_params, h->sm_count), 256, 0, st>>>(ad);
+    CK(cudaGetLastError());
+    h->launches++;
+    h->eval_stale = true;
+    // the step's activations go back to the pool when `mem` dies: the stream must have consumed them
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int avc_pm_trainer_grads(avc_pm_trainer* t, const avc_weight_view* grads, int32_t n, void* stream) {
+  if (!t) return AVC_ERR_INVALID;
+  avc_pm_handle* h = t->pm;
+  return pm_guarded(h, [&] {
+    if (!grads || n <= 0) fail(AVC_ERR_INVALID, "no tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n; ++i) {
+      const avc_weight_view& v = grads[i];
+      if (!v.name || !v.data) fail(AVC_ERR_INVALID, "bad view %d", i);
+      const PmParam* q = nullptr;
+      for (const PmParam& c : h->params) if (c.name == v.name) q = &c;
+      if (!q) fail(AVC_ERR_WEIGHTS, "unknown parameter '%s'", v.name);
+      long long cnt = 1;
+      for (int d = 0; d < v.ndim; ++d) cnt *= v.shape[d];
+      if (cnt != q->n) fail(AVC_ERR_WEIGHTS, "parameter '%s' has %lld elements, expected %lld", v.name, cnt, q->n);
+      CK(cudaMemcpyAsync(const_cast<float*>(v.data), t->G + q->off, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+int avc_pm_trainer_end(avc_pm_trainer* t) {
+  if (!t) return AVC_ERR_INVALID;
+  avc_pm_handle* h = t->pm;
+  const int rc = pm_guarded(h, [&] {
+    CK(cudaDeviceSynchronize());
+    if (t->spk) { avc_attack_end(t->spk, nullptr); t->spk = nullptr; }
+  });
+  delete t;
+  return rc;
 }
 
 }  // extern "C"

@@ -481,6 +481,50 @@ class HeaderSession:
             pass
 
 
+class SpeakerGradSession:
+    """avc_spk_grad_begin / avc_spk_grad_step / avc_attack_end: the speaker-embedding loss of train_predictive.py:113-123
+    and its gradient w.r.t. the perturbed batch.  The session owns four device tensors -- ``perturbed``, ``source``,
+    ``target`` [B,80,T] to fill before each ``step()`` and ``grad`` [B,80,T] / ``loss`` [1] it writes."""
+
+    def __init__(self, eng: "Engine", B: int, T: int, lambda_param: float = 0.5, inv_norm: float = 0.0, T_tgt: Optional[int] = None):
+        self.eng = eng
+        dev, c = eng.device, eng.c_in
+        T_tgt = T if T_tgt is None else T_tgt
+        self.perturbed = torch.zeros(B, c, T, device=dev)
+        self.source = torch.zeros(B, c, T, device=dev)
+        self.target = torch.zeros(B, c, T_tgt, device=dev)
+        self.grad = torch.zeros(B, c, T, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        a = _lib.SpkGradArgs()
+        a.perturbed, a.p_stride = self.perturbed.data_ptr(), _strides3(self.perturbed)
+        a.source, a.s_stride = self.source.data_ptr(), _strides3(self.source)
+        a.target, a.t_stride = self.target.data_ptr(), _strides3(self.target)
+        a.grad_out, a.g_stride = self.grad.data_ptr(), _strides3(self.grad)
+        a.loss_out = self.loss.data_ptr()
+        a.B, a.T, a.T_tgt, a.lam, a.inv_norm, a.use_graph = B, T, T_tgt, lambda_param, float(inv_norm), 1
+        sp = C.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.current_stream(dev).synchronize()
+            eng._check(eng._lib.avc_spk_grad_begin(eng._h, C.byref(a), eng._stream(), C.byref(sp)))
+        self._s = sp
+        eng._sessions += 1
+
+    def step(self) -> None:
+        self.eng._check(self.eng._lib.avc_spk_grad_step(self._s, self.eng._stream()))
+
+    def end(self) -> None:
+        if self._s is not None:
+            s, self._s = self._s, None
+            self.eng._sessions -= 1
+            self.eng._check(self.eng._lib.avc_attack_end(s, self.eng._stream()))
+
+    def __del__(self):
+        try:
+            self.end()
+        except Exception:
+            pass
+
+
 import weakref  # noqa: E402
 
 _ENGINES: "weakref.WeakKeyDictionary[nn.Module, Tuple[Tuple, Engine]]" = weakref.WeakKeyDictionary()

@@ -143,6 +143,27 @@ int avc_header_begin(avc_handle* h, const avc_header_args* a, void* stream, avc_
 int avc_header_step(avc_session* s, int32_t n, int32_t phase, void* stream);
 float* avc_header_grad_buffer(avc_session* s, int64_t* n_floats);
 
+/* ---- speaker-embedding loss and its gradient w.r.t. a perturbed batch ---------------------
+ * replaces: train_predictive.py:113-123 with speaker_encoder = this handle's AdaIN-VC SpeakerEncoder on mel.squeeze(1):
+ *   e_s = speaker_encoder(source); e_t = speaker_encoder(target); e_p = speaker_encoder(perturbed)
+ *   loss = mse(e_p, e_t) - lambda * mse(e_p, e_s); loss.backward()   -> d loss / d perturbed
+ * A session binds the four device buffers once; every avc_spk_grad_step re-reads their CURRENT contents (one captured
+ * graph: three encoder forwards, the loss, one backward), so a training loop refills them each step.  Ended with
+ * avc_attack_end.  The encoder's own parameter gradients (an unread side effect in the reference: the optimiser only
+ * owns the predictive model) are not computed. */
+typedef struct avc_spk_grad_args {
+  const float* perturbed; int64_t p_stride[3];  int32_t B, T;     /* [B,80,T]                                     */
+  const float* source;    int64_t s_stride[3];                    /* [B,80,T]                                     */
+  const float* target;    int64_t t_stride[3];  int32_t T_tgt;    /* [B,80,T_tgt]                                 */
+  float* grad_out;        int64_t g_stride[3];                    /* [B,80,T]: d loss / d perturbed               */
+  float* loss_out;                                                /* one float (device), may be NULL              */
+  float lambda;                                                   /* train_predictive.py:181 default 0.5          */
+  double inv_norm;                                                /* 1/(B_global*128); <= 0: this call's batch    */
+  int32_t use_graph;
+} avc_spk_grad_args;
+int avc_spk_grad_begin(avc_handle* h, const avc_spk_grad_args* a, void* stream, avc_session** out);
+int avc_spk_grad_step(avc_session* s, void* stream);              /* enqueues only */
+
 /* ---- forward-only model entry points (also used by the parity tests) --- */
 /* replaces: model.speaker_encoder(x) (models.py:327-343).  x [B,80,T] strided -> emb [B,c_out] */
 int avc_speaker_encoder(avc_handle* h, const float* x, const int64_t stride[3], int32_t B, int32_t T,
@@ -206,6 +227,51 @@ int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int3
 int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t F, int32_t T, float* out, float* loss,
                       float* grad_x, const avc_weight_view* grads, int32_t n_grads, void* stream);
 int64_t avc_pm_kernel_launches(const avc_pm_handle* h);
+/* ---- data-parallel training of the PredictiveModel (BASELINE config 5 "across 2/4/8 GPUs") ---------
+ * One process per GPU, each with its own handle and its slice of the global batch.  The sums that couple the ranks --
+ * BatchNorm2d batch statistics (sum, sum of squares per channel, predictive_model.py:23) in the forward pass, the two
+ * per-channel sums of its backward, and the parameter gradients -- are written into `comm` and handed to the caller's
+ * all-reduce (SUM over ranks, in place, ordered on `stream`; the Python host passes torch.distributed.all_reduce over
+ * NCCL), so N ranks x B windows compute exactly what one device computes on N*B windows.  world_size 1 / fn NULL
+ * switches it off.  The library itself links no communication library. */
+typedef int (*avc_allreduce_fn)(void* ctx, float* comm, int64_t n_floats, void* stream);   /* 0 = ok */
+int avc_pm_set_allreduce(avc_pm_handle* h, avc_allreduce_fn fn, void* ctx, float* comm, int64_t comm_floats, int32_t world_size);
+/* floats `comm` must hold for the gradient all-reduce (= number of trainable parameters, 6 088 904) */
+int64_t avc_pm_param_count(const avc_pm_handle* h);
+
+/* ---- VSMask predictor training step ---------------------------------------------------------
+ * replaces: the loop body of train_predictive_model (train_predictive.py:92-126) with utils/audio.py:77-116
+ * (apply_weighted_constraint) and speaker_encoder = the AdaIN-VC SpeakerEncoder of `se` on mel.squeeze(1):
+ *   pert = model(source)                                   [B,1,F',T'] = (95,63) for (80,100) windows
+ *   delta[:, :, :, fs:fe] = pert[:, :, :F, :fe-fs]          fs = future_steps, fe = min(fs + T', T)   (crop: see below)
+ *   delta = clamp per band (bins < int(.3F): eps1, < int(.7F): eps2, else eps3) of (source + delta) - source
+ *   perturbed = source + delta
+ *   loss = mse(SE(perturbed), SE(target)) - lambda * mse(SE(perturbed), SE(source)); backward; Adam(model.parameters(), lr)
+ * The reference as shipped raises at :102 ([B,1,80,63] += [B,1,95,63]) and at utils/audio.py:93 (3-D unpack of a 4-D
+ * tensor); this entry point DEFINES the two repairs a maintainer has to make for the loop to run at all: the
+ * prediction is cropped to its first F mel rows, and the constraint acts on the mel axis of the 4-D tensor.
+ * The handle's weights, BatchNorm running statistics and Adam moments are updated in place on the device. */
+typedef struct avc_pm_trainer avc_pm_trainer;
+typedef struct avc_pm_trainer_args {
+  int32_t B, F, T;                 /* windows [B,1,F,T]; F must equal the speaker encoder's c_in (80)               */
+  int32_t future_steps;            /* train_predictive.py:173, default 10                                           */
+  float eps1, eps2, eps3;          /* :178-183, 0.1 / 0.05 / 0.08                                                   */
+  float lambda;                    /* :184, 0.5                                                                      */
+  float beta1, beta2, adam_eps;    /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 (:57)                            */
+  double inv_norm;                 /* MSELoss normaliser 1/(B_global*128); <= 0: this rank's batch                   */
+} avc_pm_trainer_args;
+int avc_pm_trainer_begin(avc_pm_handle* pm, avc_handle* se, const avc_pm_trainer_args* a, void* stream, avc_pm_trainer** out);
+/* one optimiser step on (source, target) [B,1,F,T] contiguous device tensors; lr is this step's learning rate (the
+ * reference's ReduceLROnPlateau, :58-60,131, stays on the host).  loss_out: one device float or NULL (with sharding:
+ * this rank's part of the global loss).  Enqueues on `stream`; returns without synchronising. */
+int avc_pm_trainer_step(avc_pm_trainer* t, const float* source, const float* target, float lr, float* loss_out, void* stream);
+/* d loss / d (parameter) of the LAST step, by state_dict key, PyTorch shapes (test / inspection aid) */
+int avc_pm_trainer_grads(avc_pm_trainer* t, const avc_weight_view* grads, int32_t n, void* stream);
+int avc_pm_trainer_end(avc_pm_trainer* t);
+/* replaces: model.state_dict() after training (train_predictive.py:137-146): copies the handle's current parameters and
+ * running statistics into the caller's tensors, by state_dict key */
+int avc_pm_export_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_t n, void* stream);
+
 
 /* ---- introspection ----------------------------------------------------------------------- */
 int64_t avc_kernel_launches(const avc_handle* h);   /* kernels launched (graph nodes x replays) */

@@ -169,3 +169,40 @@ def test_sharded_header_equals_unsharded_gloo():
     o = O.run_header(O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0), src, tgt, 3, epsilon=0.002)
     assert torch.allclose(hdr, o["header"], rtol=0, atol=2e-6)
     assert torch.allclose(losses.double(), o["losses"], rtol=1e-4, atol=1e-9)
+
+
+def _pm_cb_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes as C
+        from attack_vc_b200 import _lib
+        from attack_vc_b200.predictive import allreduce_callback
+        comm = torch.arange(16, dtype=torch.float32) * (rank + 1)
+        cb = _lib.ALLREDUCE_FN(allreduce_callback(comm))        # exactly what PredictiveEngine.set_process_group registers
+        # called through the C function-pointer type, as libavc_b200 calls it: (ctx, comm, n_floats, stream)
+        rc = cb(None, C.c_void_p(comm.data_ptr()), 10, None)
+        if rank == 0:
+            q.put((rc, comm.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pm_allreduce_callback_gloo():
+    """The avc_allreduce_fn of the data-parallel PredictiveModel path (BatchNorm statistics, backward sums, parameter
+    gradients): sums the first n floats of the registered buffer over the ranks in place and leaves the rest alone."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pm_cb_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rc, comm = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = torch.arange(16, dtype=torch.float32)
+    want[:10] *= 3.0
+    assert rc == 0 and torch.equal(torch.from_numpy(comm), want)

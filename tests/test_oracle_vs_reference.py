@@ -111,3 +111,59 @@ def test_predictive_oracle_bit_exact():
     assert torch.equal(xin.grad, t["grad_x"])
     for k, v in t["new_stats"].items():
         assert torch.equal(pm.state_dict()[k], v), k
+
+
+def _ref_weighted_constraint():
+    """The reference's own apply_weighted_constraint (utils/audio.py:77-116).  utils/audio.py imports torchaudio, which is
+    not installed, so the method's source is cut out of the file and compiled as it stands (nothing is restated)."""
+    import ast
+    src = open(os.path.join(REFERENCE, "utils", "audio.py")).read()
+    tree = ast.parse(src)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MelSpectrogramConverter")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "apply_weighted_constraint")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"torch": torch}
+    exec(compile(mod, "ref_audio_apply_weighted_constraint", "exec"), ns)
+    return lambda p, e1, e2, e3: ns["apply_weighted_constraint"](None, p, epsilon1=e1, epsilon2=e2, epsilon3=e3)
+
+
+def test_vsmask_train_step_bit_exact(ref_model):
+    """oracle.vsmask_train_oracle.train_steps == the loop body of train_predictive.py:92-126 driven through the reference's
+    PredictiveModel module, the reference's apply_weighted_constraint and the reference's AdaIN-VC speaker encoder, with the
+    two documented repairs (crop to F mel rows, constraint on squeeze(1))."""
+    from oracle import predictive_oracle as P
+    from oracle import vsmask_train_oracle as V
+    constraint = _ref_weighted_constraint()
+    pm = _ref_predictive()
+    sd = P.pm_make_state_dict(0)
+    pm.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(21)
+    batches = [(0.5 * torch.randn(3, 1, 80, 100, generator=g), 0.5 * torch.randn(3, 1, 80, 100, generator=g)) for _ in range(3)]
+    # eps an order of magnitude below the defaults: this synthetic model predicts |p| ~ 1e-2, and the clamp must be live
+    enc = lambda m: ref_model.speaker_encoder(m.squeeze(1))
+    opt = torch.optim.Adam(pm.parameters(), lr=1e-3)                       # train_predictive.py:57
+    eps = (0.01, 0.005, 0.008)
+    losses = []
+    pm.train()                                                             # :64
+    n_clamped = 0
+    for source_mels, target_mels in batches:
+        predicted = pm(source_mels)                                        # :92
+        future_idx = 10
+        perturbed = source_mels.clone()                                    # :100
+        future_end = min(future_idx + predicted.shape[-1], perturbed.shape[-1])      # :101
+        perturbed[:, :, :, future_idx:future_end] += predicted[:, :, :80, :future_end - future_idx]   # :102 + repair 1
+        delta = (perturbed - source_mels).squeeze(1)                       # repair 2
+        weighted = constraint(delta, *eps).unsqueeze(1)                    # :105-110
+        n_clamped += int((weighted.squeeze(1) != delta).sum())
+        perturbed = source_mels + weighted                                 # :111
+        e_s, e_t, e_p = enc(source_mels), enc(target_mels), enc(perturbed)  # :114-116
+        mse = torch.nn.MSELoss()
+        loss = mse(e_p, e_t) - 0.5 * mse(e_p, e_s)                         # :119-122
+        opt.zero_grad(); loss.backward(); opt.step()                       # :125-127
+        losses.append(float(loss.detach()))
+    assert n_clamped > 0                                                   # the clamp (and its mask in the backward) is exercised
+    o = V.train_steps(sd, ref_model.speaker_encoder, batches, lr=1e-3, future_steps=10, eps=eps, lambda_param=0.5)
+    assert o["losses"].tolist() == losses
+    for k, v in pm.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert torch.equal(v, o["state"][k]), k
