@@ -157,9 +157,11 @@ class PredictiveEngine:
 
     __call__ = forward
 
-    def train_step(self, x: Tensor, want_grad_x: bool = False):
+    def train_step(self, x: Tensor, want_grad_x: bool = False, reuse_buffers: bool = False):
         """model.train(); out = model(x); loss = out.square().mean(); loss.backward() -> dict with
-        ``loss``, ``out``, ``grads`` (by state_dict key), ``new_stats`` and optionally ``grad_x``."""
+        ``loss``, ``out``, ``grads`` (by state_dict key), ``new_stats`` and optionally ``grad_x``.
+        ``reuse_buffers``: the gradients are views of ONE persistent flat tensor (``flat``: a data-parallel caller
+        all-reduces it in a single collective) and no per-call allocation is made for them."""
         x = self._x(x)
         B, _, F, T = x.shape
         Fo, To = self.out_shape(F, T)
@@ -167,15 +169,29 @@ class PredictiveEngine:
             out = torch.empty(B, 1, Fo, To, device=self.device, dtype=torch.float32)
             loss = torch.zeros(1, device=self.device, dtype=torch.float32)
             gx = torch.empty_like(x) if want_grad_x else None
-            bufs = {k: torch.zeros(s, device=self.device, dtype=torch.float32) for k, s in self.shapes.items()}
-            views, keep = _views(bufs)
+            flat = None
+            if reuse_buffers:
+                if getattr(self, "_gbufs", None) is None:
+                    names = [k for k in self.shapes if "running" not in k] + [k for k in self.shapes if "running" in k]
+                    sizes = [max(1, int(torch.Size(self.shapes[k]).numel())) for k in names]
+                    self._gflat = torch.zeros(sum(sizes), device=self.device, dtype=torch.float32)
+                    self._gparams = sum(n for k, n in zip(names, sizes) if "running" not in k)
+                    self._gbufs, o = {}, 0
+                    for k, n in zip(names, sizes):
+                        self._gbufs[k] = self._gflat[o:o + n].view(self.shapes[k]); o += n
+                    self._gviews = _views(self._gbufs)
+                bufs, (views, keep) = self._gbufs, self._gviews
+                flat = self._gflat[: self._gparams]
+            else:
+                bufs = {k: torch.zeros(s, device=self.device, dtype=torch.float32) for k, s in self.shapes.items()}
+                views, keep = _views(bufs)
             st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             self._check(self._lib.avc_pm_train_step(self._h, x.data_ptr(), B, F, T, out.data_ptr(), loss.data_ptr(),
                                                     gx.data_ptr() if gx is not None else None, views, len(bufs), st))
             del keep
         grads = {k: v for k, v in bufs.items() if "running" not in k}
         stats = {k: v for k, v in bufs.items() if "running" in k}
-        return {"loss": loss[0], "out": out, "grads": grads, "new_stats": stats, "grad_x": gx}
+        return {"loss": loss[0], "out": out, "grads": grads, "new_stats": stats, "grad_x": gx, "flat": flat}
 
 
 class PredictiveTrainer:

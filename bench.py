@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- attack iterations/s of the attack-vc perturbation loop on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload e2e|fb|emb]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload e2e|fb|emb|pm|vsmask]
 
 A *step* is one attack iteration (adv = x + eps*tanh(w); forward; loss; backward; Adam) over one
 batch of synthetic 80-bin mel utterances.  Default workload = BASELINE.json configs[1]: e2e_attack,
@@ -45,6 +45,7 @@ WORKLOADS = {
     "fb": ("fb", 64, 256, "BASELINE configs[2]: fb_attack, 80x256, batch 64 per GPU"),
     "emb": ("emb", 512, 512, "BASELINE configs[3]: emb_attack, 80x512, 512 utterances per GPU (4096 over 8)"),
     "pm": ("pm", 256, 100, "BASELINE configs[4]: VSMask predictive_model forward/backward, 80x100 windows, batch 256 per GPU"),
+    "vsmask": ("vsmask", 256, 100, "SURVEY 8f rank 3: VSMask predictor training step (train_predictive.py:92-127), 80x100 windows, batch 256 per GPU"),
 }
 KIND_NAMES = {0: "conv", 1: "norm", 2: "dense_tail", 3: "affine", 4: "loss", 5: "update", 6: "layout", 7: "copy"}
 
@@ -194,40 +195,57 @@ def gpu_eager_baseline(kind: str, B: int, T: int, dev, budget_s: float = 8.0):
 
 
 PM_GFLOP_FWD, PM_GFLOP_FWD_BWD = 0.2045, 0.6111        # per 80x100 window, SURVEY 8d
+# speaker-encoder work of one trainer step per window: three forwards + one dgrad pass = 4 x 2 x SE(T = 100) FLOP, SE(T) in MACs
+VSMASK_SE_GFLOP = 4 * 2 * (1011712 * 100 + 212992) / 1e9
 
 
-def pm_cpu_rate(B: int, budget_s: float):
-    """windows/s of the oracle training step (== reference module + autograd) on the host cores."""
+def pm_cpu_rate(B: int, budget_s: float, vsmask: bool = False):
+    """windows/s of the oracle training step (== reference module + autograd) on the host cores.  vsmask: the whole
+    trainer step of train_predictive.py:92-127 (predictive model + 3 speaker-encoder passes + Adam)."""
     from oracle import predictive_oracle as P
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = P.pm_make_state_dict(0)
-    x = torch.randn(B, 1, 80, 100, generator=torch.Generator().manual_seed(3))
-    P.pm_train_step(sd, x)
-    t0 = time.perf_counter(); P.pm_train_step(sd, x); t1 = time.perf_counter() - t0
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 1, 80, 100, generator=g)
+    if vsmask:
+        from oracle import adainvc_oracle as O
+        from oracle import vsmask_train_oracle as V
+        se = O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0)
+        y = torch.randn(B, 1, 80, 100, generator=g)
+        step = lambda: V.train_steps(sd, se.speaker_encoder, [(x, y)])      # noqa: E731
+    else:
+        step = lambda: P.pm_train_step(sd, x)                               # noqa: E731
+    step()
+    t0 = time.perf_counter(); step(); t1 = time.perf_counter() - t0
     n = int(max(2, min(50, budget_s / t1)))
     t0 = time.perf_counter()
     for _ in range(n):
-        P.pm_train_step(sd, x)
+        step()
     dt = time.perf_counter() - t0
     return n * B / dt, cores, n, dt
 
 
 def pm_arm(args, rank, world, local):
-    """BASELINE configs[4]: one step = model.train(); out = model(x); out.square().mean().backward() on a
-    batch of 80x100 windows.  Multi-GPU: independent replicas with local BatchNorm statistics."""
+    """BASELINE configs[4].  pm: one step = model.train(); out = model(x); out.square().mean().backward() on a batch of
+    80x100 windows.  vsmask: one step = the reference's whole trainer iteration (train_predictive.py:92-127).
+    Multi-GPU = data parallel as the config names it: every rank holds B windows of ONE global batch -- BatchNorm
+    statistics over the global batch (all-reduce of the per-channel sums, 7 layers forward + 7 backward), global loss
+    normaliser, one all-reduce of the 6.09 M parameter gradients per step -- NCCL through torch.distributed."""
     import torch.distributed as dist
-    _, B, T, desc = WORKLOADS["pm"]
+    vsmask = args.workload == "vsmask"
+    _, B, T, desc = WORKLOADS[args.workload]
+    metric = "predictive_model windows/s (" + ("VSMask trainer step: forward, speaker loss, backward, Adam)" if vsmask else "train forward+backward)")
     if args.impl == "reference":
         if rank != 0:
             return
-        rate, cores, n, dt = pm_cpu_rate(32, 20.0)
-        line = {"impl": "reference", "metric": "predictive_model windows/s (train forward+backward)", "value": rate, "unit": "windows/s",
+        rate, cores, n, dt = pm_cpu_rate(32, 20.0, vsmask)
+        line = {"impl": "reference", "metric": metric, "value": rate, "unit": "windows/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 32 / rate, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc, "windows_per_gpu": B, "window": "1x80x100"},
                 "cpu_baseline": {"value": rate, "unit": "windows/s", "cores": cores, "kind": "port",
-                                 "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference module), {dt:.1f} s"},
+                                 "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference pieces), {dt:.1f} s"},
                 "e2e": {"value": rate, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), flush=True)
         return
@@ -242,11 +260,20 @@ def pm_arm(args, rank, world, local):
         finally:
             sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     from attack_vc_b200.synthetic import pm_make_state_dict
-    from attack_vc_b200.predictive import PredictiveEngine
+    from attack_vc_b200.predictive import PredictiveEngine, PredictiveTrainer
     eng = PredictiveEngine({k: v.to(dev) for k, v in pm_make_state_dict(0).items()})
+    eng.set_process_group(None, world)
     K, W = args.steps, max(args.warmup, 3)
-    host = torch.randn(B, 1, 80, T, generator=torch.Generator().manual_seed(3 + rank)).pin_memory()
-    x = host.to(dev)
+    g = torch.Generator().manual_seed(3 + rank)
+    host = torch.randn(B, 1, 80, T, generator=g).pin_memory()
+    host_t = torch.randn(B, 1, 80, T, generator=g).pin_memory()
+    x, y = host.to(dev), host_t.to(dev)
+    se = trainer = None
+    if vsmask:
+        from attack_vc_b200 import Engine
+        from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree
+        se = Engine(ParamTree(SYNTH_CONFIG, seed=0).to(dev))
+        trainer = PredictiveTrainer(eng, se, batch_size=B, inv_norm=1.0 / (B * world * 128))
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -258,54 +285,71 @@ def pm_arm(args, rank, world, local):
         if world == 1:
             return v
         t = torch.tensor([v], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def step(xs, ys):
+        if vsmask:
+            return trainer.step(xs, ys, lr=1e-3)
+        r = eng.train_step(xs, reuse_buffers=True)
+        if world > 1:
+            dist.all_reduce(r["flat"])        # the gradients of the global batch: one 24.4 MB collective
+        return r["loss"]
+    launches_of = lambda: eng.kernel_launches + (se.kernel_launches if se is not None else 0)      # noqa: E731
     for _ in range(W):
-        eng.train_step(x)
-    l0 = eng.kernel_launches
+        step(x, y)
+    l0 = launches_of()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(K):
-            r = eng.train_step(x)
+            loss = step(x, y)
         e1.record()
         sync_all()
     ms = mx(e0.elapsed_time(e1))
-    launches = eng.kernel_launches - l0
+    launches = launches_of() - l0
     value = K * B * world / (ms / 1e3)
     # eval forward alone
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.forward(x); torch.cuda.synchronize(dev); a.record()
-    for _ in range(max(3, K)):
-        eng.forward(x)
-    b.record(); torch.cuda.synchronize(dev)
-    fwd_rate = max(3, K) * B * 1e3 / a.elapsed_time(b)
+    fwd_rate = None
+    if not vsmask:
+        eng.forward(x); torch.cuda.synchronize(dev); a.record()
+        for _ in range(max(3, K)):
+            eng.forward(x)
+        b.record(); torch.cuda.synchronize(dev)
+        fwd_rate = max(3, K) * B * 1e3 / a.elapsed_time(b)
     # e2e: pinned host windows -> device, training step, loss back to the host, every step
     sync_all(); t0 = time.perf_counter()
     for _ in range(K):
-        r = eng.train_step(host.to(dev, non_blocking=True)); lv = float(r["loss"].cpu())
+        loss = step(host.to(dev, non_blocking=True), host_t.to(dev, non_blocking=True) if vsmask else None); lv = float(loss.cpu())
     e2e_ms = mx(1e3 * (time.perf_counter() - t0))
     peaks = load_peaks()
-    tf = value / world * PM_GFLOP_FWD_BWD / 1e3
-    line = {"metric": "predictive_model windows/s (train forward+backward)", "value": value, "unit": "windows/s", "n_gpus": world,
+    gflop = PM_GFLOP_FWD_BWD + (VSMASK_SE_GFLOP if vsmask else 0.0)
+    tf = value / world * gflop / 1e3
+    dp = ("data parallel: BatchNorm over the global batch (all-reduce of per-channel sums, 7 layers forward + 7 backward), "
+          "one all-reduce of the 6 088 904 parameter gradients per step, NCCL via torch.distributed") if world > 1 else "single device"
+    line = {"metric": metric, "value": value, "unit": "windows/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "windows_per_gpu": B, "window": "1x80x100", "loss": "out.square().mean()",
-                       "batchnorm": "batch statistics per GPU (replicas; no cross-GPU statistics all-reduce)",
-                       "eval_forward_windows_per_s_per_gpu": fwd_rate, "l2": "activations of one step (2.6 GB at batch 256) exceed L2"},
+            "config": {"workload": desc, "windows_per_gpu": B, "window": "1x80x100",
+                       "loss": "mse(SE(perturbed), SE(target)) - 0.5 mse(SE(perturbed), SE(source)), Adam lr 1e-3" if vsmask else "out.square().mean()",
+                       "multi_gpu": dp, "l2": "activations of one step (2.6 GB at batch 256) exceed L2"},
+            "detail": {"eval_forward_windows_per_s_per_gpu": fwd_rate},
             "clocks": clk.summary(),
-            "e2e": {"value": K * B * world / (e2e_ms / 1e3), "unit": "windows/s", "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4,
-                    "api": "PredictiveEngine.train_step(pinned host windows) + loss.cpu() per step"},
+            "e2e": {"value": K * B * world / (e2e_ms / 1e3), "unit": "windows/s", "h2d_bytes_per_step": host.numel() * 4 * (2 if vsmask else 1), "d2h_bytes_per_step": 4,
+                    "api": ("PredictiveTrainer.step" if vsmask else "PredictiveEngine.train_step") + "(pinned host windows) + loss.cpu() per step"},
             "gpu_launches": launches, "launches_per_step": launches / K,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-                         "traffic": None, "kernel": "whole step (direct fp32 CUDA-core conv2d / conv-transpose / wgrad kernels, round-1 untuned)",
-                         "algorithmic_gflop_per_window": PM_GFLOP_FWD_BWD, "peak_source": peaks["source"] + ", bf16 dense burst"},
+                         "traffic": None, "kernel": "whole step (PredictiveModel conv2d / conv-transpose / wgrad kernels" + (" + speaker-encoder tcgen05 convs)" if vsmask else ")"),
+                         "algorithmic_gflop_per_window": gflop, "peak_source": peaks["source"] + ", bf16 dense burst"},
             "loss": lv}
     if world == 1 and not args.no_cpu_baseline:
-        rate, cores, n, dt = pm_cpu_rate(32, 15.0)
+        rate, cores, n, dt = pm_cpu_rate(32, 15.0, vsmask)
         line["cpu_baseline"] = {"value": rate, "unit": "windows/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference module), {dt:.1f} s"}
+                                "sample": f"{n} training steps of 32 windows, oracle (bit-identical to the reference pieces), {dt:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if trainer is not None:
+        trainer.close(); se.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -345,7 +389,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "pm":
+    if args.workload in ("pm", "vsmask"):
         if args.impl != "reference" and not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; attack_vc_b200 has no CPU fallback (use --impl reference for the CPU loop)")
         pm_arm(args, rank, world, local)

@@ -2,7 +2,9 @@
   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/nccl_check.py
 1. sharded_attack (emb, e2e): batch sliced over the ranks, global MSE normaliser, all_gather of the perturbed
    utterances + all_reduce of the loss curves == the unsharded call on one GPU.
-2. sharded_header_optimize: per-iteration all_reduce of the 80*T header gradient == the unsharded optimisation."""
+2. sharded_header_optimize: per-iteration all_reduce of the 80*T header gradient == the unsharded optimisation.
+3. data-parallel PredictiveModel (BASELINE config 5): the VSMask trainer on DIFFERENT shards per rank, BatchNorm over
+   the global batch + gradient all-reduce through the library's callback == one GPU on the concatenated batch."""
 import os
 import sys
 
@@ -56,6 +58,36 @@ def main():
     if rank == 0:
         print(f"sharded_header_optimize B={B} over {world} GPUs: median |h - unsharded| {float(err.median()):.2e}, "
               f"frac > 1e-4 {float((err > 1e-4).float().mean()):.4f}, loss rel err {lerr:.2e}, identical on all ranks {ident} -> {'PASS' if good and ident else 'FAIL'}")
+    # ---- 3. data-parallel VSMask trainer ----
+    from attack_vc_b200.predictive import PredictiveEngine, PredictiveTrainer
+    from attack_vc_b200.synthetic import pm_make_state_dict
+    Bl, steps = 3, 2
+    g = torch.Generator().manual_seed(31)
+    data = [(0.5 * torch.randn(Bl * world, 1, 80, 100, generator=g).cuda(), 0.5 * torch.randn(Bl * world, 1, 80, 100, generator=g).cuda()) for _ in range(steps)]
+    sd = {k: v.cuda() for k, v in pm_make_state_dict(0).items()}
+    eps = dict(epsilon1=0.01, epsilon2=0.005, epsilon3=0.008)
+    pm_one = PredictiveEngine(sd)
+    tr_one = PredictiveTrainer(pm_one, eng, batch_size=Bl * world, **eps)
+    pm_dp = PredictiveEngine(sd)
+    pm_dp.set_process_group(None, world)
+    tr_dp = PredictiveTrainer(pm_dp, eng, batch_size=Bl, inv_norm=1.0 / (Bl * world * 128), **eps)
+    lerr = 0.0
+    for s_, t_ in data:
+        l1 = tr_one.step(s_, t_)
+        l2 = tr_dp.step(s_[rank * Bl:(rank + 1) * Bl].contiguous(), t_[rank * Bl:(rank + 1) * Bl].contiguous()).clone()
+        dist.all_reduce(l2)
+        lerr = max(lerr, abs(float(l2) - float(l1)) / abs(float(l1)))
+    g1, g2 = tr_one.grads(), tr_dp.grads()
+    gerr = max(float((g2[k] - g1[k]).norm() / g1[k].norm().clamp_min(1e-30)) for k in g1 if not k.endswith("conv.1.bias"))
+    a, b = tr_one.state_dict(), tr_dp.state_dict()
+    serr = max(float((b[k] - a[k]).norm() / a[k].norm().clamp_min(1e-30)) for k in a if "running" in k)
+    perr = max(float((b[k] - a[k]).abs().mean()) for k in a if "running" not in k)
+    good = lerr < 1e-4 and gerr < 1e-3 and serr < 1e-5 and perr < 0.05 * steps * 1e-3
+    ok &= good
+    if rank == 0:
+        print(f"data-parallel VSMask trainer, {world} x {Bl} windows: loss rel err {lerr:.2e}, worst gradient rel err {gerr:.2e}, "
+              f"running-statistics rel err {serr:.2e}, mean |param - single GPU| {perr:.2e} -> {'PASS' if good else 'FAIL'}")
+    tr_one.close(); tr_dp.close(); pm_one.close(); pm_dp.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
