@@ -23,6 +23,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv_wgrad.cuh"
+#include "wgrad_tc.cuh"
 #include "elementwise.cuh"
 
 using namespace avc;
@@ -254,6 +255,7 @@ void launch_conv_cfg(ConvArgs a, cudaStream_t st) {
 }
 
 void init_kernel_attributes() {
+  wt_init_attributes();
   CK(cudaFuncSetAttribute(conv_simt_kernel<4, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<1, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -2194,39 +2196,84 @@ int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx, 
   });
 }
 
-int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias, int32_t B, int32_t T,
-                     int32_t c_in, int32_t c_out, int32_t k, int32_t stride, void* stream) {
+// dW[co][ci][j] = sum over splits (fp64, in order) of partial[s][j][ci][co]   (tensor-core path: c_in rows, c_out contiguous)
+__global__ void wt_final_1d_kernel(const float* __restrict__ partial, int splits, int k, int c_in, int c_out, float* __restrict__ dw) {
+  const long long n = (long long)k * c_in * c_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int q = 0; q < splits; ++q) s += (double)partial[(long long)q * n + i];
+    const int co = (int)(i % c_out);
+    const long long t = i / c_out;
+    const int ci = (int)(t % c_in), j = (int)(t / c_in);
+    dw[((long long)co * c_in + ci) * k + j] = (float)s;
+  }
+}
+
+int avc_conv1d_wgrad_ex(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias, int32_t B, int32_t T,
+                        int32_t c_in, int32_t c_out, int32_t k, int32_t stride, int32_t impl, void* stream) {
   if (!h) return AVC_ERR_INVALID;
   return guarded(h, [&] {
     check_conv_dims(B, T, c_in, c_out, k, stride);
     if (!x || !dy || !dw) fail(AVC_ERR_INVALID, "conv1d_wgrad: null tensor");
+    if (impl < 0 || impl > 2) fail(AVC_ERR_INVALID, "conv1d_wgrad: impl %d (0 auto, 1 fp32 CUDA cores, 2 tcgen05)", impl);
     const int To = cdiv(T, stride);
     const long long rows = (long long)B * To;
-    WgradArgs a{};
-    a.x = x; a.T = T; a.c_in = c_in; a.dy = dy; a.To = To; a.c_out = c_out;
-    a.B = B; a.k = k; a.stride = stride; a.pl = k / 2;
-    const int tiles = cdiv(c_out, kWgTile) * cdiv(c_in, kWgTile) * k;
-    // enough row splits for ~3 CTAs per SM, at least 64 rows each
-    int splits = std::max(1, std::min<int>((int)((rows + 63) / 64), cdiv(3 * h->sm_count, tiles)));
-    a.rows_per_split = (int)((rows + splits - 1) / splits);
-    a.rows_per_split = cdiv(a.rows_per_split, kWgRows) * kWgRows;
-    splits = (int)((rows + a.rows_per_split - 1) / a.rows_per_split);
-    a.splits = splits;
-    Arena tmp(&h->pool, (cudaStream_t)stream);   // partial tiles: a slab recycled through the handle's pool (no cudaMalloc per call)
-    a.partial = tmp.f((size_t)splits * k * c_out * c_in);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(cdiv(c_out, kWgTile), cdiv(c_in, kWgTile), k * splits);
-    conv_wgrad_kernel<<<grid, 256, 0, st>>>(a);
-    CK(cudaGetLastError());
-    conv_wgrad_final_kernel<<<ew_grid((long long)k * c_out * c_in, h->sm_count), 256, 0, st>>>(a.partial, splits, k, c_out, c_in, dw);
-    CK(cudaGetLastError());
+    Arena tmp(&h->pool, st);   // partial tiles / operand planes: slabs recycled through the handle's pool (no cudaMalloc per call)
+    const bool tc = impl == 2 || (impl == 0 && rows >= h->tc_min_rows && c_in % 4 == 0 && c_out % 4 == 0 && k <= kWtMaxTaps);
+    if (tc) {
+      if (c_in % 4 || c_out % 4 || k > kWtMaxTaps) fail(AVC_ERR_INVALID, "conv1d_wgrad: the tensor-core kernel needs channel counts that are multiples of 4 and k <= %d", kWtMaxTaps);
+      // operand planes: x reflect-padded (models.py:23-28), both operands split hi / lo for 3xTF32
+      const int pl = k / 2, pr = k / 2 - (k % 2 == 0 ? 1 : 0), Tp = T + pl + pr;
+      float* xh = tmp.f((size_t)B * Tp * c_in); float* xl = tmp.f((size_t)B * Tp * c_in);
+      float* gh = tmp.f((size_t)rows * c_out);  float* gl = tmp.f((size_t)rows * c_out);
+      wt_split_pad_kernel<<<ew_grid((long long)B * Tp * c_in / 4, h->sm_count), 256, 0, st>>>(x, xh, xl, B, 1, T, c_in, 0, pl, pr);
+      CK(cudaGetLastError());
+      wt_split_pad_kernel<<<ew_grid(rows * c_out / 4, h->sm_count), 256, 0, st>>>(dy, gh, gl, B, 1, To, c_out, 0, 0, 0);
+      CK(cudaGetLastError());
+      WtArgs p{};
+      wt_pick_boxes(p, To, 1, B);
+      p.a_wmul = stride; p.a_hmul = 1; p.g_wmul = 1; p.g_hmul = 1;
+      for (int j = 0; j < k; ++j) { p.a_woff[j] = j; p.a_hoff[j] = 0; p.g_woff[j] = 0; p.g_hoff[j] = 0; }
+      p.n_taps = k; p.Ci = c_in; p.Co = c_out; p.Cop = c_out;
+      const int S = wt_splits(p, h->sm_count);
+      p.partial = tmp.f((size_t)S * k * c_in * c_out);
+      const WtOperand A{xh, xl, c_in, Tp, 1, B, stride, 1}, G{gh, gl, c_out, To, 1, B, 1, 1};
+      launch_wgrad_tc(A, G, p, S, st);
+      wt_final_1d_kernel<<<ew_grid((long long)k * c_out * c_in, h->sm_count), 256, 0, st>>>(p.partial, S, k, c_in, c_out, dw);
+      CK(cudaGetLastError());
+      h->launches += 4;
+    } else {
+      WgradArgs a{};
+      a.x = x; a.T = T; a.c_in = c_in; a.dy = dy; a.To = To; a.c_out = c_out;
+      a.B = B; a.k = k; a.stride = stride; a.pl = k / 2;
+      const int tiles = cdiv(c_out, kWgTile) * cdiv(c_in, kWgTile) * k;
+      // enough row splits for ~3 CTAs per SM, at least 64 rows each
+      int splits = std::max(1, std::min<int>((int)((rows + 63) / 64), cdiv(3 * h->sm_count, tiles)));
+      a.rows_per_split = (int)((rows + splits - 1) / splits);
+      a.rows_per_split = cdiv(a.rows_per_split, kWgRows) * kWgRows;
+      splits = (int)((rows + a.rows_per_split - 1) / a.rows_per_split);
+      a.splits = splits;
+      a.partial = tmp.f((size_t)splits * k * c_out * c_in);
+      dim3 grid(cdiv(c_out, kWgTile), cdiv(c_in, kWgTile), k * splits);
+      conv_wgrad_kernel<<<grid, 256, 0, st>>>(a);
+      CK(cudaGetLastError());
+      conv_wgrad_final_kernel<<<ew_grid((long long)k * c_out * c_in, h->sm_count), 256, 0, st>>>(a.partial, splits, k, c_out, c_in, dw);
+      CK(cudaGetLastError());
+      h->launches += 2;
+    }
     if (dbias) {
       conv_bgrad_kernel<<<cdiv(c_out, 32), 256, 0, st>>>(dy, rows, c_out, dbias);
       CK(cudaGetLastError());
+      h->launches += 1;
     }
-    h->launches += dbias ? 3 : 2;
     CK(cudaStreamSynchronize(st));
   });
+}
+
+int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias, int32_t B, int32_t T,
+                     int32_t c_in, int32_t c_out, int32_t k, int32_t stride, void* stream) {
+  return avc_conv1d_wgrad_ex(h, x, dy, dw, dbias, B, T, c_in, c_out, k, stride, 0, stream);
 }
 
 int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond, const float* res, int32_t up, float* out,

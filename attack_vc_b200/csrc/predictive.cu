@@ -17,6 +17,7 @@
 #include "../../include/avc_b200.h"
 #include "common.cuh"
 #include "host_util.h"
+#include "wgrad_tc.cuh"
 
 using namespace avc;
 
@@ -567,6 +568,73 @@ __global__ void pm_wgrad_final_kernel(const float* partial, int S, int Ci, int C
   }
 }
 
+// ---- weight gradient of the two single-channel ends of the model ----------------------------------------------------
+// First down block (c_in = 1) and last up block (c_out = 1): out[tap][c] = sum_pix V[pix][c] * s[src(pix, tap)] with V a
+// C-channel tensor and s a scalar field -- a reduction over ~1M pixels into 9 x C numbers, bound by reading V once.
+// (The tiled GEMM kernel spends 2.1 ms on each: one useful row per 64 x 64 tile.)
+//   down: base pixel = output (oh, ow): V = gy, s = x[b, reflect(oh*sh + kh - 1), reflect(ow*sw + kw - 1)]
+//   up:   base pixel = input (ih, iw):  V = x,  s = g[b, 2 ih + kh, 2 iw + kw]
+struct PmWgradC1 {
+  const float* V; int C;
+  const float* S; int Hs, Ws;
+  int B, Hb, Wb, up, sh, sw;
+  float* partial;     // [gridDim.x][9][C]
+};
+__global__ void __launch_bounds__(256) pm_wgrad_c1_kernel(const PmWgradC1 p) {
+  __shared__ float4 red[8][9][8];
+  const int C4 = p.C >> 2;                       // 8 channel lanes (C = 32)
+  const int cl = threadIdx.x % C4, pl = threadIdx.x / C4, PL = blockDim.x / C4;
+  const long long N = (long long)p.B * p.Hb * p.Wb;
+  float4 acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = f4zero();
+  for (long long i = (long long)blockIdx.x * PL + pl; i < N; i += (long long)gridDim.x * PL) {
+    const int wb = (int)(i % p.Wb);
+    const long long r = i / p.Wb;
+    const int hb = (int)(r % p.Hb), b = (int)(r / p.Hb);
+    const float4 v = ld4(p.V + i * p.C + 4 * cl);
+    const float* sp = p.S + (long long)b * p.Hs * p.Ws;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hs = p.up ? 2 * hb + kh : pm_src(hb, kh, p.Hs, p.sh, PM_REFLECT);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ws = p.up ? 2 * wb + kw : pm_src(wb, kw, p.Ws, p.sw, PM_REFLECT);
+        const float sv = sp[hs * p.Ws + ws];
+        float4& a = acc[kh * 3 + kw];
+        a.x = fmaf(v.x, sv, a.x); a.y = fmaf(v.y, sv, a.y); a.z = fmaf(v.z, sv, a.z); a.w = fmaf(v.w, sv, a.w);
+      }
+    }
+  }
+  // lanes of a warp = 4 pixels x 8 channel lanes: fold the pixel lanes, then the 8 warps (fixed order)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float4 a = acc[t];
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    if ((threadIdx.x & 31) < 8) red[threadIdx.x >> 5][t][threadIdx.x & 7] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 * 8) {
+    const int t = threadIdx.x / 8, c = threadIdx.x % 8;
+    float4 s4 = red[0][t][c];
+    for (int w = 1; w < 8; ++w) s4 = f4add(s4, red[w][t][c]);
+    st4(p.partial + ((size_t)blockIdx.x * 9 + t) * p.C + 4 * c, s4);
+  }
+}
+// out[c*9 + tap] = sum_g partial[g][tap][c]   (PyTorch layout of both [C,1,3,3] weights)
+__global__ void pm_wgrad_c1_final_kernel(const float* partial, int G, int C, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * C) return;
+  const int tap = i / C, c = i % C;
+  double s = 0.0;
+  for (int g = 0; g < G; ++g) s += partial[((size_t)g * 9 + tap) * C + c];
+  out[c * 9 + tap] = (float)s;
+}
+
 // ---- model ---------------------------------------------------------------------------------------------
 struct DownSpec { int ci, co, sh, sw; };
 struct UpSpec { int ci, co; };
@@ -800,6 +868,49 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
   const int B = A.B;
   auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst) {
     if (!dst) return;
+    static const bool no_tc = getenv("AVC_PM_NO_TC") != nullptr;
+    if (!no_tc && Ci % 4 == 0 && Ci >= 32 && Co % 4 == 0 && Co >= 32) {
+      // tensor cores: TMA-fed tcgen05 wgrad (wgrad_tc.cuh).  The operands are split hi / lo for 3xTF32 by one elementwise
+      // pass each; for a down block that pass also materialises ReflectionPad2d(1), so that a tap is a box offset and the
+      // conv stride the tensor map's element stride (for a transposed conv the stride sits on the gradient instead).
+      const int pad = up ? 0 : 1, Hap = Ha + 2 * pad, Wap = Wa + 2 * pad;
+      const size_t na = (size_t)B * Hap * Wap * Ci, ng = (size_t)B * Hg * Wg * Co;
+      float* ah = mem.f(na); float* al = mem.f(na); float* gh = mem.f(ng); float* gl = mem.f(ng);
+      wt_split_pad_kernel<<<ew_grid((long long)na / 4, h->sm_count), 256, 0, st>>>(Ain, ah, al, B, Ha, Wa, Ci, pad, pad, pad);
+      CK(cudaGetLastError());
+      wt_split_pad_kernel<<<ew_grid((long long)ng / 4, h->sm_count), 256, 0, st>>>(G, gh, gl, B, Hg, Wg, Co, 0, 0, 0);
+      CK(cudaGetLastError());
+      WtArgs p{};
+      wt_pick_boxes(p, Wb, Hb, B);
+      p.a_wmul = up ? 1 : sw; p.a_hmul = up ? 1 : sh; p.g_wmul = up ? 2 : 1; p.g_hmul = up ? 2 : 1;
+      for (int t = 0; t < 9; ++t) {
+        p.a_woff[t] = up ? 0 : t % 3; p.a_hoff[t] = up ? 0 : t / 3;
+        p.g_woff[t] = up ? t % 3 : 0; p.g_hoff[t] = up ? t / 3 : 0;
+      }
+      p.n_taps = 9; p.Ci = Ci; p.Co = Co; p.Cop = pad4(Co);
+      const int S = wt_splits(p, h->sm_count);
+      p.partial = mem.f((size_t)S * 9 * Ci * p.Cop);
+      const WtOperand Aop{ah, al, Ci, Wap, Hap, B, up ? 1 : sw, up ? 1 : sh}, Gop{gh, gl, Co, Wg, Hg, B, up ? 2 : 1, up ? 2 : 1};
+      launch_wgrad_tc(Aop, Gop, p, S, st);
+      pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(p.partial, S, Ci, Co, p.Cop, up, dst);
+      CK(cudaGetLastError());
+      h->launches += 4;
+      return;
+    }
+    if (((up && Co == 1 && Ci == 32) || (!up && Ci == 1 && Co == 32))) {
+      PmWgradC1 c{};
+      c.V = up ? Ain : G; c.C = 32; c.S = up ? G : Ain; c.Hs = up ? Hg : Ha; c.Ws = up ? Wg : Wa;
+      c.B = B; c.Hb = Hb; c.Wb = Wb; c.up = up; c.sh = sh; c.sw = sw;
+      const long long N = (long long)B * Hb * Wb;
+      const int Gc = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 8, N / (32 * 16)));
+      c.partial = mem.f((size_t)Gc * 9 * 32);
+      pm_wgrad_c1_kernel<<<Gc, 256, 0, st>>>(c);
+      CK(cudaGetLastError());
+      pm_wgrad_c1_final_kernel<<<(9 * 32 + 127) / 128, 128, 0, st>>>(c.partial, Gc, 32, dst);
+      CK(cudaGetLastError());
+      h->launches += 2;
+      return;
+    }
     PmWgrad q{};
     q.A = Ain; q.Ha = Ha; q.Wa = Wa; q.Ci = Ci; q.G = G; q.Hg = Hg; q.Wg = Wg; q.Co = Co;
     q.B = B; q.Hb = Hb; q.Wb = Wb; q.up = up; q.sh = sh; q.sw = sw; q.Cop = pad4(Co);
@@ -1058,6 +1169,7 @@ int avc_pm_create(avc_pm_handle** out, int device) {
     auto h = std::make_unique<avc_pm_handle>();
     h->device = device; h->sm_count = p.multiProcessorCount;
     CK(cudaFuncSetAttribute(pm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    wt_init_attributes();
     *out = h.release();
   });
 }

@@ -1,0 +1,271 @@
+// wgrad_tc.cuh -- convolution weight gradients on the tensor cores: TMA tensor loads + tcgen05.mma, accumulators in TMEM.
+//
+//   dW[tap][ci][co] = sum over base pixels p of  A[srcA(p, tap)][ci] * G[srcG(p, tap)][co]
+//
+// Both operands are activation-shaped NHWC tensors (a 1-D time-major tensor is H = 1) whose contraction axis -- the
+// pixel -- is the SLOW axis and whose channels are contiguous: exactly the "MN-major" operand form of tcgen05
+// (instruction-descriptor bits 15/16).  So nothing is transposed or gathered by threads:
+//   * one elected thread issues `cp.async.bulk.tensor.4d` (TMA, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) for boxes of
+//     {32 channels x bw x bh x bb pixels}; conv stride / the 2x up-sampling of a transposed conv are the tensor map's
+//     elementStrides, the tap is an offset of the box origin, rows and images outside the tensor are zero-filled by the
+//     TMA unit.  The box lands as [pixel][128 B] rows = the canonical MN-major SWIZZLE_128B_BASE32B operand (4-row atoms
+//     of 512 B along K, channel blocks LBO apart), the only MN-major form 32-bit operands have;
+//   * one elected thread issues UTCHMMA kind::tf32, M = 128 (c_in) x N <= 128 (c_out) x K = 8 pixels;
+//   * four warps read the finished tile from TMEM and store this CTA's partial.
+// Reflect padding cannot be expressed by a tensor map, so the padded operand is materialised by the same pass that
+// splits the operands for precision (next paragraph) -- one elementwise kernel per operand.
+//
+// Precision: 3xTF32.  a = a_hi + a_lo with a_hi = tf32(a) (round to nearest, stored with a zero low mantissa so the
+// tensor core's truncation is the identity) and a_lo = a - a_hi (exact in fp32; its own truncation to tf32 costs 2^-23);
+// D += a_hi*g_hi + a_lo*g_hi + a_hi*g_lo, the dropped a_lo*g_lo term is 2^-24.  Every operand plane is fed by TMA, so the
+// kernel has no loader warps at all.  TMEM accumulates with truncation (~ -8e-8 relative per accumulate, scripts/tc_probe.py);
+// the pixel axis is split over CTAs so that one accumulator sees at most a few hundred MMAs, and the partials are summed
+// in fp64 in a fixed order.  Stated tolerance: 2e-5 relative per tensor against an fp64 evaluation (tests/test_kernels_gpu.py).
+#pragma once
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "tc_common.cuh"
+
+namespace avc {
+
+constexpr int kWtKP = 32;                        // pixels per pipeline stage
+constexpr int kWtStages = 3;
+constexpr int kWtPlane = 4 * kWtKP * 128;        // one operand plane of a stage: 4 channel blocks x KP rows x 128 B = 16 KB
+constexpr int kWtStageBytes = 4 * kWtPlane;      // A_hi | A_lo | G_hi | G_lo
+constexpr int kWtThreads = 192;                  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kWtMaxTaps = 9;
+inline size_t wt_smem_bytes() { return (size_t)kWtStages * kWtStageBytes + 1024 + 128; }
+
+struct WtArgs {
+  int nw, nh, nb;                        // boxes along w, h, b of the BASE pixel grid
+  int bw, bh, bb;                        // base pixels per box along each axis (bw*bh*bb <= kWtKP)
+  int a_wmul, a_hmul, g_wmul, g_hmul;    // tensor coordinate of base pixel (w, h): w * wmul + woff[tap], h * hmul + hoff[tap]
+  int a_woff[kWtMaxTaps], a_hoff[kWtMaxTaps], g_woff[kWtMaxTaps], g_hoff[kWtMaxTaps];
+  int n_taps;
+  int Ci, Co, Cop;
+  float* partial;                        // [gridDim.x splits][n_taps][Ci][Cop]
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+// MN-major TF32 operand.  32-bit MN-major operands have exactly one legal shared-memory form: SWIZZLE_128B_BASE32B (layout
+// type 1; 32-byte chunks of a 128-byte row XOR-ed with the row index mod 4 -- what CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+// writes): atoms of 4 rows (K) x 128 B, K groups SBO = 512 B apart (consecutive rows), 32-channel blocks `lbo` bytes apart.
+__device__ __forceinline__ uint64_t wt_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+static __global__ void __launch_bounds__(kWtThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl, const WtArgs p) {
+  extern __shared__ unsigned char wt_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wt_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWtStages * kWtStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 8 * (kWtStages + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * kWtStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, tap = blockIdx.z;
+  const int n_nt = (p.Co + 127) / 128;
+  const int ci0 = ((int)blockIdx.y / n_nt) * 128, co0 = ((int)blockIdx.y % n_nt) * 128;
+  const int mb = min(4, (p.Ci - ci0 + 31) / 32), nbk = min(4, (p.Co - co0 + 31) / 32);   // 32-channel blocks that exist
+  const int N = nbk * 32;
+  const int n_boxes = p.nw * p.nh * p.nb;
+  const int per = (n_boxes + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int q_lo = split * per, q_hi = min(n_boxes, q_lo + per);
+  const int rows = p.bw * p.bh * p.bb, ksteps = (rows + 7) >> 3;
+
+  // unloaded channel blocks and the K tail of every stage must read as zeros
+  for (int i = threadIdx.x; i < kWtStages * kWtStageBytes / 16; i += kWtThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWtStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      const uint32_t bytes = (uint32_t)((mb + nbk) * 2 * rows * 128);
+      const int awo = p.a_woff[tap], aho = p.a_hoff[tap], gwo = p.g_woff[tap], gho = p.g_hoff[tap];
+      int s = 0; uint32_t ph = 0;
+      for (int q = q_lo; q < q_hi; ++q) {
+        const int wi = q % p.nw, t = q / p.nw;
+        const int hi = t % p.nh, bi = t / p.nh;
+        const int w0 = wi * p.bw, h0 = hi * p.bh, b0 = bi * p.bb;
+        mbar_wait(empty(s), ph ^ 1);
+        mbar_expect_tx(full(s), bytes);
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * kWtStageBytes;
+        const int aw = w0 * p.a_wmul + awo, ah = h0 * p.a_hmul + aho, gw = w0 * p.g_wmul + gwo, gh = h0 * p.g_hmul + gho;
+        for (int j = 0; j < mb; ++j) {
+          tma_load_4d(base + (uint32_t)j * (kWtKP * 128), &tmAh, ci0 + 32 * j, aw, ah, b0, full(s));
+          tma_load_4d(base + kWtPlane + (uint32_t)j * (kWtKP * 128), &tmAl, ci0 + 32 * j, aw, ah, b0, full(s));
+        }
+        for (int j = 0; j < nbk; ++j) {
+          tma_load_4d(base + 2 * kWtPlane + (uint32_t)j * (kWtKP * 128), &tmGh, co0 + 32 * j, gw, gh, b0, full(s));
+          tma_load_4d(base + 3 * kWtPlane + (uint32_t)j * (kWtKP * 128), &tmGl, co0 + 32 * j, gw, gh, b0, full(s));
+        }
+        if (++s == kWtStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[ci][co] += A^T G, both operands MN-major =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const bool leader = elect_one();
+    int s = 0; uint32_t ph = 0; uint32_t acc = 0;
+    for (int q = q_lo; q < q_hi; ++q) {
+      mbar_wait(full(s), ph);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * kWtStageBytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t o = (uint32_t)ks * 1024;
+          const uint64_t dAh = wt_desc(base + o, kWtKP * 128), dAl = wt_desc(base + kWtPlane + o, kWtKP * 128);
+          const uint64_t dGh = wt_desc(base + 2 * kWtPlane + o, kWtKP * 128), dGl = wt_desc(base + 3 * kWtPlane + o, kWtKP * 128);
+          tc_mma_tf32(tmem_base, dAh, dGh, idesc, acc);
+          acc = 1;
+          tc_mma_tf32(tmem_base, dAl, dGh, idesc, 1);
+          tc_mma_tf32(tmem_base, dAh, dGl, idesc, 1);
+        }
+        tc_commit(empty(s));
+      }
+      __syncwarp();
+      if (++s == kWtStages) { s = 0; ph ^= 1; }
+    }
+    if (leader && q_lo < q_hi) tc_commit(acc_full);
+    __syncwarp();
+  } else {
+    // ===== epilogue: TMEM lane = c_in row, columns = c_out =====
+    const int quarter = warp & 3;
+    const bool any = q_lo < q_hi;
+    if (any) { mbar_wait(acc_full, 0); tc_fence_after(); }
+    const int ci = ci0 + quarter * 32 + lane;
+    float* out = p.partial + (((size_t)split * p.n_taps + tap) * p.Ci + ci) * p.Cop + co0;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t r[16];
+      if (any) {
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0u;
+      }
+      if (ci < p.Ci) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          if (co0 + c0 + i < p.Cop)
+            st4(out + c0 + i, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+// ---- operand preparation: hi / lo planes, optionally reflect-padded -------------------------------------------------------
+// dst_hi/dst_lo [B][H+2ph][W+pl+pr][C] from src [B][H][W][C]; reflect padding (edge not repeated), C % 4 == 0
+static __global__ void __launch_bounds__(256) wt_split_pad_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                                           int B, int H, int W, int C, int ph, int pl, int pr) {
+  const int C4 = C >> 2, Wp = W + pl + pr, Hp = H + 2 * ph;
+  const long long n4 = (long long)B * Hp * Wp * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) << 2;
+    long long t = i / C4;
+    const int wp = (int)(t % Wp); t /= Wp;
+    const int hp = (int)(t % Hp), b = (int)(t / Hp);
+    int w = wp - pl, h = hp - ph;
+    w = w < 0 ? -w : w; if (w >= W) w = 2 * (W - 1) - w;
+    h = h < 0 ? -h : h; if (h >= H) h = 2 * (H - 1) - h;
+    const float4 v = ld4(src + (((long long)b * H + h) * W + w) * C + c);
+    const float4 a = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    st4(hi + i * 4, a);
+    st4(lo + i * 4, f4sub(v, a));
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*WtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline WtEncodeFn wt_encode_fn() {
+  static WtEncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
+      fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    return reinterpret_cast<WtEncodeFn>(f);
+  }();
+  return fn;
+}
+
+// One operand: an NHWC fp32 tensor [B][H][W][C] (hi and lo planes of identical shape) read in boxes of
+// {32 channels, bw, bh, bb} with element strides (es_w, es_h) along w / h.
+struct WtOperand { const float* hi; const float* lo; int C, W, H, B; int es_w, es_h; };
+
+inline CUtensorMap wt_tensor_map(const float* base, const WtOperand& o, int bw, int bh, int bb) {
+  if (o.C % 4) fail(AVC_ERR_INVALID, "tensor-core wgrad: channel count %d is not a multiple of 4", o.C);
+  if (bw * o.es_w > 256 || bh * o.es_h > 256 || bb > 256) fail(AVC_ERR_INVALID, "tensor-core wgrad: box too large");
+  CUtensorMap tm;
+  const cuuint64_t dims[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)o.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)o.C * 4, (cuuint64_t)o.W * o.C * 4, (cuuint64_t)o.H * o.W * o.C * 4};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)(bw * o.es_w), (cuuint32_t)(bh * o.es_h), (cuuint32_t)bb};
+  const cuuint32_t es[4] = {1u, (cuuint32_t)o.es_w, (cuuint32_t)o.es_h, 1u};
+  const CUresult r = wt_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d,%d,%d,%d] tensor, box {32,%d,%d,%d}", (int)r, o.B, o.H, o.W, o.C, bw, bh, bb);
+  return tm;
+}
+
+// Chooses the box shape for a base pixel grid [Bn][Hb][Wb]: whole rows when they fit, then several rows, then several images.
+inline void wt_pick_boxes(WtArgs& p, int Wb, int Hb, int Bn) {
+  p.bw = std::min(Wb, kWtKP);
+  p.bh = p.bw == Wb ? std::max(1, std::min(Hb, kWtKP / p.bw)) : 1;
+  p.bb = (p.bw == Wb && p.bh == Hb) ? std::max(1, std::min(Bn, kWtKP / (p.bw * p.bh))) : 1;
+  p.nw = (Wb + p.bw - 1) / p.bw; p.nh = (Hb + p.bh - 1) / p.bh; p.nb = (Bn + p.bb - 1) / p.bb;
+}
+
+inline void wt_init_attributes() {
+  CK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem_bytes()));
+}
+
+// partial must hold wt_splits(...) * n_taps * Ci * Cop floats; returns the number of splits used
+inline int wt_splits(const WtArgs& p, int sm_count) {
+  const int tiles = ((p.Ci + 127) / 128) * ((p.Co + 127) / 128) * p.n_taps;
+  const int n_boxes = p.nw * p.nh * p.nb;
+  int S = std::max(1, std::min(n_boxes, (2 * sm_count + tiles - 1) / tiles));
+  S = std::max(S, (n_boxes + 63) / 64);             // at most 64 boxes (<= 768 MMAs) into one TMEM accumulator
+  const int per = (n_boxes + S - 1) / S;
+  return (n_boxes + per - 1) / per;
+}
+
+inline void launch_wgrad_tc(const WtOperand& A, const WtOperand& G, const WtArgs& p, int S, cudaStream_t st) {
+  const CUtensorMap tAh = wt_tensor_map(A.hi, A, p.bw, p.bh, p.bb), tAl = wt_tensor_map(A.lo, A, p.bw, p.bh, p.bb);
+  const CUtensorMap tGh = wt_tensor_map(G.hi, G, p.bw, p.bh, p.bb), tGl = wt_tensor_map(G.lo, G, p.bw, p.bh, p.bb);
+  dim3 grid((unsigned)S, (unsigned)(((p.Ci + 127) / 128) * ((p.Co + 127) / 128)), (unsigned)p.n_taps);
+  wgrad_tc_kernel<<<grid, kWtThreads, wt_smem_bytes(), st>>>(tAh, tAl, tGh, tGl, p);
+  CK(cudaGetLastError());
+}
+
+}  // namespace avc

@@ -350,17 +350,17 @@ class Engine:
                                                dx.data_ptr(), B, T, c_in, c_out, k, stride, impl, self._stream()))
         return dx
 
-    def conv1d_wgrad(self, x_tl: Tensor, dy_tl: Tensor, k: int, stride: int = 1, bias: bool = True
+    def conv1d_wgrad(self, x_tl: Tensor, dy_tl: Tensor, k: int, stride: int = 1, bias: bool = True, impl: int = 1
                      ) -> Tuple[Tensor, Optional[Tensor]]:
-        """d/dW and d/db of pad_layer + Conv1d (include/avc_b200.h avc_conv1d_wgrad): x [B,T,c_in], dy [B,T_out,c_out]
-        time-major -> dw [c_out,c_in,k], db [c_out]."""
+        """d/dW and d/db of pad_layer + Conv1d (include/avc_b200.h avc_conv1d_wgrad_ex): x [B,T,c_in], dy [B,T_out,c_out]
+        time-major -> dw [c_out,c_in,k], db [c_out].  impl 0 auto, 1 exact fp32 CUDA cores, 2 tcgen05 (TMA, 3xTF32)."""
         B, T, c_in = x_tl.shape
         c_out = dy_tl.shape[2]
         dw = torch.empty(c_out, c_in, k, device=x_tl.device, dtype=torch.float32)
         db = torch.empty(c_out, device=x_tl.device, dtype=torch.float32) if bias else None
-        self._check(self._lib.avc_conv1d_wgrad(self._h, x_tl.contiguous().data_ptr(), dy_tl.contiguous().data_ptr(),
-                                               dw.data_ptr(), db.data_ptr() if bias else None, B, T, c_in, c_out, k,
-                                               stride, self._stream()))
+        self._check(self._lib.avc_conv1d_wgrad_ex(self._h, x_tl.contiguous().data_ptr(), dy_tl.contiguous().data_ptr(),
+                                                  dw.data_ptr(), db.data_ptr() if bias else None, B, T, c_in, c_out, k,
+                                                  stride, int(impl), self._stream()))
         return dw, db
 
     def instnorm_adain_act_fwd(self, y: Tensor, cond: Optional[Tensor], res: Optional[Tensor], up: int, slope: float

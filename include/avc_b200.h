@@ -191,6 +191,11 @@ int avc_conv1d_dgrad(avc_handle* h, const float* dy, const float* w, float* dx,
  * which the attack itself never reads (SURVEY.md §8 "wgrad note"): opt-in, not part of an attack iteration. */
 int avc_conv1d_wgrad(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias,
                      int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride, void* stream);
+/* the same with the kernel chosen explicitly: impl 0 auto (tensor cores from 2048 GEMM rows), 1 exact fp32 on the CUDA
+ * cores, 2 tcgen05: TMA-fed MN-major operands, 3xTF32 (hi/lo planes), fp32 accumulation in TMEM; stated tolerance 2e-5
+ * relative per tensor against fp64 */
+int avc_conv1d_wgrad_ex(avc_handle* h, const float* x, const float* dy, float* dw, float* dbias,
+                        int32_t B, int32_t T, int32_t c_in, int32_t c_out, int32_t k, int32_t stride, int32_t impl, void* stream);
 /* replaces: act(append_cond(InstanceNorm1d(y), cond)) [+ residual] (models.py:414-431).
  * cond [B,2C] (mean | std) or NULL; res [B,T/up,C] or NULL; stats_out [B,C,2] (mean, rstd). */
 int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond, const float* res,

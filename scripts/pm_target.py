@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle.predictive_oracle import pm_make_state_dict
+from attack_vc_b200.synthetic import pm_make_state_dict
 from attack_vc_b200.predictive import PredictiveEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 eng = PredictiveEngine({k: v.cuda() for k, v in pm_make_state_dict(0).items()})

@@ -48,9 +48,12 @@ def test_conv1d_fwd(engine, B, T, ci, co, k, s, impl):
     assert rel_err(y, ref) < 2e-6
 
 
-@pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES + [(16, 512, 128, 128, 5, 1), (8, 256, 80, 128, 8, 1)])
-def test_conv1d_wgrad(engine, B, T, ci, co, k, s):
-    """d/dW, d/db of pad_layer + Conv1d against fp64 autograd (the param.grad the reference's loss.backward() fills)."""
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("B,T,ci,co,k,s", CONV_CASES + [(16, 512, 128, 128, 5, 1), (8, 256, 80, 128, 8, 1), (64, 512, 128, 128, 5, 2)])
+def test_conv1d_wgrad(engine, B, T, ci, co, k, s, impl):
+    """d/dW, d/db of pad_layer + Conv1d against fp64 autograd (the param.grad the reference's loss.backward() fills).
+    impl 1: exact fp32 on the CUDA cores (2e-6); impl 2: tcgen05, TMA-fed MN-major operands, 3xTF32, fp32 accumulation in
+    TMEM (stated tolerance 2e-5, csrc/wgrad_tc.cuh)."""
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + k + 13)
     x = torch.randn(B, T, ci, device="cuda", generator=g)
     w = (torch.randn(co, ci, k, device="cuda", generator=g) / (ci * k) ** 0.5).double().requires_grad_(True)
@@ -58,12 +61,15 @@ def test_conv1d_wgrad(engine, B, T, ci, co, k, s):
     y = ref_conv(x.double(), w, b, s)
     dy = torch.randn(y.shape, device="cuda", generator=g)
     dw_ref, db_ref = torch.autograd.grad(y, (w, b), dy.double())
-    dw, db = engine.conv1d_wgrad(x, dy, k, stride=s)
+    dw, db = engine.conv1d_wgrad(x, dy, k, stride=s, impl=impl)
     assert dw.shape == dw_ref.shape and db.shape == db_ref.shape
-    assert rel_err(dw, dw_ref) < 2e-6
+    assert rel_err(dw, dw_ref) < (2e-6 if impl == 1 else 2e-5)
     assert rel_err(db, db_ref) < 2e-6
-    dw2, _ = engine.conv1d_wgrad(x, dy, k, stride=s, bias=False)
+    dw2, _ = engine.conv1d_wgrad(x, dy, k, stride=s, bias=False, impl=impl)
     assert torch.equal(dw, dw2)          # fixed summation order: bit-reproducible
+    if impl == 2:
+        dw1, _ = engine.conv1d_wgrad(x, dy, k, stride=s, bias=False, impl=1)
+        assert not torch.equal(dw, dw1)  # really the tensor-core kernel, not a silent fallback
 
 
 @pytest.mark.parametrize("impl", [1, 3])
