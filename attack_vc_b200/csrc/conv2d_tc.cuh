@@ -1,0 +1,263 @@
+// conv2d_tc.cuh -- the PredictiveModel's 3x3 convolutions (forward, transposed forward, both dgrads) as TMA-fed tcgen05
+// implicit GEMMs:   Y[pixel][c_out] = sum over (tap, c_in block)  X[src(pixel, tap)][c_in] * W[tap][c_out][c_in]
+//
+//   M = 128 output pixels of one TMA box {32 channels x bw x bh x bb} over the NHWC activation tensor: the conv stride is the
+//       tensor map's element stride, the tap an offset of the box origin, everything outside the tensor is zero-filled by
+//       the TMA unit (the zero padding of the transposed forms; ReflectionPad2d(1) is materialised by the pass that splits
+//       the activations for precision, wgrad_tc.cuh);
+//   N <= 128 output channels, K = 32 input channels per pipeline stage (4 UMMA k-steps of 8), both operands K-major
+//       SWIZZLE_128B exactly as cp.async.bulk.tensor writes them -- no thread touches an operand;
+//   transposed convolutions (ConvTranspose2d forward, Conv2d dgrad) run one launch per output residue class
+//       (oh mod s, ow mod s): a class meets only its own taps, so nothing is multiplied through structural zeros.
+// Precision: 3xTF32 (hi / lo planes of activations and weights).  The tensor core accumulates fp32 with TRUNCATION (about
+// -8e-8 relative per accumulate, scripts/tc_probe.py): left alone over the 864 MMAs of a 256-channel 3x3 conv that is a
+// systematic 4e-5, enough to move PReLU units across their kink and the gradients by 5e-3.  So accumulation is chunked as
+// in conv_tc.cuh: one pipeline stage (12 MMAs) per TMEM buffer, two buffers; the epilogue warps add every finished chunk
+// into fp32 registers with round-to-nearest while the next chunk is being multiplied.
+// Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM allocation), 2-5 epilogue (bias, folded BatchNorm, act' mask,
+// activation, tanh; one pixel row per lane).
+#pragma once
+#include "wgrad_tc.cuh"
+
+namespace avc {
+
+constexpr int kC2Stages = 3;
+constexpr int kC2Plane = 128 * 128;              // one operand plane of a stage: 128 rows x 128 B
+constexpr int kC2StageBytes = 4 * kC2Plane;      // X_hi | X_lo | W_hi | W_lo
+inline size_t c2_smem_bytes() { return (size_t)kC2Stages * kC2StageBytes + 1024 + 128; }
+
+struct C2Args {
+  // base pixel grid of this launch (one residue class) and its boxes
+  int Hb, Wb, B;
+  int bw, bh, bb, nw, nh, nb;
+  int a_wmul, a_hmul;                    // tensor coordinate of base pixel (w, h) for tap t: w * a_wmul + a_woff[t]
+  int n_taps;
+  int tap[9], a_woff[9], a_hoff[9];      // weight tap index and box offsets
+  int Ci, Cop;                           // contraction channels; output channels incl. padding (multiple of 4)
+  // output: y[b][(h * oh_mul + oh_off)][(w * ow_mul + ow_off)][Co]
+  float* y; int Ho, Wo, Co;
+  int oh_mul, oh_off, ow_mul, ow_off;
+  const float* bias; const float* scale; const float* shift;   // v = (acc + bias) * scale + shift   (each may be null)
+  const float* dmask; float mslope;      // v *= dmask > 0 ? 1 : mslope   (tensor shaped like y)
+  const float* slope_ptr; float slope;   // act: v > 0 ? v : v * slope   (slope_ptr overrides: PReLU on the device)
+  int act;                               // 0 none, 1 leaky, 2 leaky then tanh
+};
+
+// K-major SWIZZLE_128B operand: rows of 128 B (32 tf32), 8-row groups SBO = 1024 B apart
+__device__ __forceinline__ uint64_t c2_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+static __global__ void __launch_bounds__(kWtThreads, 1)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                 const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const C2Args p) {
+  extern __shared__ unsigned char c2_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c2_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kC2Stages * kC2StageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);      // after the 10 barriers
+  const uint32_t bar0 = smem_u32(bars);
+  auto full = [&](int s) { return bar0 + 8 * s; };
+  auto empty = [&](int s) { return bar0 + 8 * (kC2Stages + s); };
+  const uint32_t acc_full0 = bar0 + 8 * (2 * kC2Stages), acc_empty0 = acc_full0 + 16;    // two TMEM buffers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;                                        // pixel box
+  const int n0 = (int)blockIdx.y * 128;
+  const int N = min(128, (p.Cop - n0 + 15) & ~15);                 // MMA N: multiple of 16
+  const int wi = q % p.nw, tq = q / p.nw;
+  const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
+  const int rows = p.bw * p.bh * p.bb;
+  const int nkb = (p.Ci + 31) >> 5;
+  const int n_stage = p.n_taps * nkb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kC2Stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full0 + 8 * b, 1); mbar_init(acc_empty0 + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      const uint32_t bytes = (uint32_t)(2 * (rows + 128) * 128);      // the weight box is always 128 rows (rows past c_out are zero-filled)
+      int s = 0; uint32_t ph = 0;
+      for (int t = 0; t < p.n_taps; ++t) {
+        const int aw = w0 * p.a_wmul + p.a_woff[t], ah = h0 * p.a_hmul + p.a_hoff[t], wt = p.tap[t];
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty(s), ph ^ 1);
+          mbar_expect_tx(full(s), bytes);
+          const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
+          tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
+          tma_load_4d(base + kC2Plane, &tmXl, kb * 32, aw, ah, b0, full(s));
+          tma_load_3d(base + 2 * kC2Plane, &tmWh, kb * 32, n0, wt, full(s));
+          tma_load_3d(base + 3 * kC2Plane, &tmWl, kb * 32, n0, wt, full(s));
+          if (++s == kC2Stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const bool leader = elect_one();
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < n_stage; ++it) {
+      const int buf = it & 1;
+      mbar_wait(acc_empty0 + 8 * buf, ((it >> 1) & 1) ^ 1);        // the drain warps have taken this buffer's previous chunk
+      mbar_wait(full(s), ph);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        uint32_t acc = 0;
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
+        const int kleft = p.Ci - (it % nkb) * 32;                   // channels of this K block that exist (the rest is zero-filled)
+        const int ksteps = min(4, (kleft + 7) >> 3);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t o = (uint32_t)ks * 32;                     // 8 tf32 = 32 B along the swizzled 128-byte row
+          const uint64_t dXh = c2_desc(base + o), dXl = c2_desc(base + kC2Plane + o);
+          const uint64_t dWh = c2_desc(base + 2 * kC2Plane + o), dWl = c2_desc(base + 3 * kC2Plane + o);
+          tc_mma_tf32(d_tmem, dXh, dWh, idesc, acc);
+          acc = 1;
+          tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
+          tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+        }
+        tc_commit(empty(s));
+        tc_commit(acc_full0 + 8 * buf);
+      }
+      __syncwarp();
+      if (++s == kC2Stages) { s = 0; ph ^= 1; }
+    }
+  } else {
+    // ===== epilogue: TMEM lane = pixel of the box, columns = output channels =====
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int w = r % p.bw, hh = (r / p.bw) % p.bh, bi = r / (p.bw * p.bh);
+    const bool ok = r < rows && w0 + w < p.Wb && h0 + hh < p.Hb && b0 + bi < p.B;
+    const long long o = ok ? ((((long long)(b0 + bi) * p.Ho + (h0 + hh) * p.oh_mul + p.oh_off) * p.Wo + (w0 + w) * p.ow_mul + p.ow_off) * p.Co + n0) : 0;
+    const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
+    float acc[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int it = 0; it < n_stage; ++it) {
+      const int buf = it & 1;
+      mbar_wait(acc_full0 + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 128);
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        if (c0 < N) {
+          uint32_t v0[16], v1[16];
+          tmem_ld16(t0 + c0, v0);
+          tmem_ld16(t0 + c0 + 16, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(v0[i]); acc[c0 + 16 + i] += __uint_as_float(v1[i]); }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+    }
+    if (ok) {
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 4) {
+        const int c = n0 + c0;
+        if (c0 < N && c < p.Co) {
+          float x[4] = {acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]};
+          if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
+          if (p.scale) {
+            const float4 sc = ld4(p.scale + c), sf = ld4(p.shift + c);
+            x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
+          }
+          if (p.dmask) {
+            const float4 m = ld4(p.dmask + o + c0);
+            x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+            if (p.act == 2) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+            }
+          }
+          st4(p.y + o + c0, make_float4(x[0], x[1], x[2], x[3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+// activation tensor map: [B][H][W][C] NHWC, K-major SWIZZLE_128B boxes {32 channels, bw, bh, bb}
+inline CUtensorMap c2_act_map(const float* base, const WtOperand& o, int bw, int bh, int bb) {
+  if (o.C % 4) fail(AVC_ERR_INVALID, "tensor-core conv: channel count %d is not a multiple of 4", o.C);
+  CUtensorMap tm;
+  const cuuint64_t dims[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)o.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)o.C * 4, (cuuint64_t)o.W * o.C * 4, (cuuint64_t)o.H * o.W * o.C * 4};
+  const cuuint32_t box[4] = {32u, (cuuint32_t)(bw * o.es_w), (cuuint32_t)(bh * o.es_h), (cuuint32_t)bb};
+  const cuuint32_t es[4] = {1u, (cuuint32_t)o.es_w, (cuuint32_t)o.es_h, 1u};
+  const CUresult r = wt_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [%d,%d,%d,%d] activation tensor", (int)r, o.B, o.H, o.W, o.C);
+  return tm;
+}
+// weight tensor map: [9][rows][K] (tap, output channel, contraction channel), boxes {32, 128, 1}
+inline CUtensorMap c2_weight_map(const float* base, int K, int rows) {
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 9};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
+  const cuuint32_t box[3] = {32u, 128u, 1u};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  const CUresult r = wt_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(AVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a [9,%d,%d] weight tensor", (int)r, rows, K);
+  return tm;
+}
+
+// box shape for a base grid [B][Hb][Wb] with up to 128 pixels per box; rows are split evenly so that the last box of an
+// image is not mostly empty
+inline void c2_pick_boxes(C2Args& p) {
+  p.bw = std::min(p.Wb, 128);
+  if (p.bw < p.Wb) { p.bw = (p.Wb + (p.Wb + 127) / 128 - 1) / ((p.Wb + 127) / 128); p.bh = 1; p.bb = 1; }
+  else {
+    const int maxh = std::max(1, 128 / p.bw);
+    if (maxh >= p.Hb) { p.bh = p.Hb; p.bb = std::max(1, std::min(p.B, 128 / (p.bw * p.bh))); }
+    else { const int nh = (p.Hb + maxh - 1) / maxh; p.bh = (p.Hb + nh - 1) / nh; p.bb = 1; }
+  }
+  p.nw = (p.Wb + p.bw - 1) / p.bw; p.nh = (p.Hb + p.bh - 1) / p.bh; p.nb = (p.B + p.bb - 1) / p.bb;
+}
+
+inline void c2_init_attributes() {
+  CK(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes()));
+}
+
+// X: activation planes (es_w / es_h = the gather stride); Wh / Wl: weight planes [9][rows >= Cop][Kp]
+inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, const C2Args& p, cudaStream_t st) {
+  const CUtensorMap tXh = c2_act_map(X.hi, X, p.bw, p.bh, p.bb), tXl = c2_act_map(X.lo, X, p.bw, p.bh, p.bb);
+  const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows), tWl = c2_weight_map(Wl, Kp, w_rows);
+  dim3 grid((unsigned)(p.nw * p.nh * p.nb), (unsigned)((p.Cop + 127) / 128));
+  conv2d_tc_kernel<<<grid, kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
+  CK(cudaGetLastError());
+}
+
+}  // namespace avc

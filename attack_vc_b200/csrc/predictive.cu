@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include "wgrad_tc.cuh"
+#include "conv2d_tc.cuh"
 
 using namespace avc;
 
@@ -42,6 +43,10 @@ struct PmConv {
   float* y; int Ho, Wo, Co, Cop;
   int B, mode, sh, sw;
   float slope; int act;           // 0 none, 1 x>0?x:slope*x, 2 the same then tanh
+  // tensor-core path (conv2d_tc.cuh), taken when the caller provides the operand planes:
+  const float* xh; const float* xl;     // hi / lo planes of x; for PM_REFLECT of the reflect-padded x [B,Hi+2,Wi+2,Ci]
+  const float* wkh; const float* wkl;   // hi / lo planes of the K-major weight image [9][Co][Ci]
+  const float* slope_ptr;               // PReLU slope on the device (overrides slope)
 };
 
 __device__ __forceinline__ int pm_src(int o, int k, int n_in, int s, int mode) {
@@ -645,6 +650,7 @@ int pad4(int c) { return (c + 3) / 4 * 4; }
 
 struct DownW {
   float *w = nullptr, *wt = nullptr;    // [9][ci][cop], transposed [9][co][cip]
+  float *w_h = nullptr, *w_l = nullptr, *wt_h = nullptr, *wt_l = nullptr;   // their hi / lo planes (3xTF32 operands of the tensor-core kernels)
   float *bias = nullptr, *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
   float *escale = nullptr, *eshift = nullptr;   // folded eval BatchNorm (+ conv bias)
   float a = 0.25f;          // host copy for the eval conv epilogue (refreshed from a_dev after training steps)
@@ -652,6 +658,7 @@ struct DownW {
 };
 struct UpW {
   float *w = nullptr, *wt = nullptr, *bias = nullptr;
+  float *w_h = nullptr, *w_l = nullptr, *wt_h = nullptr, *wt_l = nullptr;
 };
 
 }  // namespace
@@ -682,6 +689,7 @@ struct avc_pm_handle {
   float* P = nullptr;
   PmParamDev* pdev = nullptr;
   bool eval_stale = false;       // escale / eshift / host PReLU slopes are older than the parameters
+  bool planes_stale = true;      // the hi / lo weight planes are older than the weight images
   // data-parallel training: sums that couple the ranks go through the caller's all-reduce
   avc_allreduce_fn ar = nullptr;
   void* ar_ctx = nullptr;
@@ -707,7 +715,54 @@ int pm_guarded(avc_pm_handle* h, Fn&& fn) {
   }
 }
 
+bool pm_tc_enabled() {
+  static const bool off = getenv("AVC_PM_NO_TC") != nullptr;
+  return !off;
+}
+bool pm_tc_layer(int ci, int co) { return pm_tc_enabled() && ci % 32 == 0 && co % 32 == 0; }
+// A/B switch per call site (AVC_PM_TC_MASK): 1 forward down, 2 forward up, 4 dgrad of the transposed convs, 8 dgrad of the down convs, 16 wgrad
+bool pm_tc_site(int bit) {
+  static const int mask = getenv("AVC_PM_TC_MASK") ? atoi(getenv("AVC_PM_TC_MASK")) : 31;
+  return (mask & bit) != 0;
+}
+
+// the same convolution on the tensor cores (conv2d_tc.cuh); transposed forms: one launch per output residue class
+void launch_pm_conv_tc(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
+  C2Args a{};
+  a.B = c.B; a.Ci = c.Ci; a.Cop = c.Cop; a.y = c.y; a.Ho = c.Ho; a.Wo = c.Wo; a.Co = c.Co;
+  a.bias = c.bias; a.scale = c.scale; a.shift = c.shift; a.dmask = c.dmask; a.mslope = c.mslope;
+  a.slope_ptr = c.slope_ptr; a.slope = c.slope; a.act = c.act;
+  if (c.mode != PM_TRANSPOSED) {
+    const int pad = c.mode == PM_REFLECT ? 2 : 0;
+    a.Hb = c.Ho; a.Wb = c.Wo; a.a_wmul = c.sw; a.a_hmul = c.sh; a.n_taps = 9;
+    for (int t = 0; t < 9; ++t) { a.tap[t] = t; a.a_woff[t] = t % 3; a.a_hoff[t] = t / 3; }
+    a.oh_mul = a.ow_mul = 1; a.oh_off = a.ow_off = 0;
+    c2_pick_boxes(a);
+    const WtOperand X{c.xh, c.xl, c.Ci, c.Wi + pad, c.Hi + pad, c.B, c.sw, c.sh};
+    launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, st);
+    h->launches++;
+    return;
+  }
+  for (int rh = 0; rh < c.sh; ++rh)
+    for (int rw = 0; rw < c.sw; ++rw) {
+      a.Hb = (c.Ho - rh + c.sh - 1) / c.sh; a.Wb = (c.Wo - rw + c.sw - 1) / c.sw;
+      if (a.Hb <= 0 || a.Wb <= 0) continue;
+      a.a_wmul = a.a_hmul = 1; a.n_taps = 0;
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t % 3;
+        if ((kh - rh) % c.sh || (kw - rw) % c.sw) continue;
+        a.tap[a.n_taps] = t; a.a_hoff[a.n_taps] = (rh - kh) / c.sh; a.a_woff[a.n_taps] = (rw - kw) / c.sw; ++a.n_taps;
+      }
+      a.oh_mul = c.sh; a.oh_off = rh; a.ow_mul = c.sw; a.ow_off = rw;
+      c2_pick_boxes(a);
+      const WtOperand X{c.xh, c.xl, c.Ci, c.Wi, c.Hi, c.B, 1, 1};
+      launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, st);
+      h->launches++;
+    }
+}
+
 void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
+  if (c.xh && c.wkh && pm_tc_layer(c.Ci, c.Cop)) { launch_pm_conv_tc(h, c, st); return; }
   static const bool no_tiled = getenv("AVC_PM_NO_TILED") != nullptr;
   if (!no_tiled && c.Ci % kPmTK == 0 && c.Cop >= 32) {
     const int csh = c.mode == PM_TRANSPOSED ? c.sh : 1, csw = c.mode == PM_TRANSPOSED ? c.sw : 1;
@@ -779,6 +834,41 @@ struct HostSD {
   }
 };
 
+struct Planes { float* h = nullptr; float* l = nullptr; };
+
+// hi / lo planes of an NHWC tensor for the 3xTF32 tensor-core kernels, optionally with ReflectionPad2d(pad) materialised
+Planes pm_split(avc_pm_handle* h, Arena& mem, const float* src, int B, int H, int W, int C, int pad, cudaStream_t st) {
+  Planes p;
+  const size_t n = (size_t)B * (H + 2 * pad) * (W + 2 * pad) * C;
+  p.h = mem.f(n); p.l = mem.f(n);
+  wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, p.h, p.l, B, H, W, C, pad, pad, pad);
+  CK(cudaGetLastError());
+  h->launches++;
+  return p;
+}
+
+// the weight images change with every optimiser step: their planes follow lazily, once per forward pass
+void pm_refresh_weight_planes(avc_pm_handle* h, cudaStream_t st) {
+  if (!h->planes_stale || !pm_tc_enabled()) return;
+  auto one = [&](const float* src, float*& hi, float*& lo, size_t n) {
+    if (!hi) { hi = h->wmem.f(n); lo = h->wmem.f(n); }
+    wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, hi, lo, 1, 1, (int)(n / 4), 4, 0, 0, 0);
+    CK(cudaGetLastError());
+    h->launches++;
+  };
+  for (int l = 1; l < 7; ++l) {
+    DownW& d = h->down[l];
+    const size_t n = (size_t)9 * kDown[l].ci * kDown[l].co;
+    one(d.w, d.w_h, d.w_l, n); one(d.wt, d.wt_h, d.wt_l, n);
+  }
+  for (int i = 0; i < 4; ++i) {
+    UpW& u = h->up[i];
+    const size_t n = (size_t)9 * kUp[i].ci * kUp[i].co;
+    one(u.w, u.w_h, u.w_l, n); one(u.wt, u.wt_h, u.wt_l, n);
+  }
+  h->planes_stale = false;
+}
+
 // activations of one forward pass (kept for the backward)
 struct PmActs {
   int B = 0, H[8]{}, W[8]{};        // down: spatial size after block l is H[l+1], W[l+1]; H[0], W[0] = input
@@ -788,6 +878,8 @@ struct PmActs {
   float* z[7]{};                    // block outputs
   float *scale[7]{}, *shift[7]{}, *mean[7]{}, *rstd[7]{};
   float* u[5]{};                    // up block outputs (u[4] = model output when out == nullptr)
+  // tensor-core path: hi / lo operand planes of every block input (down: reflect-padded [B,H+2,W+2,C]), kept for wgrad
+  Planes zin[7]{}, uin[5]{};
 };
 
 void pm_shapes(PmActs& A, int B, int H, int W) {
@@ -804,6 +896,7 @@ void pm_shapes(PmActs& A, int B, int H, int W) {
 // forward; training: batch statistics, conv outputs kept.  new_stats (optional): [7] pairs of device pointers
 void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* out, bool training,
                 float* const* new_mean, float* const* new_var, cudaStream_t st) {
+  pm_refresh_weight_planes(h, st);
   A.x = x;
   const float* in = x;
   for (int l = 0; l < 7; ++l) {
@@ -815,6 +908,10 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.x = in; c.Hi = A.H[l]; c.Wi = A.W[l]; c.Ci = s.ci;
     c.w = w.w; c.Ho = A.H[l + 1]; c.Wo = A.W[l + 1]; c.Co = s.co; c.Cop = pad4(s.co);
     c.B = A.B; c.mode = PM_REFLECT; c.sh = s.sh; c.sw = s.sw;
+    if (pm_tc_layer(s.ci, s.co) && pm_tc_site(1)) {
+      A.zin[l] = pm_split(h, mem, in, A.B, A.H[l], A.W[l], s.ci, 1, st);
+      c.xh = A.zin[l].h; c.xl = A.zin[l].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
+    }
     if (!training) {
       c.scale = w.escale; c.shift = w.eshift; c.slope = w.a; c.act = 1; c.y = A.z[l];
       launch_pm_conv(h, c, st);
@@ -856,6 +953,10 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.x = in; c.Hi = A.Hu[i]; c.Wi = A.Wu[i]; c.Ci = s.ci;
     c.w = w.w; c.bias = w.bias; c.y = A.u[i]; c.Ho = A.Hu[i + 1]; c.Wo = A.Wu[i + 1]; c.Co = s.co; c.Cop = pad4(s.co);
     c.B = A.B; c.mode = PM_TRANSPOSED; c.sh = 2; c.sw = 2; c.slope = 0.2f; c.act = i == 4 ? 2 : 1;
+    if (pm_tc_layer(s.ci, s.co) && pm_tc_site(2)) {
+      A.uin[i] = pm_split(h, mem, in, A.B, A.Hu[i], A.Wu[i], s.ci, 0, st);
+      c.xh = A.uin[i].h; c.xl = A.uin[i].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
+    }
     launch_pm_conv(h, c, st);
     in = A.u[i];
   }
@@ -866,20 +967,18 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
 template <class Want>
 void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want, float* grad_x, cudaStream_t st) {
   const int B = A.B;
-  auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst) {
+  auto wgrad = [&](const float* Ain, int Ha, int Wa, int Ci, const float* G, int Hg, int Wg, int Co, int Hb, int Wb, int up, int sh, int sw, float* dst,
+                   Planes ap, Planes gp) {
     if (!dst) return;
     static const bool no_tc = getenv("AVC_PM_NO_TC") != nullptr;
-    if (!no_tc && Ci % 4 == 0 && Ci >= 32 && Co % 4 == 0 && Co >= 32) {
+    if (!no_tc && pm_tc_site(16) && Ci % 4 == 0 && Ci >= 32 && Co % 4 == 0 && Co >= 32) {
       // tensor cores: TMA-fed tcgen05 wgrad (wgrad_tc.cuh).  The operands are split hi / lo for 3xTF32 by one elementwise
       // pass each; for a down block that pass also materialises ReflectionPad2d(1), so that a tap is a box offset and the
       // conv stride the tensor map's element stride (for a transposed conv the stride sits on the gradient instead).
       const int pad = up ? 0 : 1, Hap = Ha + 2 * pad, Wap = Wa + 2 * pad;
-      const size_t na = (size_t)B * Hap * Wap * Ci, ng = (size_t)B * Hg * Wg * Co;
-      float* ah = mem.f(na); float* al = mem.f(na); float* gh = mem.f(ng); float* gl = mem.f(ng);
-      wt_split_pad_kernel<<<ew_grid((long long)na / 4, h->sm_count), 256, 0, st>>>(Ain, ah, al, B, Ha, Wa, Ci, pad, pad, pad);
-      CK(cudaGetLastError());
-      wt_split_pad_kernel<<<ew_grid((long long)ng / 4, h->sm_count), 256, 0, st>>>(G, gh, gl, B, Hg, Wg, Co, 0, 0, 0);
-      CK(cudaGetLastError());
+      if (!ap.h) ap = pm_split(h, mem, Ain, B, Ha, Wa, Ci, pad, st);       // normally made by the forward pass / the dgrad of this block
+      if (!gp.h) gp = pm_split(h, mem, G, B, Hg, Wg, Co, 0, st);
+      float *ah = ap.h, *al = ap.l, *gh = gp.h, *gl = gp.l;
       WtArgs p{};
       wt_pick_boxes(p, Wb, Hb, B);
       p.a_wmul = up ? 1 : sw; p.a_hmul = up ? 1 : sh; p.g_wmul = up ? 2 : 1; p.g_hmul = up ? 2 : 1;
@@ -894,7 +993,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       launch_wgrad_tc(Aop, Gop, p, S, st);
       pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(p.partial, S, Ci, Co, p.Cop, up, dst);
       CK(cudaGetLastError());
-      h->launches += 4;
+      h->launches += 2;
       return;
     }
     if (((up && Co == 1 && Ci == 32) || (!up && Ci == 1 && Co == 32))) {
@@ -955,13 +1054,16 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     const float* xin = i > 0 ? A.u[i - 1] : A.z[6];
     const long long npix = (long long)B * A.Hu[i + 1] * A.Wu[i + 1];
     bias_grad(g, npix, s.co, want(p + "bias"));
-    wgrad(xin, A.Hu[i], A.Wu[i], s.ci, g, A.Hu[i + 1], A.Wu[i + 1], s.co, A.Hu[i], A.Wu[i], 1, 2, 2, want(p + "weight"));
+    Planes gp;
+    if (pm_tc_layer(s.ci, s.co)) gp = pm_split(h, mem, g, B, A.Hu[i + 1], A.Wu[i + 1], s.co, 0, st);
+    wgrad(xin, A.Hu[i], A.Wu[i], s.ci, g, A.Hu[i + 1], A.Wu[i + 1], s.co, A.Hu[i], A.Wu[i], 1, 2, 2, want(p + "weight"), A.uin[i], gp);
     // dgrad: gx[ih,iw,ci] = sum_{kh,kw,co} g[2ih+kh, 2iw+kw, co] * W[ci][co][kh][kw]; then through the previous LeakyReLU
     float* gx = mem.f((size_t)B * A.Hu[i] * A.Wu[i] * s.ci);
     PmConv c{};
     c.x = g; c.Hi = A.Hu[i + 1]; c.Wi = A.Wu[i + 1]; c.Ci = s.co;
     c.w = h->up[i].wt; c.y = gx; c.Ho = A.Hu[i]; c.Wo = A.Wu[i]; c.Co = s.ci; c.Cop = pad4(s.ci);
     c.B = B; c.mode = PM_PLAIN; c.sh = 2; c.sw = 2;
+    if (gp.h && pm_tc_site(4)) { c.xh = gp.h; c.xl = gp.l; c.wkh = h->up[i].w_h; c.wkl = h->up[i].w_l; }
     if (i > 0) { c.dmask = A.u[i - 1]; c.mslope = 0.2f; }
     launch_pm_conv(h, c, st);
     g = gx;
@@ -1004,7 +1106,9 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     h->launches += 2;
     bias_grad(gy, npix, s.co, want(p + "1.bias"));
     const float* xin = l > 0 ? A.z[l - 1] : A.x;
-    wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"));
+    Planes gp;
+    if (pm_tc_layer(s.ci, s.co)) gp = pm_split(h, mem, gy, B, A.H[l + 1], A.W[l + 1], s.co, 0, st);
+    wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"), A.zin[l], gp);
     if (l == 0 && !grad_x) break;
     // dgrad on the padded coordinates, then fold the reflect padding back
     const int Hp = A.H[l] + 2, Wp = A.W[l] + 2;
@@ -1014,6 +1118,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     c.x = gy; c.Hi = A.H[l + 1]; c.Wi = A.W[l + 1]; c.Ci = s.co;
     c.w = w.wt; c.y = gxp; c.Ho = Hp; c.Wo = Wp; c.Co = s.ci; c.Cop = cip;
     c.B = B; c.mode = PM_TRANSPOSED; c.sh = s.sh; c.sw = s.sw;
+    if (gp.h && pm_tc_site(8)) { c.xh = gp.h; c.xl = gp.l; c.wkh = w.w_h; c.wkl = w.w_l; }
     launch_pm_conv(h, c, st);
     if (l > 0) {
       float* gx = mem.f((size_t)B * A.H[l] * A.W[l] * s.ci);
@@ -1170,6 +1275,7 @@ int avc_pm_create(avc_pm_handle** out, int device) {
     h->device = device; h->sm_count = p.multiProcessorCount;
     CK(cudaFuncSetAttribute(pm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     wt_init_attributes();
+    c2_init_attributes();
     *out = h.release();
   });
 }
@@ -1496,6 +1602,7 @@ int avc_pm_trainer_step(avc_pm_trainer* t, const float* source, const float* tar
     CK(cudaGetLastError());
     h->launches++;
     h->eval_stale = true;
+    h->planes_stale = true;
     // the step's activations go back to the pool when `mem` dies: the stream must have consumed them
     CK(cudaStreamSynchronize(st));
   });
