@@ -64,11 +64,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   auto empty = [&](int s) { return bar0 + 8 * (kC2Stages + s); };
   const uint32_t acc_full0 = bar0 + 8 * (2 * kC2Stages), acc_empty0 = acc_full0 + 16;    // two TMEM buffers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x;                                        // pixel box
-  const int n0 = (int)blockIdx.y * 128;
-  const int N = min(128, (p.Cop - n0 + 15) & ~15);                 // MMA N: multiple of 16
-  const int wi = q % p.nw, tq = q / p.nw;
-  const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
+  // persistent: this CTA walks work items (pixel box, 128-channel output tile); the stage ring and the accumulator ring run
+  // on across items, so the next item's operands are in flight while this one's epilogue stores (a launch of many small
+  // tiles used to be bound by per-CTA start-up: barrier init, TMEM allocation, a cold pipeline)
+  const int n_nt = (p.Cop + 127) / 128;
+  const int n_work = p.nw * p.nh * p.nb * n_nt;
   const int rows = p.bw * p.bh * p.bb;
   const int nkb = (p.Ci + 31) >> 5;
   const int n_stage = p.n_taps * nkb;
@@ -92,107 +92,124 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     if (elect_one()) {
       const uint32_t bytes = (uint32_t)(2 * (rows + 128) * 128);      // the weight box is always 128 rows (rows past c_out are zero-filled)
       int s = 0; uint32_t ph = 0;
-      for (int t = 0; t < p.n_taps; ++t) {
-        const int aw = w0 * p.a_wmul + p.a_woff[t], ah = h0 * p.a_hmul + p.a_hoff[t], wt = p.tap[t];
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty(s), ph ^ 1);
-          mbar_expect_tx(full(s), bytes);
-          const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
-          tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
-          tma_load_4d(base + kC2Plane, &tmXl, kb * 32, aw, ah, b0, full(s));
-          tma_load_3d(base + 2 * kC2Plane, &tmWh, kb * 32, n0, wt, full(s));
-          tma_load_3d(base + 3 * kC2Plane, &tmWl, kb * 32, n0, wt, full(s));
-          if (++s == kC2Stages) { s = 0; ph ^= 1; }
+      for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+        const int q = wk / n_nt, n0 = (wk % n_nt) * 128;
+        const int wi = q % p.nw, tq = q / p.nw;
+        const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int aw = w0 * p.a_wmul + p.a_woff[t], ah = h0 * p.a_hmul + p.a_hoff[t], wt = p.tap[t];
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty(s), ph ^ 1);
+            mbar_expect_tx(full(s), bytes);
+            const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
+            tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
+            tma_load_4d(base + kC2Plane, &tmXl, kb * 32, aw, ah, b0, full(s));
+            tma_load_3d(base + 2 * kC2Plane, &tmWh, kb * 32, n0, wt, full(s));
+            tma_load_3d(base + 3 * kC2Plane, &tmWl, kb * 32, n0, wt, full(s));
+            if (++s == kC2Stages) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     const bool leader = elect_one();
     int s = 0; uint32_t ph = 0;
-    for (int it = 0; it < n_stage; ++it) {
-      const int buf = it & 1;
-      mbar_wait(acc_empty0 + 8 * buf, ((it >> 1) & 1) ^ 1);        // the drain warps have taken this buffer's previous chunk
-      mbar_wait(full(s), ph);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
-        uint32_t acc = 0;
-        const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
-        const int kleft = p.Ci - (it % nkb) * 32;                   // channels of this K block that exist (the rest is zero-filled)
-        const int ksteps = min(4, (kleft + 7) >> 3);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t o = (uint32_t)ks * 32;                     // 8 tf32 = 32 B along the swizzled 128-byte row
-          const uint64_t dXh = c2_desc(base + o), dXl = c2_desc(base + kC2Plane + o);
-          const uint64_t dWh = c2_desc(base + 2 * kC2Plane + o), dWl = c2_desc(base + 3 * kC2Plane + o);
-          tc_mma_tf32(d_tmem, dXh, dWh, idesc, acc);
-          acc = 1;
-          tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
-          tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+    uint32_t chunk = 0;                                             // chunks issued so far: buffer chunk & 1
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const int n0 = (wk % n_nt) * 128;
+      const int N = min(128, (p.Cop - n0 + 15) & ~15);              // MMA N: multiple of 16
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      for (int it = 0; it < n_stage; ++it, ++chunk) {
+        const uint32_t buf = chunk & 1;
+        mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);    // the drain warps have taken this buffer's previous chunk
+        mbar_wait(full(s), ph);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + buf * 128;
+          uint32_t acc = 0;
+          const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
+          const int kleft = p.Ci - (it % nkb) * 32;                 // channels of this K block that exist (the rest is zero-filled)
+          const int ksteps = min(4, (kleft + 7) >> 3);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t o = (uint32_t)ks * 32;                   // 8 tf32 = 32 B along the swizzled 128-byte row
+            const uint64_t dXh = c2_desc(base + o), dXl = c2_desc(base + kC2Plane + o);
+            const uint64_t dWh = c2_desc(base + 2 * kC2Plane + o), dWl = c2_desc(base + 3 * kC2Plane + o);
+            tc_mma_tf32(d_tmem, dXh, dWh, idesc, acc);
+            acc = 1;
+            tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
+            tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+          }
+          tc_commit(empty(s));
+          tc_commit(acc_full0 + 8 * buf);
         }
-        tc_commit(empty(s));
-        tc_commit(acc_full0 + 8 * buf);
+        __syncwarp();
+        if (++s == kC2Stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == kC2Stages) { s = 0; ph ^= 1; }
     }
   } else {
     // ===== epilogue: TMEM lane = pixel of the box, columns = output channels =====
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int w = r % p.bw, hh = (r / p.bw) % p.bh, bi = r / (p.bw * p.bh);
-    const bool ok = r < rows && w0 + w < p.Wb && h0 + hh < p.Hb && b0 + bi < p.B;
-    const long long o = ok ? ((((long long)(b0 + bi) * p.Ho + (h0 + hh) * p.oh_mul + p.oh_off) * p.Wo + (w0 + w) * p.ow_mul + p.ow_off) * p.Co + n0) : 0;
     const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
-    float acc[128];
+    uint32_t chunk = 0;
+    for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+      const int q = wk / n_nt, n0 = (wk % n_nt) * 128;
+      const int N = min(128, (p.Cop - n0 + 15) & ~15);
+      const int wi = q % p.nw, tq = q / p.nw;
+      const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
+      const bool ok = r < rows && w0 + w < p.Wb && h0 + hh < p.Hb && b0 + bi < p.B;
+      const long long o = ok ? ((((long long)(b0 + bi) * p.Ho + (h0 + hh) * p.oh_mul + p.oh_off) * p.Wo + (w0 + w) * p.ow_mul + p.ow_off) * p.Co + n0) : 0;
+      float acc[128];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 #pragma unroll 1
-    for (int it = 0; it < n_stage; ++it) {
-      const int buf = it & 1;
-      mbar_wait(acc_full0 + 8 * buf, (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 128);
+      for (int it = 0; it < n_stage; ++it, ++chunk) {
+        const uint32_t buf = chunk & 1;
+        mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128;
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        if (c0 < N) {
-          uint32_t v0[16], v1[16];
-          tmem_ld16(t0 + c0, v0);
-          tmem_ld16(t0 + c0 + 16, v1);
-          tmem_ld_wait();
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          if (c0 < N) {
+            uint32_t v0[16], v1[16];
+            tmem_ld16(t0 + c0, v0);
+            tmem_ld16(t0 + c0 + 16, v1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(v0[i]); acc[c0 + 16 + i] += __uint_as_float(v1[i]); }
+            for (int i = 0; i < 16; ++i) { acc[c0 + i] += __uint_as_float(v0[i]); acc[c0 + 16 + i] += __uint_as_float(v1[i]); }
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
-    }
-    if (ok) {
+      if (ok) {
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 4) {
-        const int c = n0 + c0;
-        if (c0 < N && c < p.Co) {
-          float x[4] = {acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]};
-          if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
-          if (p.scale) {
-            const float4 sc = ld4(p.scale + c), sf = ld4(p.shift + c);
-            x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
-          }
-          if (p.dmask) {
-            const float4 m = ld4(p.dmask + o + c0);
-            x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
-          }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
-            if (p.act == 2) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+        for (int c0 = 0; c0 < 128; c0 += 4) {
+          const int c = n0 + c0;
+          if (c0 < N && c < p.Co) {
+            float x[4] = {acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]};
+            if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
+            if (p.scale) {
+              const float4 sc = ld4(p.scale + c), sf = ld4(p.shift + c);
+              x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
             }
+            if (p.dmask) {
+              const float4 m = ld4(p.dmask + o + c0);
+              x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
+            }
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+              if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+              }
+            }
+            st4(p.y + o + c0, make_float4(x[0], x[1], x[2], x[3]));
           }
-          st4(p.y + o + c0, make_float4(x[0], x[1], x[2], x[3]));
         }
       }
     }
@@ -252,11 +269,11 @@ inline void c2_init_attributes() {
 }
 
 // X: activation planes (es_w / es_h = the gather stride); Wh / Wl: weight planes [9][rows >= Cop][Kp]
-inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, const C2Args& p, cudaStream_t st) {
+inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, const C2Args& p, int sm_count, cudaStream_t st) {
   const CUtensorMap tXh = c2_act_map(X.hi, X, p.bw, p.bh, p.bb), tXl = c2_act_map(X.lo, X, p.bw, p.bh, p.bb);
   const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows), tWl = c2_weight_map(Wl, Kp, w_rows);
-  dim3 grid((unsigned)(p.nw * p.nh * p.nb), (unsigned)((p.Cop + 127) / 128));
-  conv2d_tc_kernel<<<grid, kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
+  const int n_work = p.nw * p.nh * p.nb * ((p.Cop + 127) / 128);
+  conv2d_tc_kernel<<<std::min(n_work, sm_count), kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
   CK(cudaGetLastError());
 }
 

@@ -2232,6 +2232,7 @@ int avc_conv1d_wgrad_ex(avc_handle* h, const float* x, const float* dy, float* d
       wt_split_pad_kernel<<<ew_grid(rows * c_out / 4, h->sm_count), 256, 0, st>>>(dy, gh, gl, B, 1, To, c_out, 0, 0, 0);
       CK(cudaGetLastError());
       WtArgs p{};
+      p.Ci = c_in; p.Co = c_out;
       wt_pick_boxes(p, To, 1, B);
       p.a_wmul = stride; p.a_hmul = 1; p.g_wmul = 1; p.g_hmul = 1;
       for (int j = 0; j < k; ++j) { p.a_woff[j] = j; p.a_hoff[j] = 0; p.g_woff[j] = 0; p.g_hoff[j] = 0; }

@@ -346,14 +346,22 @@ __global__ void pm_bn_finalize_kernel(const float* partial, int G, int C, long l
   }
 }
 
-// generic stage 2: out[k][c] = sum_g partial[g][k][c] (fixed order), k < 3
+// fixed-order sum of n floats `stride` apart by ONE WARP: lane j adds elements j, j+32, ... in fp64, then a xor tree.
+// (The stage-2 kernels used to walk up to 1184 partials with one thread: 30-95 us of pure latency each.)
+__device__ __forceinline__ double pm_warp_sum(const float* v, int n, size_t stride) {
+  double s = 0.0;
+  for (int i = threadIdx.x & 31; i < n; i += 32) s += (double)v[(size_t)i * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+// generic stage 2: out[k][c] = sum_g partial[g][k][c] (fixed order), k < 3; one warp per output, launch 3*C warps
 __global__ void pm_sum_partials_kernel(const float* partial, int G, int C, float* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= 3 * C) return;
   const int k = i / C, c = i - k * C;
-  double s = 0.0;
-  for (int g = 0; g < G; ++g) s += partial[((size_t)g * 3 + k) * C + c];
-  out[i] = (float)s;
+  const double s = pm_warp_sum(partial + (size_t)k * C + c, G, (size_t)3 * C);
+  if ((threadIdx.x & 31) == 0) out[i] = (float)s;
 }
 
 // z = prelu(y*scale + shift)
@@ -409,10 +417,9 @@ __global__ void __launch_bounds__(256) pm_loss_bwd_kernel(const float* out, floa
     partial[blockIdx.x] = s;
   }
 }
-__global__ void pm_loss_final_kernel(const float* partial, int G, float inv_n, float* loss) {
-  double s = 0.0;
-  for (int g = 0; g < G; ++g) s += partial[g];
-  *loss = (float)(s * inv_n);
+__global__ void pm_loss_final_kernel(const float* partial, int G, float inv_n, float* loss) {   // one warp
+  const double s = pm_warp_sum(partial, G, 1);
+  if (threadIdx.x == 0) *loss = (float)(s * inv_n);
 }
 
 // sum of all n elements of v: per-CTA partials, then pm_sum_n_kernel
@@ -429,10 +436,9 @@ __global__ void __launch_bounds__(256) pm_sum_all_kernel(const float* v, long lo
     partial[blockIdx.x] = s;
   }
 }
-__global__ void pm_sum_n_kernel(const float* v, int n, float* out) {
-  double s = 0.0;
-  for (int i = 0; i < n; ++i) s += v[i];
-  *out = (float)s;
+__global__ void pm_sum_n_kernel(const float* v, int n, float* out) {   // one warp
+  const double s = pm_warp_sum(v, n, 1);
+  if (threadIdx.x == 0) *out = (float)s;
 }
 
 // fold the gradient w.r.t. the reflect-padded input ([B,H+2,W+2,C]) back onto the input ([B,H,W,C])
@@ -631,13 +637,12 @@ __global__ void __launch_bounds__(256) pm_wgrad_c1_kernel(const PmWgradC1 p) {
   }
 }
 // out[c*9 + tap] = sum_g partial[g][tap][c]   (PyTorch layout of both [C,1,3,3] weights)
-__global__ void pm_wgrad_c1_final_kernel(const float* partial, int G, int C, float* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void pm_wgrad_c1_final_kernel(const float* partial, int G, int C, float* out) {   // one warp per output
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= 9 * C) return;
   const int tap = i / C, c = i % C;
-  double s = 0.0;
-  for (int g = 0; g < G; ++g) s += partial[((size_t)g * 9 + tap) * C + c];
-  out[c * 9 + tap] = (float)s;
+  const double s = pm_warp_sum(partial + (size_t)tap * C + c, G, (size_t)9 * C);
+  if ((threadIdx.x & 31) == 0) out[c * 9 + tap] = (float)s;
 }
 
 // ---- model ---------------------------------------------------------------------------------------------
@@ -739,7 +744,7 @@ void launch_pm_conv_tc(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
     a.oh_mul = a.ow_mul = 1; a.oh_off = a.ow_off = 0;
     c2_pick_boxes(a);
     const WtOperand X{c.xh, c.xl, c.Ci, c.Wi + pad, c.Hi + pad, c.B, c.sw, c.sh};
-    launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, st);
+    launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, h->sm_count, st);
     h->launches++;
     return;
   }
@@ -756,7 +761,7 @@ void launch_pm_conv_tc(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
       a.oh_mul = c.sh; a.oh_off = rh; a.ow_mul = c.sw; a.ow_off = rw;
       c2_pick_boxes(a);
       const WtOperand X{c.xh, c.xl, c.Ci, c.Wi, c.Hi, c.B, 1, 1};
-      launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, st);
+      launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, h->sm_count, st);
       h->launches++;
     }
 }
@@ -799,11 +804,15 @@ void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
   h->launches++;
 }
 
-int reduce_slices(long long N) { return (int)std::max<long long>(1, std::min<long long>(592, N / 256)); }
+// CTAs of a per-channel reduction over N pixels of C channels: about 8 rows per row lane (a CTA has 256 / (C/4) row lanes), at most 4 per SM
+int reduce_slices(long long N, int C) {
+  const int RL = std::max(1, 256 / std::max(1, C / 4));
+  return (int)std::max<long long>(1, std::min<long long>(592, N / (8LL * RL)));
+}
 
 // stage 1 + (for kind != 0) stage 2 of a per-channel reduction; returns G
 int launch_pm_reduce(avc_pm_handle* h, PmReduce r, cudaStream_t st) {
-  const int G = reduce_slices(r.N);
+  const int G = reduce_slices(r.N, r.C);
   const int C4 = r.C / 4, RL = 256 / C4;
   if (r.C % 4 || C4 > 256 || RL < 1) fail(AVC_ERR_INVALID, "predictive reduce: bad channel count %d", r.C);
   const size_t smem = (size_t)RL * 3 * C4 * sizeof(float4);
@@ -922,17 +931,19 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
       launch_pm_conv(h, c, st);
       PmReduce r{};
       r.y = A.y[l]; r.N = npix; r.C = s.co; r.kind = 0;
-      r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
+      r.partial = mem.f((size_t)reduce_slices(npix, s.co) * 3 * s.co);
       int G = launch_pm_reduce(h, r, st);
-      const float* part = r.partial;
+      float* sums = h->world > 1 ? h->comm : mem.f(3 * (size_t)s.co);
+      pm_sum_partials_kernel<<<(3 * s.co * 32 + 255) / 256, 256, 0, st>>>(r.partial, G, s.co, sums);
+      CK(cudaGetLastError());
+      h->launches++;
+      const float* part = sums;
       long long n_stat = npix;
+      G = 1;
       if (h->world > 1) {
         // one BatchNorm over the GLOBAL batch (a single-device batch of world x B windows): sum, sum of squares across ranks
-        pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, G, s.co, h->comm);
-        CK(cudaGetLastError());
-        h->launches++;
         pm_allreduce(h, 3LL * s.co, st);
-        part = h->comm; G = 1; n_stat = npix * h->world;
+        n_stat = npix * h->world;
       }
       pm_bn_finalize_kernel<<<(s.co + 127) / 128, 128, 0, st>>>(part, G, s.co, n_stat, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
                                                                A.rstd[l], w.rmean, w.rvar, new_mean ? new_mean[l] : nullptr, new_var ? new_var[l] : nullptr);
@@ -980,6 +991,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       if (!gp.h) gp = pm_split(h, mem, G, B, Hg, Wg, Co, 0, st);
       float *ah = ap.h, *al = ap.l, *gh = gp.h, *gl = gp.l;
       WtArgs p{};
+      p.Ci = Ci; p.Co = Co;
       wt_pick_boxes(p, Wb, Hb, B);
       p.a_wmul = up ? 1 : sw; p.a_hmul = up ? 1 : sh; p.g_wmul = up ? 2 : 1; p.g_hmul = up ? 2 : 1;
       for (int t = 0; t < 9; ++t) {
@@ -1001,11 +1013,11 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       c.V = up ? Ain : G; c.C = 32; c.S = up ? G : Ain; c.Hs = up ? Hg : Ha; c.Ws = up ? Wg : Wa;
       c.B = B; c.Hb = Hb; c.Wb = Wb; c.up = up; c.sh = sh; c.sw = sw;
       const long long N = (long long)B * Hb * Wb;
-      const int Gc = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 8, N / (32 * 16)));
+      const int Gc = (int)std::max<long long>(1, std::min<long long>((long long)h->sm_count * 4, N / (32 * 16)));
       c.partial = mem.f((size_t)Gc * 9 * 32);
       pm_wgrad_c1_kernel<<<Gc, 256, 0, st>>>(c);
       CK(cudaGetLastError());
-      pm_wgrad_c1_final_kernel<<<(9 * 32 + 127) / 128, 128, 0, st>>>(c.partial, Gc, 32, dst);
+      pm_wgrad_c1_final_kernel<<<(9 * 32 * 32 + 255) / 256, 256, 0, st>>>(c.partial, Gc, 32, dst);
       CK(cudaGetLastError());
       h->launches += 2;
       return;
@@ -1033,16 +1045,16 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       float* part = mem.f(G2);
       pm_sum_all_kernel<<<G2, 256, 0, st>>>(G, N, part);
       CK(cudaGetLastError());
-      pm_sum_n_kernel<<<1, 1, 0, st>>>(part, G2, dst);
+      pm_sum_n_kernel<<<1, 32, 0, st>>>(part, G2, dst);
       CK(cudaGetLastError());
       h->launches += 2;
       return;
     }
     PmReduce r{};
-    r.g = G; r.N = N; r.C = C; r.kind = 2; r.partial = mem.f((size_t)reduce_slices(N) * 3 * C);
+    r.g = G; r.N = N; r.C = C; r.kind = 2; r.partial = mem.f((size_t)reduce_slices(N, C) * 3 * C);
     const int Gs = launch_pm_reduce(h, r, st);
     float* s3 = mem.f(3 * (size_t)C);
-    pm_sum_partials_kernel<<<(3 * C + 127) / 128, 128, 0, st>>>(r.partial, Gs, C, s3);
+    pm_sum_partials_kernel<<<(3 * C * 32 + 255) / 256, 256, 0, st>>>(r.partial, Gs, C, s3);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, s3, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     h->launches += 1;
@@ -1077,10 +1089,10 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     PmReduce r{};
     r.y = A.y[l]; r.g = g; r.N = npix; r.C = s.co; r.kind = 1;
     r.scale = A.scale[l]; r.shift = A.shift[l]; r.mean = A.mean[l]; r.rstd = A.rstd[l]; r.a = w.a_dev;
-    r.partial = mem.f((size_t)reduce_slices(npix) * 3 * s.co);
+    r.partial = mem.f((size_t)reduce_slices(npix, s.co) * 3 * s.co);
     const int Gs = launch_pm_reduce(h, r, st);
     float* sums = mem.f(3 * (size_t)s.co);
-    pm_sum_partials_kernel<<<(3 * s.co + 127) / 128, 128, 0, st>>>(r.partial, Gs, s.co, sums);
+    pm_sum_partials_kernel<<<(3 * s.co * 32 + 255) / 256, 256, 0, st>>>(r.partial, Gs, s.co, sums);
     CK(cudaGetLastError());
     // this rank's sums are its share of the BatchNorm / PReLU parameter gradients; d x needs the sums over the GLOBAL batch
     const float* gsums = sums;
@@ -1095,7 +1107,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     if (float* d = want(p + "2.bias")) CK(cudaMemcpyAsync(d, sums, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (float* d = want(p + "2.weight")) CK(cudaMemcpyAsync(d, sums + s.co, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (float* d = want(p + "3.weight")) {   // PReLU slope: sum over channels of q2 (fixed order)
-      pm_sum_n_kernel<<<1, 1, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
+      pm_sum_n_kernel<<<1, 32, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
       CK(cudaGetLastError());
     }
     float* gy = mem.f((size_t)npix * s.co);
@@ -1464,7 +1476,7 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
     float* lpart = mem.f(LG);
     pm_loss_bwd_kernel<<<LG, 256, 0, st>>>(o, g, n_out, inv_n, lpart);
     CK(cudaGetLastError());
-    pm_loss_final_kernel<<<1, 1, 0, st>>>(lpart, LG, inv_n, loss);
+    pm_loss_final_kernel<<<1, 32, 0, st>>>(lpart, LG, inv_n, loss);
     CK(cudaGetLastError());
     h->launches += 2;
     pm_backward(h, mem, A, g, want, grad_x, st);

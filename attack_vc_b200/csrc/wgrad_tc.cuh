@@ -32,17 +32,20 @@
 
 namespace avc {
 
-constexpr int kWtKP = 32;                        // pixels per pipeline stage
-constexpr int kWtStages = 3;
-constexpr int kWtPlane = 4 * kWtKP * 128;        // one operand plane of a stage: 4 channel blocks x KP rows x 128 B = 16 KB
-constexpr int kWtStageBytes = 4 * kWtPlane;      // A_hi | A_lo | G_hi | G_lo
+// A pipeline stage holds KP pixels of every operand plane: A_hi | A_lo | G_hi | G_lo, each [32-channel block][KP rows][128 B].
+// KP follows the tile: ~64 KB per stage, so a 32 x 64 channel tile (3 blocks) gets 80 pixels per stage and a 128 x 128 tile
+// 32 -- with a fixed 32 the small-channel layers, whose pixel axis is the longest, ran on 3 KB boxes and TMA latency.
+constexpr int kWtRingBytes = 192 * 1024;
+constexpr int kWtStageTarget = 64 * 1024;
+constexpr int kWtMaxStages = 6;
 constexpr int kWtThreads = 192;                  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 constexpr int kWtMaxTaps = 9;
-inline size_t wt_smem_bytes() { return (size_t)kWtStages * kWtStageBytes + 1024 + 128; }
+inline size_t wt_smem_bytes() { return (size_t)kWtRingBytes + 1024 + 128; }
 
 struct WtArgs {
   int nw, nh, nb;                        // boxes along w, h, b of the BASE pixel grid
-  int bw, bh, bb;                        // base pixels per box along each axis (bw*bh*bb <= kWtKP)
+  int bw, bh, bb;                        // base pixels per box along each axis (bw*bh*bb <= KP)
+  int KP, n_stages, mbm, nbm;            // rows per stage (multiple of 8), ring depth, 32-channel blocks of a full tile (c_in, c_out)
   int a_wmul, a_hmul, g_wmul, g_hmul;    // tensor coordinate of base pixel (w, h): w * wmul + woff[tap], h * hmul + hoff[tap]
   int a_woff[kWtMaxTaps], a_hoff[kWtMaxTaps], g_woff[kWtMaxTaps], g_hoff[kWtMaxTaps];
   int n_taps;
@@ -67,12 +70,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl, const WtArgs p) {
   extern __shared__ unsigned char wt_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(wt_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWtStages * kWtStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWtRingBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   const uint32_t bar0 = smem_u32(bars);
+  const int n_stages = p.n_stages;
+  const uint32_t blk = (uint32_t)p.KP * 128;                                    // one 32-channel block of a plane
+  const uint32_t offAl = (uint32_t)p.mbm * blk, offGh = 2 * offAl, offGl = offGh + (uint32_t)p.nbm * blk;
+  const uint32_t stage_bytes = 2 * (uint32_t)(p.mbm + p.nbm) * blk;
   auto full = [&](int s) { return bar0 + 8 * s; };
-  auto empty = [&](int s) { return bar0 + 8 * (kWtStages + s); };
-  const uint32_t acc_full = bar0 + 8 * (2 * kWtStages);
+  auto empty = [&](int s) { return bar0 + 8 * (kWtMaxStages + s); };
+  const uint32_t acc_full = bar0 + 8 * (2 * kWtMaxStages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, tap = blockIdx.z;
   const int n_nt = (p.Co + 127) / 128;
@@ -85,9 +92,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const int rows = p.bw * p.bh * p.bb, ksteps = (rows + 7) >> 3;
 
   // unloaded channel blocks and the K tail of every stage must read as zeros
-  for (int i = threadIdx.x; i < kWtStages * kWtStageBytes / 16; i += kWtThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < (int)(n_stages * stage_bytes / 16); i += kWtThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWtStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < n_stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -113,17 +120,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         const int w0 = wi * p.bw, h0 = hi * p.bh, b0 = bi * p.bb;
         mbar_wait(empty(s), ph ^ 1);
         mbar_expect_tx(full(s), bytes);
-        const uint32_t base = smem_u32(smem) + (uint32_t)s * kWtStageBytes;
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * stage_bytes;
         const int aw = w0 * p.a_wmul + awo, ah = h0 * p.a_hmul + aho, gw = w0 * p.g_wmul + gwo, gh = h0 * p.g_hmul + gho;
         for (int j = 0; j < mb; ++j) {
-          tma_load_4d(base + (uint32_t)j * (kWtKP * 128), &tmAh, ci0 + 32 * j, aw, ah, b0, full(s));
-          tma_load_4d(base + kWtPlane + (uint32_t)j * (kWtKP * 128), &tmAl, ci0 + 32 * j, aw, ah, b0, full(s));
+          tma_load_4d(base + (uint32_t)j * blk, &tmAh, ci0 + 32 * j, aw, ah, b0, full(s));
+          tma_load_4d(base + offAl + (uint32_t)j * blk, &tmAl, ci0 + 32 * j, aw, ah, b0, full(s));
         }
         for (int j = 0; j < nbk; ++j) {
-          tma_load_4d(base + 2 * kWtPlane + (uint32_t)j * (kWtKP * 128), &tmGh, co0 + 32 * j, gw, gh, b0, full(s));
-          tma_load_4d(base + 3 * kWtPlane + (uint32_t)j * (kWtKP * 128), &tmGl, co0 + 32 * j, gw, gh, b0, full(s));
+          tma_load_4d(base + offGh + (uint32_t)j * blk, &tmGh, co0 + 32 * j, gw, gh, b0, full(s));
+          tma_load_4d(base + offGl + (uint32_t)j * blk, &tmGl, co0 + 32 * j, gw, gh, b0, full(s));
         }
-        if (++s == kWtStages) { s = 0; ph ^= 1; }
+        if (++s == n_stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -135,11 +142,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       mbar_wait(full(s), ph);
       tc_fence_after();
       if (leader) {
-        const uint32_t base = smem_u32(smem) + (uint32_t)s * kWtStageBytes;
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * stage_bytes;
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t o = (uint32_t)ks * 1024;
-          const uint64_t dAh = wt_desc(base + o, kWtKP * 128), dAl = wt_desc(base + kWtPlane + o, kWtKP * 128);
-          const uint64_t dGh = wt_desc(base + 2 * kWtPlane + o, kWtKP * 128), dGl = wt_desc(base + 3 * kWtPlane + o, kWtKP * 128);
+          const uint64_t dAh = wt_desc(base + o, blk), dAl = wt_desc(base + offAl + o, blk);
+          const uint64_t dGh = wt_desc(base + offGh + o, blk), dGl = wt_desc(base + offGl + o, blk);
           tc_mma_tf32(tmem_base, dAh, dGh, idesc, acc);
           acc = 1;
           tc_mma_tf32(tmem_base, dAl, dGh, idesc, 1);
@@ -148,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         tc_commit(empty(s));
       }
       __syncwarp();
-      if (++s == kWtStages) { s = 0; ph ^= 1; }
+      if (++s == n_stages) { s = 0; ph ^= 1; }
     }
     if (leader && q_lo < q_hi) tc_commit(acc_full);
     __syncwarp();
@@ -238,12 +245,18 @@ inline CUtensorMap wt_tensor_map(const float* base, const WtOperand& o, int bw, 
   return tm;
 }
 
-// Chooses the box shape for a base pixel grid [Bn][Hb][Wb]: whole rows when they fit, then several rows, then several images.
+// Chooses the stage geometry for c_in x c_out channels and the box shape for a base pixel grid [Bn][Hb][Wb]: whole rows
+// when they fit, then several rows, then several images.  (Set p.Ci / p.Co first.)
 inline void wt_pick_boxes(WtArgs& p, int Wb, int Hb, int Bn) {
-  p.bw = std::min(Wb, kWtKP);
-  p.bh = p.bw == Wb ? std::max(1, std::min(Hb, kWtKP / p.bw)) : 1;
-  p.bb = (p.bw == Wb && p.bh == Hb) ? std::max(1, std::min(Bn, kWtKP / (p.bw * p.bh))) : 1;
+  p.mbm = std::min(4, (p.Ci + 31) / 32); p.nbm = std::min(4, (p.Co + 31) / 32);
+  const int per_row = 2 * (p.mbm + p.nbm) * 128;
+  const int cap = std::max(8, std::min(128, kWtStageTarget / per_row / 8 * 8));       // pixels a stage can hold
+  p.bw = std::min(Wb, cap);
+  p.bh = p.bw == Wb ? std::max(1, std::min(Hb, cap / p.bw)) : 1;
+  p.bb = (p.bw == Wb && p.bh == Hb) ? std::max(1, std::min(Bn, cap / (p.bw * p.bh))) : 1;
   p.nw = (Wb + p.bw - 1) / p.bw; p.nh = (Hb + p.bh - 1) / p.bh; p.nb = (Bn + p.bb - 1) / p.bb;
+  p.KP = (p.bw * p.bh * p.bb + 7) / 8 * 8;                                             // no larger than the boxes need
+  p.n_stages = std::max(2, std::min(kWtMaxStages, kWtRingBytes / (per_row * p.KP)));
 }
 
 inline void wt_init_attributes() {
@@ -255,7 +268,7 @@ inline int wt_splits(const WtArgs& p, int sm_count) {
   const int tiles = ((p.Ci + 127) / 128) * ((p.Co + 127) / 128) * p.n_taps;
   const int n_boxes = p.nw * p.nh * p.nb;
   int S = std::max(1, std::min(n_boxes, (2 * sm_count + tiles - 1) / tiles));
-  S = std::max(S, (n_boxes + 63) / 64);             // at most 64 boxes (<= 768 MMAs) into one TMEM accumulator
+  S = std::max(S, (n_boxes * (p.KP / 8) * 3 + 767) / 768);   // at most 768 MMAs into one TMEM accumulator (truncating adds)
   const int per = (n_boxes + S - 1) / S;
   return (n_boxes + per - 1) / per;
 }
