@@ -38,7 +38,8 @@ __global__ void layout_out_kernel(const float* __restrict__ src, long long s_bs,
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm1d(affine=False) + AdaIN + act (+ skip)            (models.py:66-79, 176, 396, 414-431)
 //   out[b,t,c] = act( ((y - mu_bc) * rstd_bc) * std_bc + mean_bc ) + skip
-// grid (B, C/32); 256 threads = 8 float4 channel lanes (one full 128-byte line per row) x 32 time
+// grid (C/32, B) -- strips of one utterance are neighbours in launch order, so a row's 512-byte line is fetched by
+// co-resident CTAs; 256 threads = 8 float4 channel lanes (one full 128-byte line per row) x 32 time
 // lanes.  The CTA's [T, 32] slice is staged in shared memory while the first pass sums it, so the
 // centred second pass and the normalising third pass never go back to HBM: 8 B/element forward
 // (+4 with a skip), 12 B/element backward, each tensor touched exactly once.  Statistics are
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
   __shared__ float4 red[8][8];
   pdl_enter();
   const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
-  const int b = blockIdx.x, c = blockIdx.y * kNormCh + lane_c * 4;
+  const int b = blockIdx.y, c = blockIdx.x * kNormCh + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
   const bool staged = p.stage && !p.stats_in;
   float4 mu, rstd;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
   __shared__ float4 red[8][8];
   pdl_enter();
   const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
-  const int b = blockIdx.x, c = blockIdx.y * kNormCh + lane_c * 4;
+  const int b = blockIdx.y, c = blockIdx.x * kNormCh + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
   const float* gb = p.g + (long long)b * p.T * p.C + c;
   const float* s = p.stats + ((long long)b * p.C + c) * 2;

@@ -573,7 +573,7 @@ void emit_norm_fwd(Emitter& E, const float* y, int B, int T, int C, const float*
   n.y = y; n.T = T; n.C = C; n.cond = cond; n.cond_bs = cond_bs; n.stats_in = stats_in; n.stats_out = stats_out;
   n.out = outp; n.res = res; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
-  dim3 grid(B, C / kNormCh);
+  dim3 grid(C / kNormCh, B);      // channel strips fastest: the CTAs that share a row's 512-byte line run together (same DRAM page)
   const size_t smem = (size_t)T * kNormCh * sizeof(float);
   n.stage = smem <= (size_t)kNormSmemMax ? 1 : 0;
   const size_t dyn = n.stage ? smem : 0;
@@ -586,7 +586,7 @@ void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stat
   n.g = g; n.y = y; n.stats = stats; n.cond = cond; n.cond_bs = cond_bs; n.gy = gy; n.gcond = gcond; n.gcond_bs = gcond_bs;
   n.T = T; n.C = C; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
-  dim3 grid(B, C / kNormCh);
+  dim3 grid(C / kNormCh, B);      // channel strips fastest: the CTAs that share a row's 512-byte line run together (same DRAM page)
   const size_t smem = (size_t)T * kNormCh * sizeof(float) * 2;
   n.stage = (gy && smem <= (size_t)kNormSmemMax) ? 1 : 0;
   const size_t dyn = n.stage ? smem : 0;

@@ -339,7 +339,8 @@ def pm_arm(args, rank, world, local):
                     "api": ("PredictiveTrainer.step" if vsmask else "PredictiveEngine.train_step") + "(pinned host windows) + loss.cpu() per step"},
             "gpu_launches": launches, "launches_per_step": launches / K,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"],
-                         "traffic": None, "kernel": "whole step (PredictiveModel conv2d / conv-transpose / wgrad kernels" + (" + speaker-encoder tcgen05 convs)" if vsmask else ")"),
+                         "traffic": None, "kernel": "whole step: conv2d_tc_kernel / wgrad_tc_kernel (TMA tensor loads + tcgen05, 3xTF32: the tensor pipe executes 3x the algorithmic FLOPs at the TF32 rate, "
+                                   "i.e. 6 bf16-equivalents per FLOP) + BatchNorm / PReLU / reduction kernels" + (" + speaker-encoder tcgen05 convs" if vsmask else ""),
                          "algorithmic_gflop_per_window": gflop, "peak_source": peaks["source"] + ", bf16 dense burst"},
             "loss": lv}
     if world == 1 and not args.no_cpu_baseline:
