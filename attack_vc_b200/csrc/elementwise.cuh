@@ -46,8 +46,7 @@ __global__ void layout_out_kernel(const float* __restrict__ src, long long s_bs,
 // two-pass (mean, then centred sum of squares; biased variance, eps 1e-5) and every reduction has
 // a fixed order.  Slices longer than the staging capacity fall back to re-reading (L2).
 // ---------------------------------------------------------------------------------------------
-constexpr int kNormCh = 32;
-constexpr int kNormTL = 32;
+constexpr int kNormCh = 32;      // narrowest strip (channels)
 constexpr int kNormSmemMax = 216 * 1024;
 
 struct NormArgs {
@@ -61,15 +60,16 @@ struct NormArgs {
   int stage;                           // 1: the slice fits the dynamic shared memory of this launch
 };
 
-// sum over the 32 time lanes for each of the 8 float4 channel lanes; result broadcast to all threads
-__device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[8], int lane_c) {
+// sum over the 256 / CL time lanes for each of the CL float4 channel lanes; result broadcast to all threads
+template <int CL>
+__device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[CL], int lane_c) {
 #pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
+  for (int o = CL; o <= 16; o <<= 1) {
     v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
     v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
   }
   const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) < 8) red[warp][lane_c] = v;
+  if ((threadIdx.x & 31) < CL) red[warp][lane_c] = v;
   __syncthreads();
   float4 r = red[0][lane_c];
 #pragma unroll
@@ -78,12 +78,16 @@ __device__ __forceinline__ float4 block_reduce_t(float4 v, float4 (*red)[8], int
   return r;
 }
 
+// CL = float4 channel lanes of a CTA (strip of 4*CL channels: 128 / 256 / 512 bytes of every row); the host takes the widest
+// strip whose [T, 4*CL] slice still fits the staging memory with several CTAs per SM and that leaves >= 2 CTAs per SM
+template <int CL>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
-  extern __shared__ __align__(16) float4 ntile[];   // [T][8] when p.stage
-  __shared__ float4 red[8][8];
+  extern __shared__ __align__(16) float4 ntile[];   // [T][CL] when p.stage
+  __shared__ float4 red[8][CL];
+  constexpr int kNormTL = 256 / CL;
   pdl_enter();
-  const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
-  const int b = blockIdx.y, c = blockIdx.x * kNormCh + lane_c * 4;
+  const int lane_c = threadIdx.x % CL, lane_t = threadIdx.x / CL;
+  const int b = blockIdx.y, c = blockIdx.x * (4 * CL) + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
   const bool staged = p.stage && !p.stats_in;
   float4 mu, rstd;
@@ -101,25 +105,25 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
       for (int j = 0; j < 8; ++j) v[j] = ld4(yb + (long long)(t + j * kNormTL) * p.C);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (staged) ntile[(t + j * kNormTL) * 8 + lane_c] = v[j];
+        if (staged) ntile[(t + j * kNormTL) * CL + lane_c] = v[j];
         sum = f4add(sum, v[j]);
       }
     }
     for (; t < p.T; t += kNormTL) {
       const float4 v = ld4(yb + (long long)t * p.C);
-      if (staged) ntile[t * 8 + lane_c] = v;
+      if (staged) ntile[t * CL + lane_c] = v;
       sum = f4add(sum, v);
     }
-    sum = block_reduce_t(sum, red, lane_c);
+    sum = block_reduce_t<CL>(sum, red, lane_c);
     const float invT = 1.f / (float)p.T;
     mu = f4scale(sum, invT);
     float4 sq = f4zero();
     for (int t = lane_t; t < p.T; t += kNormTL) {
-      const float4 v = staged ? ntile[t * 8 + lane_c] : ld4(yb + (long long)t * p.C);
+      const float4 v = staged ? ntile[t * CL + lane_c] : ld4(yb + (long long)t * p.C);
       float dx = v.x - mu.x, dy = v.y - mu.y, dz = v.z - mu.z, dw = v.w - mu.w;
       sq.x = fmaf(dx, dx, sq.x); sq.y = fmaf(dy, dy, sq.y); sq.z = fmaf(dz, dz, sq.z); sq.w = fmaf(dw, dw, sq.w);
     }
-    sq = block_reduce_t(sq, red, lane_c);
+    sq = block_reduce_t<CL>(sq, red, lane_c);
     rstd = make_float4(rsqrtf(sq.x * invT + 1e-5f), rsqrtf(sq.y * invT + 1e-5f),
                        rsqrtf(sq.z * invT + 1e-5f), rsqrtf(sq.w * invT + 1e-5f));
   }
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const NormArgs p) {
   float* ob = p.out + (long long)b * p.T * p.C + c;
 #pragma unroll 4
   for (int t = lane_t; t < p.T; t += kNormTL) {
-    const float4 v = staged ? ntile[t * 8 + lane_c] : ld4(yb + (long long)t * p.C);
+    const float4 v = staged ? ntile[t * CL + lane_c] : ld4(yb + (long long)t * p.C);
     float4 a;
     a.x = fmaf((v.x - mu.x) * rstd.x, cs.x, cm.x);
     a.y = fmaf((v.y - mu.y) * rstd.y, cs.y, cm.y);
@@ -161,12 +165,14 @@ struct NormBwdArgs {
   int stage;            // 1: y and g slices both fit the dynamic shared memory of this launch
 };
 
+template <int CL>
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) {
-  extern __shared__ __align__(16) float4 ntile[];   // [T][8][2] (xhat, ga) when p.stage
-  __shared__ float4 red[8][8];
+  extern __shared__ __align__(16) float4 ntile[];   // [T][CL][2] (xhat, ga) when p.stage
+  __shared__ float4 red[8][CL];
+  constexpr int kNormTL = 256 / CL;
   pdl_enter();
-  const int lane_c = threadIdx.x & 7, lane_t = threadIdx.x >> 3;
-  const int b = blockIdx.y, c = blockIdx.x * kNormCh + lane_c * 4;
+  const int lane_c = threadIdx.x % CL, lane_t = threadIdx.x / CL;
+  const int b = blockIdx.y, c = blockIdx.x * (4 * CL) + lane_c * 4;
   const float* yb = p.y + (long long)b * p.T * p.C + c;
   const float* gb = p.g + (long long)b * p.T * p.C + c;
   const float* s = p.stats + ((long long)b * p.C + c) * 2;
@@ -186,12 +192,12 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
     const float4 xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);
     const float4 a = make_float4(fmaf(xh.x, cs.x, cm.x), fmaf(xh.y, cs.y, cm.y), fmaf(xh.z, cs.z, cm.z), fmaf(xh.w, cs.w, cm.w));
     const float4 ga = dact4mul(g, a, p.slope);
-    if (staged) { ntile[(t * 8 + lane_c) * 2] = xh; ntile[(t * 8 + lane_c) * 2 + 1] = ga; }
+    if (staged) { ntile[(t * CL + lane_c) * 2] = xh; ntile[(t * CL + lane_c) * 2 + 1] = ga; }
     S1 = f4add(S1, ga);
     S2.x = fmaf(ga.x, xh.x, S2.x); S2.y = fmaf(ga.y, xh.y, S2.y); S2.z = fmaf(ga.z, xh.z, S2.z); S2.w = fmaf(ga.w, xh.w, S2.w);
   }
-  S1 = block_reduce_t(S1, red, lane_c);
-  S2 = block_reduce_t(S2, red, lane_c);
+  S1 = block_reduce_t<CL>(S1, red, lane_c);
+  S2 = block_reduce_t<CL>(S2, red, lane_c);
   if (p.gcond && lane_t == 0) {
     st4(p.gcond + (long long)b * p.gcond_bs + c, S1);
     st4(p.gcond + (long long)b * p.gcond_bs + p.C + c, S2);
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(const NormBwdArgs p) 
   for (int t = lane_t; t < p.T; t += kNormTL) {
     float4 xh, ga;
     if (staged) {
-      xh = ntile[(t * 8 + lane_c) * 2]; ga = ntile[(t * 8 + lane_c) * 2 + 1];
+      xh = ntile[(t * CL + lane_c) * 2]; ga = ntile[(t * CL + lane_c) * 2 + 1];
     } else {
       const float4 v = ld4(yb + (long long)t * p.C), g = ld4(gb + (long long)t * p.C);
       xh = make_float4((v.x - mu.x) * rstd.x, (v.y - mu.y) * rstd.y, (v.z - mu.z) * rstd.z, (v.w - mu.w) * rstd.w);

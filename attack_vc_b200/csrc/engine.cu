@@ -263,8 +263,12 @@ void init_kernel_attributes() {
   CK(cudaFuncSetAttribute(conv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(se_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmem));
   CK(cudaFuncSetAttribute(se_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * kTailMaxDense + 1) * kTclMatBytes > (int)kSmemMax - 4096 ? (int)kSmemMax - 4096 : 2 * (2 * kTailMaxDense + 1) * kTclMatBytes));
-  CK(cudaFuncSetAttribute(norm_act_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
-  CK(cudaFuncSetAttribute(norm_act_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
+  CK(cudaFuncSetAttribute(norm_act_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_tc_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -567,17 +571,33 @@ ConvArgs bwd_conv_args(const ConvW& w, const Tens& dy, const Tens& dx, int B, fl
   return a;
 }
 
+// float4 channel lanes per CTA of the norm kernels.  Measured at 2048 x 256 x 128 (profiles/README.md, round 2): strips of
+// 128 B / 256 B / 512 B per row reach 66 % / 61 % / 48 % of the HBM peak forward and 66 % / 37 % / 49 % backward -- the wider
+// strip streams DRAM pages better but its larger staged slice leaves fewer CTAs (loads in flight) per SM, which is what the
+// kernel is bound by.  So: 128-byte strips, the wider instantiations stay for A/B runs (AVC_NORM_CL=16|32).
+int norm_lanes(int sm_count, int B, int T, int C, int planes) {
+  (void)sm_count; (void)B; (void)T; (void)planes;
+  static const int force = getenv("AVC_NORM_CL") ? atoi(getenv("AVC_NORM_CL")) : 0;
+  if ((force == 16 || force == 32) && C % (4 * force) == 0) return force;
+  return 8;
+}
+
 void emit_norm_fwd(Emitter& E, const float* y, int B, int T, int C, const float* cond, int cond_bs,
                    const float* stats_in, float* stats_out, float* outp, ResArgs res, float slope) {
   NormArgs n{};
   n.y = y; n.T = T; n.C = C; n.cond = cond; n.cond_bs = cond_bs; n.stats_in = stats_in; n.stats_out = stats_out;
   n.out = outp; n.res = res; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
-  dim3 grid(C / kNormCh, B);      // channel strips fastest: the CTAs that share a row's 512-byte line run together (same DRAM page)
-  const size_t smem = (size_t)T * kNormCh * sizeof(float);
+  const int cl = norm_lanes(E.h->sm_count, B, T, C, 1);
+  dim3 grid(C / (4 * cl), B);      // channel strips fastest: the CTAs that share a row run together (same DRAM page)
+  const size_t smem = (size_t)T * 4 * cl * sizeof(float);
   n.stage = smem <= (size_t)kNormSmemMax ? 1 : 0;
   const size_t dyn = n.stage ? smem : 0;
-  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid, dyn](cudaStream_t st) { launch_k(norm_act_fwd_kernel, grid, 256, dyn, st, n); });
+  E.push(LK_NORM, 0, 4.0 * B * T * C * ((outp ? 2 : 1) + (res.mode != RES_NONE ? 1.0 / res.rf : 0)), [n, grid, dyn, cl](cudaStream_t st) {
+    if (cl == 32) launch_k(norm_act_fwd_kernel<32>, grid, 256, dyn, st, n);
+    else if (cl == 16) launch_k(norm_act_fwd_kernel<16>, grid, 256, dyn, st, n);
+    else launch_k(norm_act_fwd_kernel<8>, grid, 256, dyn, st, n);
+  });
 }
 
 void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stats, const float* cond, int cond_bs,
@@ -586,11 +606,16 @@ void emit_norm_bwd(Emitter& E, const float* g, const float* y, const float* stat
   n.g = g; n.y = y; n.stats = stats; n.cond = cond; n.cond_bs = cond_bs; n.gy = gy; n.gcond = gcond; n.gcond_bs = gcond_bs;
   n.T = T; n.C = C; n.slope = slope;
   if (C % kNormCh) fail(AVC_ERR_INVALID, "InstanceNorm channels %d not a multiple of %d", C, kNormCh);
-  dim3 grid(C / kNormCh, B);      // channel strips fastest: the CTAs that share a row's 512-byte line run together (same DRAM page)
-  const size_t smem = (size_t)T * kNormCh * sizeof(float) * 2;
+  const int cl = norm_lanes(E.h->sm_count, B, T, C, 2);
+  dim3 grid(C / (4 * cl), B);
+  const size_t smem = (size_t)T * 4 * cl * sizeof(float) * 2;
   n.stage = (gy && smem <= (size_t)kNormSmemMax) ? 1 : 0;
   const size_t dyn = n.stage ? smem : 0;
-  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid, dyn](cudaStream_t st) { launch_k(norm_act_bwd_kernel, grid, 256, dyn, st, n); });
+  E.push(LK_NORM, 0, 4.0 * B * T * C * (gy ? 3 : 2), [n, grid, dyn, cl](cudaStream_t st) {
+    if (cl == 32) launch_k(norm_act_bwd_kernel<32>, grid, 256, dyn, st, n);
+    else if (cl == 16) launch_k(norm_act_bwd_kernel<16>, grid, 256, dyn, st, n);
+    else launch_k(norm_act_bwd_kernel<8>, grid, 256, dyn, st, n);
+  });
 }
 
 // ---- encoder (speaker / content) ------------------------------------------------------------------
