@@ -34,6 +34,7 @@ struct C2Args {
   int n_taps;
   int tap[9], a_woff[9], a_hoff[9];      // weight tap index and box offsets
   int Ci, Cop;                           // contraction channels; output channels incl. padding (multiple of 4)
+  int box_n;                             // rows of the weight box: min(128, Cop rounded up to 32) -- a 32-channel output loads 32 weight rows, not 128
   // output: y[b][(h * oh_mul + oh_off)][(w * ow_mul + ow_off)][Co]
   float* y; int Ho, Wo, Co;
   int oh_mul, oh_off, ow_mul, ow_off;
@@ -41,6 +42,10 @@ struct C2Args {
   const float* dmask; float mslope;      // v *= dmask > 0 ? 1 : mslope   (tensor shaped like y)
   const float* slope_ptr; float slope;   // act: v > 0 ? v : v * slope   (slope_ptr overrides: PReLU on the device)
   int act;                               // 0 none, 1 leaky, 2 leaky then tanh
+  // K split for launches with fewer tiles than SMs (the 2x1 .. 5x4-pixel layers: 16 tiles of 144 dependent stages each):
+  // ksplit CTAs share a tile, each takes a contiguous range of the (tap, K block) stages and stores its raw sums to
+  // part + ks * part_stride (indexed like y); c2_finish_kernel adds them in order and applies the epilogue.
+  int ksplit; float* part; long long part_stride;
 };
 
 // K-major SWIZZLE_128B operand: rows of 128 B (32 tf32), 8-row groups SBO = 1024 B apart
@@ -68,7 +73,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   // on across items, so the next item's operands are in flight while this one's epilogue stores (a launch of many small
   // tiles used to be bound by per-CTA start-up: barrier init, TMEM allocation, a cold pipeline)
   const int n_nt = (p.Cop + 127) / 128;
-  const int n_work = p.nw * p.nh * p.nb * n_nt;
+  const int ksplit = p.ksplit;
+  const int n_work = p.nw * p.nh * p.nb * n_nt * ksplit;
   const int rows = p.bw * p.bh * p.bb;
   const int nkb = (p.Ci + 31) >> 5;
   const int n_stage = p.n_taps * nkb;
@@ -90,24 +96,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      const uint32_t bytes = (uint32_t)(2 * (rows + 128) * 128);      // the weight box is always 128 rows (rows past c_out are zero-filled)
+      const uint32_t bytes = (uint32_t)(2 * (rows + p.box_n) * 128);   // weight rows past c_out inside the box are zero-filled by TMA
       int s = 0; uint32_t ph = 0;
       for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-        const int q = wk / n_nt, n0 = (wk % n_nt) * 128;
+        const int ks = wk % ksplit, wq = wk / ksplit;
+        const int q = wq / n_nt, n0 = (wq % n_nt) * 128;
         const int wi = q % p.nw, tq = q / p.nw;
         const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
-        for (int t = 0; t < p.n_taps; ++t) {
+        const int it_lo = ks * n_stage / ksplit, it_hi = (ks + 1) * n_stage / ksplit;
+        for (int it = it_lo; it < it_hi; ++it) {
+          const int t = it / nkb, kb = it - t * nkb;
           const int aw = w0 * p.a_wmul + p.a_woff[t], ah = h0 * p.a_hmul + p.a_hoff[t], wt = p.tap[t];
-          for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(empty(s), ph ^ 1);
-            mbar_expect_tx(full(s), bytes);
-            const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
-            tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
-            tma_load_4d(base + kC2Plane, &tmXl, kb * 32, aw, ah, b0, full(s));
-            tma_load_3d(base + 2 * kC2Plane, &tmWh, kb * 32, n0, wt, full(s));
-            tma_load_3d(base + 3 * kC2Plane, &tmWl, kb * 32, n0, wt, full(s));
-            if (++s == kC2Stages) { s = 0; ph ^= 1; }
-          }
+          mbar_wait(empty(s), ph ^ 1);
+          mbar_expect_tx(full(s), bytes);
+          const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
+          tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
+          tma_load_4d(base + kC2Plane, &tmXl, kb * 32, aw, ah, b0, full(s));
+          tma_load_3d(base + 2 * kC2Plane, &tmWh, kb * 32, n0, wt, full(s));
+          tma_load_3d(base + 3 * kC2Plane, &tmWl, kb * 32, n0, wt, full(s));
+          if (++s == kC2Stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -117,10 +124,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     int s = 0; uint32_t ph = 0;
     uint32_t chunk = 0;                                             // chunks issued so far: buffer chunk & 1
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-      const int n0 = (wk % n_nt) * 128;
+      const int ks = wk % ksplit, wq = wk / ksplit;
+      const int n0 = (wq % n_nt) * 128;
       const int N = min(128, (p.Cop - n0 + 15) & ~15);              // MMA N: multiple of 16
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-      for (int it = 0; it < n_stage; ++it, ++chunk) {
+      const int it_lo = ks * n_stage / ksplit, it_hi = (ks + 1) * n_stage / ksplit;
+      for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
         mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);    // the drain warps have taken this buffer's previous chunk
         mbar_wait(full(s), ph);
@@ -155,8 +164,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
     uint32_t chunk = 0;
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-      const int q = wk / n_nt, n0 = (wk % n_nt) * 128;
+      const int ks = wk % ksplit, wq = wk / ksplit;
+      const int q = wq / n_nt, n0 = (wq % n_nt) * 128;
       const int N = min(128, (p.Cop - n0 + 15) & ~15);
+      const int it_lo = ks * n_stage / ksplit, it_hi = (ks + 1) * n_stage / ksplit;
       const int wi = q % p.nw, tq = q / p.nw;
       const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
       const bool ok = r < rows && w0 + w < p.Wb && h0 + hh < p.Hb && b0 + bi < p.B;
@@ -165,7 +176,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 128; ++i) acc[i] = 0.f;
 #pragma unroll 1
-      for (int it = 0; it < n_stage; ++it, ++chunk) {
+      for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
         mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
         tc_fence_after();
@@ -185,7 +196,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
-      if (ok) {
+      if (ok && ksplit > 1) {
+        float* dst = p.part + (long long)ks * p.part_stride + o;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 4)
+          if (c0 < N && n0 + c0 < p.Co) st4(dst + c0, make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]));
+      } else if (ok) {
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 4) {
           const int c = n0 + c0;
@@ -222,6 +238,35 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
   }
 }
 
+// y = epilogue(sum over the K splits, in order) for a K-split launch (every residue class of a layer writes the same buffers)
+static __global__ void __launch_bounds__(256) c2_finish_kernel(const C2Args p, long long n4) {
+  const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % p.Co);
+    float4 a = ld4(p.part + i * 4);
+    for (int k = 1; k < p.ksplit; ++k) a = f4add(a, ld4(p.part + (long long)k * p.part_stride + i * 4));
+    float x[4] = {a.x, a.y, a.z, a.w};
+    if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
+    if (p.scale) {
+      const float4 sc = ld4(p.scale + c), sf = ld4(p.shift + c);
+      x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
+    }
+    if (p.dmask) {
+      const float4 m = ld4(p.dmask + i * 4);
+      x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
+    }
+    if (p.act) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+      if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+      }
+    }
+    st4(p.y + i * 4, make_float4(x[0], x[1], x[2], x[3]));
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 // activation tensor map: [B][H][W][C] NHWC, K-major SWIZZLE_128B boxes {32 channels, bw, bh, bb}
 inline CUtensorMap c2_act_map(const float* base, const WtOperand& o, int bw, int bh, int bb) {
@@ -238,11 +283,11 @@ inline CUtensorMap c2_act_map(const float* base, const WtOperand& o, int bw, int
   return tm;
 }
 // weight tensor map: [9][rows][K] (tap, output channel, contraction channel), boxes {32, 128, 1}
-inline CUtensorMap c2_weight_map(const float* base, int K, int rows) {
+inline CUtensorMap c2_weight_map(const float* base, int K, int rows, int box_n) {
   CUtensorMap tm;
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 9};
   const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
-  const cuuint32_t box[3] = {32u, 128u, 1u};
+  const cuuint32_t box[3] = {32u, (cuuint32_t)box_n, 1u};
   const cuuint32_t es[3] = {1u, 1u, 1u};
   const CUresult r = wt_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -269,11 +314,23 @@ inline void c2_init_attributes() {
 }
 
 // X: activation planes (es_w / es_h = the gather stride); Wh / Wl: weight planes [9][rows >= Cop][Kp]
-inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, const C2Args& p, int sm_count, cudaStream_t st) {
+inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, C2Args p, int sm_count, cudaStream_t st) {
+  p.box_n = std::min(128, (p.Cop + 31) / 32 * 32);
   const CUtensorMap tXh = c2_act_map(X.hi, X, p.bw, p.bh, p.bb), tXl = c2_act_map(X.lo, X, p.bw, p.bh, p.bb);
-  const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows), tWl = c2_weight_map(Wl, Kp, w_rows);
-  const int n_work = p.nw * p.nh * p.nb * ((p.Cop + 127) / 128);
+  const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows, p.box_n), tWl = c2_weight_map(Wl, Kp, w_rows, p.box_n);
+  if (p.ksplit < 1) p.ksplit = 1;
+  const int n_work = p.nw * p.nh * p.nb * ((p.Cop + 127) / 128) * p.ksplit;
   conv2d_tc_kernel<<<std::min(n_work, sm_count), kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
+  CK(cudaGetLastError());
+}
+
+inline int c2_tiles(const C2Args& p) { return p.nw * p.nh * p.nb * ((p.Cop + 127) / 128); }
+inline int c2_stages(const C2Args& p) { return p.n_taps * ((p.Ci + 31) / 32); }
+
+inline void launch_c2_finish(const C2Args& p, int sm_count, cudaStream_t st) {
+  const long long n4 = (long long)p.B * p.Ho * p.Wo * p.Co / 4;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)sm_count * 8));
+  c2_finish_kernel<<<grid, 256, 0, st>>>(p, n4);
   CK(cudaGetLastError());
 }
 

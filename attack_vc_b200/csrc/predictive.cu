@@ -695,6 +695,8 @@ struct avc_pm_handle {
   PmParamDev* pdev = nullptr;
   bool eval_stale = false;       // escale / eshift / host PReLU slopes are older than the parameters
   bool planes_stale = true;      // the hi / lo weight planes are older than the weight images
+  float* c2_part = nullptr;      // partial sums of K-split tensor-core convs (grows on demand, lives in wmem)
+  size_t c2_part_floats = 0;
   // data-parallel training: sums that couple the ranks go through the caller's all-reduce
   avc_allreduce_fn ar = nullptr;
   void* ar_ctx = nullptr;
@@ -733,37 +735,60 @@ bool pm_tc_site(int bit) {
 
 // the same convolution on the tensor cores (conv2d_tc.cuh); transposed forms: one launch per output residue class
 void launch_pm_conv_tc(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
-  C2Args a{};
-  a.B = c.B; a.Ci = c.Ci; a.Cop = c.Cop; a.y = c.y; a.Ho = c.Ho; a.Wo = c.Wo; a.Co = c.Co;
-  a.bias = c.bias; a.scale = c.scale; a.shift = c.shift; a.dmask = c.dmask; a.mslope = c.mslope;
-  a.slope_ptr = c.slope_ptr; a.slope = c.slope; a.act = c.act;
+  C2Args base{};
+  base.B = c.B; base.Ci = c.Ci; base.Cop = c.Cop; base.y = c.y; base.Ho = c.Ho; base.Wo = c.Wo; base.Co = c.Co;
+  base.bias = c.bias; base.scale = c.scale; base.shift = c.shift; base.dmask = c.dmask; base.mslope = c.mslope;
+  base.slope_ptr = c.slope_ptr; base.slope = c.slope; base.act = c.act; base.ksplit = 1;
+  struct Cls { C2Args a; WtOperand X; };
+  std::vector<Cls> cls;
   if (c.mode != PM_TRANSPOSED) {
     const int pad = c.mode == PM_REFLECT ? 2 : 0;
+    C2Args a = base;
     a.Hb = c.Ho; a.Wb = c.Wo; a.a_wmul = c.sw; a.a_hmul = c.sh; a.n_taps = 9;
     for (int t = 0; t < 9; ++t) { a.tap[t] = t; a.a_woff[t] = t % 3; a.a_hoff[t] = t / 3; }
     a.oh_mul = a.ow_mul = 1; a.oh_off = a.ow_off = 0;
     c2_pick_boxes(a);
-    const WtOperand X{c.xh, c.xl, c.Ci, c.Wi + pad, c.Hi + pad, c.B, c.sw, c.sh};
-    launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, h->sm_count, st);
-    h->launches++;
-    return;
-  }
-  for (int rh = 0; rh < c.sh; ++rh)
-    for (int rw = 0; rw < c.sw; ++rw) {
-      a.Hb = (c.Ho - rh + c.sh - 1) / c.sh; a.Wb = (c.Wo - rw + c.sw - 1) / c.sw;
-      if (a.Hb <= 0 || a.Wb <= 0) continue;
-      a.a_wmul = a.a_hmul = 1; a.n_taps = 0;
-      for (int t = 0; t < 9; ++t) {
-        const int kh = t / 3, kw = t % 3;
-        if ((kh - rh) % c.sh || (kw - rw) % c.sw) continue;
-        a.tap[a.n_taps] = t; a.a_hoff[a.n_taps] = (rh - kh) / c.sh; a.a_woff[a.n_taps] = (rw - kw) / c.sw; ++a.n_taps;
+    cls.push_back({a, WtOperand{c.xh, c.xl, c.Ci, c.Wi + pad, c.Hi + pad, c.B, c.sw, c.sh}});
+  } else {
+    for (int rh = 0; rh < c.sh; ++rh)
+      for (int rw = 0; rw < c.sw; ++rw) {
+        C2Args a = base;
+        a.Hb = (c.Ho - rh + c.sh - 1) / c.sh; a.Wb = (c.Wo - rw + c.sw - 1) / c.sw;
+        if (a.Hb <= 0 || a.Wb <= 0) continue;
+        a.a_wmul = a.a_hmul = 1; a.n_taps = 0;
+        for (int t = 0; t < 9; ++t) {
+          const int kh = t / 3, kw = t % 3;
+          if ((kh - rh) % c.sh || (kw - rw) % c.sw) continue;
+          a.tap[a.n_taps] = t; a.a_hoff[a.n_taps] = (rh - kh) / c.sh; a.a_woff[a.n_taps] = (rw - kw) / c.sw; ++a.n_taps;
+        }
+        a.oh_mul = c.sh; a.oh_off = rh; a.ow_mul = c.sw; a.ow_off = rw;
+        c2_pick_boxes(a);
+        cls.push_back({a, WtOperand{c.xh, c.xl, c.Ci, c.Wi, c.Hi, c.B, 1, 1}});
       }
-      a.oh_mul = c.sh; a.oh_off = rh; a.ow_mul = c.sw; a.ow_off = rw;
-      c2_pick_boxes(a);
-      const WtOperand X{c.xh, c.xl, c.Ci, c.Wi, c.Hi, c.B, 1, 1};
-      launch_conv2d_tc(X, c.wkh, c.wkl, c.Ci, c.Cop, a, h->sm_count, st);
-      h->launches++;
+  }
+  // a layer with fewer tiles than half the machine (the deep 2x1 .. 5x4-pixel layers) splits the (tap, K block) stages of
+  // every tile over several CTAs; the partial sums meet in c2_finish_kernel (fixed order), which also applies the epilogue
+  int tiles = 0, min_stages = 1 << 30;
+  for (const Cls& q : cls) { tiles += c2_tiles(q.a); min_stages = std::min(min_stages, c2_stages(q.a)); }
+  static const bool no_split = getenv("AVC_PM_NO_KSPLIT") != nullptr;
+  int ksplit = 1;
+  if (!no_split && 2 * tiles <= h->sm_count) ksplit = std::max(1, std::min({8, h->sm_count / std::max(1, tiles), min_stages}));
+  if (ksplit > 1) {
+    const size_t n = (size_t)c.B * c.Ho * c.Wo * c.Co;
+    if (h->c2_part_floats < n * ksplit) {
+      h->c2_part = h->wmem.f(n * ksplit); h->c2_part_floats = n * ksplit;
+      CK(cudaDeviceSynchronize());     // the arena's zero fill runs on the legacy stream: it must not overtake kernels of a non-blocking stream
     }
+    for (Cls& q : cls) { q.a.ksplit = ksplit; q.a.part = h->c2_part; q.a.part_stride = (long long)n; }
+  }
+  for (const Cls& q : cls) {
+    launch_conv2d_tc(q.X, c.wkh, c.wkl, c.Ci, c.Cop, q.a, h->sm_count, st);
+    h->launches++;
+  }
+  if (ksplit > 1) {
+    launch_c2_finish(cls[0].a, h->sm_count, st);
+    h->launches++;
+  }
 }
 
 void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
