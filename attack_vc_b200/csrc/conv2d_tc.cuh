@@ -283,9 +283,9 @@ inline CUtensorMap c2_act_map(const float* base, const WtOperand& o, int bw, int
   return tm;
 }
 // weight tensor map: [9][rows][K] (tap, output channel, contraction channel), boxes {32, 128, 1}
-inline CUtensorMap c2_weight_map(const float* base, int K, int rows, int box_n) {
+inline CUtensorMap c2_weight_map(const float* base, int K, int rows, int box_n, int taps = 9) {
   CUtensorMap tm;
-  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, 9};
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)taps};
   const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
   const cuuint32_t box[3] = {32u, (cuuint32_t)box_n, 1u};
   const cuuint32_t es[3] = {1u, 1u, 1u};
@@ -314,10 +314,10 @@ inline void c2_init_attributes() {
 }
 
 // X: activation planes (es_w / es_h = the gather stride); Wh / Wl: weight planes [9][rows >= Cop][Kp]
-inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, C2Args p, int sm_count, cudaStream_t st) {
+inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, C2Args p, int sm_count, cudaStream_t st, int w_taps = 9) {
   p.box_n = std::min(128, (p.Cop + 31) / 32 * 32);
   const CUtensorMap tXh = c2_act_map(X.hi, X, p.bw, p.bh, p.bb), tXl = c2_act_map(X.lo, X, p.bw, p.bh, p.bb);
-  const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows, p.box_n), tWl = c2_weight_map(Wl, Kp, w_rows, p.box_n);
+  const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows, p.box_n, w_taps), tWl = c2_weight_map(Wl, Kp, w_rows, p.box_n, w_taps);
   if (p.ksplit < 1) p.ksplit = 1;
   const int n_work = p.nw * p.nh * p.nb * ((p.Cop + 127) / 128) * p.ksplit;
   conv2d_tc_kernel<<<std::min(n_work, sm_count), kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);

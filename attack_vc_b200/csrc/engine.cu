@@ -24,6 +24,7 @@
 #include "conv_tc2.cuh"
 #include "conv_wgrad.cuh"
 #include "wgrad_tc.cuh"
+#include "conv2d_tc.cuh"
 #include "elementwise.cuh"
 
 using namespace avc;
@@ -67,6 +68,7 @@ struct ConvW {
   float* bwd = nullptr;   // [k reversed][c_out'][c_in]
   float* bias = nullptr;  // [c_out']
   TcPack tc_fwd[4], tc_bwd[4];  // tcgen05 operand images per tap residue mod stride (conv_tc.cuh); !ok when not eligible
+  float *fwd_h = nullptr, *fwd_l = nullptr;   // hi / lo planes of fwd (1x1 convs only): the K-major weight operand of the TMA-fed dgrad (conv2d_tc.cuh)
   int pl() const { return k / 2; }
   int pr() const { return (k % 2) ? k / 2 : k / 2 - 1; }
 };
@@ -256,6 +258,7 @@ void launch_conv_cfg(ConvArgs a, cudaStream_t st) {
 
 void init_kernel_attributes() {
   wt_init_attributes();
+  c2_init_attributes();
   CK(cudaFuncSetAttribute(conv_simt_kernel<4, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<2, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(conv_simt_kernel<1, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -549,6 +552,12 @@ struct Emitter {
   }
 };
 
+unsigned ew_grid(long long n4, int sm) {
+  long long g = (n4 + 255) / 256;
+  long long cap = (long long)sm * 8;
+  return (unsigned)std::max(1LL, std::min(g, cap));
+}
+
 // forward conv through pad_layer (models.py:10-30)
 ConvArgs fwd_conv_args(const ConvW& w, const Tens& in, const Tens& outT, int B, bool act, float slope) {
   ConvArgs a{};
@@ -785,7 +794,34 @@ void emit_speaker_bwd(Emitter& E, const EncoderW& W, const EncActs& A, const Ten
     Tens gcat = tens(A.gcat, A.T, W.c_cat);
     ConvArgs a = bwd_conv_args(W.in_conv, gout, gcat, A.B, slope);
     a.Mk = A.h0; a.m_bs = (long long)A.T * ch; a.m_rs = ch;
-    E.conv(a, &W.in_conv);
+    // Batched plans: a [B*T, 128] x [128, 1104] GEMM whose nine 128-column passes re-gathered the same A window in
+    // conv_tc_kernel (12 % tensor pipe, the loaders starve a 1-tap pass).  Here the masked gradient is split into hi / lo
+    // planes by one elementwise pass and conv2d_tc_kernel streams both operands with TMA tensor loads (3xTF32).
+    static const bool no_tma = getenv("AVC_NO_TMA_INCONV") != nullptr;
+    const bool contiguous = gout.rs == ch && gout.bs == (long long)A.T * ch;
+    if (!no_tma && W.in_conv.fwd_h && contiguous && ch % 32 == 0 && want_tc(E.h, a, tc_op_conv(W.in_conv, true))) {
+      const size_t n = (size_t)A.B * A.T * ch;
+      float* ph = E.mem->f(n); float* pl = E.mem->f(n);
+      const float* g = gout.p; const float* mk = A.h0;
+      const unsigned sg = ew_grid((long long)n / 4, E.h->sm_count);
+      E.push(LK_CONV, 0, 16.0 * n, [=](cudaStream_t st) {
+        wt_split_mask_kernel<<<sg, 256, 0, st>>>(g, mk, slope, ph, pl, (long long)n / 4);
+        CK(cudaGetLastError());
+      });
+      C2Args c{};
+      c.B = A.B; c.Hb = 1; c.Wb = A.T; c.a_wmul = c.a_hmul = 1; c.n_taps = 1;
+      c.Ci = ch; c.Cop = W.c_cat; c.y = gcat.p; c.Ho = 1; c.Wo = A.T; c.Co = W.c_cat;
+      c.oh_mul = c.ow_mul = 1; c.ksplit = 1;
+      c2_pick_boxes(c);
+      const WtOperand X{ph, pl, ch, A.T, 1, A.B, 1, 1};
+      const float* wh = W.in_conv.fwd_h; const float* wl = W.in_conv.fwd_l;
+      const int rows = W.c_cat, smc = E.h->sm_count;
+      E.push(LK_CONV, 2.0 * A.B * A.T * ch * W.c_cat, 4.0 * A.B * A.T * (ch + W.c_cat), [=](cudaStream_t st) {
+        launch_conv2d_tc(X, wh, wl, ch, rows, c, smc, st, 1);
+      });
+    } else {
+      E.conv(a, &W.in_conv);
+    }
   }
   {   // conv bank: sum of the 8 transposed convs of (gcat_k * act'(cat_k)) + pass-through slice
     ConvArgs a{};
@@ -1156,11 +1192,6 @@ void emit_copy(Emitter& E, float* dst, const float* src, size_t n) {
 void emit_zero(Emitter& E, void* dst, size_t bytes) {
   E.push(LK_COPY, 0, (double)bytes, [=](cudaStream_t st) { CK(cudaMemsetAsync(dst, 0, bytes, st)); });
 }
-unsigned ew_grid(long long n4, int sm) {
-  long long g = (n4 + 255) / 256;
-  long long cap = (long long)sm * 8;
-  return (unsigned)std::max(1LL, std::min(g, cap));
-}
 
 // =================================================================================================
 // weights
@@ -1208,6 +1239,20 @@ ConvW pack_conv(avc_handle* h, HostW& hw, const std::string& key, int c_in, int 
   c.fwd = h->wmem.upload(f);
   c.bwd = h->wmem.upload(r);
   c.bias = h->wmem.upload(bb);
+  if (k == 1 && c_in % 4 == 0 && c_out % 32 == 0) {
+    // 3xTF32 planes of the [c_in][c_out] image: as a [rows = c_in][K = c_out] matrix it is the K-major weight operand of
+    // this conv's dgrad (contract over c_out, produce c_in)
+    std::vector<float> fh(f.size()), fl(f.size());
+    for (size_t i = 0; i < f.size(); ++i) {
+      uint32_t u;
+      memcpy(&u, &f[i], 4);
+      u = (u + 0x1000u) & 0xffffe000u;
+      memcpy(&fh[i], &u, 4);
+      fl[i] = f[i] - fh[i];
+    }
+    c.fwd_h = h->wmem.upload(fh);
+    c.fwd_l = h->wmem.upload(fl);
+  }
   tc_pack_both(h->wmem, c, f, r);     // B operand images for the tcgen05 path
   return c;
 }

@@ -212,6 +212,19 @@ static __global__ void __launch_bounds__(256) wt_split_pad_kernel(const float* _
   }
 }
 
+// hi / lo planes of g * act'(mask): the operand of a dgrad whose input passes backwards through an activation first
+static __global__ void __launch_bounds__(256) wt_split_mask_kernel(const float* __restrict__ g, const float* __restrict__ mask, float slope,
+                                                                   float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = ld4(g + i * 4);
+    const float4 m = ld4(mask + i * 4);
+    v.x *= m.x > 0.f ? 1.f : slope; v.y *= m.y > 0.f ? 1.f : slope; v.z *= m.z > 0.f ? 1.f : slope; v.w *= m.w > 0.f ? 1.f : slope;
+    const float4 a = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    st4(hi + i * 4, a);
+    st4(lo + i * 4, f4sub(v, a));
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------
 typedef CUresult (*WtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
