@@ -14,14 +14,16 @@
 // systematic 4e-5, enough to move PReLU units across their kink and the gradients by 5e-3.  So accumulation is chunked as
 // in conv_tc.cuh: one pipeline stage (12 MMAs) per TMEM buffer, two buffers; the epilogue warps add every finished chunk
 // into fp32 registers with round-to-nearest while the next chunk is being multiplied.
-// Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM allocation), 2-5 epilogue (bias, folded BatchNorm, act' mask,
-// activation, tanh; one pixel row per lane).
+// Warp roles: 0 TMA producer, 1 MMA issuer (+ TMEM allocation), 2-9 epilogue (bias, folded BatchNorm, act' mask,
+// activation, tanh; one pixel row per lane, two warps per TMEM lane quarter with 64 columns each -- with four epilogue warps
+// of 128 columns the chunk adds and the row stores of a tile took longer than its MMAs).
 #pragma once
 #include "wgrad_tc.cuh"
 
 namespace avc {
 
 constexpr int kC2Stages = 3;
+constexpr int kC2Threads = 320;                  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter, 64 columns each)
 constexpr int kC2Plane = 128 * 128;              // one operand plane of a stage: 128 rows x 128 B
 constexpr int kC2StageBytes = 4 * kC2Plane;      // X_hi | X_lo | W_hi | W_lo
 inline size_t c2_smem_bytes() { return (size_t)kC2Stages * kC2StageBytes + 1024 + 128; }
@@ -57,7 +59,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-static __global__ void __launch_bounds__(kWtThreads, 1)
+static __global__ void __launch_bounds__(kC2Threads, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const C2Args p) {
   extern __shared__ unsigned char c2_smem_raw[];
@@ -81,7 +83,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kC2Stages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full0 + 8 * b, 1); mbar_init(acc_empty0 + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full0 + 8 * b, 1); mbar_init(acc_empty0 + 8 * b, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -158,7 +160,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     }
   } else {
     // ===== epilogue: TMEM lane = pixel of the box, columns = output channels =====
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;          // TMEM lanes 32*quarter.., columns 64*half..
+    const int cbase = half * 64;
     const int r = quarter * 32 + lane;
     const int w = r % p.bw, hh = (r / p.bw) % p.bh, bi = r / (p.bw * p.bh);
     const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
@@ -172,18 +175,18 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       const int w0 = wi * p.bw, h0 = (tq % p.nh) * p.bh, b0 = (tq / p.nh) * p.bb;
       const bool ok = r < rows && w0 + w < p.Wb && h0 + hh < p.Hb && b0 + bi < p.B;
       const long long o = ok ? ((((long long)(b0 + bi) * p.Ho + (h0 + hh) * p.oh_mul + p.oh_off) * p.Wo + (w0 + w) * p.ow_mul + p.ow_off) * p.Co + n0) : 0;
-      float acc[128];
+      float acc[64];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
 #pragma unroll 1
       for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
         mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
         tc_fence_after();
-        const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128;
+        const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + (uint32_t)cbase;
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          if (c0 < N) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          if (cbase + c0 < N) {
             uint32_t v0[16], v1[16];
             tmem_ld16(t0 + c0, v0);
             tmem_ld16(t0 + c0 + 16, v1);
@@ -197,15 +200,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
       }
       if (ok && ksplit > 1) {
-        float* dst = p.part + (long long)ks * p.part_stride + o;
+        float* dst = p.part + (long long)ks * p.part_stride + o + cbase;
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 4)
-          if (c0 < N && n0 + c0 < p.Co) st4(dst + c0, make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]));
+        for (int c0 = 0; c0 < 64; c0 += 4)
+          if (cbase + c0 < N && n0 + cbase + c0 < p.Co) st4(dst + c0, make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]));
       } else if (ok) {
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 4) {
-          const int c = n0 + c0;
-          if (c0 < N && c < p.Co) {
+        for (int c0 = 0; c0 < 64; c0 += 4) {
+          const int c = n0 + cbase + c0;
+          if (cbase + c0 < N && c < p.Co) {
             float x[4] = {acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]};
             if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
             if (p.scale) {
@@ -213,7 +216,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
               x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
             }
             if (p.dmask) {
-              const float4 m = ld4(p.dmask + o + c0);
+              const float4 m = ld4(p.dmask + o + cbase + c0);
               x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
             }
             if (p.act) {
@@ -224,7 +227,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
                 for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
               }
             }
-            st4(p.y + o + c0, make_float4(x[0], x[1], x[2], x[3]));
+            st4(p.y + o + cbase + c0, make_float4(x[0], x[1], x[2], x[3]));
           }
         }
       }
@@ -320,7 +323,7 @@ inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* W
   const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows, p.box_n, w_taps), tWl = c2_weight_map(Wl, Kp, w_rows, p.box_n, w_taps);
   if (p.ksplit < 1) p.ksplit = 1;
   const int n_work = p.nw * p.nh * p.nb * ((p.Cop + 127) / 128) * p.ksplit;
-  conv2d_tc_kernel<<<std::min(n_work, sm_count), kWtThreads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
+  conv2d_tc_kernel<<<std::min(n_work, sm_count), kC2Threads, c2_smem_bytes(), st>>>(tXh, tXl, tWh, tWl, p);
   CK(cudaGetLastError());
 }
 

@@ -1,0 +1,6 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_predictive_gpu.py tests/test_vsmask_train_gpu.py tests/test_attacks_gpu.py -q -x 2>&1 | tail -2
+python bench.py --workload pm --steps 20 --warmup 3 --no-cpu-baseline | cut -c1-230
+python bench.py --workload vsmask --steps 20 --warmup 3 --no-cpu-baseline | cut -c1-260
+for c in "emb 128 512" "emb 512 512"; do timeout 200 python scripts/batched_probe.py $c | head -2; done
+timeout 200 python scripts/batched_probe.py emb 128 512 v | sed -n 44,46p
