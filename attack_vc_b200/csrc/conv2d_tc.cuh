@@ -26,7 +26,9 @@ constexpr int kC2Stages = 3;
 constexpr int kC2Threads = 320;                  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter, 64 columns each)
 constexpr int kC2Plane = 128 * 128;              // one operand plane of a stage: 128 rows x 128 B
 constexpr int kC2StageBytes = 4 * kC2Plane;      // X_hi | X_lo | W_hi | W_lo
-inline size_t c2_smem_bytes() { return (size_t)kC2Stages * kC2StageBytes + 1024 + 128; }
+constexpr int kC2ScrPitch = 20;                  // floats per row of an epilogue warp's 32 x 16 transpose slab (16 + 4: float4-aligned rows)
+constexpr int kC2ScrBytes = 8 * 32 * kC2ScrPitch * 4;
+inline size_t c2_smem_bytes() { return (size_t)kC2Stages * kC2StageBytes + kC2ScrBytes + 1024 + 128; }
 
 struct C2Args {
   // base pixel grid of this launch (one residue class) and its boxes
@@ -59,12 +61,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
+// role-level clock stamps of CTA 0 (build with -DAVC_C2_PROFILE): where each role of the pipeline waits
+#ifdef AVC_C2_PROFILE
+#define C2P(...) __VA_ARGS__
+#else
+#define C2P(...)
+#endif
+
 static __global__ void __launch_bounds__(kC2Threads, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                  const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const C2Args p) {
   extern __shared__ unsigned char c2_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c2_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kC2Stages * kC2StageBytes);
+  float* scratch = reinterpret_cast<float*>(smem + (size_t)kC2Stages * kC2StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kC2Stages * kC2StageBytes + kC2ScrBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);      // after the 10 barriers
   const uint32_t bar0 = smem_u32(bars);
   auto full = [&](int s) { return bar0 + 8 * s; };
@@ -100,6 +110,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     if (elect_one()) {
       const uint32_t bytes = (uint32_t)(2 * (rows + p.box_n) * 128);   // weight rows past c_out inside the box are zero-filled by TMA
       int s = 0; uint32_t ph = 0;
+      C2P(long long pw = 0, pt0 = clock64(), pq;)
       for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
         const int ks = wk % ksplit, wq = wk / ksplit;
         const int q = wq / n_nt, n0 = (wq % n_nt) * 128;
@@ -109,7 +120,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         for (int it = it_lo; it < it_hi; ++it) {
           const int t = it / nkb, kb = it - t * nkb;
           const int aw = w0 * p.a_wmul + p.a_woff[t], ah = h0 * p.a_hmul + p.a_hoff[t], wt = p.tap[t];
+          C2P(pq = clock64();)
           mbar_wait(empty(s), ph ^ 1);
+          C2P(pw += clock64() - pq;)
           mbar_expect_tx(full(s), bytes);
           const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
           tma_load_4d(base, &tmXh, kb * 32, aw, ah, b0, full(s));
@@ -119,12 +132,14 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           if (++s == kC2Stages) { s = 0; ph ^= 1; }
         }
       }
+      C2P(if (blockIdx.x == 0) printf("[conv2d_tc cta0] producer: total %lld clk, wait empty %lld (stages/item %d, items %d, N tiles %d)\n", clock64() - pt0, pw, n_stage / ksplit, (n_work + (int)gridDim.x - 1) / (int)gridDim.x, n_nt);)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
     int s = 0; uint32_t ph = 0;
     uint32_t chunk = 0;                                             // chunks issued so far: buffer chunk & 1
+    C2P(long long iw_acc = 0, iw_full = 0, i_iss = 0, it0 = clock64(), iq;)
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const int ks = wk % ksplit, wq = wk / ksplit;
       const int n0 = (wq % n_nt) * 128;
@@ -133,8 +148,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       const int it_lo = ks * n_stage / ksplit, it_hi = (ks + 1) * n_stage / ksplit;
       for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
+        C2P(iq = clock64();)
         mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);    // the drain warps have taken this buffer's previous chunk
+        C2P(iw_acc += clock64() - iq; iq = clock64();)
         mbar_wait(full(s), ph);
+        C2P(iw_full += clock64() - iq; iq = clock64();)
         tc_fence_after();
         if (leader) {
           const uint32_t d_tmem = tmem_base + buf * 128;
@@ -155,9 +173,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           tc_commit(acc_full0 + 8 * buf);
         }
         __syncwarp();
+        C2P(i_iss += clock64() - iq;)
         if (++s == kC2Stages) { s = 0; ph ^= 1; }
       }
     }
+    C2P(if (blockIdx.x == 0 && lane == 0) printf("[conv2d_tc cta0] issuer: total %lld clk, wait acc_empty %lld, wait full %lld, issue %lld\n", clock64() - it0, iw_acc, iw_full, i_iss);)
   } else {
     // ===== epilogue: TMEM lane = pixel of the box, columns = output channels =====
     const int quarter = warp & 3, half = (warp - 2) >> 2;          // TMEM lanes 32*quarter.., columns 64*half..
@@ -166,6 +186,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
     const int w = r % p.bw, hh = (r / p.bw) % p.bh, bi = r / (p.bw * p.bh);
     const float slope = p.slope_ptr ? *p.slope_ptr : p.slope;
     uint32_t chunk = 0;
+    C2P(long long ew = 0, ed = 0, es = 0, et0 = clock64(), eq;)
     for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
       const int ks = wk % ksplit, wq = wk / ksplit;
       const int q = wq / n_nt, n0 = (wq % n_nt) * 128;
@@ -181,7 +202,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
 #pragma unroll 1
       for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
+        C2P(eq = clock64();)
         mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+        C2P(ew += clock64() - eq; eq = clock64();)
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128 + (uint32_t)cbase;
 #pragma unroll
@@ -198,40 +221,68 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+        C2P(ed += clock64() - eq;)
       }
-      if (ok && ksplit > 1) {
-        float* dst = p.part + (long long)ks * p.part_stride + o + cbase;
+      C2P(eq = clock64();)
+      // Output through a per-warp 32 x 16 transpose slab: a lane owns a pixel ROW of the tile, so storing from registers made
+      // every warp store hit 32 different rows with 16 bytes each (6.5 k clk per tile, more than its MMAs --
+      // profiles/r02i_conv2d_tc_roles.txt).  After the transpose a warp store covers 8 rows x 64 contiguous bytes, and the
+      // epilogue arithmetic (per-COLUMN constants, the act' mask) is read along channels too.
+      {
+        float* scr = scratch + (warp - 2) * (32 * kC2ScrPitch);
+        const int o32 = ok ? (int)(o - n0) : -1;                     // element offset of this lane's row (fits: tensors < 2^31 elements)
+        int orow[4];
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 4)
-          if (cbase + c0 < N && n0 + cbase + c0 < p.Co) st4(dst + c0, make_float4(acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]));
-      } else if (ok) {
+        for (int i = 0; i < 4; ++i) orow[i] = __shfl_sync(0xffffffffu, o32, (lane >> 2) + 8 * i);
+        const bool fin = ksplit == 1;
+        float* const dst_base = fin ? p.y : p.part + (long long)ks * p.part_stride;
+        const int cq = (lane & 3) * 4;
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 4) {
-          const int c = n0 + cbase + c0;
-          if (cbase + c0 < N && c < p.Co) {
-            float x[4] = {acc[c0], acc[c0 + 1], acc[c0 + 2], acc[c0 + 3]};
-            if (p.bias) { const float4 bq = ld4(p.bias + c); x[0] += bq.x; x[1] += bq.y; x[2] += bq.z; x[3] += bq.w; }
-            if (p.scale) {
-              const float4 sc = ld4(p.scale + c), sf = ld4(p.shift + c);
-              x[0] = fmaf(x[0], sc.x, sf.x); x[1] = fmaf(x[1], sc.y, sf.y); x[2] = fmaf(x[2], sc.z, sf.z); x[3] = fmaf(x[3], sc.w, sf.w);
+        for (int g = 0; g < 4; ++g) {
+          const int col0 = cbase + 16 * g;
+          if (col0 < N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st4(scr + lane * kC2ScrPitch + j, make_float4(acc[16 * g + j], acc[16 * g + j + 1], acc[16 * g + j + 2], acc[16 * g + j + 3]));
+            __syncwarp();
+            const int c = n0 + col0 + cq;
+            const bool c_ok = col0 + cq < N && c < p.Co;
+            float4 bq = f4zero(), sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = f4zero();
+            if (fin && c_ok) {
+              if (p.bias) bq = ld4(p.bias + c);
+              if (p.scale) { sc = ld4(p.scale + c); sf = ld4(p.shift + c); }
             }
-            if (p.dmask) {
-              const float4 m = ld4(p.dmask + o + cbase + c0);
-              x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
-            }
-            if (p.act) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
-              if (p.act == 2) {
+            for (int i = 0; i < 4; ++i) {
+              if (orow[i] >= 0 && c_ok) {
+                const float4 v = ld4(scr + ((lane >> 2) + 8 * i) * kC2ScrPitch + cq);
+                float x[4] = {v.x, v.y, v.z, v.w};
+                const long long e = (long long)orow[i] + c;
+                if (fin) {
+                  x[0] = fmaf(x[0] + bq.x, sc.x, sf.x); x[1] = fmaf(x[1] + bq.y, sc.y, sf.y);
+                  x[2] = fmaf(x[2] + bq.z, sc.z, sf.z); x[3] = fmaf(x[3] + bq.w, sc.w, sf.w);
+                  if (p.dmask) {
+                    const float4 m = ld4(p.dmask + e);
+                    x[0] *= m.x > 0.f ? 1.f : p.mslope; x[1] *= m.y > 0.f ? 1.f : p.mslope; x[2] *= m.z > 0.f ? 1.f : p.mslope; x[3] *= m.w > 0.f ? 1.f : p.mslope;
+                  }
+                  if (p.act) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+                    for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * slope;
+                    if (p.act == 2) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]);
+                    }
+                  }
+                }
+                st4(dst_base + e, make_float4(x[0], x[1], x[2], x[3]));
               }
             }
-            st4(p.y + o + cbase + c0, make_float4(x[0], x[1], x[2], x[3]));
+            __syncwarp();
           }
         }
       }
+      C2P(es += clock64() - eq;)
     }
+    C2P(if (blockIdx.x == 0 && warp == 2 && lane == 0) printf("[conv2d_tc cta0] epilogue: total %lld clk, wait acc_full %lld, drain %lld, store %lld\n", clock64() - et0, ew, ed, es);)
   }
   tc_fence_before();
   __syncthreads();
