@@ -61,3 +61,26 @@ def test_engine_refuses_cpu(oracle, cpu_model):
     from attack_vc_b200 import AvcError, Engine
     with pytest.raises(AvcError):
         Engine(cpu_model)
+
+
+def test_round2_struct_layouts_match_header():
+    """ctypes mirrors of the structs added for the VSMask trainer: sizes / offsets computed from the C declarations
+    (natural alignment; include/avc_b200.h avc_spk_grad_args, avc_pm_trainer_args)."""
+    from attack_vc_b200 import _lib
+    # avc_spk_grad_args: ptr, i64[3], i32 B, i32 T | ptr, i64[3] | ptr, i64[3], i32 T_tgt (+4 pad) | ptr, i64[3] | ptr | f32 (+4 pad) | f64 | i32 (+4 pad)
+    assert C.sizeof(_lib.SpkGradArgs) == (8 + 24 + 8) + (8 + 24) + (8 + 24 + 8) + (8 + 24) + 8 + 8 + 8 + 8
+    assert _lib.SpkGradArgs.inv_norm.offset % 8 == 0 and _lib.SpkGradArgs.grad_out.offset % 8 == 0
+    # avc_pm_trainer_args: 4 x i32, 7 x f32 (+4 pad), f64
+    assert C.sizeof(_lib.PmTrainerArgs) == 16 + 28 + 4 + 8
+    assert _lib.PmTrainerArgs.inv_norm.offset == 48
+
+
+def test_predictive_engine_refuses_cpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from attack_vc_b200 import AvcError
+    from attack_vc_b200.predictive import PredictiveEngine
+    from attack_vc_b200.synthetic import pm_make_state_dict
+    with pytest.raises(AvcError):
+        PredictiveEngine(pm_make_state_dict(0))
