@@ -126,15 +126,22 @@ __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
     float v[4] = {fmaf(acc[q][0] + bias.x, sc.x, sf.x), fmaf(acc[q][1] + bias.y, sc.y, sf.y),
                   fmaf(acc[q][2] + bias.z, sc.z, sf.z), fmaf(acc[q][3] + bias.w, sc.w, sf.w)};
     const long long o = ((long long)(b * p.Ho + oh) * p.Wo + ow0 + q) * p.Co + co;
+    const bool vec = (p.Co & 3) == 0 && co + 3 < p.Co;      // one 16-byte store per pixel (the scalar form wrote 4 bytes at a 16-byte stride)
+    float m[4] = {1.f, 1.f, 1.f, 1.f};
+    if (p.dmask) {
+      if (vec) { const float4 d = ld4(p.dmask + o); m[0] = d.x; m[1] = d.y; m[2] = d.z; m[3] = d.w; }
+      else for (int j = 0; j < 4; ++j) if (co + j < p.Co) m[j] = p.dmask[o + j];
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (co + j >= p.Co) continue;
       float x = v[j];
-      if (p.dmask) x *= p.dmask[o + j] > 0.f ? 1.f : p.mslope;
+      if (p.dmask) x *= m[j] > 0.f ? 1.f : p.mslope;
       if (p.act) x = x > 0.f ? x : x * p.slope;
       if (p.act == 2) x = tanhf(x);
-      p.y[o + j] = x;
+      v[j] = x;
     }
+    if (vec) st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
+    else for (int j = 0; j < 4; ++j) if (co + j < p.Co) p.y[o + j] = v[j];
   }
 }
 
@@ -599,18 +606,23 @@ __global__ void __launch_bounds__(256) pm_wgrad_c1_kernel(const PmWgradC1 p) {
   float4 acc[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = f4zero();
-  for (long long i = (long long)blockIdx.x * PL + pl; i < N; i += (long long)gridDim.x * PL) {
-    const int wb = (int)(i % p.Wb);
-    const long long r = i / p.Wb;
-    const int hb = (int)(r % p.Hb), b = (int)(r / p.Hb);
-    const float4 v = ld4(p.V + i * p.C + 4 * cl);
+  const unsigned Np = (unsigned)N;                 // < 2^31 pixels: 32-bit index arithmetic (the 64-bit divisions dominated the loop)
+  for (unsigned i = blockIdx.x * PL + pl; i < Np; i += gridDim.x * PL) {
+    const unsigned r = i / (unsigned)p.Wb;
+    const int wb = (int)(i - r * (unsigned)p.Wb);
+    const unsigned bq = r / (unsigned)p.Hb;
+    const int hb = (int)(r - bq * (unsigned)p.Hb), b = (int)bq;
+    const float4 v = ld4(p.V + (long long)i * p.C + 4 * cl);
     const float* sp = p.S + (long long)b * p.Hs * p.Ws;
+    int wsv[3];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) wsv[kw] = p.up ? 2 * wb + kw : pm_src(wb, kw, p.Ws, p.sw, PM_REFLECT);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hs = p.up ? 2 * hb + kh : pm_src(hb, kh, p.Hs, p.sh, PM_REFLECT);
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int ws = p.up ? 2 * wb + kw : pm_src(wb, kw, p.Ws, p.sw, PM_REFLECT);
+        const int ws = wsv[kw];
         const float sv = sp[hs * p.Ws + ws];
         float4& a = acc[kh * 3 + kw];
         a.x = fmaf(v.x, sv, a.x); a.y = fmaf(v.y, sv, a.y); a.z = fmaf(v.z, sv, a.z); a.w = fmaf(v.w, sv, a.w);

@@ -224,3 +224,54 @@ def test_data_parallel_trainer_equals_single_device(engine, pm_sd):
         else:
             assert float((a[k] - b[k]).abs().mean()) <= 0.02 * 2e-3, k
     tr1.close(); tr2.close(); pm1.close(); pm2.close()
+
+
+@pytest.mark.parametrize("B,T,fs", [(2, 80, 30), (3, 100, 0), (2, 100, 60), (1, 100, 10)])
+def test_trainer_crop_edges(cpu_model, engine, pm_sd, B, T, fs):
+    """One optimiser step at the edges of the crop (train_predictive.py:98-102): a window shorter than the prediction (the
+    prediction's columns are cut at the window end), future_steps = 0, a late start that leaves 40 columns, batch 1."""
+    from oracle import vsmask_train_oracle as V
+    from attack_vc_b200.predictive import PredictiveEngine, PredictiveTrainer
+    (s, t), = batches(1, B, seed=100 + T + fs, T=T)
+    ref = V.train_steps(pm_sd, cpu_model.speaker_encoder, [(s, t)], lr=1e-3, future_steps=fs, eps=EPS, record_grads=True)
+    pm = PredictiveEngine({k: v.cuda() for k, v in pm_sd.items()})
+    tr = PredictiveTrainer(pm, engine, batch_size=B, window_size=T, future_steps=fs, epsilon1=EPS[0], epsilon2=EPS[1], epsilon3=EPS[2])
+    loss = float(tr.step(s.cuda(), t.cuda(), lr=1e-3))
+    assert abs(loss - float(ref["losses"][0])) <= RTOL * abs(float(ref["losses"][0]))
+    g = tr.grads()
+    for k in ("up_blocks.4.conv_transpose.0.weight", "up_blocks.1.conv_transpose.0.weight", "down_blocks.2.conv.1.weight", "down_blocks.5.conv.2.weight"):
+        assert rel(g[k], ref["grads"][0][k]) < 3e-3, k      # B <= 3: a single PReLU / ReLU unit on its kink is a visible share of the batch
+    tr.close(); pm.close()
+
+
+def test_speaker_grad_session_strided_views(cpu_model, engine):
+    """The session's tensors may be arbitrary strided views (the CLI hands the attacks transposed [1,80,T] views of [T,80]
+    arrays, attack.py:49-50): here the gradient is written into a time-major buffer through its transposed view."""
+    from attack_vc_b200 import _lib
+    from attack_vc_b200.engine import _strides3
+    B, T = 2, 72
+    g = torch.Generator().manual_seed(5)
+    s, t = torch.randn(B, 80, T, generator=g), torch.randn(B, 80, T, generator=g)
+    p = (s + 0.05 * torch.randn(B, 80, T, generator=g)).requires_grad_(True)
+    e_p = cpu_model.speaker_encoder(p)
+    loss = torch.nn.functional.mse_loss(e_p, cpu_model.speaker_encoder(t)) - 0.5 * torch.nn.functional.mse_loss(e_p, cpu_model.speaker_encoder(s))
+    loss.backward()
+    dev = engine.device
+    pt = p.detach().transpose(1, 2).contiguous().cuda().transpose(1, 2)      # [B,80,T] view of a [B,T,80] buffer
+    sc, tc = s.cuda(), t.cuda()
+    gt = torch.zeros(B, T, 80, device=dev).transpose(1, 2)
+    lo = torch.zeros(1, device=dev)
+    a = _lib.SpkGradArgs()
+    a.perturbed, a.p_stride = pt.data_ptr(), _strides3(pt)
+    a.source, a.s_stride = sc.data_ptr(), _strides3(sc)
+    a.target, a.t_stride = tc.data_ptr(), _strides3(tc)
+    a.grad_out, a.g_stride = gt.data_ptr(), _strides3(gt)
+    a.loss_out = lo.data_ptr()
+    a.B, a.T, a.T_tgt, a.lam, a.inv_norm, a.use_graph = B, T, T, 0.5, 0.0, 1
+    sp = C.c_void_p()
+    torch.cuda.synchronize()
+    engine._check(engine._lib.avc_spk_grad_begin(engine._h, C.byref(a), engine._stream(), C.byref(sp)))
+    engine._check(engine._lib.avc_spk_grad_step(sp, engine._stream()))
+    engine._check(engine._lib.avc_attack_end(sp, engine._stream()))
+    assert abs(float(lo) - float(loss)) <= 1e-4 * abs(float(loss))
+    assert rel(gt, p.grad) < RTOL
