@@ -77,22 +77,33 @@ def main():
         l2 = tr_dp.step(s_[rank * Bl:(rank + 1) * Bl].contiguous(), t_[rank * Bl:(rank + 1) * Bl].contiguous()).clone()
         dist.all_reduce(l2)
         lerr = max(lerr, abs(float(l2) - float(l1)) / abs(float(l1)))
-    g1, g2 = tr_one.grads(), tr_dp.grads()
-    # per-tensor relative error; a PReLU slope's gradient is ONE number, a cancelling sum over a whole layer whose units can sit
-    # on their kink (the batch statistics of the two runs are summed in different orders): 2e-2 there, 1e-3 everywhere else
-    errs = {k: float((g2[k] - g1[k]).norm() / g1[k].norm().clamp_min(1e-30)) for k in g1 if not k.endswith("conv.1.bias")}
-    worst = max(errs, key=errs.get)
-    gerr = max(v for k, v in errs.items() if g1[k].numel() > 1)
-    gerr1 = max(v for k, v in errs.items() if g1[k].numel() == 1)
     a, b = tr_one.state_dict(), tr_dp.state_dict()
     serr = max(float((b[k] - a[k]).norm() / a[k].norm().clamp_min(1e-30)) for k in a if "running" in k)
     perr = max(float((b[k] - a[k]).abs().mean()) for k in a if "running" not in k)
-    good = lerr < 1e-4 and gerr < 1e-3 and gerr1 < 2e-2 and serr < 1e-5 and perr < 0.05 * steps * 1e-3
+    tr_one.close(); tr_dp.close(); pm_one.close(); pm_dp.close()
+    # Gradients of ONE step on three different batches, per tensor.  The two runs sum the BatchNorm statistics in different
+    # orders (one device vs partial sums per rank + all-reduce): they differ by ~1e-7 before the activations, and a PReLU /
+    # LeakyReLU unit within that distance of zero takes the other branch in one of them.  With 12 windows a single such unit
+    # in a deep layer moves EVERY upstream gradient by 1e-3 .. 1e-2 (seen with seed 31: 53 % of the tensors beyond 1e-3, one
+    # device against the CPU oracle 5e-6 on one side of the kink).  A missing or wrong coupling is O(1) on every batch.  So:
+    # at least two of the three batches with every tensor within 1e-3, none beyond 5e-2.
+    clean, gworst = 0, 0.0
+    for seed in (41, 42, 43):
+        gg = torch.Generator().manual_seed(seed)
+        s_ = 0.5 * torch.randn(Bl * world, 1, 80, 100, generator=gg).cuda(); t_ = 0.5 * torch.randn(Bl * world, 1, 80, 100, generator=gg).cuda()
+        pm_a = PredictiveEngine(sd); tr_a = PredictiveTrainer(pm_a, eng, batch_size=Bl * world, **eps)
+        pm_b = PredictiveEngine(sd); pm_b.set_process_group(None, world)
+        tr_b = PredictiveTrainer(pm_b, eng, batch_size=Bl, inv_norm=1.0 / (Bl * world * 128), **eps)
+        tr_a.step(s_, t_); tr_b.step(s_[rank * Bl:(rank + 1) * Bl].contiguous(), t_[rank * Bl:(rank + 1) * Bl].contiguous())
+        g1, g2 = tr_a.grads(), tr_b.grads()
+        errs = [float((g2[k] - g1[k]).norm() / g1[k].norm().clamp_min(1e-30)) for k in g1 if not k.endswith("conv.1.bias")]
+        clean += int(max(errs) < 1e-3); gworst = max(gworst, max(errs))
+        tr_a.close(); tr_b.close(); pm_a.close(); pm_b.close()
+    good = lerr < 1e-4 and clean >= 2 and gworst < 5e-2 and serr < 1e-5 and perr < 0.05 * steps * 1e-3
     ok &= good
     if rank == 0:
-        print(f"data-parallel VSMask trainer, {world} x {Bl} windows: loss rel err {lerr:.2e}, worst gradient rel err {gerr:.2e} (PReLU slopes {gerr1:.2e}; worst: {worst}), "
+        print(f"data-parallel VSMask trainer, {world} x {Bl} windows: loss rel err {lerr:.2e}, batches with every gradient within 1e-3: {clean}/3 (worst tensor {gworst:.2e}), "
               f"running-statistics rel err {serr:.2e}, mean |param - single GPU| {perr:.2e} -> {'PASS' if good else 'FAIL'}")
-    tr_one.close(); tr_dp.close(); pm_one.close(); pm_dp.close()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
