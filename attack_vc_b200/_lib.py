@@ -64,6 +64,11 @@ class PmTrainerArgs(C.Structure):
     ]
 
 
+class AudioDesc(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32), ("win_length", C.c_int32),
+                ("n_mels", C.c_int32), ("preemph", C.c_float), ("ref_db", C.c_float), ("max_db", C.c_float)]
+
+
 # int (*avc_allreduce_fn)(void* ctx, float* comm, int64_t n_floats, void* stream)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
@@ -92,6 +97,8 @@ EXPORTS = [
     "avc_spk_grad_begin", "avc_spk_grad_step",
     "avc_pm_set_allreduce", "avc_pm_param_count", "avc_pm_trainer_begin", "avc_pm_trainer_step", "avc_pm_trainer_grads",
     "avc_pm_trainer_end", "avc_pm_export_weights",
+    "avc_audio_create", "avc_audio_destroy", "avc_audio_last_error", "avc_audio_frames", "avc_audio_samples",
+    "avc_audio_wav2mel", "avc_audio_mel2wav", "avc_audio_kernel_launches",
 ]
 
 _lib = None
@@ -172,6 +179,19 @@ def load() -> C.CDLL:
     lib.avc_pm_trainer_grads.argtypes = [vp, P(WeightView), i32, vp]
     lib.avc_pm_trainer_end.argtypes = [vp]
     lib.avc_pm_export_weights.argtypes = [vp, P(WeightView), i32, vp]
+    lib.avc_audio_create.argtypes = [P(vp), P(AudioDesc), C.c_int]
+    lib.avc_audio_destroy.argtypes = [vp]
+    lib.avc_audio_destroy.restype = None
+    lib.avc_audio_last_error.argtypes = [vp]
+    lib.avc_audio_last_error.restype = C.c_char_p
+    lib.avc_audio_frames.argtypes = [vp, i64]
+    lib.avc_audio_frames.restype = i32
+    lib.avc_audio_samples.argtypes = [vp, i32]
+    lib.avc_audio_samples.restype = i64
+    lib.avc_audio_wav2mel.argtypes = [vp, vp, i64, vp, vp]
+    lib.avc_audio_mel2wav.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.avc_audio_kernel_launches.argtypes = [vp]
+    lib.avc_audio_kernel_launches.restype = i64
     lib.avc_version.argtypes = []
     lib.avc_version.restype = C.c_char_p
     _lib = lib

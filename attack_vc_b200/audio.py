@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference's mel front-end / Griffin-Lim back-end (``data_utils.py:65-197``) on top of the C-ABI
+(``avc_audio_*`` in include/avc_b200.h).  ``librosa.load`` / ``librosa.effects.trim`` (file I/O and silence trimming,
+data_utils.py:93-96) stay with the caller; everything from the trimmed waveform to the normalised mel and back runs on the
+GPU.  PyTorch supplies device memory and the stream only; there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .engine import AvcError
+
+
+class AudioEngine:
+    """One ``avc_audio_handle``: the preprocessing constants of ``config["preprocess"]`` (data_utils.py:214-220; the
+    reference passes them as ``**config["preprocess"]`` to file2mel / mel2wav)."""
+
+    def __init__(self, sample_rate: int = 24000, preemph: float = 0.97, n_fft: int = 2048, hop_length: int = 300,
+                 win_length: int = 1200, n_mels: int = 80, ref_db: float = 20.0, max_db: float = 100.0,
+                 top_db: Optional[float] = None, device: Optional[torch.device] = None):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise AvcError("attack_vc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        device = torch.device("cuda" if device is None else device)
+        if device.type != "cuda":
+            raise AvcError("attack_vc_b200 runs on CUDA only; there is no CPU fallback")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.n_mels, self.hop_length, self.n_fft = int(n_mels), int(hop_length), int(n_fft)
+        self.top_db = top_db          # used by librosa.effects.trim on the host, kept for signature compatibility
+        d = _lib.AudioDesc(int(sample_rate), int(n_fft), int(hop_length), int(win_length), int(n_mels), float(preemph), float(ref_db), float(max_db))
+        h = C.c_void_p()
+        rc = self._lib.avc_audio_create(C.byref(h), C.byref(d), self.device.index)
+        if rc != 0:
+            msg = self._lib.avc_audio_last_error(None).decode()
+            raise (ValueError if rc == -1 else AvcError)(f"avc_audio_create failed ({rc}): {msg}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.avc_audio_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.avc_audio_last_error(self._h).decode()
+            raise (ValueError if rc == -1 else AvcError)(f"libavc_b200: {msg}")
+
+    def _vec(self, x: Tensor, name: str, dim: int) -> Tensor:
+        if not isinstance(x, Tensor) or x.device != self.device:
+            raise AvcError(f"{name} must be a tensor on {self.device} (no CPU fallback)")
+        if x.dtype != torch.float32 or x.dim() != dim:
+            raise ValueError(f"{name} must be float32 with {dim} dimension(s) (got {x.dtype} {tuple(x.shape)})")
+        return x.contiguous()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.avc_audio_kernel_launches(self._h))
+
+    def wav2mel(self, wav: Tensor) -> Tensor:
+        """file2mel from the trimmed waveform on (data_utils.py:99-114): wav [n] -> mel [n_frames, n_mels]."""
+        wav = self._vec(wav, "wav", 1)
+        n = int(wav.numel())
+        F = int(self._lib.avc_audio_frames(self._h, n))
+        with torch.cuda.device(self.device):
+            mel = torch.empty(max(F, 0), self.n_mels, device=self.device, dtype=torch.float32)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self._check(self._lib.avc_audio_wav2mel(self._h, wav.data_ptr(), n, mel.data_ptr(), st))
+        return mel
+
+    def mel2wav(self, mel: Tensor, n_iter: int = 100) -> Tensor:
+        """mel2wav (data_utils.py:120-165): mel [n_frames, n_mels] -> waveform [hop_length * (n_frames - 1)]."""
+        mel = self._vec(mel, "mel", 2)
+        if mel.shape[1] != self.n_mels:
+            raise ValueError(f"mel must have {self.n_mels} bins (got {mel.shape[1]})")
+        F = int(mel.shape[0])
+        n = int(self._lib.avc_audio_samples(self._h, F))
+        with torch.cuda.device(self.device):
+            wav = torch.empty(max(n, 0), device=self.device, dtype=torch.float32)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self._check(self._lib.avc_audio_mel2wav(self._h, mel.data_ptr(), F, int(n_iter), wav.data_ptr(), st))
+        return wav

@@ -278,6 +278,27 @@ int avc_pm_trainer_end(avc_pm_trainer* t);
 int avc_pm_export_weights(avc_pm_handle* h, const avc_weight_view* tensors, int32_t n, void* stream);
 
 
+/* ---- mel front-end and Griffin-Lim back-end (reference data_utils.py:16-31, 65-197) ---------------
+ * Own handle: depends only on the preprocessing constants (the reference reads them from config.yaml, data_utils.py:214-220).
+ * librosa.load / librosa.effects.trim (file I/O, silence trimming: data_utils.py:93-96) stay on the host. */
+typedef struct avc_audio_handle avc_audio_handle;
+typedef struct avc_audio_desc {
+  int32_t sample_rate, n_fft, hop_length, win_length, n_mels;   /* AdaIN-VC: 24000, 2048, 300, 1200, 80 (BASELINE) / 512 */
+  float preemph, ref_db, max_db;                                /* 0.97, 20, 100                                        */
+} avc_audio_desc;
+int avc_audio_create(avc_audio_handle** out, const avc_audio_desc* d, int device);
+void avc_audio_destroy(avc_audio_handle* h);
+const char* avc_audio_last_error(const avc_audio_handle* h);
+int32_t avc_audio_frames(const avc_audio_handle* h, int64_t n_samples);    /* 1 + n_samples / hop_length (librosa.stft, center=True) */
+int64_t avc_audio_samples(const avc_audio_handle* h, int32_t n_frames);    /* hop_length * (n_frames - 1)     (librosa.istft)         */
+/* replaces: file2mel from the trimmed waveform on (data_utils.py:99-114): pre-emphasis, |librosa.stft|, mel basis, dB, clip.
+ * wav [n] device fp32 -> mel [avc_audio_frames(n)][n_mels] (the reference's mel.T).  Synchronises the stream. */
+int avc_audio_wav2mel(avc_audio_handle* h, const float* wav, int64_t n, float* mel, void* stream);
+/* replaces: mel2wav (data_utils.py:149-164) incl. griffin_lim (:168-197, n_iter = 100 there) and the de-emphasis lfilter.
+ * mel [n_frames][n_mels] -> wav [avc_audio_samples(n_frames)].  Synchronises the stream. */
+int avc_audio_mel2wav(avc_audio_handle* h, const float* mel, int32_t n_frames, int32_t n_iter, float* wav, void* stream);
+int64_t avc_audio_kernel_launches(const avc_audio_handle* h);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 int64_t avc_kernel_launches(const avc_handle* h);   /* kernels launched (graph nodes x replays) */
 int32_t avc_launches_per_iter(const avc_handle* h); /* kernels in the last captured iteration  */
