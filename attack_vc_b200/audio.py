@@ -66,25 +66,28 @@ class AudioEngine:
         return int(self._lib.avc_audio_kernel_launches(self._h))
 
     def wav2mel(self, wav: Tensor) -> Tensor:
-        """file2mel from the trimmed waveform on (data_utils.py:99-114): wav [n] -> mel [n_frames, n_mels]."""
-        wav = self._vec(wav, "wav", 1)
-        n = int(wav.numel())
+        """file2mel from the trimmed waveform on (data_utils.py:99-114): wav [n] -> mel [n_frames, n_mels];
+        a batch of equal-length waveforms [B, n] -> [B, n_frames, n_mels] (one GEMM over all frames)."""
+        batched = isinstance(wav, Tensor) and wav.dim() == 2
+        wav = self._vec(wav, "wav", 2 if batched else 1)
+        B, n = (int(wav.shape[0]), int(wav.shape[1])) if batched else (1, int(wav.numel()))
         F = int(self._lib.avc_audio_frames(self._h, n))
         with torch.cuda.device(self.device):
-            mel = torch.empty(max(F, 0), self.n_mels, device=self.device, dtype=torch.float32)
+            mel = torch.empty(B, max(F, 0), self.n_mels, device=self.device, dtype=torch.float32)
             st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            self._check(self._lib.avc_audio_wav2mel(self._h, wav.data_ptr(), n, mel.data_ptr(), st))
-        return mel
+            self._check(self._lib.avc_audio_wav2mel_batch(self._h, wav.data_ptr(), B, n, mel.data_ptr(), st))
+        return mel if batched else mel[0]
 
     def mel2wav(self, mel: Tensor, n_iter: int = 100) -> Tensor:
         """mel2wav (data_utils.py:120-165): mel [n_frames, n_mels] -> waveform [hop_length * (n_frames - 1)]."""
-        mel = self._vec(mel, "mel", 2)
-        if mel.shape[1] != self.n_mels:
-            raise ValueError(f"mel must have {self.n_mels} bins (got {mel.shape[1]})")
-        F = int(mel.shape[0])
+        batched = isinstance(mel, Tensor) and mel.dim() == 3          # [B, n_frames, n_mels]: equal-length utterances
+        mel = self._vec(mel, "mel", 3 if batched else 2)
+        if mel.shape[-1] != self.n_mels:
+            raise ValueError(f"mel must have {self.n_mels} bins (got {mel.shape[-1]})")
+        B, F = (int(mel.shape[0]), int(mel.shape[1])) if batched else (1, int(mel.shape[0]))
         n = int(self._lib.avc_audio_samples(self._h, F))
         with torch.cuda.device(self.device):
-            wav = torch.empty(max(n, 0), device=self.device, dtype=torch.float32)
+            wav = torch.empty(B, max(n, 0), device=self.device, dtype=torch.float32)
             st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            self._check(self._lib.avc_audio_mel2wav(self._h, mel.data_ptr(), F, int(n_iter), wav.data_ptr(), st))
-        return wav
+            self._check(self._lib.avc_audio_mel2wav_batch(self._h, mel.data_ptr(), B, F, int(n_iter), wav.data_ptr(), st))
+        return wav if batched else wav[0]

@@ -39,19 +39,23 @@ __device__ __forceinline__ int au_reflect(long long i, long long n) {      // np
 }
 
 // y[0] = x[0]; y[i] = x[i] - a x[i-1]                                   (data_utils.py:99)
-__global__ void au_preemph_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = i ? x[i] - a * x[i - 1] : x[0];
+// (x, y hold B utterances of n samples each, end to end)
+__global__ void au_preemph_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int B, float a) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * B; i += (long long)gridDim.x * blockDim.x)
+    y[i] = (i % n) ? x[i] - a * x[i - 1] : x[i];
 }
 
 // frame f, sample j = wav[reflect(f hop + j - n_fft/2)] * window[j], split into 3xTF32 planes      (librosa.stft, center=True)
+// n_frames per utterance; rows of the frame matrix are (utterance, frame)
 __global__ void au_frame_kernel(const float* __restrict__ wav, long long n, const float* __restrict__ window, float* __restrict__ hi,
-                                float* __restrict__ lo, int n_frames, int n_fft, int hop) {
-  const long long tot = (long long)n_frames * n_fft;
+                                float* __restrict__ lo, int n_frames, int B, int n_fft, int hop) {
+  const long long tot = (long long)B * n_frames * n_fft;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % n_fft), f = (int)(i / n_fft);
+    const int j = (int)(i % n_fft);
+    const long long r = i / n_fft;
+    const int f = (int)(r % n_frames), b = (int)(r / n_frames);
     const float w = window[j];
-    const float v = w != 0.f ? wav[au_reflect((long long)f * hop + j - n_fft / 2, n)] * w : 0.f;
+    const float v = w != 0.f ? wav[(long long)b * n + au_reflect((long long)f * hop + j - n_fft / 2, n)] * w : 0.f;
     const float h = tf32_hi(v);
     hi[i] = h; lo[i] = v - h;
   }
@@ -125,9 +129,11 @@ __global__ void au_phase_kernel(const float* __restrict__ mag, const float* __re
 
 // librosa.istft after the inverse transform: y[p] = sum_f tf[f][p - f hop] w[p - f hop] / sum_f w[p - f hop]^2 (where > tiny), the
 // n_fft/2 centre padding removed.  Gather form: every output sample walks the <= ceil(n_fft / hop) frames that cover it, in order.
-__global__ void au_ola_kernel(const float* __restrict__ tf, const float* __restrict__ window, float* __restrict__ wav, long long n_out, int n_frames,
-                              int n_fft, int hop) {
-  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_out; s += (long long)gridDim.x * blockDim.x) {
+__global__ void au_ola_kernel(const float* __restrict__ tf_all, const float* __restrict__ window, float* __restrict__ wav, long long n_out, int n_frames,
+                              int B, int n_fft, int hop) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_out * B; q += (long long)gridDim.x * blockDim.x) {
+    const long long s = q % n_out;
+    const float* tf = tf_all + (q / n_out) * (long long)n_frames * n_fft;
     const long long p = s + n_fft / 2;
     long long f_hi = p / hop;
     if (f_hi > n_frames - 1) f_hi = n_frames - 1;
@@ -141,13 +147,16 @@ __global__ void au_ola_kernel(const float* __restrict__ tf, const float* __restr
       acc = fmaf(tf[f * n_fft + j], w, acc);
       wss = fmaf(w, w, wss);
     }
-    wav[s] = wss > 1.17549435e-38f ? acc / wss : acc;
+    wav[q] = wss > 1.17549435e-38f ? acc / wss : acc;
   }
 }
 
 // scipy.signal.lfilter([1], [1, -a], x): y[n] = x[n] + a y[n-1], in place.  A 77 k-sample recurrence is 0.2 ms on one thread.
-__global__ void au_deemph_kernel(float* x, long long n, float a) {
-  if (blockIdx.x || threadIdx.x) return;
+// (one thread per utterance)
+__global__ void au_deemph_kernel(float* x_all, long long n, int B, float a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float* x = x_all + (long long)b * n;
   float acc = 0.f;
   for (long long i = 0; i < n; ++i) { acc = fmaf(a, acc, x[i]); x[i] = acc; }
 }
@@ -230,23 +239,23 @@ void au_gemm(avc_audio_handle* h, const float* xh, const float* xl, int M, int K
   h->launches += c.ksplit > 1 ? 2 : 1;
 }
 
-// frames -> spectrum [F][NP]
-void au_stft(avc_audio_handle* h, Arena& mem, const float* wav, long long n, int F, float* spec, cudaStream_t st) {
+// B utterances of n samples -> spectrum [B*F][NP]
+void au_stft(avc_audio_handle* h, Arena& mem, const float* wav, long long n, int F, int B, float* spec, cudaStream_t st) {
   const int n_fft = h->d.n_fft;
-  float* fh = mem.f((size_t)F * n_fft); float* fl = mem.f((size_t)F * n_fft);
-  au_frame_kernel<<<au_grid((long long)F * n_fft, h->sm_count), 256, 0, st>>>(wav, n, h->window, fh, fl, F, n_fft, h->d.hop_length);
+  float* fh = mem.f((size_t)B * F * n_fft); float* fl = mem.f((size_t)B * F * n_fft);
+  au_frame_kernel<<<au_grid((long long)B * F * n_fft, h->sm_count), 256, 0, st>>>(wav, n, h->window, fh, fl, F, B, n_fft, h->d.hop_length);
   CK(cudaGetLastError());
   h->launches++;
-  au_gemm(h, fh, fl, F, n_fft, h->wf_h, h->wf_l, h->NP, spec, st);
+  au_gemm(h, fh, fl, B * F, n_fft, h->wf_h, h->wf_l, h->NP, spec, st);
 }
 
 // spectrum planes [F][NP] -> waveform [hop (F - 1)]
-void au_istft(avc_audio_handle* h, Arena& mem, const float* xh, const float* xl, int F, float* tf, float* wav, cudaStream_t st) {
+void au_istft(avc_audio_handle* h, Arena& mem, const float* xh, const float* xl, int F, int B, float* tf, float* wav, cudaStream_t st) {
   const int n_fft = h->d.n_fft;
   (void)mem;
-  au_gemm(h, xh, xl, F, h->NP, h->wi_h, h->wi_l, n_fft, tf, st);
+  au_gemm(h, xh, xl, B * F, h->NP, h->wi_h, h->wi_l, n_fft, tf, st);
   const long long n_out = (long long)h->d.hop_length * (F - 1);
-  au_ola_kernel<<<au_grid(n_out, h->sm_count), 256, 0, st>>>(tf, h->window, wav, n_out, F, n_fft, h->d.hop_length);
+  au_ola_kernel<<<au_grid(n_out * B, h->sm_count), 256, 0, st>>>(tf, h->window, wav, n_out, F, B, n_fft, h->d.hop_length);
   CK(cudaGetLastError());
   h->launches++;
 }
@@ -341,66 +350,73 @@ int64_t avc_audio_kernel_launches(const avc_audio_handle* h) { return h ? h->lau
 int32_t avc_audio_frames(const avc_audio_handle* h, int64_t n_samples) { return (h && n_samples > 0) ? (int32_t)(1 + n_samples / h->d.hop_length) : -1; }
 int64_t avc_audio_samples(const avc_audio_handle* h, int32_t n_frames) { return (h && n_frames > 0) ? (int64_t)h->d.hop_length * (n_frames - 1) : -1; }
 
-int avc_audio_wav2mel(avc_audio_handle* h, const float* wav, int64_t n, float* mel, void* stream) {
+int avc_audio_wav2mel_batch(avc_audio_handle* h, const float* wav, int32_t B, int64_t n, float* mel, void* stream) {
   if (!h) return AVC_ERR_INVALID;
   return au_guarded(h, [&] {
-    if (!wav || !mel) fail(AVC_ERR_INVALID, "null tensor argument");
+    if (!wav || !mel || B < 1) fail(AVC_ERR_INVALID, "null tensor argument / bad batch");
     if (n <= h->d.n_fft / 2) fail(AVC_ERR_INVALID, "waveform of %lld samples is too short for reflect padding by n_fft / 2 = %d", (long long)n, h->d.n_fft / 2);
     cudaStream_t st = (cudaStream_t)stream;
     Arena mem(&h->pool, st);
-    const int F = 1 + (int)(n / h->d.hop_length);
-    float* pre = mem.f((size_t)n);
-    au_preemph_kernel<<<au_grid(n, h->sm_count), 256, 0, st>>>(wav, pre, n, h->d.preemph);
+    const int F = 1 + (int)(n / h->d.hop_length), R = B * F;
+    float* pre = mem.f((size_t)n * B);
+    au_preemph_kernel<<<au_grid(n * B, h->sm_count), 256, 0, st>>>(wav, pre, n, B, h->d.preemph);
     CK(cudaGetLastError());
-    float* spec = mem.f((size_t)F * h->NP);
-    au_stft(h, mem, pre, n, F, spec, st);
-    float* mag = mem.f((size_t)F * h->nbin);
-    au_mag_kernel<<<au_grid((long long)F * h->nbin, h->sm_count), 256, 0, st>>>(spec, mag, F, h->nbin, h->NP);
+    float* spec = mem.f((size_t)R * h->NP);
+    au_stft(h, mem, pre, n, F, B, spec, st);
+    float* mag = mem.f((size_t)R * h->nbin);
+    au_mag_kernel<<<au_grid((long long)R * h->nbin, h->sm_count), 256, 0, st>>>(spec, mag, R, h->nbin, h->NP);
     CK(cudaGetLastError());
-    const long long outs = (long long)F * h->d.n_mels;
-    au_mel_kernel<<<(unsigned)((outs * 32 + 255) / 256), 256, 0, st>>>(mag, h->basis, mel, F, h->nbin, h->d.n_mels, h->d.ref_db, h->d.max_db);
+    const long long outs = (long long)R * h->d.n_mels;
+    au_mel_kernel<<<(unsigned)((outs * 32 + 255) / 256), 256, 0, st>>>(mag, h->basis, mel, R, h->nbin, h->d.n_mels, h->d.ref_db, h->d.max_db);
     CK(cudaGetLastError());
     h->launches += 3;
     CK(cudaStreamSynchronize(st));
   });
 }
 
-int avc_audio_mel2wav(avc_audio_handle* h, const float* mel, int32_t n_frames, int32_t n_iter, float* wav, void* stream) {
+int avc_audio_mel2wav_batch(avc_audio_handle* h, const float* mel, int32_t B, int32_t n_frames, int32_t n_iter, float* wav, void* stream) {
   if (!h) return AVC_ERR_INVALID;
   return au_guarded(h, [&] {
-    if (!mel || !wav) fail(AVC_ERR_INVALID, "null tensor argument");
+    if (!mel || !wav || B < 1) fail(AVC_ERR_INVALID, "null tensor argument / bad batch");
     if (n_frames < 2 || n_iter < 0) fail(AVC_ERR_INVALID, "bad n_frames / n_iter");
-    const int F = n_frames, N = h->d.n_fft;
+    const int F = n_frames, N = h->d.n_fft, R = B * F;
     const long long n_out = (long long)h->d.hop_length * (F - 1);
     if (n_out <= N / 2) fail(AVC_ERR_INVALID, "%d frames give %lld samples: too short for the STFT inside Griffin-Lim", F, n_out);
     cudaStream_t st = (cudaStream_t)stream;
     Arena mem(&h->pool, st);
-    float* mag = mem.f((size_t)F * h->nbin);
-    au_invmel_kernel<<<F, 256, h->d.n_mels * sizeof(float), st>>>(mel, h->inv, mag, F, h->nbin, h->d.n_mels, h->d.ref_db, h->d.max_db);
+    float* mag = mem.f((size_t)R * h->nbin);
+    au_invmel_kernel<<<R, 256, h->d.n_mels * sizeof(float), st>>>(mel, h->inv, mag, R, h->nbin, h->d.n_mels, h->d.ref_db, h->d.max_db);
     CK(cudaGetLastError());
-    float* xh = mem.f((size_t)F * h->NP); float* xl = mem.f((size_t)F * h->NP);
-    float* tf = mem.f((size_t)F * N);
-    float* est = mem.f((size_t)F * h->NP);
-    float* fh = mem.f((size_t)F * N); float* fl = mem.f((size_t)F * N);
-    const unsigned gp = au_grid((long long)F * h->NP, h->sm_count);
-    au_phase_kernel<<<gp, 256, 0, st>>>(mag, nullptr, xh, xl, F, h->nbin, h->NP);          // X_best = spect
+    float* xh = mem.f((size_t)R * h->NP); float* xl = mem.f((size_t)R * h->NP);
+    float* tf = mem.f((size_t)R * N);
+    float* est = mem.f((size_t)R * h->NP);
+    float* fh = mem.f((size_t)R * N); float* fl = mem.f((size_t)R * N);
+    const unsigned gp = au_grid((long long)R * h->NP, h->sm_count);
+    au_phase_kernel<<<gp, 256, 0, st>>>(mag, nullptr, xh, xl, R, h->nbin, h->NP);          // X_best = spect
     CK(cudaGetLastError());
     h->launches += 2;
     for (int it = 0; it < n_iter; ++it) {                                                   // data_utils.py:183-187
-      au_istft(h, mem, xh, xl, F, tf, wav, st);
-      au_frame_kernel<<<au_grid((long long)F * N, h->sm_count), 256, 0, st>>>(wav, n_out, h->window, fh, fl, F, N, h->d.hop_length);
+      au_istft(h, mem, xh, xl, F, B, tf, wav, st);
+      au_frame_kernel<<<au_grid((long long)R * N, h->sm_count), 256, 0, st>>>(wav, n_out, h->window, fh, fl, F, B, N, h->d.hop_length);
       CK(cudaGetLastError());
-      au_gemm(h, fh, fl, F, N, h->wf_h, h->wf_l, h->NP, est, st);
-      au_phase_kernel<<<gp, 256, 0, st>>>(mag, est, xh, xl, F, h->nbin, h->NP);
+      au_gemm(h, fh, fl, R, N, h->wf_h, h->wf_l, h->NP, est, st);
+      au_phase_kernel<<<gp, 256, 0, st>>>(mag, est, xh, xl, R, h->nbin, h->NP);
       CK(cudaGetLastError());
       h->launches += 2;
     }
-    au_istft(h, mem, xh, xl, F, tf, wav, st);                                               // :188-189
-    au_deemph_kernel<<<1, 32, 0, st>>>(wav, n_out, h->d.preemph);                           // :162
+    au_istft(h, mem, xh, xl, F, B, tf, wav, st);                                            // :188-189
+    au_deemph_kernel<<<(B + 31) / 32, 32, 0, st>>>(wav, n_out, B, h->d.preemph);            // :162
     CK(cudaGetLastError());
     h->launches++;
     CK(cudaStreamSynchronize(st));
   });
+}
+
+int avc_audio_wav2mel(avc_audio_handle* h, const float* wav, int64_t n, float* mel, void* stream) {
+  return avc_audio_wav2mel_batch(h, wav, 1, n, mel, stream);
+}
+int avc_audio_mel2wav(avc_audio_handle* h, const float* mel, int32_t n_frames, int32_t n_iter, float* wav, void* stream) {
+  return avc_audio_mel2wav_batch(h, mel, 1, n_frames, n_iter, wav, stream);
 }
 
 }  // extern "C"

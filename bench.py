@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- attack iterations/s of the attack-vc perturbation loop on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload e2e|fb|emb|pm|vsmask]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload e2e|fb|emb|pm|vsmask|gl]
 
 A *step* is one attack iteration (adv = x + eps*tanh(w); forward; loss; backward; Adam) over one
 batch of synthetic 80-bin mel utterances.  Default workload = BASELINE.json configs[1]: e2e_attack,
@@ -46,6 +46,7 @@ WORKLOADS = {
     "emb": ("emb", 512, 512, "BASELINE configs[3]: emb_attack, 80x512, 512 utterances per GPU (4096 over 8)"),
     "pm": ("pm", 256, 100, "BASELINE configs[4]: VSMask predictive_model forward/backward, 80x100 windows, batch 256 per GPU"),
     "vsmask": ("vsmask", 256, 100, "SURVEY 8f rank 3: VSMask predictor training step (train_predictive.py:92-127), 80x100 windows, batch 256 per GPU"),
+    "gl": ("gl", 16, 256, "SURVEY 8f rank 4: mel2wav with 100 Griffin-Lim iterations (data_utils.py:120-197), 80-mel x 256-frame utterances, batch 16 per GPU"),
 }
 KIND_NAMES = {0: "conv", 1: "norm", 2: "dense_tail", 3: "affine", 4: "loss", 5: "update", 6: "layout", 7: "copy"}
 
@@ -356,6 +357,104 @@ def pm_arm(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def gl_cpu_rate(budget_s: float):
+    """utterances/s of the numpy oracle's mel2wav (100 Griffin-Lim iterations, 256 frames) on the host cores."""
+    from oracle import audio_oracle as A
+    import numpy as np
+    mel = np.random.default_rng(0).random((256, 80)).astype(np.float32)
+    t0 = time.perf_counter(); A.mel2wav(mel, n_iter=100); t1 = time.perf_counter() - t0
+    n = int(max(1, min(8, budget_s / t1)))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        A.mel2wav(mel, n_iter=100)
+    dt = time.perf_counter() - t0
+    return n / dt, os.cpu_count() or 1, n, dt
+
+
+def gl_arm(args, rank, world, local):
+    """one step = mel2wav (inverse mel, 100 Griffin-Lim iterations, de-emphasis) of a batch of utterances.
+    Multi-GPU: independent utterances per rank (replicas, no collective)."""
+    import torch.distributed as dist
+    _, B, F, desc = WORKLOADS["gl"]
+    metric = "mel2wav reconstructions/s (100 Griffin-Lim iterations)"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rate, cores, n, dt = gl_cpu_rate(20.0)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": rate, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": desc, "utterances_per_gpu": B, "frames": F},
+                          "cpu_baseline": {"value": rate, "unit": "utterances/s", "cores": cores, "kind": "port",
+                                           "sample": f"{n} utterances of 256 frames, numpy oracle (numpy.fft; librosa is not installed), {dt:.1f} s"},
+                          "e2e": {"value": rate, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev)); torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    from attack_vc_b200.audio import AudioEngine
+    eng = AudioEngine(device=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    host = torch.rand(B, F, 80, generator=torch.Generator().manual_seed(5 + rank)).pin_memory()
+    mel = host.to(dev)
+
+    def mx(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+    for _ in range(W):
+        eng.mel2wav(mel, n_iter=100)
+    l0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(K):
+            eng.mel2wav(mel, n_iter=100)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+    ms = mx(e0.elapsed_time(e1))
+    launches = eng.kernel_launches - l0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        w = eng.mel2wav(host.to(dev, non_blocking=True), n_iter=100).cpu()
+    e2e_ms = mx(1e3 * (time.perf_counter() - t0))
+    peaks = load_peaks()
+    # algorithmic FLOPs: 201 transforms per utterance, each a [F, 2048] x [2048, 2050] real GEMM
+    gflop = 201 * 2.0 * F * 2048 * 2050 / 1e9
+    tf = K * B * gflop / (ms / 1e3) / 1e3
+    line = {"metric": metric, "value": K * B * world / (ms / 1e3), "unit": "utterances/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "utterances_per_gpu": B, "frames": F, "n_fft": 2048, "hop_length": 300, "win_length": 1200,
+                       "l2": "the operand planes of one iteration (4 x 16 x 256 x 2048 x 4 B = 134 MB) exceed L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": K * B * world / (e2e_ms / 1e3), "unit": "utterances/s", "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": int(w.numel()) * 4,
+                    "api": "AudioEngine.mel2wav(pinned host mels) + waveform.cpu() per step"},
+            "gpu_launches": launches, "launches_per_step": launches / K,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None,
+                         "kernel": "conv2d_tc_kernel as the DFT / inverse-DFT GEMM (TMA + tcgen05, 3xTF32: 6 bf16-equivalents per algorithmic FLOP; a dense DFT does ~70x the FLOPs of an FFT)",
+                         "algorithmic_gflop_per_utterance": gflop, "peak_source": peaks["source"] + ", bf16 dense burst"}}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, cores, n, dt = gl_cpu_rate(12.0)
+        line["cpu_baseline"] = {"value": rate, "unit": "utterances/s", "cores": cores, "kind": "port",
+                                "sample": f"{n} utterances of 256 frames, numpy oracle (numpy.fft; librosa is not installed), {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def reference_arm(args, rank):
     kind, B, T, desc = WORKLOADS[args.workload]
     if rank != 0:
@@ -390,6 +489,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "gl":
+        if args.impl != "reference" and not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; attack_vc_b200 has no CPU fallback (use --impl reference for the CPU loop)")
+        gl_arm(args, rank, world, local)
+        return
     if args.workload in ("pm", "vsmask"):
         if args.impl != "reference" and not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; attack_vc_b200 has no CPU fallback (use --impl reference for the CPU loop)")

@@ -297,6 +297,10 @@ int avc_audio_wav2mel(avc_audio_handle* h, const float* wav, int64_t n, float* m
 /* replaces: mel2wav (data_utils.py:149-164) incl. griffin_lim (:168-197, n_iter = 100 there) and the de-emphasis lfilter.
  * mel [n_frames][n_mels] -> wav [avc_audio_samples(n_frames)].  Synchronises the stream. */
 int avc_audio_mel2wav(avc_audio_handle* h, const float* mel, int32_t n_frames, int32_t n_iter, float* wav, void* stream);
+/* the same for B utterances of EQUAL length laid end to end (wav [B][n], mel [B][n_frames][n_mels]): the B*n_frames frames are
+ * the rows of one GEMM per transform */
+int avc_audio_wav2mel_batch(avc_audio_handle* h, const float* wav, int32_t B, int64_t n, float* mel, void* stream);
+int avc_audio_mel2wav_batch(avc_audio_handle* h, const float* mel, int32_t B, int32_t n_frames, int32_t n_iter, float* wav, void* stream);
 int64_t avc_audio_kernel_launches(const avc_audio_handle* h);
 
 /* ---- introspection ----------------------------------------------------------------------- */

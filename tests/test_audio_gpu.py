@@ -97,3 +97,18 @@ def test_round_trip_and_errors(audio):
         audio.wav2mel(torch.zeros(500, device="cuda"))             # shorter than the reflect padding
     with pytest.raises(ValueError):
         audio.mel2wav(torch.zeros(10, 40, device="cuda"))          # wrong number of mel bins
+
+
+def test_batch_equals_single_calls(audio):
+    """B equal-length utterances as the rows of one GEMM per transform == B single calls (bit for bit for wav2mel: the same
+    per-row arithmetic; mel2wav within the K-split / tile-shape differences of the GEMM)."""
+    wavs = torch.stack([torch.from_numpy(tone(300 * 60 + 11, s)) for s in (1, 2, 3)]).cuda()
+    mel_b = audio.wav2mel(wavs)
+    assert mel_b.shape == (3, 61, 80)
+    for b in range(3):
+        assert float((mel_b[b] - audio.wav2mel(wavs[b])).abs().max()) < 2e-6
+    back_b = audio.mel2wav(mel_b, n_iter=2)
+    assert back_b.shape == (3, 300 * 60)
+    for b in range(3):
+        one = audio.mel2wav(mel_b[b].contiguous(), n_iter=2)
+        assert float((back_b[b] - one).abs().max()) < 1e-3 * float(one.abs().max())
