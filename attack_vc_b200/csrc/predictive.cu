@@ -897,7 +897,10 @@ Planes pm_split(avc_pm_handle* h, Arena& mem, const float* src, int B, int H, in
 void pm_refresh_weight_planes(avc_pm_handle* h, cudaStream_t st) {
   if (!h->planes_stale || !pm_tc_enabled()) return;
   auto one = [&](const float* src, float*& hi, float*& lo, size_t n) {
-    if (!hi) { hi = h->wmem.f(n); lo = h->wmem.f(n); }
+    if (!hi) {
+      hi = h->wmem.f(n); lo = h->wmem.f(n);
+      CK(cudaDeviceSynchronize());     // the weight arena zero-fills on the legacy stream: it must not overtake kernels of a non-blocking stream
+    }
     wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, hi, lo, 1, 1, (int)(n / 4), 4, 0, 0, 0);
     CK(cudaGetLastError());
     h->launches++;

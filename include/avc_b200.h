@@ -268,7 +268,8 @@ typedef struct avc_pm_trainer_args {
 int avc_pm_trainer_begin(avc_pm_handle* pm, avc_handle* se, const avc_pm_trainer_args* a, void* stream, avc_pm_trainer** out);
 /* one optimiser step on (source, target) [B,1,F,T] contiguous device tensors; lr is this step's learning rate (the
  * reference's ReduceLROnPlateau, :58-60,131, stays on the host).  loss_out: one device float or NULL (with sharding:
- * this rank's part of the global loss).  Enqueues on `stream`; returns without synchronising. */
+ * this rank's part of the global loss).  Synchronises `stream` before returning (the step's activations go back to the
+ * handle's pool). */
 int avc_pm_trainer_step(avc_pm_trainer* t, const float* source, const float* target, float lr, float* loss_out, void* stream);
 /* d loss / d (parameter) of the LAST step, by state_dict key, PyTorch shapes (test / inspection aid) */
 int avc_pm_trainer_grads(avc_pm_trainer* t, const avc_weight_view* grads, int32_t n, void* stream);
