@@ -84,3 +84,15 @@ def test_predictive_engine_refuses_cpu():
     from attack_vc_b200.synthetic import pm_make_state_dict
     with pytest.raises(AvcError):
         PredictiveEngine(pm_make_state_dict(0))
+
+
+def test_audio_engine_refuses_cpu_and_struct_layout():
+    import torch
+    from attack_vc_b200 import _lib
+    assert C.sizeof(_lib.AudioDesc) == 5 * 4 + 3 * 4          # avc_audio_desc: five int32, three float
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from attack_vc_b200 import AvcError
+    from attack_vc_b200.audio import AudioEngine
+    with pytest.raises(AvcError):
+        AudioEngine()
