@@ -1756,32 +1756,64 @@ std::unique_ptr<Plan> build_spkgrad(avc_handle* h, const avc_spk_grad_args* a, c
   const double inv_norm = a->inv_norm > 0 ? a->inv_norm : 1.0 / ((double)B * SE.d.c_out);
   const int parts = B;
   float* loss_parts = m.f((size_t)parts);
-  float* org = m.f((size_t)B * 128);
-  float* tgt = m.f((size_t)B * 128);
-  EncActs se1 = alloc_encoder(m, SE, B, T, true, false);
-  const Tens adv = se1.input(SE);
+  float* org = m.f((size_t)2 * B * 128);       // org | tgt adjacent ([2B,128]): the 2B-utterance tail writes both
+  float* tgt = org + (size_t)B * 128;
   const float lam = a->lambda;
-  auto se_forward = [&](const EncActs& A, int tail_mode, const float* tgt_e, const float* org_e, float* emb_dst) {
-    emit_bank_and_inconv(I, SE, A, false);
-    emit_encoder_blocks_fwd(I, SE, A, false);
-    TailArgs t = tail_args(SE, A);
-    t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm; t.lam = lam;
-    t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
-    if (emb_dst) t.emb = emb_dst;
-    emit_tail(I, t, A.B);
-  };
-  emit_layout_in(I, a->source, a->s_stride, adv, B, C);
-  se_forward(se1, TAIL_FWD, nullptr, nullptr, org);
+  EncActs se1;
   if (a->T_tgt == T) {
-    emit_layout_in(I, a->target, a->t_stride, adv, B, C);
-    se_forward(se1, TAIL_FWD, nullptr, nullptr, tgt);
+    // equal lengths (the trainer's case): ONE forward pass over [perturbed; source; target] -- 3B utterances fill the
+    // tensor-core tiles better than three passes of B -- then the dense tail forward on the last 2B utterances and
+    // forward + loss + backward on the first B.  Every buffer is batch-major, so the first B utterances of the 3B
+    // activations ARE the activations the backward pass needs.
+    EncActs se3 = alloc_encoder(m, SE, 3 * B, T, false, false);
+    const int ch = SE.d.c_h;
+    se3.gA = m.f((size_t)B * T * ch); se3.gB = m.f((size_t)B * T * ch); se3.gH = m.f((size_t)B * T * ch);
+    se3.gcat = m.f((size_t)B * T * SE.c_cat); se3.gin = m.f((size_t)B * T * SE.d.c_in);
+    Tens in = se3.input(SE);
+    emit_layout_in(I, a->perturbed, a->p_stride, in, B, C);
+    in.p += (long long)B * in.bs;
+    emit_layout_in(I, a->source, a->s_stride, in, B, C);
+    in.p += (long long)B * in.bs;
+    emit_layout_in(I, a->target, a->t_stride, in, B, C);
+    emit_bank_and_inconv(I, SE, se3, false);
+    emit_encoder_blocks_fwd(I, SE, se3, false);
+    {   // embeddings of source (-> org) and target (-> tgt): utterances [B, 3B)
+      TailArgs t = tail_args(SE, se3);
+      t.h += (long long)B * t.h_bs;
+      t.acts += (size_t)B * (3 * SE.d.n_dense_blocks + 1) * 128;
+      t.gpool += (size_t)B * 128;
+      t.mode = TAIL_FWD; t.inv_norm = (float)inv_norm; t.lam = lam;
+      t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+      t.emb = org;                      // org [B,128] and tgt [B,128] are adjacent: one [2B,128] block
+      emit_tail(I, t, 2 * B);
+    }
+    se1 = se3; se1.B = B;
+    {
+      TailArgs t = tail_args(SE, se1);
+      t.mode = TAIL_FWD | TAIL_LOSS | TAIL_BWD; t.tgt = tgt; t.org = org; t.inv_norm = (float)inv_norm; t.lam = lam;
+      t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+      emit_tail(I, t, B);
+    }
   } else {
+    se1 = alloc_encoder(m, SE, B, T, true, false);
+    const Tens adv = se1.input(SE);
+    auto se_forward = [&](const EncActs& A, int tail_mode, const float* tgt_e, const float* org_e, float* emb_dst) {
+      emit_bank_and_inconv(I, SE, A, false);
+      emit_encoder_blocks_fwd(I, SE, A, false);
+      TailArgs t = tail_args(SE, A);
+      t.mode = tail_mode; t.tgt = tgt_e; t.org = org_e; t.inv_norm = (float)inv_norm; t.lam = lam;
+      t.loss_parts = loss_parts; t.step = step; t.parts_per_step = parts;
+      if (emb_dst) t.emb = emb_dst;
+      emit_tail(I, t, A.B);
+    };
+    emit_layout_in(I, a->source, a->s_stride, adv, B, C);
+    se_forward(se1, TAIL_FWD, nullptr, nullptr, org);
     EncActs seT = alloc_encoder(m, SE, B, a->T_tgt, false, false);
     emit_layout_in(I, a->target, a->t_stride, seT.input(SE), B, C);
     se_forward(seT, TAIL_FWD, nullptr, nullptr, tgt);
+    emit_layout_in(I, a->perturbed, a->p_stride, adv, B, C);
+    se_forward(se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
   }
-  emit_layout_in(I, a->perturbed, a->p_stride, adv, B, C);
-  se_forward(se1, TAIL_FWD | TAIL_LOSS | TAIL_BWD, tgt, org, nullptr);
   Tens gin = tens(se1.gin, T, C);
   GradParts gparts;
   emit_speaker_bwd(I, SE, se1, gin, &gparts);
