@@ -2334,11 +2334,10 @@ int avc_conv1d_wgrad_ex(avc_handle* h, const float* x, const float* dy, float* d
       wt_split_pad_kernel<<<ew_grid(rows * c_out / 4, h->sm_count), 256, 0, st>>>(dy, gh, gl, B, 1, To, c_out, 0, 0, 0);
       CK(cudaGetLastError());
       WtArgs p{};
-      p.Ci = c_in; p.Co = c_out;
-      wt_pick_boxes(p, To, 1, B);
       p.a_wmul = stride; p.a_hmul = 1; p.g_wmul = 1; p.g_hmul = 1;
       for (int j = 0; j < k; ++j) { p.a_woff[j] = j; p.a_hoff[j] = 0; p.g_woff[j] = 0; p.g_hoff[j] = 0; }
       p.n_taps = k; p.Ci = c_in; p.Co = c_out; p.Cop = c_out;
+      wt_pick_boxes(p, To, 1, B);           // after the taps: the stage geometry depends on which operand moves with the tap
       const int S = wt_splits(p, h->sm_count);
       p.partial = tmp.f((size_t)S * k * c_in * c_out);
       const WtOperand A{xh, xl, c_in, Tp, 1, B, stride, 1}, G{gh, gl, c_out, To, 1, B, 1, 1};

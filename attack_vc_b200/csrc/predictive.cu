@@ -1031,14 +1031,13 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       if (!gp.h) gp = pm_split(h, mem, G, B, Hg, Wg, Co, 0, st);
       float *ah = ap.h, *al = ap.l, *gh = gp.h, *gl = gp.l;
       WtArgs p{};
-      p.Ci = Ci; p.Co = Co;
-      wt_pick_boxes(p, Wb, Hb, B);
       p.a_wmul = up ? 1 : sw; p.a_hmul = up ? 1 : sh; p.g_wmul = up ? 2 : 1; p.g_hmul = up ? 2 : 1;
       for (int t = 0; t < 9; ++t) {
         p.a_woff[t] = up ? 0 : t % 3; p.a_hoff[t] = up ? 0 : t / 3;
         p.g_woff[t] = up ? t % 3 : 0; p.g_hoff[t] = up ? t / 3 : 0;
       }
       p.n_taps = 9; p.Ci = Ci; p.Co = Co; p.Cop = pad4(Co);
+      wt_pick_boxes(p, Wb, Hb, B);          // after the taps: the stage geometry depends on which operand moves with the tap
       const int S = wt_splits(p, h->sm_count);
       p.partial = mem.f((size_t)S * 9 * Ci * p.Cop);
       const WtOperand Aop{ah, al, Ci, Wap, Hap, B, up ? 1 : sw, up ? 1 : sh}, Gop{gh, gl, Co, Wg, Hg, B, up ? 2 : 1, up ? 2 : 1};

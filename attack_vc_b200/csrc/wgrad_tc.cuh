@@ -46,6 +46,10 @@ struct WtArgs {
   int nw, nh, nb;                        // boxes along w, h, b of the BASE pixel grid
   int bw, bh, bb;                        // base pixels per box along each axis (bw*bh*bb <= KP)
   int KP, n_stages, mbm, nbm;            // rows per stage (multiple of 8), ring depth, 32-channel blocks of a full tile (c_in, c_out)
+  // A CTA can compute `tg` consecutive taps (own TMEM accumulator each) from ONE pass over the pixels: the operand whose box
+  // does not move with the tap (the gradient of a Conv2d / Conv1d, the input of a transposed conv) is then loaded once per stage
+  // instead of once per tap.  Measured slower than one tap per CTA (see wt_pick_boxes): tg = 1 by default.
+  int tg, a_same, g_same;                // taps per CTA (<= 3); 1: that operand's box offsets are identical for every tap
   int a_wmul, a_hmul, g_wmul, g_hmul;    // tensor coordinate of base pixel (w, h): w * wmul + woff[tap], h * hmul + hoff[tap]
   int a_woff[kWtMaxTaps], a_hoff[kWtMaxTaps], g_woff[kWtMaxTaps], g_hoff[kWtMaxTaps];
   int n_taps;
@@ -75,13 +79,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   const uint32_t bar0 = smem_u32(bars);
   const int n_stages = p.n_stages;
   const uint32_t blk = (uint32_t)p.KP * 128;                                    // one 32-channel block of a plane
-  const uint32_t offAl = (uint32_t)p.mbm * blk, offGh = 2 * offAl, offGl = offGh + (uint32_t)p.nbm * blk;
-  const uint32_t stage_bytes = 2 * (uint32_t)(p.mbm + p.nbm) * blk;
+  // stage = [A copy 0: hi | lo] .. [A copy na-1] [G copy 0: hi | lo] .. [G copy ng-1]
+  const int na = p.a_same ? 1 : p.tg, ng = p.g_same ? 1 : p.tg;
+  const uint32_t a_copy = 2 * (uint32_t)p.mbm * blk, g_copy = 2 * (uint32_t)p.nbm * blk;
+  const uint32_t offAl = (uint32_t)p.mbm * blk, offGl = (uint32_t)p.nbm * blk, offG = (uint32_t)na * a_copy;
+  const uint32_t stage_bytes = (uint32_t)na * a_copy + (uint32_t)ng * g_copy;
   auto full = [&](int s) { return bar0 + 8 * s; };
   auto empty = [&](int s) { return bar0 + 8 * (kWtMaxStages + s); };
   const uint32_t acc_full = bar0 + 8 * (2 * kWtMaxStages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, tap = blockIdx.z;
+  const int split = blockIdx.x, tap0 = (int)blockIdx.z * p.tg;
+  const int ntap = min(p.tg, p.n_taps - tap0);                                  // taps of this CTA
   const int n_nt = (p.Co + 127) / 128;
   const int ci0 = ((int)blockIdx.y / n_nt) * 128, co0 = ((int)blockIdx.y % n_nt) * 128;
   const int mb = min(4, (p.Ci - ci0 + 31) / 32), nbk = min(4, (p.Co - co0 + 31) / 32);   // 32-channel blocks that exist
@@ -100,7 +108,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   }
   fence_proxy_async();
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -111,8 +119,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      const uint32_t bytes = (uint32_t)((mb + nbk) * 2 * rows * 128);
-      const int awo = p.a_woff[tap], aho = p.a_hoff[tap], gwo = p.g_woff[tap], gho = p.g_hoff[tap];
+      const int na_l = p.a_same ? 1 : ntap, ng_l = p.g_same ? 1 : ntap;         // copies actually loaded
+      const uint32_t bytes = (uint32_t)((na_l * mb + ng_l * nbk) * 2 * rows * 128);
       int s = 0; uint32_t ph = 0;
       for (int q = q_lo; q < q_hi; ++q) {
         const int wi = q % p.nw, t = q / p.nw;
@@ -121,14 +129,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         mbar_wait(empty(s), ph ^ 1);
         mbar_expect_tx(full(s), bytes);
         const uint32_t base = smem_u32(smem) + (uint32_t)s * stage_bytes;
-        const int aw = w0 * p.a_wmul + awo, ah = h0 * p.a_hmul + aho, gw = w0 * p.g_wmul + gwo, gh = h0 * p.g_hmul + gho;
-        for (int j = 0; j < mb; ++j) {
-          tma_load_4d(base + (uint32_t)j * blk, &tmAh, ci0 + 32 * j, aw, ah, b0, full(s));
-          tma_load_4d(base + offAl + (uint32_t)j * blk, &tmAl, ci0 + 32 * j, aw, ah, b0, full(s));
+        for (int c = 0; c < na_l; ++c) {
+          const int aw = w0 * p.a_wmul + p.a_woff[tap0 + c], ah = h0 * p.a_hmul + p.a_hoff[tap0 + c];
+          const uint32_t cb = base + (uint32_t)c * a_copy;
+          for (int j = 0; j < mb; ++j) {
+            tma_load_4d(cb + (uint32_t)j * blk, &tmAh, ci0 + 32 * j, aw, ah, b0, full(s));
+            tma_load_4d(cb + offAl + (uint32_t)j * blk, &tmAl, ci0 + 32 * j, aw, ah, b0, full(s));
+          }
         }
-        for (int j = 0; j < nbk; ++j) {
-          tma_load_4d(base + offGh + (uint32_t)j * blk, &tmGh, co0 + 32 * j, gw, gh, b0, full(s));
-          tma_load_4d(base + offGl + (uint32_t)j * blk, &tmGl, co0 + 32 * j, gw, gh, b0, full(s));
+        for (int c = 0; c < ng_l; ++c) {
+          const int gw = w0 * p.g_wmul + p.g_woff[tap0 + c], gh = h0 * p.g_hmul + p.g_hoff[tap0 + c];
+          const uint32_t cb = base + offG + (uint32_t)c * g_copy;
+          for (int j = 0; j < nbk; ++j) {
+            tma_load_4d(cb + (uint32_t)j * blk, &tmGh, co0 + 32 * j, gw, gh, b0, full(s));
+            tma_load_4d(cb + offGl + (uint32_t)j * blk, &tmGl, co0 + 32 * j, gw, gh, b0, full(s));
+          }
         }
         if (++s == n_stages) { s = 0; ph ^= 1; }
       }
@@ -143,15 +158,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
       tc_fence_after();
       if (leader) {
         const uint32_t base = smem_u32(smem) + (uint32_t)s * stage_bytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t o = (uint32_t)ks * 1024;
-          const uint64_t dAh = wt_desc(base + o, blk), dAl = wt_desc(base + offAl + o, blk);
-          const uint64_t dGh = wt_desc(base + offGh + o, blk), dGl = wt_desc(base + offGl + o, blk);
-          tc_mma_tf32(tmem_base, dAh, dGh, idesc, acc);
-          acc = 1;
-          tc_mma_tf32(tmem_base, dAl, dGh, idesc, 1);
-          tc_mma_tf32(tmem_base, dAh, dGl, idesc, 1);
+        for (int c = 0; c < ntap; ++c) {
+          const uint32_t ab = base + (p.a_same ? 0u : (uint32_t)c * a_copy), gb = base + offG + (p.g_same ? 0u : (uint32_t)c * g_copy);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(c * 128);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t o = (uint32_t)ks * 1024;
+            const uint64_t dAh = wt_desc(ab + o, blk), dAl = wt_desc(ab + offAl + o, blk);
+            const uint64_t dGh = wt_desc(gb + o, blk), dGl = wt_desc(gb + offGl + o, blk);
+            tc_mma_tf32(d_tmem, dAh, dGh, idesc, (acc || ks) ? 1u : 0u);
+            tc_mma_tf32(d_tmem, dAl, dGh, idesc, 1);
+            tc_mma_tf32(d_tmem, dAh, dGl, idesc, 1);
+          }
         }
+        acc = 1;
         tc_commit(empty(s));
       }
       __syncwarp();
@@ -165,21 +184,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
     const bool any = q_lo < q_hi;
     if (any) { mbar_wait(acc_full, 0); tc_fence_after(); }
     const int ci = ci0 + quarter * 32 + lane;
-    float* out = p.partial + (((size_t)split * p.n_taps + tap) * p.Ci + ci) * p.Cop + co0;
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      uint32_t r[16];
-      if (any) {
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
-      } else {
+    for (int c = 0; c < ntap; ++c) {
+      float* out = p.partial + (((size_t)split * p.n_taps + tap0 + c) * p.Ci + ci) * p.Cop + co0;
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t r[16];
+        if (any) {
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 128 + c0), r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = 0u;
-      }
-      if (ci < p.Ci) {
+          for (int i = 0; i < 16; ++i) r[i] = 0u;
+        }
+        if (ci < p.Ci) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          if (co0 + c0 + i < p.Cop)
-            st4(out + c0 + i, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+          for (int i = 0; i < 16; i += 4)
+            if (co0 + c0 + i < p.Cop)
+              st4(out + c0 + i, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+        }
       }
     }
   }
@@ -187,7 +208,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -262,7 +283,21 @@ inline CUtensorMap wt_tensor_map(const float* base, const WtOperand& o, int bw, 
 // when they fit, then several rows, then several images.  (Set p.Ci / p.Co first.)
 inline void wt_pick_boxes(WtArgs& p, int Wb, int Hb, int Bn) {
   p.mbm = std::min(4, (p.Ci + 31) / 32); p.nbm = std::min(4, (p.Co + 31) / 32);
-  const int per_row = 2 * (p.mbm + p.nbm) * 128;
+  // tap grouping: possible when one operand's box does not move with the tap; three taps per CTA (one kernel row of a 3x3 conv)
+  p.a_same = p.g_same = 1;
+  for (int t = 1; t < p.n_taps; ++t) {
+    if (p.a_woff[t] != p.a_woff[0] || p.a_hoff[t] != p.a_hoff[0]) p.a_same = 0;
+    if (p.g_woff[t] != p.g_woff[0] || p.g_hoff[t] != p.g_hoff[0]) p.g_same = 0;
+  }
+  static const bool no_group = getenv("AVC_WT_NO_TAP_GROUP") != nullptr;
+  // Measured (PredictiveModel step 256 windows, Conv1d 128 -> 128 k5 at 64 x 512): grouping is parity-green and never faster --
+  // everywhere 5.76 -> 6.01 ms per step and 139 -> 180 us, on the small-channel layers only (c_in + c_out <= 96) 5.73 -> 5.77 ms:
+  // a third of the CTAs each issuing three times the MMAs loses more than the saved operand reads gain.  Off unless
+  // AVC_WT_TAP_GROUP=1 (kept for A/B runs and for shapes with more taps per operand byte).
+  static const bool group = getenv("AVC_WT_TAP_GROUP") && atoi(getenv("AVC_WT_TAP_GROUP")) == 1;
+  p.tg = (group && !no_group && p.n_taps >= 2 && (p.a_same || p.g_same)) ? std::min(3, p.n_taps) : 1;
+  const int na = p.a_same ? 1 : p.tg, ng = p.g_same ? 1 : p.tg;
+  const int per_row = 2 * (na * p.mbm + ng * p.nbm) * 128;
   const int cap = std::max(8, std::min(128, kWtStageTarget / per_row / 8 * 8));       // pixels a stage can hold
   p.bw = std::min(Wb, cap);
   p.bh = p.bw == Wb ? std::max(1, std::min(Hb, cap / p.bw)) : 1;
@@ -278,10 +313,11 @@ inline void wt_init_attributes() {
 
 // partial must hold wt_splits(...) * n_taps * Ci * Cop floats; returns the number of splits used
 inline int wt_splits(const WtArgs& p, int sm_count) {
-  const int tiles = ((p.Ci + 127) / 128) * ((p.Co + 127) / 128) * p.n_taps;
+  const int tiles = ((p.Ci + 127) / 128) * ((p.Co + 127) / 128) * ((p.n_taps + p.tg - 1) / p.tg);
   const int n_boxes = p.nw * p.nh * p.nb;
   int S = std::max(1, std::min(n_boxes, (2 * sm_count + tiles - 1) / tiles));
   S = std::max(S, (n_boxes * (p.KP / 8) * 3 + 767) / 768);   // at most 768 MMAs into one TMEM accumulator (truncating adds)
+  S = std::min(S, n_boxes);
   const int per = (n_boxes + S - 1) / S;
   return (n_boxes + per - 1) / per;
 }
@@ -289,7 +325,7 @@ inline int wt_splits(const WtArgs& p, int sm_count) {
 inline void launch_wgrad_tc(const WtOperand& A, const WtOperand& G, const WtArgs& p, int S, cudaStream_t st) {
   const CUtensorMap tAh = wt_tensor_map(A.hi, A, p.bw, p.bh, p.bb), tAl = wt_tensor_map(A.lo, A, p.bw, p.bh, p.bb);
   const CUtensorMap tGh = wt_tensor_map(G.hi, G, p.bw, p.bh, p.bb), tGl = wt_tensor_map(G.lo, G, p.bw, p.bh, p.bb);
-  dim3 grid((unsigned)S, (unsigned)(((p.Ci + 127) / 128) * ((p.Co + 127) / 128)), (unsigned)p.n_taps);
+  dim3 grid((unsigned)S, (unsigned)(((p.Ci + 127) / 128) * ((p.Co + 127) / 128)), (unsigned)((p.n_taps + p.tg - 1) / p.tg));
   wgrad_tc_kernel<<<grid, kWtThreads, wt_smem_bytes(), st>>>(tAh, tAl, tGh, tGl, p);
   CK(cudaGetLastError());
 }
