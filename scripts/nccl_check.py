@@ -84,7 +84,7 @@ def main():
     # Gradients of ONE step on three different batches, per tensor.  The two runs sum the BatchNorm statistics in different
     # orders (one device vs partial sums per rank + all-reduce): they differ by ~1e-7 before the activations, and a PReLU /
     # LeakyReLU unit within that distance of zero takes the other branch in one of them.  With 12 windows a single such unit
-    # in a deep layer moves EVERY upstream gradient by 1e-3 .. 1e-2 (seen with seed 31: 53 % of the tensors beyond 1e-3, one
+    # in a deep layer moves EVERY upstream gradient by 1e-3 .. 1e-2 (seen with seed 31, tests/tools/dp_probe.py: 53 % of the tensors beyond 1e-3, one
     # device against the CPU oracle 5e-6 on one side of the kink).  A missing or wrong coupling is O(1) on every batch.  So:
     # at least two of the three batches with every tensor within 1e-3, none beyond 5e-2.
     clean, gworst = 0, 0.0

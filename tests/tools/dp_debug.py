@@ -1,6 +1,6 @@
 """Debug: data-parallel trainer (real NCCL, different shards) vs one GPU vs the CPU oracle, ONE step, per-tensor errors."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 from attack_vc_b200 import Engine

@@ -1,6 +1,6 @@
 """Single-GPU accuracy of the trainer's gradients at the batch sizes of scripts/nccl_check.py part 3, against the CPU oracle."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from attack_vc_b200 import Engine
 from attack_vc_b200.predictive import PredictiveEngine, PredictiveTrainer
