@@ -5,7 +5,7 @@ import torch
 from attack_vc_b200 import Engine
 from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs
 from attack_vc_b200.predictive import PredictiveEngine
-from oracle.predictive_oracle import pm_make_state_dict
+from attack_vc_b200.synthetic import pm_make_state_dict
 dev = torch.device("cuda:0")
 eng = Engine(ParamTree(SYNTH_CONFIG, seed=0).to(dev))
 for kind, B, T in (("e2e", 1, 64), ("fb", 1, 40), ("emb", 9, 256), ("fb", 10, 200)):   # small-M kernels, then tcgen05 plans

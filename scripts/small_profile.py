@@ -11,14 +11,14 @@ import torch
 sys.path.insert(0, ".")
 from attack_vc_b200 import Engine  # noqa: E402
 from attack_vc_b200._lib import load  # noqa: E402
-from oracle import adainvc_oracle as O  # noqa: E402
+from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs  # noqa: E402
 
 lib = load()
 fn = lib.avc_debug_small_profile
 fn.argtypes = [C.c_void_p, C.c_int]
 fn.restype = C.c_int
-eng = Engine(O.OracleAdaInVC(O.SYNTH_CONFIG, seed=0).to("cuda"))
-inp = O.make_inputs("e2e", 1, 256, seed=1)
+eng = Engine(ParamTree(SYNTH_CONFIG, seed=0).to("cuda"))
+inp = make_inputs("e2e", 1, 256, seed=1)
 x, at, src, w0 = (inp[k].cuda() for k in ("vc_tgt", "adv_tgt", "vc_src", "w0"))
 buf = np.zeros((8192, 12), dtype=np.uint64)
 eng.attack("e2e", x, at, 0.1, 64, vc_src=src, w0=w0)

@@ -1,5 +1,5 @@
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from attack_vc_b200 import Engine
 from attack_vc_b200.synthetic import SYNTH_CONFIG, ParamTree, make_inputs
