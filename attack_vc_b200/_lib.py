@@ -89,6 +89,7 @@ EXPORTS = [
     "avc_create", "avc_destroy", "avc_last_error", "avc_load_weights", "avc_emb_attack", "avc_e2e_attack",
     "avc_fb_attack", "avc_speaker_encoder", "avc_inference", "avc_decoder_frames", "avc_conv1d_fwd",
     "avc_conv1d_dgrad", "avc_conv1d_wgrad", "avc_conv1d_wgrad_ex", "avc_instnorm_adain_act_fwd", "avc_instnorm_adain_act_bwd", "avc_adam_tanh_step",
+    "avc_unit_timing", "avc_unit_last_ms",
     "avc_kernel_launches", "avc_launches_per_iter", "avc_version",
     "avc_attack_begin", "avc_attack_step", "avc_attack_end", "avc_session_launches", "avc_session_profile",
     "avc_header_optimize", "avc_header_begin", "avc_header_step", "avc_header_grad_buffer",
@@ -149,6 +150,9 @@ def load() -> C.CDLL:
     lib.avc_instnorm_adain_act_fwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp]
     lib.avc_instnorm_adain_act_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, vp]
     lib.avc_adam_tanh_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, f32, i32, vp]
+    lib.avc_unit_timing.argtypes = [vp, i32]
+    lib.avc_unit_last_ms.argtypes = [vp]
+    lib.avc_unit_last_ms.restype = f32
     lib.avc_kernel_launches.argtypes = [vp]
     lib.avc_kernel_launches.restype = i64
     lib.avc_launches_per_iter.argtypes = [vp]

@@ -231,6 +231,10 @@ struct avc_handle {
   // and capturing a plan costs ~1 ms, as much as a few iterations at batch 1.  Small plans only, a handful of them.
   std::vector<std::unique_ptr<Plan>> plan_cache;
   long long plan_cache_hits = 0;
+  // avc_unit_timing: the HBM-bound unit entry points run their launch list 1 + unit_reps times back to back and time the
+  // last unit_reps with events recorded on the caller's stream right behind the first run (no host time in the bracket)
+  int unit_reps = 0;
+  float unit_ms = 0.f;
 };
 
 struct avc_session {
@@ -1979,6 +1983,29 @@ int guarded(avc_handle* h, Fn&& fn) {
 // =================================================================================================
 // C ABI
 // =================================================================================================
+namespace {
+// run a unit entry point's launches; with avc_unit_timing set, repeat them and keep the device time of one repetition
+template <class F>
+void run_unit(avc_handle* h, cudaStream_t st, F&& run) {
+  run();
+  h->launches += 1;
+  if (h->unit_reps > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+    for (int r = 0; r < h->unit_reps; ++r) run();
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    h->unit_ms = ms / (float)h->unit_reps;
+    h->launches += h->unit_reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  CK(cudaStreamSynchronize(st));
+}
+}  // namespace
+
 extern "C" {
 
 #ifndef AVC_SRC_HASH
@@ -2390,9 +2417,7 @@ int avc_instnorm_adain_act_fwd(avc_handle* h, const float* y, const float* cond,
     ResArgs r = no_res();
     if (res) r = mk_res(tens(const_cast<float*>(res), T / up, C), up > 1 ? RES_UP : RES_SAME, up);
     emit_norm_fwd(E, y, B, T, C, cond, 2 * C, nullptr, stats_out, out, r, neg_slope);
-    run_list(v, (cudaStream_t)stream);
-    h->launches += 1;
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    run_unit(h, (cudaStream_t)stream, [&] { run_list(v, (cudaStream_t)stream); });
   });
 }
 
@@ -2405,9 +2430,7 @@ int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, co
     Arena scratch(nullptr, (cudaStream_t)stream);
     Emitter E{h, &v, &scratch};
     emit_norm_bwd(E, g, y, stats, cond, 2 * C, gy, gcond, 2 * C, B, T, C, neg_slope);
-    run_list(v, (cudaStream_t)stream);
-    h->launches += 1;
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    run_unit(h, (cudaStream_t)stream, [&] { run_list(v, (cudaStream_t)stream); });
   });
 }
 
@@ -2429,9 +2452,7 @@ int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float*
     u.step = tmp.raw<int>(1);
     u.done = nullptr;
     const unsigned g = ew_grid(n / 4, h->sm_count);
-    launch_k(adam_tanh_update_kernel, g, 256, 0, st, u);
-    h->launches += 1;
-    CK(cudaStreamSynchronize(st));
+    run_unit(h, st, [&] { launch_k(adam_tanh_update_kernel, g, 256, 0, st, u); });
   });
 }
 
@@ -2448,6 +2469,13 @@ extern "C" int avc_debug_small_profile(unsigned long long* out, int cap) {
   return m;
 }
 #endif
+int avc_unit_timing(avc_handle* h, int32_t reps) {
+  if (!h || reps < 0 || reps > 1000) return AVC_ERR_INVALID;
+  h->unit_reps = reps;
+  h->unit_ms = 0.f;
+  return AVC_OK;
+}
+float avc_unit_last_ms(const avc_handle* h) { return h ? h->unit_ms : -1.f; }
 int64_t avc_kernel_launches(const avc_handle* h) { return h ? h->launches : -1; }
 int32_t avc_launches_per_iter(const avc_handle* h) { return h ? h->launches_per_iter : -1; }
 

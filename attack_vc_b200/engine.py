@@ -385,6 +385,13 @@ class Engine:
             slope, self._stream()))
         return gy, gcond
 
+    def unit_timing(self, reps: int) -> None:
+        """avc_unit_timing: the three HBM-bound unit entry points repeat their kernel `reps` times and time it on the device."""
+        self._check(self._lib.avc_unit_timing(self._h, int(reps)))
+
+    def unit_last_ms(self) -> float:
+        return float(self._lib.avc_unit_last_ms(self._h))
+
     def adam_tanh_step(self, g_adv: Tensor, x: Tensor, w: Tensor, m: Tensor, v: Tensor, eps: float, step: int) -> Tensor:
         adv = torch.empty_like(x)
         self._check(self._lib.avc_adam_tanh_step(self._h, g_adv.data_ptr(), x.data_ptr(), w.data_ptr(), m.data_ptr(),

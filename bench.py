@@ -709,7 +709,7 @@ def main():
             except Exception as e:   # a side measurement must never take the headline down
                 extra[name] = {"error": str(e)[:200]}
         # HBM-bound kernels at a size where the HBM roofline applies (268 MB per tensor, >> L2), through the C-ABI unit
-        # entry points (which synchronise the stream: a few us of host time ride along).  SURVEY §8d bytes per element.
+        # entry points, timed on the device over back-to-back launches.  SURVEY §8d bytes per element.
         try:
             Bn, Tn, Cn = 2048, 256, 128
             gen = torch.Generator(device="cpu").manual_seed(0)
@@ -718,11 +718,16 @@ def main():
             _, stn = eng.instnorm_adain_act_fwd(yn, cn, None, 1, 0.0)
 
             def med_ms(fn, reps=9):
-                fn(); ts = []
-                for _ in range(reps):
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(); fn(); b.record(); torch.cuda.synchronize(dev); ts.append(a.elapsed_time(b))
-                return sorted(ts)[len(ts) // 2]
+                # device time per launch of `reps` launches back to back behind a first run (avc_unit_timing): a single
+                # launch bracketed by events from Python carries ~20 us of host time between the first event and the launch
+                eng.unit_timing(reps)
+                try:
+                    ts = []
+                    for _ in range(3):
+                        fn(); ts.append(eng.unit_last_ms())
+                finally:
+                    eng.unit_timing(0)
+                return sorted(ts)[1]
             nel = Bn * Tn * Cn
             for nm, byt, fn in (("norm_fwd", 8, lambda: eng.instnorm_adain_act_fwd(yn, cn, None, 1, 0.0)),
                                 ("norm_fwd_skip", 12, lambda: eng.instnorm_adain_act_fwd(yn, cn, gn, 1, 0.0)),

@@ -210,6 +210,13 @@ int avc_instnorm_adain_act_bwd(avc_handle* h, const float* g, const float* y, co
 int avc_adam_tanh_step(avc_handle* h, const float* g_adv, const float* x, float* w, float* m,
                        float* v, float* adv, int64_t n, float eps, int32_t step, void* stream);
 
+/* Measurement aid for the three HBM-bound unit entry points above (bench.py's roofline legs): with reps > 0 each
+ * call runs its kernel once and then `reps` more times back to back, timing those with events recorded on `stream` behind the
+ * first run, so no host time sits inside the bracket.  avc_unit_last_ms = device milliseconds per repetition of the last call.
+ * (The Adam step entry point then applies 1 + reps updates: time it on scratch tensors.)  reps = 0 restores single runs. */
+int avc_unit_timing(avc_handle* h, int32_t reps);
+float avc_unit_last_ms(const avc_handle* h);
+
 /* ---- VSMask PredictiveModel (reference models/predictive_model.py:53-110) ------------
  * Own handle: the model is independent of AdaIN-VC.  x is the reference's [B,1,F,T] tensor (contiguous),
  * out [B,1,F',T'] with (F',T') = avc_pm_out_shape(F,T) -- (95,63) for the (80,100) windows of vsmask.py. */

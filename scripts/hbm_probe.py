@@ -13,15 +13,15 @@ peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6550.7
 
 
-def timed(fn, reps=20):
-    for _ in range(3): fn()
-    ts = []
-    for _ in range(reps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ts.sort()
-    return ts[len(ts) // 2]
+def timed(fn, reps=10):
+    eng.unit_timing(reps)
+    try:
+        ts = []
+        for _ in range(3):
+            fn(); ts.append(eng.unit_last_ms())
+    finally:
+        eng.unit_timing(0)
+    return sorted(ts)[1]
 
 
 out = {}
