@@ -89,15 +89,33 @@ struct Arena {
   Arena(SlabPool* p, cudaStream_t st) : pool(p), stream(st), ordered(true) {}
   Arena(const Arena&) = delete;
   Arena& operator=(const Arena&) = delete;
+  // A finished arena can be rewound and bump-allocated again: a caller that repeats the SAME allocation sequence (one
+  // training step after another on the same shapes) gets the same addresses back without a new zero fill of every slab --
+  // at 2-3 GB of step buffers the fills were a tenth of a PredictiveModel step.  Buffers then hold the previous step's
+  // bytes instead of zeros: only for callers whose kernels write everything they read.  A sequence that diverges from the
+  // recorded one simply continues on fresh (zeroed) slabs.
+  size_t replay = 0;
+  bool replaying = false;
+  void rewind() { cur = nullptr; left = 0; replay = 0; replaying = true; }
   float* f(size_t n) {
     const size_t b = (n * sizeof(float) + 255) / 256 * 256;
     if (b > left) {
       const size_t sz = b > kSlab ? (b + kSlab - 1) / kSlab * kSlab : kSlab;
-      void* p = pool ? pool->take(sz) : nullptr;
-      if (!p) CK(cudaMalloc(&p, sz));
-      if (ordered) CK(cudaMemsetAsync(p, 0, sz, stream)); else CK(cudaMemset(p, 0, sz));
-      slabs.emplace_back(p, sz);
-      bytes += sz;
+      void* p = nullptr;
+      if (replaying && replay < slabs.size() && slabs[replay].second == sz) {
+        p = slabs[replay++].first;
+      } else {
+        if (replaying && replay < slabs.size()) {      // diverged: the rest of the recording is of no use
+          for (size_t i = replay; i < slabs.size(); ++i) { if (pool) pool->give(slabs[i].first, slabs[i].second); else cudaFree(slabs[i].first); bytes -= slabs[i].second; }
+          slabs.resize(replay);
+        }
+        p = pool ? pool->take(sz) : nullptr;
+        if (!p) CK(cudaMalloc(&p, sz));
+        if (ordered) CK(cudaMemsetAsync(p, 0, sz, stream)); else CK(cudaMemset(p, 0, sz));
+        slabs.emplace_back(p, sz);
+        bytes += sz;
+        replay = slabs.size();
+      }
       if (b > kSlab) return static_cast<float*>(p);   // dedicated slab, keep the current one
       cur = static_cast<char*>(p);
       left = sz;

@@ -715,9 +715,27 @@ struct avc_pm_handle {
   float* comm = nullptr;
   long long comm_cap = 0;
   int world = 1;
+  // step buffers kept between calls of the same kind and shape (Arena::rewind): the same allocation sequence gets the same
+  // addresses back without zero-filling 2-3 GB of slabs per step (declared after `pool`: destroyed before it)
+  std::unique_ptr<Arena> ws;
+  long long ws_key[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
+
+// kind: 0 forward, 1 train step, 2 trainer step; flags: whatever else changes the allocation sequence
+Arena& pm_workspace(avc_pm_handle* h, cudaStream_t st, int kind, int B, int H, int W, int flags) {
+  static const bool off = getenv("AVC_PM_NO_WS") != nullptr;     // A/B: a fresh zero-filled arena per call
+  const long long key[6] = {kind, B, H, W, flags, (long long)(uintptr_t)st};
+  if (off || !h->ws || memcmp(key, h->ws_key, sizeof key) != 0) {
+    h->ws.reset();
+    h->ws.reset(new Arena(&h->pool, st));
+    memcpy(h->ws_key, key, sizeof key);
+  } else {
+    h->ws->rewind();
+  }
+  return *h->ws;
+}
 
 template <class Fn>
 int pm_guarded(avc_pm_handle* h, Fn&& fn) {
@@ -1468,7 +1486,7 @@ int avc_pm_forward(avc_pm_handle* h, const float* x, float* out, int32_t B, int3
     if (!h->have_weights) fail(AVC_ERR_STATE, "avc_pm_load_weights must be called first");
     if (!x || !out || B <= 0) fail(AVC_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    Arena mem(&h->pool, st);           // zero fills ordered on the caller's stream: no device-wide synchronisation per call
+    Arena& mem = pm_workspace(h, st, 0, B, H, W, (training ? 1 : 0) | (h->world << 8));   // zero fills (first call of a shape) ordered on the caller's stream
     PmActs A;
     pm_shapes(A, B, H, W);
     if (!training) pm_refresh_eval(h, st);
@@ -1496,7 +1514,7 @@ int avc_pm_train_step(avc_pm_handle* h, const float* x, int32_t B, int32_t H, in
       gout[grads[i].name] = const_cast<float*>(grads[i].data);
     }
     auto want = [&](const std::string& k) -> float* { auto it = gout.find(k); return it == gout.end() ? nullptr : it->second; };
-    Arena mem(&h->pool, st);
+    Arena& mem = pm_workspace(h, st, 1, B, H, W, (out ? 1 : 0) | (grad_x ? 2 : 0) | (n_grads << 2) | (h->world << 16));
     PmActs A;
     pm_shapes(A, B, H, W);
     float* nm[7]; float* nv[7];
@@ -1606,7 +1624,7 @@ int avc_pm_trainer_step(avc_pm_trainer* t, const float* source, const float* tar
     const size_t nel = (size_t)a.B * a.F * a.T;
     CK(cudaMemcpyAsync(t->src, source, nel * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(t->tgt, target, nel * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    Arena mem(&h->pool, st);
+    Arena& mem = pm_workspace(h, st, 2, a.B, a.F, a.T, h->world);
     PmActs A;
     pm_shapes(A, a.B, a.F, a.T);
     // model.train(); predicted_perturbation = model(source_mels): running statistics updated in place (:64,92)

@@ -157,6 +157,28 @@ def test_adam_tanh_step_matches_torch_adam(engine, step):
     assert float((eps * wd.tanh()).abs().max()) <= eps
 
 
+def test_unit_timing_repeats_do_not_change_results(engine):
+    """avc_unit_timing (bench.py's HBM roofline legs): the repeated launches are out of place, so the outputs equal a single
+    run bit for bit, and a positive device time per launch comes back."""
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(4, 64, 128, generator=g).cuda(); cond = torch.randn(4, 256, generator=g).cuda()
+    gup = torch.randn(4, 64, 128, generator=g).cuda()
+    o1, s1 = engine.instnorm_adain_act_fwd(y, cond, None, 1, 0.2)
+    gy1, gc1 = engine.instnorm_adain_act_bwd(gup, y, s1, cond, 0.2)
+    engine.unit_timing(4)
+    try:
+        o2, s2 = engine.instnorm_adain_act_fwd(y, cond, None, 1, 0.2)
+        ms_f = engine.unit_last_ms()
+        gy2, gc2 = engine.instnorm_adain_act_bwd(gup, y, s2, cond, 0.2)
+        ms_b = engine.unit_last_ms()
+    finally:
+        engine.unit_timing(0)
+    assert torch.equal(o1, o2) and torch.equal(s1, s2) and torch.equal(gy1, gy2) and torch.equal(gc1, gc2)
+    assert 0.0 < ms_f < 5.0 and 0.0 < ms_b < 5.0
+    with pytest.raises(Exception):
+        engine.unit_timing(-1)
+
+
 TC_CASES = CONV_CASES + [
     (64, 256, 128, 128, 5, 1),     # 130 tiles
     (7, 100, 128, 128, 5, 1),      # tiles straddle utterances

@@ -82,6 +82,29 @@ def test_train_step_gradients(pm, B, F, T):
         assert rel(got["new_stats"][k], v) < 1e-5, k
 
 
+def test_step_buffers_reused_between_calls_do_not_leak(pm):
+    """The handle keeps its step buffers between calls of the same shape without a new zero fill (Arena::rewind): a step must
+    not see anything of the step before it.  x1, then x2, then x1 again on the same handle: first and third answers are equal
+    bit for bit (every reduction is fixed-order); likewise for the two forward modes, and across a change of shape."""
+    P, sd, eng = pm
+    g = torch.Generator().manual_seed(5)
+    x1, x2 = torch.randn(4, 1, 80, 100, generator=g).cuda(), (3.0 * torch.randn(4, 1, 80, 100, generator=g)).cuda()
+    xs = torch.randn(2, 1, 64, 77, generator=g).cuda()
+    a = eng.train_step(x1, want_grad_x=True)
+    eng.train_step(x2, want_grad_x=True)
+    b = eng.train_step(x1, want_grad_x=True)
+    eng.train_step(xs, want_grad_x=True)                     # another shape in between: the recorded sequence diverges
+    c = eng.train_step(x1, want_grad_x=True)
+    for r in (b, c):
+        assert torch.equal(a["out"], r["out"]) and torch.equal(a["loss"], r["loss"]) and torch.equal(a["grad_x"], r["grad_x"])
+        for k, v in a["grads"].items():
+            assert torch.equal(v, r["grads"][k]), k
+    for training in (False, True):
+        o1 = eng.forward(x1, training=training).clone()
+        eng.forward(x2, training=training)
+        assert torch.equal(o1, eng.forward(x1, training=training))
+
+
 def test_errors(pm):
     P, sd, eng = pm
     from attack_vc_b200 import AvcError
