@@ -65,8 +65,33 @@ __device__ __forceinline__ int pm_src(int o, int k, int n_in, int s, int mode) {
   return o * s + k;
 }
 
-template <bool CI1>
+// The shared epilogue of the gather kernels: bias, folded BatchNorm, act' mask, activation, store of 4 channels of one pixel
+__device__ __forceinline__ void pm_conv_store4(const PmConv& p, long long o, int co, const float (&accq)[4], float4 bias, float4 sc, float4 sf) {
+  float v[4] = {fmaf(accq[0] + bias.x, sc.x, sf.x), fmaf(accq[1] + bias.y, sc.y, sf.y),
+                fmaf(accq[2] + bias.z, sc.z, sf.z), fmaf(accq[3] + bias.w, sc.w, sf.w)};
+  const bool vec = (p.Co & 3) == 0 && co + 3 < p.Co;      // one 16-byte store per pixel (the scalar form wrote 4 bytes at a 16-byte stride)
+  float m[4] = {1.f, 1.f, 1.f, 1.f};
+  if (p.dmask) {
+    if (vec) { const float4 d = ld4(p.dmask + o); m[0] = d.x; m[1] = d.y; m[2] = d.z; m[3] = d.w; }
+    else for (int j = 0; j < 4; ++j) if (co + j < p.Co) m[j] = p.dmask[o + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = v[j];
+    if (p.dmask) x *= m[j] > 0.f ? 1.f : p.mslope;
+    if (p.act) x = x > 0.f ? x : x * p.slope;
+    if (p.act == 2) x = tanhf(x);
+    v[j] = x;
+  }
+  if (vec) st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
+  else for (int j = 0; j < 4; ++j) if (co + j < p.Co) p.y[o + j] = v[j];
+}
+
+// MODE: the gather mode as a compile-time constant for the single-input-channel launches (-1: read p.mode) -- with the mode
+// known the source-index function is two or three instructions instead of a three-way branch with an integer division
+template <bool CI1, int MODE = -1>
 __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
+  const int mode = MODE >= 0 ? MODE : p.mode;
   const int co = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const long long pg = (long long)blockIdx.x * blockDim.y + threadIdx.y;
   const int wg = (p.Wo + 3) / 4;
@@ -78,27 +103,54 @@ __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
   float acc[4][4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
-  for (int kh = 0; kh < 3; ++kh) {
-    const int ih = pm_src(oh, kh, p.Hi, p.sh, p.mode);
-    if (ih < 0 || ih >= p.Hi) continue;
-    for (int kw = 0; kw < 3; ++kw) {
-      int iw[4];
+  if (CI1) {
+    // single input channel (the first down block and the dgrad of the last up block): the 12 source columns, the 3 source
+    // rows and the 9 weight vectors are loop constants of the thread -- computed once, then 36 loads and 144 FMAs straight
+    // (the generic loop below recomputed the columns per row and fetched the weights inside it: 125 us for a 131 MB output)
+    int iw[3][4];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        iw[q] = (ow0 + q < p.Wo) ? pm_src(ow0 + q, kw, p.Wi, p.sw, p.mode) : -1;
-        if (iw[q] >= p.Wi) iw[q] = -1;
+        int i = (ow0 + q < p.Wo) ? pm_src(ow0 + q, kw, p.Wi, p.sw, mode) : -1;
+        iw[kw][q] = i >= p.Wi ? -1 : i;
       }
-      const float* wt = p.w + (size_t)(kh * 3 + kw) * p.Ci * p.Cop + co;
-      const float* xr = p.x + ((long long)(b * p.Hi + ih) * p.Wi) * p.Ci;
-      if (CI1) {
-        const float4 w4 = ld4(wt);
+    float4 w4[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w4[k] = ld4(p.w + (size_t)k * p.Cop + co);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = pm_src(oh, kh, p.Hi, p.sh, mode);
+      if (ih < 0 || ih >= p.Hi) continue;
+      const float* xr = p.x + (long long)(b * p.Hi + ih) * p.Wi;
+      float a[3][4];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[kw][q] = iw[kw][q] >= 0 ? __ldg(xr + iw[kw][q]) : 0.f;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4 w = w4[kh * 3 + kw];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float a = iw[q] >= 0 ? xr[iw[q]] : 0.f;
-          acc[q][0] = fmaf(a, w4.x, acc[q][0]); acc[q][1] = fmaf(a, w4.y, acc[q][1]);
-          acc[q][2] = fmaf(a, w4.z, acc[q][2]); acc[q][3] = fmaf(a, w4.w, acc[q][3]);
+          acc[q][0] = fmaf(a[kw][q], w.x, acc[q][0]); acc[q][1] = fmaf(a[kw][q], w.y, acc[q][1]);
+          acc[q][2] = fmaf(a[kw][q], w.z, acc[q][2]); acc[q][3] = fmaf(a[kw][q], w.w, acc[q][3]);
         }
-      } else {
+      }
+    }
+  } else {
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = pm_src(oh, kh, p.Hi, p.sh, mode);
+      if (ih < 0 || ih >= p.Hi) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        int iw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          iw[q] = (ow0 + q < p.Wo) ? pm_src(ow0 + q, kw, p.Wi, p.sw, mode) : -1;
+          if (iw[q] >= p.Wi) iw[q] = -1;
+        }
+        const float* wt = p.w + (size_t)(kh * 3 + kw) * p.Ci * p.Cop + co;
+        const float* xr = p.x + ((long long)(b * p.Hi + ih) * p.Wi) * p.Ci;
         for (int ci = 0; ci < p.Ci; ci += 4) {
           float4 a[4];
 #pragma unroll
@@ -117,31 +169,74 @@ __global__ void __launch_bounds__(256) pm_conv_kernel(const PmConv p) {
       }
     }
   }
-  float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
-  float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
-  float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
+  const float4 bias = p.bias ? ld4(p.bias + co) : f4zero();
+  const float4 sc = p.scale ? ld4(p.scale + co) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 sf = p.shift ? ld4(p.shift + co) : f4zero();
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (ow0 + q >= p.Wo) continue;
-    float v[4] = {fmaf(acc[q][0] + bias.x, sc.x, sf.x), fmaf(acc[q][1] + bias.y, sc.y, sf.y),
-                  fmaf(acc[q][2] + bias.z, sc.z, sf.z), fmaf(acc[q][3] + bias.w, sc.w, sf.w)};
     const long long o = ((long long)(b * p.Ho + oh) * p.Wo + ow0 + q) * p.Co + co;
-    const bool vec = (p.Co & 3) == 0 && co + 3 < p.Co;      // one 16-byte store per pixel (the scalar form wrote 4 bytes at a 16-byte stride)
-    float m[4] = {1.f, 1.f, 1.f, 1.f};
-    if (p.dmask) {
-      if (vec) { const float4 d = ld4(p.dmask + o); m[0] = d.x; m[1] = d.y; m[2] = d.z; m[3] = d.w; }
-      else for (int j = 0; j < 4; ++j) if (co + j < p.Co) m[j] = p.dmask[o + j];
-    }
+    pm_conv_store4(p, o, co, acc[q], bias, sc, sf);
+  }
+}
+
+// Single OUTPUT channel (the last up block: ConvTranspose2d 32 -> 1, stride 2, + tanh).  Eight lanes share a 2 x 2 block of
+// output pixels (2i + a, 2j + c), each lane with four of the input channels: the block reads input pixels (i, j), (i, j-1),
+// (i-1, j), (i-1, j-1) once (coalesced 128-byte pixel reads) and every output meets exactly its own taps (kh = a mod 2, ...):
+//   out(2i,   2j)   = x[i,j] w00 + x[i,j-1] w02 + x[i-1,j] w20 + x[i-1,j-1] w22      out(2i,   2j+1) = x[i,j] w01 + x[i-1,j] w21
+//   out(2i+1, 2j)   = x[i,j] w10 + x[i,j-1] w12                                      out(2i+1, 2j+1) = x[i,j] w11
+// folded over the eight lanes by three shuffles in a fixed order.  The generic kernel gave a pixel to one thread: eight
+// uncoalesced 16-byte loads per tap, 181 us for a 6 MB output; one thread group per output pixel with generic index
+// arithmetic was slower still (593 us: the integer divisions of 12 M threads).
+__global__ void __launch_bounds__(256) pm_convT_co1_kernel(const PmConv p) {
+  const int lane_c = threadIdx.x & 7, grp = threadIdx.x >> 3;            // 32 groups per CTA
+  const int nbi = p.Hi + 1, nbj = p.Wi + 1;                              // blocks: i in [0, Hi], j in [0, Wi]
+  const int ci = lane_c * 4;
+  float4 w[9];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = v[j];
-      if (p.dmask) x *= m[j] > 0.f ? 1.f : p.mslope;
-      if (p.act) x = x > 0.f ? x : x * p.slope;
-      if (p.act == 2) x = tanhf(x);
-      v[j] = x;
+  for (int k = 0; k < 9; ++k) {
+    w[k] = f4zero();
+    for (int c = ci; c < p.Ci; c += 32) {                                // Ci = 32: one trip
+      const float* wt = p.w + ((size_t)k * p.Ci + c) * p.Cop;
+      w[k] = make_float4(__ldg(wt), __ldg(wt + p.Cop), __ldg(wt + 2 * p.Cop), __ldg(wt + 3 * p.Cop));
     }
-    if (vec) st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
-    else for (int j = 0; j < 4; ++j) if (co + j < p.Co) p.y[o + j] = v[j];
+  }
+  const float bias = p.bias ? p.bias[0] : 0.f;
+  const long long nblk = (long long)p.B * nbi * nbj;
+  for (long long q = (long long)blockIdx.x * 32 + grp; q < nblk; q += (long long)gridDim.x * 32) {
+    const int j = (int)(q % nbj);
+    const long long t = q / nbj;
+    const int i = (int)(t % nbi), b = (int)(t / nbi);
+    const float* xb = p.x + (long long)b * p.Hi * p.Wi * p.Ci + ci;
+    const bool i0 = i < p.Hi, i1 = i > 0, j0 = j < p.Wi, j1 = j > 0;
+    const float4 x00 = i0 && j0 ? ld4(xb + ((long long)i * p.Wi + j) * p.Ci) : f4zero();
+    const float4 x01 = i0 && j1 ? ld4(xb + ((long long)i * p.Wi + j - 1) * p.Ci) : f4zero();
+    const float4 x10 = i1 && j0 ? ld4(xb + ((long long)(i - 1) * p.Wi + j) * p.Ci) : f4zero();
+    const float4 x11 = i1 && j1 ? ld4(xb + ((long long)(i - 1) * p.Wi + j - 1) * p.Ci) : f4zero();
+    auto dot = [](float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); };
+    float o[4];
+    o[0] = dot(x00, w[0]) + dot(x01, w[2]) + dot(x10, w[6]) + dot(x11, w[8]);
+    o[1] = dot(x00, w[1]) + dot(x10, w[7]);
+    o[2] = dot(x00, w[3]) + dot(x01, w[5]);
+    o[3] = dot(x00, w[4]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
+      o[k] += __shfl_xor_sync(0xffffffffu, o[k], 2);
+      o[k] += __shfl_xor_sync(0xffffffffu, o[k], 4);
+    }
+    if (lane_c < 4) {                                                    // lane k of the group finishes output k of the block
+      const int oh = 2 * i + (lane_c >> 1), ow = 2 * j + (lane_c & 1);
+      if (oh < p.Ho && ow < p.Wo) {
+        float x = (lane_c == 0 ? o[0] : lane_c == 1 ? o[1] : lane_c == 2 ? o[2] : o[3]) + bias;
+        if (p.scale) x = fmaf(x, p.scale[0], p.shift[0]);
+        const long long e = (long long)(b * p.Ho + oh) * p.Wo + ow;
+        if (p.dmask) x *= p.dmask[e] > 0.f ? 1.f : p.mslope;
+        if (p.act) x = x > 0.f ? x : x * p.slope;
+        if (p.act == 2) x = tanhf(x);
+        p.y[e] = x;
+      }
+    }
   }
 }
 
@@ -280,8 +375,12 @@ __global__ void __launch_bounds__(256) pm_conv_tiled_kernel(const PmConv p) {
 struct PmReduce {
   const float* y; const float* g; long long N; int C;
   const float* scale; const float* shift; const float* mean; const float* rstd; const float* a;   // a: the PReLU slope (device: the trainer's Adam step updates it)
-  int kind;
+  int kind;         // 0: sum y, sum y^2   1: the three sums of the BatchNorm + PReLU backward   2: sum g   3: kind 1's elementwise follow-up, fused (below)
   float* partial;   // [G][3][C]
+  // kind 3: gy = gamma*rstd * (gyn - sums[0]/N - xh * sums[1]/N) written as gy (optional) and / or as the hi / lo operand planes of
+  // the tensor-core dgrad and wgrad (optional), with partial[.][0][c] = sum of gy (the conv bias gradient) -- one pass over y
+  // and g instead of three passes (elementwise, bias reduction, operand split) with gy stored and read back twice
+  const float* sums; float invN; float* gy; float* hi; float* lo;
 };
 __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
   extern __shared__ float4 pm_red[];   // [rowlanes][3][C4]
@@ -292,8 +391,10 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
     const long long per = (p.N + gridDim.x - 1) / gridDim.x;
     const long long lo = (long long)blockIdx.x * per, hi = min(p.N, lo + per);
     float4 sc = f4zero(), sf = f4zero(), mu = f4zero(), rs = f4zero();
-    const float pa = p.kind == 1 ? *p.a : 0.f;
-    if (p.kind == 1) { sc = ld4(p.scale + 4 * cl); sf = ld4(p.shift + 4 * cl); mu = ld4(p.mean + 4 * cl); rs = ld4(p.rstd + 4 * cl); }
+    const float pa = (p.kind == 1 || p.kind == 3) ? *p.a : 0.f;
+    float4 t0 = f4zero(), t1 = f4zero();
+    if (p.kind == 3) { t0 = f4scale(ld4(p.sums + 4 * cl), p.invN); t1 = f4scale(ld4(p.sums + p.C + 4 * cl), p.invN); }
+    if (p.kind == 1 || p.kind == 3) { sc = ld4(p.scale + 4 * cl); sf = ld4(p.shift + 4 * cl); mu = ld4(p.mean + 4 * cl); rs = ld4(p.rstd + 4 * cl); }
     for (long long i = lo + rl; i < hi; i += RL) {
       if (p.kind == 0) {
         const float4 v = ld4(p.y + i * p.C + 4 * cl);
@@ -314,6 +415,28 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
         q0 = f4add(q0, make_float4(o0[0], o0[1], o0[2], o0[3]));
         q1 = f4add(q1, make_float4(o1[0], o1[1], o1[2], o1[3]));
         q2 = f4add(q2, make_float4(o2[0], o2[1], o2[2], o2[3]));
+      } else if (p.kind == 3) {
+        const long long e = i * p.C + 4 * cl;
+        const float4 v = ld4(p.y + e), gz = ld4(p.g + e);
+        const float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {gz.x, gz.y, gz.z, gz.w};
+        const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, f4[4] = {sf.x, sf.y, sf.z, sf.w}, m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w};
+        const float a0[4] = {t0.x, t0.y, t0.z, t0.w}, a1[4] = {t1.x, t1.y, t1.z, t1.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float yn = fmaf(vv[j], s4[j], f4[j]);
+          const float gyn = gg[j] * (yn > 0.f ? 1.f : pa);
+          const float xh = (vv[j] - m4[j]) * r4[j];
+          o[j] = s4[j] * (gyn - a0[j] - xh * a1[j]);     // scale = gamma*rstd
+        }
+        const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+        q0 = f4add(q0, o4);
+        if (p.gy) st4(p.gy + e, o4);
+        if (p.hi) {
+          const float4 oh = make_float4(tf32_hi(o[0]), tf32_hi(o[1]), tf32_hi(o[2]), tf32_hi(o[3]));
+          st4(p.hi + e, oh);
+          st4(p.lo + e, f4sub(o4, oh));
+        }
       } else {
         q0 = f4add(q0, ld4(p.g + i * p.C + 4 * cl));
       }
@@ -332,13 +455,24 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
 
 // stage 2 of the BatchNorm forward statistics: mean / biased variance -> scale, shift, saved mean / rstd,
 // and PyTorch's running-statistics update (momentum 0.1, unbiased variance).
+// fixed-order sum of n floats `stride` apart by ONE WARP: lane j adds elements j, j+32, ... in fp64, then a xor tree.
+// (The stage-2 kernels used to walk up to 1184 partials with one thread: 30-95 us of pure latency each.)
+__device__ __forceinline__ double pm_warp_sum(const float* v, int n, size_t stride) {
+  double s = 0.0;
+  for (int i = threadIdx.x & 31; i < n; i += 32) s += (double)v[(size_t)i * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+// one warp per channel: the G partials of both sums are folded by pm_warp_sum (single-device runs hand the CTA partials of
+// pm_reduce_kernel straight in: no separate stage-2 launch)
 __global__ void pm_bn_finalize_kernel(const float* partial, int G, int C, long long N, const float* gamma, const float* beta,
                                       float* scale, float* shift, float* mean, float* rstd,
                                       const float* run_mean, const float* run_var, float* new_mean, float* new_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int g = 0; g < G; ++g) { s += partial[((size_t)g * 3 + 0) * C + c]; ss += partial[((size_t)g * 3 + 1) * C + c]; }
+  const double s = pm_warp_sum(partial + c, G, (size_t)3 * C), ss = pm_warp_sum(partial + (size_t)C + c, G, (size_t)3 * C);
+  if (threadIdx.x & 31) return;
   const double m = s / (double)N;
   double var = ss / (double)N - m * m;
   if (var < 0.0) var = 0.0;
@@ -353,15 +487,6 @@ __global__ void pm_bn_finalize_kernel(const float* partial, int G, int C, long l
   }
 }
 
-// fixed-order sum of n floats `stride` apart by ONE WARP: lane j adds elements j, j+32, ... in fp64, then a xor tree.
-// (The stage-2 kernels used to walk up to 1184 partials with one thread: 30-95 us of pure latency each.)
-__device__ __forceinline__ double pm_warp_sum(const float* v, int n, size_t stride) {
-  double s = 0.0;
-  for (int i = threadIdx.x & 31; i < n; i += 32) s += (double)v[(size_t)i * stride];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  return s;
-}
 // generic stage 2: out[k][c] = sum_g partial[g][k][c] (fixed order), k < 3; one warp per output, launch 3*C warps
 __global__ void pm_sum_partials_kernel(const float* partial, int G, int C, float* out) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -379,6 +504,30 @@ __global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const
     const float4 v = ld4(y + i * 4), sc = ld4(scale + c), sf = ld4(shift + c);
     float4 o = make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w));
     st4(z + i * 4, act4(o, a));
+  }
+}
+
+// The same, written straight into the NEXT layer's tensor-core operand planes: hi / lo (3xTF32) of prelu(y*scale + shift) with
+// ReflectionPad2d(pad) materialised -- z itself is never stored (it was written once and read once, by the split pass)
+__global__ void __launch_bounds__(256) pm_affine_prelu_split_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                    const float* __restrict__ ap, float* __restrict__ hi, float* __restrict__ lo,
+                                                                    int B, int H, int W, int C, int pad) {
+  const float a = *ap;
+  const int C4 = C >> 2, Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const long long n4 = (long long)B * Hp * Wp * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) << 2;
+    long long t = i / C4;
+    const int wp = (int)(t % Wp); t /= Wp;
+    const int hp = (int)(t % Hp), b = (int)(t / Hp);
+    int w = wp - pad, hh = hp - pad;
+    w = w < 0 ? -w : w; if (w >= W) w = 2 * (W - 1) - w;
+    hh = hh < 0 ? -hh : hh; if (hh >= H) hh = 2 * (H - 1) - hh;
+    const float4 v = ld4(y + (((long long)b * H + hh) * W + w) * C + c), sc = ld4(scale + c), sf = ld4(shift + c);
+    const float4 z = act4(make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w)), a);
+    const float4 zh = make_float4(tf32_hi(z.x), tf32_hi(z.y), tf32_hi(z.z), tf32_hi(z.w));
+    st4(hi + i * 4, zh);
+    st4(lo + i * 4, f4sub(z, zh));
   }
 }
 
@@ -573,17 +722,58 @@ __global__ void __launch_bounds__(256) pm_wgrad_kernel(const PmWgrad p) {
   }
 }
 // gw_out (PyTorch layout) = sum_s partial[s]; down: out[co][ci][kh][kw]; up: out[ci][co][kh][kw]
-__global__ void pm_wgrad_final_kernel(const float* partial, int S, int Ci, int Co, int Cop, int up, float* out) {
+// SL split lanes per output (blockDim = 32 outputs x SL): lane j adds partials j, j + SL, ... in fp64, the SL sums meet in
+// shared memory in a fixed order.  With one thread per output the 138 splits of the 32 -> 64 layer were 138 dependent-latency
+// loads in a row on 18 k threads (66 us for 10 MB).
+template <int SL>
+__global__ void __launch_bounds__(256) pm_wgrad_final_kernel(const float* partial, int S, int Ci, int Co, int Cop, int up, float* out) {
+  constexpr int OPB = 256 / SL;                      // outputs per CTA
+  __shared__ double red[SL][OPB + 1];
   const long long n = 9LL * Ci * Co;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % Co);
-    long long t = i / Co;
+  const int ol = threadIdx.x % OPB, sl = threadIdx.x / OPB;
+  for (long long base = (long long)blockIdx.x * OPB; base < n; base += (long long)gridDim.x * OPB) {
+    const long long i = base + ol;
+    const bool ok = i < n;
+    const int co = ok ? (int)(i % Co) : 0;
+    const long long t = ok ? i / Co : 0;
     const int ci = (int)(t % Ci), tap = (int)(t / Ci);
+    const float* src = partial + ((size_t)tap * Ci + ci) * Cop + co;
+    const size_t stride = (size_t)9 * Ci * Cop;
     double s = 0.0;
-    for (int k = 0; k < S; ++k) s += partial[(((size_t)k * 9 + tap) * Ci + ci) * Cop + co];
-    const long long o = up ? ((long long)ci * Co + co) * 9 + tap : ((long long)co * Ci + ci) * 9 + tap;
-    out[o] = (float)s;
+    if (ok) {
+      int k = sl;
+      for (; k + 3 * SL < S; k += 4 * SL) {          // four independent loads in flight
+        const float a = src[(size_t)k * stride], b = src[(size_t)(k + SL) * stride], c = src[(size_t)(k + 2 * SL) * stride], d = src[(size_t)(k + 3 * SL) * stride];
+        s += (double)a; s += (double)b; s += (double)c; s += (double)d;
+      }
+      for (; k < S; k += SL) s += (double)src[(size_t)k * stride];
+    }
+    if (SL > 1) {
+      red[sl][ol] = s;
+      __syncthreads();
+      if (sl == 0) {
+#pragma unroll
+        for (int j = 1; j < SL; ++j) s += red[j][ol];
+      }
+    }
+    if (ok && sl == 0) {
+      const long long o = up ? ((long long)ci * Co + co) * 9 + tap : ((long long)co * Ci + ci) * 9 + tap;
+      out[o] = (float)s;
+    }
+    if (SL > 1) __syncthreads();
   }
+}
+void launch_pm_wgrad_final(const float* partial, int S, int Ci, int Co, int Cop, int up, float* out, int sm_count, cudaStream_t st) {
+  const long long n = 9LL * Ci * Co;
+  // enough split lanes per output to put ~300 k threads on the machine, no more than the splits there are
+  const int sl = (S >= 16 && n * 4 <= 300000) ? 8 : (S >= 8 && n * 2 <= 300000) ? 4 : (S >= 4 && n <= 300000) ? 2 : 1;
+  const int opb = 256 / sl;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n + opb - 1) / opb, (long long)sm_count * 16));
+  if (sl == 8) pm_wgrad_final_kernel<8><<<grid, 256, 0, st>>>(partial, S, Ci, Co, Cop, up, out);
+  else if (sl == 4) pm_wgrad_final_kernel<4><<<grid, 256, 0, st>>>(partial, S, Ci, Co, Cop, up, out);
+  else if (sl == 2) pm_wgrad_final_kernel<2><<<grid, 256, 0, st>>>(partial, S, Ci, Co, Cop, up, out);
+  else pm_wgrad_final_kernel<1><<<grid, 256, 0, st>>>(partial, S, Ci, Co, Cop, up, out);
+  CK(cudaGetLastError());
 }
 
 // ---- weight gradient of the two single-channel ends of the model ----------------------------------------------------
@@ -607,27 +797,40 @@ __global__ void __launch_bounds__(256) pm_wgrad_c1_kernel(const PmWgradC1 p) {
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = f4zero();
   const unsigned Np = (unsigned)N;                 // < 2^31 pixels: 32-bit index arithmetic (the 64-bit divisions dominated the loop)
-  for (unsigned i = blockIdx.x * PL + pl; i < Np; i += gridDim.x * PL) {
-    const unsigned r = i / (unsigned)p.Wb;
-    const int wb = (int)(i - r * (unsigned)p.Wb);
-    const unsigned bq = r / (unsigned)p.Hb;
-    const int hb = (int)(r - bq * (unsigned)p.Hb), b = (int)bq;
-    const float4 v = ld4(p.V + (long long)i * p.C + 4 * cl);
-    const float* sp = p.S + (long long)b * p.Hs * p.Ws;
-    int wsv[3];
+  // four pixels per trip: their 16-byte loads of V and 36 scalar loads of S are all issued before the first FMA (one pixel per
+  // trip left 16 KB in flight per SM: 1.0-1.4 TB/s on a 131 MB tensor)
+  const unsigned stride = gridDim.x * PL;
+  for (unsigned i0 = blockIdx.x * PL + pl; i0 < Np; i0 += 4 * stride) {
+    float4 v[4];
+    float sv[4][9];
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) wsv[kw] = p.up ? 2 * wb + kw : pm_src(wb, kw, p.Ws, p.sw, PM_REFLECT);
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = i0 + u * stride;
+      const bool in = i < Np;
+      const unsigned ii = in ? i : 0u;
+      const unsigned r = ii / (unsigned)p.Wb;
+      const int wb = (int)(ii - r * (unsigned)p.Wb);
+      const unsigned bq = r / (unsigned)p.Hb;
+      const int hb = (int)(r - bq * (unsigned)p.Hb), b = (int)bq;
+      v[u] = in ? ld4(p.V + (long long)ii * p.C + 4 * cl) : f4zero();
+      const float* sp = p.S + (long long)b * p.Hs * p.Ws;
+      int wsv[3];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hs = p.up ? 2 * hb + kh : pm_src(hb, kh, p.Hs, p.sh, PM_REFLECT);
+      for (int kw = 0; kw < 3; ++kw) wsv[kw] = p.up ? 2 * wb + kw : pm_src(wb, kw, p.Ws, p.sw, PM_REFLECT);
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ws = wsv[kw];
-        const float sv = sp[hs * p.Ws + ws];
-        float4& a = acc[kh * 3 + kw];
-        a.x = fmaf(v.x, sv, a.x); a.y = fmaf(v.y, sv, a.y); a.z = fmaf(v.z, sv, a.z); a.w = fmaf(v.w, sv, a.w);
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hs = p.up ? 2 * hb + kh : pm_src(hb, kh, p.Hs, p.sh, PM_REFLECT);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) sv[u][kh * 3 + kw] = __ldg(sp + hs * p.Ws + wsv[kw]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float4& a = acc[t];
+        a.x = fmaf(v[u].x, sv[u][t], a.x); a.y = fmaf(v[u].y, sv[u][t], a.y); a.z = fmaf(v[u].z, sv[u][t], a.z); a.w = fmaf(v[u].w, sv[u][t], a.w);
+      }
   }
   // lanes of a warp = 4 pixels x 8 channel lanes: fold the pixel lanes, then the 8 warps (fixed order)
 #pragma unroll
@@ -846,11 +1049,24 @@ void launch_pm_conv(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
     h->launches++;
     return;
   }
+  static const bool no_co1 = getenv("AVC_PM_NO_CO1") != nullptr;
+  if (!no_co1 && c.Co == 1 && c.Ci == 32 && c.mode == PM_TRANSPOSED && c.sh == 2 && c.sw == 2 && c.Ho <= 2 * c.Hi + 1 && c.Wo <= 2 * c.Wi + 1) {
+    const long long nblk = (long long)c.B * (c.Hi + 1) * (c.Wi + 1);
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((nblk + 31) / 32, (long long)h->sm_count * 32));
+    pm_convT_co1_kernel<<<grid, 256, 0, st>>>(c);
+    CK(cudaGetLastError());
+    h->launches++;
+    return;
+  }
   const int lanes = std::min(c.Cop / 4, 32);
   dim3 block(lanes, 256 / lanes);
   const long long npg = (long long)c.B * c.Ho * ((c.Wo + 3) / 4);
   dim3 grid((unsigned)((npg + block.y - 1) / block.y), (unsigned)((c.Cop / 4 + lanes - 1) / lanes));
-  if (c.Ci == 1) pm_conv_kernel<true><<<grid, block, 0, st>>>(c);
+  if (c.Ci == 1) {
+    if (c.mode == PM_REFLECT) pm_conv_kernel<true, PM_REFLECT><<<grid, block, 0, st>>>(c);
+    else if (c.mode == PM_PLAIN) pm_conv_kernel<true, PM_PLAIN><<<grid, block, 0, st>>>(c);
+    else pm_conv_kernel<true><<<grid, block, 0, st>>>(c);
+  }
   else {
     if (c.Ci % 4) fail(AVC_ERR_INVALID, "predictive conv: c_in %d not a multiple of 4", c.Ci);
     pm_conv_kernel<false><<<grid, block, 0, st>>>(c);
@@ -966,6 +1182,8 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
   pm_refresh_weight_planes(h, st);
   A.x = x;
   const float* in = x;
+  static const bool no_fuse = getenv("AVC_PM_NO_FUSE") != nullptr;     // A/B: activation and operand split as two passes
+  Planes ready;                                                          // operand planes of `in` made by the producing layer
   for (int l = 0; l < 7; ++l) {
     const DownSpec& s = kDown[l];
     const DownW& w = h->down[l];
@@ -976,7 +1194,7 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.w = w.w; c.Ho = A.H[l + 1]; c.Wo = A.W[l + 1]; c.Co = s.co; c.Cop = pad4(s.co);
     c.B = A.B; c.mode = PM_REFLECT; c.sh = s.sh; c.sw = s.sw;
     if (pm_tc_layer(s.ci, s.co) && pm_tc_site(1)) {
-      A.zin[l] = pm_split(h, mem, in, A.B, A.H[l], A.W[l], s.ci, 1, st);
+      A.zin[l] = ready.h ? ready : pm_split(h, mem, in, A.B, A.H[l], A.W[l], s.ci, 1, st);
       c.xh = A.zin[l].h; c.xl = A.zin[l].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
     }
     if (!training) {
@@ -991,23 +1209,34 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
       r.y = A.y[l]; r.N = npix; r.C = s.co; r.kind = 0;
       r.partial = mem.f((size_t)reduce_slices(npix, s.co) * 3 * s.co);
       int G = launch_pm_reduce(h, r, st);
-      float* sums = h->world > 1 ? h->comm : mem.f(3 * (size_t)s.co);
-      pm_sum_partials_kernel<<<(3 * s.co * 32 + 255) / 256, 256, 0, st>>>(r.partial, G, s.co, sums);
-      CK(cudaGetLastError());
-      h->launches++;
-      const float* part = sums;
+      const float* part = r.partial;
       long long n_stat = npix;
-      G = 1;
       if (h->world > 1) {
         // one BatchNorm over the GLOBAL batch (a single-device batch of world x B windows): sum, sum of squares across ranks
+        pm_sum_partials_kernel<<<(3 * s.co * 32 + 255) / 256, 256, 0, st>>>(r.partial, G, s.co, h->comm);
+        CK(cudaGetLastError());
+        h->launches++;
         pm_allreduce(h, 3LL * s.co, st);
+        part = h->comm; G = 1;
         n_stat = npix * h->world;
       }
-      pm_bn_finalize_kernel<<<(s.co + 127) / 128, 128, 0, st>>>(part, G, s.co, n_stat, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
-                                                               A.rstd[l], w.rmean, w.rvar, new_mean ? new_mean[l] : nullptr, new_var ? new_var[l] : nullptr);
+      pm_bn_finalize_kernel<<<(s.co * 32 + 255) / 256, 256, 0, st>>>(part, G, s.co, n_stat, w.gamma, w.beta, A.scale[l], A.shift[l], A.mean[l],
+                                                                  A.rstd[l], w.rmean, w.rvar, new_mean ? new_mean[l] : nullptr, new_var ? new_var[l] : nullptr);
       CK(cudaGetLastError());
-      const long long n4 = npix * s.co / 4;
-      pm_affine_prelu_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, A.z[l], n4, s.co);
+      // the consumer of z[l]: the next down block (reflect-padded planes) or the first up block.  When it runs on the tensor
+      // cores (and so does every wgrad, which otherwise reads z), the activation is written as operand planes directly
+      const bool next_tc = l < 6 ? pm_tc_layer(kDown[l + 1].ci, kDown[l + 1].co) && pm_tc_site(1) : pm_tc_layer(kUp[0].ci, kUp[0].co) && pm_tc_site(2);
+      ready = Planes();
+      if (next_tc && pm_tc_site(16) && !no_fuse) {
+        const int pad = l < 6 ? 1 : 0;
+        const size_t n = (size_t)A.B * (A.H[l + 1] + 2 * pad) * (A.W[l + 1] + 2 * pad) * s.co;
+        ready.h = mem.f(n); ready.l = mem.f(n);
+        pm_affine_prelu_split_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, ready.h, ready.l,
+                                                                                              A.B, A.H[l + 1], A.W[l + 1], s.co, pad);
+      } else {
+        const long long n4 = npix * s.co / 4;
+        pm_affine_prelu_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, A.z[l], n4, s.co);
+      }
       CK(cudaGetLastError());
       h->launches += 2;
     }
@@ -1023,7 +1252,7 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.w = w.w; c.bias = w.bias; c.y = A.u[i]; c.Ho = A.Hu[i + 1]; c.Wo = A.Wu[i + 1]; c.Co = s.co; c.Cop = pad4(s.co);
     c.B = A.B; c.mode = PM_TRANSPOSED; c.sh = 2; c.sw = 2; c.slope = 0.2f; c.act = i == 4 ? 2 : 1;
     if (pm_tc_layer(s.ci, s.co) && pm_tc_site(2)) {
-      A.uin[i] = pm_split(h, mem, in, A.B, A.Hu[i], A.Wu[i], s.ci, 0, st);
+      A.uin[i] = (i == 0 && ready.h) ? ready : pm_split(h, mem, in, A.B, A.Hu[i], A.Wu[i], s.ci, 0, st);
       c.xh = A.uin[i].h; c.xl = A.uin[i].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
     }
     launch_pm_conv(h, c, st);
@@ -1060,8 +1289,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       p.partial = mem.f((size_t)S * 9 * Ci * p.Cop);
       const WtOperand Aop{ah, al, Ci, Wap, Hap, B, up ? 1 : sw, up ? 1 : sh}, Gop{gh, gl, Co, Wg, Hg, B, up ? 2 : 1, up ? 2 : 1};
       launch_wgrad_tc(Aop, Gop, p, S, st);
-      pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(p.partial, S, Ci, Co, p.Cop, up, dst);
-      CK(cudaGetLastError());
+      launch_pm_wgrad_final(p.partial, S, Ci, Co, p.Cop, up, dst, h->sm_count, st);
       h->launches += 2;
       return;
     }
@@ -1090,8 +1318,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     dim3 grid(S, (Ci + kWgT - 1) / kWgT, 9 * ((q.Cop + kWgT - 1) / kWgT));
     pm_wgrad_kernel<<<grid, 256, 0, st>>>(q);
     CK(cudaGetLastError());
-    pm_wgrad_final_kernel<<<ew_grid(9LL * Ci * Co, h->sm_count), 256, 0, st>>>(q.partial, S, Ci, Co, q.Cop, up, dst);
-    CK(cudaGetLastError());
+    launch_pm_wgrad_final(q.partial, S, Ci, Co, q.Cop, up, dst, h->sm_count, st);
     h->launches += 2;
   };
   auto bias_grad = [&](const float* G, long long N, int C, float* dst) {
@@ -1167,16 +1394,41 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       pm_sum_n_kernel<<<1, 32, 0, st>>>(sums + 2 * (size_t)s.co, s.co, d);
       CK(cudaGetLastError());
     }
-    float* gy = mem.f((size_t)npix * s.co);
-    const long long n4 = npix * s.co / 4;
-    pm_bn_bwd_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], g, A.scale[l], A.shift[l], A.mean[l], A.rstd[l], gsums, w.a_dev,
-                                                            1.f / (float)n_stat, gy, n4, s.co);
-    CK(cudaGetLastError());
-    h->launches += 2;
-    bias_grad(gy, npix, s.co, want(p + "1.bias"));
-    const float* xin = l > 0 ? A.z[l - 1] : A.x;
+    static const bool no_fuse = getenv("AVC_PM_NO_FUSE") != nullptr;     // A/B: elementwise pass, bias reduction and operand split as three passes
+    const bool tc = pm_tc_layer(s.ci, s.co);
+    float* gy = nullptr;
     Planes gp;
-    if (pm_tc_layer(s.ci, s.co)) gp = pm_split(h, mem, gy, B, A.H[l + 1], A.W[l + 1], s.co, 0, st);
+    if (!no_fuse) {
+      // one pass over y and g: gy as the operand planes of the tensor-core dgrad / wgrad (and as a tensor only where a
+      // CUDA-core consumer remains: the single-channel first block, A/B switches), the bias gradient as per-CTA partial sums
+      const bool need_gy = !tc || !pm_tc_site(16) || !pm_tc_site(8);
+      if (need_gy) gy = mem.f((size_t)npix * s.co);
+      if (tc) { gp.h = mem.f((size_t)npix * s.co); gp.l = mem.f((size_t)npix * s.co); }
+      PmReduce f{};
+      f.y = A.y[l]; f.g = g; f.N = npix; f.C = s.co; f.kind = 3;
+      f.scale = A.scale[l]; f.shift = A.shift[l]; f.mean = A.mean[l]; f.rstd = A.rstd[l]; f.a = w.a_dev;
+      f.sums = gsums; f.invN = 1.f / (float)n_stat; f.gy = gy; f.hi = gp.h; f.lo = gp.l;
+      f.partial = mem.f((size_t)reduce_slices(npix, s.co) * 3 * s.co);
+      const int Gf = launch_pm_reduce(h, f, st);
+      if (float* d = want(p + "1.bias")) {
+        float* s3 = mem.f(3 * (size_t)s.co);
+        pm_sum_partials_kernel<<<(3 * s.co * 32 + 255) / 256, 256, 0, st>>>(f.partial, Gf, s.co, s3);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(d, s3, s.co * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        h->launches++;
+      }
+    } else {
+      gy = mem.f((size_t)npix * s.co);
+      const long long n4 = npix * s.co / 4;
+      pm_bn_bwd_kernel<<<ew_grid(n4, h->sm_count), 256, 0, st>>>(A.y[l], g, A.scale[l], A.shift[l], A.mean[l], A.rstd[l], gsums, w.a_dev,
+                                                              1.f / (float)n_stat, gy, n4, s.co);
+      CK(cudaGetLastError());
+      h->launches += 1;
+      bias_grad(gy, npix, s.co, want(p + "1.bias"));
+      if (tc) gp = pm_split(h, mem, gy, B, A.H[l + 1], A.W[l + 1], s.co, 0, st);
+    }
+    h->launches += 1;
+    const float* xin = l > 0 ? A.z[l - 1] : A.x;
     wgrad(xin, A.H[l], A.W[l], s.ci, gy, A.H[l + 1], A.W[l + 1], s.co, A.H[l + 1], A.W[l + 1], 0, s.sh, s.sw, want(p + "1.weight"), A.zin[l], gp);
     if (l == 0 && !grad_x) break;
     // dgrad on the padded coordinates, then fold the reflect padding back
