@@ -9,7 +9,8 @@
 //       SWIZZLE_128B exactly as cp.async.bulk.tensor writes them -- no thread touches an operand;
 //   transposed convolutions (ConvTranspose2d forward, Conv2d dgrad) run one launch per output residue class
 //       (oh mod s, ow mod s): a class meets only its own taps, so nothing is multiplied through structural zeros.
-// Precision: 3xTF32 (hi / lo planes of activations and weights).  The tensor core accumulates fp32 with TRUNCATION (about
+// Precision: 3xTF32 (hi / lo planes of activations and weights), or with C2Args.pair the hi planes plus bf16 pair planes
+// (two MMAs per k-step).  The tensor core accumulates fp32 with TRUNCATION (about
 // -8e-8 relative per accumulate, scripts/tc_probe.py): left alone over the 864 MMAs of a 256-channel 3x3 conv that is a
 // systematic 4e-5, enough to move PReLU units across their kink and the gradients by 5e-3.  So accumulation is chunked as
 // in conv_tc.cuh: one pipeline stage (12 MMAs) per TMEM buffer, two buffers; the epilogue warps add every finished chunk
@@ -50,6 +51,11 @@ struct C2Args {
   // ksplit CTAs share a tile, each takes a contiguous range of the (tap, K block) stages and stores its raw sums to
   // part + ks * part_stride (indexed like y); c2_finish_kernel adds them in order and applies the epilogue.
   int ksplit; float* part; long long part_stride;
+  // pair = 1: the "lo" tensor maps address bf16 PAIR planes (wgrad_tc.cuh st_pair4) and a k-step is TWO MMAs,
+  // kind::tf32 X_hi W_hi + kind::f16 (K = 16) [x_lo | x_hi] . [w_hi | w_lo], instead of three TF32 MMAs.  At M = N = 128 every
+  // MMA reads 8 KB of operands from shared memory (64 clk at 128 B/clk, 87 measured next to the TMA writes): the MMA count is
+  // the kernel's clock.  Error of the bf16 cross terms: 2^-9 of a 2^-11 term, unbiased (the same split conv_tc.cuh uses).
+  int pair;
 };
 
 // K-major SWIZZLE_128B operand: rows of 128 B (32 tf32), 8-row groups SBO = 1024 B apart
@@ -145,6 +151,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
       const int n0 = (wq % n_nt) * 128;
       const int N = min(128, (p.Cop - n0 + 15) & ~15);              // MMA N: multiple of 16
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // BF16 x BF16 -> fp32, K = 16
       const int it_lo = ks * n_stage / ksplit, it_hi = (ks + 1) * n_stage / ksplit;
       for (int it = it_lo; it < it_hi; ++it, ++chunk) {
         const uint32_t buf = chunk & 1;
@@ -166,8 +173,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
             const uint64_t dWh = c2_desc(base + 2 * kC2Plane + o), dWl = c2_desc(base + 3 * kC2Plane + o);
             tc_mma_tf32(d_tmem, dXh, dWh, idesc, acc);
             acc = 1;
-            tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
-            tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+            if (p.pair) {
+              tc_mma_bf16(d_tmem, dXl, dWl, idesc16);               // x_lo w_hi + x_hi w_lo
+            } else {
+              tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
+              tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+            }
           }
           tc_commit(empty(s));
           tc_commit(acc_full0 + 8 * buf);
@@ -363,12 +374,19 @@ inline void c2_pick_boxes(C2Args& p) {
   p.nw = (p.Wb + p.bw - 1) / p.bw; p.nh = (p.Hb + p.bh - 1) / p.bh; p.nb = (p.B + p.bb - 1) / p.bb;
 }
 
-inline void c2_init_attributes() {
+// static, not inline: see wt_init_attributes (wgrad_tc.cuh)
+static void c2_init_attributes() {
+  static bool done[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return;
   CK(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2_smem_bytes()));
+  if (dev >= 0 && dev < 64) done[dev] = true;
 }
 
 // X: activation planes (es_w / es_h = the gather stride); Wh / Wl: weight planes [9][rows >= Cop][Kp]
-inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, C2Args p, int sm_count, cudaStream_t st, int w_taps = 9) {
+static void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* Wl, int Kp, int w_rows, C2Args p, int sm_count, cudaStream_t st, int w_taps = 9) {
+  c2_init_attributes();
   p.box_n = std::min(128, (p.Cop + 31) / 32 * 32);
   const CUtensorMap tXh = c2_act_map(X.hi, X, p.bw, p.bh, p.bb), tXl = c2_act_map(X.lo, X, p.bw, p.bh, p.bb);
   const CUtensorMap tWh = c2_weight_map(Wh, Kp, w_rows, p.box_n, w_taps), tWl = c2_weight_map(Wl, Kp, w_rows, p.box_n, w_taps);
@@ -381,7 +399,7 @@ inline void launch_conv2d_tc(const WtOperand& X, const float* Wh, const float* W
 inline int c2_tiles(const C2Args& p) { return p.nw * p.nh * p.nb * ((p.Cop + 127) / 128); }
 inline int c2_stages(const C2Args& p) { return p.n_taps * ((p.Ci + 31) / 32); }
 
-inline void launch_c2_finish(const C2Args& p, int sm_count, cudaStream_t st) {
+static void launch_c2_finish(const C2Args& p, int sm_count, cudaStream_t st) {
   const long long n4 = (long long)p.B * p.Ho * p.Wo * p.Co / 4;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)sm_count * 8));
   c2_finish_kernel<<<grid, 256, 0, st>>>(p, n4);

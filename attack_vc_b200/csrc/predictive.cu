@@ -46,6 +46,7 @@ struct PmConv {
   // tensor-core path (conv2d_tc.cuh), taken when the caller provides the operand planes:
   const float* xh; const float* xl;     // hi / lo planes of x; for PM_REFLECT of the reflect-padded x [B,Hi+2,Wi+2,Ci]
   const float* wkh; const float* wkl;   // hi / lo planes of the K-major weight image [9][Co][Ci]
+  const float* xp; const float* wkp;    // bf16 pair planes of both (wgrad_tc.cuh st_pair4): with them the two cross terms are ONE kind::f16 MMA
   const float* slope_ptr;               // PReLU slope on the device (overrides slope)
 };
 
@@ -380,7 +381,7 @@ struct PmReduce {
   // kind 3: gy = gamma*rstd * (gyn - sums[0]/N - xh * sums[1]/N) written as gy (optional) and / or as the hi / lo operand planes of
   // the tensor-core dgrad and wgrad (optional), with partial[.][0][c] = sum of gy (the conv bias gradient) -- one pass over y
   // and g instead of three passes (elementwise, bias reduction, operand split) with gy stored and read back twice
-  const float* sums; float invN; float* gy; float* hi; float* lo;
+  const float* sums; float invN; float* gy; float* hi; float* lo; float* pair;
 };
 __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
   extern __shared__ float4 pm_red[];   // [rowlanes][3][C4]
@@ -434,8 +435,10 @@ __global__ void __launch_bounds__(256) pm_reduce_kernel(const PmReduce p) {
         if (p.gy) st4(p.gy + e, o4);
         if (p.hi) {
           const float4 oh = make_float4(tf32_hi(o[0]), tf32_hi(o[1]), tf32_hi(o[2]), tf32_hi(o[3]));
+          const float4 ol = f4sub(o4, oh);
           st4(p.hi + e, oh);
-          st4(p.lo + e, f4sub(o4, oh));
+          st4(p.lo + e, ol);
+          if (p.pair) st_pair4(p.pair, e, oh, ol, false);
         }
       } else {
         q0 = f4add(q0, ld4(p.g + i * p.C + 4 * cl));
@@ -511,7 +514,7 @@ __global__ void pm_affine_prelu_kernel(const float* y, const float* scale, const
 // ReflectionPad2d(pad) materialised -- z itself is never stored (it was written once and read once, by the split pass)
 __global__ void __launch_bounds__(256) pm_affine_prelu_split_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                                                                     const float* __restrict__ ap, float* __restrict__ hi, float* __restrict__ lo,
-                                                                    int B, int H, int W, int C, int pad) {
+                                                                    float* __restrict__ pair, int B, int H, int W, int C, int pad) {
   const float a = *ap;
   const int C4 = C >> 2, Wp = W + 2 * pad, Hp = H + 2 * pad;
   const long long n4 = (long long)B * Hp * Wp * C4;
@@ -526,8 +529,10 @@ __global__ void __launch_bounds__(256) pm_affine_prelu_split_kernel(const float*
     const float4 v = ld4(y + (((long long)b * H + hh) * W + w) * C + c), sc = ld4(scale + c), sf = ld4(shift + c);
     const float4 z = act4(make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w)), a);
     const float4 zh = make_float4(tf32_hi(z.x), tf32_hi(z.y), tf32_hi(z.z), tf32_hi(z.w));
+    const float4 zl = f4sub(z, zh);
     st4(hi + i * 4, zh);
-    st4(lo + i * 4, f4sub(z, zh));
+    st4(lo + i * 4, zl);
+    if (pair) st_pair4(pair, i * 4, zh, zl, false);
   }
 }
 
@@ -871,6 +876,7 @@ int pad4(int c) { return (c + 3) / 4 * 4; }
 struct DownW {
   float *w = nullptr, *wt = nullptr;    // [9][ci][cop], transposed [9][co][cip]
   float *w_h = nullptr, *w_l = nullptr, *wt_h = nullptr, *wt_l = nullptr;   // their hi / lo planes (3xTF32 operands of the tensor-core kernels)
+  float *w_p = nullptr, *wt_p = nullptr;                                     // and bf16 pair planes (weight order)
   float *bias = nullptr, *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr;
   float *escale = nullptr, *eshift = nullptr;   // folded eval BatchNorm (+ conv bias)
   float a = 0.25f;          // host copy for the eval conv epilogue (refreshed from a_dev after training steps)
@@ -878,7 +884,7 @@ struct DownW {
 };
 struct UpW {
   float *w = nullptr, *wt = nullptr, *bias = nullptr;
-  float *w_h = nullptr, *w_l = nullptr, *wt_h = nullptr, *wt_l = nullptr;
+  float *w_h = nullptr, *w_l = nullptr, *wt_h = nullptr, *wt_l = nullptr, *w_p = nullptr, *wt_p = nullptr;
 };
 
 }  // namespace
@@ -959,6 +965,13 @@ bool pm_tc_enabled() {
   static const bool off = getenv("AVC_PM_NO_TC") != nullptr;
   return !off;
 }
+bool pm_pair_enabled() {
+  // Opt-in (AVC_PM_PAIR=1).  Measured on B200, 256 windows: conv2d_tc 2016 -> 1928 us per step, the third operand plane costs
+  // 57 us in the producers, step 4.67 -> 4.54 ms (3 %) -- the convs are bound by operand delivery (64 KB per 12-MMA stage
+  // through L2), not by the MMA count -- and one gradient case (3 x 64 x 77) leaves the 1e-3 tolerance.  Default: 3xTF32.
+  static const bool on = getenv("AVC_PM_PAIR") != nullptr;
+  return on;
+}
 bool pm_tc_layer(int ci, int co) { return pm_tc_enabled() && ci % 32 == 0 && co % 32 == 0; }
 // A/B switch per call site (AVC_PM_TC_MASK): 1 forward down, 2 forward up, 4 dgrad of the transposed convs, 8 dgrad of the down convs, 16 wgrad
 bool pm_tc_site(int bit) {
@@ -1014,8 +1027,15 @@ void launch_pm_conv_tc(avc_pm_handle* h, const PmConv& c, cudaStream_t st) {
     }
     for (Cls& q : cls) { q.a.ksplit = ksplit; q.a.part = h->c2_part; q.a.part_stride = (long long)n; }
   }
+  const bool pair = c.xp && c.wkp && c.Ci % 8 == 0 && pm_pair_enabled();
   for (const Cls& q : cls) {
-    launch_conv2d_tc(q.X, c.wkh, c.wkl, c.Ci, c.Cop, q.a, h->sm_count, st);
+    if (pair) {
+      C2Args a2 = q.a; a2.pair = 1;
+      WtOperand X2 = q.X; X2.lo = c.xp;
+      launch_conv2d_tc(X2, c.wkh, c.wkp, c.Ci, c.Cop, a2, h->sm_count, st);
+    } else {
+      launch_conv2d_tc(q.X, c.wkh, c.wkl, c.Ci, c.Cop, q.a, h->sm_count, st);
+    }
     h->launches++;
   }
   if (ksplit > 1) {
@@ -1114,14 +1134,16 @@ struct HostSD {
   }
 };
 
-struct Planes { float* h = nullptr; float* l = nullptr; };
+struct Planes { float* h = nullptr; float* l = nullptr; float* p = nullptr; };   // hi, lo (wgrad), bf16 pair (convs)
+
 
 // hi / lo planes of an NHWC tensor for the 3xTF32 tensor-core kernels, optionally with ReflectionPad2d(pad) materialised
 Planes pm_split(avc_pm_handle* h, Arena& mem, const float* src, int B, int H, int W, int C, int pad, cudaStream_t st) {
   Planes p;
   const size_t n = (size_t)B * (H + 2 * pad) * (W + 2 * pad) * C;
   p.h = mem.f(n); p.l = mem.f(n);
-  wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, p.h, p.l, B, H, W, C, pad, pad, pad);
+  if (pm_pair_enabled() && C % 8 == 0) p.p = mem.f(n);
+  wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, p.h, p.l, B, H, W, C, pad, pad, pad, p.p, 0);
   CK(cudaGetLastError());
   h->launches++;
   return p;
@@ -1130,24 +1152,24 @@ Planes pm_split(avc_pm_handle* h, Arena& mem, const float* src, int B, int H, in
 // the weight images change with every optimiser step: their planes follow lazily, once per forward pass
 void pm_refresh_weight_planes(avc_pm_handle* h, cudaStream_t st) {
   if (!h->planes_stale || !pm_tc_enabled()) return;
-  auto one = [&](const float* src, float*& hi, float*& lo, size_t n) {
+  auto one = [&](const float* src, float*& hi, float*& lo, float*& pr, size_t n) {
     if (!hi) {
-      hi = h->wmem.f(n); lo = h->wmem.f(n);
+      hi = h->wmem.f(n); lo = h->wmem.f(n); pr = h->wmem.f(n);
       CK(cudaDeviceSynchronize());     // the weight arena zero-fills on the legacy stream: it must not overtake kernels of a non-blocking stream
     }
-    wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, hi, lo, 1, 1, (int)(n / 4), 4, 0, 0, 0);
+    wt_split_pad_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(src, hi, lo, 1, 1, (int)(n / 4), 4, 0, 0, 0, pr, 1);
     CK(cudaGetLastError());
     h->launches++;
   };
   for (int l = 1; l < 7; ++l) {
     DownW& d = h->down[l];
     const size_t n = (size_t)9 * kDown[l].ci * kDown[l].co;
-    one(d.w, d.w_h, d.w_l, n); one(d.wt, d.wt_h, d.wt_l, n);
+    one(d.w, d.w_h, d.w_l, d.w_p, n); one(d.wt, d.wt_h, d.wt_l, d.wt_p, n);
   }
   for (int i = 0; i < 4; ++i) {
     UpW& u = h->up[i];
     const size_t n = (size_t)9 * kUp[i].ci * kUp[i].co;
-    one(u.w, u.w_h, u.w_l, n); one(u.wt, u.wt_h, u.wt_l, n);
+    one(u.w, u.w_h, u.w_l, u.w_p, n); one(u.wt, u.wt_h, u.wt_l, u.wt_p, n);
   }
   h->planes_stale = false;
 }
@@ -1195,7 +1217,7 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.B = A.B; c.mode = PM_REFLECT; c.sh = s.sh; c.sw = s.sw;
     if (pm_tc_layer(s.ci, s.co) && pm_tc_site(1)) {
       A.zin[l] = ready.h ? ready : pm_split(h, mem, in, A.B, A.H[l], A.W[l], s.ci, 1, st);
-      c.xh = A.zin[l].h; c.xl = A.zin[l].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
+      c.xh = A.zin[l].h; c.xl = A.zin[l].l; c.xp = A.zin[l].p; c.wkh = w.wt_h; c.wkl = w.wt_l; c.wkp = w.wt_p;
     }
     if (!training) {
       c.scale = w.escale; c.shift = w.eshift; c.slope = w.a; c.act = 1; c.y = A.z[l];
@@ -1231,7 +1253,8 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
         const int pad = l < 6 ? 1 : 0;
         const size_t n = (size_t)A.B * (A.H[l + 1] + 2 * pad) * (A.W[l + 1] + 2 * pad) * s.co;
         ready.h = mem.f(n); ready.l = mem.f(n);
-        pm_affine_prelu_split_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, ready.h, ready.l,
+        if (pm_pair_enabled()) ready.p = mem.f(n);
+        pm_affine_prelu_split_kernel<<<ew_grid((long long)n / 4, h->sm_count), 256, 0, st>>>(A.y[l], A.scale[l], A.shift[l], w.a_dev, ready.h, ready.l, ready.p,
                                                                                               A.B, A.H[l + 1], A.W[l + 1], s.co, pad);
       } else {
         const long long n4 = npix * s.co / 4;
@@ -1253,7 +1276,7 @@ void pm_forward(avc_pm_handle* h, Arena& mem, PmActs& A, const float* x, float* 
     c.B = A.B; c.mode = PM_TRANSPOSED; c.sh = 2; c.sw = 2; c.slope = 0.2f; c.act = i == 4 ? 2 : 1;
     if (pm_tc_layer(s.ci, s.co) && pm_tc_site(2)) {
       A.uin[i] = (i == 0 && ready.h) ? ready : pm_split(h, mem, in, A.B, A.Hu[i], A.Wu[i], s.ci, 0, st);
-      c.xh = A.uin[i].h; c.xl = A.uin[i].l; c.wkh = w.wt_h; c.wkl = w.wt_l;
+      c.xh = A.uin[i].h; c.xl = A.uin[i].l; c.xp = A.uin[i].p; c.wkh = w.wt_h; c.wkl = w.wt_l; c.wkp = w.wt_p;
     }
     launch_pm_conv(h, c, st);
     in = A.u[i];
@@ -1359,7 +1382,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     c.x = g; c.Hi = A.Hu[i + 1]; c.Wi = A.Wu[i + 1]; c.Ci = s.co;
     c.w = h->up[i].wt; c.y = gx; c.Ho = A.Hu[i]; c.Wo = A.Wu[i]; c.Co = s.ci; c.Cop = pad4(s.ci);
     c.B = B; c.mode = PM_PLAIN; c.sh = 2; c.sw = 2;
-    if (gp.h && pm_tc_site(4)) { c.xh = gp.h; c.xl = gp.l; c.wkh = h->up[i].w_h; c.wkl = h->up[i].w_l; }
+    if (gp.h && pm_tc_site(4)) { c.xh = gp.h; c.xl = gp.l; c.xp = gp.p; c.wkh = h->up[i].w_h; c.wkl = h->up[i].w_l; c.wkp = h->up[i].w_p; }
     if (i > 0) { c.dmask = A.u[i - 1]; c.mslope = 0.2f; }
     launch_pm_conv(h, c, st);
     g = gx;
@@ -1403,11 +1426,11 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
       // CUDA-core consumer remains: the single-channel first block, A/B switches), the bias gradient as per-CTA partial sums
       const bool need_gy = !tc || !pm_tc_site(16) || !pm_tc_site(8);
       if (need_gy) gy = mem.f((size_t)npix * s.co);
-      if (tc) { gp.h = mem.f((size_t)npix * s.co); gp.l = mem.f((size_t)npix * s.co); }
+      if (tc) { gp.h = mem.f((size_t)npix * s.co); gp.l = mem.f((size_t)npix * s.co); if (pm_pair_enabled()) gp.p = mem.f((size_t)npix * s.co); }
       PmReduce f{};
       f.y = A.y[l]; f.g = g; f.N = npix; f.C = s.co; f.kind = 3;
       f.scale = A.scale[l]; f.shift = A.shift[l]; f.mean = A.mean[l]; f.rstd = A.rstd[l]; f.a = w.a_dev;
-      f.sums = gsums; f.invN = 1.f / (float)n_stat; f.gy = gy; f.hi = gp.h; f.lo = gp.l;
+      f.sums = gsums; f.invN = 1.f / (float)n_stat; f.gy = gy; f.hi = gp.h; f.lo = gp.l; f.pair = gp.p;
       f.partial = mem.f((size_t)reduce_slices(npix, s.co) * 3 * s.co);
       const int Gf = launch_pm_reduce(h, f, st);
       if (float* d = want(p + "1.bias")) {
@@ -1439,7 +1462,7 @@ void pm_backward(avc_pm_handle* h, Arena& mem, PmActs& A, float* g, Want&& want,
     c.x = gy; c.Hi = A.H[l + 1]; c.Wi = A.W[l + 1]; c.Ci = s.co;
     c.w = w.wt; c.y = gxp; c.Ho = Hp; c.Wo = Wp; c.Co = s.ci; c.Cop = cip;
     c.B = B; c.mode = PM_TRANSPOSED; c.sh = s.sh; c.sw = s.sw;
-    if (gp.h && pm_tc_site(8)) { c.xh = gp.h; c.xl = gp.l; c.wkh = w.w_h; c.wkl = w.w_l; }
+    if (gp.h && pm_tc_site(8)) { c.xh = gp.h; c.xl = gp.l; c.xp = gp.p; c.wkh = w.w_h; c.wkl = w.w_l; c.wkp = w.w_p; }
     launch_pm_conv(h, c, st);
     if (l > 0) {
       float* gx = mem.f((size_t)B * A.H[l] * A.W[l] * s.ci);

@@ -213,9 +213,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 }
 
 // ---- operand preparation: hi / lo planes, optionally reflect-padded -------------------------------------------------------
-// dst_hi/dst_lo [B][H+2ph][W+pl+pr][C] from src [B][H][W][C]; reflect padding (edge not repeated), C % 4 == 0
+// The bf16 PAIR plane (conv2d_tc.cuh, C2Args.pair): the two cross terms of the split product, a_lo*b_hi + a_hi*b_lo, as ONE
+// kind::f16 MMA with K = 16 per 8 channels.  Per group of 8 channels the plane holds 16 bf16 in the 32 bytes the 8 floats of
+// an fp32 plane occupy: an ACTIVATION stores [lo(c0..c7) | hi(c0..c7)], a WEIGHT [hi(c0..c7) | lo(c0..c7)], so that the
+// K = 16 dot product pairs lo with hi and hi with lo.  Same tensor shape, same TMA boxes, same swizzle as the fp32 planes.
+// A thread owns 4 channels (float index e of the plane, e % 4 == 0, C % 8 == 0): two 8-byte stores.
+__device__ __forceinline__ void st_pair4(float* pair, long long e, float4 hi, float4 lo, bool weight_order) {
+  const long long u = (e >> 2) & 1;                  // first or second half of the 8-channel group
+  float* first = pair + e - 2 * u;                   // group base + 2u floats (8 bytes per 4 bf16)
+  float* second = pair + e + 4 - 2 * u;
+  st_bf16x4(first, weight_order ? hi : lo);
+  st_bf16x4(second, weight_order ? lo : hi);
+}
+// dst_hi/dst_lo [B][H+2ph][W+pl+pr][C] from src [B][H][W][C]; reflect padding (edge not repeated), C % 4 == 0;
+// pair (optional, C % 8 == 0): the bf16 pair plane, in weight order when pair_w
 static __global__ void __launch_bounds__(256) wt_split_pad_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
-                                                           int B, int H, int W, int C, int ph, int pl, int pr) {
+                                                           int B, int H, int W, int C, int ph, int pl, int pr,
+                                                           float* __restrict__ pair = nullptr, int pair_w = 0) {
   const int C4 = C >> 2, Wp = W + pl + pr, Hp = H + 2 * ph;
   const long long n4 = (long long)B * Hp * Wp * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -228,8 +242,10 @@ static __global__ void __launch_bounds__(256) wt_split_pad_kernel(const float* _
     h = h < 0 ? -h : h; if (h >= H) h = 2 * (H - 1) - h;
     const float4 v = ld4(src + (((long long)b * H + h) * W + w) * C + c);
     const float4 a = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    const float4 l = f4sub(v, a);
     st4(hi + i * 4, a);
-    st4(lo + i * 4, f4sub(v, a));
+    if (lo) st4(lo + i * 4, l);
+    if (pair) st_pair4(pair, i * 4, a, l, pair_w != 0);
   }
 }
 
@@ -307,8 +323,18 @@ inline void wt_pick_boxes(WtArgs& p, int Wb, int Hb, int Bn) {
   p.n_stages = std::max(2, std::min(kWtMaxStages, kWtRingBytes / (per_row * p.KP)));
 }
 
-inline void wt_init_attributes() {
+// The kernels of this header are `static __global__`: every translation unit that includes it owns a copy.  The functions
+// that name a kernel are therefore `static` too (an `inline` function is merged across translation units by the linker: the
+// surviving definition would launch ITS unit's copy while another unit's call had raised the shared-memory limit of a
+// different copy -- "invalid argument" at launch, depending on which definitions the linker kept), and the launch functions
+// raise the limit themselves, once per device and translation unit.
+static void wt_init_attributes() {
+  static bool done[64] = {};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return;
   CK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wt_smem_bytes()));
+  if (dev >= 0 && dev < 64) done[dev] = true;
 }
 
 // partial must hold wt_splits(...) * n_taps * Ci * Cop floats; returns the number of splits used
@@ -322,7 +348,8 @@ inline int wt_splits(const WtArgs& p, int sm_count) {
   return (n_boxes + per - 1) / per;
 }
 
-inline void launch_wgrad_tc(const WtOperand& A, const WtOperand& G, const WtArgs& p, int S, cudaStream_t st) {
+static void launch_wgrad_tc(const WtOperand& A, const WtOperand& G, const WtArgs& p, int S, cudaStream_t st) {
+  wt_init_attributes();
   const CUtensorMap tAh = wt_tensor_map(A.hi, A, p.bw, p.bh, p.bb), tAl = wt_tensor_map(A.lo, A, p.bw, p.bh, p.bb);
   const CUtensorMap tGh = wt_tensor_map(G.hi, G, p.bw, p.bh, p.bb), tGl = wt_tensor_map(G.lo, G, p.bw, p.bh, p.bb);
   dim3 grid((unsigned)S, (unsigned)(((p.Ci + 127) / 128) * ((p.Co + 127) / 128)), (unsigned)((p.n_taps + p.tg - 1) / p.tg));
