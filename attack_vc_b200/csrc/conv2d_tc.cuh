@@ -167,17 +167,32 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
           const uint32_t base = smem_u32(smem) + (uint32_t)s * kC2StageBytes;
           const int kleft = p.Ci - (it % nkb) * 32;                 // channels of this K block that exist (the rest is zero-filled)
           const int ksteps = min(4, (kleft + 7) >> 3);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t o = (uint32_t)ks * 32;                   // 8 tf32 = 32 B along the swizzled 128-byte row
-            const uint64_t dXh = c2_desc(base + o), dXl = c2_desc(base + kC2Plane + o);
-            const uint64_t dWh = c2_desc(base + 2 * kC2Plane + o), dWl = c2_desc(base + 3 * kC2Plane + o);
-            tc_mma_tf32(d_tmem, dXh, dWh, idesc, acc);
-            acc = 1;
-            if (p.pair) {
-              tc_mma_bf16(d_tmem, dXl, dWl, idesc16);               // x_lo w_hi + x_hi w_lo
+          // separate loops: a branch on p.pair inside the k-step loop cost the three-MMA path 9 % (2016 -> 2194 us per
+          // PredictiveModel step) -- the single issuing thread is the kernel's clock
+          // descriptors of the stage's four planes once; a k-step is +2 in the start-address field (32 B >> 4; shared memory
+          // addresses stay below 2^18, so the 14-bit field cannot carry)
+          const uint64_t dXh = c2_desc(base), dXl = c2_desc(base + kC2Plane), dWh = c2_desc(base + 2 * kC2Plane), dWl = c2_desc(base + 3 * kC2Plane);
+          if (!p.pair) {
+            if (ksteps == 4) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                tc_mma_tf32(d_tmem, dXh + 2 * ks, dWh + 2 * ks, idesc, ks ? 1u : 0u);
+                tc_mma_tf32(d_tmem, dXl + 2 * ks, dWh + 2 * ks, idesc, 1);
+                tc_mma_tf32(d_tmem, dXh + 2 * ks, dWl + 2 * ks, idesc, 1);
+              }
             } else {
-              tc_mma_tf32(d_tmem, dXl, dWh, idesc, 1);
-              tc_mma_tf32(d_tmem, dXh, dWl, idesc, 1);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                tc_mma_tf32(d_tmem, dXh + 2 * ks, dWh + 2 * ks, idesc, acc);
+                acc = 1;
+                tc_mma_tf32(d_tmem, dXl + 2 * ks, dWh + 2 * ks, idesc, 1);
+                tc_mma_tf32(d_tmem, dXh + 2 * ks, dWl + 2 * ks, idesc, 1);
+              }
+            }
+          } else {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              tc_mma_tf32(d_tmem, dXh + 2 * ks, dWh + 2 * ks, idesc, acc);
+              acc = 1;
+              tc_mma_bf16(d_tmem, dXl + 2 * ks, dWl + 2 * ks, idesc16);   // x_lo w_hi + x_hi w_lo
             }
           }
           tc_commit(empty(s));

@@ -161,13 +161,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         for (int c = 0; c < ntap; ++c) {
           const uint32_t ab = base + (p.a_same ? 0u : (uint32_t)c * a_copy), gb = base + offG + (p.g_same ? 0u : (uint32_t)c * g_copy);
           const uint32_t d_tmem = tmem_base + (uint32_t)(c * 128);
+          // the four descriptors once per tap; a k-step (8 pixel rows = 1024 B) is +64 in the start-address field (shared-memory
+          // addresses stay below 2^18: no carry out of the 14 bits) -- the issuing thread is the kernel's clock (conv2d_tc.cuh)
+          const uint64_t dAh = wt_desc(ab, blk), dAl = wt_desc(ab + offAl, blk), dGh = wt_desc(gb, blk), dGl = wt_desc(gb + offGl, blk);
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t o = (uint32_t)ks * 1024;
-            const uint64_t dAh = wt_desc(ab + o, blk), dAl = wt_desc(ab + offAl + o, blk);
-            const uint64_t dGh = wt_desc(gb + o, blk), dGl = wt_desc(gb + offGl + o, blk);
-            tc_mma_tf32(d_tmem, dAh, dGh, idesc, (acc || ks) ? 1u : 0u);
-            tc_mma_tf32(d_tmem, dAl, dGh, idesc, 1);
-            tc_mma_tf32(d_tmem, dAh, dGl, idesc, 1);
+            const uint64_t k = (uint64_t)ks * 64;
+            tc_mma_tf32(d_tmem, dAh + k, dGh + k, idesc, (acc || ks) ? 1u : 0u);
+            tc_mma_tf32(d_tmem, dAl + k, dGh + k, idesc, 1);
+            tc_mma_tf32(d_tmem, dAh + k, dGl + k, idesc, 1);
           }
         }
         acc = 1;
