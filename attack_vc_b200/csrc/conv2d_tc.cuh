@@ -189,11 +189,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant
               }
             }
           } else {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              tc_mma_tf32(d_tmem, dXh + 2 * ks, dWh + 2 * ks, idesc, acc);
-              acc = 1;
-              tc_mma_bf16(d_tmem, dXl + 2 * ks, dWl + 2 * ks, idesc16);   // x_lo w_hi + x_hi w_lo
-            }
+            // all TF32 MMAs of the stage, then all BF16 ones (same accumulator, the order is free): a change of MMA kind costs
+            // ~64 clk at N = 128 (scripts/ubench/mma_shapes.cu), alternating per k-step ate the whole gain of the shorter stage
+            for (int ks = 0; ks < ksteps; ++ks) tc_mma_tf32(d_tmem, dXh + 2 * ks, dWh + 2 * ks, idesc, ks ? 1u : 0u);
+            for (int ks = 0; ks < ksteps; ++ks) tc_mma_bf16(d_tmem, dXl + 2 * ks, dWl + 2 * ks, idesc16);   // x_lo w_hi + x_hi w_lo
           }
           tc_commit(empty(s));
           tc_commit(acc_full0 + 8 * buf);

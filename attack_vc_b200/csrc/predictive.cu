@@ -966,9 +966,11 @@ bool pm_tc_enabled() {
   return !off;
 }
 bool pm_pair_enabled() {
-  // Opt-in (AVC_PM_PAIR=1).  Measured on B200, 256 windows: conv2d_tc 2016 -> 1928 us per step, the third operand plane costs
-  // 57 us in the producers, step 4.67 -> 4.54 ms (3 %) -- the convs are bound by operand delivery (64 KB per 12-MMA stage
-  // through L2), not by the MMA count -- and one gradient case (3 x 64 x 77) leaves the 1e-3 tolerance.  Default: 3xTF32.
+  // Opt-in (AVC_PM_PAIR=1).  Measured on B200, 256 windows: step 4.53 -> 4.36 ms (58.8 k windows/s) with the MMAs of a stage
+  // grouped by kind (alternating kinds per k-step: 4.51 -- a change of kind costs ~64 clk); the third operand plane costs 57 us
+  // in the producers.  Not the default: tests/test_predictive_gpu.py::test_train_step_gradients[3-64-77] then misses 1e-3
+  // (d loss / d x off by 2e-2: the last down block normalises over 3 values per channel there, which amplifies the ~1e-6
+  // forward error of the bf16 cross terms; with 3xTF32 the same case is at 2e-5).
   static const bool on = getenv("AVC_PM_PAIR") != nullptr;
   return on;
 }
