@@ -5,13 +5,23 @@ GPU.  PyTorch supplies device memory and the stream only; there is no CPU fallba
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib
 from .engine import AvcError
+
+
+def group_by_length(lengths: Sequence[int]) -> List[Tuple[int, List[int]]]:
+    """Indices of equal-length items, in order of first appearance: [(length, [i, j, ...]), ...].  Utterances of one length
+    form ONE batched call (the frames of the whole group are the rows of one GEMM per transform); ragged inputs therefore cost
+    one call per distinct length, not one per utterance."""
+    groups: Dict[int, List[int]] = {}
+    for i, n in enumerate(lengths):
+        groups.setdefault(int(n), []).append(i)
+    return list(groups.items())
 
 
 class AudioEngine:
@@ -91,3 +101,22 @@ class AudioEngine:
             st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             self._check(self._lib.avc_audio_mel2wav_batch(self._h, mel.data_ptr(), B, F, int(n_iter), wav.data_ptr(), st))
         return wav if batched else wav[0]
+
+    def wav2mel_list(self, wavs: Sequence[Tensor]) -> List[Tensor]:
+        """file2mel over utterances of ANY lengths (the reference loops over files, data_utils.py:65-117): equal-length
+        waveforms are batched into one call each, results come back in input order."""
+        out: List[Optional[Tensor]] = [None] * len(wavs)
+        for _, idx in group_by_length([int(w.numel()) for w in wavs]):
+            mel = self.wav2mel(torch.stack([self._vec(wavs[i], "wav", 1) for i in idx]))
+            for k, i in enumerate(idx):
+                out[i] = mel[k]
+        return out  # type: ignore[return-value]
+
+    def mel2wav_list(self, mels: Sequence[Tensor], n_iter: int = 100) -> List[Tensor]:
+        """mel2wav over mels of ANY frame counts: one batched Griffin-Lim per distinct length, input order kept."""
+        out: List[Optional[Tensor]] = [None] * len(mels)
+        for _, idx in group_by_length([int(m.shape[0]) for m in mels]):
+            wav = self.mel2wav(torch.stack([self._vec(mels[i], "mel", 2) for i in idx]), n_iter=n_iter)
+            for k, i in enumerate(idx):
+                out[i] = wav[k]
+        return out  # type: ignore[return-value]

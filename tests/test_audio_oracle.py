@@ -69,3 +69,34 @@ def test_wav2mel_shape_range_and_griffin_lim_consistency(A):
     e0, e5 = err(0), err(5)
     assert e5 < 0.6 * e0
     assert A.inv_mel_matrix(24000, 2048, 80).shape == (1025, 80)
+
+
+def test_ragged_list_helpers_group_equal_lengths_and_keep_order():
+    """AudioEngine.wav2mel_list / mel2wav_list (host logic only, no GPU): utterances of one length go into ONE batched call,
+    results come back in input order.  The engine is a stub whose batched transforms are recognisable functions of the input."""
+    import torch
+    from attack_vc_b200.audio import AudioEngine, group_by_length
+    assert group_by_length([5, 3, 5, 7, 3, 5]) == [(5, [0, 2, 5]), (3, [1, 4]), (7, [3])]
+    assert group_by_length([]) == []
+    eng = AudioEngine.__new__(AudioEngine)
+    eng.device = torch.device("cpu")
+    eng.n_mels = 4
+    eng._h = None
+    calls = []
+
+    def fake_wav2mel(wav):
+        calls.append(("w", tuple(wav.shape)))
+        return wav.sum(dim=1)[:, None, None].expand(-1, 2, 4).clone()
+
+    def fake_mel2wav(mel, n_iter=100):
+        calls.append(("m", tuple(mel.shape), n_iter))
+        return mel.sum(dim=(1, 2))[:, None].expand(-1, 3).clone()
+    eng.wav2mel, eng.mel2wav = fake_wav2mel, fake_mel2wav
+    wavs = [torch.full((n,), float(i + 1)) for i, n in enumerate([5, 3, 5, 7, 3])]
+    mels = eng.wav2mel_list(wavs)
+    assert [c for c in calls if c[0] == "w"] == [("w", (2, 5)), ("w", (2, 3)), ("w", (1, 7))]
+    for i, w in enumerate(wavs):
+        assert mels[i].shape == (2, 4) and float(mels[i][0, 0]) == float(w.sum())
+    back = eng.mel2wav_list([torch.full((f, 4), float(i + 1)) for i, f in enumerate([6, 2, 6])], n_iter=7)
+    assert [c for c in calls if c[0] == "m"] == [("m", (2, 6, 4), 7), ("m", (1, 2, 4), 7)]
+    assert [float(b[0]) for b in back] == [24.0, 16.0, 72.0]
