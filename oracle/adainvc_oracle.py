@@ -10,7 +10,7 @@ Parity pinning: the reference ships no tests, golden vectors or checkpoints (SUR
 reference; torch 2.11.0 here).  The oracle is therefore pinned by EXECUTING the unmodified
 reference in the build container: ``tests/test_oracle_vs_reference.py`` imports
 ``/root/reference/models.py`` + ``attack_utils.py`` and asserts equality, and
-``scripts/make_golden.py`` stores reference outputs under ``tests/golden/`` so the same
+``tests/tools/make_golden.py`` stores reference outputs under ``tests/golden/`` so the same
 check travels to the GPU box where ``/root/reference`` does not exist.
 
 Reference lines followed (``/root/reference``):

@@ -11,7 +11,7 @@ RTOL = 1e-3            # north_star tolerance (loss and gradient, relative)
 GOLDEN_CASES = ["emb_T128_it100", "e2e_T64_it20", "fb_T64_it20", "emb_B2_ragged_cli", "e2e_B2_ragged", "fb_B2_ragged",
                 "e2e_T256_it1500"]          # the last one is BASELINE configs[1] at its own size and length
 # max |adv - reference adv| allowed.  Short runs: fp32 noise.  1500 iterations: the reference's own 8-thread vs
-# 1-thread runs end 9.3e-5 apart (scripts/make_golden.py), so 5e-4 (0.5 % of eps) is ~5x its noise floor.
+# 1-thread runs end 9.3e-5 apart (tests/tools/make_golden.py), so 5e-4 (0.5 % of eps) is ~5x its noise floor.
 ADV_ATOL = {"e2e_T256_it1500": 5e-4}
 
 
@@ -46,7 +46,7 @@ def assert_grads_per_utterance(oracle, kind, inp, wi, g_gpu, g_ref32, inv_norm, 
          the kernel's gradient (least squares, rounded to flip / no flip) and RE-EVALUATES the fp64 gradient with exactly
          those units on their other branch: the kernel must match that exact gradient to 1e-3.
     One flipped unit of a layer with N units moves the gradient by ~1/sqrt(N) (1e-3..2e-2 here), which is why ANY two
-    fp32 implementations -- the reference at 1 vs 8 threads included, scripts/make_golden.py -- disagree in such states.
+    fp32 implementations -- the reference at 1 vs 8 threads included, tests/tools/make_golden.py -- disagree in such states.
     Returns how many utterances needed the arbiter."""
     g, r = g_gpu.cpu().double(), g_ref32.double()
     per = ((g - r).flatten(1).norm(dim=1) / r.flatten(1).norm(dim=1))
@@ -107,7 +107,7 @@ def test_attack_vs_golden(engine, golden, oracle, name):
     # Gradient parity is teacher-forced: golden holds (w_i, grad_i) pairs of the reference; one
     # iteration from w_i must reproduce grad_i.  (Comparing free-running trajectories is not a test
     # of the kernels: the reference itself, 8 threads vs 1 thread, differs by 6.8e-3 at iteration 30
-    # of this very case, whenever a ReLU unit of the dense tail crosses zero -- scripts/make_golden.py.)
+    # of this very case, whenever a ReLU unit of the dense tail crosses zero -- tests/tools/make_golden.py.)
     for key in [k for k in g if k.startswith("grad_")]:
         i = int(key.split("_")[1])
         wi = cuda(g, f"w_{i}", cli)
@@ -302,7 +302,7 @@ def test_tensor_core_plans_vs_host_oracle(engine, oracle, cpu_model, kind, B, T,
     ~1e-5), EVERY utterance's teacher-forced gradient within 1e-3 of the fp32 oracle or, failing that, of an fp64
     evaluation at the same w (assert_grads_per_utterance: a piecewise-linear network has states where one ReLU unit of
     the 128-wide dense tail sits within rounding distance of zero, and there the fp32 ORACLE is as likely the side that
-    flipped as the kernel -- the reference itself differs by 6.8e-3 between 1 and 8 threads, scripts/make_golden.py)."""
+    flipped as the kernel -- the reference itself differs by 6.8e-3 between 1 and 8 threads, tests/tools/make_golden.py)."""
     inp = oracle.make_inputs(kind, B, T, seed=77)
     src = inp.get("vc_src")
     o = oracle.run_attack(kind, cpu_model, inp["vc_tgt"], inp["adv_tgt"], 0.1, n, inp["w0"], vc_src=src,

@@ -1,4 +1,4 @@
-"""Oracle vs the committed golden vectors (generated from the reference by scripts/make_golden.py).
+"""Oracle vs the committed golden vectors (generated from the reference by tests/tools/make_golden.py).
 Runs everywhere (CPU), so the pin travels to the GPU box."""
 import numpy as np
 import pytest

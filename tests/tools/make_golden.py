@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
 
 Run in the build container only (the GPU box has no /root/reference):
-    python scripts/make_golden.py
+    python tests/tools/make_golden.py
 Weights: oracle.make_state_dict(seed=0) loaded into the reference's AdaInVC with strict=True.
 Inputs:  oracle.make_inputs(...).  The reference's own attack functions draw w0 from the global
 RNG (attack_utils.py:30,68,112); we seed it, draw the same tensor first, and store it.
@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
